@@ -1,0 +1,251 @@
+/*
+ * volta_b200 C ABI - the drop-in boundary of the B200-native VOLTA encoder path.
+ *
+ * The reference (IntuitionMachines/volta) has exactly one native boundary on
+ * this path: the pybind module `fused_layer_norm_cuda` with
+ *   forward_affine(input, normalized_shape, gamma, beta, eps) -> (out, mean, invvar)
+ *   backward_affine(dout, mean, invvar, input, shape, gamma, beta, eps) -> (dx, dgamma, dbeta)
+ * (apex/csrc/layer_norm_cuda.cpp:139-160, 205-240).  Everything else on the
+ * path is ATen calls issued from volta/encoders.py / volta/embeddings.py.
+ * This header replaces both: `vb_layernorm_*` is the LN boundary, the other
+ * entry points are the fused ops that stand in for the ATen call sites cited
+ * on each declaration.  INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *  - plain C: raw device pointers, int32/int64 extents, no torch types.
+ *  - the caller owns every buffer; nothing is allocated or retained here
+ *    (the only process state is a driver entry point looked up once).
+ *  - every call launches on the `stream` argument only (a cudaStream_t passed
+ *    as void*), never synchronises the device, and is re-entrant (PyTorch's
+ *    autograd thread calls the backward entry points).
+ *  - return value: 0 ok; negative = argument error (VB_ERR_*); positive =
+ *    cudaError_t.  `vb_last_error()` returns a thread-local message.
+ *  - dtype codes: VB_F32 = 0, VB_BF16 = 1.  Matrices are row-major with an
+ *    explicit leading dimension in elements.
+ */
+#ifndef VOLTA_B200_H_
+#define VOLTA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VB_F32 0
+#define VB_BF16 1
+
+#define VB_ERR_ARG (-1)
+#define VB_ERR_UNSUPPORTED (-2)
+#define VB_ERR_DEVICE (-3)
+#define VB_ERR_WORKSPACE (-4)
+
+/* ---- library ---------------------------------------------------------- */
+int vb_version(void);                 /* ABI version (major*1000+minor) */
+const char* vb_last_error(void);      /* thread-local, never NULL */
+/* 0 if the current device is sm_100 (B200); VB_ERR_DEVICE otherwise. */
+int vb_device_check(void);
+int vb_sm_count(void);
+
+/* ---- GEMM -------------------------------------------------------------
+ * D[M,N] = epilogue( sum_k opA[m,k] * opB[n,k] )
+ *
+ * Replaces nn.Linear forward (volta/encoders.py:204-206,215-217,376,390,463,
+ * 477,518,533; volta/embeddings.py:134,323,419; heads :646,663,686-696,727,
+ * 747) and its autograd (dgrad / wgrad).
+ *
+ * a_kmajor = 1: A is [M,K] row-major (lda >= K).  a_kmajor = 0: A is stored
+ *   [K,M] row-major (lda >= M), i.e. the reduction index is the slow one
+ *   (wgrad: A = dY[rows, N] read as dY^T).
+ * b_kmajor = 1: B is [N,K] row-major (nn.Linear weight layout).
+ * b_kmajor = 0: B is [K,N] row-major (dgrad: B = W[out,in]; wgrad: B = X).
+ *
+ * backend: VB_GEMM_AUTO picks the tcgen05/TMEM/TMA kernel for bf16 operands
+ *   whose layout TMA accepts (16-byte aligned bases and row pitches) and the
+ *   SIMT kernel otherwise (fp32 validation mode, K=5 box projection, ...).
+ *   VB_GEMM_TC / VB_GEMM_SIMT force one and fail if it cannot run.
+ */
+#define VB_GEMM_AUTO 0
+#define VB_GEMM_TC 1
+#define VB_GEMM_SIMT 2
+
+#define VB_EPI_NONE 0          /* D = acc                                    */
+#define VB_EPI_BIAS 1          /* D = acc + bias[n]                          */
+#define VB_EPI_BIAS_GELU 2     /* aux_out = acc + bias; D = gelu_erf(aux_out)  (encoders.py:136) */
+#define VB_EPI_BIAS_RELU 3     /* D = relu(acc + bias)          (poolers, encoders.py:596-637)   */
+#define VB_EPI_BIAS_DROP_RES 4 /* D = dropout(acc + bias) + aux_in   (encoders.py:410-423, 552-565) */
+#define VB_EPI_DGELU 5         /* D = acc * gelu'(aux_in)                    */
+#define VB_EPI_ADD 6           /* D = acc + aux_in                           */
+#define VB_EPI_DRELU 7         /* D = acc * (aux_in > 0)                     */
+#define VB_EPI_ACCUM 8         /* D += acc  (fp32 D, atomic; split-K allowed) */
+#define VB_EPI_BIAS_ADD 9      /* D = acc + bias[n] + aux_in                 */
+
+typedef struct vb_gemm_args {
+  const void* A; const void* B; void* D;
+  int64_t M, N, K;
+  int64_t lda, ldb, ldd;
+  int32_t ab_dtype;      /* VB_F32 | VB_BF16 (A and B) */
+  int32_t d_dtype;       /* VB_F32 | VB_BF16 */
+  int32_t a_kmajor, b_kmajor;
+  int32_t epilogue;      /* VB_EPI_* */
+  int32_t backend;       /* VB_GEMM_* */
+  const float* bias;     /* [N] fp32 or NULL */
+  const void* aux_in;    /* [M, ld_aux] in d_dtype (residual / pre-activation) */
+  void* aux_out;         /* [M, ld_aux] in d_dtype (pre-activation for BIAS_GELU) */
+  int64_t ld_aux;
+  float alpha;           /* scales acc before the epilogue (1.0 normally) */
+  float dropout_p;       /* BIAS_DROP_RES only; 0 disables */
+  uint64_t seed, offset; /* Philox stream for the dropout mask: element index = m*N+n */
+  int32_t split_k;       /* ACCUM only: 0 = auto */
+  int32_t reserved;
+} vb_gemm_args;
+
+int vb_gemm(const vb_gemm_args* args, void* stream);
+/* Which backend vb_gemm would use for these arguments (VB_GEMM_TC / VB_GEMM_SIMT). */
+int vb_gemm_backend(const vb_gemm_args* args);
+
+/* ---- LayerNorm --------------------------------------------------------
+ * Replaces apex fused_layer_norm_cuda.forward_affine / backward_affine
+ * (apex/csrc/layer_norm_cuda.cpp:139-160, 205-240; kernels
+ * layer_norm_cuda_kernel.cu:279-322, 403-637) and the Python BertLayerNorm
+ * (volta/encoders.py:48-61): biased variance, eps inside the sqrt.
+ *
+ * forward : y = gamma * (x - mean) * rstd + beta ; mean/rstd saved in fp32.
+ *   out_scale multiplies y (LXMERT averages two LNs, embeddings.py:169);
+ *   if `accum` != 0, y += ... instead of y = ....
+ * backward: dx = rstd * (g - mean_H(g) - xhat * mean_H(g * xhat)),  g = dy*gamma*out_scale
+ *   dgamma/dbeta are ACCUMULATED (fp32 atomics) - the caller zeroes them.
+ *   Optional fused extras for the residual blocks:
+ *     dx_drop  = dx * dropmask / (1-p)  (mask regenerated from seed/offset, index = row*H+col)
+ *     dbias   += column sums of (dx_drop if given else dx)
+ */
+int vb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int64_t rows, int32_t H, float eps, float out_scale, int32_t accum, int32_t dtype,
+                     void* stream);
+int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                     void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t H, float out_scale,
+                     void* dx_drop, float dropout_p, uint64_t seed, uint64_t offset, float* dbias,
+                     int32_t dtype, void* stream);
+
+/* ---- gated attention --------------------------------------------------
+ * Replaces BertGatedSelfAttention.forward after the Q/K/V projections
+ * (volta/encoders.py:258-340): scores = QK^T/sqrt(d) + (1-mask)*-10000 for
+ * each enabled pair, JOINT softmax over the concatenated key axis (text keys
+ * first, then vision keys), dropout on the probabilities, context = P.V with
+ * heads merged back to [rows, heads*d].
+ *
+ * Q/K/V are read in place from the packed projection outputs:
+ *   qkv_t: [B*Lt, ld_t] with Q at column 0, K at column A, V at column 2A
+ *   (A = heads*d); qkv_v likewise.  pair_mask bit0=tt bit1=tv bit2=vt bit3=vv.
+ * mask_t/mask_v are the 0/1 int32 padding masks [B,Lt] / [B,Lv].
+ * lse_t/lse_v: [B, heads, L] fp32 row log-sum-exp saved for the backward,
+ * which recomputes P from them (no probability tensor is stored).
+ * dropout: Philox mask indexed by ((b*heads+h)*Lq_total + q)*Lk_total + k over the
+ * concatenated sequence [text; vision].
+ */
+#define VB_ATTN_AUTO 0
+#define VB_ATTN_MMA 1
+#define VB_ATTN_SIMT 2
+
+typedef struct vb_attn_args {
+  const void* qkv_t; const void* qkv_v;
+  int64_t ld_t, ld_v;
+  const int32_t* mask_t; const int32_t* mask_v;
+  void* ctx_t; void* ctx_v;           /* [B*L, heads*d], ld = ld_ctx_* */
+  int64_t ld_ctx_t, ld_ctx_v;
+  float* lse_t; float* lse_v;
+  /* backward only */
+  const void* dctx_t; const void* dctx_v;
+  void* dqkv_t; void* dqkv_v;         /* same layout as qkv_* */
+  int32_t B, Lt, Lv, heads, d;
+  int32_t pair_mask;
+  int32_t dtype;
+  float scale;                        /* 1/sqrt(d) */
+  float dropout_p_t, dropout_p_v;     /* text-query rows / vision-query rows */
+  uint64_t seed, offset;
+  int32_t backend;                    /* VB_ATTN_AUTO | VB_ATTN_MMA (bf16 tensor-core path) | VB_ATTN_SIMT */
+  int32_t reserved;
+} vb_attn_args;
+
+int vb_attention_fwd(const vb_attn_args* args, void* stream);
+int vb_attention_bwd(const vb_attn_args* args, void* stream);
+
+/* ---- embeddings -------------------------------------------------------
+ * vb_embed_gather_fwd: out[r,:] = (accum? out[r,:] : 0) + sum_j table_j[idx_j[r], :]  for up to 4
+ *   fp32 tables (word + position + token-type, volta/embeddings.py:55-65).  idx_j == NULL with
+ *   table_j != NULL means a constant row `const_row_j` (VisualBERT's visual position / type rows,
+ *   embeddings.py:352-386).  idx are int64 (loader dtype).  Output in `dtype`, stride ld_out.
+ * vb_embed_gather_bwd: scatter-add of d_out rows into the fp32 table grads (atomic).
+ * vb_box_project: out[r,:] (+)= loc[r,0:nl] . W[:,0:nl]^T + b   - the K = num_locs (4/5)
+ *   Linear of embeddings.py:135,141 done as FMAs; bwd accumulates dW, db.
+ */
+int vb_embed_gather_fwd(const float* const* tables, const int64_t* const* idx, const int64_t* const_rows,
+                        int32_t n_tables, void* out, int64_t ld_out, int64_t rows, int32_t H, int32_t accum,
+                        int32_t dtype, void* stream);
+int vb_embed_gather_bwd(float* const* dtables, const int64_t* const* idx, const int64_t* const_rows,
+                        int32_t n_tables, const void* dout, int64_t ld_dout, int64_t rows, int32_t H,
+                        int32_t dtype, void* stream);
+int vb_box_project_fwd(const float* loc, int32_t nl, const float* W, const float* b, void* out, int64_t ld_out,
+                       int64_t rows, int32_t H, int32_t accum, int32_t dtype, void* stream);
+int vb_box_project_bwd(const float* loc, int32_t nl, const void* dout, int64_t ld_dout, float* dW, float* db,
+                       int64_t rows, int32_t H, int32_t dtype, void* stream);
+
+/* ---- losses -----------------------------------------------------------
+ * vb_xent_fwd: CrossEntropyLoss(ignore_index=-1), mean over non-ignored rows
+ *   (volta/encoders.py:1030, 1095-1109).  logits [rows, ld] in `dtype`, C classes, labels int64.
+ *   Writes per-row lse (fp32), loss_sum and count (fp32 scalars, ACCUMULATED - zero them first).
+ * vb_xent_bwd: dlogits = (softmax - onehot) * (*dloss) / max(count,1) on non-ignored rows, 0 elsewhere.
+ * vb_kl_fwd / vb_kl_bwd: the `kl_1601` criterion (volta/losses.py:16-22):
+ *   sum_{label==1} KL(target || softmax(pred)) / max(#label==1, 1) * weight; target fp32 [rows, C].
+ *   `row_map`: pred row r reads logits row row_map_base(r) = (r / per) * per_ld + r % per + skip, so the
+ *   global-feature row is skipped in place (encoders.py:1085) without a copy.
+ */
+int vb_xent_fwd(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C, float* lse,
+                float* loss_sum, float* count, int32_t dtype, void* stream);
+int vb_xent_bwd(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C, const float* lse,
+                const float* count, const float* dloss, void* dlogits, int32_t dtype, void* stream);
+int vb_kl_fwd(const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32_t skip, const int64_t* label,
+              const float* target, int64_t rows, int32_t C, float weight, float* lse, float* loss_sum,
+              float* count, int32_t dtype, void* stream);
+int vb_kl_bwd(const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32_t skip, const int64_t* label,
+              const float* target, int64_t rows, int32_t C, float weight, const float* lse, const float* count,
+              const float* dloss, void* dlogits, int32_t dtype, void* stream);
+/* loss = loss_sum / max(count, 1) for `n` (sum,count) pairs -> out[n] */
+int vb_loss_finalize(const float* loss_sum, const float* count, float* out, int32_t n, void* stream);
+
+/* ---- element-wise / reductions (glue that the reference issues as ATen ops) */
+#define VB_ELT_COPY 0      /* out = a                     (also dtype conversion)       */
+#define VB_ELT_ADD 1       /* out = a + b                                                */
+#define VB_ELT_MUL 2       /* out = a * b                 (pooled_t * pooled_v, :770)    */
+#define VB_ELT_RELU 3      /* out = relu(a)                                              */
+#define VB_ELT_DRELU 4     /* out = a * (b > 0)                                          */
+#define VB_ELT_GELU 5
+#define VB_ELT_DGELU 6     /* out = a * gelu'(b)                                         */
+#define VB_ELT_SCALE 7     /* out = a * alpha                                            */
+#define VB_ELT_DROPOUT 8   /* out = a * mask / (1-p)      (Philox, index = element)      */
+#define VB_ELT_AXPY 9      /* out = out + alpha * a                                      */
+/* 2-D strided element-wise op over [rows, cols]; a/b/out may have different dtypes. */
+int vb_eltwise(int32_t op, const void* a, int32_t a_dtype, int64_t lda, const void* b, int32_t b_dtype,
+               int64_t ldb, void* out, int32_t out_dtype, int64_t ldo, int64_t rows, int64_t cols,
+               float alpha, float p, uint64_t seed, uint64_t offset, void* stream);
+/* out[c] += sum_r a[r,c]   (fp32 out, atomic accumulate; bias gradients) */
+int vb_colsum(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t cols, float* out, void* stream);
+/* out[r,:] = a[idx[r],:] (gather rows; idx int64) and its scatter-add adjoint */
+int vb_gather_rows(const void* a, int64_t lda, const int64_t* idx, void* out, int64_t ldo, int64_t rows,
+                   int64_t cols, int32_t dtype, void* stream);
+int vb_scatter_rows_add(const void* a, int64_t lda, const int64_t* idx, void* out, int64_t ldo, int64_t rows,
+                        int64_t cols, int32_t dtype, void* stream);
+/* fp32 [rows, cols] -> bf16, n_mats matrices described by a device table; one launch for all weights. */
+typedef struct vb_cast_item { const float* src; void* dst; int64_t n; } vb_cast_item;
+int vb_multi_cast_bf16(const vb_cast_item* items_dev, int32_t n_items, int64_t max_n, void* stream);
+/* VL-BERT sin/cos box embedding (volta/embeddings.py:102-124): boxes fp32 [rows, nl] -> out [rows, 8*dim] */
+int vb_box_sincos(const float* boxes, int32_t nl, int32_t dim, void* out, int64_t ldo, int64_t rows,
+                  int32_t dtype, void* stream);
+/* L2-flush helper for benchmarks: writes `bytes` to buf. */
+int vb_fill(void* buf, int64_t bytes, int32_t value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOLTA_B200_H_ */

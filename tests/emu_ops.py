@@ -1,0 +1,327 @@
+"""CPU emulation of the C ABI (include/volta_b200.h) in plain PyTorch - TEST INFRASTRUCTURE ONLY.
+
+`install()` monkey-patches `volta_b200.ops` so that the engine's host logic (the launch plan, the
+hand-written backward, the flat parameter store) can be exercised on a machine without a GPU and compared
+with the oracle.  Each function restates the documented semantics of one entry point; the GPU tests check
+the real kernels against these same functions.  Nothing in the product imports this file.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from volta_b200 import _lib, engine, ops
+
+
+def _gelu(x):
+    return x * 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+
+
+def _dgelu(x):
+    cdf = 0.5 * (1.0 + torch.erf(x / math.sqrt(2.0)))
+    pdf = torch.exp(-0.5 * x * x) / math.sqrt(2.0 * math.pi)
+    return cdf + x * pdf
+
+
+def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
+         dropout_p=0.0, seed=0, offset=0, backend=0, split_k=0, M=None, N=None, K=None):
+    A = a.float() if a_kmajor else a.float().t()
+    B = b.float() if b_kmajor else b.float().t()
+    M = A.shape[0] if M is None else M
+    N = B.shape[0] if N is None else N
+    K = A.shape[1] if K is None else K
+    acc = A[:M, :K] @ B[:N, :K].t()
+    o = out[:M, :N]
+    ai = aux_in[:M, :N].float() if aux_in is not None else None
+    bb = bias[:N].float() if bias is not None else None
+    E = _lib
+    assert dropout_p == 0.0, "the CPU emulation covers the deterministic (eval / p=0) path"
+    if epilogue == E.EPI_NONE:
+        r = acc
+    elif epilogue == E.EPI_BIAS:
+        r = acc + bb
+    elif epilogue == E.EPI_BIAS_GELU:
+        pre = acc + bb
+        aux_out[:M, :N] = pre.to(aux_out.dtype)
+        r = _gelu(pre)
+    elif epilogue == E.EPI_BIAS_RELU:
+        r = torch.relu(acc + bb)
+    elif epilogue == E.EPI_BIAS_DROP_RES:
+        r = acc + bb + ai
+    elif epilogue == E.EPI_DGELU:
+        r = acc * _dgelu(ai)
+    elif epilogue == E.EPI_ADD:
+        r = acc + ai
+    elif epilogue == E.EPI_DRELU:
+        r = acc * (ai > 0)
+    elif epilogue == E.EPI_BIAS_ADD:
+        r = acc + bb + ai
+    elif epilogue == E.EPI_ACCUM:
+        r = o.float() + acc
+    else:
+        raise ValueError(epilogue)
+    o.copy_(r.to(out.dtype))
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=1.0, accum=False):
+    xf = x.float()
+    mu = xf.mean(-1, keepdim=True)
+    var = (xf - mu).pow(2).mean(-1, keepdim=True)
+    rs = torch.rsqrt(var + eps)
+    r = (gamma * ((xf - mu) * rs) + beta) * out_scale
+    if accum:
+        r = r + y.float()
+    y.copy_(r.to(y.dtype))
+    if mean is not None:
+        mean.copy_(mu.reshape(-1))
+    if rstd is not None:
+        rstd.copy_(rs.reshape(-1))
+    return y
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, out_scale=1.0, dx_drop=None, dropout_p=0.0, seed=0,
+                  offset=0, dbias=None):
+    assert dropout_p == 0.0
+    dyo = dy.float() * out_scale
+    xh = (x.float() - mean[:, None]) * rstd[:, None]
+    g = dyo * gamma
+    c1 = g.mean(-1, keepdim=True)
+    c2 = (g * xh).mean(-1, keepdim=True)
+    r = rstd[:, None] * (g - c1 - xh * c2)
+    dx.copy_(r.to(dx.dtype))
+    if dgamma is not None:
+        dgamma += (dyo * xh).sum(0)
+    if dbeta is not None:
+        dbeta += dyo.sum(0)
+    if dbias is not None:
+        dbias += dx.float().sum(0)
+    return dx
+
+
+def _attn_core(qkv_t, qkv_v, mask_t, mask_v, B, Lt, Lv, heads, d, pair_mask):
+    A = heads * d
+    streams = {}
+    for s, (qkv, L) in enumerate(((qkv_t, Lt), (qkv_v, Lv))):
+        if qkv is None:
+            continue
+        x = qkv.float().view(B, L, -1)
+        q, k, v = (x[..., i * A:(i + 1) * A].reshape(B, L, heads, d).transpose(1, 2) for i in range(3))
+        streams[s] = (q, k, v)
+    madd = {0: None if mask_t is None else (1.0 - mask_t.float()) * -10000.0,
+            1: None if mask_v is None else (1.0 - mask_v.float()) * -10000.0}
+    return A, streams, madd
+
+
+def _attn_forward_math(qkv_t, qkv_v, mask_t, mask_v, B, Lt, Lv, heads, d, pair_mask):
+    A, streams, madd = _attn_core(qkv_t, qkv_v, mask_t, mask_v, B, Lt, Lv, heads, d, pair_mask)
+    out = {}
+    for qs in streams:
+        segs = [ks for ks in streams if (pair_mask >> (qs * 2 + ks)) & 1]
+        if not segs:
+            continue
+        q = streams[qs][0]
+        sc = torch.cat([q @ streams[ks][1].transpose(-1, -2) / math.sqrt(d) + madd[ks][:, None, None, :] for ks in segs], -1)
+        lse = torch.logsumexp(sc, -1)
+        p = torch.exp(sc - lse[..., None])
+        vv = torch.cat([streams[ks][2] for ks in segs], 2)
+        ctx = (p @ vv).transpose(1, 2).reshape(B * q.shape[2], A)
+        out[qs] = (ctx, lse)
+    return out
+
+
+def attention_fwd(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, Lv, heads, d, pair_mask, p_t, p_v,
+                  seed, backend, **kw):
+    assert p_t == 0.0 and p_v == 0.0
+    out = _attn_forward_math(qkv_t, qkv_v, mask_t, mask_v, B, Lt, Lv, heads, d, pair_mask)
+    for qs, (ctx, lse) in out.items():
+        dst, ldst = (ctx_t, lse_t) if qs == 0 else (ctx_v, lse_v)
+        dst.copy_(ctx.to(dst.dtype))
+        ldst.copy_(lse)
+
+
+def attention_bwd(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, Lv, heads, d, pair_mask, p_t, p_v,
+                  seed, backend, dctx_t=None, dctx_v=None, dqkv_t=None, dqkv_v=None):
+    leaves = {}
+    with torch.enable_grad():
+        a = qkv_t.detach().float().requires_grad_(True) if qkv_t is not None else None
+        b = qkv_v.detach().float().requires_grad_(True) if qkv_v is not None else None
+        out = _attn_forward_math(a, b, mask_t, mask_v, B, Lt, Lv, heads, d, pair_mask)
+        tot = 0
+        for qs, (ctx, _) in out.items():
+            g = dctx_t if qs == 0 else dctx_v
+            tot = tot + (ctx * g.float()).sum()
+        tot.backward()
+    if a is not None:
+        dqkv_t.copy_((a.grad if a.grad is not None else torch.zeros_like(a)).to(dqkv_t.dtype))
+    if b is not None:
+        dqkv_v.copy_((b.grad if b.grad is not None else torch.zeros_like(b)).to(dqkv_v.dtype))
+
+
+def embed_gather_fwd(tables, idx, const_rows, out, accum=False):
+    r = out.float() if accum else torch.zeros_like(out, dtype=torch.float32)
+    for t, i, c in zip(tables, idx, const_rows):
+        r = r + (t[i] if i is not None else t[c][None, :])
+    out.copy_(r.to(out.dtype))
+    return out
+
+
+def embed_gather_bwd(dtables, idx, const_rows, dout):
+    d = dout.float()
+    for t, i, c in zip(dtables, idx, const_rows):
+        if t is None:
+            continue
+        if i is not None:
+            t.index_add_(0, i, d)
+        else:
+            t[c] += d.sum(0)
+
+
+def box_project_fwd(loc, W, b, out, accum=False):
+    r = loc @ W.t() + (b if b is not None else 0)
+    if accum:
+        r = r + out.float()
+    out.copy_(r.to(out.dtype))
+    return out
+
+
+def box_project_bwd(loc, dout, dW, db):
+    d = dout.float()
+    dW += d.t() @ loc
+    if db is not None:
+        db += d.sum(0)
+
+
+def xent_fwd(logits, labels, C_, lse, loss_sum, count):
+    x = logits[:, :C_].float()
+    live = labels >= 0
+    l = torch.logsumexp(x, -1)
+    lse.copy_(torch.where(live, l, torch.zeros_like(l)))
+    picked = x.gather(1, labels.clamp(min=0)[:, None])[:, 0]
+    loss_sum += ((l - picked) * live).sum()
+    count += live.sum()
+
+
+def xent_bwd(logits, labels, C_, lse, count, dloss, dlogits):
+    x = logits[:, :C_].float()
+    live = (labels >= 0)[:, None]
+    g = dloss / count.clamp(min=1.0)
+    p = torch.exp(x - lse[:, None])
+    onehot = F.one_hot(labels.clamp(min=0), C_).float()
+    dlogits[:, :C_] = ((p - onehot) * g * live).to(dlogits.dtype)
+
+
+def _kl_rows(per, per_ld, skip, rows):
+    r = torch.arange(rows)
+    return (r // per) * per_ld + (r % per) + skip
+
+
+def kl_fwd(logits, per, per_ld, skip, label, target, C_, weight, lse, loss_sum, count):
+    rows = label.numel()
+    x = logits[_kl_rows(per, per_ld, skip, rows), :C_].float()
+    live = label == 1
+    l = torch.logsumexp(x, -1)
+    lse.copy_(torch.where(live, l, torch.zeros_like(l)))
+    kl = torch.where(target > 0, target * (torch.log(target.clamp(min=1e-45)) - (x - l[:, None])), torch.zeros_like(x)).sum(-1)
+    loss_sum += weight * (kl * live).sum()
+    count += live.sum()
+
+
+def kl_bwd(logits, per, per_ld, skip, label, target, C_, weight, lse, count, dloss, dlogits):
+    rows = label.numel()
+    idx = _kl_rows(per, per_ld, skip, rows)
+    x = logits[idx, :C_].float()
+    live = (label == 1)[:, None]
+    g = weight * dloss / count.clamp(min=1.0)
+    p = torch.exp(x - lse[:, None])
+    d = g * (p * target.sum(-1, keepdim=True) - target) * live
+    full = torch.zeros(dlogits.shape[0], C_)
+    full[idx] = d
+    dlogits[:, :C_] = full.to(dlogits.dtype)
+
+
+def loss_finalize(loss_sum, count, out):
+    out.copy_(loss_sum / count.clamp(min=1.0))
+    return out
+
+
+def eltwise(op, a, out, b=None, alpha=1.0, p=0.0, seed=0, offset=0):
+    E = _lib
+    af = a.float()
+    bf = b.float() if b is not None else None
+    if op == E.ELT_COPY:
+        r = af
+    elif op == E.ELT_ADD:
+        r = af + bf
+    elif op == E.ELT_MUL:
+        r = af * bf
+    elif op == E.ELT_RELU:
+        r = torch.relu(af)
+    elif op == E.ELT_DRELU:
+        r = af * (bf > 0)
+    elif op == E.ELT_GELU:
+        r = _gelu(af)
+    elif op == E.ELT_DGELU:
+        r = af * _dgelu(bf)
+    elif op == E.ELT_SCALE:
+        r = af * alpha
+    elif op == E.ELT_DROPOUT:
+        assert p == 0.0
+        r = af
+    elif op == E.ELT_AXPY:
+        r = out.float() + alpha * af
+    else:
+        raise ValueError(op)
+    out.copy_(r.reshape(out.shape).to(out.dtype))
+    return out
+
+
+def colsum(a, out):
+    out[:a.shape[-1]] += a.float().reshape(-1, a.shape[-1]).sum(0)
+    return out
+
+
+def gather_rows(a, idx, out):
+    out.copy_(a[idx])
+    return out
+
+
+def scatter_rows_add(a, idx, out):
+    out.index_add_(0, idx, a)
+    return out
+
+
+def cast_bf16(src, dst):
+    dst.copy_(src.to(torch.bfloat16))
+    return dst
+
+
+def box_sincos(boxes, dim, out):
+    cx = (boxes[:, 0] + boxes[:, 2]) / 2 * 100
+    cy = (boxes[:, 1] + boxes[:, 3]) / 2 * 100
+    w = (boxes[:, 2] - boxes[:, 0]) * 100
+    h = (boxes[:, 3] - boxes[:, 1]) * 100
+    pos = torch.stack([cx, cy, w, h], -1)
+    freq = 1000 ** (torch.arange(dim, dtype=torch.float32) / float(dim))
+    ang = pos[..., None] / freq
+    out.copy_(torch.cat([ang.sin(), ang.cos()], -1).reshape(out.shape).to(out.dtype))
+    return out
+
+
+def fill(buf, value=0):
+    assert value == 0
+    buf.zero_()
+
+
+_NAMES = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "embed_gather_fwd",
+          "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd",
+          "loss_finalize", "eltwise", "colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill"]
+
+
+def install(monkeypatch):
+    """Route volta_b200.ops through the emulation for the duration of one test."""
+    g = globals()
+    for n in _NAMES:
+        monkeypatch.setattr(ops, n, g[n])
+    monkeypatch.setattr(ops, "require_cuda", lambda *a: None)
+    monkeypatch.setattr(engine, "_check_inputs", lambda *a: None)

@@ -1,0 +1,200 @@
+// Embedding kernels: the gather-sum of word/position/token-type rows (volta/embeddings.py:55-65, 345-348,
+// 442-445) and the K = num_locs box projection (embeddings.py:135,141; a 5-wide Linear is FMAs, not a GEMM).
+// The LayerNorm that follows is vb_layernorm_fwd; the 2048-d region projection is vb_gemm.
+#include "common.cuh"
+
+namespace vb {
+namespace emb {
+
+constexpr int MAX_TABLES = 4;
+struct Tables {
+  const float* table[MAX_TABLES];
+  const int64_t* idx[MAX_TABLES];
+  int64_t const_row[MAX_TABLES];
+  int n;
+};
+struct GradTables {
+  float* table[MAX_TABLES];
+  const int64_t* idx[MAX_TABLES];
+  int64_t const_row[MAX_TABLES];
+  int n;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_fwd_kernel(Tables t, T* __restrict__ out, int64_t ld_out, int64_t rows, int H, int accum) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  int64_t src[MAX_TABLES];
+#pragma unroll
+  for (int j = 0; j < MAX_TABLES; ++j) src[j] = (j < t.n) ? (t.idx[j] ? t.idx[j][r] : t.const_row[j]) : 0;
+  for (int c = lane * 8; c < H; c += 256) {
+    float acc[8];
+    if (accum) Vec8<T>::load(out + r * ld_out + c, acc);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < MAX_TABLES; ++j) {
+      if (j < t.n) {
+        float v[8];
+        Vec8<float>::load(t.table[j] + src[j] * H + c, v);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v[k];
+      }
+    }
+    Vec8<T>::store(out + r * ld_out + c, acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_bwd_kernel(GradTables t, const T* __restrict__ dout, int64_t ld, int64_t rows, int H) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  int64_t dst[MAX_TABLES];
+#pragma unroll
+  for (int j = 0; j < MAX_TABLES; ++j) dst[j] = (j < t.n) ? (t.idx[j] ? t.idx[j][r] : t.const_row[j]) : 0;
+  for (int c = lane * 8; c < H; c += 256) {
+    float v[8];
+    Vec8<T>::load(dout + r * ld + c, v);
+#pragma unroll
+    for (int j = 0; j < MAX_TABLES; ++j) {
+      if (j < t.n && t.table[j] != nullptr) {
+        float* d = t.table[j] + dst[j] * H + c;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) atomicAdd(d + k, v[k]);
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+box_fwd_kernel(const float* __restrict__ loc, int nl, const float* __restrict__ W, const float* __restrict__ b,
+               T* __restrict__ out, int64_t ld_out, int64_t rows, int H, int accum) {
+  const int64_t total = rows * H;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / H;
+    const int c = (int)(i - r * H);
+    float s = b ? b[c] : 0.f;
+    for (int j = 0; j < nl; ++j) s = fmaf(loc[r * nl + j], W[c * nl + j], s);
+    if (accum) s += to_f<T>(out[r * ld_out + c]);
+    out[r * ld_out + c] = from_f<T>(s);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+box_bwd_kernel(const float* __restrict__ loc, int nl, const T* __restrict__ dout, int64_t ld, float* __restrict__ dW,
+               float* __restrict__ db, int64_t rows, int H, int64_t rows_per_block) {
+  __shared__ float part[8][9][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) acc[j] = 0.f;
+  if (c < H) {
+    for (int64_t r = r0 + warp; r < r1; r += 8) {
+      const float g = to_f<T>(dout[r * ld + c]);
+      acc[8] += g;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nl) acc[j] = fmaf(g, loc[r * nl + j], acc[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 9; ++j) part[warp][j][lane] = acc[j];
+  __syncthreads();
+  if (warp == 0 && c < H) {
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += part[w][j][lane];
+      if (j < nl) atomicAdd(dW + (int64_t)c * nl + j, s);
+      else if (j == 8 && db) atomicAdd(db + c, s);
+    }
+  }
+}
+
+}  // namespace emb
+}  // namespace vb
+
+extern "C" {
+
+int vb_embed_gather_fwd(const float* const* tables, const int64_t* const* idx, const int64_t* const_rows,
+                        int32_t n_tables, void* out, int64_t ld_out, int64_t rows, int32_t H, int32_t accum,
+                        int32_t dtype, void* stream) {
+  VB_REQUIRE(tables && out && n_tables >= 1 && n_tables <= vb::emb::MAX_TABLES, VB_ERR_ARG, "embed_gather_fwd: bad table list");
+  VB_REQUIRE(H % 8 == 0 && vb::aligned16(out) && (ld_out % 8) == 0, VB_ERR_ARG, "embed_gather_fwd: H/ld must be multiples of 8");
+  if (rows == 0) return 0;
+  vb::emb::Tables t{};
+  t.n = n_tables;
+  for (int j = 0; j < n_tables; ++j) {
+    VB_REQUIRE(tables[j] && vb::aligned16(tables[j]), VB_ERR_ARG, "embed_gather_fwd: table %d null/unaligned", j);
+    t.table[j] = tables[j];
+    t.idx[j] = idx ? idx[j] : nullptr;
+    t.const_row[j] = const_rows ? const_rows[j] : 0;
+  }
+  const unsigned grid = (unsigned)vb::ceil_div(rows, 8);
+  if (dtype == VB_BF16)
+    vb::emb::gather_fwd_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(t, (vb::bf16*)out, ld_out, rows, H, accum);
+  else
+    vb::emb::gather_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(t, (float*)out, ld_out, rows, H, accum);
+  return vb::check_launch("embed_gather_fwd_kernel");
+}
+
+int vb_embed_gather_bwd(float* const* dtables, const int64_t* const* idx, const int64_t* const_rows, int32_t n_tables,
+                        const void* dout, int64_t ld_dout, int64_t rows, int32_t H, int32_t dtype, void* stream) {
+  VB_REQUIRE(dtables && dout && n_tables >= 1 && n_tables <= vb::emb::MAX_TABLES, VB_ERR_ARG, "embed_gather_bwd: bad table list");
+  VB_REQUIRE(H % 8 == 0 && vb::aligned16(dout) && (ld_dout % 8) == 0, VB_ERR_ARG, "embed_gather_bwd: H/ld must be multiples of 8");
+  if (rows == 0) return 0;
+  vb::emb::GradTables t{};
+  t.n = n_tables;
+  for (int j = 0; j < n_tables; ++j) {
+    t.table[j] = dtables[j];  // may be NULL: that table gets no gradient (frozen)
+    t.idx[j] = idx ? idx[j] : nullptr;
+    t.const_row[j] = const_rows ? const_rows[j] : 0;
+  }
+  const unsigned grid = (unsigned)vb::ceil_div(rows, 8);
+  if (dtype == VB_BF16)
+    vb::emb::gather_bwd_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(t, (const vb::bf16*)dout, ld_dout, rows, H);
+  else
+    vb::emb::gather_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(t, (const float*)dout, ld_dout, rows, H);
+  return vb::check_launch("embed_gather_bwd_kernel");
+}
+
+int vb_box_project_fwd(const float* loc, int32_t nl, const float* W, const float* b, void* out, int64_t ld_out,
+                       int64_t rows, int32_t H, int32_t accum, int32_t dtype, void* stream) {
+  VB_REQUIRE(loc && W && out && nl >= 1 && nl <= 8, VB_ERR_ARG, "box_project_fwd: bad arguments (nl=%d)", nl);
+  if (rows == 0) return 0;
+  const unsigned g = (unsigned)std::min<int64_t>(vb::ceil_div(rows * H, 256), 148 * 16);
+  if (dtype == VB_BF16)
+    vb::emb::box_fwd_kernel<vb::bf16><<<g, 256, 0, (cudaStream_t)stream>>>(loc, nl, W, b, (vb::bf16*)out, ld_out, rows, H, accum);
+  else
+    vb::emb::box_fwd_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(loc, nl, W, b, (float*)out, ld_out, rows, H, accum);
+  return vb::check_launch("box_fwd_kernel");
+}
+
+int vb_box_project_bwd(const float* loc, int32_t nl, const void* dout, int64_t ld_dout, float* dW, float* db,
+                       int64_t rows, int32_t H, int32_t dtype, void* stream) {
+  VB_REQUIRE(loc && dout && dW && nl >= 1 && nl <= 8, VB_ERR_ARG, "box_project_bwd: bad arguments (nl=%d)", nl);
+  if (rows == 0) return 0;
+  const int64_t strips = vb::ceil_div(H, 32);
+  int64_t slabs = std::max<int64_t>(1, std::min<int64_t>(vb::ceil_div(rows, 64), (148 * 4) / strips));
+  const int64_t rpb = vb::ceil_div(rows, slabs);
+  slabs = vb::ceil_div(rows, rpb);
+  dim3 grid((unsigned)strips, (unsigned)slabs);
+  if (dtype == VB_BF16)
+    vb::emb::box_bwd_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(loc, nl, (const vb::bf16*)dout, ld_dout, dW, db, rows, H, rpb);
+  else
+    vb::emb::box_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(loc, nl, (const float*)dout, ld_dout, dW, db, rows, H, rpb);
+  return vb::check_launch("box_bwd_kernel");
+}
+
+}  // extern "C"

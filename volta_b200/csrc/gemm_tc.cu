@@ -1,0 +1,463 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = epilogue( A . B^T ), bf16 operands, fp32 accumulation.
+//
+// One persistent, warp-specialised kernel serves nn.Linear forward, dgrad and wgrad
+// (volta/encoders.py:204-206,376,463,518 ... and their autograd):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx)
+//   warp 1   : MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, accumulators in TMEM)
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue       (tcgen05.ld 32x32b -> bias/GELU/dropout/residual/... -> global)
+// The TMEM accumulator is double buffered (2 x BN columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1.  Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]);
+// the latter is what dgrad (B = W[out,in]) and wgrad (A = dY, B = X) need, and is expressed purely
+// through the shared-memory matrix descriptors - no transposed copies are ever made.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "gemm_common.cuh"
+
+namespace vb {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;               // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr uint32_t MN_BLOCK_BYTES = 64 * BK * 2;  // one 64(mn) x 64(k) MN-major TMA box = 8 KB
+
+template <int BN> struct Cfg {
+  static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256 (power of two >= 32)
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+};
+
+struct Params {
+  EpiParams epi;
+  int32_t num_m_blocks, num_n_blocks;
+  int32_t kb_total, kb_per_split, split_k;
+  int32_t a_kmajor, b_kmajor;
+  uint32_t idesc;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("volta_b200 gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <uint32_t COLS> __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// mbarrier arrives when all tcgen05.mma issued so far by this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
+//   K-major : rows of 128 B (64 bf16 of K); 8-row groups SBO = 1024 B apart; LBO unused.
+//   MN-major: rows of 128 B (64 bf16 of M/N) per K index; 8-K groups SBO = 1024 B apart;
+//             successive 64-element M/N blocks LBO = 8192 B apart (one TMA box each).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool kmajor) {
+  const uint64_t lbo = kmajor ? 1ull : (uint64_t)(MN_BLOCK_BYTES >> 4);
+  const uint64_t sbo = 1024ull >> 4;
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ---- epilogue for one row, 32 consecutive columns ------------------------------
+template <typename OutT>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const uint32_t (&acc)[32], int64_t m, int64_t n0) {
+  const int e = p.epilogue;
+  if (e == VB_EPI_ACCUM) {
+    float* d = reinterpret_cast<float*>(p.D) + m * p.ldd + n0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n0 + j < p.N) atomicAdd(d + j, __uint_as_float(acc[j]) * p.alpha);
+    return;
+  }
+  const bool use_bias = epi_uses_bias(e), use_aux = epi_uses_aux_in(e);
+  OutT* d = reinterpret_cast<OutT*>(p.D) + m * p.ldd + n0;
+  const OutT* ai = use_aux ? reinterpret_cast<const OutT*>(p.aux_in) + m * p.ld_aux + n0 : nullptr;
+  OutT* ao = (e == VB_EPI_BIAS_GELU) ? reinterpret_cast<OutT*>(p.aux_out) + m * p.ld_aux + n0 : nullptr;
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {  // groups of 8 columns (16 B of bf16 / 32 B of fp32)
+    const int64_t n = n0 + g * 8;
+    if (n >= p.N) break;
+    const bool full = (n + 8 <= p.N);
+    float b[8], x[8], o[8], pre[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { b[j] = 0.f; x[j] = 0.f; pre[j] = 0.f; }
+    if (use_bias) {
+      if (full) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+      } else {
+        for (int j = 0; j < 8; ++j) if (n + j < p.N) b[j] = __ldg(p.bias + n + j);
+      }
+    }
+    if (use_aux) {
+      if (full) Vec8<OutT>::load(ai + g * 8, x);
+      else for (int j = 0; j < 8; ++j) if (n + j < p.N) x[j] = to_f<OutT>(ai[g * 8 + j]);
+    }
+    if (e == VB_EPI_BIAS_DROP_RES && p.drop_thresh != 0u && (p.N & 3) == 0) {
+      // vectorised dropout: one Philox block per 4 columns
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        bool keep[4];
+        dropout_keep4(p.seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + h * 4), p.drop_thresh, keep);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float v = __uint_as_float(acc[g * 8 + h * 4 + j]) * p.alpha + b[h * 4 + j];
+          o[h * 4 + j] = (keep[j] ? v * p.drop_scale : 0.0f) + x[h * 4 + j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = epilogue_scalar(p, __uint_as_float(acc[g * 8 + j]), b[j], x[j], m, n + j, pre[j]);
+    }
+    if (full) {
+      Vec8<OutT>::store(d + g * 8, o);
+      if (ao) Vec8<OutT>::store(ao + g * 8, pre);
+    } else {
+      for (int j = 0; j < 8; ++j)
+        if (n + j < p.N) {
+          d[g * 8 + j] = from_f<OutT>(o[j]);
+          if (ao) ao[g * 8 + j] = from_f<OutT>(pre[j]);
+        }
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024 B alignment
+  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int64_t tiles = (int64_t)p.num_m_blocks * p.num_n_blocks;
+  const int64_t total_work = tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = (int)(w % p.split_k);
+      const int64_t tile = w / p.split_k;
+      const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+        if (p.a_kmajor) {
+          tma_load_2d(smem_a(stage), &tmA, full_bar(stage), kb * BK, m_blk * BM);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_2d(smem_a(stage) + j * MN_BLOCK_BYTES, &tmA, full_bar(stage), m_blk * BM + j * 64, kb * BK);
+        }
+        if (p.b_kmajor) {
+          tma_load_2d(smem_b(stage), &tmB, full_bar(stage), kb * BK, n_blk * BN);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(smem_b(stage) + j * MN_BLOCK_BYTES, &tmB, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+        }
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    const uint32_t a_step = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);  // bytes per UMMA_K step
+    const uint32_t b_step = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
+    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const int split = (int)(w % p.split_k);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t adesc = make_smem_desc(smem_a(stage) + k * a_step, p.a_kmajor);
+          const uint64_t bdesc = make_smem_desc(smem_b(stage) + k * b_step, p.b_kmajor);
+          umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue =====================
+    const int ew = warp - EPI_WARP0;  // == warp % 4: TMEM lane quarter this warp may access
+    int it = 0;
+    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const int64_t tile = w / p.split_k;
+      const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
+      const int split = (int)(w % p.split_k);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(as), aphase);
+      tcgen05_fence_after();
+      const int64_t m = (int64_t)m_blk * BM + ew * 32 + lane;
+      const bool row_ok = (m < p.epi.M) && (kb1 > kb0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int64_t n0 = (int64_t)n_blk * BN + c * 32;
+        if (n0 >= p.epi.N) break;  // warp-uniform
+        uint32_t acc[32];
+        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
+        tmem_ld_wait();
+        if (row_ok) {
+          if (p.epi.d_bf16) epilogue_chunk<bf16>(p.epi, acc, m, n0);
+          else epilogue_chunk<float>(p.epi, acc, m, n0);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major matrix [rows, cols] (pitch ld elements), box = 64 cols x box_rows, 128B swizzle.
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  VB_REQUIRE(enc != nullptr, VB_ERR_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VB_REQUIRE(r == CUDA_SUCCESS, VB_ERR_ARG, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+             (long long)rows, (long long)cols, (long long)ld);
+  return 0;
+}
+
+static int g_sm_count = 0;
+static int sm_count() {
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_sm_count;
+}
+
+template <int BN>
+static int launch(const vb_gemm_args& a, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  Params p;
+  int rc = fill_epi_params(a, p.epi);
+  if (rc) return rc;
+  p.num_m_blocks = (int)ceil_div(a.M, BM);
+  p.num_n_blocks = (int)ceil_div(a.N, BN);
+  p.kb_total = (int)ceil_div(a.K, BK);
+  p.a_kmajor = a.a_kmajor;
+  p.b_kmajor = a.b_kmajor;
+  const int64_t tiles = (int64_t)p.num_m_blocks * p.num_n_blocks;
+  int split = 1;
+  if (a.epilogue == VB_EPI_ACCUM) {
+    split = a.split_k;
+    if (split <= 0) {  // fill the machine: as many K slices as keep >= 4 k-blocks per slice
+      split = (int)ceil_div(sm_count(), tiles);
+      split = (int)std::min<int64_t>(split, std::max<int64_t>(1, p.kb_total / 4));
+    }
+    split = std::max(1, std::min(split, p.kb_total));
+  }
+  p.kb_per_split = (int)ceil_div(p.kb_total, split);
+  p.split_k = (int)ceil_div(p.kb_total, p.kb_per_split);
+  // instruction descriptor (cute::UMMA::InstrDescriptor): F32 accum, BF16 x BF16, majors, N>>3, M>>4
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a.a_kmajor ? 0u : 1u) << 15) | ((a.b_kmajor ? 0u : 1u) << 16) |
+            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  CUtensorMap tmA, tmB;
+  if (a.a_kmajor) rc = make_map(&tmA, a.A, a.M, a.K, a.lda, BM);
+  else rc = make_map(&tmA, a.A, a.K, a.M, a.lda, BK);
+  if (rc) return rc;
+  if (a.b_kmajor) rc = make_map(&tmB, a.B, a.N, a.K, a.ldb, BN);
+  else rc = make_map(&tmB, a.B, a.K, a.N, a.ldb, BK);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    VB_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int64_t work = tiles * p.split_k;
+  const int grid = (int)std::min<int64_t>(work, sm_count());
+  gemm_tc_kernel<BN><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+}  // namespace tc
+
+bool gemm_tc_supported(const vb_gemm_args& a, const char** why) {
+  auto fail = [&](const char* w) { if (why) *why = w; return false; };
+  if (a.ab_dtype != VB_BF16) return fail("operands are not bf16");
+  if (!aligned16(a.A) || !aligned16(a.B)) return fail("operand base not 16-byte aligned");
+  if ((a.lda % 8) != 0 || (a.ldb % 8) != 0) return fail("operand pitch not a multiple of 8 elements");
+  if (a.M < 1 || a.N < 1 || a.K < 1) return fail("empty problem");
+  const int esz = a.d_dtype == VB_BF16 ? 2 : 4;
+  if (!aligned16(a.D) || (a.ldd * esz) % 16 != 0) return fail("D not 16-byte aligned");
+  if (epi_uses_aux_in(a.epilogue) && (!aligned16(a.aux_in) || (a.ld_aux * esz) % 16 != 0)) return fail("aux_in alignment");
+  if (a.epilogue == VB_EPI_BIAS_GELU && (!aligned16(a.aux_out) || (a.ld_aux * esz) % 16 != 0)) return fail("aux_out alignment");
+  if (epi_uses_bias(a.epilogue) && !aligned16(a.bias)) return fail("bias alignment");
+  if (a.epilogue == VB_EPI_ACCUM && a.d_dtype != VB_F32) return fail("ACCUM needs fp32 D");
+  return true;
+}
+
+int gemm_tc_launch(const vb_gemm_args& a, cudaStream_t stream) {
+  const char* why = nullptr;
+  VB_REQUIRE(gemm_tc_supported(a, &why), VB_ERR_UNSUPPORTED, "tcgen05 GEMM cannot run this problem: %s", why);
+  // BN = 256 halves B traffic per MMA; BN = 128 wastes fewer columns when N is small.
+  if (a.N > 128) return tc::launch<256>(a, stream);
+  return tc::launch<128>(a, stream);
+}
+
+}  // namespace vb

@@ -1,0 +1,276 @@
+// LayerNorm forward / backward - replaces apex FusedLayerNorm (apex/csrc/layer_norm_cuda_kernel.cu:
+// cuApplyLayerNorm :279-322, cuComputeGradInput :522-637, cuCompute(Part)GradGammaBeta :403-520) and the
+// Python BertLayerNorm (volta/encoders.py:48-61).  HBM-bound: one warp per row, 16-byte vector loads, the
+// row stays in registers between the statistics and the normalisation (one read, one write per element),
+// fp32 statistics, warp-shuffle reductions.  The backward fuses the residual blocks' extras: the dropout-
+// masked copy of dx that feeds the preceding dense layer's dgrad/wgrad, and the dense bias gradient.
+#include "common.cuh"
+
+namespace vb {
+namespace ln {
+
+constexpr int WARPS = 8;
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+              T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int H,
+              float eps, float out_scale, int accum) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
+  if (row >= rows) return;
+  const T* xr = x + row * H;
+  float v[NV][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) {
+      Vec8<T>::load(xr + c, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+    }
+  }
+  const float mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; q += d * d; }
+    }
+  }
+  const float var = warp_sum(q) / (float)H;       // biased variance
+  const float rstd = rsqrtf(var + eps);           // eps inside the sqrt
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  T* yr = y + row * H;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) {
+      float g[8], b[8], o[8];
+      Vec8<float>::load(gamma + c, g);
+      Vec8<float>::load(beta + c, b);
+      if (accum) Vec8<T>::load(yr + c, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float t = (g[j] * ((v[i][j] - mean) * rstd) + b[j]) * out_scale;
+        o[j] = accum ? o[j] + t : t;
+      }
+      Vec8<T>::store(yr + c, o);
+    }
+  }
+}
+
+// Backward.  Each warp walks rows (row = warp_global + k * total_warps) and keeps per-lane column partial
+// sums for dgamma / dbeta (/ dbias) in registers; the block reduces them through shared memory and issues
+// one atomicAdd per column.
+template <typename T, int NV, bool EXTRA>
+__global__ void __launch_bounds__(WARPS * 32)
+ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
+              float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int H, float out_scale,
+              T* __restrict__ dx_drop, uint32_t drop_thresh, float drop_scale, uint64_t seed, uint64_t offset,
+              float* __restrict__ dbias) {
+  extern __shared__ float red[];  // [WARPS][H] reused for each of the column sums
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
+  const int64_t total_warps = (int64_t)gridDim.x * WARPS;
+  float ag[NV][8], ab[NV][8], abias[NV][8];
+  float gm[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (lane + 32 * i) * 8;
+    if (c < H) Vec8<float>::load(gamma + c, gm[i]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      ag[i][j] = 0.f; ab[i][j] = 0.f;
+      abias[i][j] = 0.f;
+      if (c >= H) gm[i][j] = 0.f;
+    }
+  }
+  for (int64_t row = warp_global; row < rows; row += total_warps) {
+    const float mu = mean[row], rs = rstd[row];
+    float xh[NV][8], g[NV][8];
+    float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < H) {
+        float d[8], xv[8];
+        Vec8<T>::load(dy + row * H + c, d);
+        Vec8<T>::load(x + row * H + c, xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dyo = d[j] * out_scale;
+          xh[i][j] = (xv[j] - mu) * rs;
+          g[i][j] = dyo * gm[i][j];
+          c1 += g[i][j];
+          c2 += g[i][j] * xh[i][j];
+          ag[i][j] += dyo * xh[i][j];
+          ab[i][j] += dyo;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { xh[i][j] = 0.f; g[i][j] = 0.f; }
+      }
+    }
+    c1 = warp_sum(c1) / (float)H;
+    c2 = warp_sum(c2) / (float)H;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < H) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - c1 - xh[i][j] * c2);
+        Vec8<T>::store(dx + row * H + c, o);
+        if constexpr (EXTRA) {
+          if (dx_drop != nullptr) {
+            float od[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              bool keep[4];
+              dropout_keep4(seed, offset, (uint64_t)row * (uint64_t)H + (uint64_t)(c + h * 4), drop_thresh, keep);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) od[h * 4 + j] = keep[j] ? o[h * 4 + j] * drop_scale : 0.f;
+            }
+            Vec8<T>::store(dx_drop + row * H + c, od);
+            // the bias gradient sees what the dense layer's output gradient is: the rounded, masked copy
+#pragma unroll
+            for (int j = 0; j < 8; ++j) abias[i][j] += to_f<T>(from_f<T>(od[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) abias[i][j] += to_f<T>(from_f<T>(o[j]));
+          }
+        }
+      }
+    }
+  }
+  // block reduction of the column partials
+  auto reduce_store = [&](float (&acc)[NV][8], float* out) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < H) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[warp * H + c + j] = acc[i][j];
+      }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < H; c += WARPS * 32) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < WARPS; ++w) s += red[w * H + c];
+      atomicAdd(out + c, s);
+    }
+  };
+  if (dgamma) reduce_store(ag, dgamma);
+  if (dbeta) reduce_store(ab, dbeta);
+  if constexpr (EXTRA) {
+    if (dbias) reduce_store(abias, dbias);
+  }
+}
+
+template <typename T>
+static int fwd_dispatch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                        int64_t rows, int H, float eps, float out_scale, int accum, cudaStream_t st) {
+  const int nv = (H + 255) / 256;
+  const unsigned grid = (unsigned)ceil_div(rows, WARPS);
+#define VB_LN_FWD(NV_)                                                                                             \
+  ln_fwd_kernel<T, NV_><<<grid, WARPS * 32, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, rows, H, eps, \
+                                                     out_scale, accum)
+  switch (nv) {
+    case 1: VB_LN_FWD(1); break;
+    case 2: VB_LN_FWD(2); break;
+    case 3: VB_LN_FWD(3); break;
+    case 4: VB_LN_FWD(4); break;
+    case 5: case 6: VB_LN_FWD(6); break;
+    case 7: case 8: VB_LN_FWD(8); break;
+    default: set_error("layernorm: H=%d > 2048 unsupported", H); return VB_ERR_UNSUPPORTED;
+  }
+#undef VB_LN_FWD
+  return check_launch("ln_fwd_kernel");
+}
+
+template <typename T>
+static int bwd_dispatch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                        void* dx, float* dgamma, float* dbeta, int64_t rows, int H, float out_scale, void* dx_drop,
+                        float p, uint64_t seed, uint64_t offset, float* dbias, cudaStream_t st) {
+  const int nv = (H + 255) / 256;
+  const bool extra = (dx_drop != nullptr) || (dbias != nullptr);
+  static int sms = 0;
+  if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  // enough rows per warp to amortise the column reduction, enough blocks to fill the machine
+  int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), (int64_t)sms * 4);
+  const size_t smem = (size_t)WARPS * H * sizeof(float);
+  const uint32_t thresh = dx_drop ? dropout_thresh(p) : 0u;
+  const float scale = 1.f / (1.f - p);
+#define VB_LN_BWD(NV_, EX_)                                                                                      \
+  do {                                                                                                           \
+    if (smem > 48 * 1024)                                                                                        \
+      cudaFuncSetAttribute(ln_bwd_kernel<T, NV_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+    ln_bwd_kernel<T, NV_, EX_><<<(unsigned)grid, WARPS * 32, smem, st>>>(                                        \
+        (const T*)dy, (const T*)x, mean, rstd, gamma, (T*)dx, dgamma, dbeta, rows, H, out_scale, (T*)dx_drop,    \
+        thresh, scale, seed, offset, dbias);                                                                     \
+  } while (0)
+#define VB_LN_BWD2(NV_) do { if (extra) VB_LN_BWD(NV_, true); else VB_LN_BWD(NV_, false); } while (0)
+  switch (nv) {
+    case 1: VB_LN_BWD2(1); break;
+    case 2: VB_LN_BWD2(2); break;
+    case 3: VB_LN_BWD2(3); break;
+    case 4: VB_LN_BWD2(4); break;
+    case 5: case 6: VB_LN_BWD2(6); break;
+    case 7: case 8: VB_LN_BWD2(8); break;
+    default: set_error("layernorm: H=%d > 2048 unsupported", H); return VB_ERR_UNSUPPORTED;
+  }
+#undef VB_LN_BWD2
+#undef VB_LN_BWD
+  return check_launch("ln_bwd_kernel");
+}
+
+}  // namespace ln
+}  // namespace vb
+
+extern "C" {
+
+int vb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                     int64_t rows, int32_t H, float eps, float out_scale, int32_t accum, int32_t dtype, void* stream) {
+  VB_REQUIRE(x && gamma && beta && y, VB_ERR_ARG, "layernorm_fwd: null pointer");
+  VB_REQUIRE(rows >= 0 && H > 0 && H % 8 == 0, VB_ERR_ARG, "layernorm_fwd: H=%d must be a positive multiple of 8", H);
+  VB_REQUIRE(vb::aligned16(x) && vb::aligned16(y) && vb::aligned16(gamma) && vb::aligned16(beta), VB_ERR_ARG,
+             "layernorm_fwd: pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  if (dtype == VB_BF16)
+    return vb::ln::fwd_dispatch<vb::bf16>(x, gamma, beta, y, mean, rstd, rows, H, eps, out_scale, accum, (cudaStream_t)stream);
+  VB_REQUIRE(dtype == VB_F32, VB_ERR_ARG, "layernorm_fwd: bad dtype %d", dtype);
+  return vb::ln::fwd_dispatch<float>(x, gamma, beta, y, mean, rstd, rows, H, eps, out_scale, accum, (cudaStream_t)stream);
+}
+
+int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                     float* dgamma, float* dbeta, int64_t rows, int32_t H, float out_scale, void* dx_drop,
+                     float dropout_p, uint64_t seed, uint64_t offset, float* dbias, int32_t dtype, void* stream) {
+  VB_REQUIRE(dy && x && mean && rstd && gamma && dx, VB_ERR_ARG, "layernorm_bwd: null pointer");
+  VB_REQUIRE(rows >= 0 && H > 0 && H % 8 == 0, VB_ERR_ARG, "layernorm_bwd: H=%d must be a positive multiple of 8", H);
+  VB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, VB_ERR_ARG, "layernorm_bwd: dropout_p out of range");
+  VB_REQUIRE(vb::aligned16(dy) && vb::aligned16(x) && vb::aligned16(dx) && vb::aligned16(gamma) &&
+                 (!dx_drop || vb::aligned16(dx_drop)), VB_ERR_ARG, "layernorm_bwd: pointers must be 16-byte aligned");
+  if (rows == 0) return 0;
+  if (dropout_p == 0.f) dx_drop = nullptr;
+  if (dtype == VB_BF16)
+    return vb::ln::bwd_dispatch<vb::bf16>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, H, out_scale, dx_drop,
+                                          dropout_p, seed, offset, dbias, (cudaStream_t)stream);
+  VB_REQUIRE(dtype == VB_F32, VB_ERR_ARG, "layernorm_bwd: bad dtype %d", dtype);
+  return vb::ln::bwd_dispatch<float>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, H, out_scale, dx_drop,
+                                     dropout_p, seed, offset, dbias, (cudaStream_t)stream);
+}
+
+}  // extern "C"

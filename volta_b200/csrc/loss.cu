@@ -1,0 +1,250 @@
+// Pre-training criteria on device: CrossEntropyLoss(ignore_index=-1) for MLM / ITM
+// (volta/encoders.py:1030, 1095-1109) and the masked-region KL `kl_1601` (volta/losses.py:16-22).
+// One block per logits row; rows whose label is ignored are never read (their gradient is zero).
+// The backward recomputes the softmax from the saved row log-sum-exp and may run in place over the logits.
+#include "common.cuh"
+
+namespace vb {
+namespace loss {
+
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ float block_max(float v, float* sh) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = sh[0];
+#pragma unroll
+  for (int w = 1; w < THREADS / 32; ++w) r = fmaxf(r, sh[w]);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float r = 0.f;
+#pragma unroll
+  for (int w = 0; w < THREADS / 32; ++w) r += sh[w];
+  __syncthreads();
+  return r;
+}
+
+// log-sum-exp of one row (block-cooperative).  Vector path when the row is 16-byte aligned.
+template <typename T>
+__device__ __forceinline__ float row_lse(const T* __restrict__ x, int C, bool vec_ok, float* sh) {
+  float mx = -INFINITY;
+  const int C8 = vec_ok ? (C & ~7) : 0;
+  for (int c = threadIdx.x * 8; c < C8; c += THREADS * 8) {
+    float v[8];
+    Vec8<T>::load(x + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mx = fmaxf(mx, v[j]);
+  }
+  for (int c = C8 + threadIdx.x; c < C; c += THREADS) mx = fmaxf(mx, to_f<T>(x[c]));
+  mx = block_max(mx, sh);
+  float s = 0.f;
+  for (int c = threadIdx.x * 8; c < C8; c += THREADS * 8) {
+    float v[8];
+    Vec8<T>::load(x + c, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += __expf(v[j] - mx);
+  }
+  for (int c = C8 + threadIdx.x; c < C; c += THREADS) s += __expf(to_f<T>(x[c]) - mx);
+  s = block_sum(s, sh);
+  return mx + __logf(s);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+xent_fwd_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels, int C,
+                float* __restrict__ lse_out, float* __restrict__ loss_sum, float* __restrict__ count, bool vec_ok) {
+  __shared__ float sh[THREADS / 32];
+  const int64_t r = blockIdx.x;
+  const int64_t lab = labels[r];
+  if (lab < 0 || lab >= C) {  // ignore_index = -1
+    if (threadIdx.x == 0) lse_out[r] = 0.f;
+    return;
+  }
+  const T* x = logits + r * ld;
+  const float lse = row_lse<T>(x, C, vec_ok, sh);
+  if (threadIdx.x == 0) {
+    lse_out[r] = lse;
+    atomicAdd(loss_sum, lse - to_f<T>(x[lab]));
+    atomicAdd(count, 1.0f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+xent_bwd_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels, int C,
+                const float* __restrict__ lse, const float* __restrict__ count, const float* __restrict__ dloss,
+                T* __restrict__ dlogits, bool vec_ok) {
+  const int64_t r = blockIdx.x;
+  const int64_t lab = labels[r];
+  const T* x = logits + r * ld;
+  T* d = dlogits + r * ld;
+  const bool live = (lab >= 0 && lab < C);
+  const float g = live ? (*dloss) / fmaxf(*count, 1.0f) : 0.f;
+  const float l = live ? lse[r] : 0.f;
+  const int C8 = vec_ok ? (C & ~7) : 0;
+  for (int c = threadIdx.x * 8; c < C8; c += THREADS * 8) {
+    float v[8], o[8];
+    if (live) {
+      Vec8<T>::load(x + c, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (__expf(v[j] - l) - ((c + j) == lab ? 1.f : 0.f)) * g;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    }
+    Vec8<T>::store(d + c, o);
+  }
+  for (int c = C8 + threadIdx.x; c < C; c += THREADS)
+    d[c] = from_f<T>(live ? (__expf(to_f<T>(x[c]) - l) - (c == lab ? 1.f : 0.f)) * g : 0.f);
+}
+
+// ---- kl_1601 ---------------------------------------------------------------------
+// prediction row r (0 <= r < rows = B*per) lives at logits row (r/per)*per_ld + r%per + skip.
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+kl_fwd_kernel(const T* __restrict__ logits, int64_t ld, int per, int per_ld, int skip, const int64_t* __restrict__ label,
+              const float* __restrict__ target, int C, float weight, float* __restrict__ lse_out,
+              float* __restrict__ loss_sum, float* __restrict__ count, bool vec_ok) {
+  __shared__ float sh[THREADS / 32];
+  const int64_t r = blockIdx.x;
+  if (label[r] != 1) {
+    if (threadIdx.x == 0) lse_out[r] = 0.f;
+    return;
+  }
+  const T* x = logits + ((r / per) * per_ld + (r % per) + skip) * ld;
+  const float* t = target + r * (int64_t)C;
+  const float lse = row_lse<T>(x, C, vec_ok, sh);
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += THREADS) {
+    const float tv = t[c];
+    if (tv > 0.f) s += tv * (__logf(tv) - (to_f<T>(x[c]) - lse));  // KLDivLoss(log_softmax(pred), target)
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) {
+    lse_out[r] = lse;
+    atomicAdd(loss_sum, weight * s);
+    atomicAdd(count, 1.0f);
+  }
+}
+
+// grid over ALL logits rows (B*per_ld) so that skipped / unpicked rows get an explicit zero gradient.
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+kl_bwd_kernel(const T* __restrict__ logits, int64_t ld, int per, int per_ld, int skip, const int64_t* __restrict__ label,
+              const float* __restrict__ target, int C, float weight, const float* __restrict__ lse,
+              const float* __restrict__ count, const float* __restrict__ dloss, T* __restrict__ dlogits) {
+  __shared__ float sh[THREADS / 32];
+  const int64_t lr = blockIdx.x;
+  const int64_t b = lr / per_ld;
+  const int within = (int)(lr % per_ld) - skip;
+  const bool is_pred = within >= 0 && within < per;
+  const int64_t r = b * per + within;
+  const bool live = is_pred && label[r] == 1;
+  T* d = dlogits + lr * ld;
+  if (!live) {
+    for (int c = threadIdx.x; c < C; c += THREADS) d[c] = from_f<T>(0.f);
+    return;
+  }
+  const T* x = logits + lr * ld;
+  const float* t = target + r * (int64_t)C;
+  float ts = 0.f;
+  for (int c = threadIdx.x; c < C; c += THREADS) ts += t[c];
+  ts = block_sum(ts, sh);
+  const float g = weight * (*dloss) / fmaxf(*count, 1.0f);
+  const float l = lse[r];
+  for (int c = threadIdx.x; c < C; c += THREADS)
+    d[c] = from_f<T>(g * (__expf(to_f<T>(x[c]) - l) * ts - t[c]));
+}
+
+__global__ void finalize_kernel(const float* __restrict__ loss_sum, const float* __restrict__ count, float* __restrict__ out, int n) {
+  const int i = threadIdx.x;
+  if (i < n) out[i] = loss_sum[i] / fmaxf(count[i], 1.0f);
+}
+
+template <typename T> static bool row_vec_ok(const void* p, int64_t ld) {
+  return aligned16(p) && ((ld * (int64_t)sizeof(T)) % 32 == 0 || (sizeof(T) == 2 && (ld % 8) == 0));
+}
+
+}  // namespace loss
+}  // namespace vb
+
+extern "C" {
+
+int vb_xent_fwd(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C, float* lse,
+                float* loss_sum, float* count, int32_t dtype, void* stream) {
+  VB_REQUIRE(logits && labels && lse && loss_sum && count && C > 0 && ld >= C, VB_ERR_ARG, "xent_fwd: bad arguments");
+  if (rows == 0) return 0;
+  using namespace vb::loss;
+  if (dtype == VB_BF16)
+    xent_fwd_kernel<vb::bf16><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
+        (const vb::bf16*)logits, ld, labels, C, lse, loss_sum, count, row_vec_ok<vb::bf16>(logits, ld));
+  else
+    xent_fwd_kernel<float><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
+        (const float*)logits, ld, labels, C, lse, loss_sum, count, row_vec_ok<float>(logits, ld));
+  return vb::check_launch("xent_fwd_kernel");
+}
+
+int vb_xent_bwd(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C, const float* lse,
+                const float* count, const float* dloss, void* dlogits, int32_t dtype, void* stream) {
+  VB_REQUIRE(logits && labels && lse && count && dloss && dlogits && C > 0 && ld >= C, VB_ERR_ARG, "xent_bwd: bad arguments");
+  if (rows == 0) return 0;
+  using namespace vb::loss;
+  if (dtype == VB_BF16)
+    xent_bwd_kernel<vb::bf16><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
+        (const vb::bf16*)logits, ld, labels, C, lse, count, dloss, (vb::bf16*)dlogits,
+        row_vec_ok<vb::bf16>(logits, ld) && row_vec_ok<vb::bf16>(dlogits, ld));
+  else
+    xent_bwd_kernel<float><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
+        (const float*)logits, ld, labels, C, lse, count, dloss, (float*)dlogits,
+        row_vec_ok<float>(logits, ld) && row_vec_ok<float>(dlogits, ld));
+  return vb::check_launch("xent_bwd_kernel");
+}
+
+int vb_kl_fwd(const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32_t skip, const int64_t* label,
+              const float* target, int64_t rows, int32_t C, float weight, float* lse, float* loss_sum, float* count,
+              int32_t dtype, void* stream) {
+  VB_REQUIRE(logits && label && target && lse && loss_sum && count && C > 0 && ld >= C && per > 0 && per_ld >= per + skip,
+             VB_ERR_ARG, "kl_fwd: bad arguments");
+  if (rows == 0) return 0;
+  using namespace vb::loss;
+  if (dtype == VB_BF16)
+    kl_fwd_kernel<vb::bf16><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
+        (const vb::bf16*)logits, ld, per, per_ld, skip, label, target, C, weight, lse, loss_sum, count,
+        row_vec_ok<vb::bf16>(logits, ld));
+  else
+    kl_fwd_kernel<float><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
+        (const float*)logits, ld, per, per_ld, skip, label, target, C, weight, lse, loss_sum, count,
+        row_vec_ok<float>(logits, ld));
+  return vb::check_launch("kl_fwd_kernel");
+}
+
+int vb_kl_bwd(const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32_t skip, const int64_t* label,
+              const float* target, int64_t rows, int32_t C, float weight, const float* lse, const float* count,
+              const float* dloss, void* dlogits, int32_t dtype, void* stream) {
+  VB_REQUIRE(logits && label && target && lse && count && dloss && dlogits && C > 0 && ld >= C && per > 0 &&
+                 per_ld >= per + skip, VB_ERR_ARG, "kl_bwd: bad arguments");
+  if (rows == 0) return 0;
+  using namespace vb::loss;
+  const int64_t logit_rows = (rows / per) * per_ld;
+  if (dtype == VB_BF16)
+    kl_bwd_kernel<vb::bf16><<<(unsigned)logit_rows, THREADS, 0, (cudaStream_t)stream>>>(
+        (const vb::bf16*)logits, ld, per, per_ld, skip, label, target, C, weight, lse, count, dloss, (vb::bf16*)dlogits);
+  else
+    kl_bwd_kernel<float><<<(unsigned)logit_rows, THREADS, 0, (cudaStream_t)stream>>>(
+        (const float*)logits, ld, per, per_ld, skip, label, target, C, weight, lse, count, dloss, (float*)dlogits);
+  return vb::check_launch("kl_bwd_kernel");
+}
+
+int vb_loss_finalize(const float* loss_sum, const float* count, float* out, int32_t n, void* stream) {
+  VB_REQUIRE(loss_sum && count && out && n > 0 && n <= 32, VB_ERR_ARG, "loss_finalize: bad arguments");
+  vb::loss::finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(loss_sum, count, out, n);
+  return vb::check_launch("finalize_kernel");
+}
+
+}  // extern "C"

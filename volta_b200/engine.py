@@ -1,0 +1,1276 @@
+"""Execution engine: runs the VOLTA encoder forward and backward as an explicit plan of fused sm_100a kernels.
+
+The reference executes ~3000 ATen ops per forward through nn.Module.__call__ and autograd
+(SURVEY.md 2.2).  Here one `torch.autograd.Function` node covers the whole model: its forward walks the
+config's sub-layer schedule and launches the fused kernels of libvolta_b200.so (include/volta_b200.h),
+recording what each block needs for its hand-written backward; its backward walks the record in reverse
+and writes parameter gradients straight into the flat fp32 gradient buffer (store.py).  PyTorch supplies
+device memory, the current stream and the autograd hook - no arithmetic.
+
+Data layout in HBM: hidden states are row-major [rows, H] in the compute dtype (bf16, or fp32 in the
+validation mode); when both streams have the same width they share ONE buffer [B*T + B*V, H] (text rows
+first) so that sub-layers whose weights are shared between the streams (`shared_sublayers`) run as a
+single GEMM over all rows - a single-stream model (VisualBERT / UNITER / VL-BERT) is then an ordinary BERT
+layer over T+V tokens, which is what the reference's four-block gated attention with joint softmax
+computes (volta/encoders.py:285-306).
+"""
+import math
+import os
+
+import torch
+
+from . import _lib, ops
+from ._lib import (EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_BIAS_ADD, EPI_BIAS_DROP_RES, EPI_BIAS_GELU, EPI_BIAS_RELU,
+                   EPI_DGELU, EPI_DRELU, EPI_NONE, ELT_ADD, ELT_COPY, ELT_DGELU, ELT_DRELU, ELT_DROPOUT, ELT_GELU,
+                   ELT_MUL, ELT_RELU)
+from .losses import pre_vis_targets
+from .store import ParamStore
+
+LN_EPS = 1e-12
+_ACT_EPI = {"gelu": (EPI_BIAS_GELU, EPI_DGELU)}
+
+# counters the benchmark reads: kernels launched through the C ABI in this process
+launch_count = 0
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class Pair:
+    """Hidden states of both streams.  `all` is the joint [Mt+Mv, H] buffer when the widths match."""
+
+    def __init__(self, t, v, joint=None):
+        self.t, self.v, self.all = t, v, joint
+
+    @staticmethod
+    def alloc(rt, Mt, Ht, Mv, Hv, dtype=None):
+        if Ht == Hv:
+            joint = rt.empty(Mt + Mv, Ht, dtype=dtype)
+            return Pair(joint[:Mt], joint[Mt:], joint)
+        return Pair(rt.empty(Mt, Ht, dtype=dtype), rt.empty(Mv, Hv, dtype=dtype), None)
+
+
+class Runtime:
+    """Per-call context: shapes, compute dtype, dropout seeds, parameter views."""
+
+    def __init__(self, model, device, B, T, V, training, grad=False):
+        self.model = model
+        self.store = model_store(model)
+        self.precision = self.store.model.precision
+        self.cdtype = torch.bfloat16 if self.precision == "bf16" else torch.float32
+        self.device = device
+        self.B, self.T, self.V = B, T, V
+        self.Mt, self.Mv = B * T, B * V
+        self.training = training
+        self.grad_enabled = grad  # autograd.Function.forward runs with grad mode off: the caller decides
+        self._seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0  # CPU generator: no device sync
+        self._site = 0
+        self.gemm_backend = {"auto": _lib.GEMM_AUTO, "tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT}[
+            os.environ.get("VOLTA_B200_GEMM", "auto")]
+        self.attn_backend = {"auto": _lib.ATTN_AUTO, "mma": _lib.ATTN_MMA, "simt": _lib.ATTN_SIMT}[
+            os.environ.get("VOLTA_B200_ATTN", "auto")]
+        if self.precision == "fp32":
+            self.gemm_backend, self.attn_backend = _lib.GEMM_SIMT, _lib.ATTN_SIMT
+        self.store.ensure(device, self.precision)
+
+    def empty(self, *shape, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.cdtype, device=self.device)
+
+    def zeros(self, *shape, dtype=None):
+        t = torch.empty(shape, dtype=dtype or self.cdtype, device=self.device)
+        nbytes = t.numel() * t.element_size()
+        if nbytes % 16 == 0 and t.data_ptr() % 16 == 0:
+            ops.fill(t, 0)
+            _count()
+        else:
+            t.zero_()
+        return t
+
+    def seed(self):
+        """A fresh Philox seed per dropout site (masks are regenerated in the backward, never stored)."""
+        self._site += 1
+        return (self._seed + 0x9E3779B97F4A7C15 * self._site) & 0x7FFFFFFFFFFFFFFF
+
+    def p(self, prob):
+        return float(prob) if self.training else 0.0
+
+    # parameter views
+    def cw(self, *ps):
+        return self.store.cw(*ps)
+
+    def w32(self, *ps):
+        return self.store.w32(*ps)
+
+    def g32(self, *ps):
+        return self.store.g32(*ps)
+
+    # kernels with launch accounting
+    def gemm(self, *a, **k):
+        _count()
+        k.setdefault("backend", self.gemm_backend)
+        return ops.gemm(*a, **k)
+
+
+def model_store(model):
+    parent = model.__dict__.get("_engine_parent") if hasattr(model, "__dict__") else None
+    if parent is not None and parent() is not None:
+        return model_store(parent())
+    st = getattr(model, "_engine_state", None)
+    if st is None:
+        st = ParamStore(model)
+        model._engine_state = st
+    return st
+
+
+# ====================================================================================================
+# building blocks (forward returns outputs + a `saved` record; backward consumes it)
+# ====================================================================================================
+def linear_fwd(rt, x, lin, epilogue=EPI_BIAS, out=None, **kw):
+    """y = x W^T + b through vb_gemm; W may be several stacked Linears (fused QKV)."""
+    lins = lin if isinstance(lin, (list, tuple)) else [lin]
+    W = rt.cw(*[l.weight for l in lins])
+    b = rt.w32(*[l.bias for l in lins]) if lins[0].bias is not None else None
+    rows = x.shape[0]
+    if out is None:
+        out = rt.empty(rows, W.shape[0])
+    if b is None and epilogue == EPI_BIAS:
+        epilogue = EPI_NONE
+    rt.gemm(x, W, out, epilogue=epilogue, bias=b, **kw)
+    return out
+
+
+def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, bias_done=False, **kw):
+    """dW += dy^T x (fp32, accumulated into the flat gradient buffer), db += colsum(dy), dx = dy W (+epilogue)."""
+    lins = lin if isinstance(lin, (list, tuple)) else [lin]
+    dW = rt.g32(*[l.weight for l in lins])
+    rt.gemm(dy, x, dW, a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)
+    if lins[0].bias is not None and not bias_done:
+        ops.colsum(dy, rt.g32(*[l.bias for l in lins]))
+        _count()
+    if not need_dx:
+        return None
+    W = rt.cw(*[l.weight for l in lins])
+    if dx_out is None:
+        dx_out = rt.empty(dy.shape[0], W.shape[1])
+    rt.gemm(dy, W, dx_out, a_kmajor=True, b_kmajor=False, epilogue=dx_epilogue, **kw)
+    return dx_out
+
+
+def ln_fwd(rt, x, ln, y=None, out_scale=1.0, accum=False, save=True):
+    y = rt.empty(*x.shape) if y is None else y
+    mean = rt.empty(x.shape[0], dtype=torch.float32) if save else None
+    rstd = rt.empty(x.shape[0], dtype=torch.float32) if save else None
+    ops.layernorm_fwd(x, rt.w32(ln.weight), rt.w32(ln.bias), y, mean, rstd, LN_EPS, out_scale, accum)
+    _count()
+    return y, (mean, rstd)
+
+
+def ln_bwd(rt, dy, x, stats, ln, out_scale=1.0, dx=None, dx_drop=None, p=0.0, seed=0, dbias=None):
+    dx = rt.empty(*x.shape) if dx is None else dx
+    ops.layernorm_bwd(dy, x, stats[0], stats[1], rt.w32(ln.weight), dx, rt.g32(ln.weight), rt.g32(ln.bias), out_scale,
+                      dx_drop, p, seed, 0, dbias)
+    _count()
+    return dx
+
+
+def dropout_(rt, x, p, seed):
+    """In-place inverted dropout (embedding / pooled-output sites); the same call is its own backward."""
+    if p > 0.0:
+        ops.eltwise(ELT_DROPOUT, x, x, p=p, seed=seed)
+        _count()
+    return x
+
+
+# ---- residual block tail:  u = dropout(dense(h)) + x ;  y = LN(u) -------------------------------------
+def out_block_fwd(rt, h, x, dense, ln, p, y):
+    seed = rt.seed() if p > 0 else 0
+    u = linear_fwd(rt, h, dense, epilogue=EPI_BIAS_DROP_RES, aux_in=x, dropout_p=p, seed=seed)
+    _, stats = ln_fwd(rt, u, ln, y=y)
+    return (h, u, stats, p, seed)
+
+
+def out_block_bwd(rt, dy, saved, dense, ln, dh_epilogue=EPI_NONE, dh_aux=None):
+    """Returns (du, dh): du is the gradient of the residual input, dh = dense-input gradient (+epilogue)."""
+    h, u, stats, p, seed = saved
+    du = rt.empty(*u.shape)
+    du_drop = rt.empty(*u.shape) if p > 0 else None
+    ln_bwd(rt, dy, u, stats, ln, dx=du, dx_drop=du_drop, p=p, seed=seed, dbias=rt.g32(dense.bias))
+    dz = du_drop if p > 0 else du
+    dh = linear_bwd(rt, h, dz, dense, dx_epilogue=dh_epilogue, bias_done=True, aux_in=dh_aux)
+    return du, dh
+
+
+# ====================================================================================================
+# encoder sub-layers
+# ====================================================================================================
+def _streams(sub_has_t, sub_has_v, shared, x):
+    """Yields (tag, rows-view selector) for the GEMM groups of a sub-layer."""
+    if sub_has_t and sub_has_v and shared and x.all is not None:
+        return ["all"]
+    return [s for s, on in (("t", sub_has_t), ("v", sub_has_v)) if on]
+
+
+def _grad_pair_like(rt, x):
+    """Gradient buffers for a sub-layer input: joint (one [Mt+Mv, H] buffer) whenever the input was joint,
+    because the producer of `x` may be a shared sub-layer that back-propagates over all rows at once."""
+    if x.all is not None:
+        return Pair.alloc(rt, x.t.shape[0], x.t.shape[1], x.v.shape[0], x.v.shape[1])
+    return Pair(None, None, None)
+
+
+def _pass_through(dy, dst):
+    """A stream a sub-layer does not touch passes its gradient through (copied only into a joint buffer)."""
+    if dst is None:
+        return dy
+    ops.eltwise(ELT_COPY, dy, dst)
+    _count()
+    return dst
+
+
+def attention_fwd(rt, layer, x, masks):
+    sa, so = layer.attention_self, layer.attention_output
+    groups = _streams(sa.has_text, sa.has_vision, sa.share_layer, x)
+    A_t, A_v = sa.all_head_size, sa.v_all_head_size
+    joint = groups == ["all"]
+    qkv, ctx = {}, {}
+    if joint:
+        q_all = linear_fwd(rt, x.all, [sa.query, sa.key, sa.value])
+        qkv["t"], qkv["v"] = q_all[:rt.Mt], q_all[rt.Mt:]
+        c_all = rt.empty(rt.Mt + rt.Mv, A_t)
+        ctx["t"], ctx["v"], ctx["all"] = c_all[:rt.Mt], c_all[rt.Mt:], c_all
+    else:
+        if sa.has_text:
+            qkv["t"] = linear_fwd(rt, x.t, [sa.query, sa.key, sa.value])
+            ctx["t"] = rt.empty(rt.Mt, A_t)
+        if sa.has_vision:
+            qkv["v"] = linear_fwd(rt, x.v, [sa.v_query, sa.v_key, sa.v_value])
+            ctx["v"] = rt.empty(rt.Mv, A_v)
+    heads = sa.num_attention_heads if sa.has_text else sa.v_num_attention_heads
+    d = sa.attention_head_size if sa.has_text else sa.v_attention_head_size
+    if sa.has_text and sa.has_vision and (sa.has_tv or sa.has_vt or joint):
+        assert sa.num_attention_heads == sa.v_num_attention_heads and sa.attention_head_size == sa.v_attention_head_size
+    lse_t = rt.empty(rt.B, heads, rt.T, dtype=torch.float32) if sa.has_text else None
+    lse_v = rt.empty(rt.B, sa.v_num_attention_heads, rt.V, dtype=torch.float32) if sa.has_vision else None
+    p_t, p_v = rt.p(sa.dropout.p) if sa.has_text else 0.0, rt.p(sa.v_dropout.p) if sa.has_vision else 0.0
+    seed = rt.seed() if (p_t > 0 or p_v > 0) else 0
+    cross = sa.has_tv or sa.has_vt
+    calls = []
+    if cross or joint or not (sa.has_text and sa.has_vision):
+        calls.append((sa.pair_mask, qkv.get("t"), qkv.get("v"), heads, d))
+    else:
+        # independent self-attentions (tt + vv): the streams may even differ in head size (vilbert_base)
+        calls.append((1, qkv["t"], None, sa.num_attention_heads, sa.attention_head_size))
+        calls.append((8, None, qkv["v"], sa.v_num_attention_heads, sa.v_attention_head_size))
+    for pm, qt, qv, h_, d_ in calls:
+        ops.attention_fwd(qt, qv, masks[0] if qt is not None else None, masks[1] if qv is not None else None,
+                          ctx.get("t") if qt is not None else None, ctx.get("v") if qv is not None else None,
+                          lse_t, lse_v, rt.B, rt.T, rt.V, h_, d_, pm, p_t, p_v, seed, rt.attn_backend)
+        _count()
+    y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1]) if (sa.has_text and sa.has_vision) else None
+    saved_out = {}
+    if joint:
+        saved_out["all"] = out_block_fwd(rt, ctx["all"], x.all, so.dense, so.LayerNorm, rt.p(so.dropout.p), y.all)
+    else:
+        if y is None:  # only one stream is touched: the other passes through unchanged (encoders.py:380-396)
+            y = Pair(rt.empty(*x.t.shape) if sa.has_text else x.t, rt.empty(*x.v.shape) if sa.has_vision else x.v, None)
+        if sa.has_text:
+            saved_out["t"] = out_block_fwd(rt, ctx["t"], x.t, so.dense, so.LayerNorm, rt.p(so.dropout.p), y.t)
+        if sa.has_vision:
+            saved_out["v"] = out_block_fwd(rt, ctx["v"], x.v, so.v_dense, so.v_LayerNorm, rt.p(so.v_dropout.p), y.v)
+    saved = dict(x=x, qkv=qkv, ctx=ctx, lse=(lse_t, lse_v), calls=calls, seed=seed, p=(p_t, p_v), out=saved_out,
+                 joint=joint, masks=masks)
+    return y, saved
+
+
+def attention_bwd(rt, layer, dy, s):
+    """dy: Pair of gradients w.r.t. the sub-layer outputs; returns the Pair w.r.t. its inputs."""
+    sa, so = layer.attention_self, layer.attention_output
+    x, qkv, ctx = s["x"], s["qkv"], s["ctx"]
+    du, dctx = {}, {}
+    if s["joint"]:
+        du_all, dc_all = out_block_bwd(rt, dy.all, s["out"]["all"], so.dense, so.LayerNorm)
+        du["all"], dctx["t"], dctx["v"] = du_all, dc_all[:rt.Mt], dc_all[rt.Mt:]
+    else:
+        if sa.has_text:
+            du["t"], dctx["t"] = out_block_bwd(rt, dy.t, s["out"]["t"], so.dense, so.LayerNorm)
+        if sa.has_vision:
+            du["v"], dctx["v"] = out_block_bwd(rt, dy.v, s["out"]["v"], so.v_dense, so.v_LayerNorm)
+    dqkv = {}
+    if s["joint"]:
+        dq_all = rt.empty(rt.Mt + rt.Mv, qkv["t"].shape[1])
+        dqkv["t"], dqkv["v"], dqkv["all"] = dq_all[:rt.Mt], dq_all[rt.Mt:], dq_all
+    else:
+        for k in qkv:
+            dqkv[k] = rt.empty(*qkv[k].shape)
+    lse_t, lse_v = s["lse"]
+    for pm, qt, qv, h_, d_ in s["calls"]:
+        ops.attention_bwd(qt, qv, s["masks"][0] if qt is not None else None, s["masks"][1] if qv is not None else None,
+                          ctx.get("t") if qt is not None else None, ctx.get("v") if qv is not None else None,
+                          lse_t, lse_v, rt.B, rt.T, rt.V, h_, d_, pm, s["p"][0], s["p"][1], s["seed"], rt.attn_backend,
+                          dctx_t=dctx.get("t") if qt is not None else None, dctx_v=dctx.get("v") if qv is not None else None,
+                          dqkv_t=dqkv.get("t") if qt is not None else None, dqkv_v=dqkv.get("v") if qv is not None else None)
+        _count()
+    # dx = dqkv . Wqkv + du   (the residual gradient is folded into the dgrad epilogue)
+    if s["joint"]:
+        dx_all = linear_bwd(rt, x.all, dqkv["all"], [sa.query, sa.key, sa.value], dx_epilogue=EPI_ADD, aux_in=du["all"])
+        return Pair(dx_all[:rt.Mt], dx_all[rt.Mt:], dx_all)
+    dx = _grad_pair_like(rt, x)
+    if sa.has_text:
+        dx.t = linear_bwd(rt, x.t, dqkv["t"], [sa.query, sa.key, sa.value], dx_epilogue=EPI_ADD, aux_in=du["t"], dx_out=dx.t)
+    else:
+        dx.t = _pass_through(dy.t, dx.t)
+    if sa.has_vision:
+        dx.v = linear_bwd(rt, x.v, dqkv["v"], [sa.v_query, sa.v_key, sa.v_value], dx_epilogue=EPI_ADD, aux_in=du["v"], dx_out=dx.v)
+    else:
+        dx.v = _pass_through(dy.v, dx.v)
+    return dx
+
+
+def _act_epilogues(name):
+    if name == "gelu":
+        return EPI_BIAS_GELU, EPI_DGELU
+    if name == "relu":
+        return EPI_BIAS_RELU, EPI_DRELU
+    raise NotImplementedError("hidden_act=%r: the shipped configs use 'gelu'; 'relu' is supported, 'swish' is not" % (name,))
+
+
+def _ffn_stream_fwd(rt, x, inter, dense2, ln, p, y, act):
+    epi_f, _ = _act_epilogues(act)
+    I = inter.weight.shape[0]
+    h = rt.empty(x.shape[0], I)
+    if epi_f == EPI_BIAS_GELU:
+        pre = rt.empty(x.shape[0], I)
+        linear_fwd(rt, x, inter, epilogue=EPI_BIAS_GELU, out=h, aux_out=pre)
+    else:
+        linear_fwd(rt, x, inter, epilogue=EPI_BIAS_RELU, out=h)
+        pre = h  # relu'(pre) = (h > 0)
+    return (x, pre, out_block_fwd(rt, h, x, dense2, ln, p, y))
+
+
+def _ffn_stream_bwd(rt, dy, saved, inter, dense2, ln, act, dx_out=None):
+    x, pre, out_saved = saved
+    _, epi_b = _act_epilogues(act)
+    du, dpre = out_block_bwd(rt, dy, out_saved, dense2, ln, dh_epilogue=epi_b, dh_aux=pre)
+    return linear_bwd(rt, x, dpre, inter, dx_epilogue=EPI_ADD, aux_in=du, dx_out=dx_out)
+
+
+def ffn_fwd(rt, layer, x):
+    it, out = layer.intermediate, layer.output
+    groups = _streams(it.has_language, it.has_vision, it.share_layer, x)
+    saved = {"x": x}
+    if groups == ["all"]:
+        y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
+        saved["all"] = _ffn_stream_fwd(rt, x.all, it.dense, out.dense, out.LayerNorm, rt.p(out.dropout.p), y.all, it.hidden_act)
+    else:
+        if it.has_language and it.has_vision:
+            y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
+        else:
+            y = Pair(rt.empty(*x.t.shape) if it.has_language else x.t, rt.empty(*x.v.shape) if it.has_vision else x.v, None)
+        if it.has_language:
+            saved["t"] = _ffn_stream_fwd(rt, x.t, it.dense, out.dense, out.LayerNorm, rt.p(out.dropout.p), y.t, it.hidden_act)
+        if it.has_vision:
+            saved["v"] = _ffn_stream_fwd(rt, x.v, it.v_dense, out.v_dense, out.v_LayerNorm, rt.p(out.v_dropout.p), y.v, it.v_hidden_act)
+    return y, saved
+
+
+def ffn_bwd(rt, layer, dy, saved):
+    it, out = layer.intermediate, layer.output
+    if "all" in saved:
+        dx = _ffn_stream_bwd(rt, dy.all, saved["all"], it.dense, out.dense, out.LayerNorm, it.hidden_act)
+        return Pair(dx[:rt.Mt], dx[rt.Mt:], dx)
+    dx = _grad_pair_like(rt, saved["x"])
+    if "t" in saved:
+        dx.t = _ffn_stream_bwd(rt, dy.t, saved["t"], it.dense, out.dense, out.LayerNorm, it.hidden_act, dx.t)
+    else:
+        dx.t = _pass_through(dy.t, dx.t)
+    if "v" in saved:
+        dx.v = _ffn_stream_bwd(rt, dy.v, saved["v"], it.v_dense, out.v_dense, out.v_LayerNorm, it.v_hidden_act, dx.v)
+    else:
+        dx.v = _pass_through(dy.v, dx.v)
+    return dx
+
+
+# ====================================================================================================
+# embeddings
+# ====================================================================================================
+_POS_CACHE = {}
+
+
+def _pos_ids(rt, offset=0):
+    key = (rt.device, rt.B, rt.T, offset)
+    if key not in _POS_CACHE:
+        _POS_CACHE[key] = (torch.arange(offset, rt.T + offset, dtype=torch.int64).repeat(rt.B)).to(rt.device)
+    return _POS_CACHE[key]
+
+
+def _to_compute(rt, feat):
+    """Region features arrive fp32 from the loader; the GEMM operand is the compute dtype."""
+    feat = feat.reshape(-1, feat.shape[-1])
+    if feat.dtype == rt.cdtype:
+        return feat
+    out = rt.empty(*feat.shape)
+    ops.eltwise(ELT_COPY, feat, out)
+    _count()
+    return out
+
+
+def _text_gather(rt, emb, ids, seg, out, pos_offset=0):
+    idx = [ids.reshape(-1), _pos_ids(rt, pos_offset), seg.reshape(-1)]
+    tables = [emb.word_embeddings.weight, emb.position_embeddings.weight, emb.token_type_embeddings.weight]
+    ops.embed_gather_fwd([rt.w32(t) for t in tables], idx, [0, 0, 0], out)
+    _count()
+    return (tables, idx)
+
+
+def _text_gather_bwd(rt, saved, dout):
+    tables, idx = saved
+    ops.embed_gather_bwd([rt.g32(t) for t in tables], idx, [0] * len(tables), dout)
+    _count()
+
+
+def _region_proj_fwd(rt, lin, feat_c, out):
+    linear_fwd(rt, feat_c, lin, epilogue=EPI_BIAS, out=out)
+
+
+def _box_fwd(rt, lin, loc, out, accum):
+    ops.box_project_fwd(loc, rt.w32(lin.weight), rt.w32(lin.bias), out, accum)
+    _count()
+
+
+def _box_bwd(rt, lin, loc, dout):
+    ops.box_project_bwd(loc, dout, rt.g32(lin.weight), rt.g32(lin.bias))
+    _count()
+
+
+def embeddings_fwd(rt, bert, ids, feat, loc, seg):
+    cfg = bert.config
+    kind = cfg.image_embeddings
+    H, Hv = cfg.hidden_size, cfg.v_hidden_size
+    x = Pair.alloc(rt, rt.Mt, H, rt.Mv, Hv)
+    feat_c = _to_compute(rt, feat)
+    loc2 = loc.reshape(-1, loc.shape[-1]).contiguous().float()
+    pos_off = bert.embeddings.padding_idx + 1 if hasattr(bert.embeddings, "padding_idx") and not bert.shared_embeddings else 0
+    s = dict(kind=kind, feat=feat_c, loc=loc2)
+    if kind in ("vilbert", "lxmert"):
+        e, ve = bert.embeddings, bert.v_embeddings
+        st = rt.empty(rt.Mt, H)
+        s["text"] = _text_gather(rt, e, ids, seg, st, pos_off)
+        _, s["t_stats"] = ln_fwd(rt, st, e.LayerNorm, y=x.t)
+        s["t_sum"] = st
+        s["t_drop"] = (rt.p(e.dropout.p), rt.seed())
+        dropout_(rt, x.t, *s["t_drop"])
+        a = rt.empty(rt.Mv, Hv)
+        _region_proj_fwd(rt, ve.image_embeddings, feat_c, a)
+        if kind == "vilbert":
+            _box_fwd(rt, ve.image_location_embeddings, loc2, a, True)
+            _, s["v_stats"] = ln_fwd(rt, a, ve.LayerNorm, y=x.v)
+            s["v_sum"] = a
+        else:
+            l = rt.empty(rt.Mv, Hv)
+            _box_fwd(rt, ve.image_location_embeddings, loc2, l, False)
+            _, s["img_stats"] = ln_fwd(rt, a, ve.ImgLayerNorm, y=x.v, out_scale=0.5)
+            _, s["loc_stats"] = ln_fwd(rt, l, ve.LocLayerNorm, y=x.v, out_scale=0.5, accum=True)
+            s["img_sum"], s["loc_sum"] = a, l
+        s["v_drop"] = (rt.p(ve.dropout.p), rt.seed())
+        dropout_(rt, x.v, *s["v_drop"])
+    elif kind == "visualbert":
+        e = bert.embeddings
+        assert x.all is not None
+        u = Pair.alloc(rt, rt.Mt, H, rt.Mv, Hv)
+        s["text"] = _text_gather(rt, e, ids, seg, u.t)
+        _region_proj_fwd(rt, e.projection, feat_c, u.v)
+        vt = [e.position_embeddings_visual.weight, e.token_type_embeddings_visual.weight]
+        ops.embed_gather_fwd([rt.w32(t) for t in vt], [None, None], [0, 1], u.v, accum=True)
+        _count()
+        s["v_tables"] = vt
+        _, s["stats"] = ln_fwd(rt, u.all, e.LayerNorm, y=x.all)
+        s["sum"] = u
+        s["drop"] = (rt.p(e.dropout.p), rt.seed())
+        dropout_(rt, x.all, *s["drop"])
+    elif kind == "uniter":
+        e = bert.embeddings
+        st = rt.empty(rt.Mt, H)
+        s["text"] = _text_gather(rt, e, ids, seg, st)
+        _, s["t_stats"] = ln_fwd(rt, st, e.LayerNorm, y=x.t)
+        s["t_sum"] = st
+        s["t_drop"] = (rt.p(e.dropout.p), rt.seed())
+        dropout_(rt, x.t, *s["t_drop"])
+        a, l, z = rt.empty(rt.Mv, Hv), rt.empty(rt.Mv, Hv), rt.empty(rt.Mv, Hv)
+        _region_proj_fwd(rt, e.image_embeddings, feat_c, a)
+        _box_fwd(rt, e.image_location_embeddings, loc2, l, False)
+        _, s["img_stats"] = ln_fwd(rt, a, e.image_layer_norm, y=z)
+        _, s["loc_stats"] = ln_fwd(rt, l, e.image_location_layer_norm, y=z, accum=True)
+        ops.embed_gather_fwd([rt.w32(e.token_type_embeddings.weight)], [None], [1], z, accum=True)
+        _count()
+        _, s["v_stats"] = ln_fwd(rt, z, e.v_LayerNorm, y=x.v)
+        s["img_sum"], s["loc_sum"], s["v_sum"] = a, l, z
+        s["v_drop"] = (rt.p(e.v_dropout.p), rt.seed())
+        dropout_(rt, x.v, *s["v_drop"])
+    elif kind == "vl-bert":
+        from .vlbert import vlbert_embeddings_fwd
+        vlbert_embeddings_fwd(rt, bert, ids, feat, loc2, seg, x, s)
+    else:
+        raise ValueError("unknown image_embeddings %r" % kind)
+    return x, s
+
+
+def embeddings_bwd(rt, bert, dx, s):
+    kind = s["kind"]
+    feat_c, loc2 = s["feat"], s["loc"]
+    if kind in ("vilbert", "lxmert"):
+        e, ve = bert.embeddings, bert.v_embeddings
+        dropout_(rt, dx.t, *s["t_drop"])
+        ds = ln_bwd(rt, dx.t, s["t_sum"], s["t_stats"], e.LayerNorm)
+        _text_gather_bwd(rt, s["text"], ds)
+        dropout_(rt, dx.v, *s["v_drop"])
+        if kind == "vilbert":
+            da = ln_bwd(rt, dx.v, s["v_sum"], s["v_stats"], ve.LayerNorm, dbias=rt.g32(ve.image_embeddings.bias))
+            _box_bwd(rt, ve.image_location_embeddings, loc2, da)
+        else:
+            da = ln_bwd(rt, dx.v, s["img_sum"], s["img_stats"], ve.ImgLayerNorm, out_scale=0.5,
+                        dbias=rt.g32(ve.image_embeddings.bias))
+            dl = ln_bwd(rt, dx.v, s["loc_sum"], s["loc_stats"], ve.LocLayerNorm, out_scale=0.5)
+            _box_bwd(rt, ve.image_location_embeddings, loc2, dl)
+        linear_bwd(rt, feat_c, da, ve.image_embeddings, need_dx=False, bias_done=True)
+    elif kind == "visualbert":
+        e = bert.embeddings
+        dropout_(rt, dx.all, *s["drop"])
+        du = ln_bwd(rt, dx.all, s["sum"].all, s["stats"], e.LayerNorm)
+        _text_gather_bwd(rt, s["text"], du[:rt.Mt])
+        dv = du[rt.Mt:]
+        linear_bwd(rt, feat_c, dv, e.projection, need_dx=False)
+        ops.colsum(dv, rt.g32(e.position_embeddings_visual.weight)[0])
+        ops.colsum(dv, rt.g32(e.token_type_embeddings_visual.weight)[1])
+        _count(2)
+    elif kind == "uniter":
+        e = bert.embeddings
+        dropout_(rt, dx.t, *s["t_drop"])
+        ds = ln_bwd(rt, dx.t, s["t_sum"], s["t_stats"], e.LayerNorm)
+        _text_gather_bwd(rt, s["text"], ds)
+        dropout_(rt, dx.v, *s["v_drop"])
+        dz = ln_bwd(rt, dx.v, s["v_sum"], s["v_stats"], e.v_LayerNorm)
+        ops.colsum(dz, rt.g32(e.token_type_embeddings.weight)[1])
+        _count()
+        da = ln_bwd(rt, dz, s["img_sum"], s["img_stats"], e.image_layer_norm, dbias=rt.g32(e.image_embeddings.bias))
+        dl = ln_bwd(rt, dz, s["loc_sum"], s["loc_stats"], e.image_location_layer_norm)
+        _box_bwd(rt, e.image_location_embeddings, loc2, dl)
+        linear_bwd(rt, feat_c, da, e.image_embeddings, need_dx=False, bias_done=True)
+    elif kind == "vl-bert":
+        from .vlbert import vlbert_embeddings_bwd
+        vlbert_embeddings_bwd(rt, bert, dx, s)
+
+
+# ====================================================================================================
+# BertModel: embeddings -> encoder -> poolers
+# ====================================================================================================
+def _int_mask(rt, mask, B, L):
+    if mask is None:
+        return torch.ones(B, L, dtype=torch.int32, device=rt.device)
+    return mask.reshape(B, L).to(device=rt.device, dtype=torch.int32).contiguous()
+
+
+def _pool_fwd(rt, pooler, x, L, rows=None):
+    """relu(W x[:, 0] + b): the [CLS] / global rows are read in place through the leading dimension."""
+    H = x.shape[1]
+    a = x.view(rt.B, L * H)[:, :H] if rows is None else rows
+    out = rt.empty(rt.B, pooler.dense.weight.shape[0])
+    linear_fwd(rt, a, pooler.dense, epilogue=EPI_BIAS_RELU, out=out)
+    return out, a
+
+
+def _pool_bwd(rt, pooler, dpooled, pooled, a, dx, L):
+    """dx[:, 0] += (dpooled * (pooled > 0)) W, in place through the leading dimension."""
+    dpre = rt.empty(*pooled.shape)
+    ops.eltwise(ELT_DRELU, dpooled, dpre, b=pooled)
+    _count()
+    H = dx.shape[1]
+    rows0 = dx.view(rt.B, L * H)[:, :H]
+    linear_bwd(rt, a, dpre, pooler.dense, dx_epilogue=EPI_ADD, dx_out=rows0, aux_in=rows0)
+
+
+def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
+    cfg = bert.config
+    x, s_emb = embeddings_fwd(rt, bert, ids, feat, loc, seg)
+    masks = (_int_mask(rt, mask_t, rt.B, rt.T), _int_mask(rt, mask_v, rt.B, rt.V))
+    tape, layers = [], []
+    for n, layer in enumerate(bert.encoder.layer):
+        if bert.encoder.num2type[n] == "attn":
+            x, saved = attention_fwd(rt, layer, x, masks)
+        else:
+            x, saved = ffn_fwd(rt, layer, x)
+        tape.append(saved if rt.grad_enabled else None)
+        if keep_layers:
+            layers.append(x)
+    pooled_t = pooled_v = None
+    s_pool = {}
+    fm = cfg.fusion_method
+    if fm == "vl-bert_vqa":
+        end = ((ids != 0).sum(1) - 2).clamp(min=0) + torch.arange(rt.B, device=rt.device) * rt.T
+        rows = rt.empty(rt.B, x.t.shape[1])
+        ops.gather_rows(x.t, end, rows)
+        _count()
+        pooled_t, a = _pool_fwd(rt, bert.t_pooler, x.t, rt.T, rows=rows)
+        s_pool["t"] = (pooled_t, a, end)
+    elif fm != "none":
+        pooled_t, a = _pool_fwd(rt, bert.t_pooler, x.t, rt.T)
+        s_pool["t"] = (pooled_t, a, None)
+    if fm not in ("none", "text", "vl-bert_vqa"):
+        pooled_v, a = _pool_fwd(rt, bert.v_pooler, x.v, rt.V)
+        s_pool["v"] = (pooled_v, a, None)
+    return x, pooled_t, pooled_v, layers, dict(emb=s_emb, tape=tape, pool=s_pool, x=x)
+
+
+def bert_bwd(rt, bert, s, dx, dpooled_t, dpooled_v):
+    """dx: Pair of gradients w.r.t. the final hidden states (modified in place)."""
+    if dpooled_t is not None and "t" in s["pool"]:
+        pooled, a, end = s["pool"]["t"]
+        if end is None:
+            _pool_bwd(rt, bert.t_pooler, dpooled_t, pooled, a, dx.t, rt.T)
+        else:
+            dpre = rt.empty(*pooled.shape)
+            ops.eltwise(ELT_DRELU, dpooled_t, dpre, b=pooled)
+            drows = linear_bwd(rt, a, dpre, bert.t_pooler.dense)
+            ops.scatter_rows_add(drows, end, dx.t)
+            _count(2)
+    if dpooled_v is not None and "v" in s["pool"]:
+        pooled, a, _ = s["pool"]["v"]
+        _pool_bwd(rt, bert.v_pooler, dpooled_v, pooled, a, dx.v, rt.V)
+    for n in range(len(bert.encoder.layer) - 1, -1, -1):
+        layer = bert.encoder.layer[n]
+        if bert.encoder.num2type[n] == "attn":
+            dx = attention_bwd(rt, layer, dx, s["tape"][n])
+        else:
+            dx = ffn_bwd(rt, layer, dx, s["tape"][n])
+        s["tape"][n] = None  # free activations as the backward retires them
+    embeddings_bwd(rt, bert, dx, s["emb"])
+
+
+# ====================================================================================================
+# pre-training heads + losses
+# ====================================================================================================
+def _transform_fwd(rt, tr, x, has_ln=True):
+    epi_f, _ = _act_epilogues(tr.hidden_act)
+    H = tr.dense.weight.shape[0]
+    h, pre = rt.empty(x.shape[0], H), rt.empty(x.shape[0], H)
+    if epi_f == EPI_BIAS_GELU:
+        linear_fwd(rt, x, tr.dense, epilogue=EPI_BIAS_GELU, out=h, aux_out=pre)
+    else:
+        linear_fwd(rt, x, tr.dense, epilogue=EPI_BIAS_RELU, out=h)
+        pre = h
+    if not has_ln:
+        return h, (x, pre, h, None)
+    y, stats = ln_fwd(rt, h, tr.LayerNorm)
+    return y, (x, pre, h, stats)
+
+
+def _transform_bwd(rt, tr, dy, saved, dx_out, accumulate_dx=False):
+    x, pre, h, stats = saved
+    _, epi_b = _act_epilogues(tr.hidden_act)
+    dh = ln_bwd(rt, dy, h, stats, tr.LayerNorm) if stats is not None else dy
+    dpre = rt.empty(*dh.shape)
+    ops.eltwise(ELT_DGELU if epi_b == EPI_DGELU else ELT_DRELU, dh, dpre, b=pre)
+    _count()
+    if accumulate_dx:
+        linear_bwd(rt, x, dpre, tr.dense, dx_epilogue=EPI_ADD, dx_out=dx_out, aux_in=dx_out)
+    else:
+        linear_bwd(rt, x, dpre, tr.dense, dx_out=dx_out)
+
+
+def heads_fwd(rt, model, x, pooled_t, pooled_v, labels, want_logits=False):
+    """BertPreTrainingHeads + the three criteria (reference: volta/encoders.py:766-784, 1079-1109)."""
+    cfg, cls = model.config, model.cls
+    s = {}
+    V_, C_ = cfg.vocab_size, None
+    # --- MLM: transform -> tied decoder
+    hn, s["mlm_tr"] = _transform_fwd(rt, cls.predictions.transform, x.t)
+    E = rt.cw(cls.predictions.decoder.weight)
+    ldv = _pad8(V_)
+    mlm_logits = rt.empty(rt.Mt, ldv)
+    rt.gemm(hn, E, mlm_logits, epilogue=EPI_BIAS, bias=rt.w32(cls.predictions.bias), N=V_)
+    s["mlm"] = (hn, mlm_logits)
+    # --- ITM
+    itm_logits, pooled = None, None
+    fm = cfg.fusion_method
+    if fm != "none":
+        if fm in ("sum", "mul"):
+            pooled = rt.empty(*pooled_t.shape)
+            ops.eltwise(ELT_ADD if fm == "sum" else ELT_MUL, pooled_t, pooled, b=pooled_v)
+            _count()
+        elif fm in ("text", "vl-bert_vqa"):
+            pooled = rt.empty(*pooled_t.shape)
+            ops.eltwise(ELT_COPY, pooled_t, pooled)
+            _count()
+        else:
+            raise AssertionError("unknown fusion_method %r" % fm)
+        s["pool_drop"] = (rt.p(cls.dropout.p), rt.seed())
+        dropout_(rt, pooled, *s["pool_drop"])
+        if cls.has_itm:
+            itm_logits = rt.empty(rt.B, 8)[:, :2]
+            linear_fwd(rt, pooled, cls.bi_seq_relationship, out=itm_logits)
+        s["itm"] = (pooled, itm_logits, pooled_t, pooled_v)
+    # --- MRM
+    ip = cls.imagePredictions
+    hv, s["img_tr"] = _transform_fwd(rt, ip.transform, x.v, has_ln=ip.transform.has_ln)
+    img_logits = {}
+    for ix, dec in ip.decoder_dict.items():
+        n_cls = dec.weight.shape[0]
+        lg = rt.empty(rt.Mv, _pad8(n_cls))
+        linear_fwd(rt, hv, dec, out=lg, N=n_cls)
+        img_logits[ix] = lg
+    s["img"] = (hv, img_logits)
+    # --- criteria
+    sums = rt.zeros(8, dtype=torch.float32)  # [sum_mlm, sum_img, sum_itm, -, cnt_mlm, cnt_img, cnt_itm, -]
+    losses = rt.empty(4, dtype=torch.float32)
+    s["sums"] = sums
+    if labels.get("mlm") is not None:
+        lab = labels["mlm"].reshape(-1).to(torch.int64).contiguous()
+        lse = rt.empty(rt.Mt, dtype=torch.float32)
+        ops.xent_fwd(mlm_logits, lab, V_, lse, sums[0:1], sums[4:5])
+        _count()
+        s["mlm_loss"] = (lab, lse)
+    if labels.get("image_label") is not None:
+        for ix, w in cfg.visual_target_weights.items():
+            if w <= 0:
+                continue
+            if ix != "0":
+                raise NotImplementedError("visual target %s (%s) has no device criterion yet; the shipped ctrl_* "
+                                          "configs use target '0' (kl_1601)" % (ix, ix))
+            if labels.get("image_cls") is None:
+                continue
+            per = labels["image_label"].shape[1]
+            skip = 0 if cfg.add_global_imgfeat != "first" else 1
+            lab = labels["image_label"].reshape(-1).to(torch.int64).contiguous()
+            tgt = labels["image_cls"].reshape(-1, labels["image_cls"].shape[-1]).float().contiguous()
+            lse = rt.empty(lab.numel(), dtype=torch.float32)
+            ops.kl_fwd(img_logits[ix], per, rt.V, skip, lab, tgt, pre_vis_targets[ix], w, lse, sums[1:2], sums[5:6])
+            _count()
+            s["img_loss"] = (ix, per, skip, lab, tgt, w, lse)
+    if labels.get("itm") is not None and itm_logits is not None:
+        lab = labels["itm"].reshape(-1).to(torch.int64).contiguous()
+        lse = rt.empty(rt.B, dtype=torch.float32)
+        ops.xent_fwd(itm_logits, lab, 2, lse, sums[2:3], sums[6:7])
+        _count()
+        s["itm_loss"] = (lab, lse)
+    ops.loss_finalize(sums[0:4], sums[4:8], losses)
+    _count()
+    return losses, (mlm_logits, img_logits, itm_logits, pooled), s
+
+
+def heads_bwd(rt, model, s, dlosses, x):
+    """dlosses: fp32 [4] device tensor of upstream gradients (mlm, img, itm).  Returns (dx Pair, dpooled_t, dpooled_v)."""
+    cfg, cls = model.config, model.cls
+    sums = s["sums"]
+    dx = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
+    # --- MLM
+    hn, mlm_logits = s["mlm"]
+    if "mlm_loss" in s:
+        lab, lse = s["mlm_loss"]
+        ops.xent_bwd(mlm_logits, lab, cfg.vocab_size, lse, sums[4:5], dlosses[0:1], mlm_logits)  # in place
+        _count()
+        dlog = mlm_logits[:, :cfg.vocab_size]
+        E = cls.predictions.decoder
+        rt.gemm(dlog, hn, rt.g32(E.weight), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)
+        ops.colsum(dlog, rt.g32(cls.predictions.bias))
+        _count()
+        dhn = rt.empty(*hn.shape)
+        rt.gemm(dlog, rt.cw(E.weight), dhn, a_kmajor=True, b_kmajor=False)
+        _transform_bwd(rt, cls.predictions.transform, dhn, s["mlm_tr"], dx.t)
+    else:
+        ops.fill(dx.t, 0)
+    # --- MRM
+    hv, img_logits = s["img"]
+    if "img_loss" in s:
+        ix, per, skip, lab, tgt, w, lse = s["img_loss"]
+        lg = img_logits[ix]
+        n_cls = pre_vis_targets[ix]
+        ops.kl_bwd(lg, per, rt.V, skip, lab, tgt, n_cls, w, lse, sums[5:6], dlosses[1:2], lg)  # in place
+        _count()
+        dec = cls.imagePredictions.decoder_dict[ix]
+        dhv = linear_bwd(rt, hv, lg[:, :n_cls], dec)
+        _transform_bwd(rt, cls.imagePredictions.transform, dhv, s["img_tr"], dx.v)
+    else:
+        ops.fill(dx.v, 0)
+    # --- ITM
+    dpt = dpv = None
+    if "itm_loss" in s:
+        pooled, itm_logits, pooled_t, pooled_v = s["itm"]
+        lab, lse = s["itm_loss"]
+        ops.xent_bwd(itm_logits, lab, 2, lse, sums[6:7], dlosses[2:3], itm_logits)
+        _count()
+        dpooled = linear_bwd(rt, pooled, itm_logits, cls.bi_seq_relationship)
+        dropout_(rt, dpooled, *s["pool_drop"])
+        fm = cfg.fusion_method
+        if fm == "mul":
+            dpt, dpv = rt.empty(*dpooled.shape), rt.empty(*dpooled.shape)
+            ops.eltwise(ELT_MUL, dpooled, dpt, b=pooled_v)
+            ops.eltwise(ELT_MUL, dpooled, dpv, b=pooled_t)
+            _count(2)
+        elif fm == "sum":
+            dpt = dpv = dpooled
+        else:
+            dpt = dpooled
+    return dx, dpt, dpv
+
+
+# ====================================================================================================
+# autograd boundary
+# ====================================================================================================
+def _anchor(model):
+    for p in model.parameters():
+        if p.requires_grad:
+            return p
+    return None
+
+
+def _check_inputs(input_txt, input_imgs, image_loc):
+    ops.require_cuda(input_txt, input_imgs, image_loc)
+    if input_txt.dim() != 2 or input_imgs.dim() != 3 or image_loc.dim() != 3:
+        raise ValueError("expected input_txt [B,T], input_imgs [B,V,F], image_loc [B,V,num_locs]")
+    _lib.check(_lib.load().vb_device_check(), "vb_device_check")
+
+
+class _PretrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, model, args):
+        (ids, feat, loc, seg, mask_t, mask_v, mlm_labels, image_label, image_cls, itm_label) = args
+        B, T = ids.shape
+        V = feat.shape[1]
+        rt = Runtime(model, ids.device, B, T, V, model.training, grad=anchor is not None)
+        seg = torch.zeros_like(ids) if seg is None else seg
+        x, pt, pv, _, s_bert = bert_fwd(rt, model.bert, ids.contiguous(), feat.contiguous(), loc, seg.contiguous(), mask_t, mask_v)
+        labels = dict(mlm=mlm_labels, image_label=image_label, image_cls=image_cls, itm=itm_label)
+        losses, logits, s_heads = heads_fwd(rt, model, x, pt, pv, labels)
+        ctx.rt, ctx.model, ctx.s_bert, ctx.s_heads, ctx.x = rt, model, s_bert, s_heads, x
+        ctx.logits = logits
+        return losses[0:1], losses[1:2], losses[2:3]
+
+    @staticmethod
+    def backward(ctx, g_mlm, g_img, g_itm):
+        rt, model = ctx.rt, ctx.model
+        rt.store.prepare_grads()
+        dl = rt.zeros(4, dtype=torch.float32)
+        for i, g in enumerate((g_mlm, g_img, g_itm)):
+            if g is not None:
+                ops.eltwise(ELT_COPY, g.reshape(1, 1).float(), dl[i:i + 1].view(1, 1))
+                _count()
+        dx, dpt, dpv = heads_bwd(rt, model, ctx.s_heads, dl, ctx.x)
+        bert_bwd(rt, model.bert, ctx.s_bert, dx, dpt, dpv)
+        _notify_grads_ready(model)
+        ctx.s_bert = ctx.s_heads = ctx.x = ctx.logits = None
+        return None, None, None
+
+
+_GRAD_HOOKS = {}
+
+
+def register_grad_ready_hook(model, fn):
+    """Called once per backward after all parameter gradients are written (used by the data-parallel wrapper)."""
+    _GRAD_HOOKS[id(model)] = fn
+
+
+def _notify_grads_ready(model):
+    fn = _GRAD_HOOKS.get(id(model))
+    if fn is not None:
+        fn()
+
+
+def pretraining_forward(model, input_ids, image_feat, image_loc, token_type_ids, attention_mask, image_attention_mask,
+                        masked_lm_labels, image_label, image_cls, obj_labels, obj_confs, attr_labels, attr_confs,
+                        image_attrs, next_sentence_label, output_all_attention_masks):
+    _check_inputs(input_ids, image_feat, image_loc)
+    if output_all_attention_masks:
+        raise NotImplementedError("attention probabilities are never materialised on this path "
+                                  "(output_all_attention_masks / config.visualization)")
+    args = (input_ids, image_feat, image_loc, token_type_ids, attention_mask, image_attention_mask, masked_lm_labels,
+            image_label, image_cls, next_sentence_label)
+    no_labels = masked_lm_labels is None and image_label is None and next_sentence_label is None
+    if no_labels:
+        with torch.no_grad():
+            B, T = input_ids.shape
+            rt = Runtime(model, input_ids.device, B, T, image_feat.shape[1], model.training)
+            seg = torch.zeros_like(input_ids) if token_type_ids is None else token_type_ids
+            x, pt, pv, _, _ = bert_fwd(rt, model.bert, input_ids.contiguous(), image_feat.contiguous(), image_loc,
+                                       seg.contiguous(), attention_mask, image_attention_mask)
+            _, (mlm, img, itm, pooled), _ = heads_fwd(rt, model, x, pt, pv, {})
+        V_ = model.config.vocab_size
+        img = {ix: v.view(B, -1, v.shape[-1])[..., :pre_vis_targets[ix]].float() for ix, v in img.items()}
+        return (mlm.view(B, T, -1)[..., :V_].float(), img, None if itm is None else itm.float(), None,
+                None if pooled is None else pooled.float())
+    anchor = _anchor(model) if torch.is_grad_enabled() else None
+    if anchor is None:
+        with torch.no_grad():
+            return _PretrainFn.apply(None, model, args)
+    return _PretrainFn.apply(anchor, model, args)
+
+
+class _BertFn(torch.autograd.Function):
+    """BertModel alone: differentiable w.r.t. parameters through (seq_t, seq_v, pooled_t, pooled_v)."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, args, keep_layers):
+        ids, feat, loc, seg, mask_t, mask_v = args
+        B, T = ids.shape
+        rt = Runtime(model, ids.device, B, T, feat.shape[1], model.training, grad=anchor is not None)
+        seg = torch.zeros_like(ids) if seg is None else seg
+        x, pt, pv, layers, s = bert_fwd(rt, model, ids.contiguous(), feat.contiguous(), loc, seg.contiguous(), mask_t, mask_v,
+                                        keep_layers=keep_layers)
+        ctx.rt, ctx.model, ctx.s = rt, model, s
+        ctx.n_layers = len(layers)
+        outs = [x.t.view(B, T, -1), x.v.view(B, rt.V, -1)]
+        dummy = rt.empty(1)
+        outs += [pt if pt is not None else dummy, pv if pv is not None else dummy]
+        ctx.has_pool = (pt is not None, pv is not None)
+        for l in layers:
+            outs += [l.t.view(B, T, -1), l.v.view(B, rt.V, -1)]
+        ctx.mark_non_differentiable(*outs[4:])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_t, g_v, g_pt, g_pv, *rest):
+        rt, model, s = ctx.rt, ctx.model, ctx.s
+        rt.store.prepare_grads()
+        x = s["x"]
+        dx = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
+        for g, d in ((g_t, dx.t), (g_v, dx.v)):
+            if g is None:
+                ops.fill(d, 0)
+            else:
+                ops.eltwise(ELT_COPY, g.reshape(d.shape).contiguous(), d)
+            _count()
+
+        def conv(g, on):
+            if g is None or not on:
+                return None
+            out = rt.empty(*g.shape)
+            ops.eltwise(ELT_COPY, g.contiguous(), out)
+            return out
+        bert_bwd(rt, model, s, dx, conv(g_pt, ctx.has_pool[0]), conv(g_pv, ctx.has_pool[1]))
+        _notify_grads_ready(model)
+        ctx.s = None
+        return None, None, None, None
+
+
+def _run_bert(model, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, keep_layers):
+    _check_inputs(input_txt, input_imgs, image_loc)
+    args = (input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask)
+    anchor = _anchor(model) if torch.is_grad_enabled() else None
+    if anchor is None:
+        with torch.no_grad():
+            outs = _BertFn.apply(None, model, args, keep_layers)
+    else:
+        outs = _BertFn.apply(anchor, model, args, keep_layers)
+    cfg = model.config
+    seq_t, seq_v = outs[0], outs[1]
+    pt = outs[2] if cfg.fusion_method != "none" else None
+    pv = outs[3] if cfg.fusion_method not in ("none", "text", "vl-bert_vqa") else None
+    layers = outs[4:]
+    return seq_t, seq_v, pt, pv, layers
+
+
+def bert_model_forward(model, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask,
+                       output_all_encoded_layers, output_all_attention_masks):
+    """BertModel.forward contract (reference: volta/encoders.py:954-1017).  Hidden states come back in the
+    compute dtype (bf16 unless the fp32 validation mode is on)."""
+    if output_all_attention_masks:
+        raise NotImplementedError("attention probabilities are never materialised on this path")
+    seq_t, seq_v, pt, pv, layers = _run_bert(model, input_txt, input_imgs, image_loc, token_type_ids, attention_mask,
+                                             image_attention_mask, output_all_encoded_layers)
+    if output_all_encoded_layers:
+        return list(layers[0::2]), list(layers[1::2]), pt, pv, ([], [])
+    return seq_t, seq_v, pt, pv, ([], [])
+
+
+# ====================================================================================================
+# small differentiable ops for the task heads (thin autograd.Functions over single kernels)
+# ====================================================================================================
+def _cd(model_or_dtype):
+    return model_or_dtype
+
+
+class LayerNormFn(torch.autograd.Function):
+    """Stand-alone LayerNorm on a CUDA tensor - the reference-facing replacement of apex
+    `fused_layer_norm_cuda.forward_affine/backward_affine` (apex/apex/normalization/fused_layer_norm.py:12-37)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        ops.require_cuda(x, weight, bias)
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        rows = xc.numel() // xc.shape[-1]
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        w32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        ops.layernorm_fwd(xc, w32, b32, y, mean, rstd, eps)
+        _count()
+        ctx.save_for_backward(xc, mean, rstd, w32)
+        ctx.wdtype = weight.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, mean, rstd, w32 = ctx.saved_tensors
+        dx = torch.empty_like(xc)
+        dg = torch.zeros_like(w32)
+        db = torch.zeros_like(w32)
+        ops.layernorm_bwd(dy.contiguous().to(xc.dtype), xc, mean, rstd, w32, dx, dg, db)
+        _count()
+        return dx, dg.to(ctx.wdtype), db.to(ctx.wdtype), None
+
+
+class GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ops.require_cuda(x)
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        ops.eltwise(ELT_GELU, xc, y)
+        _count()
+        ctx.save_for_backward(xc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        dx = torch.empty_like(xc)
+        ops.eltwise(ELT_DGELU, dy.contiguous(), dx, b=xc)
+        _count()
+        return dx
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x W^T + b) for the small task heads; weights are used in the activation dtype."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu):
+        ops.require_cuda(x, weight)
+        x2 = x.reshape(-1, x.shape[-1]).contiguous()
+        w = weight.detach().to(x2.dtype).contiguous()
+        N = w.shape[0]
+        out = torch.empty(x2.shape[0], _pad8(N), dtype=x2.dtype, device=x.device)[:, :N]
+        b32 = bias.detach().float().contiguous() if bias is not None else None
+        epi = (EPI_BIAS_RELU if relu else EPI_BIAS) if b32 is not None else EPI_NONE
+        ops.gemm(x2, w, out, epilogue=epi, bias=b32)
+        _count()
+        ctx.save_for_backward(x2, w, out if relu else None)
+        ctx.meta = (x.shape, weight.dtype, bias is not None, relu)
+        return out.reshape(x.shape[:-1] + (N,))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, out = ctx.saved_tensors
+        xshape, wdtype, has_bias, relu = ctx.meta
+        N = w.shape[0]
+        d2 = torch.empty(x2.shape[0], _pad8(N), dtype=x2.dtype, device=x2.device)[:, :N]
+        if relu:
+            ops.eltwise(ELT_DRELU, dy.reshape(-1, N).contiguous().to(x2.dtype), d2, b=out)
+        else:
+            ops.eltwise(ELT_COPY, dy.reshape(-1, N).contiguous(), d2)
+        dW = torch.zeros(w.shape, dtype=torch.float32, device=w.device)
+        ops.gemm(d2, x2, dW, a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)
+        db = None
+        if has_bias:
+            db = torch.zeros(N, dtype=torch.float32, device=w.device)
+            ops.colsum(d2, db)
+        dx = torch.empty_like(x2)
+        ops.gemm(d2, w, dx, a_kmajor=True, b_kmajor=False)
+        _count(4)
+        return dx.reshape(xshape), dW.to(wdtype), None if db is None else db.to(wdtype), None
+
+
+class DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        y = torch.empty_like(x.contiguous())
+        ops.eltwise(ELT_DROPOUT, x.contiguous(), y, p=p, seed=seed)
+        _count()
+        ctx.ps = (p, seed)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dx = torch.empty_like(dy.contiguous())
+        ops.eltwise(ELT_DROPOUT, dy.contiguous(), dx, p=ctx.ps[0], seed=ctx.ps[1])
+        _count()
+        return dx, None, None
+
+
+class MulFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        y = torch.empty_like(a)
+        ops.eltwise(ELT_MUL, a, y, b=b)
+        _count()
+        ctx.save_for_backward(a, b)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, b = ctx.saved_tensors
+        dy = dy.contiguous()
+        da, db = torch.empty_like(a), torch.empty_like(b)
+        ops.eltwise(ELT_MUL, dy, da, b=b)
+        ops.eltwise(ELT_MUL, dy, db, b=a)
+        _count(2)
+        return da, db
+
+
+class AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a = a.contiguous()
+        y = torch.empty_like(a)
+        ops.eltwise(ELT_ADD, a, y, b=b.contiguous())
+        _count()
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def _dropout(x, p, training):
+    if not training or p <= 0.0:
+        return x
+    return DropoutFn.apply(x, float(p), int(torch.randint(0, 2 ** 62, (1,)).item()))
+
+
+def _apply_head(mod, x, training):
+    """Runs a task classifier (nn.Linear / SimpleClassifier / the 2-layer V-logit Sequential) with our kernels."""
+    from .encoders import BertLayerNorm, GeLU, SimpleClassifier
+    from torch import nn
+    if isinstance(mod, SimpleClassifier):
+        return _apply_head(mod.logit_fc, x, training)
+    if isinstance(mod, nn.Sequential):
+        for m in mod:
+            x = _apply_head(m, x, training)
+        return x
+    if isinstance(mod, nn.Linear):
+        return LinearFn.apply(x, mod.weight, mod.bias, False)
+    if isinstance(mod, GeLU):
+        return GeluFn.apply(x)
+    if isinstance(mod, BertLayerNorm):
+        return mod(x)
+    if isinstance(mod, nn.Dropout):
+        return _dropout(x, mod.p, training)
+    raise TypeError("unsupported head module %r" % type(mod))
+
+
+def tasks_forward(model, input_txt, input_imgs, image_loc, task_id, token_type_ids, attention_mask,
+                  image_attention_mask, output_all_encoded_layers, output_all_attention_masks):
+    """BertForVLTasks.forward (reference: volta/encoders.py:1158-1206)."""
+    seq_t, seq_v, pt, pv, all_masks = bert_model_forward(model.bert, input_txt, input_imgs, image_loc, token_type_ids,
+                                                         attention_mask, image_attention_mask,
+                                                         output_all_encoded_layers, output_all_attention_masks)
+    fm = model.fusion_method
+    if fm == "sum":
+        pooled = _dropout(AddFn.apply(pt, pv), model.dropout.p, model.training)
+    elif fm == "mul":
+        pooled = _dropout(MulFn.apply(pt, pv), model.dropout.p, model.training)
+    elif fm in ("text", "vl-bert_vqa"):
+        pooled = _dropout(pt, model.dropout.p, model.training)
+    elif fm == "none":
+        pooled = None
+    else:
+        raise ValueError("Invalid fusion method: %s" % fm)
+    ttype = model.task_cfg[task_id]["type"]
+    clf = model.clfs_dict[task_id]
+    if ttype.startswith("V-logit"):
+        sv = seq_v[-1] if output_all_encoded_layers else seq_v
+        mask = _int_mask_like(image_attention_mask, sv)
+        logits = _apply_head(clf, _dropout(sv, model.dropout.p, model.training), model.training)
+        vil = AddFn.apply(logits, mask.unsqueeze(2).to(logits.dtype))
+    elif ttype == "VL-binary-classifier":
+        vil = _apply_head(clf, pooled.reshape(-1, pooled.shape[1] * 2), model.training)
+    else:
+        vil = _apply_head(clf, pooled, model.training)
+    return vil, None, None, all_masks
+
+
+def _int_mask_like(mask, sv):
+    B, V = sv.shape[0], sv.shape[1]
+    if mask is None:
+        return torch.zeros(B, V, device=sv.device)
+    out = torch.empty(B, V, dtype=torch.float32, device=sv.device)
+    ones = mask.reshape(B, V).to(torch.float32)
+    # (1 - m) * -10000 : additive mask of padded regions (reference: volta/encoders.py:1198-1199)
+    ops.eltwise(_lib.ELT_SCALE, ones, out, alpha=10000.0)
+    ops.eltwise(_lib.ELT_AXPY, torch.full_like(out, 1.0), out, alpha=-10000.0)
+    _count(2)
+    return out
+
+
+# ====================================================================================================
+# stand-alone sub-layer call (module API parity for BertGatedAttention / BertGatedFeedForward)
+# ====================================================================================================
+class _SublayerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, anchor, owner, layer, kind, xt, xv, masks):
+        B, T, V = xt.shape[0], xt.shape[1], xv.shape[1]
+        rt = Runtime(owner, xt.device, B, T, V, layer.training, grad=True)
+        x = Pair.alloc(rt, rt.Mt, xt.shape[2], rt.Mv, xv.shape[2])
+        ops.eltwise(ELT_COPY, xt.reshape(rt.Mt, -1).contiguous(), x.t)
+        ops.eltwise(ELT_COPY, xv.reshape(rt.Mv, -1).contiguous(), x.v)
+        _count(2)
+        if kind == "attn":
+            y, saved = attention_fwd(rt, layer, x, masks)
+        else:
+            y, saved = ffn_fwd(rt, layer, x)
+        ctx.rt, ctx.layer, ctx.kind, ctx.saved = rt, layer, kind, saved
+        ctx.shapes = (xt.shape, xv.shape, xt.dtype)
+        return y.t.view(B, T, -1).to(xt.dtype), y.v.view(B, V, -1).to(xv.dtype)
+
+    @staticmethod
+    def backward(ctx, gt, gv):
+        rt = ctx.rt
+        rt.store.prepare_grads()
+        (st, sv, dtype) = ctx.shapes
+        dy = Pair.alloc(rt, rt.Mt, st[2], rt.Mv, sv[2])
+        for g, d in ((gt, dy.t), (gv, dy.v)):
+            if g is None:
+                ops.fill(d, 0)
+            else:
+                ops.eltwise(ELT_COPY, g.reshape(d.shape).contiguous(), d)
+        dx = attention_bwd(rt, ctx.layer, dy, ctx.saved) if ctx.kind == "attn" else ffn_bwd(rt, ctx.layer, dy, ctx.saved)
+        return None, None, None, None, dx.t.view(st).to(dtype), dx.v.view(sv).to(dtype), None
+
+
+def standalone_sublayer(layer, kind, xt, xv, mask_t_add, mask_v_add):
+    """Runs one gated sub-layer on its own.  `layer` must belong to a model (its parameters are flattened per
+    layer otherwise).  Masks follow the reference: additive [bs,1,1,L] with -10000 on padded keys."""
+    ops.require_cuda(xt, xv)
+    owner = getattr(layer, "_owner", None)
+    if owner is None:
+        owner = _LayerOwner(layer)
+        layer._owner = owner
+    masks = None
+    if kind == "attn":
+        B, T, V = xt.shape[0], xt.shape[1], xv.shape[1]
+        mt = torch.ones(B, T, dtype=torch.int32, device=xt.device) if mask_t_add is None else (mask_t_add.reshape(B, T) > -1.0).to(torch.int32)
+        mv = torch.ones(B, V, dtype=torch.int32, device=xt.device) if mask_v_add is None else (mask_v_add.reshape(B, V) > -1.0).to(torch.int32)
+        masks = (mt.contiguous(), mv.contiguous())
+    anchor = _anchor(layer)
+    return _SublayerFn.apply(anchor, owner, layer, kind, xt, xv, masks)
+
+
+class _LayerOwner:
+    """Gives a bare sub-layer the store interface of a model."""
+
+    def __init__(self, layer):
+        self.layer = layer
+        self._engine_state = None
+        self.precision = "bf16"
+        self.training = layer.training
+
+    def parameters(self):
+        return self.layer.parameters()
+
+    def _fused_groups(self):
+        from .encoders import BertPreTrainedModel
+        return BertPreTrainedModel._fused_groups(self.layer)

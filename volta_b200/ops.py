@@ -1,0 +1,279 @@
+"""Tensor-level wrappers over the C ABI: they take torch tensors (used only as device buffers), pass raw
+pointers, extents and the current CUDA stream to libvolta_b200.so, and return.  No arithmetic happens
+in PyTorch here."""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def dt(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError("volta_b200 kernels take float32 or bfloat16 tensors, got %s" % t.dtype)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _rows2d(t):
+    """(rows, cols, ld) of a tensor viewed as a row-major matrix over its last dim."""
+    assert t.stride(-1) == 1, "innermost dimension must be contiguous"
+    cols = t.shape[-1]
+    rows = t.numel() // cols
+    if t.dim() >= 2:
+        ld = t.stride(-2)
+        for i in range(t.dim() - 2):
+            assert t.stride(i) == t.stride(i + 1) * t.shape[i + 1], "leading dimensions must be collapsible"
+    else:
+        ld = cols
+    return rows, cols, ld
+
+
+def require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("volta_b200 has no CPU path: tensors must live on a CUDA (sm_100a) device")
+
+
+# --------------------------------------------------------------------------- GEMM
+def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
+         dropout_p=0.0, seed=0, offset=0, backend=_lib.GEMM_AUTO, split_k=0, M=None, N=None, K=None):
+    """out[M,N] = epilogue(opA . opB^T); see vb_gemm in include/volta_b200.h."""
+    require_cuda(a, b, out)
+    ar, ac, lda = _rows2d(a)
+    br, bc, ldb = _rows2d(b)
+    m, k = (ar, ac) if a_kmajor else (ac, ar)
+    n, kb = (br, bc) if b_kmajor else (bc, br)
+    M = m if M is None else M
+    N = n if N is None else N
+    K = k if K is None else K
+    assert kb >= K and k >= K, "reduction extents differ: A has %d, B has %d" % (k, kb)
+    orow, ocol, ldd = _rows2d(out)
+    assert orow >= M and ocol >= N, "output too small: %s for M=%d N=%d" % (tuple(out.shape), M, N)
+    assert a.dtype == b.dtype
+    g = _lib.GemmArgs()
+    g.A, g.B, g.D = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    g.M, g.N, g.K = M, N, K
+    g.lda, g.ldb, g.ldd = lda, ldb, ldd
+    g.ab_dtype, g.d_dtype = dt(a), dt(out)
+    g.a_kmajor, g.b_kmajor = int(a_kmajor), int(b_kmajor)
+    g.epilogue, g.backend = epilogue, backend
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= N
+    g.bias = _ptr(bias)
+    ld_aux = 0
+    for x in (aux_in, aux_out):
+        if x is not None:
+            assert x.dtype == out.dtype
+            _, _, ld_aux = _rows2d(x)
+    g.aux_in, g.aux_out, g.ld_aux = _ptr(aux_in), _ptr(aux_out), ld_aux
+    g.alpha, g.dropout_p, g.seed, g.offset, g.split_k = 1.0, float(dropout_p), int(seed), int(offset), int(split_k)
+    _lib.call("vb_gemm", C.byref(g), _stream())
+    return out
+
+
+def gemm_backend(a, b, out, **kw):
+    """Which back-end vb_gemm would pick (for tests / bench accounting)."""
+    ar, ac, lda = _rows2d(a)
+    br, bc, ldb = _rows2d(b)
+    a_k, b_k = kw.get("a_kmajor", True), kw.get("b_kmajor", True)
+    g = _lib.GemmArgs()
+    g.A, g.B, g.D = a.data_ptr(), b.data_ptr(), out.data_ptr()
+    g.M, g.K = (ar, ac) if a_k else (ac, ar)
+    g.N = br if b_k else bc
+    g.lda, g.ldb, g.ldd = lda, ldb, _rows2d(out)[2]
+    g.ab_dtype, g.d_dtype = dt(a), dt(out)
+    g.a_kmajor, g.b_kmajor = int(a_k), int(b_k)
+    g.epilogue, g.backend = kw.get("epilogue", 0), kw.get("backend", 0)
+    return _lib.load().vb_gemm_backend(C.byref(g))
+
+
+# --------------------------------------------------------------------------- LayerNorm
+def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=1.0, accum=False):
+    require_cuda(x, y)
+    rows, H, ld = _rows2d(x)
+    assert ld == H and _rows2d(y)[2] == H, "LayerNorm rows must be dense"
+    _lib.call("vb_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(mean), _ptr(rstd),
+              rows, H, eps, out_scale, int(accum), dt(x), _stream())
+    return y
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, out_scale=1.0, dx_drop=None, dropout_p=0.0, seed=0,
+                  offset=0, dbias=None):
+    require_cuda(dy, x, dx)
+    rows, H, ld = _rows2d(x)
+    assert ld == H
+    _lib.call("vb_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+              dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), rows, H, out_scale, _ptr(dx_drop), float(dropout_p), int(seed),
+              int(offset), _ptr(dbias), dt(x), _stream())
+    return dx
+
+
+# --------------------------------------------------------------------------- attention
+def _attn_args(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, Lv, heads, d, pair_mask, p_t, p_v,
+               seed, backend, dctx_t=None, dctx_v=None, dqkv_t=None, dqkv_v=None):
+    a = _lib.AttnArgs()
+    ref = qkv_t if qkv_t is not None else qkv_v
+    require_cuda(ref)
+    a.qkv_t, a.qkv_v = _ptr(qkv_t), _ptr(qkv_v)
+    a.ld_t = qkv_t.stride(0) if qkv_t is not None else 0
+    a.ld_v = qkv_v.stride(0) if qkv_v is not None else 0
+    for m in (mask_t, mask_v):
+        assert m is None or m.dtype == torch.int32
+    a.mask_t, a.mask_v = _ptr(mask_t), _ptr(mask_v)
+    a.ctx_t, a.ctx_v = _ptr(ctx_t), _ptr(ctx_v)
+    a.ld_ctx_t = ctx_t.stride(0) if ctx_t is not None else 0
+    a.ld_ctx_v = ctx_v.stride(0) if ctx_v is not None else 0
+    a.lse_t, a.lse_v = _ptr(lse_t), _ptr(lse_v)
+    a.dctx_t, a.dctx_v, a.dqkv_t, a.dqkv_v = _ptr(dctx_t), _ptr(dctx_v), _ptr(dqkv_t), _ptr(dqkv_v)
+    a.B, a.Lt, a.Lv, a.heads, a.d, a.pair_mask = B, Lt, Lv, heads, d, pair_mask
+    a.dtype = dt(ref)
+    a.scale = 1.0 / (d ** 0.5)
+    a.dropout_p_t, a.dropout_p_v, a.seed, a.offset, a.backend = float(p_t), float(p_v), int(seed), 0, backend
+    return a
+
+
+def attention_fwd(*args, **kw):
+    a = _attn_args(*args, **kw)
+    _lib.call("vb_attention_fwd", C.byref(a), _stream())
+
+
+def attention_bwd(*args, **kw):
+    a = _attn_args(*args, **kw)
+    _lib.call("vb_attention_bwd", C.byref(a), _stream())
+
+
+# --------------------------------------------------------------------------- embeddings
+def _table_arrays(tables, idx, const_rows):
+    n = len(tables)
+    tp = (C.c_void_p * n)(*[_ptr(t) for t in tables])
+    ip = (C.c_void_p * n)(*[_ptr(i) for i in idx])
+    cr = (C.c_int64 * n)(*[int(c) for c in const_rows])
+    return n, tp, ip, cr
+
+
+def embed_gather_fwd(tables, idx, const_rows, out, accum=False):
+    rows, H, ld = _rows2d(out)
+    for i in idx:
+        assert i is None or (i.dtype == torch.int64 and i.is_contiguous() and i.numel() == rows)
+    n, tp, ip, cr = _table_arrays(tables, idx, const_rows)
+    _lib.call("vb_embed_gather_fwd", tp, ip, cr, n, out.data_ptr(), ld, rows, H, int(accum), dt(out), _stream())
+    return out
+
+
+def embed_gather_bwd(dtables, idx, const_rows, dout):
+    rows, H, ld = _rows2d(dout)
+    n, tp, ip, cr = _table_arrays(dtables, idx, const_rows)
+    _lib.call("vb_embed_gather_bwd", tp, ip, cr, n, dout.data_ptr(), ld, rows, H, dt(dout), _stream())
+
+
+def box_project_fwd(loc, W, b, out, accum=False):
+    rows, H, ld = _rows2d(out)
+    nl = loc.shape[-1]
+    assert loc.dtype == torch.float32 and loc.is_contiguous() and W.shape == (H, nl)
+    _lib.call("vb_box_project_fwd", loc.data_ptr(), nl, W.data_ptr(), _ptr(b), out.data_ptr(), ld, rows, H, int(accum),
+              dt(out), _stream())
+    return out
+
+
+def box_project_bwd(loc, dout, dW, db):
+    rows, H, ld = _rows2d(dout)
+    _lib.call("vb_box_project_bwd", loc.data_ptr(), loc.shape[-1], dout.data_ptr(), ld, _ptr(dW), _ptr(db), rows, H,
+              dt(dout), _stream())
+
+
+# --------------------------------------------------------------------------- losses
+def xent_fwd(logits, labels, C_, lse, loss_sum, count):
+    rows, _, ld = _rows2d(logits)
+    assert labels.dtype == torch.int64 and labels.numel() == rows
+    _lib.call("vb_xent_fwd", logits.data_ptr(), ld, labels.data_ptr(), rows, C_, lse.data_ptr(), loss_sum.data_ptr(),
+              count.data_ptr(), dt(logits), _stream())
+
+
+def xent_bwd(logits, labels, C_, lse, count, dloss, dlogits):
+    rows, _, ld = _rows2d(logits)
+    assert _rows2d(dlogits)[2] == ld
+    _lib.call("vb_xent_bwd", logits.data_ptr(), ld, labels.data_ptr(), rows, C_, lse.data_ptr(), count.data_ptr(),
+              dloss.data_ptr(), dlogits.data_ptr(), dt(logits), _stream())
+
+
+def kl_fwd(logits, per, per_ld, skip, label, target, C_, weight, lse, loss_sum, count):
+    _, _, ld = _rows2d(logits)
+    rows = label.numel()
+    assert label.dtype == torch.int64 and target.dtype == torch.float32 and target.is_contiguous()
+    _lib.call("vb_kl_fwd", logits.data_ptr(), ld, per, per_ld, skip, label.data_ptr(), target.data_ptr(), rows, C_,
+              float(weight), lse.data_ptr(), loss_sum.data_ptr(), count.data_ptr(), dt(logits), _stream())
+
+
+def kl_bwd(logits, per, per_ld, skip, label, target, C_, weight, lse, count, dloss, dlogits):
+    _, _, ld = _rows2d(logits)
+    rows = label.numel()
+    _lib.call("vb_kl_bwd", logits.data_ptr(), ld, per, per_ld, skip, label.data_ptr(), target.data_ptr(), rows, C_,
+              float(weight), lse.data_ptr(), count.data_ptr(), dloss.data_ptr(), dlogits.data_ptr(), dt(logits),
+              _stream())
+
+
+def loss_finalize(loss_sum, count, out):
+    _lib.call("vb_loss_finalize", loss_sum.data_ptr(), count.data_ptr(), out.data_ptr(), out.numel(), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- element-wise glue
+def eltwise(op, a, out, b=None, alpha=1.0, p=0.0, seed=0, offset=0):
+    require_cuda(a, out)
+    rows, cols, lda = _rows2d(a)
+    ldb = _rows2d(b)[2] if b is not None else 0
+    ldo = _rows2d(out)[2]
+    _lib.call("vb_eltwise", op, a.data_ptr(), dt(a), lda, _ptr(b), dt(b) if b is not None else 0, ldb, out.data_ptr(),
+              dt(out), ldo, rows, cols, float(alpha), float(p), int(seed), int(offset), _stream())
+    return out
+
+
+def colsum(a, out):
+    rows, cols, lda = _rows2d(a)
+    assert out.dtype == torch.float32 and out.numel() >= cols
+    _lib.call("vb_colsum", a.data_ptr(), dt(a), lda, rows, cols, out.data_ptr(), _stream())
+    return out
+
+
+def gather_rows(a, idx, out):
+    rows, cols, ldo = _rows2d(out)
+    assert idx.dtype == torch.int64 and idx.numel() == rows
+    _lib.call("vb_gather_rows", a.data_ptr(), _rows2d(a)[2], idx.data_ptr(), out.data_ptr(), ldo, rows, cols, dt(a), _stream())
+    return out
+
+
+def scatter_rows_add(a, idx, out):
+    rows, cols, lda = _rows2d(a)
+    _lib.call("vb_scatter_rows_add", a.data_ptr(), lda, idx.data_ptr(), out.data_ptr(), _rows2d(out)[2], rows, cols,
+              dt(a), _stream())
+    return out
+
+
+def cast_bf16(src, dst):
+    """fp32 -> bf16 copy of one flat buffer (weight refresh after an optimizer step)."""
+    assert src.dtype == torch.float32 and dst.dtype == torch.bfloat16 and src.numel() == dst.numel()
+    item = torch.tensor([src.data_ptr(), dst.data_ptr(), src.numel()], dtype=torch.int64).to(src.device)
+    _lib.call("vb_multi_cast_bf16", item.data_ptr(), 1, src.numel(), _stream())
+    return dst
+
+
+def box_sincos(boxes, dim, out):
+    rows, _, ldo = _rows2d(out)
+    _lib.call("vb_box_sincos", boxes.data_ptr(), boxes.shape[-1], dim, out.data_ptr(), ldo, rows, dt(out), _stream())
+    return out
+
+
+def fill(buf, value=0):
+    _lib.call("vb_fill", buf.data_ptr(), buf.numel() * buf.element_size(), int(value), _stream())

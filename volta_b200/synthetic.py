@@ -1,0 +1,96 @@
+"""Seeded synthetic batches with the shapes and dtypes the reference's loaders produce.
+
+Field list and dtypes follow the pre-training call in the reference
+(`train_concap.py:275-289`) and the Conceptual-Captions loader
+(`volta/datasets/concept_cap_dataset.py:229-286`): a mean-pooled global region
+is prepended (row 0 of `image_feat`), 15 % of tokens / regions are masked,
+`image_cls` is a 1601-way soft label per detected region.  All tensors are
+created on the CPU from a `torch.Generator`, so the same seed gives the same
+batch here, on the GPU box and for the CPU baseline.
+"""
+import torch
+
+
+def pretraining_batch(batch, seq_len, num_regions, *, vocab_size=30522, feat_dim=2048, num_locs=5,
+                      num_classes=1601, seed=1234, full_length=False, global_first=True):
+    """Returns a dict of CPU tensors.  `num_regions` counts the global row (V)."""
+    g = torch.Generator().manual_seed(seed)
+    B, T, V = batch, seq_len, num_regions
+    n_det = V - 1 if global_first else V
+
+    lens = torch.full((B,), T) if full_length else torch.randint(min(8, T), T + 1, (B,), generator=g)
+    pos = torch.arange(T).unsqueeze(0)
+    input_mask = (pos < lens.unsqueeze(1)).long()
+    ids = torch.randint(min(1000, vocab_size // 2), vocab_size, (B, T), generator=g)
+    ids[:, 0] = 101 % vocab_size
+    ids[torch.arange(B), lens - 1] = 102 % vocab_size
+    ids = ids * input_mask
+    inner = input_mask.bool() & (pos > 0) & (pos < (lens - 1).unsqueeze(1))
+    pick = (torch.rand(B, T, generator=g) < 0.15) & inner
+    pick[:, 1] = True  # at least one masked token per sample
+    lm_label_ids = torch.where(pick, ids, torch.full_like(ids, -1))
+    ids = torch.where(pick, torch.full_like(ids, 103 % vocab_size), ids)
+    segment_ids = torch.zeros(B, T, dtype=torch.long)
+    is_match = torch.randint(0, 2, (B,), generator=g)
+
+    nbox = torch.full((B,), n_det) if full_length else torch.randint(min(10, n_det), n_det + 1, (B,), generator=g)
+    feat = torch.relu(torch.randn(B, n_det, feat_dim, generator=g))
+    region_pick = torch.rand(B, n_det, generator=g) < 0.15
+    region_pick[:, 0] = True
+    region_pick &= torch.arange(n_det).unsqueeze(0) < nbox.unsqueeze(1)
+    feat = feat * (~region_pick).unsqueeze(-1).float()
+    x1 = torch.rand(B, n_det, generator=g) * 0.7
+    y1 = torch.rand(B, n_det, generator=g) * 0.7
+    w = 0.05 + 0.25 * torch.rand(B, n_det, generator=g)
+    h = 0.05 + 0.25 * torch.rand(B, n_det, generator=g)
+    loc = torch.stack([x1, y1, x1 + w, y1 + h, w * h], dim=-1)[..., :num_locs]
+    image_label = torch.where(region_pick, torch.ones(B, n_det, dtype=torch.long),
+                              torch.full((B, n_det), -1, dtype=torch.long))
+    image_cls = torch.softmax(3.0 * torch.randn(B, n_det, num_classes, generator=g), dim=-1)
+    det_mask = (torch.arange(n_det).unsqueeze(0) < nbox.unsqueeze(1)).long()
+
+    if global_first:
+        keep = (det_mask.bool() & ~region_pick).float().unsqueeze(-1)
+        g_feat = (feat * keep).sum(1, keepdim=True) / keep.sum(1, keepdim=True).clamp(min=1.0)
+        g_loc = torch.tensor([0.0, 0.0, 1.0, 1.0, 1.0])[:num_locs].expand(B, 1, num_locs)
+        feat = torch.cat([g_feat, feat], dim=1)
+        loc = torch.cat([g_loc, loc], dim=1)
+        image_mask = torch.cat([torch.ones(B, 1, dtype=torch.long), det_mask], dim=1)
+    else:
+        image_mask = det_mask
+
+    return dict(
+        input_ids=ids, image_feat=feat.contiguous(), image_loc=loc.contiguous(), segment_ids=segment_ids,
+        input_mask=input_mask, image_mask=image_mask, lm_label_ids=lm_label_ids,
+        image_label=image_label, image_cls=image_cls.contiguous(), is_match=is_match,
+    )
+
+
+def retrieval_batch(num_pairs, seq_len, num_regions, *, vocab_size=30522, feat_dim=2048, num_locs=5, seed=4321):
+    """One caption repeated against `num_pairs` candidate images (`eval_retrieval.py:172-191`)."""
+    b = pretraining_batch(num_pairs, seq_len, num_regions, vocab_size=vocab_size, feat_dim=feat_dim,
+                          num_locs=num_locs, seed=seed)
+    for k in ("input_ids", "segment_ids", "input_mask"):
+        b[k] = b[k][:1].expand(num_pairs, -1).contiguous()
+    return {k: b[k] for k in ("input_ids", "image_feat", "image_loc", "segment_ids", "input_mask", "image_mask")}
+
+
+def seeded_state_dict(reference_state, seed=0, std=0.02):
+    """Deterministic weights for parity tests: N(0, std) for matrices / embeddings,
+    N(1, std) for LayerNorm weights, N(0, std) for biases, drawn key by key in
+    sorted order.  Aliased entries (same storage in `reference_state`) get the
+    same tensor.  `reference_state` only supplies names, shapes and aliasing."""
+    g = torch.Generator().manual_seed(seed)
+    by_ptr, out = {}, {}
+    for key in sorted(reference_state):
+        t = reference_state[key]
+        ptr = t.data_ptr()
+        if ptr in by_ptr:
+            out[key] = by_ptr[ptr]
+            continue
+        v = torch.randn(t.shape, generator=g) * std
+        if key.endswith("LayerNorm.weight") or key.endswith("layer_norm.weight") or \
+                (key.endswith(".weight") and t.dim() == 1):
+            v = v + 1.0
+        by_ptr[ptr] = out[key] = v
+    return out
