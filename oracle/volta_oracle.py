@@ -431,4 +431,4 @@ def fwd_bwd(P, cfg, batch, train=False):
     losses = pretraining_losses(P, cfg, batch, train)
     total = losses[0] + losses[1] + losses[2]
     total.backward()
-    return [float(l) for l in losses]
+    return [float(l.detach()) for l in losses]

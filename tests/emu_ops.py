@@ -211,14 +211,14 @@ def xent_bwd(logits, labels, C_, lse, count, dloss, dlogits):
     dlogits[:, :C_] = ((p - onehot) * g * live).to(dlogits.dtype)
 
 
-def _kl_rows(per, per_ld, skip, rows):
-    r = torch.arange(rows)
+def _kl_rows(per, per_ld, skip, rows, device=None):
+    r = torch.arange(rows, device=device)
     return (r // per) * per_ld + (r % per) + skip
 
 
 def kl_fwd(logits, per, per_ld, skip, label, target, C_, weight, lse, loss_sum, count):
     rows = label.numel()
-    x = logits[_kl_rows(per, per_ld, skip, rows), :C_].float()
+    x = logits[_kl_rows(per, per_ld, skip, rows, logits.device), :C_].float()
     live = label == 1
     l = torch.logsumexp(x, -1)
     lse.copy_(torch.where(live, l, torch.zeros_like(l)))
@@ -229,13 +229,13 @@ def kl_fwd(logits, per, per_ld, skip, label, target, C_, weight, lse, loss_sum, 
 
 def kl_bwd(logits, per, per_ld, skip, label, target, C_, weight, lse, count, dloss, dlogits):
     rows = label.numel()
-    idx = _kl_rows(per, per_ld, skip, rows)
+    idx = _kl_rows(per, per_ld, skip, rows, logits.device)
     x = logits[idx, :C_].float()
     live = (label == 1)[:, None]
     g = weight * dloss / count.clamp(min=1.0)
     p = torch.exp(x - lse[:, None])
     d = g * (p * target.sum(-1, keepdim=True) - target) * live
-    full = torch.zeros(dlogits.shape[0], C_)
+    full = torch.zeros(dlogits.shape[0], C_, device=logits.device)
     full[idx] = d
     dlogits[:, :C_] = full.to(dlogits.dtype)
 
@@ -302,7 +302,7 @@ def box_sincos(boxes, dim, out):
     w = (boxes[:, 2] - boxes[:, 0]) * 100
     h = (boxes[:, 3] - boxes[:, 1]) * 100
     pos = torch.stack([cx, cy, w, h], -1)
-    freq = 1000 ** (torch.arange(dim, dtype=torch.float32) / float(dim))
+    freq = 1000 ** (torch.arange(dim, dtype=torch.float32, device=boxes.device) / float(dim))
     ang = pos[..., None] / freq
     out.copy_(torch.cat([ang.sin(), ang.cos()], -1).reshape(out.shape).to(out.dtype))
     return out

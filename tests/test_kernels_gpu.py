@@ -1,0 +1,353 @@
+"""Kernel-level parity on the B200: every C-ABI entry point against its PyTorch restatement (tests/emu_ops.py).
+bf16 tolerances are relative L2 per tensor (stated per test); integer/index outputs must be exact."""
+import math
+
+import pytest
+import torch
+
+import emu_ops
+from volta_b200 import _lib, ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp(min=1e-30))
+
+
+def rnd(*shape, dtype=torch.bfloat16, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+# ------------------------------------------------------------------ GEMM
+GEMM_SHAPES = [(256, 256, 128), (300, 768, 768), (130, 1601, 768), (1000, 128, 3072), (72, 2304, 768), (520, 200, 72)]
+
+
+@pytest.mark.parametrize("backend", ["tc", "simt"])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_forward_bias(backend, M, N, K):
+    a, w, bias = rnd(M, K), rnd(N, K, scale=0.05), rnd(N, dtype=torch.float32)
+    ldn = (N + 7) // 8 * 8
+    out = torch.zeros(M, ldn, dtype=torch.bfloat16, device=DEV)[:, :N]
+    ops.gemm(a, w, out, epilogue=_lib.EPI_BIAS, bias=bias, backend=_lib.GEMM_TC if backend == "tc" else _lib.GEMM_SIMT)
+    ref = a.float() @ w.float().t() + bias
+    assert rel(out.float(), ref) < 6e-3
+
+
+@pytest.mark.parametrize("epi", ["none", "gelu", "relu", "res", "dgelu", "add", "drelu", "bias_add"])
+@pytest.mark.parametrize("odt", [torch.bfloat16, torch.float32])
+def test_gemm_tc_epilogues(epi, odt):
+    M, N, K = 260, 392, 256
+    a, w, bias = rnd(M, K), rnd(N, K, scale=0.1), rnd(N, dtype=torch.float32)
+    aux = rnd(M, N, dtype=odt, seed=3)
+    out, out_ref = torch.zeros(M, N, dtype=odt, device=DEV), torch.zeros(M, N, dtype=odt, device=DEV)
+    pre, pre_ref = torch.zeros(M, N, dtype=odt, device=DEV), torch.zeros(M, N, dtype=odt, device=DEV)
+    code = dict(none=_lib.EPI_NONE, gelu=_lib.EPI_BIAS_GELU, relu=_lib.EPI_BIAS_RELU, res=_lib.EPI_BIAS_DROP_RES,
+                dgelu=_lib.EPI_DGELU, add=_lib.EPI_ADD, drelu=_lib.EPI_DRELU, bias_add=_lib.EPI_BIAS_ADD)[epi]
+    kw = dict(epilogue=code, bias=bias, aux_in=aux)
+    ops.gemm(a, w, out, aux_out=pre, backend=_lib.GEMM_TC, **kw)
+    emu_ops.gemm(a, w, out_ref, aux_out=pre_ref, **kw)
+    assert rel(out.float(), out_ref.float()) < 8e-3
+    if epi == "gelu":
+        assert rel(pre.float(), pre_ref.float()) < 8e-3
+
+
+@pytest.mark.parametrize("backend", ["tc", "simt"])
+def test_gemm_dgrad_mn_major_b(backend):
+    """dX[M,K] = dY[M,N] . W[N,K]: B operand is MN-major (row-major [reduction, out])."""
+    M, N, K = 300, 520, 384
+    dy, w = rnd(M, N), rnd(N, K, scale=0.1)
+    out = torch.zeros(M, K, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(dy, w, out, a_kmajor=True, b_kmajor=False, backend=_lib.GEMM_TC if backend == "tc" else _lib.GEMM_SIMT)
+    assert rel(out.float(), dy.float() @ w.float()) < 6e-3
+
+
+@pytest.mark.parametrize("backend", ["tc", "simt"])
+@pytest.mark.parametrize("M,N,K,split", [(1000, 256, 384, 0), (4096, 768, 768, 0), (333, 1601, 128, 1), (2000, 130, 264, 3)])
+def test_gemm_wgrad_accumulate(backend, M, N, K, split):
+    """dW[N,K] += dY[M,N]^T . X[M,K]: both operands MN-major, fp32 atomic accumulation (split-K)."""
+    # operands keep a 16-byte row pitch (the engine pads logits to a multiple of 8 columns)
+    dy = rnd(M, (N + 7) // 8 * 8, scale=0.5)[:, :N]
+    x = rnd(M, (K + 7) // 8 * 8, scale=0.5)[:, :K]
+    base = rnd(N, K, dtype=torch.float32, seed=9)
+    out = base.clone()
+    ops.gemm(dy, x, out, a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ACCUM, split_k=split,
+             backend=_lib.GEMM_TC if backend == "tc" else _lib.GEMM_SIMT)
+    ref = base + dy.float().t() @ x.float()
+    assert rel(out, ref) < 2e-3
+
+
+def test_gemm_tc_strided_rows_and_inplace_add():
+    """The pooler reads row 0 of every sample through lda = T*H and adds its dgrad in place through ldd."""
+    B, T, H, P = 64, 12, 256, 512
+    x = rnd(B * T, H)
+    w, bias = rnd(P, H, scale=0.1), rnd(P, dtype=torch.float32)
+    rows0 = x.view(B, T * H)[:, :H]
+    out = torch.zeros(B, P, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(rows0, w, out, epilogue=_lib.EPI_BIAS_RELU, bias=bias, backend=_lib.GEMM_TC)
+    assert rel(out.float(), torch.relu(rows0.float() @ w.float().t() + bias)) < 6e-3
+    dpre = rnd(B, P, seed=5)
+    dx = rnd(B * T, H, seed=6)
+    ref = dx.clone().float().view(B, T, H)
+    ref[:, 0] += dpre.float() @ w.float()
+    d0 = dx.view(B, T * H)[:, :H]
+    ops.gemm(dpre, w, d0, a_kmajor=True, b_kmajor=False, epilogue=_lib.EPI_ADD, aux_in=d0, backend=_lib.GEMM_TC)
+    assert rel(dx.float().view(B, T, H), ref) < 6e-3
+
+
+def test_gemm_fp32_simt_matches_fp32():
+    M, N, K = 200, 96, 40
+    a, w = rnd(M, K, dtype=torch.float32), rnd(N, K, dtype=torch.float32)
+    out = torch.zeros(M, N, dtype=torch.float32, device=DEV)
+    ops.gemm(a, w, out)
+    assert rel(out, a @ w.t()) < 1e-5
+
+
+def test_gemm_dropout_mask_is_shared_with_layernorm_bwd():
+    """BIAS_DROP_RES and vb_layernorm_bwd(dx_drop) must regenerate the same Philox mask."""
+    M, H, p, seed = 256, 768, 0.1, 1234567
+    a = torch.zeros(M, 64, dtype=torch.bfloat16, device=DEV)
+    w = torch.zeros(H, 64, dtype=torch.bfloat16, device=DEV)
+    bias = torch.ones(H, dtype=torch.float32, device=DEV)
+    res = torch.zeros(M, H, dtype=torch.bfloat16, device=DEV)
+    for backend in (_lib.GEMM_TC, _lib.GEMM_SIMT):
+        out = torch.empty(M, H, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(a, w, out, epilogue=_lib.EPI_BIAS_DROP_RES, bias=bias, aux_in=res, dropout_p=p, seed=seed, backend=backend)
+        keep = out.float() > 0
+        assert abs(float(keep.float().mean()) - (1 - p)) < 0.01
+        assert torch.allclose(out.float()[keep], torch.tensor(1 / (1 - p)).bfloat16().float().to(DEV))
+        x = rnd(M, H)
+        dy = rnd(M, H, seed=2)
+        gamma = torch.ones(H, device=DEV)
+        mean, rstd = torch.zeros(M, device=DEV), torch.ones(M, device=DEV)
+        dx, dxd = torch.empty_like(x), torch.empty_like(x)
+        ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, None, None, dx_drop=dxd, dropout_p=p, seed=seed)
+        assert torch.equal(dxd.float() != 0, keep & (dx.float() != 0))
+
+
+# ------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("H", [128, 768, 1024, 1536])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_layernorm_fwd_bwd(H, dtype):
+    rows = 1000
+    x, dy = rnd(rows, H, dtype=dtype, scale=2.0), rnd(rows, H, dtype=dtype, seed=1)
+    gamma, beta = 1 + rnd(H, dtype=torch.float32, scale=0.1), rnd(H, dtype=torch.float32, scale=0.1)
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    y, y_ref = torch.empty_like(x), torch.empty_like(x)
+    mean, rstd = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    mean_r, rstd_r = torch.empty(rows, device=DEV), torch.empty(rows, device=DEV)
+    ops.layernorm_fwd(x, gamma, beta, y, mean, rstd)
+    emu_ops.layernorm_fwd(x, gamma, beta, y_ref, mean_r, rstd_r)
+    assert rel(y.float(), y_ref.float()) < tol
+    assert rel(mean, mean_r) < 1e-4 and rel(rstd, rstd_r) < 1e-4
+    dx, dx_ref = torch.empty_like(x), torch.empty_like(x)
+    grads = [torch.zeros(H, device=DEV) for _ in range(6)]
+    ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, grads[0], grads[1], dbias=grads[2])
+    emu_ops.layernorm_bwd(dy, x, mean_r, rstd_r, gamma, dx_ref, grads[3], grads[4], dbias=grads[5])
+    assert rel(dx.float(), dx_ref.float()) < tol
+    for got, ref in zip(grads[:3], grads[3:]):
+        assert rel(got, ref) < max(tol, 1e-4)
+
+
+def test_layernorm_scale_accumulate():
+    rows, H = 300, 768
+    a, b = rnd(rows, H), rnd(rows, H, seed=1)
+    g1, b1, g2, b2 = (1 + rnd(H, dtype=torch.float32, scale=0.1, seed=s) for s in range(4))
+    y = torch.empty_like(a)
+    ops.layernorm_fwd(a, g1, b1, y, out_scale=0.5)
+    ops.layernorm_fwd(b, g2, b2, y, out_scale=0.5, accum=True)
+    ref = 0.5 * torch.nn.functional.layer_norm(a.float(), (H,), g1, b1, 1e-12) + \
+        0.5 * torch.nn.functional.layer_norm(b.float(), (H,), g2, b2, 1e-12)
+    assert rel(y.float(), ref) < 8e-3
+
+
+# ------------------------------------------------------------------ attention
+ATTN_CASES = [  # (B, Lt, Lv, heads, d, pair_mask)
+    (3, 36, 37, 12, 64, 1), (3, 36, 37, 12, 64, 8), (3, 36, 37, 12, 64, 6), (3, 36, 37, 12, 64, 15),
+    (2, 30, 101, 8, 128, 6), (2, 30, 101, 8, 128, 8), (2, 10, 7, 2, 64, 15), (2, 38, 37, 12, 64, 9),
+    (2, 56, 80, 4, 64, 15),
+]
+
+
+def _attn_inputs(B, Lt, Lv, heads, d, pm, dtype):
+    A = heads * d
+    has_t, has_v = bool(pm & 7), bool(pm & 14)
+    qt = rnd(B * Lt, 3 * A, dtype=dtype, scale=0.7) if has_t else None
+    qv = rnd(B * Lv, 3 * A, dtype=dtype, scale=0.7, seed=1) if has_v else None
+    mt = (torch.arange(Lt)[None] < torch.tensor([Lt, max(3, Lt // 2), Lt - 1][:B])[:, None]).int().to(DEV)
+    mv = (torch.arange(Lv)[None] < torch.tensor([Lv - 2, Lv, max(2, Lv // 3)][:B])[:, None]).int().to(DEV)
+    return qt, qv, mt, mv, A
+
+
+@pytest.mark.parametrize("backend", ["mma", "simt"])
+@pytest.mark.parametrize("B,Lt,Lv,heads,d,pm", ATTN_CASES)
+def test_attention_fwd_bwd(backend, B, Lt, Lv, heads, d, pm):
+    dtype = torch.bfloat16
+    qt, qv, mt, mv, A = _attn_inputs(B, Lt, Lv, heads, d, pm, dtype)
+    tq, vq = bool(pm & 3), bool(pm & 12)
+    be = _lib.ATTN_MMA if backend == "mma" else _lib.ATTN_SIMT
+
+    def bufs():
+        return (torch.zeros(B * Lt, A, dtype=dtype, device=DEV) if tq else None,
+                torch.zeros(B * Lv, A, dtype=dtype, device=DEV) if vq else None,
+                torch.zeros(B, heads, Lt, device=DEV), torch.zeros(B, heads, Lv, device=DEV))
+    ct, cv, lt, lv = bufs()
+    rt_, rv_, rlt, rlv = bufs()
+    args = (qt, qv, mt if qt is not None else None, mv if qv is not None else None)
+    ops.attention_fwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, be)
+    emu_ops.attention_fwd(*args, rt_, rv_, rlt, rlv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, 0)
+    for got, ref, on in ((ct, rt_, tq), (cv, rv_, vq)):
+        if on:
+            assert rel(got.float(), ref.float()) < 1e-2
+    if tq:
+        assert torch.allclose(lt, rlt, atol=2e-2)
+    if vq:
+        assert torch.allclose(lv, rlv, atol=2e-2)
+    dct = rnd(B * Lt, A, dtype=dtype, seed=7) if tq else None
+    dcv = rnd(B * Lv, A, dtype=dtype, seed=8) if vq else None
+    dqt = torch.full_like(qt, 7.0) if qt is not None else None
+    dqv = torch.full_like(qv, 7.0) if qv is not None else None
+    rqt = torch.zeros_like(qt) if qt is not None else None
+    rqv = torch.zeros_like(qv) if qv is not None else None
+    ops.attention_bwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, be, dctx_t=dct, dctx_v=dcv, dqkv_t=dqt, dqkv_v=dqv)
+    emu_ops.attention_bwd(*args, rt_, rv_, rlt, rlv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, 0, dctx_t=dct, dctx_v=dcv, dqkv_t=rqt, dqkv_v=rqv)
+    for got, ref in ((dqt, rqt), (dqv, rqv)):
+        if got is not None:
+            assert rel(got.float(), ref.float()) < 2e-2
+
+
+def test_attention_simt_fp32_exact():
+    B, Lt, Lv, heads, d, pm = 2, 12, 9, 2, 32, 15
+    qt, qv, mt, mv, A = _attn_inputs(B, Lt, Lv, heads, d, pm, torch.float32)
+    ct, cv = torch.zeros(B * Lt, A, device=DEV), torch.zeros(B * Lv, A, device=DEV)
+    lt, lv = torch.zeros(B, heads, Lt, device=DEV), torch.zeros(B, heads, Lv, device=DEV)
+    rt_, rv_, rlt, rlv = torch.zeros_like(ct), torch.zeros_like(cv), torch.zeros_like(lt), torch.zeros_like(lv)
+    ops.attention_fwd(qt, qv, mt, mv, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, _lib.ATTN_SIMT)
+    emu_ops.attention_fwd(qt, qv, mt, mv, rt_, rv_, rlt, rlv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, 0)
+    assert rel(ct, rt_) < 1e-5 and rel(cv, rv_) < 1e-5
+
+
+def test_attention_dropout_fwd_bwd_consistent():
+    """With dropout on, the MMA and SIMT back-ends must drop the same probabilities (same Philox indexing),
+    and the backward must regenerate the forward's mask."""
+    B, Lt, Lv, heads, d, pm = 2, 36, 37, 4, 64, 15
+    qt, qv, mt, mv, A = _attn_inputs(B, Lt, Lv, heads, d, pm, torch.bfloat16)
+    outs = []
+    for be in (_lib.ATTN_MMA, _lib.ATTN_SIMT):
+        ct, cv = torch.zeros(B * Lt, A, dtype=torch.bfloat16, device=DEV), torch.zeros(B * Lv, A, dtype=torch.bfloat16, device=DEV)
+        lt, lv = torch.zeros(B, heads, Lt, device=DEV), torch.zeros(B, heads, Lv, device=DEV)
+        ops.attention_fwd(qt, qv, mt, mv, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.3, 0.3, 99, be)
+        dct, dcv = rnd(B * Lt, A, seed=7), rnd(B * Lv, A, seed=8)
+        dqt, dqv = torch.zeros_like(qt), torch.zeros_like(qv)
+        ops.attention_bwd(qt, qv, mt, mv, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.3, 0.3, 99, be,
+                          dctx_t=dct, dctx_v=dcv, dqkv_t=dqt, dqkv_v=dqv)
+        outs.append((ct, cv, dqt, dqv))
+    for a, b in zip(*outs):
+        assert rel(a.float(), b.float()) < 2e-2
+
+
+# ------------------------------------------------------------------ embeddings / losses / glue
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_embed_gather_and_box(dtype):
+    rows, H, V = 500, 768, 1000
+    g = torch.Generator().manual_seed(0)
+    tabs = [rnd(V, H, dtype=torch.float32), rnd(64, H, dtype=torch.float32, seed=1), rnd(2, H, dtype=torch.float32, seed=2)]
+    idx = [torch.randint(0, V, (rows,), generator=g).to(DEV), torch.randint(0, 64, (rows,), generator=g).to(DEV), None]
+    out, ref = torch.zeros(rows, H, dtype=dtype, device=DEV), torch.zeros(rows, H, dtype=dtype, device=DEV)
+    ops.embed_gather_fwd(tabs, idx, [0, 0, 1], out)
+    emu_ops.embed_gather_fwd(tabs, idx, [0, 0, 1], ref)
+    assert rel(out.float(), ref.float()) < 1e-6
+    dout = rnd(rows, H, dtype=dtype, seed=5)
+    gt = [torch.zeros_like(t) for t in tabs]
+    gr = [torch.zeros_like(t) for t in tabs]
+    ops.embed_gather_bwd(gt, idx, [0, 0, 1], dout)
+    emu_ops.embed_gather_bwd(gr, idx, [0, 0, 1], dout)
+    for a, b in zip(gt, gr):
+        assert rel(a, b) < 1e-4
+    loc = torch.rand(rows, 5, generator=g).to(DEV)
+    W, b = rnd(H, 5, dtype=torch.float32), rnd(H, dtype=torch.float32)
+    o2, r2 = out.clone(), out.clone()
+    ops.box_project_fwd(loc, W, b, o2, accum=True)
+    emu_ops.box_project_fwd(loc, W, b, r2, accum=True)
+    assert rel(o2.float(), r2.float()) < 1e-5
+    dW, db, rW, rb = torch.zeros_like(W), torch.zeros_like(b), torch.zeros_like(W), torch.zeros_like(b)
+    ops.box_project_bwd(loc, dout, dW, db)
+    emu_ops.box_project_bwd(loc, dout, rW, rb)
+    assert rel(dW, rW) < 1e-4 and rel(db, rb) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("C_", [30522, 2, 1601])
+def test_xent(dtype, C_):
+    rows = 96
+    ld = (C_ + 7) // 8 * 8
+    g = torch.Generator().manual_seed(1)
+    logits = rnd(rows, ld, dtype=dtype, scale=2.0)
+    labels = torch.randint(0, C_, (rows,), generator=g)
+    labels[torch.rand(rows, generator=g) < 0.6] = -1
+    labels = labels.to(DEV)
+    acc, acc_r = torch.zeros(2, device=DEV), torch.zeros(2, device=DEV)
+    lse, lse_r = torch.zeros(rows, device=DEV), torch.zeros(rows, device=DEV)
+    ops.xent_fwd(logits, labels, C_, lse, acc[0:1], acc[1:2])
+    emu_ops.xent_fwd(logits, labels, C_, lse_r, acc_r[0:1], acc_r[1:2])
+    assert torch.allclose(acc, acc_r, rtol=1e-4) and torch.allclose(lse, lse_r, atol=1e-4)
+    dl = torch.tensor([0.7], device=DEV)
+    d, d_r = torch.full_like(logits, 3.0), torch.zeros_like(logits)
+    ops.xent_bwd(logits, labels, C_, lse, acc[1:2], dl, d)
+    emu_ops.xent_bwd(logits, labels, C_, lse_r, acc_r[1:2], dl, d_r)
+    assert rel(d[:, :C_].float(), d_r[:, :C_].float()) < (1e-5 if dtype == torch.float32 else 6e-3)
+    # in place
+    ops.xent_bwd(logits, labels, C_, lse, acc[1:2], dl, logits)
+    assert rel(logits[:, :C_].float(), d_r[:, :C_].float()) < (1e-5 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("skip", [0, 1])
+def test_kl(dtype, skip):
+    B, V, C_ = 6, 9, 1601
+    per = V - 1
+    ld = 1608
+    g = torch.Generator().manual_seed(2)
+    logits = rnd(B * V, ld, dtype=dtype, scale=2.0)
+    label = torch.where(torch.rand(B * per, generator=g) < 0.3, 1, -1).to(DEV)
+    target = torch.softmax(3 * torch.randn(B * per, C_, generator=g), -1).to(DEV)
+    acc, acc_r = torch.zeros(2, device=DEV), torch.zeros(2, device=DEV)
+    lse, lse_r = torch.zeros(B * per, device=DEV), torch.zeros(B * per, device=DEV)
+    ops.kl_fwd(logits, per, V, skip, label, target, C_, 1.5, lse, acc[0:1], acc[1:2])
+    emu_ops.kl_fwd(logits, per, V, skip, label, target, C_, 1.5, lse_r, acc_r[0:1], acc_r[1:2])
+    assert abs(float(acc[0]) - float(acc_r[0])) < 1e-3 * max(1.0, abs(float(acc_r[0]))) and float(acc[1]) == float(acc_r[1])
+    dl = torch.tensor([1.3], device=DEV)
+    d, d_r = torch.full_like(logits, 5.0), torch.zeros_like(logits)
+    ops.kl_bwd(logits, per, V, skip, label, target, C_, 1.5, lse, acc[1:2], dl, d)
+    emu_ops.kl_bwd(logits, per, V, skip, label, target, C_, 1.5, lse_r, acc_r[1:2], dl, d_r)
+    assert rel(d[:, :C_].float(), d_r[:, :C_].float()) < (1e-4 if dtype == torch.float32 else 6e-3)
+
+
+def test_eltwise_colsum_gather():
+    a, b = rnd(300, 1024), rnd(300, 1024, seed=1)
+    for op in (_lib.ELT_ADD, _lib.ELT_MUL, _lib.ELT_RELU, _lib.ELT_DRELU, _lib.ELT_GELU, _lib.ELT_DGELU):
+        o, r = torch.empty_like(a), torch.empty_like(a)
+        ops.eltwise(op, a, o, b=b)
+        emu_ops.eltwise(op, a, r, b=b)
+        assert rel(o.float(), r.float()) < 4e-3, op
+    f32 = torch.empty(300, 1024, device=DEV)
+    ops.eltwise(_lib.ELT_COPY, a, f32)
+    assert torch.equal(f32, a.float())
+    cs, cr = torch.zeros(1024, device=DEV), a.float().sum(0)
+    ops.colsum(a, cs)
+    assert rel(cs, cr) < 1e-5
+    idx = torch.randperm(300)[:100].to(DEV)
+    o = torch.empty(100, 1024, dtype=torch.bfloat16, device=DEV)
+    ops.gather_rows(a, idx, o)
+    assert torch.equal(o, a[idx])
+    w = rnd(100000, dtype=torch.float32)
+    h = torch.empty(100000, dtype=torch.bfloat16, device=DEV)
+    ops.cast_bf16(w, h)
+    assert torch.equal(h, w.bfloat16())
+    keep = torch.empty_like(a)
+    ops.eltwise(_lib.ELT_DROPOUT, torch.ones_like(a), keep, p=0.25, seed=5)
+    frac = float((keep.float() > 0).float().mean())
+    assert abs(frac - 0.75) < 0.01

@@ -32,7 +32,8 @@ template <int BN> struct Cfg {
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // 512 or 256 (power of two >= 32)
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
+                                       4 * 4608 /*epilogue staging*/ + 256 /*barriers*/;
 };
 
 struct Params {
@@ -144,69 +145,232 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool kmajor) 
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// ---- epilogue for one row, 32 consecutive columns ------------------------------
-template <typename OutT>
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, const uint32_t (&acc)[32], int64_t m, int64_t n0) {
-  const int e = p.epilogue;
-  if (e == VB_EPI_ACCUM) {
-    float* d = reinterpret_cast<float*>(p.D) + m * p.ldd + n0;
+// ---- epilogue ---------------------------------------------------------------------------------
+// Each epilogue warp owns 32 accumulator rows (its TMEM lane quarter).  tcgen05.ld hands every thread ONE
+// row, so writing straight from registers would touch 32 different cache lines per store instruction.
+// Instead the warp goes through a private shared-memory staging tile of 32 rows x 128 B (pitch 144 B keeps
+// both the row-owner accesses and the transposed accesses bank-conflict free) so that every global load /
+// store / red instruction covers 4 whole 128-byte lines: residual / pre-activation reads, D writes and the
+// split-K fp32 reductions are all fully coalesced.
+constexpr uint32_t STG_PITCH = 144;                  // bytes per staged row (128 B payload + 16 B pad)
+constexpr uint32_t STG_WARP_BYTES = 32 * STG_PITCH;  // 4608 B per epilogue warp
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <typename OutT> struct Stg {
+  static constexpr int EV = 16 / (int)sizeof(OutT);  // elements per 16-byte vector (8 bf16 / 4 fp32)
+  static constexpr int CW = 128 / (int)sizeof(OutT); // columns per staged chunk (64 bf16 / 32 fp32)
+  static constexpr int NLD = CW / 32;                // tcgen05.ld.x32 per chunk
+
+  // coalesced global -> staging (rows of this warp; zero fill out of range)
+  static __device__ __forceinline__ void load_tile(uint8_t* stg, const OutT* g, int64_t ld, int64_t m0, int64_t n0,
+                                                   int64_t M, int64_t N, int lane) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n0 + j < p.N) atomicAdd(d + j, __uint_as_float(acc[j]) * p.alpha);
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3), v = lane & 7;
+      const int64_t m = m0 + r, n = n0 + v * EV;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (m < M) {
+        const OutT* src = g + m * ld + n;
+        if (n + EV <= N) {
+          val = *reinterpret_cast<const uint4*>(src);
+        } else if (n < N) {
+          OutT tmp[EV];
+#pragma unroll
+          for (int j = 0; j < EV; ++j) tmp[j] = (n + j < N) ? src[j] : from_f<OutT>(0.f);
+          val = *reinterpret_cast<uint4*>(tmp);
+        }
+      }
+      *reinterpret_cast<uint4*>(stg + r * STG_PITCH + v * 16) = val;
+    }
+  }
+  // coalesced staging -> global store
+  static __device__ __forceinline__ void store_tile(const uint8_t* stg, OutT* g, int64_t ld, int64_t m0, int64_t n0,
+                                                    int64_t M, int64_t N, int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int r = i * 4 + (lane >> 3), v = lane & 7;
+      const int64_t m = m0 + r, n = n0 + v * EV;
+      if (m < M && n < N) {
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + r * STG_PITCH + v * 16);
+        OutT* dst = g + m * ld + n;
+        if (n + EV <= N) {
+          *reinterpret_cast<uint4*>(dst) = val;
+        } else {
+          const OutT* tmp = reinterpret_cast<const OutT*>(&val);
+#pragma unroll
+          for (int j = 0; j < EV; ++j) if (n + j < N) dst[j] = tmp[j];
+        }
+      }
+    }
+  }
+};
+
+// coalesced staging -> global fp32 reduction (split-K / shared-weight accumulation)
+__device__ __forceinline__ void red_tile(const uint8_t* stg, float* g, int64_t ld, int64_t m0, int64_t n0, int64_t M,
+                                         int64_t N, int lane) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = i * 4 + (lane >> 3), v = lane & 7;
+    const int64_t m = m0 + r, n = n0 + v * 4;
+    if (m < M && n < N) {
+      const float4 val = *reinterpret_cast<const float4*>(stg + r * STG_PITCH + v * 16);
+      float* dst = g + m * ld + n;
+      if (n + 4 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+        red_add_v4(dst, val.x, val.y, val.z, val.w);
+      } else {
+        const float t[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (n + j < N) atomicAdd(dst + j, t[j]);
+      }
+    }
+  }
+}
+
+// Out-of-line Philox: the epilogue is fully unrolled over its row, and ten inlined rounds per 4 columns would
+// push the loop body out of the instruction cache (an earlier version of this epilogue was 95 % stall_no_inst).
+__device__ __noinline__ uint4 philox_block(uint64_t seed, uint64_t ctr) { return Philox::gen(seed, ctr); }
+
+// One chunk (CW columns) of one warp's 32 rows.  `acc` holds this thread's row: CW fp32 accumulators.
+// EPI is a compile-time constant: the epilogue kind is dispatched ONCE per tile, never per element.
+template <typename OutT, int EPI>
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& p, float (&acc)[Stg<OutT>::CW], uint8_t* stg, int64_t m0,
+                                               int64_t n0, int lane) {
+  using S = Stg<OutT>;
+  constexpr bool use_bias = EPI == VB_EPI_BIAS || EPI == VB_EPI_BIAS_GELU || EPI == VB_EPI_BIAS_RELU ||
+                            EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_BIAS_ADD;
+  constexpr bool use_aux = EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_DGELU || EPI == VB_EPI_ADD ||
+                           EPI == VB_EPI_DRELU || EPI == VB_EPI_BIAS_ADD;
+  uint8_t* my_row = stg + lane * STG_PITCH;
+  const int64_t m = m0 + lane;
+  if constexpr (use_aux) {
+    S::load_tile(stg, reinterpret_cast<const OutT*>(p.aux_in), p.ld_aux, m0, n0, p.M, p.N, lane);
+    __syncwarp();
+  }
+  const bool full = (n0 + S::CW <= p.N);
+#pragma unroll
+  for (int v = 0; v < S::CW / S::EV; ++v) {
+    const int64_t n = n0 + v * S::EV;
+    float b[S::EV], x[S::EV];
+#pragma unroll
+    for (int j = 0; j < S::EV; ++j) { b[j] = 0.f; x[j] = 0.f; }
+    if constexpr (use_bias) {
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < S::EV; j += 4) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+          b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < S::EV; ++j) if (n + j < p.N) b[j] = __ldg(p.bias + n + j);
+      }
+    }
+    if constexpr (use_aux) {
+      uint4 raw = *reinterpret_cast<const uint4*>(my_row + v * 16);
+      const OutT* t = reinterpret_cast<const OutT*>(&raw);
+#pragma unroll
+      for (int j = 0; j < S::EV; ++j) x[j] = to_f<OutT>(t[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < S::EV; ++j) {
+      float a = acc[v * S::EV + j] * p.alpha;
+      if constexpr (EPI == VB_EPI_BIAS) a = a + b[j];
+      else if constexpr (EPI == VB_EPI_BIAS_GELU) a = a + b[j];            // pre-activation; GELU in the 2nd pass
+      else if constexpr (EPI == VB_EPI_BIAS_RELU) a = fmaxf(a + b[j], 0.f);
+      else if constexpr (EPI == VB_EPI_BIAS_DROP_RES) a = a + b[j];        // mask + residual below
+      else if constexpr (EPI == VB_EPI_DGELU) a = a * dgelu_fast(x[j]);
+      else if constexpr (EPI == VB_EPI_ADD) a = a + x[j];
+      else if constexpr (EPI == VB_EPI_DRELU) a = x[j] > 0.f ? a : 0.f;
+      else if constexpr (EPI == VB_EPI_BIAS_ADD) a = a + b[j] + x[j];
+      acc[v * S::EV + j] = a;
+    }
+    if constexpr (EPI == VB_EPI_BIAS_DROP_RES) {
+      if (p.drop_thresh != 0u) {
+        if ((p.N & 3) == 0) {  // one Philox block per 4 consecutive columns
+#pragma unroll
+          for (int h = 0; h < S::EV; h += 4) {
+            const uint64_t idx = (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + h);
+            const uint4 r = philox_block(p.seed, p.offset + (idx >> 2));
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              acc[v * S::EV + h + j] = rr[j] >= p.drop_thresh ? acc[v * S::EV + h + j] * p.drop_scale : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < S::EV; ++j) {
+            const uint64_t idx = (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + j);
+            const uint4 r = philox_block(p.seed, p.offset + (idx >> 2));
+            const uint32_t lane4 = (uint32_t)idx & 3u;
+            const uint32_t rv = lane4 == 0 ? r.x : lane4 == 1 ? r.y : lane4 == 2 ? r.z : r.w;
+            acc[v * S::EV + j] = rv >= p.drop_thresh ? acc[v * S::EV + j] * p.drop_scale : 0.f;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < S::EV; ++j) acc[v * S::EV + j] += x[j];
+    }
+    OutT o[S::EV];
+#pragma unroll
+    for (int j = 0; j < S::EV; ++j) o[j] = from_f<OutT>(acc[v * S::EV + j]);
+    *reinterpret_cast<uint4*>(my_row + v * 16) = *reinterpret_cast<uint4*>(o);
+  }
+  __syncwarp();
+  if constexpr (EPI == VB_EPI_ACCUM) {
+    if constexpr (sizeof(OutT) == 4) red_tile(stg, reinterpret_cast<float*>(p.D), p.ldd, m0, n0, p.M, p.N, lane);
+    __syncwarp();
     return;
   }
-  const bool use_bias = epi_uses_bias(e), use_aux = epi_uses_aux_in(e);
-  OutT* d = reinterpret_cast<OutT*>(p.D) + m * p.ldd + n0;
-  const OutT* ai = use_aux ? reinterpret_cast<const OutT*>(p.aux_in) + m * p.ld_aux + n0 : nullptr;
-  OutT* ao = (e == VB_EPI_BIAS_GELU) ? reinterpret_cast<OutT*>(p.aux_out) + m * p.ld_aux + n0 : nullptr;
+  if constexpr (EPI == VB_EPI_BIAS_GELU) {  // first the pre-activation (aux_out), then D = gelu(pre)
+    S::store_tile(stg, reinterpret_cast<OutT*>(p.aux_out), p.ld_aux, m0, n0, p.M, p.N, lane);
+    __syncwarp();
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {  // groups of 8 columns (16 B of bf16 / 32 B of fp32)
-    const int64_t n = n0 + g * 8;
-    if (n >= p.N) break;
-    const bool full = (n + 8 <= p.N);
-    float b[8], x[8], o[8], pre[8];
+    for (int v = 0; v < S::CW / S::EV; ++v) {
+      OutT o[S::EV];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { b[j] = 0.f; x[j] = 0.f; pre[j] = 0.f; }
-    if (use_bias) {
-      if (full) {
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-        b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
-      } else {
-        for (int j = 0; j < 8; ++j) if (n + j < p.N) b[j] = __ldg(p.bias + n + j);
-      }
+      for (int j = 0; j < S::EV; ++j) o[j] = from_f<OutT>(gelu_fast(acc[v * S::EV + j]));
+      *reinterpret_cast<uint4*>(my_row + v * 16) = *reinterpret_cast<uint4*>(o);
     }
-    if (use_aux) {
-      if (full) Vec8<OutT>::load(ai + g * 8, x);
-      else for (int j = 0; j < 8; ++j) if (n + j < p.N) x[j] = to_f<OutT>(ai[g * 8 + j]);
-    }
-    if (e == VB_EPI_BIAS_DROP_RES && p.drop_thresh != 0u && (p.N & 3) == 0) {
-      // vectorised dropout: one Philox block per 4 columns
+    __syncwarp();
+  }
+  S::store_tile(stg, reinterpret_cast<OutT*>(p.D), p.ldd, m0, n0, p.M, p.N, lane);
+  __syncwarp();
+}
+
+template <typename OutT, int BN, int EPI>
+__device__ __noinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, uint8_t* stg, int64_t m0, int64_t nb0,
+                                           int lane, bool active) {
+  using S = Stg<OutT>;
+#pragma unroll 1
+  for (int c = 0; c < BN / S::CW; ++c) {
+    const int64_t n0 = nb0 + c * S::CW;
+    if (n0 >= p.N) break;  // warp-uniform
+    float acc[S::CW];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        bool keep[4];
-        dropout_keep4(p.seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + h * 4), p.drop_thresh, keep);
+    for (int h = 0; h < S::NLD; ++h) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_acc + (uint32_t)(c * S::CW + h * 32), raw);
+      tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float v = __uint_as_float(acc[g * 8 + h * 4 + j]) * p.alpha + b[h * 4 + j];
-          o[h * 4 + j] = (keep[j] ? v * p.drop_scale : 0.0f) + x[h * 4 + j];
-        }
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = epilogue_scalar(p, __uint_as_float(acc[g * 8 + j]), b[j], x[j], m, n + j, pre[j]);
+      for (int j = 0; j < 32; ++j) acc[h * 32 + j] = __uint_as_float(raw[j]);
     }
-    if (full) {
-      Vec8<OutT>::store(d + g * 8, o);
-      if (ao) Vec8<OutT>::store(ao + g * 8, pre);
-    } else {
-      for (int j = 0; j < 8; ++j)
-        if (n + j < p.N) {
-          d[g * 8 + j] = from_f<OutT>(o[j]);
-          if (ao) ao[g * 8 + j] = from_f<OutT>(pre[j]);
-        }
-    }
+    if (active) epilogue_chunk<OutT, EPI>(p, acc, stg, m0, n0, lane);
+  }
+}
+
+template <typename OutT, int BN>
+__device__ __forceinline__ void epilogue_dispatch(const EpiParams& p, uint32_t tmem_acc, uint8_t* stg, int64_t m0,
+                                                  int64_t nb0, int lane, bool active) {
+  switch (p.epilogue) {
+#define VB_CASE(E) case E: epilogue_tile<OutT, BN, E>(p, tmem_acc, stg, m0, nb0, lane, active); break;
+    VB_CASE(VB_EPI_NONE) VB_CASE(VB_EPI_BIAS) VB_CASE(VB_EPI_BIAS_GELU) VB_CASE(VB_EPI_BIAS_RELU)
+    VB_CASE(VB_EPI_BIAS_DROP_RES) VB_CASE(VB_EPI_DGELU) VB_CASE(VB_EPI_ADD) VB_CASE(VB_EPI_DRELU)
+    VB_CASE(VB_EPI_BIAS_ADD)
+#undef VB_CASE
+    default: break;
   }
 }
 
@@ -216,7 +380,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024 B alignment
-  const uint32_t bars = smem_base + C::STAGES * C::STAGE_BYTES;
+  const uint32_t stg_u32 = smem_base + C::STAGES * C::STAGE_BYTES;
+  uint8_t* stg_base = smem_raw + (stg_u32 - smem_u32(smem_raw));
+  const uint32_t bars = stg_u32 + 4 * STG_WARP_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
@@ -316,20 +482,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tfull_bar(as), aphase);
       tcgen05_fence_after();
-      const int64_t m = (int64_t)m_blk * BM + ew * 32 + lane;
-      const bool row_ok = (m < p.epi.M) && (kb1 > kb0);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int64_t n0 = (int64_t)n_blk * BN + c * 32;
-        if (n0 >= p.epi.N) break;  // warp-uniform
-        uint32_t acc[32];
-        tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN + c * 32), acc);
-        tmem_ld_wait();
-        if (row_ok) {
-          if (p.epi.d_bf16) epilogue_chunk<bf16>(p.epi, acc, m, n0);
-          else epilogue_chunk<float>(p.epi, acc, m, n0);
-        }
-      }
+      const int64_t m0 = (int64_t)m_blk * BM + ew * 32;
+      const bool active = (m0 < p.epi.M) && (kb1 > kb0);  // warp-uniform
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+      uint8_t* stg = stg_base + ew * STG_WARP_BYTES;
+      if (p.epi.epilogue == VB_EPI_ACCUM) epilogue_tile<float, BN, VB_EPI_ACCUM>(p.epi, tmem_acc, stg, m0, (int64_t)n_blk * BN, lane, active);
+      else if (p.epi.d_bf16) epilogue_dispatch<bf16, BN>(p.epi, tmem_acc, stg, m0, (int64_t)n_blk * BN, lane, active);
+      else epilogue_dispatch<float, BN>(p.epi, tmem_acc, stg, m0, (int64_t)n_blk * BN, lane, active);
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));

@@ -31,6 +31,7 @@ _ACT_EPI = {"gelu": (EPI_BIAS_GELU, EPI_DGELU)}
 
 # counters the benchmark reads: kernels launched through the C ABI in this process
 launch_count = 0
+GEMM_TIMER = None  # set to a list by bench.py to time every GEMM launch with CUDA events
 
 
 def _count(n=1):
@@ -111,10 +112,22 @@ class Runtime:
         return self.store.g32(*ps)
 
     # kernels with launch accounting
-    def gemm(self, *a, **k):
+    def gemm(self, a, b, out, **k):
         _count()
         k.setdefault("backend", self.gemm_backend)
-        return ops.gemm(*a, **k)
+        if GEMM_TIMER is None:
+            return ops.gemm(a, b, out, **k)
+        # bench.py's roofline leg: CUDA events around every GEMM launch on the launching stream
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = ops.gemm(a, b, out, **k)
+        e1.record()
+        M = k.get("M") or (a.shape[0] if k.get("a_kmajor", True) else a.shape[1])
+        N = k.get("N") or (b.shape[0] if k.get("b_kmajor", True) else b.shape[1])
+        K = k.get("K") or (a.shape[1] if k.get("a_kmajor", True) else a.shape[0])
+        tc = ops.gemm_backend(a, b, out, **{kk: vv for kk, vv in k.items() if kk in ("a_kmajor", "b_kmajor", "epilogue", "backend")}) == _lib.GEMM_TC
+        GEMM_TIMER.append((2.0 * M * N * K, e0, e1, tc))
+        return r
 
 
 def model_store(model):
@@ -641,6 +654,8 @@ def bert_bwd(rt, bert, s, dx, dpooled_t, dpooled_v):
     if dpooled_v is not None and "v" in s["pool"]:
         pooled, a, _ = s["pool"]["v"]
         _pool_bwd(rt, bert.v_pooler, dpooled_v, pooled, a, dx.v, rt.V)
+    if hasattr(bert, "t_pooler"):
+        _notify_progress(rt, bert.t_pooler)
     for n in range(len(bert.encoder.layer) - 1, -1, -1):
         layer = bert.encoder.layer[n]
         if bert.encoder.num2type[n] == "attn":
@@ -648,6 +663,7 @@ def bert_bwd(rt, bert, s, dx, dpooled_t, dpooled_v):
         else:
             dx = ffn_bwd(rt, layer, dx, s["tape"][n])
         s["tape"][n] = None  # free activations as the backward retires them
+        _notify_progress(rt, layer)
     embeddings_bwd(rt, bert, dx, s["emb"])
 
 
@@ -860,6 +876,8 @@ class _PretrainFn(torch.autograd.Function):
                 ops.eltwise(ELT_COPY, g.reshape(1, 1).float(), dl[i:i + 1].view(1, 1))
                 _count()
         dx, dpt, dpv = heads_bwd(rt, model, ctx.s_heads, dl, ctx.x)
+        # head gradients are final (the tied decoder/embedding weight lives with the embeddings, at offset 0)
+        _notify_progress(rt, model.cls, skip_below=_frontier(rt.store, model.bert.encoder) or 0)
         bert_bwd(rt, model.bert, ctx.s_bert, dx, dpt, dpv)
         _notify_grads_ready(model)
         ctx.s_bert = ctx.s_heads = ctx.x = ctx.logits = None
@@ -867,6 +885,31 @@ class _PretrainFn(torch.autograd.Function):
 
 
 _GRAD_HOOKS = {}
+_PROGRESS_HOOKS = {}
+
+
+def register_progress_hook(model, fn):
+    """fn(frontier_offset): every gradient at flat offset >= frontier_offset is final (backward runs from the
+    heads towards the embeddings, i.e. from the end of the flat buffer to its start)."""
+    _PROGRESS_HOOKS[id(model)] = fn
+
+
+def _frontier(store, module, skip_below=0):
+    key = ("frontier", id(module), skip_below)
+    cache = store.__dict__.setdefault("_frontier_cache", {})
+    if key not in cache:
+        offs = [store.offsets[id(p)][0] for p in module.parameters() if store.offsets[id(p)][0] >= skip_below]
+        cache[key] = min(offs) if offs else None
+    return cache[key]
+
+
+def _notify_progress(rt, module, skip_below=0):
+    fn = _PROGRESS_HOOKS.get(id(rt.store.model))
+    if fn is None:
+        return
+    off = _frontier(rt.store, module, skip_below)
+    if off is not None:
+        fn(off)
 
 
 def register_grad_ready_hook(model, fn):

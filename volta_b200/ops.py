@@ -28,7 +28,7 @@ def _ptr(t):
 
 def _rows2d(t):
     """(rows, cols, ld) of a tensor viewed as a row-major matrix over its last dim."""
-    assert t.stride(-1) == 1, "innermost dimension must be contiguous"
+    assert t.stride(-1) == 1 or t.shape[-1] == 1, "innermost dimension must be contiguous"
     cols = t.shape[-1]
     rows = t.numel() // cols
     if t.dim() >= 2:
