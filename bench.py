@@ -267,7 +267,14 @@ def main():
         step(resident)
     torch.cuda.synchronize()
     recs, engine.GEMM_TIMER = engine.GEMM_TIMER, None
-    tc = [(f, a.elapsed_time(b)) for f, a, b, is_tc in recs if is_tc]
+    tc = [(f, a.elapsed_time(b)) for f, a, b, is_tc, *_ in recs if is_tc]
+    if os.environ.get("VOLTA_B200_BENCH_VERBOSE") and rank == 0:
+        agg = {}
+        for f, a, b, is_tc, shape in recs:
+            t = agg.setdefault((shape, is_tc), [0, 0.0, 0.0])
+            t[0] += 1; t[1] += a.elapsed_time(b); t[2] += f
+        for (shape, is_tc), (n, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            print("gemm %-44s tc=%d n=%3d  %8.3f ms  %7.1f TFLOP/s" % (shape, is_tc, n, ms, fl / ms / 1e9 if ms > 0 else 0), file=sys.stderr)
     pk = peaks()
     flops_tc, ms_tc = sum(f for f, _ in tc), sum(t for _, t in tc)
     achieved = flops_tc / (ms_tc * 1e-3) / 1e12 if ms_tc > 0 else 0.0

@@ -80,21 +80,31 @@ __device__ __forceinline__ float dgelu_erf(float x) {           // d/dx of the a
 // Fast erf for the tensor-core epilogues (Abramowitz & Stegun 7.1.26, |abs err| <= 1.5e-7 - far below bf16
 // resolution): one MUFU.RCP + one MUFU.EX2 + ~10 FMAs instead of erff()'s ~40-instruction polynomial, so the
 // GELU epilogue stays hidden under the MMA of the next tile.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 __device__ __forceinline__ float erf_fast(float x) {
   const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, ax, 1.0f));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = exp2f(-1.4426950408889634f * ax * ax);
+  const float e = ex2_approx(-1.4426950408889634f * ax * ax);
   const float r = 1.0f - poly * t * e;
   return copysignf(r, x);
 }
 __device__ __forceinline__ float gelu_fast(float x) { return x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float dgelu_fast(float x) {
   const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * exp2f(-0.72134752044448170368f * x * x);
+  const float pdf = 0.39894228040143267794f * ex2_approx(-0.72134752044448170368f * x * x);
   return fmaf(x, pdf, cdf);
 }
 

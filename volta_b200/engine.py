@@ -126,7 +126,8 @@ class Runtime:
         N = k.get("N") or (b.shape[0] if k.get("b_kmajor", True) else b.shape[1])
         K = k.get("K") or (a.shape[1] if k.get("a_kmajor", True) else a.shape[0])
         tc = ops.gemm_backend(a, b, out, **{kk: vv for kk, vv in k.items() if kk in ("a_kmajor", "b_kmajor", "epilogue", "backend")}) == _lib.GEMM_TC
-        GEMM_TIMER.append((2.0 * M * N * K, e0, e1, tc))
+        shape = "M%d N%d K%d a%d b%d epi%d" % (M, N, K, k.get("a_kmajor", True), k.get("b_kmajor", True), k.get("epilogue", 0))
+        GEMM_TIMER.append((2.0 * M * N * K, e0, e1, tc, shape))
         return r
 
 
