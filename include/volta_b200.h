@@ -72,10 +72,10 @@ int vb_sm_count(void);
 
 #define VB_EPI_NONE 0          /* D = acc                                    */
 #define VB_EPI_BIAS 1          /* D = acc + bias[n]                          */
-#define VB_EPI_BIAS_GELU 2     /* aux_out = acc + bias; D = gelu_erf(aux_out)  (encoders.py:136) */
+#define VB_EPI_BIAS_GELU 2     /* x = acc + bias; D = gelu_erf(x) (encoders.py:136); aux_out = gelu'(x) for the backward */
 #define VB_EPI_BIAS_RELU 3     /* D = relu(acc + bias)          (poolers, encoders.py:596-637)   */
 #define VB_EPI_BIAS_DROP_RES 4 /* D = dropout(acc + bias) + aux_in   (encoders.py:410-423, 552-565) */
-#define VB_EPI_DGELU 5         /* D = acc * gelu'(aux_in)                    */
+#define VB_EPI_MUL 5           /* D = acc * aux_in   (activation backward: aux_in = saved gelu'(x)) */
 #define VB_EPI_ADD 6           /* D = acc + aux_in                           */
 #define VB_EPI_DRELU 7         /* D = acc * (aux_in > 0)                     */
 #define VB_EPI_ACCUM 8         /* D += acc  (fp32 D, atomic; split-K allowed) */
@@ -92,11 +92,11 @@ typedef struct vb_gemm_args {
   int32_t backend;       /* VB_GEMM_* */
   const float* bias;     /* [N] fp32 or NULL */
   const void* aux_in;    /* [M, ld_aux] in d_dtype (residual / pre-activation) */
-  void* aux_out;         /* [M, ld_aux] in d_dtype (pre-activation for BIAS_GELU) */
+  void* aux_out;         /* [M, ld_aux] in d_dtype (activation derivative for BIAS_GELU) */
   int64_t ld_aux;
   float alpha;           /* scales acc before the epilogue (1.0 normally) */
   float dropout_p;       /* BIAS_DROP_RES only; 0 disables */
-  uint64_t seed, offset; /* Philox stream for the dropout mask: element index = m*N+n */
+  uint64_t seed, offset; /* counter-hash RNG stream for the dropout mask: element index = m*N+n */
   int32_t split_k;       /* ACCUM only: 0 = auto */
   int32_t reserved;
 } vb_gemm_args;
@@ -141,7 +141,7 @@ int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const flo
  * mask_t/mask_v are the 0/1 int32 padding masks [B,Lt] / [B,Lv].
  * lse_t/lse_v: [B, heads, L] fp32 row log-sum-exp saved for the backward,
  * which recomputes P from them (no probability tensor is stored).
- * dropout: Philox mask indexed by ((b*heads+h)*Lq_total + q)*Lk_total + k over the
+ * dropout: counter-hash mask indexed by ((b*heads+h)*Lq_total + q)*Lk_total + k over the
  * concatenated sequence [text; vision].
  */
 #define VB_ATTN_AUTO 0
@@ -176,7 +176,10 @@ int vb_attention_bwd(const vb_attn_args* args, void* stream);
  *   fp32 tables (word + position + token-type, volta/embeddings.py:55-65).  idx_j == NULL with
  *   table_j != NULL means a constant row `const_row_j` (VisualBERT's visual position / type rows,
  *   embeddings.py:352-386).  idx are int64 (loader dtype).  Output in `dtype`, stride ld_out.
- * vb_embed_gather_bwd: scatter-add of d_out rows into the fp32 table grads (atomic).
+ * vb_embed_gather_bwd: scatter-add of d_out rows into the fp32 table grads (atomic).  Rows whose index equals
+ *   skip_idx[j] get no gradient (nn.Embedding(padding_idx=0) of the word table, embeddings.py:46); -1 = none.
+ * vb_colsum_by_key: out[key[r], c] += a[r, c] for a handful of keys (token-type table gradient: 2-3 rows that
+ *   every token hits - done as per-block column sums instead of contended atomics).
  * vb_box_project: out[r,:] (+)= loc[r,0:nl] . W[:,0:nl]^T + b   - the K = num_locs (4/5)
  *   Linear of embeddings.py:135,141 done as FMAs; bwd accumulates dW, db.
  */
@@ -184,8 +187,10 @@ int vb_embed_gather_fwd(const float* const* tables, const int64_t* const* idx, c
                         int32_t n_tables, void* out, int64_t ld_out, int64_t rows, int32_t H, int32_t accum,
                         int32_t dtype, void* stream);
 int vb_embed_gather_bwd(float* const* dtables, const int64_t* const* idx, const int64_t* const_rows,
-                        int32_t n_tables, const void* dout, int64_t ld_dout, int64_t rows, int32_t H,
-                        int32_t dtype, void* stream);
+                        const int64_t* skip_idx, int32_t n_tables, const void* dout, int64_t ld_dout, int64_t rows,
+                        int32_t H, int32_t dtype, void* stream);
+int vb_colsum_by_key(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t cols, const int64_t* keys,
+                     int32_t nkeys, float* out, void* stream);
 int vb_box_project_fwd(const float* loc, int32_t nl, const float* W, const float* b, void* out, int64_t ld_out,
                        int64_t rows, int32_t H, int32_t accum, int32_t dtype, void* stream);
 int vb_box_project_bwd(const float* loc, int32_t nl, const void* dout, int64_t ld_dout, float* dW, float* db,
@@ -223,7 +228,7 @@ int vb_loss_finalize(const float* loss_sum, const float* count, float* out, int3
 #define VB_ELT_GELU 5
 #define VB_ELT_DGELU 6     /* out = a * gelu'(b)                                         */
 #define VB_ELT_SCALE 7     /* out = a * alpha                                            */
-#define VB_ELT_DROPOUT 8   /* out = a * mask / (1-p)      (Philox, index = element)      */
+#define VB_ELT_DROPOUT 8   /* out = a * mask / (1-p)      (counter hash, index = element) */
 #define VB_ELT_AXPY 9      /* out = out + alpha * a                                      */
 /* 2-D strided element-wise op over [rows, cols]; a/b/out may have different dtypes. */
 int vb_eltwise(int32_t op, const void* a, int32_t a_dtype, int64_t lda, const void* b, int32_t b_dtype,

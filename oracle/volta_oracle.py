@@ -73,7 +73,8 @@ def _text_sum(P, pre, ids, seg):
     """word + position + token-type (volta/embeddings.py:55-65)."""
     T = ids.shape[1]
     pos = torch.arange(T, device=ids.device)
-    return (P[pre + "word_embeddings.weight"][ids] + P[pre + "position_embeddings.weight"][pos][None]
+    # nn.Embedding(padding_idx=0): the padding row receives no gradient from the lookup (volta/embeddings.py:46)
+    return (F.embedding(ids, P[pre + "word_embeddings.weight"], padding_idx=0) + P[pre + "position_embeddings.weight"][pos][None]
             + P[pre + "token_type_embeddings.weight"][seg])
 
 
@@ -162,7 +163,7 @@ def embed_vlbert(P, cfg, ids, feat, loc, seg, train=False):
     if (pre + "visual_1x1_text.weight") in P:
         txt_vis = linear(txt_vis, P, pre + "visual_1x1_text")
     txt_vis = layer_norm(txt_vis, P[pre + "visual_ln_text.weight"], P[pre + "visual_ln_text.bias"])
-    txt = P[pre + "word_embeddings.weight"][ids] + txt_vis
+    txt = F.embedding(ids, P[pre + "word_embeddings.weight"], padding_idx=0) + txt_vis
     text_end = (ids != 0).sum(1, keepdim=True)                                     # :278-279
     # :285-287 - the reference adds K in place to an EXPANDED [1,T]->[B,T] view, so the shift lands in the one
     # shared row: position p moves by K for every sample as soon as p >= text_end of ANY sample (min over batch).

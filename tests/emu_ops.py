@@ -42,14 +42,14 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bia
         r = acc + bb
     elif epilogue == E.EPI_BIAS_GELU:
         pre = acc + bb
-        aux_out[:M, :N] = pre.to(aux_out.dtype)
+        aux_out[:M, :N] = _dgelu(pre).to(aux_out.dtype)
         r = _gelu(pre)
     elif epilogue == E.EPI_BIAS_RELU:
         r = torch.relu(acc + bb)
     elif epilogue == E.EPI_BIAS_DROP_RES:
         r = acc + bb + ai
-    elif epilogue == E.EPI_DGELU:
-        r = acc * _dgelu(ai)
+    elif epilogue == E.EPI_MUL:
+        r = acc * ai
     elif epilogue == E.EPI_ADD:
         r = acc + ai
     elif epilogue == E.EPI_DRELU:
@@ -166,13 +166,19 @@ def embed_gather_fwd(tables, idx, const_rows, out, accum=False):
     return out
 
 
-def embed_gather_bwd(dtables, idx, const_rows, dout):
+def colsum_by_key(a, keys, nkeys, out):
+    out.index_add_(0, keys, a.float())
+    return out
+
+
+def embed_gather_bwd(dtables, idx, const_rows, dout, skip=None):
     d = dout.float()
-    for t, i, c in zip(dtables, idx, const_rows):
+    skip = skip or [None] * len(dtables)
+    for t, i, c, sk in zip(dtables, idx, const_rows, skip):
         if t is None:
             continue
         if i is not None:
-            t.index_add_(0, i, d)
+            t.index_add_(0, i, d if sk is None else d * (i != sk)[:, None])
         else:
             t[c] += d.sum(0)
 
@@ -315,7 +321,7 @@ def fill(buf, value=0):
 
 _NAMES = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "embed_gather_fwd",
           "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd",
-          "loss_finalize", "eltwise", "colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill"]
+          "loss_finalize", "eltwise", "colsum", "colsum_by_key", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill"]
 
 
 def install(monkeypatch):

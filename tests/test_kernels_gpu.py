@@ -37,7 +37,7 @@ def test_gemm_forward_bias(backend, M, N, K):
     assert rel(out.float(), ref) < 6e-3
 
 
-@pytest.mark.parametrize("epi", ["none", "gelu", "relu", "res", "dgelu", "add", "drelu", "bias_add"])
+@pytest.mark.parametrize("epi", ["none", "gelu", "relu", "res", "mul", "add", "drelu", "bias_add"])
 @pytest.mark.parametrize("odt", [torch.bfloat16, torch.float32])
 def test_gemm_tc_epilogues(epi, odt):
     M, N, K = 260, 392, 256
@@ -46,7 +46,7 @@ def test_gemm_tc_epilogues(epi, odt):
     out, out_ref = torch.zeros(M, N, dtype=odt, device=DEV), torch.zeros(M, N, dtype=odt, device=DEV)
     pre, pre_ref = torch.zeros(M, N, dtype=odt, device=DEV), torch.zeros(M, N, dtype=odt, device=DEV)
     code = dict(none=_lib.EPI_NONE, gelu=_lib.EPI_BIAS_GELU, relu=_lib.EPI_BIAS_RELU, res=_lib.EPI_BIAS_DROP_RES,
-                dgelu=_lib.EPI_DGELU, add=_lib.EPI_ADD, drelu=_lib.EPI_DRELU, bias_add=_lib.EPI_BIAS_ADD)[epi]
+                mul=_lib.EPI_MUL, add=_lib.EPI_ADD, drelu=_lib.EPI_DRELU, bias_add=_lib.EPI_BIAS_ADD)[epi]
     kw = dict(epilogue=code, bias=bias, aux_in=aux)
     ops.gemm(a, w, out, aux_out=pre, backend=_lib.GEMM_TC, **kw)
     emu_ops.gemm(a, w, out_ref, aux_out=pre_ref, **kw)
@@ -267,6 +267,17 @@ def test_embed_gather_and_box(dtype):
     emu_ops.embed_gather_bwd(gr, idx, [0, 0, 1], dout)
     for a, b in zip(gt, gr):
         assert rel(a, b) < 1e-4
+    # padding row skipped (nn.Embedding(padding_idx)) + keyed column sums for the tiny token-type table
+    gt2, gr2 = torch.zeros_like(tabs[0]), torch.zeros_like(tabs[0])
+    skip_id = int(idx[0][0])
+    ops.embed_gather_bwd([gt2], [idx[0]], [0], dout, skip=[skip_id])
+    emu_ops.embed_gather_bwd([gr2], [idx[0]], [0], dout, skip=[skip_id])
+    assert rel(gt2, gr2) < 1e-4 and float(gt2[skip_id].abs().sum()) == 0.0
+    keys = torch.randint(0, 3, (rows,), generator=g).to(DEV)
+    kt, kr = torch.zeros(3, H, device=DEV), torch.zeros(3, H, device=DEV)
+    ops.colsum_by_key(dout, keys, 3, kt)
+    emu_ops.colsum_by_key(dout, keys, 3, kr)
+    assert rel(kt, kr) < 1e-4
     loc = torch.rand(rows, 5, generator=g).to(DEV)
     W, b = rnd(H, 5, dtype=torch.float32), rnd(H, dtype=torch.float32)
     o2, r2 = out.clone(), out.clone()

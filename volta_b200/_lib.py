@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libvolta_b200.so")
 F32, BF16 = 0, 1
 GEMM_AUTO, GEMM_TC, GEMM_SIMT = 0, 1, 2
 ATTN_AUTO, ATTN_MMA, ATTN_SIMT = 0, 1, 2
-(EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_DROP_RES, EPI_DGELU, EPI_ADD, EPI_DRELU, EPI_ACCUM,
+(EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_DROP_RES, EPI_MUL, EPI_ADD, EPI_DRELU, EPI_ACCUM,
  EPI_BIAS_ADD) = range(10)
 (ELT_COPY, ELT_ADD, ELT_MUL, ELT_RELU, ELT_DRELU, ELT_GELU, ELT_DGELU, ELT_SCALE, ELT_DROPOUT, ELT_AXPY) = range(10)
 
@@ -54,7 +54,8 @@ SIGNATURES = {
     "vb_attention_fwd": (_i32, [C.POINTER(AttnArgs), _vp]),
     "vb_attention_bwd": (_i32, [C.POINTER(AttnArgs), _vp]),
     "vb_embed_gather_fwd": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i32, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
-    "vb_embed_gather_bwd": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "vb_embed_gather_bwd": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "vb_colsum_by_key": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),
     "vb_box_project_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "vb_box_project_bwd": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp]),
     "vb_xent_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp]),

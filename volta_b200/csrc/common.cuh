@@ -101,6 +101,21 @@ __device__ __forceinline__ float erf_fast(float x) {
   const float r = 1.0f - poly * t * e;
   return copysignf(r, x);
 }
+// GELU and its derivative from shared intermediates (exp(-x^2/2) serves both erf and the Gaussian pdf):
+// 2 MUFU + ~16 FMA/ALU per element.
+__device__ __forceinline__ void gelu_fwd_grad_fast(float x, float& y, float& dy) {
+  const float az = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, az, 1.0f));
+  const float e = ex2_approx(-1.4426950408889634f * az * az);  // exp(-x^2/2)
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erfv = copysignf(1.0f - poly * t * e, x);
+  const float cdf = fmaf(0.5f, erfv, 0.5f);
+  y = x * cdf;
+  dy = fmaf(x, 0.39894228040143267794f * e, cdf);
+}
 __device__ __forceinline__ float gelu_fast(float x) { return x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float dgelu_fast(float x) {
   const float cdf = 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
@@ -119,39 +134,36 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ---- Philox4x32-10 counter RNG (dropout masks are regenerated, never stored) ---
-struct Philox {
-  static __device__ __forceinline__ uint4 gen(uint64_t seed, uint64_t ctr) {
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x1BD11BDAu, c3 = 0xA9FC1A22u;
-#pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-      const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-      const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-      c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
-      k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c0, c1, c2, c3);
-  }
-};
-// keep-probability test for one element: element index `idx` in a logical tensor.
-// 4 elements share one Philox block: block = idx >> 2, lane = idx & 3.
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, uint64_t idx, uint32_t thresh) {
-  uint4 r = Philox::gen(seed, offset + (idx >> 2));
-  const uint32_t lane = (uint32_t)idx & 3u;
-  const uint32_t v = lane == 0 ? r.x : lane == 1 ? r.y : lane == 2 ? r.z : r.w;
-  return v >= thresh;  // drop when v < p * 2^32
+// ---- counter-based dropout RNG (masks are regenerated in the backward, never stored) -----------------
+// One 32-bit hash (lowbias32 finaliser over a seeded multiply-mix of the 64-bit pair index) yields the keep
+// decisions of TWO consecutive elements, 16 bits each: ~5 integer instructions per element.  An earlier
+// version used Philox4x32-10 (~18 instructions per element): inside the GEMM epilogue and the LayerNorm
+// backward that made the dropout mask, not the tensor core or HBM, the bottleneck.
+__device__ __forceinline__ uint32_t rng_pair(uint64_t seed, uint64_t pair) {
+  const uint32_t lo = (uint32_t)pair, hi = (uint32_t)(pair >> 32);
+  uint32_t h = (lo * 0x9E3779B1u) ^ (uint32_t)seed;
+  h ^= (hi + (uint32_t)(seed >> 32)) * 0x85EBCA77u;
+  h ^= h >> 16; h *= 0x7FEB352Du;
+  h ^= h >> 15; h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
 }
+// threshold on 16 bits: drop when r16 < p * 65536
 __host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) {
-  double t = (double)p * 4294967296.0;
-  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+  const double t = (double)p * 65536.0 + 0.5;
+  return t >= 65535.0 ? 65535u : (uint32_t)t;
 }
-// keep flags for 4 consecutive elements starting at idx (idx % 4 == 0): one Philox call.
-__device__ __forceinline__ void dropout_keep4(uint64_t seed, uint64_t offset, uint64_t idx, uint32_t thresh,
-                                              bool (&keep)[4]) {
-  uint4 r = Philox::gen(seed, offset + (idx >> 2));
-  keep[0] = r.x >= thresh; keep[1] = r.y >= thresh; keep[2] = r.z >= thresh; keep[3] = r.w >= thresh;
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t offset, uint64_t idx, uint32_t thresh) {
+  idx += offset;
+  const uint32_t h = rng_pair(seed, idx >> 1);
+  const uint32_t r16 = (idx & 1) ? (h >> 16) : (h & 0xFFFFu);
+  return r16 >= thresh;
+}
+// keep flags for 2 consecutive elements starting at an EVEN index: one hash
+__device__ __forceinline__ void dropout_keep2(uint64_t seed, uint64_t offset, uint64_t idx, uint32_t thresh, bool& k0, bool& k1) {
+  const uint32_t h = rng_pair(seed, (idx + offset) >> 1);
+  k0 = (h & 0xFFFFu) >= thresh;
+  k1 = (h >> 16) >= thresh;
 }
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -17,6 +17,7 @@ struct GradTables {
   float* table[MAX_TABLES];
   const int64_t* idx[MAX_TABLES];
   int64_t const_row[MAX_TABLES];
+  int64_t skip[MAX_TABLES];
   int n;
 };
 
@@ -63,13 +64,35 @@ gather_bwd_kernel(GradTables t, const T* __restrict__ dout, int64_t ld, int64_t 
     Vec8<T>::load(dout + r * ld + c, v);
 #pragma unroll
     for (int j = 0; j < MAX_TABLES; ++j) {
-      if (j < t.n && t.table[j] != nullptr) {
+      if (j < t.n && t.table[j] != nullptr && dst[j] != t.skip[j]) {
         float* d = t.table[j] + dst[j] * H + c;
 #pragma unroll
         for (int k = 0; k < 8; ++k) atomicAdd(d + k, v[k]);
       }
     }
   }
+}
+
+// out[key[r], c] += a[r, c]: a thread owns a column and keeps one partial per key, so no atomics inside a block.
+template <typename T, int NK>
+__global__ void __launch_bounds__(256)
+colsum_by_key_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t cols, const int64_t* __restrict__ keys,
+                     int nkeys, float* __restrict__ out, int64_t rows_per_block) {
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  if (c >= cols) return;
+  float acc[NK];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) acc[k] = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const int key = (int)keys[r];
+    const float v = to_f<T>(a[r * lda + c]);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) acc[k] += (key == k) ? v : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < NK; ++k)
+    if (k < nkeys && acc[k] != 0.f) atomicAdd(out + (int64_t)k * cols + c, acc[k]);
 }
 
 template <typename T>
@@ -149,8 +172,9 @@ int vb_embed_gather_fwd(const float* const* tables, const int64_t* const* idx, c
   return vb::check_launch("embed_gather_fwd_kernel");
 }
 
-int vb_embed_gather_bwd(float* const* dtables, const int64_t* const* idx, const int64_t* const_rows, int32_t n_tables,
-                        const void* dout, int64_t ld_dout, int64_t rows, int32_t H, int32_t dtype, void* stream) {
+int vb_embed_gather_bwd(float* const* dtables, const int64_t* const* idx, const int64_t* const_rows,
+                        const int64_t* skip_idx, int32_t n_tables, const void* dout, int64_t ld_dout, int64_t rows,
+                        int32_t H, int32_t dtype, void* stream) {
   VB_REQUIRE(dtables && dout && n_tables >= 1 && n_tables <= vb::emb::MAX_TABLES, VB_ERR_ARG, "embed_gather_bwd: bad table list");
   VB_REQUIRE(H % 8 == 0 && vb::aligned16(dout) && (ld_dout % 8) == 0, VB_ERR_ARG, "embed_gather_bwd: H/ld must be multiples of 8");
   if (rows == 0) return 0;
@@ -160,6 +184,7 @@ int vb_embed_gather_bwd(float* const* dtables, const int64_t* const* idx, const 
     t.table[j] = dtables[j];  // may be NULL: that table gets no gradient (frozen)
     t.idx[j] = idx ? idx[j] : nullptr;
     t.const_row[j] = const_rows ? const_rows[j] : 0;
+    t.skip[j] = skip_idx ? skip_idx[j] : -1;
   }
   const unsigned grid = (unsigned)vb::ceil_div(rows, 8);
   if (dtype == VB_BF16)
@@ -167,6 +192,22 @@ int vb_embed_gather_bwd(float* const* dtables, const int64_t* const* idx, const 
   else
     vb::emb::gather_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(t, (const float*)dout, ld_dout, rows, H);
   return vb::check_launch("embed_gather_bwd_kernel");
+}
+
+int vb_colsum_by_key(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t cols, const int64_t* keys,
+                     int32_t nkeys, float* out, void* stream) {
+  VB_REQUIRE(a && keys && out && nkeys >= 1 && nkeys <= 4, VB_ERR_ARG, "colsum_by_key: needs 1..4 keys (got %d)", nkeys);
+  if (rows * cols == 0) return 0;
+  const int64_t strips = vb::ceil_div(cols, 256);
+  int64_t slabs = std::max<int64_t>(1, std::min<int64_t>(vb::ceil_div(rows, 32), (148 * 8) / strips));
+  const int64_t rpb = vb::ceil_div(rows, slabs);
+  slabs = vb::ceil_div(rows, rpb);
+  dim3 grid((unsigned)strips, (unsigned)slabs);
+  if (dtype == VB_BF16)
+    vb::emb::colsum_by_key_kernel<vb::bf16, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const vb::bf16*)a, lda, rows, cols, keys, nkeys, out, rpb);
+  else
+    vb::emb::colsum_by_key_kernel<float, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, rows, cols, keys, nkeys, out, rpb);
+  return vb::check_launch("colsum_by_key_kernel");
 }
 
 int vb_box_project_fwd(const float* loc, int32_t nl, const float* W, const float* b, void* out, int64_t ld_out,

@@ -15,7 +15,7 @@ struct EpiParams {
   int64_t M, N;
   float alpha;
   float drop_scale;      // 1/(1-p)
-  uint32_t drop_thresh;  // p * 2^32
+  uint32_t drop_thresh;  // p * 2^16
   uint64_t seed, offset;
   int32_t epilogue;      // VB_EPI_*
   int32_t d_bf16;        // 1: D/aux are bf16, 0: fp32
@@ -29,7 +29,7 @@ __device__ __forceinline__ float epilogue_scalar(const EpiParams& p, float acc, 
   switch (p.epilogue) {
     case VB_EPI_NONE: return acc;
     case VB_EPI_BIAS: return acc + bias;
-    case VB_EPI_BIAS_GELU: pre = acc + bias; return gelu_erf(pre);
+    case VB_EPI_BIAS_GELU: { const float x = acc + bias; pre = dgelu_erf(x); return gelu_erf(x); }
     case VB_EPI_BIAS_RELU: return fmaxf(acc + bias, 0.0f);
     case VB_EPI_BIAS_DROP_RES: {
       float v = acc + bias;
@@ -39,7 +39,7 @@ __device__ __forceinline__ float epilogue_scalar(const EpiParams& p, float acc, 
       }
       return v + aux;
     }
-    case VB_EPI_DGELU: return acc * dgelu_erf(aux);
+    case VB_EPI_MUL: return acc * aux;
     case VB_EPI_ADD: return acc + aux;
     case VB_EPI_DRELU: return aux > 0.0f ? acc : 0.0f;
     case VB_EPI_BIAS_ADD: return acc + bias + aux;
@@ -52,7 +52,7 @@ __host__ __device__ __forceinline__ bool epi_uses_bias(int e) {
          e == VB_EPI_BIAS_ADD;
 }
 __host__ __device__ __forceinline__ bool epi_uses_aux_in(int e) {
-  return e == VB_EPI_BIAS_DROP_RES || e == VB_EPI_DGELU || e == VB_EPI_ADD || e == VB_EPI_DRELU ||
+  return e == VB_EPI_BIAS_DROP_RES || e == VB_EPI_MUL || e == VB_EPI_ADD || e == VB_EPI_DRELU ||
          e == VB_EPI_BIAS_ADD;
 }
 

@@ -229,10 +229,6 @@ __device__ __forceinline__ void red_tile(const uint8_t* stg, float* g, int64_t l
   }
 }
 
-// Out-of-line Philox: the epilogue is fully unrolled over its row, and ten inlined rounds per 4 columns would
-// push the loop body out of the instruction cache (an earlier version of this epilogue was 95 % stall_no_inst).
-__device__ __noinline__ uint4 philox_block(uint64_t seed, uint64_t ctr) { return Philox::gen(seed, ctr); }
-
 // One chunk (CW columns) of one warp's 32 rows.  `acc` holds this thread's row: CW fp32 accumulators.
 // EPI is a compile-time constant: the epilogue kind is dispatched ONCE per tile, never per element.
 template <typename OutT, int EPI>
@@ -241,7 +237,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, float (&acc)[
   using S = Stg<OutT>;
   constexpr bool use_bias = EPI == VB_EPI_BIAS || EPI == VB_EPI_BIAS_GELU || EPI == VB_EPI_BIAS_RELU ||
                             EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_BIAS_ADD;
-  constexpr bool use_aux = EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_DGELU || EPI == VB_EPI_ADD ||
+  constexpr bool use_aux = EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_MUL || EPI == VB_EPI_ADD ||
                            EPI == VB_EPI_DRELU || EPI == VB_EPI_BIAS_ADD;
   uint8_t* my_row = stg + lane * STG_PITCH;
   const int64_t m = m0 + lane;
@@ -278,10 +274,10 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, float (&acc)[
     for (int j = 0; j < S::EV; ++j) {
       float a = acc[v * S::EV + j] * p.alpha;
       if constexpr (EPI == VB_EPI_BIAS) a = a + b[j];
-      else if constexpr (EPI == VB_EPI_BIAS_GELU) a = a + b[j];            // pre-activation; GELU in the 2nd pass
+      else if constexpr (EPI == VB_EPI_BIAS_GELU) a = a + b[j];            // pre-activation; GELU + GELU' below
       else if constexpr (EPI == VB_EPI_BIAS_RELU) a = fmaxf(a + b[j], 0.f);
       else if constexpr (EPI == VB_EPI_BIAS_DROP_RES) a = a + b[j];        // mask + residual below
-      else if constexpr (EPI == VB_EPI_DGELU) a = a * dgelu_fast(x[j]);
+      else if constexpr (EPI == VB_EPI_MUL) a = a * x[j];
       else if constexpr (EPI == VB_EPI_ADD) a = a + x[j];
       else if constexpr (EPI == VB_EPI_DRELU) a = x[j] > 0.f ? a : 0.f;
       else if constexpr (EPI == VB_EPI_BIAS_ADD) a = a + b[j] + x[j];
@@ -289,29 +285,36 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, float (&acc)[
     }
     if constexpr (EPI == VB_EPI_BIAS_DROP_RES) {
       if (p.drop_thresh != 0u) {
-        if ((p.N & 3) == 0) {  // one Philox block per 4 consecutive columns
+        if ((p.N & 1) == 0) {  // one hash per 2 consecutive columns
 #pragma unroll
-          for (int h = 0; h < S::EV; h += 4) {
-            const uint64_t idx = (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + h);
-            const uint4 r = philox_block(p.seed, p.offset + (idx >> 2));
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              acc[v * S::EV + h + j] = rr[j] >= p.drop_thresh ? acc[v * S::EV + h + j] * p.drop_scale : 0.f;
+          for (int h = 0; h < S::EV; h += 2) {
+            bool k0, k1;
+            dropout_keep2(p.seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + h), p.drop_thresh, k0, k1);
+            acc[v * S::EV + h] = k0 ? acc[v * S::EV + h] * p.drop_scale : 0.f;
+            acc[v * S::EV + h + 1] = k1 ? acc[v * S::EV + h + 1] * p.drop_scale : 0.f;
           }
         } else {
 #pragma unroll
-          for (int j = 0; j < S::EV; ++j) {
-            const uint64_t idx = (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + j);
-            const uint4 r = philox_block(p.seed, p.offset + (idx >> 2));
-            const uint32_t lane4 = (uint32_t)idx & 3u;
-            const uint32_t rv = lane4 == 0 ? r.x : lane4 == 1 ? r.y : lane4 == 2 ? r.z : r.w;
-            acc[v * S::EV + j] = rv >= p.drop_thresh ? acc[v * S::EV + j] * p.drop_scale : 0.f;
-          }
+          for (int j = 0; j < S::EV; ++j)
+            acc[v * S::EV + j] = dropout_keep(p.seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + j), p.drop_thresh)
+                                     ? acc[v * S::EV + j] * p.drop_scale : 0.f;
         }
       }
 #pragma unroll
       for (int j = 0; j < S::EV; ++j) acc[v * S::EV + j] += x[j];
+    }
+    if constexpr (EPI == VB_EPI_BIAS_GELU) {
+      // stage gelu'(x) first (aux_out), keep gelu(x) in the accumulator registers for the second store pass
+      OutT g[S::EV];
+#pragma unroll
+      for (int j = 0; j < S::EV; ++j) {
+        float y, dy;
+        gelu_fwd_grad_fast(acc[v * S::EV + j], y, dy);
+        acc[v * S::EV + j] = y;
+        g[j] = from_f<OutT>(dy);
+      }
+      *reinterpret_cast<uint4*>(my_row + v * 16) = *reinterpret_cast<uint4*>(g);
+      continue;
     }
     OutT o[S::EV];
 #pragma unroll
@@ -324,14 +327,14 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& p, float (&acc)[
     __syncwarp();
     return;
   }
-  if constexpr (EPI == VB_EPI_BIAS_GELU) {  // first the pre-activation (aux_out), then D = gelu(pre)
+  if constexpr (EPI == VB_EPI_BIAS_GELU) {  // first the derivative (aux_out), then D = gelu(x)
     S::store_tile(stg, reinterpret_cast<OutT*>(p.aux_out), p.ld_aux, m0, n0, p.M, p.N, lane);
     __syncwarp();
 #pragma unroll
     for (int v = 0; v < S::CW / S::EV; ++v) {
       OutT o[S::EV];
 #pragma unroll
-      for (int j = 0; j < S::EV; ++j) o[j] = from_f<OutT>(gelu_fast(acc[v * S::EV + j]));
+      for (int j = 0; j < S::EV; ++j) o[j] = from_f<OutT>(acc[v * S::EV + j]);
       *reinterpret_cast<uint4*>(my_row + v * 16) = *reinterpret_cast<uint4*>(o);
     }
     __syncwarp();
@@ -367,7 +370,7 @@ __device__ __forceinline__ void epilogue_dispatch(const EpiParams& p, uint32_t t
   switch (p.epilogue) {
 #define VB_CASE(E) case E: epilogue_tile<OutT, BN, E>(p, tmem_acc, stg, m0, nb0, lane, active); break;
     VB_CASE(VB_EPI_NONE) VB_CASE(VB_EPI_BIAS) VB_CASE(VB_EPI_BIAS_GELU) VB_CASE(VB_EPI_BIAS_RELU)
-    VB_CASE(VB_EPI_BIAS_DROP_RES) VB_CASE(VB_EPI_DGELU) VB_CASE(VB_EPI_ADD) VB_CASE(VB_EPI_DRELU)
+    VB_CASE(VB_EPI_BIAS_DROP_RES) VB_CASE(VB_EPI_MUL) VB_CASE(VB_EPI_ADD) VB_CASE(VB_EPI_DRELU)
     VB_CASE(VB_EPI_BIAS_ADD)
 #undef VB_CASE
     default: break;

@@ -136,11 +136,11 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
           if (dx_drop != nullptr) {
             float od[8];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              bool keep[4];
-              dropout_keep4(seed, offset, (uint64_t)row * (uint64_t)H + (uint64_t)(c + h * 4), drop_thresh, keep);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) od[h * 4 + j] = keep[j] ? o[h * 4 + j] * drop_scale : 0.f;
+            for (int h = 0; h < 8; h += 2) {
+              bool k0, k1;
+              dropout_keep2(seed, offset, (uint64_t)row * (uint64_t)H + (uint64_t)(c + h), drop_thresh, k0, k1);
+              od[h] = k0 ? o[h] * drop_scale : 0.f;
+              od[h + 1] = k1 ? o[h + 1] * drop_scale : 0.f;
             }
             Vec8<T>::store(dx_drop + row * H + c, od);
             // the bias gradient sees what the dense layer's output gradient is: the rounded, masked copy

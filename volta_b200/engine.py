@@ -21,13 +21,12 @@ import torch
 
 from . import _lib, ops
 from ._lib import (EPI_ACCUM, EPI_ADD, EPI_BIAS, EPI_BIAS_ADD, EPI_BIAS_DROP_RES, EPI_BIAS_GELU, EPI_BIAS_RELU,
-                   EPI_DGELU, EPI_DRELU, EPI_NONE, ELT_ADD, ELT_COPY, ELT_DGELU, ELT_DRELU, ELT_DROPOUT, ELT_GELU,
+                   EPI_DRELU, EPI_MUL, EPI_NONE, ELT_ADD, ELT_COPY, ELT_DGELU, ELT_DRELU, ELT_DROPOUT, ELT_GELU,
                    ELT_MUL, ELT_RELU)
 from .losses import pre_vis_targets
 from .store import ParamStore
 
 LN_EPS = 1e-12
-_ACT_EPI = {"gelu": (EPI_BIAS_GELU, EPI_DGELU)}
 
 # counters the benchmark reads: kernels launched through the C ABI in this process
 launch_count = 0
@@ -275,7 +274,9 @@ def attention_fwd(rt, layer, x, masks):
     seed = rt.seed() if (p_t > 0 or p_v > 0) else 0
     cross = sa.has_tv or sa.has_vt
     calls = []
-    if cross or joint or not (sa.has_text and sa.has_vision):
+    same_heads = (sa.num_attention_heads == sa.v_num_attention_heads and sa.attention_head_size == sa.v_attention_head_size)
+    if cross or joint or not (sa.has_text and sa.has_vision) or same_heads:
+        # one launch covers both streams; disabled (query, key) blocks are skipped inside the kernel
         calls.append((sa.pair_mask, qkv.get("t"), qkv.get("v"), heads, d))
     else:
         # independent self-attentions (tt + vv): the streams may even differ in head size (vilbert_base)
@@ -348,7 +349,7 @@ def attention_bwd(rt, layer, dy, s):
 
 def _act_epilogues(name):
     if name == "gelu":
-        return EPI_BIAS_GELU, EPI_DGELU
+        return EPI_BIAS_GELU, EPI_MUL  # the forward epilogue saves gelu'(x); the backward epilogue multiplies by it
     if name == "relu":
         return EPI_BIAS_RELU, EPI_DRELU
     raise NotImplementedError("hidden_act=%r: the shipped configs use 'gelu'; 'relu' is supported, 'swish' is not" % (name,))
@@ -435,6 +436,7 @@ def _to_compute(rt, feat):
 
 
 def _text_gather(rt, emb, ids, seg, out, pos_offset=0):
+    rt._pos_offset = pos_offset
     idx = [ids.reshape(-1), _pos_ids(rt, pos_offset), seg.reshape(-1)]
     tables = [emb.word_embeddings.weight, emb.position_embeddings.weight, emb.token_type_embeddings.weight]
     ops.embed_gather_fwd([rt.w32(t) for t in tables], idx, [0, 0, 0], out)
@@ -443,9 +445,22 @@ def _text_gather(rt, emb, ids, seg, out, pos_offset=0):
 
 
 def _text_gather_bwd(rt, saved, dout):
+    """Scatter of the embedding-sum gradient.  Word rows: atomics (the padding row gets none, as with
+    nn.Embedding(padding_idx=0)); positions: every sample hits the same T rows, so their gradient is a column sum
+    of dout viewed as [B, T*H]; token types: 2-3 rows hit by every token -> per-key column sums."""
     tables, idx = saved
-    ops.embed_gather_bwd([rt.g32(t) for t in tables], idx, [0] * len(tables), dout)
-    _count()
+    word, pos, typ = tables
+    H = dout.shape[1]
+    ops.embed_gather_bwd([rt.g32(word)], [idx[0]], [0], dout, skip=[0])
+    gpos = rt.g32(pos)
+    off = rt._pos_offset
+    ops.colsum(dout.view(rt.B, rt.T * H), gpos[off:off + rt.T].view(-1))
+    ntypes = typ.shape[0]
+    if ntypes <= 4:
+        ops.colsum_by_key(dout, idx[2], ntypes, rt.g32(typ))
+    else:
+        ops.embed_gather_bwd([rt.g32(typ)], [idx[2]], [0], dout)
+    _count(3)
 
 
 def _region_proj_fwd(rt, lin, feat_c, out):
@@ -691,7 +706,7 @@ def _transform_bwd(rt, tr, dy, saved, dx_out, accumulate_dx=False):
     _, epi_b = _act_epilogues(tr.hidden_act)
     dh = ln_bwd(rt, dy, h, stats, tr.LayerNorm) if stats is not None else dy
     dpre = rt.empty(*dh.shape)
-    ops.eltwise(ELT_DGELU if epi_b == EPI_DGELU else ELT_DRELU, dh, dpre, b=pre)
+    ops.eltwise(ELT_MUL if epi_b == EPI_MUL else ELT_DRELU, dh, dpre, b=pre)
     _count()
     if accumulate_dx:
         linear_bwd(rt, x, dpre, tr.dense, dx_epilogue=EPI_ADD, dx_out=dx_out, aux_in=dx_out)

@@ -172,10 +172,19 @@ def embed_gather_fwd(tables, idx, const_rows, out, accum=False):
     return out
 
 
-def embed_gather_bwd(dtables, idx, const_rows, dout):
+def embed_gather_bwd(dtables, idx, const_rows, dout, skip=None):
     rows, H, ld = _rows2d(dout)
     n, tp, ip, cr = _table_arrays(dtables, idx, const_rows)
-    _lib.call("vb_embed_gather_bwd", tp, ip, cr, n, dout.data_ptr(), ld, rows, H, dt(dout), _stream())
+    sk = (C.c_int64 * n)(*[int(-1 if skip is None or s is None else s) for s in (skip or [None] * n)])
+    _lib.call("vb_embed_gather_bwd", tp, ip, cr, sk, n, dout.data_ptr(), ld, rows, H, dt(dout), _stream())
+
+
+def colsum_by_key(a, keys, nkeys, out):
+    """out[keys[r], :] += a[r, :] for nkeys <= 4 distinct keys (fp32 out [nkeys, cols])."""
+    rows, cols, lda = _rows2d(a)
+    assert keys.dtype == torch.int64 and keys.numel() == rows and out.dtype == torch.float32
+    _lib.call("vb_colsum_by_key", a.data_ptr(), dt(a), lda, rows, cols, keys.data_ptr(), nkeys, out.data_ptr(), _stream())
+    return out
 
 
 def box_project_fwd(loc, W, b, out, accum=False):
