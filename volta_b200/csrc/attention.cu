@@ -307,7 +307,7 @@ __device__ __forceinline__ void load_rows(bf16* dst, const P& p, const Geo& g, i
 }
 
 template <int D, int MAXKB>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (D == 64 && MAXKB <= 6) ? 4 : 2)
 mma_fwd_kernel(P p) {
   extern __shared__ __align__(16) uint8_t smraw[];
   using TL = Tile<D>;
@@ -446,7 +446,7 @@ mma_fwd_kernel(P p) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, D == 64 ? 4 : 2)
 mma_bwd_kernel(P p) {
   extern __shared__ __align__(16) uint8_t smraw[];
   using TL = Tile<D>;

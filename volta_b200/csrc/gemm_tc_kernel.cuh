@@ -1,0 +1,612 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:  D[M,N] = epilogue( A . B^T ), bf16 operands, fp32 accumulation.
+//
+// One persistent, warp-specialised kernel serves nn.Linear forward, dgrad and wgrad
+// (volta/encoders.py:204-206,376,463,518 ... and their autograd):
+//   warp 0   : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier expect_tx)
+//   warp 1   : MMA issuer     (one lane issues tcgen05.mma 128 x BN x 16, accumulators in TMEM)
+//   warp 2   : TMEM allocator
+//   warps 4-11: epilogue      (tcgen05.ld 32x32b -> bias/GELU/dropout/residual/... -> smem staging -> global)
+// The TMEM accumulator is double buffered (2 x BN columns) so the epilogue of tile i overlaps the
+// MMAs of tile i+1.  Eight epilogue warps (two per TMEM lane quarter, alternating 32-column chunks) keep two
+// warps on every SM sub-partition so the epilogue's shared-memory / TMEM / global latencies overlap.
+// BN = 192 divides every hidden width of the model (768, 2304, 3072) and gives 72*4 = 288 tiles for a
+// [9216 x 768] output: 1.95 waves on 148 SMs instead of 1.46 with BN = 256.  Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]);
+// the latter is what dgrad (B = W[out,in]) and wgrad (A = dY, B = X) need, and is expressed purely
+// through the shared-memory matrix descriptors - no transposed copies are ever made.
+#pragma once
+#include <cuda.h>
+
+#include <mutex>
+
+#include "gemm_common.cuh"
+
+namespace vb {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 64;               // 64 bf16 = 128 B = one swizzle-128B row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 384;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int EPI_WARP0 = 4;
+constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr uint32_t MN_BLOCK_BYTES = 64 * BK * 2;  // one 64(mn) x 64(k) MN-major TMA box = 8 KB
+
+template <int BN> struct Cfg {
+  static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static_assert(BN == 128 || BN == 192, "tile widths: 128 or 192 columns");
+  static constexpr int STAGES = (BN == 192) ? 4 : 5;            // 160 KB of operand ring either way
+  static constexpr uint32_t TMEM_COLS = (BN == 192) ? 512 : 256;  // 2 accumulator stages, power of two
+  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
+                                       NUM_EPI_WARPS * 4608 /*epilogue staging*/ + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+};
+
+struct Params {
+  EpiParams epi;
+  int32_t num_m_blocks, num_n_blocks;
+  int32_t kb_total, kb_per_split, split_k;
+  int32_t a_kmajor, b_kmajor;
+  uint32_t idesc;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("volta_b200 gemm_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <uint32_t COLS> __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <uint32_t COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// mbarrier arrives when all tcgen05.mma issued so far by this thread have completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B.
+//   K-major : rows of 128 B (64 bf16 of K); 8-row groups SBO = 1024 B apart; LBO unused.
+//   MN-major: rows of 128 B (64 bf16 of M/N) per K index; 8-K groups SBO = 1024 B apart;
+//             successive 64-element M/N blocks LBO = 8192 B apart (one TMA box each).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool kmajor) {
+  const uint64_t lbo = kmajor ? 1ull : (uint64_t)(MN_BLOCK_BYTES >> 4);
+  const uint64_t sbo = 1024ull >> 4;
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// ---- epilogue ---------------------------------------------------------------------------------
+// Each epilogue warp owns 32 accumulator rows (its TMEM lane quarter) and every other 32-column chunk.
+// tcgen05.ld hands every thread ONE row, so writing straight from registers would touch 32 different cache lines
+// per store instruction.  Instead the warp goes through a private, padded shared-memory staging tile
+// (32 rows x 32 columns) so that every global load / store / red instruction covers whole 64/128-byte row
+// segments: residual / activation-derivative reads, D writes and the split-K fp32 reductions are coalesced.
+constexpr uint32_t STG_WARP_BYTES = 4608;  // 32 rows x 144 B (fp32 chunk); bf16 chunks use 32 x 80 B of it
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <typename OutT> struct Stg {
+  static constexpr int CW = 32;                          // columns per chunk = one tcgen05.ld.x32
+  static constexpr int EV = 16 / (int)sizeof(OutT);      // elements per 16-byte vector (8 bf16 / 4 fp32)
+  static constexpr int VPR = CW / EV;                    // vectors per staged row (4 / 8)
+  static constexpr int RPI = 32 / VPR;                   // rows covered by one warp-wide 16 B access (8 / 4)
+  static constexpr int ITERS = 32 / RPI;                 // accesses per tile (4 / 8)
+  static constexpr uint32_t PITCH = CW * sizeof(OutT) + 16;  // 80 B / 144 B: conflict-free for both access patterns
+
+  // coalesced global -> registers (rows of this warp; zero fill out of range)
+  static __device__ __forceinline__ void load_regs(uint4 (&r)[ITERS], const OutT* g, int64_t ld, int64_t m0, int64_t n0,
+                                                   int64_t M, int64_t N, int lane) {
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int row = i * RPI + lane / VPR, v = lane % VPR;
+      const int64_t m = m0 + row, n = n0 + v * EV;
+      uint4 val = make_uint4(0u, 0u, 0u, 0u);
+      if (m < M) {
+        const OutT* src = g + m * ld + n;
+        if (n + EV <= N) {
+          val = *reinterpret_cast<const uint4*>(src);
+        } else if (n < N) {
+          OutT tmp[EV];
+#pragma unroll
+          for (int j = 0; j < EV; ++j) tmp[j] = (n + j < N) ? src[j] : from_f<OutT>(0.f);
+          val = *reinterpret_cast<uint4*>(tmp);
+        }
+      }
+      r[i] = val;
+    }
+  }
+  static __device__ __forceinline__ void regs_to_stage(const uint4 (&r)[ITERS], uint8_t* stg, int lane) {
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i)
+      *reinterpret_cast<uint4*>(stg + (i * RPI + lane / VPR) * PITCH + (lane % VPR) * 16) = r[i];
+  }
+  // coalesced staging -> global store
+  static __device__ __forceinline__ void store_tile(const uint8_t* stg, OutT* g, int64_t ld, int64_t m0, int64_t n0,
+                                                    int64_t M, int64_t N, int lane) {
+#pragma unroll
+    for (int i = 0; i < ITERS; ++i) {
+      const int row = i * RPI + lane / VPR, v = lane % VPR;
+      const int64_t m = m0 + row, n = n0 + v * EV;
+      if (m < M && n < N) {
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + row * PITCH + v * 16);
+        OutT* dst = g + m * ld + n;
+        if (n + EV <= N) {
+          *reinterpret_cast<uint4*>(dst) = val;
+        } else {
+          const OutT* tmp = reinterpret_cast<const OutT*>(&val);
+#pragma unroll
+          for (int j = 0; j < EV; ++j) if (n + j < N) dst[j] = tmp[j];
+        }
+      }
+    }
+  }
+};
+
+// coalesced staging -> global fp32 reduction (split-K / shared-weight accumulation)
+__device__ __forceinline__ void red_tile(const uint8_t* stg, float* g, int64_t ld, int64_t m0, int64_t n0, int64_t M,
+                                         int64_t N, int lane) {
+  using S = Stg<float>;
+#pragma unroll
+  for (int i = 0; i < S::ITERS; ++i) {
+    const int row = i * S::RPI + lane / S::VPR, v = lane % S::VPR;
+    const int64_t m = m0 + row, n = n0 + v * 4;
+    if (m < M && n < N) {
+      const float4 val = *reinterpret_cast<const float4*>(stg + row * S::PITCH + v * 16);
+      float* dst = g + m * ld + n;
+      if (n + 4 <= N && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+        red_add_v4(dst, val.x, val.y, val.z, val.w);
+      } else {
+        const float t[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (n + j < N) atomicAdd(dst + j, t[j]);
+      }
+    }
+  }
+}
+
+// All chunks of one tile that belong to this warp.  EPI is a compile-time constant: the epilogue kind is
+// dispatched ONCE per tile (a per-element switch made the unrolled body overflow the instruction cache).
+template <typename OutT, int BN, int EPI>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, uint8_t* stg, int64_t m0, int64_t nb0,
+                                           int lane, int group, const float* bias_s) {
+  using S = Stg<OutT>;
+  constexpr bool use_bias = EPI == VB_EPI_BIAS || EPI == VB_EPI_BIAS_GELU || EPI == VB_EPI_BIAS_RELU ||
+                            EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_BIAS_ADD;
+  constexpr bool use_aux = EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_MUL || EPI == VB_EPI_ADD ||
+                           EPI == VB_EPI_DRELU || EPI == VB_EPI_BIAS_ADD;
+  constexpr int NCH = BN / S::CW;
+  uint8_t* my_row = stg + lane * S::PITCH;
+  const int64_t m = m0 + lane;
+  const OutT* aux = reinterpret_cast<const OutT*>(p.aux_in);
+  uint4 pre[S::ITERS];
+  if constexpr (use_aux) {
+    if (nb0 + group * S::CW < p.N) S::load_regs(pre, aux, p.ld_aux, m0, nb0 + group * S::CW, p.M, p.N, lane);
+  }
+#pragma unroll 1
+  for (int c = group; c < NCH; c += 2) {
+    const int64_t n0 = nb0 + c * S::CW;
+    if (n0 >= p.N) break;  // warp-uniform
+    uint32_t raw[32];
+    tmem_ld32(tmem_acc + (uint32_t)(c * S::CW), raw);
+    if constexpr (use_aux) {
+      S::regs_to_stage(pre, stg, lane);
+      __syncwarp();
+      // prefetch the next chunk's residual / derivative tile while this chunk is processed
+      if (c + 2 < NCH && n0 + 2 * S::CW < p.N) S::load_regs(pre, aux, p.ld_aux, m0, n0 + 2 * S::CW, p.M, p.N, lane);
+    }
+    tmem_ld_wait();
+    float acc[S::CW];
+#pragma unroll
+    for (int j = 0; j < S::CW; ++j) acc[j] = __uint_as_float(raw[j]) * p.alpha;
+#pragma unroll
+    for (int v = 0; v < S::VPR; ++v) {
+      const int64_t n = n0 + v * S::EV;
+      float b[S::EV], x[S::EV];
+#pragma unroll
+      for (int j = 0; j < S::EV; ++j) { b[j] = 0.f; x[j] = 0.f; }
+      if constexpr (use_bias) {  // this tile's bias slice was staged in shared memory (zero beyond N): broadcast reads
+#pragma unroll
+        for (int j = 0; j < S::EV; j += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(bias_s + c * S::CW + v * S::EV + j);
+          b[j] = t.x; b[j + 1] = t.y; b[j + 2] = t.z; b[j + 3] = t.w;
+        }
+      }
+      if constexpr (use_aux) {
+        uint4 rawx = *reinterpret_cast<const uint4*>(my_row + v * 16);
+        const OutT* t = reinterpret_cast<const OutT*>(&rawx);
+#pragma unroll
+        for (int j = 0; j < S::EV; ++j) x[j] = to_f<OutT>(t[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < S::EV; ++j) {
+        float a = acc[v * S::EV + j];
+        if constexpr (EPI == VB_EPI_BIAS || EPI == VB_EPI_BIAS_GELU || EPI == VB_EPI_BIAS_DROP_RES) a = a + b[j];
+        else if constexpr (EPI == VB_EPI_BIAS_RELU) a = fmaxf(a + b[j], 0.f);
+        else if constexpr (EPI == VB_EPI_MUL) a = a * x[j];
+        else if constexpr (EPI == VB_EPI_ADD) a = a + x[j];
+        else if constexpr (EPI == VB_EPI_DRELU) a = x[j] > 0.f ? a : 0.f;
+        else if constexpr (EPI == VB_EPI_BIAS_ADD) a = a + b[j] + x[j];
+        acc[v * S::EV + j] = a;
+      }
+      if constexpr (EPI == VB_EPI_BIAS_DROP_RES) {
+        if (p.drop_thresh != 0u) {
+          if ((p.N & 1) == 0) {  // one hash per 2 consecutive columns
+#pragma unroll
+            for (int h = 0; h < S::EV; h += 2) {
+              bool k0, k1;
+              dropout_keep2(p.seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + h), p.drop_thresh, k0, k1);
+              acc[v * S::EV + h] = k0 ? acc[v * S::EV + h] * p.drop_scale : 0.f;
+              acc[v * S::EV + h + 1] = k1 ? acc[v * S::EV + h + 1] * p.drop_scale : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < S::EV; ++j)
+              acc[v * S::EV + j] = dropout_keep(p.seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + j), p.drop_thresh)
+                                       ? acc[v * S::EV + j] * p.drop_scale : 0.f;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < S::EV; ++j) acc[v * S::EV + j] += x[j];
+      }
+      OutT o[S::EV];
+      if constexpr (EPI == VB_EPI_BIAS_GELU) {
+        // stage gelu'(x) first (aux_out); gelu(x) stays in the accumulator registers for the second store pass
+#pragma unroll
+        for (int j = 0; j < S::EV; ++j) {
+          float y, dy;
+          gelu_fwd_grad_fast(acc[v * S::EV + j], y, dy);
+          acc[v * S::EV + j] = y;
+          o[j] = from_f<OutT>(dy);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < S::EV; ++j) o[j] = from_f<OutT>(acc[v * S::EV + j]);
+      }
+      *reinterpret_cast<uint4*>(my_row + v * 16) = *reinterpret_cast<uint4*>(o);
+    }
+    __syncwarp();
+    if constexpr (EPI == VB_EPI_ACCUM) {
+      if constexpr (sizeof(OutT) == 4) red_tile(stg, reinterpret_cast<float*>(p.D), p.ldd, m0, n0, p.M, p.N, lane);
+    } else {
+      if constexpr (EPI == VB_EPI_BIAS_GELU) {
+        S::store_tile(stg, reinterpret_cast<OutT*>(p.aux_out), p.ld_aux, m0, n0, p.M, p.N, lane);
+        __syncwarp();
+#pragma unroll
+        for (int v = 0; v < S::VPR; ++v) {
+          OutT o[S::EV];
+#pragma unroll
+          for (int j = 0; j < S::EV; ++j) o[j] = from_f<OutT>(acc[v * S::EV + j]);
+          *reinterpret_cast<uint4*>(my_row + v * 16) = *reinterpret_cast<uint4*>(o);
+        }
+        __syncwarp();
+      }
+      S::store_tile(stg, reinterpret_cast<OutT*>(p.D), p.ldd, m0, n0, p.M, p.N, lane);
+    }
+    __syncwarp();
+  }
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024 B alignment
+  const uint32_t stg_u32 = smem_base + C::STAGES * C::STAGE_BYTES;
+  uint8_t* stg_base = smem_raw + (stg_u32 - smem_u32(smem_raw));
+  float* bias_smem = reinterpret_cast<float*>(stg_base + NUM_EPI_WARPS * STG_WARP_BYTES);  // [2][BN]
+  const uint32_t bars = stg_u32 + NUM_EPI_WARPS * STG_WARP_BYTES + 2 * BN * 4;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (C::STAGES + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
+  const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NUM_EPI_WARPS); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int64_t tiles = (int64_t)p.num_m_blocks * p.num_n_blocks;
+  const int64_t total_work = tiles * p.split_k;
+
+  if (warp == 0 && lane == 0) {
+    // ===================== TMA producer =====================
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+      const int split = (int)(w % p.split_k);
+      const int64_t tile = w / p.split_k;
+      const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+        if (p.a_kmajor) {
+          tma_load_2d(smem_a(stage), &tmA, full_bar(stage), kb * BK, m_blk * BM);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j)
+            tma_load_2d(smem_a(stage) + j * MN_BLOCK_BYTES, &tmA, full_bar(stage), m_blk * BM + j * 64, kb * BK);
+        }
+        if (p.b_kmajor) {
+          tma_load_2d(smem_b(stage), &tmB, full_bar(stage), kb * BK, n_blk * BN);
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_2d(smem_b(stage) + j * MN_BLOCK_BYTES, &tmB, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+        }
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0; int it = 0;
+    const uint32_t a_step = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);  // bytes per UMMA_K step
+    const uint32_t b_step = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
+    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const int split = (int)(w % p.split_k);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(as), aphase ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t adesc = make_smem_desc(smem_a(stage) + k * a_step, p.a_kmajor);
+          const uint64_t bdesc = make_smem_desc(smem_b(stage) + k * b_step, p.b_kmajor);
+          umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue =====================
+    const int ew = (warp - EPI_WARP0) & 3;    // == warp % 4: TMEM lane quarter this warp may access
+    const int group = (warp - EPI_WARP0) >> 2;  // which half of the 32-column chunks
+    uint8_t* stg = stg_base + (warp - EPI_WARP0) * STG_WARP_BYTES;
+    int it = 0;
+    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const int64_t tile = w / p.split_k;
+      const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
+      const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
+      // Stage this tile's bias slice in shared memory while the MMAs are still running.  Double buffered by
+      // accumulator stage; the named barrier also guarantees nobody still reads the buffer of tile it-2.
+      float* bias_cur = bias_smem + as * BN;
+      if constexpr (EPI == VB_EPI_BIAS || EPI == VB_EPI_BIAS_GELU || EPI == VB_EPI_BIAS_RELU || EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_BIAS_ADD) {
+        for (int j = threadIdx.x - EPI_WARP0 * 32; j < BN; j += NUM_EPI_WARPS * 32) {
+          const int64_t n = (int64_t)n_blk * BN + j;
+          bias_cur[j] = n < p.epi.N ? __ldg(p.epi.bias + n) : 0.f;
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
+      mbar_wait(tfull_bar(as), aphase);
+      tcgen05_fence_after();
+      const int64_t m0 = (int64_t)m_blk * BM + ew * 32;
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+      if (m0 < p.epi.M) {  // warp-uniform
+        if constexpr (EPI == VB_EPI_ACCUM) epilogue_tile<float, BN, EPI>(p.epi, tmem_acc, stg, m0, (int64_t)n_blk * BN, lane, group, bias_cur);
+        else if (p.epi.d_bf16) epilogue_tile<bf16, BN, EPI>(p.epi, tmem_acc, stg, m0, (int64_t)n_blk * BN, lane, group, bias_cur);
+        else epilogue_tile<float, BN, EPI>(p.epi, tmem_acc, stg, m0, (int64_t)n_blk * BN, lane, group, bias_cur);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  return fn;
+}
+
+// 2-D bf16 row-major matrix [rows, cols] (pitch ld elements), box = 64 cols x box_rows, 128B swizzle.
+inline int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  VB_REQUIRE(enc != nullptr, VB_ERR_DEVICE, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VB_REQUIRE(r == CUDA_SUCCESS, VB_ERR_ARG, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
+             (long long)rows, (long long)cols, (long long)ld);
+  return 0;
+}
+
+inline int sm_count() {
+  static int g_sm_count = 0;
+  if (g_sm_count == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_sm_count;
+}
+
+template <int BN, int EPI>
+static int launch(const vb_gemm_args& a, cudaStream_t stream) {
+  using C = Cfg<BN>;
+  Params p;
+  int rc = fill_epi_params(a, p.epi);
+  if (rc) return rc;
+  p.num_m_blocks = (int)ceil_div(a.M, BM);
+  p.num_n_blocks = (int)ceil_div(a.N, BN);
+  p.kb_total = (int)ceil_div(a.K, BK);
+  p.a_kmajor = a.a_kmajor;
+  p.b_kmajor = a.b_kmajor;
+  const int64_t tiles = (int64_t)p.num_m_blocks * p.num_n_blocks;
+  int split = 1;
+  if (a.epilogue == VB_EPI_ACCUM) {
+    split = a.split_k;
+    if (split <= 0) {  // fill the machine: as many K slices as keep >= 4 k-blocks per slice
+      split = (int)ceil_div(sm_count(), tiles);
+      split = (int)std::min<int64_t>(split, std::max<int64_t>(1, p.kb_total / 4));
+    }
+    split = std::max(1, std::min(split, p.kb_total));
+  }
+  p.kb_per_split = (int)ceil_div(p.kb_total, split);
+  p.split_k = (int)ceil_div(p.kb_total, p.kb_per_split);
+  // instruction descriptor (cute::UMMA::InstrDescriptor): F32 accum, BF16 x BF16, majors, N>>3, M>>4
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a.a_kmajor ? 0u : 1u) << 15) | ((a.b_kmajor ? 0u : 1u) << 16) |
+            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+  CUtensorMap tmA, tmB;
+  if (a.a_kmajor) rc = make_map(&tmA, a.A, a.M, a.K, a.lda, BM);
+  else rc = make_map(&tmA, a.A, a.K, a.M, a.lda, BK);
+  if (rc) return rc;
+  if (a.b_kmajor) rc = make_map(&tmB, a.B, a.N, a.K, a.ldb, BN);
+  else rc = make_map(&tmB, a.B, a.K, a.N, a.ldb, BK);
+  if (rc) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    VB_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int64_t work = tiles * p.split_k;
+  const int grid = (int)std::min<int64_t>(work, sm_count());
+  gemm_tc_kernel<BN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  return check_launch("gemm_tc_kernel");
+}
+
+
+// Tile width: minimise (rounds over the SMs) x (tile width), i.e. wasted columns + wave quantisation.
+template <int EPI>
+static int launch_epi(const vb_gemm_args& a, cudaStream_t stream) {
+  const int64_t mb = ceil_div(a.M, BM);
+  const int64_t sms = std::max(1, sm_count());
+  auto cost = [&](int bn) { return ceil_div(mb * ceil_div(a.N, bn), sms) * bn; };
+  if (a.N <= 128 || (EPI != VB_EPI_ACCUM && cost(128) < cost(192))) return launch<128, EPI>(a, stream);
+  return launch<192, EPI>(a, stream);
+}
+
+// one translation unit per group of epilogues (parallel build; each kernel gets its own register allocation)
+#define VB_DEFINE_TC_LAUNCH(E) \
+  int gemm_tc_launch_##E(const vb_gemm_args& a, cudaStream_t stream) { return tc::launch_epi<E>(a, stream); }
+
+}  // namespace tc
+}  // namespace vb
