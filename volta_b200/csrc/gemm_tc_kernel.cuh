@@ -561,9 +561,18 @@ static int launch(const vb_gemm_args& a, cudaStream_t stream) {
   int split = 1;
   if (a.epilogue == VB_EPI_ACCUM) {
     split = a.split_k;
-    if (split <= 0) {  // fill the machine: as many K slices as keep >= 4 k-blocks per slice
-      split = (int)ceil_div(sm_count(), tiles);
-      split = (int)std::min<int64_t>(split, std::max<int64_t>(1, p.kb_total / 4));
+    if (split <= 0) {
+      // Split-K for the weight gradients (few output tiles, long reduction).  Cost model in k-block units:
+      // rounds over the SMs x (k-blocks per slice + epilogue of one fp32 red tile ~ 8 k-blocks); smallest wins.
+      const int64_t sms = sm_count();
+      const int max_split = (int)std::max<int64_t>(1, p.kb_total / 4);
+      int64_t best = -1;
+      for (int s_ = 1; s_ <= max_split && s_ <= 64; ++s_) {
+        const int64_t per = ceil_div(p.kb_total, s_);
+        const int64_t eff = ceil_div(p.kb_total, per);
+        const int64_t cost = ceil_div(tiles * eff, sms) * (per + 8);
+        if (best < 0 || cost < best) { best = cost; split = s_; }
+      }
     }
     split = std::max(1, std::min(split, p.kb_total));
   }
@@ -601,7 +610,7 @@ static int launch_epi(const vb_gemm_args& a, cudaStream_t stream) {
   const int64_t sms = std::max(1, sm_count());
   auto cost = [&](int bn) { return ceil_div(mb * ceil_div(a.N, bn), sms) * bn; };
   if (a.N <= 128 || (EPI != VB_EPI_ACCUM && cost(128) < cost(192))) return launch<128, EPI>(a, stream);
-  return launch<192, EPI>(a, stream);
+  return launch<192, EPI>(a, stream);  // ACCUM: split-K evens out the waves, keep the wider tile
 }
 
 // one translation unit per group of epilogues (parallel build; each kernel gets its own register allocation)

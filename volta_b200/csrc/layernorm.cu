@@ -69,31 +69,36 @@ ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const fl
   }
 }
 
-// Backward.  Each warp walks rows (row = warp_global + k * total_warps) and keeps per-lane column partial
-// sums for dgamma / dbeta (/ dbias) in registers; the block reduces them through shared memory and issues
-// one atomicAdd per column.
+// Backward.  Each warp walks rows (row = warp_global + k * total_warps).  The per-column partial sums for
+// dgamma / dbeta (/ dbias) live in a per-warp slice of shared memory (conflict-free 16-byte read-modify-write,
+// no block barrier inside the row loop) instead of ~70 registers per thread: the kernel fits two 8-warp blocks per
+// SM, which is what a bandwidth-bound kernel needs.  The block reduces the slices and issues one atomicAdd per column.
 template <typename T, int NV, bool EXTRA>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 2)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int H, float out_scale,
               T* __restrict__ dx_drop, uint32_t drop_thresh, float drop_scale, uint64_t seed, uint64_t offset,
               float* __restrict__ dbias) {
-  extern __shared__ float red[];  // [WARPS][H] reused for each of the column sums
+  extern __shared__ __align__(16) float red[];  // [3 or 2][WARPS][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
   const int64_t total_warps = (int64_t)gridDim.x * WARPS;
-  float ag[NV][8], ab[NV][8], abias[NV][8];
+  float* sg = red + warp * H;
+  float* sb = red + (WARPS + warp) * H;
+  float* sx = red + (2 * WARPS + warp) * H;
   float gm[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * 8;
-    if (c < H) Vec8<float>::load(gamma + c, gm[i]);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      ag[i][j] = 0.f; ab[i][j] = 0.f;
-      abias[i][j] = 0.f;
-      if (c >= H) gm[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) gm[i][j] = 0.f;
+    if (c < H) {
+      Vec8<float>::load(gamma + c, gm[i]);
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      Vec8<float>::store(sg + c, z);
+      Vec8<float>::store(sb + c, z);
+      if constexpr (EXTRA) Vec8<float>::store(sx + c, z);
     }
   }
   for (int64_t row = warp_global; row < rows; row += total_warps) {
@@ -104,9 +109,11 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + 32 * i) * 8;
       if (c < H) {
-        float d[8], xv[8];
+        float d[8], xv[8], a8[8], b8[8];
         Vec8<T>::load(dy + row * H + c, d);
         Vec8<T>::load(x + row * H + c, xv);
+        Vec8<float>::load(sg + c, a8);
+        Vec8<float>::load(sb + c, b8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float dyo = d[j] * out_scale;
@@ -114,9 +121,11 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
           g[i][j] = dyo * gm[i][j];
           c1 += g[i][j];
           c2 += g[i][j] * xh[i][j];
-          ag[i][j] += dyo * xh[i][j];
-          ab[i][j] += dyo;
+          a8[j] = fmaf(dyo, xh[i][j], a8[j]);
+          b8[j] += dyo;
         }
+        Vec8<float>::store(sg + c, a8);
+        Vec8<float>::store(sb + c, b8);
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) { xh[i][j] = 0.f; g[i][j] = 0.f; }
@@ -133,6 +142,8 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
         for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - c1 - xh[i][j] * c2);
         Vec8<T>::store(dx + row * H + c, o);
         if constexpr (EXTRA) {
+          float e8[8];
+          Vec8<float>::load(sx + c, e8);
           if (dx_drop != nullptr) {
             float od[8];
 #pragma unroll
@@ -145,38 +156,30 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
             Vec8<T>::store(dx_drop + row * H + c, od);
             // the bias gradient sees what the dense layer's output gradient is: the rounded, masked copy
 #pragma unroll
-            for (int j = 0; j < 8; ++j) abias[i][j] += to_f<T>(from_f<T>(od[j]));
+            for (int j = 0; j < 8; ++j) e8[j] += to_f<T>(from_f<T>(od[j]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) abias[i][j] += to_f<T>(from_f<T>(o[j]));
+            for (int j = 0; j < 8; ++j) e8[j] += to_f<T>(from_f<T>(o[j]));
           }
+          Vec8<float>::store(sx + c, e8);
         }
       }
     }
   }
-  // block reduction of the column partials
-  auto reduce_store = [&](float (&acc)[NV][8], float* out) {
-    __syncthreads();
+  __syncthreads();
+  for (int c = threadIdx.x; c < H; c += WARPS * 32) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + 32 * i) * 8;
-      if (c < H) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) red[warp * H + c + j] = acc[i][j];
-      }
+    for (int w = 0; w < WARPS; ++w) {
+      s0 += red[w * H + c];
+      s1 += red[(WARPS + w) * H + c];
+      if constexpr (EXTRA) s2 += red[(2 * WARPS + w) * H + c];
     }
-    __syncthreads();
-    for (int c = threadIdx.x; c < H; c += WARPS * 32) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < WARPS; ++w) s += red[w * H + c];
-      atomicAdd(out + c, s);
+    if (dgamma) atomicAdd(dgamma + c, s0);
+    if (dbeta) atomicAdd(dbeta + c, s1);
+    if constexpr (EXTRA) {
+      if (dbias) atomicAdd(dbias + c, s2);
     }
-  };
-  if (dgamma) reduce_store(ag, dgamma);
-  if (dbeta) reduce_store(ab, dbeta);
-  if constexpr (EXTRA) {
-    if (dbias) reduce_store(abias, dbias);
   }
 }
 
@@ -210,8 +213,8 @@ static int bwd_dispatch(const void* dy, const void* x, const float* mean, const 
   static int sms = 0;
   if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   // enough rows per warp to amortise the column reduction, enough blocks to fill the machine
-  int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), (int64_t)sms * 4);
-  const size_t smem = (size_t)WARPS * H * sizeof(float);
+  int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), (int64_t)sms * 2);  // two resident blocks per SM
+  const size_t smem = (size_t)(extra ? 3 : 2) * WARPS * H * sizeof(float);
   const uint32_t thresh = dx_drop ? dropout_thresh(p) : 0u;
   const float scale = 1.f / (1.f - p);
 #define VB_LN_BWD(NV_, EX_)                                                                                      \
