@@ -247,6 +247,18 @@ int vb_multi_cast_bf16(const vb_cast_item* items_dev, int32_t n_items, int64_t m
 /* VL-BERT sin/cos box embedding (volta/embeddings.py:102-124): boxes fp32 [rows, nl] -> out [rows, 8*dim] */
 int vb_box_sincos(const float* boxes, int32_t nl, int32_t dim, void* out, int64_t ldo, int64_t rows,
                   int32_t dtype, void* stream);
+/* VL-BERT input preparation (volta/embeddings.py:240-292):
+ *  vb_vlbert_prep : per region row r: masked[r] = all(feat[r,:] == 0); out[r, 0:F] = masked ? mask_emb : feat[r,:]
+ *                   (in `dtype`, stride ld_out); kind[r] = (r % K == K-1) ? end_kind : (masked && mvrc ? 1 : 0).
+ *  vb_vlbert_index: text_end[b] = #non-zero ids; the reference shifts text position p by K for EVERY sample as
+ *                   soon as p >= min_b text_end[b] (in-place add on an expanded view, embeddings.py:285-287);
+ *                   tpos[b,t], opos[b,k] = text_end[b] (+1 for the last region), last_row[b] = b*K + K-1.
+ *  vb_batched_colsum: out[b, c] = sum_r a[b, r, c]  (fp32 out). */
+int vb_vlbert_prep(const float* feat, const float* mask_emb, void* out, int64_t ld_out, int64_t* masked, int64_t* kind,
+                   int64_t rows, int32_t F, int32_t K, int32_t mvrc, int32_t end_kind, int32_t dtype, void* stream);
+int vb_vlbert_index(const int64_t* ids, int32_t B, int32_t T, int32_t K, int64_t* tpos, int64_t* opos, int64_t* text_end,
+                    int64_t* last_row, void* stream);
+int vb_batched_colsum(const void* a, int32_t dtype, int64_t batch, int64_t rows, int64_t cols, float* out, void* stream);
 /* L2-flush helper for benchmarks: writes `bytes` to buf. */
 int vb_fill(void* buf, int64_t bytes, int32_t value, void* stream);
 

@@ -314,6 +314,32 @@ def box_sincos(boxes, dim, out):
     return out
 
 
+def vlbert_prep(feat, mask_emb, out, masked, kind, K, mvrc, end_kind):
+    m = (feat == 0).all(-1)
+    out.copy_(torch.where(m[:, None], mask_emb[None, :].expand_as(feat), feat).to(out.dtype))
+    masked.copy_(m.long())
+    r = torch.arange(feat.shape[0], device=feat.device)
+    k = torch.where(m & bool(mvrc), torch.ones_like(r), torch.zeros_like(r))
+    kind.copy_(torch.where(r % K == K - 1, torch.full_like(r, end_kind), k))
+
+
+def vlbert_index(ids, K, tpos, opos, text_end, last_row):
+    B, T = ids.shape
+    te = (ids != 0).sum(1)
+    text_end.copy_(te)
+    t = torch.arange(T, device=ids.device)
+    tpos.copy_(torch.where(t >= te.min(), t + K, t).repeat(B))
+    o = te[:, None].expand(B, K).clone()
+    o[:, -1] += 1
+    opos.copy_(o.reshape(-1))
+    last_row.copy_(torch.arange(B, device=ids.device) * K + K - 1)
+
+
+def batched_colsum(a, batch, rows, cols, out):
+    out.copy_(a.float().reshape(batch, rows, cols).sum(1).reshape(out.shape))
+    return out
+
+
 def fill(buf, value=0):
     assert value == 0
     buf.zero_()
@@ -321,7 +347,7 @@ def fill(buf, value=0):
 
 _NAMES = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "embed_gather_fwd",
           "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd",
-          "loss_finalize", "eltwise", "colsum", "colsum_by_key", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill"]
+          "loss_finalize", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill"]
 
 
 def install(monkeypatch):

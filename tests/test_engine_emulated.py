@@ -10,7 +10,7 @@ from golden_util import MINI_CASES, load_case, rel_l2
 from oracle import volta_oracle as O
 from volta_b200.synthetic import seeded_state_dict
 
-CASES = [c for c in MINI_CASES if "vlbert" not in c]
+CASES = list(MINI_CASES)
 
 
 def _build(name):

@@ -13,7 +13,7 @@ from oracle import volta_oracle as O
 from volta_b200.synthetic import seeded_state_dict
 
 pytestmark = pytest.mark.gpu
-GPU_MINI = [c for c in MINI_CASES if "vlbert" not in c]
+GPU_MINI = list(MINI_CASES)
 GPU_FULL = FULL_CASES
 
 

@@ -70,6 +70,9 @@ SIGNATURES = {
     "vb_multi_cast_bf16": (_i32, [_vp, _i32, _i64, _vp]),
     "vb_box_sincos": (_i32, [_vp, _i32, _i32, _vp, _i64, _i64, _i32, _vp]),
     "vb_fill": (_i32, [_vp, _i64, _i32, _vp]),
+    "vb_vlbert_prep": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "vb_vlbert_index": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vb_batched_colsum": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp]),
 }
 
 _lib = None

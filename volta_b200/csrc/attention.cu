@@ -290,19 +290,32 @@ __device__ __forceinline__ Geo make_geo(const P& p) {
   return g;
 }
 
-// Cooperative load of one operand (column block `which`: 0=Q,1=K,2=V of qkv, or a ctx-layout tensor)
+// Cooperative ASYNCHRONOUS load of one operand (column block: Q / K / V of the packed qkv, or a ctx-layout tensor)
+// into its padded shared-memory tile with cp.async (LDGSTS): all 16-byte copies of all operands are in flight
+// at once and rows beyond the sequence are zero-filled (src-size 0).  A register-staged loop (LDG -> STS per
+// iteration) serialised ~18 global round trips per thread and dominated the kernel.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
 template <int D>
 __device__ __forceinline__ void load_rows(bf16* dst, const P& p, const Geo& g, int b, int h, const void* const src[2],
                                           const int64_t ld[2], int col_off) {
   constexpr int CH = D / 8;
+  const void* any = src[0] ? src[0] : src[1];
   for (int e = threadIdx.x; e < g.R * CH; e += blockDim.x) {
     const int r = e / CH, c = (e % CH) * 8;
     const int s = r < g.Lp[0] ? 0 : 1;
     const int j = s ? r - g.Lp[0] : r;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (j < p.L[s] && src[s] != nullptr)
-      v = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(src[s]) + ((int64_t)b * p.L[s] + j) * ld[s] + col_off + h * D + c);
-    *reinterpret_cast<uint4*>(dst + r * Tile<D>::PITCH + c) = v;
+    const bool valid = j < p.L[s] && src[s] != nullptr;
+    const void* from = valid ? (const void*)(reinterpret_cast<const bf16*>(src[s]) + ((int64_t)b * p.L[s] + j) * ld[s] + col_off + h * D + c)
+                             : any;
+    cp_async16(smem_u32(dst + r * Tile<D>::PITCH + c), from, valid);
   }
 }
 
@@ -329,6 +342,7 @@ mma_fwd_kernel(P p) {
     const int j = s ? r - g.Lp[0] : r;
     madd[r] = j < p.L[s] ? (p.mask[s][(int64_t)b * p.L[s] + j] ? 0.f : -10000.0f) : -INFINITY;
   }
+  cp_async_wait_all();
   __syncthreads();
 
   const int nkb = g.R / 16;
@@ -455,7 +469,8 @@ mma_bwd_kernel(P p) {
   bf16* Ks = Qs + g.R * TL::PITCH;
   bf16* Vs = Ks + g.R * TL::PITCH;
   bf16* dOs = Vs + g.R * TL::PITCH;
-  float* madd = reinterpret_cast<float*>(dOs + g.R * TL::PITCH);
+  bf16* Os = dOs + g.R * TL::PITCH;
+  float* madd = reinterpret_cast<float*>(Os + g.R * TL::PITCH);
   float* lse_s = madd + g.R;
   float* delta_s = lse_s + g.R;
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
@@ -467,6 +482,10 @@ mma_bwd_kernel(P p) {
   load_rows<D>(Ks, p, g, b, h, p.qkv, p.ld, p.A);
   load_rows<D>(Vs, p, g, b, h, p.qkv, p.ld, 2 * p.A);
   load_rows<D>(dOs, p, g, b, h, p.dctx, p.ld_ctx, 0);
+  {
+    const void* octx[2] = {p.ctx[0], p.ctx[1]};
+    load_rows<D>(Os, p, g, b, h, octx, p.ld_ctx, 0);
+  }
   for (int r = threadIdx.x; r < g.R; r += blockDim.x) {
     const int s = r < g.Lp[0] ? 0 : 1;
     const int j = s ? r - g.Lp[0] : r;
@@ -475,22 +494,19 @@ mma_bwd_kernel(P p) {
     lse_s[r] = (valid && p.lse[s]) ? p.lse[s][((int64_t)b * p.heads + h) * p.L[s] + j] : INFINITY;  // pad rows: P = 0
     delta_s[r] = 0.f;
   }
+  cp_async_wait_all();
   __syncthreads();
-  {  // delta[r] = sum_d dO[r,d] * O[r,d]
+  {  // delta[r] = sum_d dO[r,d] * O[r,d]  (both tiles are in shared memory; padded rows are zero)
     constexpr int CH = D / 8;
     for (int e = threadIdx.x; e < g.R * CH; e += blockDim.x) {
       const int r = e / CH, c = (e % CH) * 8;
-      const int s = r < g.Lp[0] ? 0 : 1;
-      const int j = s ? r - g.Lp[0] : r;
-      if (j < p.L[s] && p.ctx[s] != nullptr) {
-        float ov[8], dv[8];
-        Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.ctx[s]) + ((int64_t)b * p.L[s] + j) * p.ld_ctx[s] + h * D + c, ov);
-        Vec8<bf16>::load(dOs + r * TL::PITCH + c, dv);
-        float acc = 0.f;
+      float ov[8], dv[8];
+      Vec8<bf16>::load(Os + r * TL::PITCH + c, ov);
+      Vec8<bf16>::load(dOs + r * TL::PITCH + c, dv);
+      float acc = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) acc = fmaf(ov[k], dv[k], acc);
-        atomicAdd(delta_s + r, acc);
-      }
+      for (int k = 0; k < 8; ++k) acc = fmaf(ov[k], dv[k], acc);
+      atomicAdd(delta_s + r, acc);
     }
   }
   __syncthreads();
@@ -737,7 +753,7 @@ static int run(const vb_attn_args& a, cudaStream_t st, bool bwd) {
 #undef VB_FWD
       return check_launch("attention mma_fwd_kernel");
     }
-    const size_t smem = 4 * tile + 3 * R * sizeof(float);
+    const size_t smem = 5 * tile + 3 * R * sizeof(float);
     if (a.d == 64) {
       if ((rc = set_smem(mma_bwd_kernel<64>, smem))) return rc;
       mma_bwd_kernel<64><<<grid, 128, smem, st>>>(p);

@@ -97,6 +97,62 @@ colsum_by_key_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t
 
 template <typename T>
 __global__ void __launch_bounds__(256)
+vlbert_prep_kernel(const float* __restrict__ feat, const float* __restrict__ mask_emb, T* __restrict__ out, int64_t ld_out,
+                   int64_t* __restrict__ masked, int64_t* __restrict__ kind, int64_t rows, int F, int K, int mvrc, int end_kind) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * 8 + warp;
+  if (r >= rows) return;
+  const float* f = feat + r * F;
+  bool nz = false;
+  for (int c = lane; c < F; c += 32) nz |= (f[c] != 0.f);
+  const bool is_masked = !__any_sync(0xffffffffu, nz);
+  for (int c = lane; c < F; c += 32) out[r * ld_out + c] = from_f<T>(is_masked ? mask_emb[c] : f[c]);
+  if (lane == 0) {
+    masked[r] = is_masked ? 1 : 0;
+    kind[r] = (r % K == K - 1) ? end_kind : ((is_masked && mvrc) ? 1 : 0);
+  }
+}
+
+// single block: B is a few hundred at most
+__global__ void __launch_bounds__(1024)
+vlbert_index_kernel(const int64_t* __restrict__ ids, int B, int T, int K, int64_t* __restrict__ tpos,
+                    int64_t* __restrict__ opos, int64_t* __restrict__ text_end, int64_t* __restrict__ last_row) {
+  __shared__ int s_min;
+  if (threadIdx.x == 0) s_min = T;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    int n = 0;
+    for (int t = 0; t < T; ++t) n += ids[(int64_t)b * T + t] != 0;
+    text_end[b] = n;
+    last_row[b] = (int64_t)b * K + K - 1;
+    atomicMin(&s_min, n);
+  }
+  __syncthreads();
+  const int mn = s_min;
+  for (int i = threadIdx.x; i < B * T; i += blockDim.x) {
+    const int t = i % T;
+    tpos[i] = t >= mn ? t + K : t;
+  }
+  for (int i = threadIdx.x; i < B * K; i += blockDim.x) {
+    const int b = i / K, k = i % K;
+    opos[i] = text_end[b] + (k == K - 1 ? 1 : 0);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+batched_colsum_kernel(const T* __restrict__ a, int64_t rows, int64_t cols, float* __restrict__ out) {
+  const int64_t b = blockIdx.y;
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const T* p = a + b * rows * cols + c;
+  float s = 0.f;
+  for (int64_t r = 0; r < rows; ++r) s += to_f<T>(p[r * cols]);
+  out[b * cols + c] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
 box_fwd_kernel(const float* __restrict__ loc, int nl, const float* __restrict__ W, const float* __restrict__ b,
                T* __restrict__ out, int64_t ld_out, int64_t rows, int H, int accum) {
   const int64_t total = rows * H;
@@ -208,6 +264,36 @@ int vb_colsum_by_key(const void* a, int32_t dtype, int64_t lda, int64_t rows, in
   else
     vb::emb::colsum_by_key_kernel<float, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, rows, cols, keys, nkeys, out, rpb);
   return vb::check_launch("colsum_by_key_kernel");
+}
+
+int vb_vlbert_prep(const float* feat, const float* mask_emb, void* out, int64_t ld_out, int64_t* masked, int64_t* kind,
+                   int64_t rows, int32_t F, int32_t K, int32_t mvrc, int32_t end_kind, int32_t dtype, void* stream) {
+  VB_REQUIRE(feat && mask_emb && out && masked && kind && F > 0 && K > 0, VB_ERR_ARG, "vlbert_prep: bad arguments");
+  if (rows == 0) return 0;
+  const unsigned grid = (unsigned)vb::ceil_div(rows, 8);
+  if (dtype == VB_BF16)
+    vb::emb::vlbert_prep_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, mask_emb, (vb::bf16*)out, ld_out, masked, kind, rows, F, K, mvrc, end_kind);
+  else
+    vb::emb::vlbert_prep_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(feat, mask_emb, (float*)out, ld_out, masked, kind, rows, F, K, mvrc, end_kind);
+  return vb::check_launch("vlbert_prep_kernel");
+}
+
+int vb_vlbert_index(const int64_t* ids, int32_t B, int32_t T, int32_t K, int64_t* tpos, int64_t* opos, int64_t* text_end,
+                    int64_t* last_row, void* stream) {
+  VB_REQUIRE(ids && tpos && opos && text_end && last_row && B > 0 && T > 0 && K > 0, VB_ERR_ARG, "vlbert_index: bad arguments");
+  vb::emb::vlbert_index_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(ids, B, T, K, tpos, opos, text_end, last_row);
+  return vb::check_launch("vlbert_index_kernel");
+}
+
+int vb_batched_colsum(const void* a, int32_t dtype, int64_t batch, int64_t rows, int64_t cols, float* out, void* stream) {
+  VB_REQUIRE(a && out && batch > 0 && batch <= 65535, VB_ERR_ARG, "batched_colsum: bad arguments");
+  if (rows * cols == 0) return 0;
+  dim3 grid((unsigned)vb::ceil_div(cols, 256), (unsigned)batch);
+  if (dtype == VB_BF16)
+    vb::emb::batched_colsum_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const vb::bf16*)a, rows, cols, out);
+  else
+    vb::emb::batched_colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, rows, cols, out);
+  return vb::check_launch("batched_colsum_kernel");
 }
 
 int vb_box_project_fwd(const float* loc, int32_t nl, const float* W, const float* b, void* out, int64_t ld_out,

@@ -398,6 +398,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps
+  // the tail of the previous kernel in the stream; global memory is only touched after this point.
+  cudaGridDependencySynchronize();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
@@ -598,7 +601,18 @@ static int launch(const vb_gemm_args& a, cudaStream_t stream) {
   }
   const int64_t work = tiles * p.split_k;
   const int grid = (int)std::min<int64_t>(work, sm_count());
-  gemm_tc_kernel<BN, EPI><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI>, tmA, tmB, p);
+  VB_REQUIRE(le == cudaSuccess, (int)le, "gemm_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   return check_launch("gemm_tc_kernel");
 }
 

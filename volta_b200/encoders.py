@@ -337,6 +337,9 @@ class BertPreTrainedModel(nn.Module):
                     k, v = getattr(m, pre + "key"), getattr(m, pre + "value")
                     groups.append([q.weight, k.weight, v.weight])
                     groups.append([q.bias, k.bias, v.bias])
+            elif type(m).__name__ == "VLBertEmbeddings":
+                from .vlbert import _ling_tables
+                groups.append(_ling_tables(m))  # object / masked-object / end rows form one 2-3 row table
         return groups
 
     @classmethod

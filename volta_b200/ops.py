@@ -286,3 +286,24 @@ def box_sincos(boxes, dim, out):
 
 def fill(buf, value=0):
     _lib.call("vb_fill", buf.data_ptr(), buf.numel() * buf.element_size(), int(value), _stream())
+
+
+# --------------------------------------------------------------------------- VL-BERT input preparation
+def vlbert_prep(feat, mask_emb, out, masked, kind, K, mvrc, end_kind):
+    rows, F = feat.shape
+    assert feat.dtype == torch.float32 and feat.is_contiguous() and mask_emb.dtype == torch.float32
+    _lib.call("vb_vlbert_prep", feat.data_ptr(), mask_emb.data_ptr(), out.data_ptr(), out.stride(0), masked.data_ptr(),
+              kind.data_ptr(), rows, F, K, int(mvrc), int(end_kind), dt(out), _stream())
+
+
+def vlbert_index(ids, K, tpos, opos, text_end, last_row):
+    B, T = ids.shape
+    assert ids.dtype == torch.int64 and ids.is_contiguous()
+    _lib.call("vb_vlbert_index", ids.data_ptr(), B, T, K, tpos.data_ptr(), opos.data_ptr(), text_end.data_ptr(),
+              last_row.data_ptr(), _stream())
+
+
+def batched_colsum(a, batch, rows, cols, out):
+    assert a.is_contiguous() and out.dtype == torch.float32 and out.numel() == batch * cols
+    _lib.call("vb_batched_colsum", a.data_ptr(), dt(a), batch, rows, cols, out.data_ptr(), _stream())
+    return out
