@@ -350,6 +350,15 @@ def test_eltwise_colsum_gather():
     cs, cr = torch.zeros(1024, device=DEV), a.float().sum(0)
     ops.colsum(a, cs)
     assert rel(cs, cr) < 1e-5
+    for rows, cols, dtype in ((9472, 2304, torch.bfloat16), (1000, 776, torch.float32), (77, 1024, torch.bfloat16), (333, 100, torch.bfloat16)):
+        big = rnd(rows, cols, dtype=dtype, seed=3)      # vector path (and its fall-backs: odd widths, few rows)
+        cs = torch.full((cols,), 1.0, device=DEV)       # accumulates into the existing content
+        ops.colsum(big, cs)
+        assert rel(cs, big.float().sum(0) + 1.0) < 1e-5, (rows, cols, dtype)
+    sl = rnd(512, 2048, seed=4)[:, 1024:]                # strided column slice
+    cs = torch.zeros(1024, device=DEV)
+    ops.colsum(sl, cs)
+    assert rel(cs, sl.float().sum(0)) < 1e-5
     idx = torch.randperm(300)[:100].to(DEV)
     o = torch.empty(100, 1024, dtype=torch.bfloat16, device=DEV)
     ops.gather_rows(a, idx, o)

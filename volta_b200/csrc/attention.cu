@@ -8,6 +8,8 @@
 //  * MMA  (bf16, d in {64,128}): warp-level mma.sync.m16n8k16 with ldmatrix operands, fp32 softmax.
 //    (tcgen05 wants 128-row tiles; Lq = 36 would fill 28 % of one - see DESIGN.md.)
 //  * SIMT (fp32 validation mode / any d): one warp per query (or key) row.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vb {
@@ -27,10 +29,32 @@ struct P {
   float scale;
   uint32_t thresh[2];        // per query stream
   float keep_scale[2];
-  uint64_t seed, offset;
+  uint64_t seed;             // seed + offset
+  int ngroups;               // MMA back-end: independent (query set, key set) groups per (sample, head)
 };
 
-__device__ __forceinline__ bool pair_on(int pair_mask, int qs, int ks) { return (pair_mask >> (qs * 2 + ks)) & 1; }
+__host__ __device__ __forceinline__ bool pair_on(int pair_mask, int qs, int ks) { return (pair_mask >> (qs * 2 + ks)) & 1; }
+
+// Dropout on the attention probabilities (volta/encoders.py:294-299, 309-314).  The keep decision of the element
+// (sample b, head h, global query row qg | key stream ks, key j) is a pure function of
+//   row_id = (b*heads + h)*Ltot + qg   and   (ks, j >> 1):
+// one 32-bit hash serves the two keys 2m, 2m+1 of a stream (16 bits each), and it splits into a per-row term and a
+// per-column term, so in the mma.sync fragment layout (2 rows x 2 adjacent keys per thread and n-tile) the cost
+// is ~5 integer instructions per probability.  Forward, backward and the SIMT validation back-end all use it.
+__device__ __forceinline__ uint32_t attn_rowterm(uint64_t seed, uint32_t row_id) { return (row_id * 0x9E3779B1u) ^ (uint32_t)seed; }
+__device__ __forceinline__ uint32_t attn_colterm(uint64_t seed, int ks, int j) {
+  return ((((uint32_t)ks << 16) | ((uint32_t)j >> 1)) + (uint32_t)(seed >> 32)) * 0x85EBCA77u;
+}
+__device__ __forceinline__ uint32_t attn_mix(uint32_t h) {
+  h ^= h >> 16; h *= 0x7FEB352Du;
+  h ^= h >> 15; h *= 0x846CA68Bu;
+  h ^= h >> 16;
+  return h;
+}
+__device__ __forceinline__ bool attn_keep(uint64_t seed, uint32_t row_id, int ks, int j, uint32_t thresh) {
+  const uint32_t h = attn_mix(attn_rowterm(seed, row_id) ^ attn_colterm(seed, ks, j));
+  return ((j & 1) ? (h >> 16) : (h & 0xFFFFu)) >= thresh;
+}
 
 // =====================================================================================
 // SIMT back-end
@@ -73,10 +97,13 @@ simt_fwd_kernel(P p) {
     const float lse = mx + __logf(sum);
     if (lane == 0) p.lse[qs][((int64_t)b * p.heads + h) * p.L[qs] + i] = lse;
     const int qg = qs ? p.L[0] + i : i;
-    const uint64_t base = (((uint64_t)b * p.heads + h) * Ltot + qg) * (uint64_t)Ltot;
+    const uint32_t row_id = ((uint32_t)b * p.heads + h) * Ltot + qg;
     for (int kg = lane; kg < Ltot; kg += 32) {
       float pr = __expf(pbuf[kg] - lse);
-      if (p.thresh[qs]) pr = dropout_keep(p.seed, p.offset, base + kg, p.thresh[qs]) ? pr * p.keep_scale[qs] : 0.f;
+      if (p.thresh[qs]) {
+        const int ks = kg < p.L[0] ? 0 : 1;
+        pr = attn_keep(p.seed, row_id, ks, ks ? kg - p.L[0] : kg, p.thresh[qs]) ? pr * p.keep_scale[qs] : 0.f;
+      }
       pbuf[kg] = pr;
     }
     __syncwarp();
@@ -129,7 +156,7 @@ simt_bwd_dq_kernel(P p) {
     __syncwarp();
     const float lse = p.lse[qs][((int64_t)b * p.heads + h) * p.L[qs] + i];
     const int qg = qs ? p.L[0] + i : i;
-    const uint64_t base = (((uint64_t)b * p.heads + h) * Ltot + qg) * (uint64_t)Ltot;
+    const uint32_t row_id = ((uint32_t)b * p.heads + h) * Ltot + qg;
     for (int kg = lane; kg < Ltot; kg += 32) {
       const int ks = kg < p.L[0] ? 0 : 1;
       const int j = ks ? kg - p.L[0] : kg;
@@ -144,7 +171,7 @@ simt_bwd_dq_kernel(P p) {
         }
         s = s * p.scale + (p.mask[ks][(int64_t)b * p.L[ks] + j] ? 0.f : -10000.0f);
         const float pr = __expf(s - lse);
-        if (p.thresh[qs]) dp = dropout_keep(p.seed, p.offset, base + kg, p.thresh[qs]) ? dp * p.keep_scale[qs] : 0.f;
+        if (p.thresh[qs]) dp = attn_keep(p.seed, row_id, ks, j, p.thresh[qs]) ? dp * p.keep_scale[qs] : 0.f;
         ds = pr * (dp - delta) * p.scale;
       }
       pbuf[kg] = ds;
@@ -190,7 +217,6 @@ simt_bwd_dkv_kernel(P p) {
       dk[r] = 0.f; dv[r] = 0.f;
     }
     const float madd = p.mask[ks][krow] ? 0.f : -10000.0f;
-    const int kg = ks ? p.L[0] + j : j;
     for (int qs = 0; qs < 2; ++qs) {
       if (!pair_on(p.pair_mask, qs, ks) || p.qkv[qs] == nullptr) continue;
       for (int i = 0; i < p.L[qs]; ++i) {
@@ -216,8 +242,7 @@ simt_bwd_dkv_kernel(P p) {
         float pd = pr;
         if (p.thresh[qs]) {
           const int qg = qs ? p.L[0] + i : i;
-          const uint64_t idx = (((uint64_t)b * p.heads + h) * Ltot + qg) * (uint64_t)Ltot + kg;
-          const bool keep = dropout_keep(p.seed, p.offset, idx, p.thresh[qs]);
+          const bool keep = attn_keep(p.seed, ((uint32_t)b * p.heads + h) * Ltot + qg, ks, j, p.thresh[qs]);
           pd = keep ? pr * p.keep_scale[qs] : 0.f;
           dp = keep ? dp * p.keep_scale[qs] : 0.f;
         }
@@ -242,6 +267,19 @@ simt_bwd_dkv_kernel(P p) {
 // =====================================================================================
 // MMA back-end (bf16)
 // =====================================================================================
+// Work decomposition.  The (query-stream, key-stream) blocks a sub-layer enables split a (sample, head) into one or
+// two independent GROUPS: tt+vv (pair_mask 9) and tv+vt (6) give two groups with one query stream and one key
+// stream each; every other mask is one group holding all its streams.  One CTA = one (sample, head, group):
+//   forward : one warp per 16-query tile - S = Q K^T, joint softmax over the enabled key n-tiles (8 keys each,
+//             so 36 keys cost 5 n-tiles, not 6), dropout, O = P V; O leaves through shared memory in 16-byte rows.
+//   backward: one warp per 16-KEY tile - S^T = K Q^T and dP^T = V dO^T per 16-query block, P and dS recomputed
+//             ONCE; dV += P^T dO and dK += dS^T Q accumulate in registers (every element written exactly once);
+//             the warp also leaves its dS^T tile (bf16) in shared memory, and after one block barrier a second
+//             phase (one warp per 16-QUERY tile) forms dQ = dS K with dS read back through ldmatrix.trans - no
+//             atomics (red.shared.add.f32 is a CAS spin loop in SASS), no second softmax/dropout recomputation.
+// An earlier version kept a fixed 6/10-block key loop per query tile and recomputed S, the softmax and the dropout
+// hash in two separate backward phases: ncu showed both kernels issue-bound (25 M / 84 M warp instructions per
+// launch at B=256 for ~100 MB of HBM traffic).
 __device__ __forceinline__ uint32_t smem_u32(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
@@ -257,6 +295,11 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2f(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 template <int D> struct Tile {
   static constexpr int PITCH = D + 8;  // bf16 elements; 16-byte padding keeps ldmatrix conflict-free
@@ -271,6 +314,11 @@ template <int D> struct Tile {
     const int lane = threadIdx.x & 31;
     ldsm_x4(smem_u32(base + (n0 + (lane & 7) + (lane >> 4) * 8) * PITCH + k0 + ((lane >> 3) & 1) * 8), r);
   }
+  // A operand with A[m][k] = M[k][m] (M row-major, pitch in elements): 16 m x 16 k block at (m0, k0), transposing load
+  static __device__ __forceinline__ void load_at(const bf16* base, int pitch, int m0, int k0, uint32_t (&r)[4]) {
+    const int lane = threadIdx.x & 31;
+    ldsm_x4_t(smem_u32(base + (k0 + (lane & 7) + (lane >> 4) * 8) * pitch + m0 + ((lane >> 3) & 1) * 8), r);
+  }
   // B operand with B[k][n] = M[k][n] (M row-major [k][D]): 16 k x 16 n block at (k0, n0), transposing load
   static __device__ __forceinline__ void load_bt(const bf16* base, int k0, int n0, uint32_t (&r)[4]) {
     const int lane = threadIdx.x & 31;
@@ -278,22 +326,32 @@ template <int D> struct Tile {
   }
 };
 
-struct Geo {  // padded geometry of one (sample, head)
-  int Lp[2];  // rows padded to 16 per stream (0 if the stream is absent)
-  int R;      // Lp[0] + Lp[1]
+// Geometry of one group: which streams supply queries / keys, and where their (16-row padded) tiles sit.
+struct Geo {
+  int qset, kset;          // bit s = stream s has query rows / key rows in this CTA
+  int qrows[2], krows[2];  // padded rows (0 if absent); stream 0 first, stream 1 at offset rows[0]
+  int RQ, RK;
 };
-__device__ __forceinline__ Geo make_geo(const P& p) {
+__host__ __device__ __forceinline__ int attn_groups(int pair_mask) { return (pair_mask == 9 || pair_mask == 6) ? 2 : 1; }
+__host__ __device__ __forceinline__ Geo make_geo(int pair_mask, int L0, int L1, int group) {
   Geo g;
-  g.Lp[0] = p.qkv[0] ? ((p.L[0] + 15) & ~15) : 0;
-  g.Lp[1] = p.qkv[1] ? ((p.L[1] + 15) & ~15) : 0;
-  g.R = g.Lp[0] + g.Lp[1];
+  if (attn_groups(pair_mask) == 2) {
+    g.qset = 1 << group;
+    g.kset = pair_mask == 9 ? (1 << group) : (1 << (1 - group));
+  } else {
+    g.qset = ((pair_mask & 3) ? 1 : 0) | ((pair_mask & 12) ? 2 : 0);
+    g.kset = ((pair_mask & 5) ? 1 : 0) | ((pair_mask & 10) ? 2 : 0);
+  }
+  const int Lp[2] = {(L0 + 15) & ~15, (L1 + 15) & ~15};
+  for (int s = 0; s < 2; ++s) {
+    g.qrows[s] = ((g.qset >> s) & 1) ? Lp[s] : 0;
+    g.krows[s] = ((g.kset >> s) & 1) ? Lp[s] : 0;
+  }
+  g.RQ = g.qrows[0] + g.qrows[1];
+  g.RK = g.krows[0] + g.krows[1];
   return g;
 }
 
-// Cooperative ASYNCHRONOUS load of one operand (column block: Q / K / V of the packed qkv, or a ctx-layout tensor)
-// into its padded shared-memory tile with cp.async (LDGSTS): all 16-byte copies of all operands are in flight
-// at once and rows beyond the sequence are zero-filled (src-size 0).  A register-staged loop (LDG -> STS per
-// iteration) serialised ~18 global round trips per thread and dominated the kernel.
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
   const int bytes = valid ? 16 : 0;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
@@ -303,309 +361,284 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// Asynchronous copy of rows [0, L) of one sample's [L, D] head slice into a padded tile (rows [L, Lp) zero-filled).
 template <int D>
-__device__ __forceinline__ void load_rows(bf16* dst, const P& p, const Geo& g, int b, int h, const void* const src[2],
-                                          const int64_t ld[2], int col_off) {
+__device__ __forceinline__ void load_seg(bf16* dst, const bf16* src, int64_t ld, int L, int Lp) {
   constexpr int CH = D / 8;
-  const void* any = src[0] ? src[0] : src[1];
-  for (int e = threadIdx.x; e < g.R * CH; e += blockDim.x) {
+  for (int e = threadIdx.x; e < Lp * CH; e += blockDim.x) {
     const int r = e / CH, c = (e % CH) * 8;
-    const int s = r < g.Lp[0] ? 0 : 1;
-    const int j = s ? r - g.Lp[0] : r;
-    const bool valid = j < p.L[s] && src[s] != nullptr;
-    const void* from = valid ? (const void*)(reinterpret_cast<const bf16*>(src[s]) + ((int64_t)b * p.L[s] + j) * ld[s] + col_off + h * D + c)
-                             : any;
-    cp_async16(smem_u32(dst + r * Tile<D>::PITCH + c), from, valid);
+    const bool valid = r < L;
+    cp_async16(smem_u32(dst + r * Tile<D>::PITCH + c), valid ? (const void*)(src + (int64_t)r * ld + c) : (const void*)src, valid);
+  }
+}
+// additive key mask in the log2 domain: 0 / -10000*log2(e) (encoders.py:983-991), -inf on padding rows
+__device__ __forceinline__ void load_madd(float* dst, const int32_t* mask, int L, int Lp) {
+  for (int r = threadIdx.x; r < Lp; r += blockDim.x)
+    dst[r] = r < L ? (mask[r] ? 0.f : -14426.950408889634f) : -INFINITY;
+}
+// 16 rows x D of a warp's own tile rows -> global, 16 bytes per lane (rows of the sample beyond L are dropped)
+template <int D>
+__device__ __forceinline__ void store_rows16(const bf16* tile_rows, bf16* dst, int64_t ld, int j0, int L) {
+  constexpr int CH = D / 8;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 16 * CH / 32; ++i) {
+    const int e = i * 32 + lane, r = e / CH, c = (e % CH) * 8;
+    if (j0 + r < L)
+      *reinterpret_cast<uint4*>(dst + (int64_t)(j0 + r) * ld + c) = *reinterpret_cast<const uint4*>(tile_rows + r * Tile<D>::PITCH + c);
+  }
+}
+// C fragments (16 x D fp32, scaled per row half) -> bf16 in the warp's own 16 tile rows
+template <int D>
+__device__ __forceinline__ void frag_to_rows16(bf16* tile_rows, const float (&o)[D / 8][4], float s0, float s1) {
+  const int lane = threadIdx.x & 31, gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int nd = 0; nd < D / 8; ++nd) {
+    *reinterpret_cast<uint32_t*>(tile_rows + gq * Tile<D>::PITCH + nd * 8 + 2 * tq) = pack_bf16x2(o[nd][0] * s0, o[nd][1] * s0);
+    *reinterpret_cast<uint32_t*>(tile_rows + (gq + 8) * Tile<D>::PITCH + nd * 8 + 2 * tq) = pack_bf16x2(o[nd][2] * s1, o[nd][3] * s1);
   }
 }
 
-template <int D, int MAXKB>
-__global__ void __launch_bounds__(128, (D == 64 && MAXKB <= 6) ? 4 : 2)
+// ---------------------------------------------------------------------------------------------- forward
+template <int D, int NKB>
+__global__ void __launch_bounds__(320)
 mma_fwd_kernel(P p) {
   extern __shared__ __align__(16) uint8_t smraw[];
   using TL = Tile<D>;
-  const Geo g = make_geo(p);
+  const Geo g = make_geo(p.pair_mask, p.L[0], p.L[1], blockIdx.y);
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
-  bf16* Ks = Qs + g.R * TL::PITCH;
-  bf16* Vs = Ks + g.R * TL::PITCH;
-  float* madd = reinterpret_cast<float*>(Vs + g.R * TL::PITCH);
+  bf16* Ks = Qs + g.RQ * TL::PITCH;
+  bf16* Vs = Ks + g.RK * TL::PITCH;
+  float* madd = reinterpret_cast<float*>(Vs + g.RK * TL::PITCH);
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, tq = lane & 3;
-  const int Ltot = p.L[0] + p.L[1];
 
-  load_rows<D>(Qs, p, g, b, h, p.qkv, p.ld, 0);
-  load_rows<D>(Ks, p, g, b, h, p.qkv, p.ld, p.A);
-  load_rows<D>(Vs, p, g, b, h, p.qkv, p.ld, 2 * p.A);
-  for (int r = threadIdx.x; r < g.R; r += blockDim.x) {
-    const int s = r < g.Lp[0] ? 0 : 1;
-    const int j = s ? r - g.Lp[0] : r;
-    madd[r] = j < p.L[s] ? (p.mask[s][(int64_t)b * p.L[s] + j] ? 0.f : -10000.0f) : -INFINITY;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const bf16* base = reinterpret_cast<const bf16*>(p.qkv[s]) + (int64_t)b * p.L[s] * p.ld[s] + h * D;
+    if (g.qrows[s]) load_seg<D>(Qs + (s ? g.qrows[0] : 0) * TL::PITCH, base, p.ld[s], p.L[s], g.qrows[s]);
+    if (g.krows[s]) {
+      const int off = s ? g.krows[0] : 0;
+      load_seg<D>(Ks + off * TL::PITCH, base + p.A, p.ld[s], p.L[s], g.krows[s]);
+      load_seg<D>(Vs + off * TL::PITCH, base + 2 * p.A, p.ld[s], p.L[s], g.krows[s]);
+      load_madd(madd + off, p.mask[s] + (int64_t)b * p.L[s], p.L[s], g.krows[s]);
+    }
   }
   cp_async_wait_all();
   __syncthreads();
+  if (warp * 16 >= g.RQ) return;
 
-  const int nkb = g.R / 16;
-  for (int qt = warp; qt < nkb; qt += 4) {
-    const int qs = (qt * 16 < g.Lp[0]) ? 0 : 1;
-    if (p.ctx[qs] == nullptr) continue;
-    float s[2 * MAXKB][4];
+  const int qt = warp;
+  const int qs = (qt * 16 < g.qrows[0]) ? 0 : 1;
+  const int jq0 = qt * 16 - (qs ? g.qrows[0] : 0);  // first row of this tile inside its stream
+  // key n-tiles (8 keys) this query stream attends: enabled key streams, rows below their length
+  uint32_t ntmask = 0;
 #pragma unroll
-    for (int i = 0; i < 2 * MAXKB; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+  for (int ks = 0; ks < 2; ++ks)
+    if (g.krows[ks] && pair_on(p.pair_mask, qs, ks))
+      ntmask |= ((1u << ((p.L[ks] + 7) >> 3)) - 1u) << ((ks ? g.krows[0] : 0) >> 3);
+  const float sc2 = p.scale * 1.4426950408889634f;
+
+  float s[2 * NKB][4];
 #pragma unroll
-    for (int ks = 0; ks < D / 16; ++ks) {
+  for (int i = 0; i < 2 * NKB; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk) {
+    uint32_t a[4];
+    TL::load_a(Qs, qt * 16, kk * 16, a);
+#pragma unroll
+    for (int kb = 0; kb < NKB; ++kb) {
+      if ((ntmask >> (2 * kb)) & 3u) {
+        uint32_t bb[4];
+        TL::load_b(Ks, kb * 16, kk * 16, bb);
+        mma16816(s[2 * kb], a, bb[0], bb[1]);
+        if ((ntmask >> (2 * kb + 1)) & 1u) mma16816(s[2 * kb + 1], a, bb[2], bb[3]);
+      }
+    }
+  }
+  // scale + additive mask (log2 domain), row max over rows gq and gq+8
+  float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+  for (int nt = 0; nt < 2 * NKB; ++nt) {
+    if ((ntmask >> nt) & 1u) {
+      const float2 md = *reinterpret_cast<const float2*>(madd + nt * 8 + 2 * tq);
+      s[nt][0] = fmaf(s[nt][0], sc2, md.x); s[nt][1] = fmaf(s[nt][1], sc2, md.y);
+      s[nt][2] = fmaf(s[nt][2], sc2, md.x); s[nt][3] = fmaf(s[nt][3], sc2, md.y);
+      mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+    mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    if (mx[r] == -INFINITY) mx[r] = 0.f;
+  }
+  float sum[2] = {0.f, 0.f};
+#pragma unroll
+  for (int nt = 0; nt < 2 * NKB; ++nt) {
+    if ((ntmask >> nt) & 1u) {
+      s[nt][0] = ex2f(s[nt][0] - mx[0]); s[nt][1] = ex2f(s[nt][1] - mx[0]);
+      s[nt][2] = ex2f(s[nt][2] - mx[1]); s[nt][3] = ex2f(s[nt][3] - mx[1]);
+      sum[0] += s[nt][0] + s[nt][1];
+      sum[1] += s[nt][2] + s[nt][3];
+    }
+  }
+  float osc[2];  // 1/sum (and the dropout scale) is applied to O, not to the 16 x Lk probabilities
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
+    sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
+    osc[r] = p.keep_scale[qs] / sum[r];
+    const int j = jq0 + gq + r * 8;
+    if (tq == 0 && j < p.L[qs]) p.lse[qs][((int64_t)b * p.heads + h) * p.L[qs] + j] = (mx[r] + __log2f(sum[r])) * 0.6931471805599453f;
+  }
+  const uint32_t thresh = p.thresh[qs];
+  if (thresh) {
+    const int Ltot = p.L[0] + p.L[1];
+    const uint32_t row0 = ((uint32_t)b * p.heads + h) * Ltot + (qs ? p.L[0] : 0) + jq0 + gq;
+    const uint32_t rt0 = attn_rowterm(p.seed, row0), rt1 = attn_rowterm(p.seed, row0 + 8);
+#pragma unroll
+    for (int nt = 0; nt < 2 * NKB; ++nt) {
+      if ((ntmask >> nt) & 1u) {
+        const int kr = nt * 8 + 2 * tq;
+        const int ks = (kr < g.krows[0]) ? 0 : 1;
+        const uint32_t ct = attn_colterm(p.seed, ks, kr - (ks ? g.krows[0] : 0));
+        const uint32_t h0 = attn_mix(rt0 ^ ct), h1 = attn_mix(rt1 ^ ct);
+        if ((h0 & 0xFFFFu) < thresh) s[nt][0] = 0.f;
+        if ((h0 >> 16) < thresh) s[nt][1] = 0.f;
+        if ((h1 & 0xFFFFu) < thresh) s[nt][2] = 0.f;
+        if ((h1 >> 16) < thresh) s[nt][3] = 0.f;
+      }
+    }
+  }
+  // O = P . V
+  float o[D / 8][4];
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb) {
+    if ((ntmask >> (2 * kb)) & 3u) {
       uint32_t a[4];
-      TL::load_a(Qs, qt * 16, ks * 16, a);
-#pragma unroll
-      for (int kb = 0; kb < MAXKB; ++kb) {
-        if (kb < nkb && pair_on(p.pair_mask, qs, (kb * 16 < g.Lp[0]) ? 0 : 1)) {
-          uint32_t bb[4];
-          TL::load_b(Ks, kb * 16, ks * 16, bb);
-          mma16816(s[2 * kb], a, bb[0], bb[1]);
-          mma16816(s[2 * kb + 1], a, bb[2], bb[3]);
-        }
-      }
-    }
-    // scale + masks, row max (rows gq and gq+8)
-    float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-    for (int kb = 0; kb < MAXKB; ++kb) {
-      const bool on = kb < nkb && pair_on(p.pair_mask, qs, (kb * 16 < g.Lp[0]) ? 0 : 1);
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float v = -INFINITY;
-          if (on) v = s[2 * kb + nt][e] * p.scale + madd[kb * 16 + nt * 8 + 2 * tq + (e & 1)];
-          s[2 * kb + nt][e] = v;
-          mx[e >> 1] = fmaxf(mx[e >> 1], v);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      if (mx[r] == -INFINITY) mx[r] = 0.f;
-    }
-    float sum[2] = {0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < 2 * MAXKB; ++i)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float ex = __expf(s[i][e] - mx[e >> 1]);
-        s[i][e] = ex;
-        sum[e >> 1] += ex;
-      }
-    float inv[2];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
-      sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
-      inv[r] = 1.f / sum[r];
-      const int j = qt * 16 - (qs ? g.Lp[0] : 0) + gq + r * 8;
-      if (tq == 0 && j < p.L[qs]) p.lse[qs][((int64_t)b * p.heads + h) * p.L[qs] + j] = mx[r] + __logf(sum[r]);
-    }
-    const uint32_t thresh = p.thresh[qs];
-    const float ksc = p.keep_scale[qs];
-#pragma unroll
-    for (int kb = 0; kb < MAXKB; ++kb)
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float pr = s[2 * kb + nt][e] * inv[e >> 1];
-          if (thresh) {
-            const int kr = kb * 16 + nt * 8 + 2 * tq + (e & 1);
-            const int kstream = kr < g.Lp[0] ? 0 : 1;
-            const int kg = kstream ? p.L[0] + (kr - g.Lp[0]) : kr;
-            const int jq = qt * 16 - (qs ? g.Lp[0] : 0) + gq + (e >> 1) * 8;
-            const int qg = qs ? p.L[0] + jq : jq;
-            const uint64_t idx = (((uint64_t)b * p.heads + h) * Ltot + qg) * (uint64_t)Ltot + kg;
-            if (pr != 0.f) pr = dropout_keep(p.seed, p.offset, idx, thresh) ? pr * ksc : 0.f;
-          }
-          s[2 * kb + nt][e] = pr;
-        }
-    // O = P . V
-    float o[D / 8][4];
-#pragma unroll
-    for (int i = 0; i < D / 8; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
-#pragma unroll
-    for (int kb = 0; kb < MAXKB; ++kb) {
-      if (kb < nkb && pair_on(p.pair_mask, qs, (kb * 16 < g.Lp[0]) ? 0 : 1)) {
-        uint32_t a[4];
-        a[0] = pack_bf16x2(s[2 * kb][0], s[2 * kb][1]);
-        a[1] = pack_bf16x2(s[2 * kb][2], s[2 * kb][3]);
-        a[2] = pack_bf16x2(s[2 * kb + 1][0], s[2 * kb + 1][1]);
-        a[3] = pack_bf16x2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
-#pragma unroll
-        for (int nd = 0; nd < D / 16; ++nd) {
-          uint32_t bb[4];
-          TL::load_bt(Vs, kb * 16, nd * 16, bb);
-          mma16816(o[2 * nd], a, bb[0], bb[1]);
-          mma16816(o[2 * nd + 1], a, bb[2], bb[3]);
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int j = qt * 16 - (qs ? g.Lp[0] : 0) + gq + r * 8;
-      if (j < p.L[qs]) {
-        bf16* O = reinterpret_cast<bf16*>(p.ctx[qs]) + ((int64_t)b * p.L[qs] + j) * p.ld_ctx[qs] + h * D;
-#pragma unroll
-        for (int nd = 0; nd < D / 8; ++nd)
-          *reinterpret_cast<uint32_t*>(O + nd * 8 + 2 * tq) = pack_bf16x2(o[nd][r * 2], o[nd][r * 2 + 1]);
-      }
-    }
-  }
-}
-
-template <int D>
-__global__ void __launch_bounds__(128, D == 64 ? 4 : 2)
-mma_bwd_kernel(P p) {
-  extern __shared__ __align__(16) uint8_t smraw[];
-  using TL = Tile<D>;
-  const Geo g = make_geo(p);
-  bf16* Qs = reinterpret_cast<bf16*>(smraw);
-  bf16* Ks = Qs + g.R * TL::PITCH;
-  bf16* Vs = Ks + g.R * TL::PITCH;
-  bf16* dOs = Vs + g.R * TL::PITCH;
-  bf16* Os = dOs + g.R * TL::PITCH;
-  float* madd = reinterpret_cast<float*>(Os + g.R * TL::PITCH);
-  float* lse_s = madd + g.R;
-  float* delta_s = lse_s + g.R;
-  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int gq = lane >> 2, tq = lane & 3;
-  const int Ltot = p.L[0] + p.L[1];
-
-  load_rows<D>(Qs, p, g, b, h, p.qkv, p.ld, 0);
-  load_rows<D>(Ks, p, g, b, h, p.qkv, p.ld, p.A);
-  load_rows<D>(Vs, p, g, b, h, p.qkv, p.ld, 2 * p.A);
-  load_rows<D>(dOs, p, g, b, h, p.dctx, p.ld_ctx, 0);
-  {
-    const void* octx[2] = {p.ctx[0], p.ctx[1]};
-    load_rows<D>(Os, p, g, b, h, octx, p.ld_ctx, 0);
-  }
-  for (int r = threadIdx.x; r < g.R; r += blockDim.x) {
-    const int s = r < g.Lp[0] ? 0 : 1;
-    const int j = s ? r - g.Lp[0] : r;
-    const bool valid = j < p.L[s];
-    madd[r] = valid ? (p.mask[s][(int64_t)b * p.L[s] + j] ? 0.f : -10000.0f) : -INFINITY;
-    lse_s[r] = (valid && p.lse[s]) ? p.lse[s][((int64_t)b * p.heads + h) * p.L[s] + j] : INFINITY;  // pad rows: P = 0
-    delta_s[r] = 0.f;
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  {  // delta[r] = sum_d dO[r,d] * O[r,d]  (both tiles are in shared memory; padded rows are zero)
-    constexpr int CH = D / 8;
-    for (int e = threadIdx.x; e < g.R * CH; e += blockDim.x) {
-      const int r = e / CH, c = (e % CH) * 8;
-      float ov[8], dv[8];
-      Vec8<bf16>::load(Os + r * TL::PITCH + c, ov);
-      Vec8<bf16>::load(dOs + r * TL::PITCH + c, dv);
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc = fmaf(ov[k], dv[k], acc);
-      atomicAdd(delta_s + r, acc);
-    }
-  }
-  __syncthreads();
-
-  const int nb = g.R / 16;
-  // ---------------- phase 1: dQ (warp per 16-query tile) ----------------
-  for (int qt = warp; qt < nb; qt += 4) {
-    const int qs = (qt * 16 < g.Lp[0]) ? 0 : 1;
-    uint32_t aq[D / 16][4], ado[D / 16][4];
-#pragma unroll
-    for (int ks = 0; ks < D / 16; ++ks) {
-      TL::load_a(Qs, qt * 16, ks * 16, aq[ks]);
-      TL::load_a(dOs, qt * 16, ks * 16, ado[ks]);
-    }
-    float dq[D / 8][4];
-#pragma unroll
-    for (int i = 0; i < D / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
-    const uint32_t thresh = p.thresh[qs];
-    const float ksc = p.keep_scale[qs];
-    for (int kb = 0; kb < nb; ++kb) {
-      if (!pair_on(p.pair_mask, qs, (kb * 16 < g.Lp[0]) ? 0 : 1)) continue;
-      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks) {
-        uint32_t bk[4], bv[4];
-        TL::load_b(Ks, kb * 16, ks * 16, bk);
-        TL::load_b(Vs, kb * 16, ks * 16, bv);
-        mma16816(s[0], aq[ks], bk[0], bk[1]);
-        mma16816(s[1], aq[ks], bk[2], bk[3]);
-        mma16816(dp[0], ado[ks], bv[0], bv[1]);
-        mma16816(dp[1], ado[ks], bv[2], bv[3]);
-      }
-      float ds[2][4];
-#pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int kr = kb * 16 + nt * 8 + 2 * tq + (e & 1);
-          const int qr = qt * 16 + gq + (e >> 1) * 8;
-          const float pr = __expf(s[nt][e] * p.scale + madd[kr] - lse_s[qr]);
-          float dpe = dp[nt][e];
-          if (thresh && pr != 0.f) {
-            const int kstream = kr < g.Lp[0] ? 0 : 1;
-            const int kg = kstream ? p.L[0] + (kr - g.Lp[0]) : kr;
-            const int jq = qr - (qs ? g.Lp[0] : 0);
-            const int qg = qs ? p.L[0] + jq : jq;
-            const uint64_t idx = (((uint64_t)b * p.heads + h) * Ltot + qg) * (uint64_t)Ltot + kg;
-            dpe = dropout_keep(p.seed, p.offset, idx, thresh) ? dpe * ksc : 0.f;
-          }
-          ds[nt][e] = pr == 0.f ? 0.f : pr * (dpe - delta_s[qr]) * p.scale;
-        }
-      uint32_t a[4];
-      a[0] = pack_bf16x2(ds[0][0], ds[0][1]);
-      a[1] = pack_bf16x2(ds[0][2], ds[0][3]);
-      a[2] = pack_bf16x2(ds[1][0], ds[1][1]);
-      a[3] = pack_bf16x2(ds[1][2], ds[1][3]);
+      a[0] = pack_bf16x2(s[2 * kb][0], s[2 * kb][1]);
+      a[1] = pack_bf16x2(s[2 * kb][2], s[2 * kb][3]);
+      a[2] = pack_bf16x2(s[2 * kb + 1][0], s[2 * kb + 1][1]);   // zero when that n-tile is disabled
+      a[3] = pack_bf16x2(s[2 * kb + 1][2], s[2 * kb + 1][3]);
 #pragma unroll
       for (int nd = 0; nd < D / 16; ++nd) {
         uint32_t bb[4];
-        TL::load_bt(Ks, kb * 16, nd * 16, bb);
-        mma16816(dq[2 * nd], a, bb[0], bb[1]);
-        mma16816(dq[2 * nd + 1], a, bb[2], bb[3]);
-      }
-    }
-    if (p.dqkv[qs] != nullptr) {
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int j = qt * 16 - (qs ? g.Lp[0] : 0) + gq + r * 8;
-        if (j < p.L[qs]) {
-          bf16* dQ = reinterpret_cast<bf16*>(p.dqkv[qs]) + ((int64_t)b * p.L[qs] + j) * p.ld[qs] + h * D;
-#pragma unroll
-          for (int nd = 0; nd < D / 8; ++nd)
-            *reinterpret_cast<uint32_t*>(dQ + nd * 8 + 2 * tq) = pack_bf16x2(dq[nd][r * 2], dq[nd][r * 2 + 1]);
-        }
+        TL::load_bt(Vs, kb * 16, nd * 16, bb);
+        mma16816(o[2 * nd], a, bb[0], bb[1]);
+        mma16816(o[2 * nd + 1], a, bb[2], bb[3]);
       }
     }
   }
-  // ---------------- phase 2: dK, dV (warp per 16-key tile; S^T = K Q^T) ----------------
-  for (int kt = warp; kt < nb; kt += 4) {
-    const int kst = (kt * 16 < g.Lp[0]) ? 0 : 1;
+  // the warp's 16 Q rows are dead (only this warp read them): stage O there, then 16-byte coalesced stores
+  bf16* mine = Qs + qt * 16 * TL::PITCH;
+  __syncwarp();
+  frag_to_rows16<D>(mine, o, osc[0], osc[1]);
+  __syncwarp();
+  store_rows16<D>(mine, reinterpret_cast<bf16*>(p.ctx[qs]) + (int64_t)b * p.L[qs] * p.ld_ctx[qs] + h * D, p.ld_ctx[qs], jq0, p.L[qs]);
+}
+
+// ---------------------------------------------------------------------------------------------- backward
+template <int D>
+__global__ void __launch_bounds__(320)
+mma_bwd_kernel(P p) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  using TL = Tile<D>;
+  constexpr int CH = D / 8;
+  const Geo g = make_geo(p.pair_mask, p.L[0], p.L[1], blockIdx.y);
+  bf16* Qs = reinterpret_cast<bf16*>(smraw);
+  bf16* dOs = Qs + g.RQ * TL::PITCH;
+  bf16* Ks = dOs + g.RQ * TL::PITCH;
+  bf16* Vs = Ks + g.RK * TL::PITCH;
+  float* madd = reinterpret_cast<float*>(Vs + g.RK * TL::PITCH);
+  float* lse2 = madd + g.RK;                       // per query row: lse * log2(e); +inf on padding rows (P = 0)
+  float* delta = lse2 + g.RQ;                      // rowsum(dO * O)
+  uint32_t* rowt = reinterpret_cast<uint32_t*>(delta + g.RQ);  // dropout row terms
+  bf16* dSt = reinterpret_cast<bf16*>(rowt + g.RQ);            // dS^T [RK][RQ + 8]
+  const int SP = g.RQ + 8;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gq = lane >> 2, tq = lane & 3;
+  const int Ltot = p.L[0] + p.L[1];
+
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const bf16* base = reinterpret_cast<const bf16*>(p.qkv[s]) + (int64_t)b * p.L[s] * p.ld[s] + h * D;
+    if (g.qrows[s]) load_seg<D>(Qs + (s ? g.qrows[0] : 0) * TL::PITCH, base, p.ld[s], p.L[s], g.qrows[s]);
+    if (g.krows[s]) {
+      const int off = s ? g.krows[0] : 0;
+      load_seg<D>(Ks + off * TL::PITCH, base + p.A, p.ld[s], p.L[s], g.krows[s]);
+      load_seg<D>(Vs + off * TL::PITCH, base + 2 * p.A, p.ld[s], p.L[s], g.krows[s]);
+      load_madd(madd + off, p.mask[s] + (int64_t)b * p.L[s], p.L[s], g.krows[s]);
+    }
+  }
+  // dO -> shared memory through registers, delta = rowsum(dO * O) on the way (O itself is never staged)
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (!g.qrows[s]) continue;
+    const int off = s ? g.qrows[0] : 0;
+    const bf16* dO = reinterpret_cast<const bf16*>(p.dctx[s]) + (int64_t)b * p.L[s] * p.ld_ctx[s] + h * D;
+    const bf16* O = reinterpret_cast<const bf16*>(p.ctx[s]) + (int64_t)b * p.L[s] * p.ld_ctx[s] + h * D;
+    for (int e = threadIdx.x; e < g.qrows[s] * CH; e += blockDim.x) {   // warp-uniform trip count (multiple of 128)
+      const int r = e / CH, c = (e % CH) * 8;
+      uint4 vd = make_uint4(0u, 0u, 0u, 0u), vo = make_uint4(0u, 0u, 0u, 0u);
+      if (r < p.L[s]) {
+        vd = __ldg(reinterpret_cast<const uint4*>(dO + (int64_t)r * p.ld_ctx[s] + c));
+        vo = __ldg(reinterpret_cast<const uint4*>(O + (int64_t)r * p.ld_ctx[s] + c));
+      }
+      *reinterpret_cast<uint4*>(dOs + (off + r) * TL::PITCH + c) = vd;
+      const uint32_t* pd = reinterpret_cast<const uint32_t*>(&vd);
+      const uint32_t* po = reinterpret_cast<const uint32_t*>(&vo);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 x = unpack_bf16x2(pd[k]), y = unpack_bf16x2(po[k]);
+        acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
+      }
+#pragma unroll
+      for (int m = 1; m < CH; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
+      if ((e % CH) == 0) {
+        delta[off + r] = acc;
+        lse2[off + r] = r < p.L[s] ? p.lse[s][((int64_t)b * p.heads + h) * p.L[s] + r] * 1.4426950408889634f : INFINITY;
+        rowt[off + r] = attn_rowterm(p.seed, ((uint32_t)b * p.heads + h) * Ltot + (s ? p.L[0] : 0) + r);
+      }
+    }
+  }
+  cp_async_wait_all();
+  __syncthreads();
+
+  if (warp * 16 < g.RK) {
+    const int kt = warp;
+    const int ks = (kt * 16 < g.krows[0]) ? 0 : 1;
+    const int jk0 = kt * 16 - (ks ? g.krows[0] : 0);
+    const float sc2 = p.scale * 1.4426950408889634f;
     float dk[D / 8][4], dv[D / 8][4];
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) {
       dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
       dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
     }
-    for (int qb = 0; qb < nb; ++qb) {
-      const int qs = (qb * 16 < g.Lp[0]) ? 0 : 1;
-      if (!pair_on(p.pair_mask, qs, kst) || p.dctx[qs] == nullptr) continue;
+    const float md0 = madd[kt * 16 + gq], md1 = madd[kt * 16 + gq + 8];
+    const uint32_t ct0 = attn_colterm(p.seed, ks, jk0 + gq), ct1 = attn_colterm(p.seed, ks, jk0 + gq + 8);
+    const int hsh = (gq & 1) * 16;  // which 16-bit half of the pair hash belongs to this thread's keys
+#pragma unroll 1
+    for (int qb = 0; qb * 16 < g.RQ; ++qb) {
+      const int qs = (qb * 16 < g.qrows[0]) ? 0 : 1;
+      if (!pair_on(p.pair_mask, qs, ks)) continue;
       const uint32_t thresh = p.thresh[qs];
       const float ksc = p.keep_scale[qs];
       float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
-      for (int ks = 0; ks < D / 16; ++ks) {
+      for (int kk = 0; kk < D / 16; ++kk) {
         uint32_t ak[4], av[4], bq[4], bdo[4];
-        TL::load_a(Ks, kt * 16, ks * 16, ak);
-        TL::load_a(Vs, kt * 16, ks * 16, av);
-        TL::load_b(Qs, qb * 16, ks * 16, bq);
-        TL::load_b(dOs, qb * 16, ks * 16, bdo);
+        TL::load_a(Ks, kt * 16, kk * 16, ak);
+        TL::load_a(Vs, kt * 16, kk * 16, av);
+        TL::load_b(Qs, qb * 16, kk * 16, bq);
+        TL::load_b(dOs, qb * 16, kk * 16, bdo);
         mma16816(st[0], ak, bq[0], bq[1]);
         mma16816(st[1], ak, bq[2], bq[3]);
         mma16816(dpt[0], av, bdo[0], bdo[1]);
@@ -613,30 +646,33 @@ mma_bwd_kernel(P p) {
       }
       float pd[2][4], ds[2][4];
 #pragma unroll
-      for (int nt = 0; nt < 2; ++nt)
+      for (int nt = 0; nt < 2; ++nt) {
+        const int qr = qb * 16 + nt * 8 + 2 * tq;  // query rows qr, qr+1 (tile columns)
+        const float2 l2 = *reinterpret_cast<const float2*>(lse2 + qr);
+        const float2 dl = *reinterpret_cast<const float2*>(delta + qr);
+        const uint2 rt = *reinterpret_cast<const uint2*>(rowt + qr);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int kr = kt * 16 + gq + (e >> 1) * 8;              // key row (tile row)
-          const int qr = qb * 16 + nt * 8 + 2 * tq + (e & 1);      // query row (tile column)
-          const float pr = __expf(st[nt][e] * p.scale + madd[kr] - lse_s[qr]);
-          float pdv = pr, dpe = dpt[nt][e];
-          if (thresh && pr != 0.f) {
-            const int kg = kst ? p.L[0] + (kr - g.Lp[0]) : kr;
-            const int jq = qr - (qs ? g.Lp[0] : 0);
-            const int qg = qs ? p.L[0] + jq : jq;
-            const uint64_t idx = (((uint64_t)b * p.heads + h) * Ltot + qg) * (uint64_t)Ltot + kg;
-            const bool keep = dropout_keep(p.seed, p.offset, idx, thresh);
-            pdv = keep ? pr * ksc : 0.f;
-            dpe = keep ? dpe * ksc : 0.f;
+          const float pr = ex2f(fmaf(st[nt][e], sc2, (e >> 1) ? md1 : md0) - ((e & 1) ? l2.y : l2.x));
+          float pdv = pr * ksc, dpe = dpt[nt][e] * ksc;
+          if (thresh) {
+            const uint32_t hh = attn_mix(((e & 1) ? rt.y : rt.x) ^ ((e >> 1) ? ct1 : ct0));
+            if (((hh >> hsh) & 0xFFFFu) < thresh) { pdv = 0.f; dpe = 0.f; }
           }
           pd[nt][e] = pdv;
-          ds[nt][e] = pr == 0.f ? 0.f : pr * (dpe - delta_s[qr]) * p.scale;
+          ds[nt][e] = pr * (dpe - ((e & 1) ? dl.y : dl.x)) * p.scale;
         }
+      }
       uint32_t apd[4], ads[4];
       apd[0] = pack_bf16x2(pd[0][0], pd[0][1]); apd[1] = pack_bf16x2(pd[0][2], pd[0][3]);
       apd[2] = pack_bf16x2(pd[1][0], pd[1][1]); apd[3] = pack_bf16x2(pd[1][2], pd[1][3]);
       ads[0] = pack_bf16x2(ds[0][0], ds[0][1]); ads[1] = pack_bf16x2(ds[0][2], ds[0][3]);
       ads[2] = pack_bf16x2(ds[1][0], ds[1][1]); ads[3] = pack_bf16x2(ds[1][2], ds[1][3]);
+      {  // dS^T tile -> shared memory for the dQ phase
+        uint32_t* r0 = reinterpret_cast<uint32_t*>(dSt + (kt * 16 + gq) * SP + qb * 16 + 2 * tq);
+        uint32_t* r1 = reinterpret_cast<uint32_t*>(dSt + (kt * 16 + gq + 8) * SP + qb * 16 + 2 * tq);
+        r0[0] = ads[0]; r1[0] = ads[1]; r0[4] = ads[2]; r1[4] = ads[3];
+      }
 #pragma unroll
       for (int nd = 0; nd < D / 16; ++nd) {
         uint32_t bdo[4], bq[4];
@@ -648,19 +684,63 @@ mma_bwd_kernel(P p) {
         mma16816(dk[2 * nd + 1], ads, bq[2], bq[3]);
       }
     }
-    if (p.dqkv[kst] != nullptr) {
+    // dV, then dK: staged in the warp's own (now dead) V rows - its K rows are still read by the dQ phase -
+    // and stored as 16-byte coalesced rows
+    if (p.dqkv[ks] != nullptr) {
+      bf16* dst = reinterpret_cast<bf16*>(p.dqkv[ks]) + (int64_t)b * p.L[ks] * p.ld[ks] + h * D;
+      bf16* mv = Vs + kt * 16 * TL::PITCH;
+      __syncwarp();
+      frag_to_rows16<D>(mv, dv, 1.f, 1.f);
+      __syncwarp();
+      store_rows16<D>(mv, dst + 2 * p.A, p.ld[ks], jk0, p.L[ks]);
+      __syncwarp();
+      frag_to_rows16<D>(mv, dk, 1.f, 1.f);
+      __syncwarp();
+      store_rows16<D>(mv, dst + p.A, p.ld[ks], jk0, p.L[ks]);
+    }
+  }
+  __syncthreads();
+  // ---- dQ = dS . K : one warp per 16-query tile, dS through ldmatrix.trans from the dS^T tile
+  if (warp * 16 < g.RQ) {
+    const int qt = warp;
+    const int qs = (qt * 16 < g.qrows[0]) ? 0 : 1;
+    const int jq0 = qt * 16 - (qs ? g.qrows[0] : 0);
+    float dq[D / 8][4];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int j = kt * 16 - (kst ? g.Lp[0] : 0) + gq + r * 8;
-        if (j < p.L[kst]) {
-          bf16* dK = reinterpret_cast<bf16*>(p.dqkv[kst]) + ((int64_t)b * p.L[kst] + j) * p.ld[kst] + p.A + h * D;
-          bf16* dV = dK + p.A;
+    for (int i = 0; i < D / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
+    for (int kt = 0; kt * 16 < g.RK; ++kt) {
+      if (!pair_on(p.pair_mask, qs, (kt * 16 < g.krows[0]) ? 0 : 1)) continue;
+      uint32_t a[4];
+      TL::load_at(dSt, SP, qt * 16, kt * 16, a);
 #pragma unroll
-          for (int nd = 0; nd < D / 8; ++nd) {
-            *reinterpret_cast<uint32_t*>(dK + nd * 8 + 2 * tq) = pack_bf16x2(dk[nd][r * 2], dk[nd][r * 2 + 1]);
-            *reinterpret_cast<uint32_t*>(dV + nd * 8 + 2 * tq) = pack_bf16x2(dv[nd][r * 2], dv[nd][r * 2 + 1]);
-          }
-        }
+      for (int nd = 0; nd < D / 16; ++nd) {
+        uint32_t bk[4];
+        TL::load_bt(Ks, kt * 16, nd * 16, bk);
+        mma16816(dq[2 * nd], a, bk[0], bk[1]);
+        mma16816(dq[2 * nd + 1], a, bk[2], bk[3]);
+      }
+    }
+    if (p.dqkv[qs] != nullptr) {
+      bf16* mine = Qs + qt * 16 * TL::PITCH;  // nobody reads Q after the barrier
+      frag_to_rows16<D>(mine, dq, 1.f, 1.f);
+      __syncwarp();
+      store_rows16<D>(mine, reinterpret_cast<bf16*>(p.dqkv[qs]) + (int64_t)b * p.L[qs] * p.ld[qs] + h * D, p.ld[qs], jq0, p.L[qs]);
+    }
+  }
+  // streams that only supply keys (queries) get zero dQ (dK, dV)
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    if (p.dqkv[s] == nullptr) continue;
+    bf16* dst = reinterpret_cast<bf16*>(p.dqkv[s]) + (int64_t)b * p.L[s] * p.ld[s] + h * D;
+    if (g.qrows[s]) {
+    } else if (g.krows[s] && attn_groups(p.pair_mask) == 1) {
+      for (int e = threadIdx.x; e < p.L[s] * CH; e += blockDim.x)
+        *reinterpret_cast<uint4*>(dst + (int64_t)(e / CH) * p.ld[s] + (e % CH) * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (g.qrows[s] && !g.krows[s] && attn_groups(p.pair_mask) == 1) {
+      for (int e = threadIdx.x; e < p.L[s] * CH * 2; e += blockDim.x) {
+        const int r = e / (2 * CH), c = (e % (2 * CH)) * 8;  // K and V column blocks
+        *reinterpret_cast<uint4*>(dst + (int64_t)r * p.ld[s] + p.A + (c / D) * p.A + (c % D)) = make_uint4(0u, 0u, 0u, 0u);
       }
     }
   }
@@ -685,15 +765,16 @@ static int fill(const vb_attn_args& a, P& p, bool bwd) {
   }
   VB_REQUIRE(a.dropout_p_t >= 0.f && a.dropout_p_t < 1.f && a.dropout_p_v >= 0.f && a.dropout_p_v < 1.f, VB_ERR_ARG,
              "attention: dropout out of range");
-  p.qkv[0] = a.qkv_t; p.qkv[1] = a.qkv_v;
+  p.qkv[0] = (tq || tk) ? a.qkv_t : nullptr; p.qkv[1] = (vq || vk) ? a.qkv_v : nullptr;  // a stream no enabled pair touches is absent
   p.ld[0] = a.ld_t; p.ld[1] = a.ld_v;
   p.mask[0] = a.mask_t; p.mask[1] = a.mask_v;
   p.ctx[0] = tq ? a.ctx_t : nullptr; p.ctx[1] = vq ? a.ctx_v : nullptr;
   p.ld_ctx[0] = a.ld_ctx_t; p.ld_ctx[1] = a.ld_ctx_v;
   p.lse[0] = a.lse_t; p.lse[1] = a.lse_v;
   p.dctx[0] = tq ? a.dctx_t : nullptr; p.dctx[1] = vq ? a.dctx_v : nullptr;
-  p.dqkv[0] = a.dqkv_t; p.dqkv[1] = a.dqkv_v;
-  p.B = a.B; p.L[0] = a.qkv_t ? a.Lt : 0; p.L[1] = a.qkv_v ? a.Lv : 0;
+  p.dqkv[0] = p.qkv[0] ? a.dqkv_t : nullptr; p.dqkv[1] = p.qkv[1] ? a.dqkv_v : nullptr;
+  p.B = a.B; p.L[0] = p.qkv[0] ? a.Lt : 0; p.L[1] = p.qkv[1] ? a.Lv : 0;
+  p.ngroups = attn_groups(a.pair_mask);
   p.heads = a.heads; p.d = a.d; p.A = a.heads * a.d;
   p.pair_mask = a.pair_mask;
   p.scale = a.scale;
@@ -701,16 +782,33 @@ static int fill(const vb_attn_args& a, P& p, bool bwd) {
   p.thresh[1] = a.dropout_p_v > 0.f ? dropout_thresh(a.dropout_p_v) : 0u;
   p.keep_scale[0] = 1.f / (1.f - a.dropout_p_t);
   p.keep_scale[1] = 1.f / (1.f - a.dropout_p_v);
-  p.seed = a.seed; p.offset = a.offset;
+  p.seed = a.seed + a.offset;
   return 0;
 }
 
-static bool mma_ok(const vb_attn_args& a, const P& p, const char** why) {
+struct LaunchGeo { int warps_fwd, warps_bwd, nkb; size_t smem_fwd, smem_bwd; };
+static LaunchGeo launch_geo(const P& p, int d) {
+  LaunchGeo lg = {0, 0, 0, 0, 0};
+  const size_t pitch = (size_t)(d + 8) * 2;
+  for (int grp = 0; grp < p.ngroups; ++grp) {
+    const Geo g = make_geo(p.pair_mask, p.L[0], p.L[1], grp);
+    lg.warps_fwd = std::max(lg.warps_fwd, g.RQ / 16);
+    lg.warps_bwd = std::max(lg.warps_bwd, std::max(g.RQ, g.RK) / 16);
+    lg.nkb = std::max(lg.nkb, g.RK / 16);
+    lg.smem_fwd = std::max(lg.smem_fwd, (size_t)(g.RQ + 2 * g.RK) * pitch + (size_t)g.RK * 4);
+    lg.smem_bwd = std::max(lg.smem_bwd, (size_t)(2 * g.RQ + 2 * g.RK) * pitch + (size_t)(g.RK + 3 * g.RQ) * 4 +
+                                            (size_t)g.RK * (g.RQ + 8) * 2);
+  }
+  return lg;
+}
+
+static bool mma_ok(const vb_attn_args& a, const P& p, bool bwd, const char** why) {
   auto fail = [&](const char* w) { if (why) *why = w; return false; };
   if (a.dtype != VB_BF16) return fail("dtype is not bf16");
   if (a.d != 64 && a.d != 128) return fail("head size is not 64 or 128");
-  const int R = (p.qkv[0] ? ((p.L[0] + 15) & ~15) : 0) + (p.qkv[1] ? ((p.L[1] + 15) & ~15) : 0);
-  if (R > 160) return fail("more than 160 padded rows per (sample, head)");
+  const LaunchGeo lg = launch_geo(p, a.d);
+  if (lg.nkb > 10 || lg.warps_bwd > 10) return fail("more than 160 padded query or key rows per (sample, head)");
+  if ((bwd ? lg.smem_bwd : lg.smem_fwd) > 227 * 1024) return fail("tiles exceed 227 KB of shared memory");
   for (int s = 0; s < 2; ++s) {
     if (!p.qkv[s]) continue;
     if (!aligned16(p.qkv[s]) || (p.ld[s] % 8) != 0) return fail("qkv not 16-byte aligned");
@@ -733,33 +831,36 @@ static int run(const vb_attn_args& a, cudaStream_t st, bool bwd) {
   P p;
   int rc = fill(a, p, bwd);
   if (rc) return rc;
+  if (bwd) {  // a stream no enabled pair touches receives no gradient
+    const size_t es = a.dtype == VB_BF16 ? 2 : 4, width = (size_t)3 * a.heads * a.d * es;
+    if (a.dqkv_t && !p.qkv[0]) cudaMemset2DAsync(a.dqkv_t, (size_t)a.ld_t * es, 0, width, (size_t)a.B * a.Lt, st);
+    if (a.dqkv_v && !p.qkv[1]) cudaMemset2DAsync(a.dqkv_v, (size_t)a.ld_v * es, 0, width, (size_t)a.B * a.Lv, st);
+  }
   const char* why = nullptr;
-  const bool can_mma = mma_ok(a, p, &why);
+  const bool can_mma = mma_ok(a, p, bwd, &why);
   VB_REQUIRE(a.backend != VB_ATTN_MMA || can_mma, VB_ERR_UNSUPPORTED, "attention: MMA back-end cannot run: %s", why);
   const bool use_mma = can_mma && a.backend != VB_ATTN_SIMT;
   const unsigned grid = (unsigned)(a.B * a.heads);
   if (use_mma) {
-    const int R = (p.qkv[0] ? ((p.L[0] + 15) & ~15) : 0) + (p.qkv[1] ? ((p.L[1] + 15) & ~15) : 0);
-    const size_t tile = (size_t)R * (a.d + 8) * 2;
+    const LaunchGeo lg = launch_geo(p, a.d);
+    const dim3 g2(grid, (unsigned)p.ngroups);
     if (!bwd) {
-      const size_t smem = 3 * tile + R * sizeof(float);
-#define VB_FWD(D_, KB_)                                                   \
-  do {                                                                    \
-    if ((rc = set_smem(mma_fwd_kernel<D_, KB_>, smem))) return rc;        \
-    mma_fwd_kernel<D_, KB_><<<grid, 128, smem, st>>>(p);                  \
+#define VB_FWD(D_, KB_)                                                          \
+  do {                                                                           \
+    if ((rc = set_smem(mma_fwd_kernel<D_, KB_>, lg.smem_fwd))) return rc;        \
+    mma_fwd_kernel<D_, KB_><<<g2, lg.warps_fwd * 32, lg.smem_fwd, st>>>(p);      \
   } while (0)
-      if (a.d == 64) { if (R <= 96) VB_FWD(64, 6); else VB_FWD(64, 10); }
-      else { if (R <= 96) VB_FWD(128, 6); else VB_FWD(128, 10); }
+      if (a.d == 64) { if (lg.nkb <= 3) VB_FWD(64, 3); else if (lg.nkb <= 6) VB_FWD(64, 6); else VB_FWD(64, 10); }
+      else { if (lg.nkb <= 3) VB_FWD(128, 3); else if (lg.nkb <= 6) VB_FWD(128, 6); else VB_FWD(128, 10); }
 #undef VB_FWD
       return check_launch("attention mma_fwd_kernel");
     }
-    const size_t smem = 5 * tile + 3 * R * sizeof(float);
     if (a.d == 64) {
-      if ((rc = set_smem(mma_bwd_kernel<64>, smem))) return rc;
-      mma_bwd_kernel<64><<<grid, 128, smem, st>>>(p);
+      if ((rc = set_smem(mma_bwd_kernel<64>, lg.smem_bwd))) return rc;
+      mma_bwd_kernel<64><<<g2, lg.warps_bwd * 32, lg.smem_bwd, st>>>(p);
     } else {
-      if ((rc = set_smem(mma_bwd_kernel<128>, smem))) return rc;
-      mma_bwd_kernel<128><<<grid, 128, smem, st>>>(p);
+      if ((rc = set_smem(mma_bwd_kernel<128>, lg.smem_bwd))) return rc;
+      mma_bwd_kernel<128><<<g2, lg.warps_bwd * 32, lg.smem_bwd, st>>>(p);
     }
     return check_launch("attention mma_bwd_kernel");
   }

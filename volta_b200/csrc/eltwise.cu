@@ -67,6 +67,47 @@ colsum_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t cols, 
   }
 }
 
+// Vector version (the bias gradients of the big activations: rows ~ 9e3, cols 768..3072): every lane owns 8
+// adjacent columns (one 16-byte load of bf16), a warp covers 256 columns of a row, the 8 warps of the block walk
+// the slab's rows with 4 loads in flight each; partials meet in shared memory, one atomicAdd per column and block.
+template <typename T>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t cols, float* __restrict__ out, int64_t rows_per_block) {
+  __shared__ float part[8][32][9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c = ((int64_t)blockIdx.x * 32 + lane) * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < cols) {
+    int64_t r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      float v0[8], v1[8], v2[8], v3[8];
+      Vec8<T>::load(a + r * lda + c, v0);
+      Vec8<T>::load(a + (r + 8) * lda + c, v1);
+      Vec8<T>::load(a + (r + 16) * lda + c, v2);
+      Vec8<T>::load(a + (r + 24) * lda + c, v3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (v0[j] + v1[j]) + (v2[j] + v3[j]);
+    }
+    for (; r < r1; r += 8) {
+      float v0[8];
+      Vec8<T>::load(a + r * lda + c, v0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v0[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[warp][lane][j] = acc[j];
+  __syncthreads();
+  const int l2 = threadIdx.x >> 3, j2 = threadIdx.x & 7;
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += part[w][l2][j2];
+  const int64_t oc = ((int64_t)blockIdx.x * 32 + l2) * 8 + j2;
+  if (oc < cols) atomicAdd(out + oc, t);
+}
+
 template <typename T, bool SCATTER>
 __global__ void __launch_bounds__(256)
 rows_kernel(const T* __restrict__ a, int64_t lda, const int64_t* __restrict__ idx, T* __restrict__ out, int64_t ldo,
@@ -154,6 +195,20 @@ int vb_eltwise(int32_t op, const void* a, int32_t a_dtype, int64_t lda, const vo
 int vb_colsum(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t cols, float* out, void* stream) {
   VB_REQUIRE(a && out, VB_ERR_ARG, "colsum: null pointer");
   if (rows * cols == 0) return 0;
+  const int64_t es = dtype == VB_BF16 ? 2 : 4;
+  if (cols % 8 == 0 && lda % 8 == 0 && vb::aligned16(a) && rows >= 64) {
+    const int64_t strips = vb::ceil_div(cols, 256);
+    int64_t slabs = std::max<int64_t>(1, std::min<int64_t>(vb::ceil_div(rows, 32), (148 * 4) / strips));
+    const int64_t rpb = vb::ceil_div(vb::ceil_div(rows, slabs), 8) * 8;
+    slabs = vb::ceil_div(rows, rpb);
+    dim3 grid((unsigned)strips, (unsigned)slabs);
+    if (dtype == VB_BF16)
+      vb::elt::colsum_vec_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const vb::bf16*)a, lda, rows, cols, out, rpb);
+    else
+      vb::elt::colsum_vec_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, rows, cols, out, rpb);
+    (void)es;
+    return vb::check_launch("colsum_vec_kernel");
+  }
   const int64_t strips = vb::ceil_div(cols, 32);
   int64_t slabs = std::max<int64_t>(1, std::min<int64_t>(vb::ceil_div(rows, 64), (148 * 8) / std::max<int64_t>(1, strips)));
   const int64_t rpb = vb::ceil_div(rows, slabs);
