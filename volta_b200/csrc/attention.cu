@@ -365,11 +365,13 @@ __device__ __forceinline__ void cp_async_wait_all() {
 template <int D>
 __device__ __forceinline__ void load_seg(bf16* dst, const bf16* src, int64_t ld, int L, int Lp) {
   constexpr int CH = D / 8;
-  for (int e = threadIdx.x; e < Lp * CH; e += blockDim.x) {
-    const int r = e / CH, c = (e % CH) * 8;
-    const bool valid = r < L;
-    cp_async16(smem_u32(dst + r * Tile<D>::PITCH + c), valid ? (const void*)(src + (int64_t)r * ld + c) : (const void*)src, valid);
-  }
+  // thread -> (row r0 + k*rstep, fixed 16-byte column chunk): pointer increments only, no div/mod per copy
+  const int r0 = threadIdx.x / CH, c = (threadIdx.x % CH) * 8, rstep = blockDim.x / CH;
+  uint32_t d = smem_u32(dst + r0 * Tile<D>::PITCH + c);
+  const bf16* g = src + (int64_t)r0 * ld + c;
+  const uint32_t dstep = rstep * Tile<D>::PITCH * 2;
+  const int64_t gstep = (int64_t)rstep * ld;
+  for (int r = r0; r < Lp; r += rstep, d += dstep, g += gstep) cp_async16(d, r < L ? (const void*)g : (const void*)src, r < L);
 }
 // additive key mask in the log2 domain: 0 / -10000*log2(e) (encoders.py:983-991), -inf on padding rows
 __device__ __forceinline__ void load_madd(float* dst, const int32_t* mask, int L, int Lp) {
@@ -499,6 +501,7 @@ mma_fwd_kernel(P p) {
     const int Ltot = p.L[0] + p.L[1];
     const uint32_t row0 = ((uint32_t)b * p.heads + h) * Ltot + (qs ? p.L[0] : 0) + jq0 + gq;
     const uint32_t rt0 = attn_rowterm(p.seed, row0), rt1 = attn_rowterm(p.seed, row0 + 8);
+    const uint32_t thr_hi = thresh << 16;
 #pragma unroll
     for (int nt = 0; nt < 2 * NKB; ++nt) {
       if ((ntmask >> nt) & 1u) {
@@ -506,10 +509,10 @@ mma_fwd_kernel(P p) {
         const int ks = (kr < g.krows[0]) ? 0 : 1;
         const uint32_t ct = attn_colterm(p.seed, ks, kr - (ks ? g.krows[0] : 0));
         const uint32_t h0 = attn_mix(rt0 ^ ct), h1 = attn_mix(rt1 ^ ct);
-        if ((h0 & 0xFFFFu) < thresh) s[nt][0] = 0.f;
-        if ((h0 >> 16) < thresh) s[nt][1] = 0.f;
-        if ((h1 & 0xFFFFu) < thresh) s[nt][2] = 0.f;
-        if ((h1 >> 16) < thresh) s[nt][3] = 0.f;
+        if ((h0 << 16) < thr_hi) s[nt][0] = 0.f;   // low half: even key;  (r16 < thresh) <=> (r16 << 16 < thresh << 16)
+        if (h0 < thr_hi) s[nt][1] = 0.f;           // high half: odd key
+        if ((h1 << 16) < thr_hi) s[nt][2] = 0.f;
+        if (h1 < thr_hi) s[nt][3] = 0.f;
       }
     }
   }
@@ -552,7 +555,8 @@ mma_bwd_kernel(P p) {
   const Geo g = make_geo(p.pair_mask, p.L[0], p.L[1], blockIdx.y);
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
   bf16* dOs = Qs + g.RQ * TL::PITCH;
-  bf16* Ks = dOs + g.RQ * TL::PITCH;
+  bf16* Os = dOs + g.RQ * TL::PITCH;
+  bf16* Ks = Os + g.RQ * TL::PITCH;
   bf16* Vs = Ks + g.RK * TL::PITCH;
   float* madd = reinterpret_cast<float*>(Vs + g.RK * TL::PITCH);
   float* lse2 = madd + g.RK;                       // per query row: lse * log2(e); +inf on padding rows (P = 0)
@@ -576,39 +580,38 @@ mma_bwd_kernel(P p) {
       load_madd(madd + off, p.mask[s] + (int64_t)b * p.L[s], p.L[s], g.krows[s]);
     }
   }
-  // dO -> shared memory through registers, delta = rowsum(dO * O) on the way (O itself is never staged)
+  // dO and O tiles (O only feeds delta; its tile is reused for nothing else), per-query-row scalars
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     if (!g.qrows[s]) continue;
     const int off = s ? g.qrows[0] : 0;
-    const bf16* dO = reinterpret_cast<const bf16*>(p.dctx[s]) + (int64_t)b * p.L[s] * p.ld_ctx[s] + h * D;
-    const bf16* O = reinterpret_cast<const bf16*>(p.ctx[s]) + (int64_t)b * p.L[s] * p.ld_ctx[s] + h * D;
-    for (int e = threadIdx.x; e < g.qrows[s] * CH; e += blockDim.x) {   // warp-uniform trip count (multiple of 128)
-      const int r = e / CH, c = (e % CH) * 8;
-      uint4 vd = make_uint4(0u, 0u, 0u, 0u), vo = make_uint4(0u, 0u, 0u, 0u);
-      if (r < p.L[s]) {
-        vd = __ldg(reinterpret_cast<const uint4*>(dO + (int64_t)r * p.ld_ctx[s] + c));
-        vo = __ldg(reinterpret_cast<const uint4*>(O + (int64_t)r * p.ld_ctx[s] + c));
-      }
-      *reinterpret_cast<uint4*>(dOs + (off + r) * TL::PITCH + c) = vd;
-      const uint32_t* pd = reinterpret_cast<const uint32_t*>(&vd);
-      const uint32_t* po = reinterpret_cast<const uint32_t*>(&vo);
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 x = unpack_bf16x2(pd[k]), y = unpack_bf16x2(po[k]);
-        acc = fmaf(x.x, y.x, fmaf(x.y, y.y, acc));
-      }
-#pragma unroll
-      for (int m = 1; m < CH; m <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
-      if ((e % CH) == 0) {
-        delta[off + r] = acc;
-        lse2[off + r] = r < p.L[s] ? p.lse[s][((int64_t)b * p.heads + h) * p.L[s] + r] * 1.4426950408889634f : INFINITY;
-        rowt[off + r] = attn_rowterm(p.seed, ((uint32_t)b * p.heads + h) * Ltot + (s ? p.L[0] : 0) + r);
-      }
+    const int64_t head0 = (int64_t)b * p.L[s] * p.ld_ctx[s] + h * D;
+    load_seg<D>(dOs + off * TL::PITCH, reinterpret_cast<const bf16*>(p.dctx[s]) + head0, p.ld_ctx[s], p.L[s], g.qrows[s]);
+    load_seg<D>(Os + off * TL::PITCH, reinterpret_cast<const bf16*>(p.ctx[s]) + head0, p.ld_ctx[s], p.L[s], g.qrows[s]);
+    for (int r = threadIdx.x; r < g.qrows[s]; r += blockDim.x) {
+      lse2[off + r] = r < p.L[s] ? p.lse[s][((int64_t)b * p.heads + h) * p.L[s] + r] * 1.4426950408889634f : INFINITY;
+      rowt[off + r] = attn_rowterm(p.seed, ((uint32_t)b * p.heads + h) * Ltot + (s ? p.L[0] : 0) + r);
     }
   }
   cp_async_wait_all();
+  __syncthreads();
+  // delta[q] = sum_d dO[q,d] * O[q,d] = diag(dO . O^T): one 16x16 product per query tile on the tensor core
+  // (8 HMMA) instead of a per-element dot product; lane (gq, tq = gq/2) holds the diagonal entries of rows gq, gq+8.
+  if (warp * 16 < g.RQ) {
+    float dd[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      uint32_t a[4], bb[4];
+      TL::load_a(dOs, warp * 16, kk * 16, a);
+      TL::load_b(Os, warp * 16, kk * 16, bb);
+      mma16816(dd[0], a, bb[0], bb[1]);
+      mma16816(dd[1], a, bb[2], bb[3]);
+    }
+    if (tq == (gq >> 1)) {
+      delta[warp * 16 + gq] = (gq & 1) ? dd[0][1] : dd[0][0];
+      delta[warp * 16 + gq + 8] = (gq & 1) ? dd[1][3] : dd[1][2];
+    }
+  }
   __syncthreads();
 
   if (warp * 16 < g.RK) {
@@ -624,13 +627,15 @@ mma_bwd_kernel(P p) {
     }
     const float md0 = madd[kt * 16 + gq], md1 = madd[kt * 16 + gq + 8];
     const uint32_t ct0 = attn_colterm(p.seed, ks, jk0 + gq), ct1 = attn_colterm(p.seed, ks, jk0 + gq + 8);
-    const int hsh = (gq & 1) * 16;  // which 16-bit half of the pair hash belongs to this thread's keys
+    const int hshl = (gq & 1) ? 0 : 16;  // keys jk0+gq and jk0+gq+8 have the parity of gq: which half of the pair hash
+    const uint32_t thr_hi[2] = {p.thresh[0] << 16, p.thresh[1] << 16};
+    const float kscs[2] = {p.keep_scale[0], p.keep_scale[1]};
 #pragma unroll 1
     for (int qb = 0; qb * 16 < g.RQ; ++qb) {
       const int qs = (qb * 16 < g.qrows[0]) ? 0 : 1;
       if (!pair_on(p.pair_mask, qs, ks)) continue;
-      const uint32_t thresh = p.thresh[qs];
-      const float ksc = p.keep_scale[qs];
+      const uint32_t thr = qs ? thr_hi[1] : thr_hi[0];   // (r16 < thresh)  <=>  ((h << hshl) < thresh << 16)
+      const float ksc = qs ? kscs[1] : kscs[0];
       float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk) {
@@ -654,12 +659,10 @@ mma_bwd_kernel(P p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float pr = ex2f(fmaf(st[nt][e], sc2, (e >> 1) ? md1 : md0) - ((e & 1) ? l2.y : l2.x));
-          float pdv = pr * ksc, dpe = dpt[nt][e] * ksc;
-          if (thresh) {
-            const uint32_t hh = attn_mix(((e & 1) ? rt.y : rt.x) ^ ((e >> 1) ? ct1 : ct0));
-            if (((hh >> hsh) & 0xFFFFu) < thresh) { pdv = 0.f; dpe = 0.f; }
-          }
-          pd[nt][e] = pdv;
+          const uint32_t hh = attn_mix(((e & 1) ? rt.y : rt.x) ^ ((e >> 1) ? ct1 : ct0)) << hshl;
+          const bool keep = hh >= thr;              // thr == 0 (no dropout) keeps everything
+          pd[nt][e] = keep ? pr * ksc : 0.f;
+          const float dpe = keep ? dpt[nt][e] * ksc : 0.f;
           ds[nt][e] = pr * (dpe - ((e & 1) ? dl.y : dl.x)) * p.scale;
         }
       }
@@ -796,7 +799,7 @@ static LaunchGeo launch_geo(const P& p, int d) {
     lg.warps_bwd = std::max(lg.warps_bwd, std::max(g.RQ, g.RK) / 16);
     lg.nkb = std::max(lg.nkb, g.RK / 16);
     lg.smem_fwd = std::max(lg.smem_fwd, (size_t)(g.RQ + 2 * g.RK) * pitch + (size_t)g.RK * 4);
-    lg.smem_bwd = std::max(lg.smem_bwd, (size_t)(2 * g.RQ + 2 * g.RK) * pitch + (size_t)(g.RK + 3 * g.RQ) * 4 +
+    lg.smem_bwd = std::max(lg.smem_bwd, (size_t)(3 * g.RQ + 2 * g.RK) * pitch + (size_t)(g.RK + 3 * g.RQ) * 4 +
                                             (size_t)g.RK * (g.RQ + 8) * 2);
   }
   return lg;
