@@ -80,6 +80,28 @@ def test_gemm_wgrad_accumulate(backend, M, N, K, split):
     assert rel(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("tile", ["128x1", "192x1", "192x2", "256x2"])
+def test_gemm_tc_every_tile_configuration(tile, monkeypatch):
+    """Each instantiation of the tcgen05 kernel (tile width x CTA-group size) on all three operand layouts, ragged
+    edges, several persistent rounds and split-K; CTA pairs (x2) run the cta_group::2 protocol."""
+    monkeypatch.setenv("VOLTA_B200_GEMM_TILE", tile)
+    for (M, N, K) in [(300, 776, 328), (9472, 1536, 256), (129, 200, 64)]:
+        a, w, bias = rnd(M, K), rnd(N, K, scale=0.05), rnd(N, dtype=torch.float32)
+        res = rnd(M, N, seed=2)
+        out = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(a, w, out, epilogue=_lib.EPI_BIAS_ADD, bias=bias, aux_in=res, backend=_lib.GEMM_TC)
+        assert rel(out.float(), a.float() @ w.float().t() + bias + res.float()) < 6e-3, (tile, M, N, K, "fwd")
+        if tile != "192x2":  # an MN-major B splits between the CTAs of a pair only in 64-column blocks
+            wt = w.t().contiguous()  # [K, N]
+            out2 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+            ops.gemm(a, wt, out2, a_kmajor=True, b_kmajor=False, backend=_lib.GEMM_TC)
+            assert rel(out2.float(), a.float() @ w.float().t()) < 6e-3, (tile, M, N, K, "dgrad")
+            dy = rnd(M, N, scale=0.5, seed=4)
+            dW = torch.ones(N, K, device=DEV)
+            ops.gemm(dy, a, dW, a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ACCUM, backend=_lib.GEMM_TC)
+            assert rel(dW, 1.0 + dy.float().t() @ a.float()) < 2e-3, (tile, M, N, K, "wgrad")
+
+
 def test_gemm_tc_strided_rows_and_inplace_add():
     """The pooler reads row 0 of every sample through lda = T*H and adds its dgrad in place through ldd."""
     B, T, H, P = 64, 12, 256, 512

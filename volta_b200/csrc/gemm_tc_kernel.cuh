@@ -13,9 +13,20 @@
 // [9216 x 768] output: 1.95 waves on 148 SMs instead of 1.46 with BN = 256.  Operands may be K-major (row-major [rows, K]) or MN-major (row-major [K, rows]);
 // the latter is what dgrad (B = W[out,in]) and wgrad (A = dY, B = X) need, and is expressed purely
 // through the shared-memory matrix descriptors - no transposed copies are ever made.
+//
+// CG = 2 ("CTA pair", tcgen05 cta_group::2): two CTAs of a cluster on the two SMs of a TPC compute one 256 x BN tile.
+// Each CTA stages its own 128 rows of A but only HALF of the B tile (BN/2 rows); the leader CTA's single MMA thread
+// issues tcgen05.mma.cta_group::2 (M = 256), which reads both halves and writes each CTA's 128 x BN accumulator into
+// its own TMEM.  ncu showed the CG = 1 kernel pinned at the chip's L2->SM operand bandwidth (~12 TB/s of TMA loads,
+// tensor pipe ~50 % busy): a 128 x 192 tile pulls 40 KB per 64-deep k-block (79 FLOP/B); the pair's 256 x 256 tile
+// pulls 32 KB per CTA (131 FLOP/B).  Protocol: every CTA's TMA signals the LEADER's full barrier (mapa address,
+// .cta_group::2 copies); tcgen05.commit multicasts the smem-slot release and the accumulator-ready signal to both
+// CTAs; the peer's epilogue warps release the accumulator stage on the leader's barrier through DSMEM.
 #pragma once
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm_common.cuh"
@@ -32,14 +43,19 @@ constexpr int EPI_WARP0 = 4;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr uint32_t MN_BLOCK_BYTES = 64 * BK * 2;  // one 64(mn) x 64(k) MN-major TMA box = 8 KB
 
-template <int BN> struct Cfg {
-  static constexpr uint32_t B_STAGE_BYTES = BN * BK * 2;
+template <int BN, int CG> struct Cfg {
+  static_assert(BN == 128 || BN == 192 || BN == 256, "tile widths: 128, 192 or 256 columns");
+  static_assert(CG == 1 || CG == 2, "cta_group::1 or ::2");
+  static constexpr uint32_t B_ROWS = BN / CG;                      // B rows (tile columns) staged by ONE CTA
+  static constexpr uint32_t B_STAGE_BYTES = B_ROWS * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static_assert(BN == 128 || BN == 192, "tile widths: 128 or 192 columns");
-  static constexpr int STAGES = (BN == 192) ? 4 : 5;            // 160 KB of operand ring either way
-  static constexpr uint32_t TMEM_COLS = (BN == 192) ? 512 : 256;  // 2 accumulator stages, power of two
-  static constexpr size_t SMEM_BYTES = 1024 /*align slack*/ + (size_t)STAGES * STAGE_BYTES +
-                                       NUM_EPI_WARPS * 4608 /*epilogue staging*/ + 2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = (BN <= 128) ? 256 : 512;    // 2 accumulator stages, power of two
+  static constexpr size_t FIXED_BYTES = 1024 /*align slack*/ + NUM_EPI_WARPS * 4608 /*epilogue staging*/ +
+                                        2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+  static constexpr int STAGES_FIT = (int)((227 * 1024 - FIXED_BYTES) / STAGE_BYTES);
+  static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;    // CG1: 5 / 4 / 3,  CG2: 7 / 6 / 5 stages
+  static_assert(STAGES >= 3, "operand ring too shallow");
+  static constexpr size_t SMEM_BYTES = FIXED_BYTES + (size_t)STAGES * STAGE_BYTES;
 };
 
 struct Params {
@@ -97,6 +113,34 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- CTA-pair (cluster of 2) helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA-pair kernel: data lands in THIS CTA's shared memory, completion is counted on `bar`, a
+// shared::cluster address that may name the leader CTA's barrier.
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -104,12 +148,18 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-template <uint32_t COLS> __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+template <uint32_t COLS, int CG> __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {  // one warp of EACH CTA of the pair executes this
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
-template <uint32_t COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+template <uint32_t COLS, int CG> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(COLS) : "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread on behalf of the CTA.
@@ -122,9 +172,24 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+__device__ __forceinline__ void umma_bf16_cg2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
 // mbarrier arrives when all tcgen05.mma issued so far by this thread have completed.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// pair version: the barrier at this offset in BOTH CTAs of the pair receives the arrive
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
@@ -364,11 +429,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
   }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
+  // identical carve-up in both CTAs of a pair: the MMA descriptors and the multicast commits address the peer's
+  // shared memory by the same offsets (dynamic shared memory starts at the same window offset in every CTA).
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024 B alignment
   const uint32_t stg_u32 = smem_base + C::STAGES * C::STAGE_BYTES;
   uint8_t* stg_base = smem_raw + (stg_u32 - smem_u32(smem_raw));
@@ -383,6 +450,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto smem_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -390,13 +458,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), NUM_EPI_WARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG * NUM_EPI_WARPS); }
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_slot);
+  if (warp == 2) tmem_alloc<C::TMEM_COLS, CG>(tmem_slot);
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlaps
   // the tail of the previous kernel in the stream; global memory is only touched after this point.
@@ -404,44 +472,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int64_t tiles = (int64_t)p.num_m_blocks * p.num_n_blocks;
+  const int64_t tiles = (int64_t)p.num_m_blocks * p.num_n_blocks;   // tiles of (CG*128) x BN
   const int64_t total_work = tiles * p.split_k;
+  const int64_t first = blockIdx.x / CG, step = gridDim.x / CG;     // one work item per CTA (pair) at a time
 
   if (warp == 0 && lane == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====================
     int stage = 0; uint32_t phase = 0;
-    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x) {
+    for (int64_t w = first; w < total_work; w += step) {
       const int split = (int)(w % p.split_k);
       const int64_t tile = w / p.split_k;
       const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
+      const int m0 = (m_blk * CG + (int)rank) * BM;
+      const int n0 = n_blk * BN + (int)rank * (int)C::B_ROWS;
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+        uint32_t fb = full_bar(stage);
+        if constexpr (CG == 2) {
+          if (rank == 0) mbar_expect_tx(fb, 2 * C::STAGE_BYTES);  // both CTAs' copies complete on the leader's barrier
+          fb = mapa_shared(fb, 0);
+        } else {
+          mbar_expect_tx(fb, C::STAGE_BYTES);
+        }
+        auto load = [&](uint32_t dst, const CUtensorMap* map, int c0, int c1) {
+          if constexpr (CG == 2) tma_load_2d_cg2(dst, map, fb, c0, c1); else tma_load_2d(dst, map, fb, c0, c1);
+        };
         if (p.a_kmajor) {
-          tma_load_2d(smem_a(stage), &tmA, full_bar(stage), kb * BK, m_blk * BM);
+          load(smem_a(stage), &tmA, kb * BK, m0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BM / 64; ++j)
-            tma_load_2d(smem_a(stage) + j * MN_BLOCK_BYTES, &tmA, full_bar(stage), m_blk * BM + j * 64, kb * BK);
+          for (int j = 0; j < BM / 64; ++j) load(smem_a(stage) + j * MN_BLOCK_BYTES, &tmA, m0 + j * 64, kb * BK);
         }
         if (p.b_kmajor) {
-          tma_load_2d(smem_b(stage), &tmB, full_bar(stage), kb * BK, n_blk * BN);
+          load(smem_b(stage), &tmB, kb * BK, n0);
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_2d(smem_b(stage) + j * MN_BLOCK_BYTES, &tmB, full_bar(stage), n_blk * BN + j * 64, kb * BK);
+          for (int j = 0; j < (int)C::B_ROWS / 64; ++j) load(smem_b(stage) + j * MN_BLOCK_BYTES, &tmB, n0 + j * 64, kb * BK);
         }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1 && lane == 0) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && lane == 0 && rank == 0) {
+    // ===================== MMA issuer (leader CTA only) =====================
     int stage = 0; uint32_t phase = 0; int it = 0;
     const uint32_t a_step = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);  // bytes per UMMA_K step
     const uint32_t b_step = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
-    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+    for (int64_t w = first; w < total_work; w += step, ++it) {
       const int split = (int)(w % p.split_k);
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -456,20 +534,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t adesc = make_smem_desc(smem_a(stage) + k * a_step, p.a_kmajor);
           const uint64_t bdesc = make_smem_desc(smem_b(stage) + k * b_step, p.b_kmajor);
-          umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          if constexpr (CG == 2) umma_bf16_cg2(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          else umma_bf16(tmem_d, adesc, bdesc, p.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
-        umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs retire
+        // smem slot reusable (in both CTAs) once these MMAs retire
+        if constexpr (CG == 2) umma_commit_cg2(empty_bar(stage)); else umma_commit(empty_bar(stage));
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
-      umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
+      // accumulator ready for the epilogue warps (of both CTAs)
+      if constexpr (CG == 2) umma_commit_cg2(tfull_bar(as)); else umma_commit(tfull_bar(as));
     }
   } else if (warp >= EPI_WARP0) {
-    // ===================== epilogue =====================
+    // ===================== epilogue (every CTA drains its own 128 x BN accumulator) =====================
     const int ew = (warp - EPI_WARP0) & 3;    // == warp % 4: TMEM lane quarter this warp may access
     const int group = (warp - EPI_WARP0) >> 2;  // which half of the 32-column chunks
     uint8_t* stg = stg_base + (warp - EPI_WARP0) * STG_WARP_BYTES;
     int it = 0;
-    for (int64_t w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+    for (int64_t w = first; w < total_work; w += step, ++it) {
       const int64_t tile = w / p.split_k;
       const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
@@ -485,7 +566,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
       mbar_wait(tfull_bar(as), aphase);
       tcgen05_fence_after();
-      const int64_t m0 = (int64_t)m_blk * BM + ew * 32;
+      const int64_t m0 = ((int64_t)m_blk * CG + rank) * BM + ew * 32;
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
       if (m0 < p.epi.M) {  // warp-uniform
         if constexpr (EPI == VB_EPI_ACCUM) epilogue_tile<float, BN, EPI>(p.epi, tmem_acc, stg, m0, (int64_t)n_blk * BN, lane, group, bias_cur);
@@ -494,15 +575,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));  // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(tempty_bar(as));
+      }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();  // the peer's shared memory / TMEM stay valid until both are done
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    tmem_dealloc<C::TMEM_COLS, CG>(tmem_base);
   }
 }
 
@@ -549,31 +633,31 @@ inline int sm_count() {
   return g_sm_count;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 static int launch(const vb_gemm_args& a, cudaStream_t stream) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   Params p;
   int rc = fill_epi_params(a, p.epi);
   if (rc) return rc;
-  p.num_m_blocks = (int)ceil_div(a.M, BM);
+  p.num_m_blocks = (int)ceil_div(a.M, BM * CG);
   p.num_n_blocks = (int)ceil_div(a.N, BN);
   p.kb_total = (int)ceil_div(a.K, BK);
   p.a_kmajor = a.a_kmajor;
   p.b_kmajor = a.b_kmajor;
   const int64_t tiles = (int64_t)p.num_m_blocks * p.num_n_blocks;
+  const int64_t units = std::max(1, sm_count() / CG);  // CTAs (pairs) that run concurrently
   int split = 1;
   if (a.epilogue == VB_EPI_ACCUM) {
     split = a.split_k;
     if (split <= 0) {
       // Split-K for the weight gradients (few output tiles, long reduction).  Cost model in k-block units:
       // rounds over the SMs x (k-blocks per slice + epilogue of one fp32 red tile ~ 8 k-blocks); smallest wins.
-      const int64_t sms = sm_count();
       const int max_split = (int)std::max<int64_t>(1, p.kb_total / 4);
       int64_t best = -1;
       for (int s_ = 1; s_ <= max_split && s_ <= 64; ++s_) {
         const int64_t per = ceil_div(p.kb_total, s_);
         const int64_t eff = ceil_div(p.kb_total, per);
-        const int64_t cost = ceil_div(tiles * eff, sms) * (per + 8);
+        const int64_t cost = ceil_div(tiles * eff, units) * (per + 8);
         if (best < 0 || cost < best) { best = cost; split = s_; }
       }
     }
@@ -583,48 +667,76 @@ static int launch(const vb_gemm_args& a, cudaStream_t stream) {
   p.split_k = (int)ceil_div(p.kb_total, p.kb_per_split);
   // instruction descriptor (cute::UMMA::InstrDescriptor): F32 accum, BF16 x BF16, majors, N>>3, M>>4
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((a.a_kmajor ? 0u : 1u) << 15) | ((a.b_kmajor ? 0u : 1u) << 16) |
-            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
 
   CUtensorMap tmA, tmB;
   if (a.a_kmajor) rc = make_map(&tmA, a.A, a.M, a.K, a.lda, BM);
   else rc = make_map(&tmA, a.A, a.K, a.M, a.lda, BK);
   if (rc) return rc;
-  if (a.b_kmajor) rc = make_map(&tmB, a.B, a.N, a.K, a.ldb, BN);
+  if (a.b_kmajor) rc = make_map(&tmB, a.B, a.N, a.K, a.ldb, (int)C::B_ROWS);
   else rc = make_map(&tmB, a.B, a.K, a.N, a.ldb, BK);
   if (rc) return rc;
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
     VB_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(e));
     attr_set = true;
   }
   const int64_t work = tiles * p.split_k;
-  const int grid = (int)std::min<int64_t>(work, sm_count());
+  const int grid = (int)std::min<int64_t>(work, units) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI>, tmA, tmB, p);
+  if (CG == 2) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
+  cfg.attrs = attr;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, CG>, tmA, tmB, p);
   VB_REQUIRE(le == cudaSuccess, (int)le, "gemm_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   return check_launch("gemm_tc_kernel");
 }
 
-
-// Tile width: minimise (rounds over the SMs) x (tile width), i.e. wasted columns + wave quantisation.
+// Tile selection.  The kernel is bound by the L2 -> SM operand stream or by the tensor pipe, whichever is slower
+// (cycles per 64-deep k-block of one CTA): bytes / ~44 B per cycle per SM  vs  2 * BN cycles of MMA, plus the
+// epilogue tail of the last tile; total = rounds over the CTAs (pairs) x k-blocks x that.  CTA pairs (CG = 2) halve the
+// B-operand bytes; they need M > 128 to be worth the idle half, and an MN-major B splits only in 64-column blocks.
 template <int EPI>
 static int launch_epi(const vb_gemm_args& a, cudaStream_t stream) {
-  const int64_t mb = ceil_div(a.M, BM);
   const int64_t sms = std::max(1, sm_count());
-  auto cost = [&](int bn) { return ceil_div(mb * ceil_div(a.N, bn), sms) * bn; };
-  if (a.N <= 128 || (EPI != VB_EPI_ACCUM && cost(128) < cost(192))) return launch<128, EPI>(a, stream);
-  return launch<192, EPI>(a, stream);  // ACCUM: split-K evens out the waves, keep the wider tile
+  struct Opt { int bn, cg; };
+  const Opt opts[] = {{128, 1}, {192, 1}, {192, 2}, {256, 2}};
+  double best = -1.0;
+  Opt pick = {192, 1};
+  // VOLTA_B200_GEMM_TILE=<BN>x<CG> pins the tile (tests exercise every instantiation with it)
+  const char* force = getenv("VOLTA_B200_GEMM_TILE");
+  int fbn = 0, fcg = 0;
+  if (force && sscanf(force, "%dx%d", &fbn, &fcg) != 2) fbn = fcg = 0;
+  for (const Opt& o : opts) {
+    if (o.cg == 2 && !a.b_kmajor && ((o.bn / 2) % 64) != 0) continue;   // not expressible
+    if (fbn) {
+      if (o.bn == fbn && o.cg == fcg) { pick = o; best = 0.0; }
+      continue;
+    }
+    if (o.cg == 2 && (a.M <= 128 || (sms % 2) != 0)) continue;
+    if (o.bn > 128 && a.N <= 128 && o.cg == 1) continue;
+    const int64_t tiles = ceil_div(a.M, 128 * o.cg) * ceil_div(a.N, o.bn);
+    const int64_t rounds = ceil_div(tiles, sms / o.cg);
+    const double per_kb = std::max(2.0 * o.bn, (16384.0 + 128.0 * o.bn / o.cg) / 44.0);
+    double cost = (double)rounds * per_kb;
+    if (EPI == VB_EPI_ACCUM) cost = per_kb / o.bn;  // split-K evens out the rounds: cheapest bytes per column wins
+    if (best < 0 || cost < best) { best = cost; pick = o; }
+  }
+  if (pick.cg == 2) return pick.bn == 256 ? launch<256, EPI, 2>(a, stream) : launch<192, EPI, 2>(a, stream);
+  return pick.bn == 128 ? launch<128, EPI, 1>(a, stream) : launch<192, EPI, 1>(a, stream);
 }
 
 // one translation unit per group of epilogues (parallel build; each kernel gets its own register allocation)
