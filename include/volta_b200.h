@@ -47,6 +47,12 @@ const char* vb_last_error(void);      /* thread-local, never NULL */
 /* 0 if the current device is sm_100 (B200); VB_ERR_DEVICE otherwise. */
 int vb_device_check(void);
 int vb_sm_count(void);
+/* Device-resident seed base for CUDA-graph replay.  After vb_set_seed_pointer(p) (p: device uint64, or NULL to
+ * switch the feature off) every launch that draws a dropout mask - vb_gemm BIAS_DROP_RES, vb_layernorm_bwd dx_drop,
+ * vb_attention_fwd/bwd, vb_eltwise DROPOUT - uses `seed + *p`, read on the device when the kernel runs.  A captured
+ * graph therefore draws new masks on every replay once the host updates *p; forward and backward captured against
+ * the same p regenerate identical masks.  Process-wide; set it around capture, not concurrently with other launches. */
+int vb_set_seed_pointer(const void* dev_ptr);
 
 /* ---- GEMM -------------------------------------------------------------
  * D[M,N] = epilogue( sum_k opA[m,k] * opB[n,k] )

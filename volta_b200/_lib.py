@@ -47,6 +47,7 @@ SIGNATURES = {
     "vb_last_error": (C.c_char_p, []),
     "vb_device_check": (_i32, []),
     "vb_sm_count": (_i32, []),
+    "vb_set_seed_pointer": (_i32, [_vp]),
     "vb_gemm": (_i32, [C.POINTER(GemmArgs), _vp]),
     "vb_gemm_backend": (_i32, [C.POINTER(GemmArgs)]),
     "vb_layernorm_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _i32, _i32, _vp]),

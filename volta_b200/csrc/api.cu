@@ -16,6 +16,9 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static const uint64_t* g_seed_ptr = nullptr;
+const uint64_t* seed_pointer() { return g_seed_ptr; }
+
 int check_launch(const char* what) {
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
@@ -30,7 +33,12 @@ int check_launch(const char* what) {
 
 extern "C" {
 
-int vb_version(void) { return 1000; }
+int vb_version(void) { return 1001; }
+
+int vb_set_seed_pointer(const void* dev_ptr) {
+  vb::g_seed_ptr = reinterpret_cast<const uint64_t*>(dev_ptr);
+  return 0;
+}
 
 const char* vb_last_error(void) { return vb::g_err; }
 

@@ -30,6 +30,7 @@ struct P {
   uint32_t thresh[2];        // per query stream
   float keep_scale[2];
   uint64_t seed;             // seed + offset
+  const uint64_t* seed_ptr;  // see vb_set_seed_pointer
   int ngroups;               // MMA back-end: independent (query set, key set) groups per (sample, head)
 };
 
@@ -102,7 +103,7 @@ simt_fwd_kernel(P p) {
       float pr = __expf(pbuf[kg] - lse);
       if (p.thresh[qs]) {
         const int ks = kg < p.L[0] ? 0 : 1;
-        pr = attn_keep(p.seed, row_id, ks, ks ? kg - p.L[0] : kg, p.thresh[qs]) ? pr * p.keep_scale[qs] : 0.f;
+        pr = attn_keep(effective_seed(p.seed, p.seed_ptr), row_id, ks, ks ? kg - p.L[0] : kg, p.thresh[qs]) ? pr * p.keep_scale[qs] : 0.f;
       }
       pbuf[kg] = pr;
     }
@@ -171,7 +172,7 @@ simt_bwd_dq_kernel(P p) {
         }
         s = s * p.scale + (p.mask[ks][(int64_t)b * p.L[ks] + j] ? 0.f : -10000.0f);
         const float pr = __expf(s - lse);
-        if (p.thresh[qs]) dp = attn_keep(p.seed, row_id, ks, j, p.thresh[qs]) ? dp * p.keep_scale[qs] : 0.f;
+        if (p.thresh[qs]) dp = attn_keep(effective_seed(p.seed, p.seed_ptr), row_id, ks, j, p.thresh[qs]) ? dp * p.keep_scale[qs] : 0.f;
         ds = pr * (dp - delta) * p.scale;
       }
       pbuf[kg] = ds;
@@ -242,7 +243,7 @@ simt_bwd_dkv_kernel(P p) {
         float pd = pr;
         if (p.thresh[qs]) {
           const int qg = qs ? p.L[0] + i : i;
-          const bool keep = attn_keep(p.seed, ((uint32_t)b * p.heads + h) * Ltot + qg, ks, j, p.thresh[qs]);
+          const bool keep = attn_keep(effective_seed(p.seed, p.seed_ptr), ((uint32_t)b * p.heads + h) * Ltot + qg, ks, j, p.thresh[qs]);
           pd = keep ? pr * p.keep_scale[qs] : 0.f;
           dp = keep ? dp * p.keep_scale[qs] : 0.f;
         }
@@ -413,6 +414,7 @@ mma_fwd_kernel(P p) {
   bf16* Vs = Ks + g.RK * TL::PITCH;
   float* madd = reinterpret_cast<float*>(Vs + g.RK * TL::PITCH);
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const uint64_t seed_eff = effective_seed(p.seed, p.seed_ptr);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, tq = lane & 3;
 
@@ -500,14 +502,14 @@ mma_fwd_kernel(P p) {
   if (thresh) {
     const int Ltot = p.L[0] + p.L[1];
     const uint32_t row0 = ((uint32_t)b * p.heads + h) * Ltot + (qs ? p.L[0] : 0) + jq0 + gq;
-    const uint32_t rt0 = attn_rowterm(p.seed, row0), rt1 = attn_rowterm(p.seed, row0 + 8);
+    const uint32_t rt0 = attn_rowterm(seed_eff, row0), rt1 = attn_rowterm(seed_eff, row0 + 8);
     const uint32_t thr_hi = thresh << 16;
 #pragma unroll
     for (int nt = 0; nt < 2 * NKB; ++nt) {
       if ((ntmask >> nt) & 1u) {
         const int kr = nt * 8 + 2 * tq;
         const int ks = (kr < g.krows[0]) ? 0 : 1;
-        const uint32_t ct = attn_colterm(p.seed, ks, kr - (ks ? g.krows[0] : 0));
+        const uint32_t ct = attn_colterm(seed_eff, ks, kr - (ks ? g.krows[0] : 0));
         const uint32_t h0 = attn_mix(rt0 ^ ct), h1 = attn_mix(rt1 ^ ct);
         if ((h0 << 16) < thr_hi) s[nt][0] = 0.f;   // low half: even key;  (r16 < thresh) <=> (r16 << 16 < thresh << 16)
         if (h0 < thr_hi) s[nt][1] = 0.f;           // high half: odd key
@@ -565,6 +567,7 @@ mma_bwd_kernel(P p) {
   bf16* dSt = reinterpret_cast<bf16*>(rowt + g.RQ);            // dS^T [RK][RQ + 8]
   const int SP = g.RQ + 8;
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const uint64_t seed_eff = effective_seed(p.seed, p.seed_ptr);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, tq = lane & 3;
   const int Ltot = p.L[0] + p.L[1];
@@ -590,7 +593,7 @@ mma_bwd_kernel(P p) {
     load_seg<D>(Os + off * TL::PITCH, reinterpret_cast<const bf16*>(p.ctx[s]) + head0, p.ld_ctx[s], p.L[s], g.qrows[s]);
     for (int r = threadIdx.x; r < g.qrows[s]; r += blockDim.x) {
       lse2[off + r] = r < p.L[s] ? p.lse[s][((int64_t)b * p.heads + h) * p.L[s] + r] * 1.4426950408889634f : INFINITY;
-      rowt[off + r] = attn_rowterm(p.seed, ((uint32_t)b * p.heads + h) * Ltot + (s ? p.L[0] : 0) + r);
+      rowt[off + r] = attn_rowterm(seed_eff, ((uint32_t)b * p.heads + h) * Ltot + (s ? p.L[0] : 0) + r);
     }
   }
   cp_async_wait_all();
@@ -626,7 +629,7 @@ mma_bwd_kernel(P p) {
       dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = 0.f;
     }
     const float md0 = madd[kt * 16 + gq], md1 = madd[kt * 16 + gq + 8];
-    const uint32_t ct0 = attn_colterm(p.seed, ks, jk0 + gq), ct1 = attn_colterm(p.seed, ks, jk0 + gq + 8);
+    const uint32_t ct0 = attn_colterm(seed_eff, ks, jk0 + gq), ct1 = attn_colterm(seed_eff, ks, jk0 + gq + 8);
     const int hshl = (gq & 1) ? 0 : 16;  // keys jk0+gq and jk0+gq+8 have the parity of gq: which half of the pair hash
     const uint32_t thr_hi[2] = {p.thresh[0] << 16, p.thresh[1] << 16};
     const float kscs[2] = {p.keep_scale[0], p.keep_scale[1]};
@@ -786,6 +789,7 @@ static int fill(const vb_attn_args& a, P& p, bool bwd) {
   p.keep_scale[0] = 1.f / (1.f - a.dropout_p_t);
   p.keep_scale[1] = 1.f / (1.f - a.dropout_p_v);
   p.seed = a.seed + a.offset;
+  p.seed_ptr = seed_pointer();
   return 0;
 }
 

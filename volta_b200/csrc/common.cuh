@@ -166,6 +166,11 @@ __device__ __forceinline__ void dropout_keep2(uint64_t seed, uint64_t offset, ui
   k1 = (h >> 16) >= thresh;
 }
 
+// Device-resident seed base (vb_set_seed_pointer): when set, every dropout-bearing launch adds *ptr to its seed at run
+// time, so a captured CUDA graph draws fresh masks on every replay.  NULL = seeds are plain by-value arguments.
+const uint64_t* seed_pointer();
+__device__ __forceinline__ uint64_t effective_seed(uint64_t seed, const uint64_t* ptr) { return ptr ? seed + __ldg(ptr) : seed; }
+
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

@@ -32,8 +32,9 @@ __device__ __forceinline__ float apply(int op, float a, float b, float o, float 
 
 __global__ void __launch_bounds__(256)
 eltwise_kernel(int op, const void* a, int a_dt, int64_t lda, const void* b, int b_dt, int64_t ldb, void* out, int o_dt,
-               int64_t ldo, int64_t rows, int64_t cols, float alpha, uint32_t thresh, float scale, uint64_t seed,
-               uint64_t offset) {
+               int64_t ldo, int64_t rows, int64_t cols, float alpha, uint32_t thresh, float scale, uint64_t seed_in,
+               uint64_t offset, const uint64_t* seed_ptr) {
+  const uint64_t seed = effective_seed(seed_in, seed_ptr);
   const int64_t total = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols, c = i - r * cols;
@@ -188,7 +189,7 @@ int vb_eltwise(int32_t op, const void* a, int32_t a_dtype, int64_t lda, const vo
   const uint32_t thresh = (op == VB_ELT_DROPOUT && p > 0.f) ? vb::dropout_thresh(p) : 0u;
   vb::elt::eltwise_kernel<<<vb::elt::grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(
       op, a, a_dtype, lda, needs_b ? b : nullptr, b_dtype, ldb, out, out_dtype, ldo, rows, cols, alpha, thresh,
-      1.f / (1.f - p), seed, offset);
+      1.f / (1.f - p), seed, offset, vb::seed_pointer());
   return vb::check_launch("eltwise_kernel");
 }
 

@@ -17,6 +17,7 @@ struct EpiParams {
   float drop_scale;      // 1/(1-p)
   uint32_t drop_thresh;  // p * 2^16
   uint64_t seed, offset;
+  const uint64_t* seed_ptr;  // see vb_set_seed_pointer
   int32_t epilogue;      // VB_EPI_*
   int32_t d_bf16;        // 1: D/aux are bf16, 0: fp32
 };
@@ -34,7 +35,7 @@ __device__ __forceinline__ float epilogue_scalar(const EpiParams& p, float acc, 
     case VB_EPI_BIAS_DROP_RES: {
       float v = acc + bias;
       if (p.drop_thresh != 0u) {
-        const bool keep = dropout_keep(p.seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)n, p.drop_thresh);
+        const bool keep = dropout_keep(effective_seed(p.seed, p.seed_ptr), p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)n, p.drop_thresh);
         v = keep ? v * p.drop_scale : 0.0f;
       }
       return v + aux;

@@ -111,7 +111,7 @@ int fill_epi_params(const vb_gemm_args& a, EpiParams& p) {
   p.alpha = a.alpha == 0.f ? 1.f : a.alpha;
   p.drop_thresh = (a.epilogue == VB_EPI_BIAS_DROP_RES && a.dropout_p > 0.f) ? dropout_thresh(a.dropout_p) : 0u;
   p.drop_scale = 1.f / (1.f - a.dropout_p);
-  p.seed = a.seed; p.offset = a.offset;
+  p.seed = a.seed; p.offset = a.offset; p.seed_ptr = seed_pointer();
   p.epilogue = a.epilogue;
   p.d_bf16 = a.d_dtype == VB_BF16;
   return 0;

@@ -321,6 +321,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
   uint8_t* my_row = stg + lane * S::PITCH;
   const int64_t m = m0 + lane;
   const OutT* aux = reinterpret_cast<const OutT*>(p.aux_in);
+  uint64_t seed = 0;
+  if constexpr (EPI == VB_EPI_BIAS_DROP_RES) seed = effective_seed(p.seed, p.seed_ptr);
   uint4 pre[S::ITERS];
   if constexpr (use_aux) {
     if (nb0 + group * S::CW < p.N) S::load_regs(pre, aux, p.ld_aux, m0, nb0 + group * S::CW, p.M, p.N, lane);
@@ -377,14 +379,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
 #pragma unroll
             for (int h = 0; h < S::EV; h += 2) {
               bool k0, k1;
-              dropout_keep2(p.seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + h), p.drop_thresh, k0, k1);
+              dropout_keep2(seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + h), p.drop_thresh, k0, k1);
               acc[v * S::EV + h] = k0 ? acc[v * S::EV + h] * p.drop_scale : 0.f;
               acc[v * S::EV + h + 1] = k1 ? acc[v * S::EV + h + 1] * p.drop_scale : 0.f;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < S::EV; ++j)
-              acc[v * S::EV + j] = dropout_keep(p.seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + j), p.drop_thresh)
+              acc[v * S::EV + j] = dropout_keep(seed, p.offset, (uint64_t)m * (uint64_t)p.N + (uint64_t)(n + j), p.drop_thresh)
                                        ? acc[v * S::EV + j] * p.drop_scale : 0.f;
           }
         }

@@ -78,8 +78,9 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
 ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int H, float out_scale,
-              T* __restrict__ dx_drop, uint32_t drop_thresh, float drop_scale, uint64_t seed, uint64_t offset,
-              float* __restrict__ dbias) {
+              T* __restrict__ dx_drop, uint32_t drop_thresh, float drop_scale, uint64_t seed_in, uint64_t offset,
+              float* __restrict__ dbias, const uint64_t* __restrict__ seed_ptr) {
+  const uint64_t seed = effective_seed(seed_in, seed_ptr);
   extern __shared__ __align__(16) float red[];  // [3 or 2][WARPS][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
@@ -223,7 +224,7 @@ static int bwd_dispatch(const void* dy, const void* x, const float* mean, const 
       cudaFuncSetAttribute(ln_bwd_kernel<T, NV_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     ln_bwd_kernel<T, NV_, EX_><<<(unsigned)grid, WARPS * 32, smem, st>>>(                                        \
         (const T*)dy, (const T*)x, mean, rstd, gamma, (T*)dx, dgamma, dbeta, rows, H, out_scale, (T*)dx_drop,    \
-        thresh, scale, seed, offset, dbias);                                                                     \
+        thresh, scale, seed, offset, dbias, seed_pointer());                                                                     \
   } while (0)
 #define VB_LN_BWD2(NV_) do { if (extra) VB_LN_BWD(NV_, true); else VB_LN_BWD(NV_, false); } while (0)
   switch (nv) {

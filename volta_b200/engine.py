@@ -59,7 +59,7 @@ class Pair:
 class Runtime:
     """Per-call context: shapes, compute dtype, dropout seeds, parameter views."""
 
-    def __init__(self, model, device, B, T, V, training, grad=False):
+    def __init__(self, model, device, B, T, V, training, grad=False, seed_base=None):
         self.model = model
         self.store = model_store(model)
         self.precision = self.store.model.precision
@@ -69,7 +69,13 @@ class Runtime:
         self.Mt, self.Mv = B * T, B * V
         self.training = training
         self.grad_enabled = grad  # autograd.Function.forward runs with grad mode off: the caller decides
-        self._seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0  # CPU generator: no device sync
+        # CPU generator: no device sync.  Under graph capture the per-step seed lives on the device (graphs.py).
+        if seed_base is not None:
+            self._seed = seed_base
+        else:
+            self._seed = int(torch.randint(0, 2 ** 62, (1,)).item()) if training else 0
+        self.quiet = False               # graphs.py: no progress notifications while the forward is captured
+        self.progress_override = None    # graphs.py: receives the notifications while the backward is captured
         self._site = 0
         self.gemm_backend = {"auto": _lib.GEMM_AUTO, "tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT}[
             os.environ.get("VOLTA_B200_GEMM", "auto")]
@@ -95,7 +101,7 @@ class Runtime:
     def seed(self):
         """A fresh Philox seed per dropout site (masks are regenerated in the backward, never stored)."""
         self._site += 1
-        return (self._seed + 0x9E3779B97F4A7C15 * self._site) & 0x7FFFFFFFFFFFFFFF
+        return (self._seed + 0x9E3779B97F4A7C15 * self._site) & 0xFFFFFFFFFFFFFFFF  # uint64 wrap, as on the device
 
     def p(self, prob):
         return float(prob) if self.training else 0.0
@@ -904,10 +910,21 @@ _GRAD_HOOKS = {}
 _PROGRESS_HOOKS = {}
 
 
-def register_progress_hook(model, fn):
+_PROGRESS_CUTS = {}
+
+
+def register_progress_hook(model, fn, cut_fn_factory=None):
     """fn(frontier_offset): every gradient at flat offset >= frontier_offset is final (backward runs from the
-    heads towards the embeddings, i.e. from the end of the flat buffer to its start)."""
+    heads towards the embeddings, i.e. from the end of the flat buffer to its start).
+    cut_fn_factory() -> cut(frontier) -> bool tells the graph executor at which notifications the hook will act
+    (issue a collective), i.e. where the captured backward has to be cut into separately replayed segments."""
     _PROGRESS_HOOKS[id(model)] = fn
+    _PROGRESS_CUTS[id(model)] = cut_fn_factory
+
+
+def progress_cut_fn(model):
+    f = _PROGRESS_CUTS.get(id(model_store(model).model))
+    return f() if f is not None else None
 
 
 def _frontier(store, module, skip_below=0):
@@ -920,7 +937,9 @@ def _frontier(store, module, skip_below=0):
 
 
 def _notify_progress(rt, module, skip_below=0):
-    fn = _PROGRESS_HOOKS.get(id(rt.store.model))
+    if rt.quiet:
+        return
+    fn = rt.progress_override or _PROGRESS_HOOKS.get(id(rt.store.model))
     if fn is None:
         return
     off = _frontier(rt.store, module, skip_below)
@@ -965,6 +984,10 @@ def pretraining_forward(model, input_ids, image_feat, image_loc, token_type_ids,
     if anchor is None:
         with torch.no_grad():
             return _PretrainFn.apply(None, model, args)
+    from . import graphs
+    out = graphs.maybe_run(model, anchor, args)
+    if out is not None:
+        return out
     return _PretrainFn.apply(anchor, model, args)
 
 

@@ -69,6 +69,25 @@ class GradBucketer:
         if self.hi - lo >= self.message_size or lo == 0:
             self._issue(lo, self.hi)
 
+    def simulate(self):
+        """cut(frontier) -> bool: would `advance(frontier)` issue a collective?  Replays the bucketing decisions
+        on a private copy of the state; the CUDA-graph executor cuts the captured backward at those points."""
+        state = {"hi": self.total}
+
+        def cut(frontier):
+            frontier = max(0, min(int(frontier), state["hi"]))
+            candidates = [b for b in self.boundaries if frontier <= b < state["hi"]]
+            if frontier == 0:
+                candidates.append(0)
+            if not candidates:
+                return False
+            lo = min(candidates)
+            if (state["hi"] - lo >= self.message_size or lo == 0) and state["hi"] > lo:
+                state["hi"] = lo
+                return True
+            return False
+        return cut
+
     def finish(self):
         self._issue(0, self.hi)
         for work, chunk in self.works:
@@ -96,7 +115,7 @@ class DistributedDataParallel(torch.nn.Module):
         self._bucketer = None
         self.last_num_buckets = 0
         self._broadcast_params()
-        engine.register_progress_hook(module, self._on_progress)
+        engine.register_progress_hook(module, self._on_progress, self._make_cut_fn)
         engine.register_grad_ready_hook(module, self._on_done)
 
     def _device(self):
@@ -131,6 +150,11 @@ class DistributedDataParallel(torch.nn.Module):
         if b.hi == b.total and not b.works:
             b.reset()
         b.advance(frontier_offset)
+
+    def _make_cut_fn(self):
+        if self.delay_allreduce or self.world_size == 1:
+            return lambda frontier: False
+        return self._ensure_bucketer().simulate()
 
     def _on_done(self):
         if self.world_size == 1:
