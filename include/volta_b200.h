@@ -108,6 +108,9 @@ typedef struct vb_gemm_args {
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
+/* Measurement helper (bench.py's roofline leg): launches the same GEMM `repeats` times back to back between two CUDA
+ * events on `stream` and returns the average device time per launch in milliseconds.  Synchronises the stream. */
+int vb_gemm_bench(const vb_gemm_args* args, void* stream, int32_t repeats, float* ms_per_launch);
 /* Which backend vb_gemm would use for these arguments (VB_GEMM_TC / VB_GEMM_SIMT). */
 int vb_gemm_backend(const vb_gemm_args* args);
 

@@ -50,6 +50,7 @@ SIGNATURES = {
     "vb_set_seed_pointer": (_i32, [_vp]),
     "vb_gemm": (_i32, [C.POINTER(GemmArgs), _vp]),
     "vb_gemm_backend": (_i32, [C.POINTER(GemmArgs)]),
+    "vb_gemm_bench": (_i32, [C.POINTER(GemmArgs), _vp, _i32, C.POINTER(C.c_float)]),
     "vb_layernorm_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _i32, _i32, _vp]),
     "vb_layernorm_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _vp, _f, _u64, _u64, _vp, _i32, _vp]),
     "vb_attention_fwd": (_i32, [C.POINTER(AttnArgs), _vp]),

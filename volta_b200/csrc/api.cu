@@ -69,6 +69,26 @@ int vb_gemm_backend(const vb_gemm_args* a) {
   return vb::gemm_tc_supported(*a, nullptr) ? VB_GEMM_TC : VB_GEMM_SIMT;
 }
 
+int vb_gemm(const vb_gemm_args* a, void* stream);
+
+int vb_gemm_bench(const vb_gemm_args* a, void* stream, int32_t repeats, float* ms_per_launch) {
+  VB_REQUIRE(a != nullptr && ms_per_launch != nullptr && repeats > 0, VB_ERR_ARG, "vb_gemm_bench: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaEvent_t e0, e1;
+  VB_REQUIRE(cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess, VB_ERR_DEVICE, "vb_gemm_bench: no events");
+  int rc = vb_gemm(a, stream);  // warm: tensor maps, attributes, L2
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < repeats && rc == 0; ++i) rc = vb_gemm(a, stream);
+  cudaEventRecord(e1, st);
+  cudaEventSynchronize(e1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / (float)repeats;
+  return rc;
+}
+
 int vb_gemm(const vb_gemm_args* a, void* stream) {
   VB_REQUIRE(a != nullptr, VB_ERR_ARG, "vb_gemm: null args");
   VB_REQUIRE(a->ab_dtype == VB_F32 || a->ab_dtype == VB_BF16, VB_ERR_ARG, "vb_gemm: bad ab_dtype %d", a->ab_dtype);

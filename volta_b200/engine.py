@@ -30,7 +30,6 @@ LN_EPS = 1e-12
 
 # counters the benchmark reads: kernels launched through the C ABI in this process
 launch_count = 0
-GEMM_TIMER = None  # set to a list by bench.py to time every GEMM launch with CUDA events
 
 
 def _count(n=1):
@@ -120,20 +119,7 @@ class Runtime:
     def gemm(self, a, b, out, **k):
         _count()
         k.setdefault("backend", self.gemm_backend)
-        if GEMM_TIMER is None:
-            return ops.gemm(a, b, out, **k)
-        # bench.py's roofline leg: CUDA events around every GEMM launch on the launching stream
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        r = ops.gemm(a, b, out, **k)
-        e1.record()
-        M = k.get("M") or (a.shape[0] if k.get("a_kmajor", True) else a.shape[1])
-        N = k.get("N") or (b.shape[0] if k.get("b_kmajor", True) else b.shape[1])
-        K = k.get("K") or (a.shape[1] if k.get("a_kmajor", True) else a.shape[0])
-        tc = ops.gemm_backend(a, b, out, **{kk: vv for kk, vv in k.items() if kk in ("a_kmajor", "b_kmajor", "epilogue", "backend")}) == _lib.GEMM_TC
-        shape = "M%d N%d K%d a%d b%d epi%d" % (M, N, K, k.get("a_kmajor", True), k.get("b_kmajor", True), k.get("epilogue", 0))
-        GEMM_TIMER.append((2.0 * M * N * K, e0, e1, tc, shape))
-        return r
+        return ops.gemm(a, b, out, **k)
 
 
 def model_store(model):

@@ -80,7 +80,15 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bia
     g.aux_in, g.aux_out, g.ld_aux = _ptr(aux_in), _ptr(aux_out), ld_aux
     g.alpha, g.dropout_p, g.seed, g.offset, g.split_k = 1.0, float(dropout_p), int(seed), int(offset), int(split_k)
     _lib.call("vb_gemm", C.byref(g), _stream())
+    if GEMM_BENCH is not None:  # bench.py: device time of this launch, repeated back to back (no host gaps)
+        ms = C.c_float(0.0)
+        _lib.call("vb_gemm_bench", C.byref(g), _stream(), 5, C.byref(ms))
+        GEMM_BENCH.append((2.0 * M * N * K, ms.value, _lib.load().vb_gemm_backend(C.byref(g)) == _lib.GEMM_TC,
+                           "M%d N%d K%d a%d b%d epi%d" % (M, N, K, a_kmajor, b_kmajor, epilogue)))
     return out
+
+
+GEMM_BENCH = None  # set to a list by bench.py
 
 
 def gemm_backend(a, b, out, **kw):
