@@ -37,8 +37,9 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;               // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 384;
-constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_EPI_WARPS = 8;                     // two per SM sub-partition (TMEM lane quarter = warp % 4); 12 warps cap the kernel at 128 registers and the aux epilogues spill
+constexpr int NUM_EPI_GROUPS = NUM_EPI_WARPS / 4;   // warps of a lane quarter take the 32-column chunks round-robin
+constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int EPI_WARP0 = 4;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr uint32_t MN_BLOCK_BYTES = 64 * BK * 2;  // one 64(mn) x 64(k) MN-major TMA box = 8 KB
@@ -236,9 +237,17 @@ template <typename OutT> struct Stg {
   static constexpr int ITERS = 32 / RPI;                 // accesses per tile (4 / 8)
   static constexpr uint32_t PITCH = CW * sizeof(OutT) + 16;  // 80 B / 144 B: conflict-free for both access patterns
 
-  // coalesced global -> registers (rows of this warp; zero fill out of range)
+  // coalesced global -> registers (rows of this warp; zero fill out of range).  INTERIOR: the whole 32 x CW chunk is
+  // inside the matrix - one base pointer, no per-vector bounds logic (the common case; ~25 instructions less per vector).
+  template <bool INTERIOR>
   static __device__ __forceinline__ void load_regs(uint4 (&r)[ITERS], const OutT* g, int64_t ld, int64_t m0, int64_t n0,
                                                    int64_t M, int64_t N, int lane) {
+    if constexpr (INTERIOR) {
+      const OutT* src = g + (m0 + lane / VPR) * ld + n0 + (lane % VPR) * EV;
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i) r[i] = *reinterpret_cast<const uint4*>(src + (int64_t)(i * RPI) * ld);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < ITERS; ++i) {
       const int row = i * RPI + lane / VPR, v = lane % VPR;
@@ -264,8 +273,17 @@ template <typename OutT> struct Stg {
       *reinterpret_cast<uint4*>(stg + (i * RPI + lane / VPR) * PITCH + (lane % VPR) * 16) = r[i];
   }
   // coalesced staging -> global store
+  template <bool INTERIOR>
   static __device__ __forceinline__ void store_tile(const uint8_t* stg, OutT* g, int64_t ld, int64_t m0, int64_t n0,
                                                     int64_t M, int64_t N, int lane) {
+    if constexpr (INTERIOR) {
+      OutT* dst = g + (m0 + lane / VPR) * ld + n0 + (lane % VPR) * EV;
+      const uint8_t* src = stg + (lane / VPR) * PITCH + (lane % VPR) * 16;
+#pragma unroll
+      for (int i = 0; i < ITERS; ++i)
+        *reinterpret_cast<uint4*>(dst + (int64_t)(i * RPI) * ld) = *reinterpret_cast<const uint4*>(src + i * RPI * PITCH);
+      return;
+    }
 #pragma unroll
     for (int i = 0; i < ITERS; ++i) {
       const int row = i * RPI + lane / VPR, v = lane % VPR;
@@ -286,9 +304,22 @@ template <typename OutT> struct Stg {
 };
 
 // coalesced staging -> global fp32 reduction (split-K / shared-weight accumulation)
+template <bool INTERIOR>
 __device__ __forceinline__ void red_tile(const uint8_t* stg, float* g, int64_t ld, int64_t m0, int64_t n0, int64_t M,
                                          int64_t N, int lane) {
   using S = Stg<float>;
+  if constexpr (INTERIOR) {
+    float* dst = g + (m0 + lane / S::VPR) * ld + n0 + (lane % S::VPR) * 4;
+    if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0 && (ld & 3) == 0) {
+      const uint8_t* src = stg + (lane / S::VPR) * S::PITCH + (lane % S::VPR) * 16;
+#pragma unroll
+      for (int i = 0; i < S::ITERS; ++i) {
+        const float4 val = *reinterpret_cast<const float4*>(src + i * S::RPI * S::PITCH);
+        red_add_v4(dst + (int64_t)(i * S::RPI) * ld, val.x, val.y, val.z, val.w);
+      }
+      return;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < S::ITERS; ++i) {
     const int row = i * S::RPI + lane / S::VPR, v = lane % S::VPR;
@@ -309,7 +340,7 @@ __device__ __forceinline__ void red_tile(const uint8_t* stg, float* g, int64_t l
 
 // All chunks of one tile that belong to this warp.  EPI is a compile-time constant: the epilogue kind is
 // dispatched ONCE per tile (a per-element switch made the unrolled body overflow the instruction cache).
-template <typename OutT, int BN, int EPI>
+template <typename OutT, int BN, int EPI, bool INTERIOR>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, uint8_t* stg, int64_t m0, int64_t nb0,
                                            int lane, int group, const float* bias_s) {
   using S = Stg<OutT>;
@@ -325,10 +356,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
   if constexpr (EPI == VB_EPI_BIAS_DROP_RES) seed = effective_seed(p.seed, p.seed_ptr);
   uint4 pre[S::ITERS];
   if constexpr (use_aux) {
-    if (nb0 + group * S::CW < p.N) S::load_regs(pre, aux, p.ld_aux, m0, nb0 + group * S::CW, p.M, p.N, lane);
+    if (nb0 + group * S::CW < p.N) S::template load_regs<INTERIOR>(pre, aux, p.ld_aux, m0, nb0 + group * S::CW, p.M, p.N, lane);
   }
 #pragma unroll 1
-  for (int c = group; c < NCH; c += 2) {
+  for (int c = group; c < NCH; c += NUM_EPI_GROUPS) {
     const int64_t n0 = nb0 + c * S::CW;
     if (n0 >= p.N) break;  // warp-uniform
     uint32_t raw[32];
@@ -337,7 +368,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
       S::regs_to_stage(pre, stg, lane);
       __syncwarp();
       // prefetch the next chunk's residual / derivative tile while this chunk is processed
-      if (c + 2 < NCH && n0 + 2 * S::CW < p.N) S::load_regs(pre, aux, p.ld_aux, m0, n0 + 2 * S::CW, p.M, p.N, lane);
+      if (c + NUM_EPI_GROUPS < NCH && n0 + NUM_EPI_GROUPS * S::CW < p.N)
+        S::template load_regs<INTERIOR>(pre, aux, p.ld_aux, m0, n0 + NUM_EPI_GROUPS * S::CW, p.M, p.N, lane);
     }
     tmem_ld_wait();
     float acc[S::CW];
@@ -411,10 +443,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
     }
     __syncwarp();
     if constexpr (EPI == VB_EPI_ACCUM) {
-      if constexpr (sizeof(OutT) == 4) red_tile(stg, reinterpret_cast<float*>(p.D), p.ldd, m0, n0, p.M, p.N, lane);
+      if constexpr (sizeof(OutT) == 4) red_tile<INTERIOR>(stg, reinterpret_cast<float*>(p.D), p.ldd, m0, n0, p.M, p.N, lane);
     } else {
       if constexpr (EPI == VB_EPI_BIAS_GELU) {
-        S::store_tile(stg, reinterpret_cast<OutT*>(p.aux_out), p.ld_aux, m0, n0, p.M, p.N, lane);
+        S::template store_tile<INTERIOR>(stg, reinterpret_cast<OutT*>(p.aux_out), p.ld_aux, m0, n0, p.M, p.N, lane);
         __syncwarp();
 #pragma unroll
         for (int v = 0; v < S::VPR; ++v) {
@@ -425,13 +457,13 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
         }
         __syncwarp();
       }
-      S::store_tile(stg, reinterpret_cast<OutT*>(p.D), p.ldd, m0, n0, p.M, p.N, lane);
+      S::template store_tile<INTERIOR>(stg, reinterpret_cast<OutT*>(p.D), p.ldd, m0, n0, p.M, p.N, lane);
     }
     __syncwarp();
   }
 }
 
-template <int BN, int EPI, int CG>
+template <int BN, int EPI, int CG, typename OutT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
   using C = Cfg<BN, CG>;
@@ -549,7 +581,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue (every CTA drains its own 128 x BN accumulator) =====================
     const int ew = (warp - EPI_WARP0) & 3;    // == warp % 4: TMEM lane quarter this warp may access
-    const int group = (warp - EPI_WARP0) >> 2;  // which half of the 32-column chunks
+    const int group = (warp - EPI_WARP0) >> 2;  // which share of the 32-column chunks
     uint8_t* stg = stg_base + (warp - EPI_WARP0) * STG_WARP_BYTES;
     int it = 0;
     for (int64_t w = first; w < total_work; w += step, ++it) {
@@ -571,9 +603,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int64_t m0 = ((int64_t)m_blk * CG + rank) * BM + ew * 32;
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
       if (m0 < p.epi.M) {  // warp-uniform
-        if constexpr (EPI == VB_EPI_ACCUM) epilogue_tile<float, BN, EPI>(p.epi, tmem_acc, stg, m0, (int64_t)n_blk * BN, lane, group, bias_cur);
-        else if (p.epi.d_bf16) epilogue_tile<bf16, BN, EPI>(p.epi, tmem_acc, stg, m0, (int64_t)n_blk * BN, lane, group, bias_cur);
-        else epilogue_tile<float, BN, EPI>(p.epi, tmem_acc, stg, m0, (int64_t)n_blk * BN, lane, group, bias_cur);
+        const int64_t nb0 = (int64_t)n_blk * BN;
+        const bool interior = m0 + 32 <= p.epi.M && nb0 + BN <= p.epi.N;  // warp-uniform
+        // OutT is a kernel template parameter: one epilogue body per kernel (code size, register allocation)
+        if (interior) epilogue_tile<OutT, BN, EPI, true>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur);
+        else epilogue_tile<OutT, BN, EPI, false>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -635,8 +669,8 @@ inline int sm_count() {
   return g_sm_count;
 }
 
-template <int BN, int EPI, int CG>
-static int launch(const vb_gemm_args& a, cudaStream_t stream) {
+template <int BN, int EPI, int CG, typename OutT>
+static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
   using C = Cfg<BN, CG>;
   Params p;
   int rc = fill_epi_params(a, p.epi);
@@ -681,7 +715,7 @@ static int launch(const vb_gemm_args& a, cudaStream_t stream) {
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, CG, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
     VB_REQUIRE(e == cudaSuccess, (int)e, "cudaFuncSetAttribute(gemm_tc): %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -702,9 +736,15 @@ static int launch(const vb_gemm_args& a, cudaStream_t stream) {
     cfg.numAttrs = 2;
   }
   cfg.attrs = attr;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, CG>, tmA, tmB, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, CG, OutT>, tmA, tmB, p);
   VB_REQUIRE(le == cudaSuccess, (int)le, "gemm_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   return check_launch("gemm_tc_kernel");
+}
+
+template <int BN, int EPI, int CG>
+static int launch(const vb_gemm_args& a, cudaStream_t stream) {
+  if constexpr (EPI == VB_EPI_ACCUM) return launch_t<BN, EPI, CG, float>(a, stream);
+  else return a.d_dtype == VB_BF16 ? launch_t<BN, EPI, CG, bf16>(a, stream) : launch_t<BN, EPI, CG, float>(a, stream);
 }
 
 // Tile selection.  The kernel is bound by the L2 -> SM operand stream or by the tensor pipe, whichever is slower
