@@ -37,21 +37,29 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 64;               // 64 bf16 = 128 B = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;                     // two per SM sub-partition (TMEM lane quarter = warp % 4); 12 warps cap the kernel at 128 registers and the aux epilogues spill
-constexpr int NUM_EPI_GROUPS = NUM_EPI_WARPS / 4;   // warps of a lane quarter take the 32-column chunks round-robin
-constexpr int NUM_THREADS = 128 + NUM_EPI_WARPS * 32;
+// Epilogue warps: a multiple of 4 (TMEM lane quarter = warp % 4); the warps of a lane quarter take the 32-column
+// chunks round-robin.  Measured: 12 warps do not help - the GELU epilogue (59.6 us vs 58.5 us with 8) is bound by
+// the latency chain tcgen05.ld -> math -> staging -> store inside a warp, not by issue slots, and the residual /
+// dropout epilogues spill under the 128-register cap of a 512-thread block.  The count stays a per-kernel constant
+// so a future epilogue can choose differently.
+template <int EPI, typename OutT> __host__ __device__ constexpr int epi_warps() {
+  (void)sizeof(OutT);
+  return 8;
+}
+constexpr int MAX_EPI_WARPS = 12;
 constexpr int EPI_WARP0 = 4;
 constexpr uint32_t A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr uint32_t MN_BLOCK_BYTES = 64 * BK * 2;  // one 64(mn) x 64(k) MN-major TMA box = 8 KB
 
-template <int BN, int CG> struct Cfg {
+template <int BN, int CG, int EW> struct Cfg {
   static_assert(BN == 128 || BN == 192 || BN == 256, "tile widths: 128, 192 or 256 columns");
   static_assert(CG == 1 || CG == 2, "cta_group::1 or ::2");
   static constexpr uint32_t B_ROWS = BN / CG;                      // B rows (tile columns) staged by ONE CTA
   static constexpr uint32_t B_STAGE_BYTES = B_ROWS * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr uint32_t TMEM_COLS = (BN <= 128) ? 256 : 512;    // 2 accumulator stages, power of two
-  static constexpr size_t FIXED_BYTES = 1024 /*align slack*/ + NUM_EPI_WARPS * 4608 /*epilogue staging*/ +
+  static constexpr int NUM_THREADS = 128 + EW * 32;
+  static constexpr size_t FIXED_BYTES = 1024 /*align slack*/ + EW * 4608 /*epilogue staging*/ +
                                         2 * BN * 4 /*bias*/ + 256 /*barriers*/;
   static constexpr int STAGES_FIT = (int)((227 * 1024 - FIXED_BYTES) / STAGE_BYTES);
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;    // CG1: 5 / 4 / 3,  CG2: 7 / 6 / 5 stages
@@ -340,7 +348,7 @@ __device__ __forceinline__ void red_tile(const uint8_t* stg, float* g, int64_t l
 
 // All chunks of one tile that belong to this warp.  EPI is a compile-time constant: the epilogue kind is
 // dispatched ONCE per tile (a per-element switch made the unrolled body overflow the instruction cache).
-template <typename OutT, int BN, int EPI, bool INTERIOR>
+template <typename OutT, int BN, int EPI, bool INTERIOR, int NUM_EPI_GROUPS>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, uint8_t* stg, int64_t m0, int64_t nb0,
                                            int lane, int group, const float* bias_s) {
   using S = Stg<OutT>;
@@ -464,9 +472,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
 }
 
 template <int BN, int EPI, int CG, typename OutT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(128 + 32 * epi_warps<EPI, OutT>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
-  using C = Cfg<BN, CG>;
+  constexpr int NUM_EPI_WARPS = epi_warps<EPI, OutT>();
+  using C = Cfg<BN, CG, NUM_EPI_WARPS>;
   extern __shared__ uint8_t smem_raw[];
   // identical carve-up in both CTAs of a pair: the MMA descriptors and the multicast commits address the peer's
   // shared memory by the same offsets (dynamic shared memory starts at the same window offset in every CTA).
@@ -606,8 +615,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t nb0 = (int64_t)n_blk * BN;
         const bool interior = m0 + 32 <= p.epi.M && nb0 + BN <= p.epi.N;  // warp-uniform
         // OutT is a kernel template parameter: one epilogue body per kernel (code size, register allocation)
-        if (interior) epilogue_tile<OutT, BN, EPI, true>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur);
-        else epilogue_tile<OutT, BN, EPI, false>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur);
+        if (interior) epilogue_tile<OutT, BN, EPI, true, NUM_EPI_WARPS / 4>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur);
+        else epilogue_tile<OutT, BN, EPI, false, NUM_EPI_WARPS / 4>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -671,7 +680,7 @@ inline int sm_count() {
 
 template <int BN, int EPI, int CG, typename OutT>
 static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, epi_warps<EPI, OutT>()>;
   Params p;
   int rc = fill_epi_params(a, p.epi);
   if (rc) return rc;
@@ -723,7 +732,7 @@ static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
   const int grid = (int)std::min<int64_t>(work, units) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(C::NUM_THREADS);
   cfg.dynamicSmemBytes = C::SMEM_BYTES;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
