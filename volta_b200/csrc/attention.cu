@@ -406,6 +406,7 @@ __device__ __forceinline__ void frag_to_rows16(bf16* tile_rows, const float (&o)
 template <int D, int NKB>
 __global__ void __launch_bounds__(320)
 mma_fwd_kernel(P p) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smraw[];
   using TL = Tile<D>;
   const Geo g = make_geo(p.pair_mask, p.L[0], p.L[1], blockIdx.y);
@@ -551,6 +552,7 @@ mma_fwd_kernel(P p) {
 template <int D>
 __global__ void __launch_bounds__(320)
 mma_bwd_kernel(P p) {
+  pdl_enter();
   extern __shared__ __align__(16) uint8_t smraw[];
   using TL = Tile<D>;
   constexpr int CH = D / 8;
@@ -855,7 +857,7 @@ static int run(const vb_attn_args& a, cudaStream_t st, bool bwd) {
 #define VB_FWD(D_, KB_)                                                          \
   do {                                                                           \
     if ((rc = set_smem(mma_fwd_kernel<D_, KB_>, lg.smem_fwd))) return rc;        \
-    mma_fwd_kernel<D_, KB_><<<g2, lg.warps_fwd * 32, lg.smem_fwd, st>>>(p);      \
+    launch_pdl(mma_fwd_kernel<D_, KB_>, g2, dim3(lg.warps_fwd * 32), lg.smem_fwd, st, p); \
   } while (0)
       if (a.d == 64) { if (lg.nkb <= 3) VB_FWD(64, 3); else if (lg.nkb <= 6) VB_FWD(64, 6); else VB_FWD(64, 10); }
       else { if (lg.nkb <= 3) VB_FWD(128, 3); else if (lg.nkb <= 6) VB_FWD(128, 6); else VB_FWD(128, 10); }
@@ -864,10 +866,10 @@ static int run(const vb_attn_args& a, cudaStream_t st, bool bwd) {
     }
     if (a.d == 64) {
       if ((rc = set_smem(mma_bwd_kernel<64>, lg.smem_bwd))) return rc;
-      mma_bwd_kernel<64><<<g2, lg.warps_bwd * 32, lg.smem_bwd, st>>>(p);
+      launch_pdl(mma_bwd_kernel<64>, g2, dim3(lg.warps_bwd * 32), lg.smem_bwd, st, p);
     } else {
       if ((rc = set_smem(mma_bwd_kernel<128>, lg.smem_bwd))) return rc;
-      mma_bwd_kernel<128><<<g2, lg.warps_bwd * 32, lg.smem_bwd, st>>>(p);
+      launch_pdl(mma_bwd_kernel<128>, g2, dim3(lg.warps_bwd * 32), lg.smem_bwd, st, p);
     }
     return check_launch("attention mma_bwd_kernel");
   }

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256)
 eltwise_kernel(int op, const void* a, int a_dt, int64_t lda, const void* b, int b_dt, int64_t ldb, void* out, int o_dt,
                int64_t ldo, int64_t rows, int64_t cols, float alpha, uint32_t thresh, float scale, uint64_t seed_in,
                uint64_t offset, const uint64_t* seed_ptr) {
+  pdl_enter();
   const uint64_t seed = effective_seed(seed_in, seed_ptr);
   const int64_t total = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -74,6 +75,7 @@ colsum_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t cols, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 colsum_vec_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t cols, float* __restrict__ out, int64_t rows_per_block) {
+  pdl_enter();
   __shared__ float part[8][32][9];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t c = ((int64_t)blockIdx.x * 32 + lane) * 8;
@@ -187,9 +189,9 @@ int vb_eltwise(int32_t op, const void* a, int32_t a_dtype, int64_t lda, const vo
   VB_REQUIRE(p >= 0.f && p < 1.f, VB_ERR_ARG, "eltwise: dropout p out of range");
   if (rows * cols == 0) return 0;
   const uint32_t thresh = (op == VB_ELT_DROPOUT && p > 0.f) ? vb::dropout_thresh(p) : 0u;
-  vb::elt::eltwise_kernel<<<vb::elt::grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(
-      op, a, a_dtype, lda, needs_b ? b : nullptr, b_dtype, ldb, out, out_dtype, ldo, rows, cols, alpha, thresh,
-      1.f / (1.f - p), seed, offset, vb::seed_pointer());
+  vb::launch_pdl(vb::elt::eltwise_kernel, dim3(vb::elt::grid_for(rows * cols)), dim3(256), 0, (cudaStream_t)stream,
+                 op, a, a_dtype, lda, needs_b ? b : nullptr, b_dtype, ldb, out, out_dtype, ldo, rows, cols, alpha, thresh,
+                 1.f / (1.f - p), seed, offset, vb::seed_pointer());
   return vb::check_launch("eltwise_kernel");
 }
 
@@ -204,9 +206,9 @@ int vb_colsum(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t c
     slabs = vb::ceil_div(rows, rpb);
     dim3 grid((unsigned)strips, (unsigned)slabs);
     if (dtype == VB_BF16)
-      vb::elt::colsum_vec_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const vb::bf16*)a, lda, rows, cols, out, rpb);
+      vb::launch_pdl(vb::elt::colsum_vec_kernel<vb::bf16>, grid, dim3(256), 0, (cudaStream_t)stream, (const vb::bf16*)a, lda, rows, cols, out, rpb);
     else
-      vb::elt::colsum_vec_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, rows, cols, out, rpb);
+      vb::launch_pdl(vb::elt::colsum_vec_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)a, lda, rows, cols, out, rpb);
     (void)es;
     return vb::check_launch("colsum_vec_kernel");
   }

@@ -494,6 +494,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+  // Programmatic dependent launch, primary side: let the next kernel of the stream (if it was launched with the
+  // programmatic-serialization attribute, as every GEMM here is) be scheduled as soon as SMs drain.  This kernel owns
+  // a whole SM per CTA, so a dependent CTA starts only where one of ours has exited, runs its prologue (barriers,
+  // TMEM allocation, descriptor prefetch) under our tail and then blocks in cudaGridDependencySynchronize().
+  cudaTriggerProgrammaticLaunchCompletion();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);

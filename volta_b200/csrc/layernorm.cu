@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(WARPS * 32)
 ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int H,
               float eps, float out_scale, int accum) {
+  pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
   if (row >= rows) return;
@@ -80,6 +81,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int H, float out_scale,
               T* __restrict__ dx_drop, uint32_t drop_thresh, float drop_scale, uint64_t seed_in, uint64_t offset,
               float* __restrict__ dbias, const uint64_t* __restrict__ seed_ptr) {
+  pdl_enter();
   const uint64_t seed = effective_seed(seed_in, seed_ptr);
   extern __shared__ __align__(16) float red[];  // [3 or 2][WARPS][H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -190,8 +192,8 @@ static int fwd_dispatch(const void* x, const float* gamma, const float* beta, vo
   const int nv = (H + 255) / 256;
   const unsigned grid = (unsigned)ceil_div(rows, WARPS);
 #define VB_LN_FWD(NV_)                                                                                             \
-  ln_fwd_kernel<T, NV_><<<grid, WARPS * 32, 0, st>>>((const T*)x, gamma, beta, (T*)y, mean, rstd, rows, H, eps, \
-                                                     out_scale, accum)
+  launch_pdl(ln_fwd_kernel<T, NV_>, dim3(grid), dim3(WARPS * 32), 0, st, (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, H, \
+             eps, out_scale, accum)
   switch (nv) {
     case 1: VB_LN_FWD(1); break;
     case 2: VB_LN_FWD(2); break;
@@ -222,7 +224,7 @@ static int bwd_dispatch(const void* dy, const void* x, const float* mean, const 
   do {                                                                                                           \
     if (smem > 48 * 1024)                                                                                        \
       cudaFuncSetAttribute(ln_bwd_kernel<T, NV_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-    ln_bwd_kernel<T, NV_, EX_><<<(unsigned)grid, WARPS * 32, smem, st>>>(                                        \
+    launch_pdl(ln_bwd_kernel<T, NV_, EX_>, dim3((unsigned)grid), dim3(WARPS * 32), smem, st,                    \
         (const T*)dy, (const T*)x, mean, rstd, gamma, (T*)dx, dgamma, dbeta, rows, H, out_scale, (T*)dx_drop,    \
         thresh, scale, seed, offset, dbias, seed_pointer());                                                                     \
   } while (0)
