@@ -411,6 +411,34 @@ def retrieval_scores(P, cfg, batch, clf="clfs_dict.TASK8"):
     return linear(fuse_pooled(cfg, pt, pv), P, clf)
 
 
+def task_prediction(P, cfg, batch, task_id, task_cfg):
+    """BertForVLTasks.forward for every head type (volta/encoders.py:1128-1206; SimpleClassifier :787-814), eval mode:
+    the dropouts (:1185-1190, :1197) are identities."""
+    lt, lv, pt, pv = bert_model(P, cfg, batch["input_ids"], batch["image_feat"], batch["image_loc"],
+                                batch["segment_ids"], batch["input_mask"], batch["image_mask"])
+    pooled = fuse_pooled(cfg, pt, pv)
+    ttype = task_cfg[task_id]["type"]
+    pre = "clfs_dict.%s" % task_id
+
+    def simple_classifier(x):  # Linear -> GeLU -> BertLayerNorm -> Linear
+        h = gelu(linear(x, P, pre + ".logit_fc.0"))
+        h = layer_norm(h, P[pre + ".logit_fc.2.weight"], P[pre + ".logit_fc.2.bias"])
+        return linear(h, P, pre + ".logit_fc.3")
+
+    if ttype.startswith("V-logit"):  # :1197-1199: per-region logit + additive mask of padded regions
+        xv = lv[-1]
+        if task_cfg[task_id].get("num_clf_layers", 1) == 2:
+            y = linear(gelu(linear(xv, P, pre + ".0")), P, pre + ".3")
+        else:
+            y = linear(xv, P, pre)
+        return y + ((1.0 - batch["image_mask"].float()) * -10000.0).unsqueeze(2)
+    if ttype == "VL-binary-classifier":  # NLVR2: two consecutive samples form one example (:1200-1202)
+        return simple_classifier(pooled.view(-1, pooled.shape[1] * 2))
+    if ttype in ("VL-classifier", "VL-classifier-GQA"):
+        return simple_classifier(pooled)
+    return linear(pooled, P, pre)  # VL-tri-classifier, VL-logit
+
+
 # ----------------------------------------------------------------------------
 # helpers for tests / baseline
 # ----------------------------------------------------------------------------

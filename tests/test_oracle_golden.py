@@ -58,3 +58,25 @@ def test_oracle_gradients_match_reference(name):
         assert abs(grad_projection(gr) - p_ref) <= 2e-4 * max(n_ref, 1e-3) * 4, (name, key)
         checked += 1
     assert checked == len(g["grad_norm"])
+
+
+# ---- BertForVLTasks heads (volta/encoders.py:1117-1206) ---------------------------------------------------------
+import make_golden_tasks  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(make_golden_tasks.CASES))
+def test_oracle_task_heads_match_reference(name):
+    g = torch.load(__import__("os").path.join(__import__("golden_util").ROOT, "tests", "golden", name + ".pt"), weights_only=False)
+    cfg = volta_b200.BertConfig.from_dict(g["config"])
+    model = volta_b200.BertForVLTasks(cfg, g["task_cfg"], g["tasks"])
+    sd = model.state_dict()
+    assert sorted(sd.keys()) == g["state_keys"], "state_dict keys differ from the reference"
+    state = seeded_state_dict(sd, seed=0)
+    assert abs(weights_checksum(state) - g["weights_checksum"]) < 1e-6 * max(1.0, abs(g["weights_checksum"]))
+    P = O.params_from_state_dict(state)
+    b = make_golden_tasks.case_batch(name)
+    with torch.no_grad():
+        for t in g["tasks"]:
+            mine = O.task_prediction(P, cfg, b, t, g["task_cfg"])
+            assert mine.shape == g["pred"][t].shape, (name, t)
+            assert torch.allclose(mine, g["pred"][t], atol=5e-5, rtol=1e-5), (name, t, float((mine - g["pred"][t]).abs().max()))
