@@ -311,8 +311,14 @@ def main():
     model_frac = None
     if key in FLOPS_PER_SAMPLE:
         model_frac = FLOPS_PER_SAMPLE[key] * 1e9 * (value / world) / (pk["burst"] * 1e12)
+    traffic = None  # DRAM bytes of the step's GEMM launches from the committed ncu capture of this exact workload
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if key == ("ctrl_vilbert_base", 36, 37) and B == 256 and os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_step")
     roofline = {"bound": "tensor", "kernel": "vb::tc::gemm_tc_kernel (tcgen05/TMEM/TMA)", "achieved": achieved,
-                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": None,
+                "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"], "traffic": traffic,
+                "traffic_note": "DRAM read+write bytes of all GEMM launches of one step (ncu, profiles/r01_gemm_traffic.json); "
+                                "achieved/peak are FLOP-weighted over the same launches",
                 "peak_source": pk["source"], "launches_per_step": len(tc), "gemm_ms_per_step": ms_tc,
                 "gemm_share_of_step": ms_tc / ms_step,
                 "whole_step_frac_of_burst_peak": model_frac}

@@ -5,7 +5,7 @@ h = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
 H = rows[h]
 agg = collections.defaultdict(lambda: [0, 0.0])
 for r in rows[h + 1:]:
-    if len(r) < len(H):
+    if len(r) < len(H) or r[H.index("Metric Name")] != "gpu__time_duration.sum":
         continue
     name = re.sub(r"\(.*", "", r[H.index("Kernel Name")]).replace("void ", "")
     try:
