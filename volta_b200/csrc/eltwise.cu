@@ -47,6 +47,43 @@ eltwise_kernel(int op, const void* a, int a_dt, int64_t lda, const void* b, int 
   }
 }
 
+// Vector path: 8 elements (one 16-byte load of bf16) per thread and step.  The scalar kernel above moves 14 MB in
+// ~34 us (0.8 TB/s); the pass-through copies, dropouts and casts of a step go through this one instead.
+template <typename TA, typename TO>
+__global__ void __launch_bounds__(256)
+eltwise_vec_kernel(int op, const TA* __restrict__ a, int64_t lda, const TA* __restrict__ b, int64_t ldb, TO* out, int64_t ldo,
+                   int64_t rows, int64_t cols, float alpha, uint32_t thresh, float scale, uint64_t seed_in, uint64_t offset,
+                   const uint64_t* seed_ptr) {
+  pdl_enter();
+  const uint64_t seed = effective_seed(seed_in, seed_ptr);
+  const int64_t cv = cols >> 3, total = rows * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cv, c = (i - r * cv) << 3;
+    float av[8], bv[8], ov[8], res[8];
+    Vec8<TA>::load(a + r * lda + c, av);
+    if (b) Vec8<TA>::load(b + r * ldb + c, bv);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bv[j] = 0.f;
+    }
+    if (op == VB_ELT_AXPY) Vec8<TO>::load(out + r * ldo + c, ov);
+    else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ov[j] = 0.f;
+    }
+    bool keep[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) keep[j] = true;
+    if (op == VB_ELT_DROPOUT && thresh) {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) dropout_keep2(seed, offset, (uint64_t)(r * cols + c + j), thresh, keep[j], keep[j + 1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) res[j] = apply(op, av[j], bv[j], ov[j], alpha, scale, keep[j]);
+    Vec8<TO>::store(out + r * ldo + c, res);
+  }
+}
+
 // column sums: block handles a 32-column strip x a slab of rows; lanes walk columns (coalesced), warps walk rows.
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -189,6 +226,22 @@ int vb_eltwise(int32_t op, const void* a, int32_t a_dtype, int64_t lda, const vo
   VB_REQUIRE(p >= 0.f && p < 1.f, VB_ERR_ARG, "eltwise: dropout p out of range");
   if (rows * cols == 0) return 0;
   const uint32_t thresh = (op == VB_ELT_DROPOUT && p > 0.f) ? vb::dropout_thresh(p) : 0u;
+  const bool vec_ok = (cols % 8) == 0 && (lda % 8) == 0 && (ldo % 8) == 0 && (!needs_b || ((ldb % 8) == 0 && b_dtype == a_dtype)) &&
+                      vb::aligned16(a) && vb::aligned16(out) && (!needs_b || vb::aligned16(b)) && rows * cols >= 4096;
+  if (vec_ok) {
+    const unsigned g = vb::elt::grid_for(rows * cols / 8);
+    const void* bb = needs_b ? b : nullptr;
+    const float sc = 1.f / (1.f - p);
+#define VB_ELT_VEC(TA_, TO_)                                                                                              \
+  vb::launch_pdl(vb::elt::eltwise_vec_kernel<TA_, TO_>, dim3(g), dim3(256), 0, (cudaStream_t)stream, op, (const TA_*)a, lda, \
+                 (const TA_*)bb, ldb, (TO_*)out, ldo, rows, cols, alpha, thresh, sc, seed, offset, vb::seed_pointer())
+    if (a_dtype == VB_BF16 && out_dtype == VB_BF16) VB_ELT_VEC(vb::bf16, vb::bf16);
+    else if (a_dtype == VB_F32 && out_dtype == VB_BF16) VB_ELT_VEC(float, vb::bf16);
+    else if (a_dtype == VB_BF16 && out_dtype == VB_F32) VB_ELT_VEC(vb::bf16, float);
+    else VB_ELT_VEC(float, float);
+#undef VB_ELT_VEC
+    return vb::check_launch("eltwise_vec_kernel");
+  }
   vb::launch_pdl(vb::elt::eltwise_kernel, dim3(vb::elt::grid_for(rows * cols)), dim3(256), 0, (cudaStream_t)stream,
                  op, a, a_dtype, lda, needs_b ? b : nullptr, b_dtype, ldb, out, out_dtype, ldo, rows, cols, alpha, thresh,
                  1.f / (1.f - p), seed, offset, vb::seed_pointer());

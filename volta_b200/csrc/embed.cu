@@ -66,8 +66,13 @@ gather_bwd_kernel(GradTables t, const T* __restrict__ dout, int64_t ld, int64_t 
     for (int j = 0; j < MAX_TABLES; ++j) {
       if (j < t.n && t.table[j] != nullptr && dst[j] != t.skip[j]) {
         float* d = t.table[j] + dst[j] * H + c;
+        if ((reinterpret_cast<uintptr_t>(d) & 15u) == 0) {  // two 16-byte vector reductions instead of eight scalar atomics
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) atomicAdd(d + k, v[k]);
+          for (int k = 0; k < 8; ++k) atomicAdd(d + k, v[k]);
+        }
       }
     }
   }
