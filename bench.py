@@ -198,6 +198,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("VOLTA_B200_NCCL_CTAS"):  # experiments with VOLTA_B200_DDP_RESERVE_SMS (parallel.py)
+            os.environ.setdefault("NCCL_MAX_CTAS", os.environ["VOLTA_B200_NCCL_CTAS"])
         dist.init_process_group(backend="nccl", device_id=dev)
 
     cfg = make_cfg(args)

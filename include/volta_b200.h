@@ -53,6 +53,9 @@ int vb_sm_count(void);
  * graph therefore draws new masks on every replay once the host updates *p; forward and backward captured against
  * the same p regenerate identical masks.  Process-wide; set it around capture, not concurrently with other launches. */
 int vb_set_seed_pointer(const void* dev_ptr);
+/* Caps the number of SMs the persistent tcgen05 GEMM occupies (0 = all).  Used by the data-parallel wrapper during the
+ * backward so NCCL's all-reduce blocks find free SMs instead of displacing GEMM blocks (tiles are assigned statically). */
+int vb_set_gemm_sm_limit(int32_t sms);
 
 /* ---- GEMM -------------------------------------------------------------
  * D[M,N] = epilogue( sum_k opA[m,k] * opB[n,k] )

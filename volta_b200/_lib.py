@@ -48,6 +48,7 @@ SIGNATURES = {
     "vb_device_check": (_i32, []),
     "vb_sm_count": (_i32, []),
     "vb_set_seed_pointer": (_i32, [_vp]),
+    "vb_set_gemm_sm_limit": (_i32, [_i32]),
     "vb_gemm": (_i32, [C.POINTER(GemmArgs), _vp]),
     "vb_gemm_backend": (_i32, [C.POINTER(GemmArgs)]),
     "vb_gemm_bench": (_i32, [C.POINTER(GemmArgs), _vp, _i32, C.POINTER(C.c_float)]),

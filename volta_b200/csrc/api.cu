@@ -17,6 +17,8 @@ void set_error(const char* fmt, ...) {
 }
 
 static const uint64_t* g_seed_ptr = nullptr;
+static int g_gemm_sm_limit = 0;
+int gemm_sm_limit() { return g_gemm_sm_limit; }
 const uint64_t* seed_pointer() { return g_seed_ptr; }
 
 int check_launch(const char* what) {
@@ -34,6 +36,11 @@ int check_launch(const char* what) {
 extern "C" {
 
 int vb_version(void) { return 1001; }
+
+int vb_set_gemm_sm_limit(int32_t sms) {
+  vb::g_gemm_sm_limit = sms > 0 ? sms : 0;
+  return 0;
+}
 
 int vb_set_seed_pointer(const void* dev_ptr) {
   vb::g_seed_ptr = reinterpret_cast<const uint64_t*>(dev_ptr);

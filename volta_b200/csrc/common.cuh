@@ -170,6 +170,7 @@ __device__ __forceinline__ void dropout_keep2(uint64_t seed, uint64_t offset, ui
 // Device-resident seed base (vb_set_seed_pointer): when set, every dropout-bearing launch adds *ptr to its seed at run
 // time, so a captured CUDA graph draws fresh masks on every replay.  NULL = seeds are plain by-value arguments.
 const uint64_t* seed_pointer();
+int gemm_sm_limit();  // vb_set_gemm_sm_limit: 0 = use every SM
 __device__ __forceinline__ uint64_t effective_seed(uint64_t seed, const uint64_t* ptr) { return ptr ? seed + __ldg(ptr) : seed; }
 
 // Programmatic dependent launch hooks for the short kernels between the GEMMs.  Host side: launch_pdl() can set the

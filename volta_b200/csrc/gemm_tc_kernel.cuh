@@ -680,7 +680,10 @@ inline int sm_count() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
-  return g_sm_count;
+  // vb_set_gemm_sm_limit: the data-parallel backward leaves a few SMs to NCCL.  The persistent kernel assigns tiles
+  // statically, so a CTA that cannot be placed (its SM runs a collective) would delay its tiles by the whole collective.
+  const int lim = gemm_sm_limit();
+  return (lim > 0 && lim < g_sm_count) ? std::max(2, lim & ~1) : g_sm_count;
 }
 
 template <int BN, int EPI, int CG, typename OutT>

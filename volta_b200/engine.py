@@ -883,10 +883,11 @@ class _PretrainFn(torch.autograd.Function):
             if g is not None:
                 ops.eltwise(ELT_COPY, g.reshape(1, 1).float(), dl[i:i + 1].view(1, 1))
                 _count()
-        dx, dpt, dpv = heads_bwd(rt, model, ctx.s_heads, dl, ctx.x)
-        # head gradients are final (the tied decoder/embedding weight lives with the embeddings, at offset 0)
-        _notify_progress(rt, model.cls, skip_below=_frontier(rt.store, model.bert.encoder) or 0)
-        bert_bwd(rt, model.bert, ctx.s_bert, dx, dpt, dpv)
+        with backward_sm_limit(model):
+            dx, dpt, dpv = heads_bwd(rt, model, ctx.s_heads, dl, ctx.x)
+            # head gradients are final (the tied decoder/embedding weight lives with the embeddings, at offset 0)
+            _notify_progress(rt, model.cls, skip_below=_frontier(rt.store, model.bert.encoder) or 0)
+            bert_bwd(rt, model.bert, ctx.s_bert, dx, dpt, dpv)
         _notify_grads_ready(model)
         ctx.s_bert = ctx.s_heads = ctx.x = ctx.logits = None
         return None, None, None
@@ -897,6 +898,26 @@ _PROGRESS_HOOKS = {}
 
 
 _PROGRESS_CUTS = {}
+_BACKWARD_SM_LIMIT = {}   # id(model) -> SMs the GEMMs may use during the backward (data-parallel: the rest is NCCL's)
+
+
+def set_backward_sm_limit(model, sms):
+    _BACKWARD_SM_LIMIT[id(model)] = int(sms)
+
+
+class backward_sm_limit:
+    """Context: GEMM launches issued (or captured) inside use at most the model's backward SM limit."""
+
+    def __init__(self, model):
+        self.sms = _BACKWARD_SM_LIMIT.get(id(model_store(model).model), 0)
+
+    def __enter__(self):
+        if self.sms:
+            _lib.load().vb_set_gemm_sm_limit(self.sms)
+
+    def __exit__(self, *a):
+        if self.sms:
+            _lib.load().vb_set_gemm_sm_limit(0)
 
 
 def register_progress_hook(model, fn, cut_fn_factory=None):

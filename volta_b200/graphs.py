@@ -92,9 +92,10 @@ class GraphedPretrainStep:
                         state["g"].capture_begin(pool=pool)
                 rt.quiet = False
                 rt.progress_override = on_progress
-                dx, dpt, dpv = engine.heads_bwd(rt, model, s_heads, self.dl, x)
-                engine._notify_progress(rt, model.cls, skip_below=engine._frontier(rt.store, model.bert.encoder) or 0)
-                engine.bert_bwd(rt, model.bert, s_bert, dx, dpt, dpv)
+                with engine.backward_sm_limit(model):   # grid sizes are baked into the captured launches
+                    dx, dpt, dpv = engine.heads_bwd(rt, model, s_heads, self.dl, x)
+                    engine._notify_progress(rt, model.cls, skip_below=engine._frontier(rt.store, model.bert.encoder) or 0)
+                    engine.bert_bwd(rt, model.bert, s_bert, dx, dpt, dpv)
                 state["g"].capture_end()
                 self.bwd_segments.append((state["g"], None))
                 self.n_bwd = engine.launch_count - n0
