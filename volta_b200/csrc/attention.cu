@@ -403,6 +403,7 @@ __device__ __forceinline__ void frag_to_rows16(bf16* tile_rows, const float (&o)
 }
 
 // ---------------------------------------------------------------------------------------------- forward
+// (A 3-warp variant capped at 64 registers for ten blocks per SM measured the same as this one: 23.6 / 38.5 us.)
 template <int D, int NKB>
 __global__ void __launch_bounds__(320)
 mma_fwd_kernel(P p) {
@@ -549,8 +550,10 @@ mma_fwd_kernel(P p) {
 }
 
 // ---------------------------------------------------------------------------------------------- backward
-template <int D>
-__global__ void __launch_bounds__(320)
+// SMALL: the block has at most 3 warps (<= 48 padded query and key rows per group - every ctrl_* pre-training shape):
+// capping the registers at 65536 / (96 * 6) lets six blocks share an SM (the kernel is issue-bound at 45 % with five).
+template <int D, bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 96 : 320, SMALL ? 6 : 1)
 mma_bwd_kernel(P p) {
   pdl_enter();
   extern __shared__ __align__(16) uint8_t smraw[];
@@ -559,14 +562,14 @@ mma_bwd_kernel(P p) {
   const Geo g = make_geo(p.pair_mask, p.L[0], p.L[1], blockIdx.y);
   bf16* Qs = reinterpret_cast<bf16*>(smraw);
   bf16* dOs = Qs + g.RQ * TL::PITCH;
-  bf16* Os = dOs + g.RQ * TL::PITCH;
-  bf16* Ks = Os + g.RQ * TL::PITCH;
+  bf16* Ks = dOs + g.RQ * TL::PITCH;
   bf16* Vs = Ks + g.RK * TL::PITCH;
   float* madd = reinterpret_cast<float*>(Vs + g.RK * TL::PITCH);
   float* lse2 = madd + g.RK;                       // per query row: lse * log2(e); +inf on padding rows (P = 0)
   float* delta = lse2 + g.RQ;                      // rowsum(dO * O)
   uint32_t* rowt = reinterpret_cast<uint32_t*>(delta + g.RQ);  // dropout row terms
   bf16* dSt = reinterpret_cast<bf16*>(rowt + g.RQ);            // dS^T [RK][RQ + 8]
+  bf16* Os = dSt;                                              // O tile [RQ][PITCH]: dead (delta done) before dS^T is written
   const int SP = g.RQ + 8;
   const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
   const uint64_t seed_eff = effective_seed(p.seed, p.seed_ptr);
@@ -805,8 +808,8 @@ static LaunchGeo launch_geo(const P& p, int d) {
     lg.warps_bwd = std::max(lg.warps_bwd, std::max(g.RQ, g.RK) / 16);
     lg.nkb = std::max(lg.nkb, g.RK / 16);
     lg.smem_fwd = std::max(lg.smem_fwd, (size_t)(g.RQ + 2 * g.RK) * pitch + (size_t)g.RK * 4);
-    lg.smem_bwd = std::max(lg.smem_bwd, (size_t)(3 * g.RQ + 2 * g.RK) * pitch + (size_t)(g.RK + 3 * g.RQ) * 4 +
-                                            (size_t)g.RK * (g.RQ + 8) * 2);
+    lg.smem_bwd = std::max(lg.smem_bwd, (size_t)(2 * g.RQ + 2 * g.RK) * pitch + (size_t)(g.RK + 3 * g.RQ) * 4 +
+                                            std::max((size_t)g.RK * (g.RQ + 8) * 2, (size_t)g.RQ * pitch));
   }
   return lg;
 }
@@ -854,9 +857,9 @@ static int run(const vb_attn_args& a, cudaStream_t st, bool bwd) {
     const LaunchGeo lg = launch_geo(p, a.d);
     const dim3 g2(grid, (unsigned)p.ngroups);
     if (!bwd) {
-#define VB_FWD(D_, KB_)                                                          \
-  do {                                                                           \
-    if ((rc = set_smem(mma_fwd_kernel<D_, KB_>, lg.smem_fwd))) return rc;        \
+#define VB_FWD(D_, KB_)                                                              \
+  do {                                                                               \
+    if ((rc = set_smem(mma_fwd_kernel<D_, KB_>, lg.smem_fwd))) return rc;            \
     launch_pdl(mma_fwd_kernel<D_, KB_>, g2, dim3(lg.warps_fwd * 32), lg.smem_fwd, st, p); \
   } while (0)
       if (a.d == 64) { if (lg.nkb <= 3) VB_FWD(64, 3); else if (lg.nkb <= 6) VB_FWD(64, 6); else VB_FWD(64, 10); }
@@ -864,13 +867,14 @@ static int run(const vb_attn_args& a, cudaStream_t st, bool bwd) {
 #undef VB_FWD
       return check_launch("attention mma_fwd_kernel");
     }
-    if (a.d == 64) {
-      if ((rc = set_smem(mma_bwd_kernel<64>, lg.smem_bwd))) return rc;
-      launch_pdl(mma_bwd_kernel<64>, g2, dim3(lg.warps_bwd * 32), lg.smem_bwd, st, p);
-    } else {
-      if ((rc = set_smem(mma_bwd_kernel<128>, lg.smem_bwd))) return rc;
-      launch_pdl(mma_bwd_kernel<128>, g2, dim3(lg.warps_bwd * 32), lg.smem_bwd, st, p);
-    }
+#define VB_BWD(D_, S_)                                                                       \
+  do {                                                                                       \
+    if ((rc = set_smem(mma_bwd_kernel<D_, S_>, lg.smem_bwd))) return rc;                     \
+    launch_pdl(mma_bwd_kernel<D_, S_>, g2, dim3(lg.warps_bwd * 32), lg.smem_bwd, st, p);     \
+  } while (0)
+    if (a.d == 64) { if (lg.warps_bwd <= 3) VB_BWD(64, true); else VB_BWD(64, false); }
+    else VB_BWD(128, false);  // the 128-wide head spills heavily under the 6-blocks-per-SM register cap
+#undef VB_BWD
     return check_launch("attention mma_bwd_kernel");
   }
   VB_REQUIRE(a.d <= 256, VB_ERR_UNSUPPORTED, "attention (SIMT): head size %d > 256", a.d);
