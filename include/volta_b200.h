@@ -229,6 +229,23 @@ int vb_kl_bwd(const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32
               const float* target, int64_t rows, int32_t C, float weight, const float* lse, const float* count,
               const float* dloss, void* dlogits, int32_t dtype, void* stream);
 /* loss = loss_sum / max(count, 1) for `n` (sum,count) pairs -> out[n] */
+/* The remaining masked-region criteria of volta/losses.py over the same row mapping as vb_kl_*:
+ *   VB_REGION_XENT  : xent_1600 / xent_400 (confidence-weighted, losses.py:87-107) and xent_1601 (conf = NULL, :125-133);
+ *                     tgt_idx int64 [rows], conf fp32 [rows] or NULL; lse [rows] is written by fwd and read by bwd.
+ *   VB_REGION_MSE / VB_REGION_HUBER : mse_2048 (:25-33) / huber_2048 (:110-122) against tgt_vec fp32 [rows, ld_t];
+ *                     pass weight / C: the shared denominator max(#label==1, 1) then gives the reference's mean.
+ * loss_sum / count are accumulated; add_count != 0 for exactly one criterion per step (they share the denominator). */
+#define VB_REGION_XENT 0
+#define VB_REGION_MSE 1
+#define VB_REGION_HUBER 2
+int vb_region_loss_fwd(int32_t kind, const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32_t skip,
+                       const int64_t* label, const int64_t* tgt_idx, const float* conf, const float* tgt_vec, int64_t ld_t,
+                       int64_t rows, int32_t C, float weight, float* lse, float* loss_sum, float* count, int32_t add_count,
+                       int32_t dtype, void* stream);
+int vb_region_loss_bwd(int32_t kind, const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32_t skip,
+                       const int64_t* label, const int64_t* tgt_idx, const float* conf, const float* tgt_vec, int64_t ld_t,
+                       int64_t rows, int32_t C, float weight, const float* lse, const float* count, const float* dloss,
+                       void* dlogits, int32_t dtype, void* stream);
 int vb_loss_finalize(const float* loss_sum, const float* count, float* out, int32_t n, void* stream);
 
 /* ---- element-wise / reductions (glue that the reference issues as ATen ops) */

@@ -387,9 +387,9 @@ def pretraining_losses(P, cfg, batch, train=False, taps=None):
         if ix == "0":
             img_loss = img_loss + kl_1601(pred, w, lab, batch["image_cls"])
         elif ix == "1":
-            img_loss = img_loss + regress_masked(pred, w, lab, batch["image_feat_target"], "mse")
+            img_loss = img_loss + regress_masked(pred, w, lab, batch.get("image_feat_target", batch["image_feat"]), "mse")
         elif ix == "5":
-            img_loss = img_loss + regress_masked(pred, w, lab, batch["image_feat_target"], "huber")
+            img_loss = img_loss + regress_masked(pred, w, lab, batch.get("image_feat_target", batch["image_feat"]), "huber")
         elif ix == "3":
             img_loss = img_loss + xent_masked(pred, w, lab, batch["obj_labels"], batch["obj_confs"])
         elif ix == "4":

@@ -246,6 +246,40 @@ def kl_bwd(logits, per, per_ld, skip, label, target, C_, weight, lse, count, dlo
     dlogits[:, :C_] = full.to(dlogits.dtype)
 
 
+def region_loss_fwd(kind, logits, per, per_ld, skip, label, tgt_idx, conf, tgt_vec, C_, weight, lse, loss_sum, count, add_count):
+    rows = label.numel()
+    x = logits[_kl_rows(per, per_ld, skip, rows, logits.device), :C_].float()
+    live = label == 1
+    if kind == _lib.REGION_XENT:
+        l = torch.logsumexp(x, -1)
+        lse.copy_(torch.where(live, l, torch.zeros_like(l)))
+        per_row = (l - x.gather(1, tgt_idx[:, None]).squeeze(1)) * (conf if conf is not None else 1.0)
+    else:
+        d = x - tgt_vec[:, :C_]
+        per_row = ((d * d) if kind == _lib.REGION_MSE else torch.where(d.abs() < 1, 0.5 * d * d, d.abs() - 0.5)).sum(-1)
+    loss_sum += weight * (per_row * live).sum()
+    if add_count:
+        count += live.sum()
+
+
+def region_loss_bwd(kind, logits, per, per_ld, skip, label, tgt_idx, conf, tgt_vec, C_, weight, lse, count, dloss, dlogits):
+    rows = label.numel()
+    idx = _kl_rows(per, per_ld, skip, rows, logits.device)
+    x = logits[idx, :C_].float()
+    live = (label == 1)[:, None]
+    g = weight * dloss / count.clamp(min=1.0)
+    if kind == _lib.REGION_XENT:
+        p = torch.exp(x - lse[:, None])
+        onehot = torch.zeros_like(x).scatter_(1, tgt_idx[:, None], 1.0)
+        d = g * (p - onehot) * (conf[:, None] if conf is not None else 1.0) * live
+    else:
+        e = x - tgt_vec[:, :C_]
+        d = g * (2 * e if kind == _lib.REGION_MSE else e.clamp(-1, 1)) * live
+    full = torch.zeros(dlogits.shape[0], C_, device=logits.device)
+    full[idx] = d
+    dlogits[:, :C_] = full.to(dlogits.dtype)
+
+
 def loss_finalize(loss_sum, count, out):
     out.copy_(loss_sum / count.clamp(min=1.0))
     return out
@@ -346,7 +380,7 @@ def fill(buf, value=0):
 
 
 _NAMES = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "embed_gather_fwd",
-          "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd",
+          "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd", "region_loss_fwd", "region_loss_bwd",
           "loss_finalize", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill"]
 
 

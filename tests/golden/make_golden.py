@@ -38,6 +38,10 @@ CASES = {
     "mini_ctrl_visualbert": ("ctrl_visualbert_base", MINI, 3, 10, 7),
     "mini_ctrl_uniter": ("ctrl_uniter_base", MINI, 3, 10, 7),
     "mini_ctrl_vlbert": ("ctrl_vl-bert_base", dict(MINI, v_coordinate_embeddings_dim=8), 3, 10, 7),
+    # the non-ctrl configs exercise the other masked-region criteria (volta/losses.py): lxmert = xent_1600 + xent_400 +
+    # huber_2048 (no global feature, 4-d boxes, fusion "text"); vl-bert_base = xent_1601 (global feature last, no poolers)
+    "mini_lxmert": ("lxmert", dict(MINI, v_feature_size=2048), 3, 10, 7),
+    "mini_vlbert_base": ("vl-bert_base", dict(MINI, v_coordinate_embeddings_dim=8), 3, 10, 7),
     "full_ctrl_vilbert": ("ctrl_vilbert_base", {}, 2, 12, 9),
     "full_ctrl_visualbert": ("ctrl_visualbert_base", {}, 2, 12, 9),
     "full_ctrl_lxmert": ("ctrl_lxmert", {}, 2, 12, 9),
@@ -57,8 +61,10 @@ def case_config_dict(name):
 
 def case_batch(name):
     d, (B, T, V) = case_config_dict(name)
+    glob = d.get("add_global_imgfeat")
     return pretraining_batch(B, T, V, vocab_size=d["vocab_size"], feat_dim=d["v_feature_size"],
-                             num_locs=d["num_locs"], seed=77)
+                             num_locs=d["num_locs"], seed=77, global_first=glob == "first", global_last=glob == "last",
+                             detector_labels=any(ix in ("3", "4", "6") for ix, w in d["visual_target_weights"].items() if w > 0))
 
 
 def grad_projection(g):
@@ -104,12 +110,14 @@ def run_case(name, BertConfig, BertForVLPreTraining):
     out["layer_ids"] = [0, len(lt) // 2, len(lt) - 1] if full else list(range(len(lt)))
     out["pooled_t"], out["pooled_v"] = pt, pv
     out["mlm_logits"] = mlm[:, :, :64].clone() if full else mlm
-    out["img_logits"] = img["0"][:, :, :64].clone() if full else img["0"]
+    ix0 = sorted(img)[0]
+    out["img_target"] = ix0
+    out["img_logits"] = img[ix0][:, :, :64].clone() if full else img[ix0]
     out["itm_logits"] = itm
     model.zero_grad()
     losses = model(b["input_ids"], b["image_feat"].clone(), b["image_loc"], b["segment_ids"], b["input_mask"],
-                   b["image_mask"], b["lm_label_ids"], b["image_label"], b["image_cls"], None, None, None, None,
-                   None, b["is_match"])
+                   b["image_mask"], b["lm_label_ids"], b["image_label"], b["image_cls"], b.get("obj_labels"), b.get("obj_confs"),
+                   b.get("attr_labels"), b.get("attr_confs"), None, b["is_match"])
     out["losses"] = [float(l) for l in losses]
     (losses[0] + losses[1] + losses[2]).sum().backward()
     gn, gp = {}, {}

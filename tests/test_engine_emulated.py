@@ -27,7 +27,8 @@ def test_engine_forward_backward_matches_oracle(name, monkeypatch):
     emu_ops.install(monkeypatch)
     g, cfg, b, model, state = _build(name)
     losses = model(b["input_ids"], b["image_feat"], b["image_loc"], b["segment_ids"], b["input_mask"], b["image_mask"],
-                   b["lm_label_ids"], b["image_label"], b["image_cls"], None, None, None, None, None, b["is_match"])
+                   b["lm_label_ids"], b["image_label"], b["image_cls"], b.get("obj_labels"), b.get("obj_confs"), b.get("attr_labels"),
+                   b.get("attr_confs"), None, b["is_match"])
     for mine, ref in zip(losses, g["losses"]):
         assert abs(float(mine) - ref) < 2e-4 * max(1.0, abs(ref)), (name, float(mine), ref)
     (losses[0] + losses[1] + losses[2]).sum().backward()

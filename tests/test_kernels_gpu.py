@@ -359,6 +359,36 @@ def test_kl(dtype, skip):
     assert rel(d[:, :C_].float(), d_r[:, :C_].float()) < (1e-4 if dtype == torch.float32 else 6e-3)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("kind,C_,skip,with_conf", [("xent", 1600, 0, True), ("xent", 1601, 1, False), ("xent", 400, 0, True),
+                                                     ("mse", 2048, 0, False), ("huber", 2048, 0, False)])
+def test_region_criteria(dtype, kind, C_, skip, with_conf):
+    """xent_1600 / xent_400 / xent_1601 / mse_2048 / huber_2048 (volta/losses.py) against their restatement."""
+    B, per = 5, 9
+    V = per + skip
+    code = {"xent": _lib.REGION_XENT, "mse": _lib.REGION_MSE, "huber": _lib.REGION_HUBER}[kind]
+    ld = (C_ + 7) // 8 * 8
+    logits = rnd(B * V, ld, dtype=dtype, scale=2.0)
+    g = torch.Generator().manual_seed(3)
+    label = torch.where(torch.rand(B * per, generator=g) < 0.4, 1, -1).to(DEV)
+    idx = torch.randint(0, C_, (B * per,), generator=g).to(DEV) if kind == "xent" else None
+    conf = torch.rand(B * per, generator=g).to(DEV) if with_conf else None
+    vec = rnd(B * per, C_, dtype=torch.float32, seed=5) if kind != "xent" else None
+    w = 6.667 if kind == "xent" else 6.667 / C_
+    outs = []
+    for mod in (ops, emu_ops):
+        acc = torch.zeros(2, device=DEV)
+        lse = torch.zeros(B * per, device=DEV)
+        mod.region_loss_fwd(code, logits, per, V, skip, label, idx, conf, vec, C_, w, lse, acc[0:1], acc[1:2], True)
+        d = torch.full_like(logits, 9.0)
+        mod.region_loss_bwd(code, logits, per, V, skip, label, idx, conf, vec, C_, w, lse, acc[1:2], torch.tensor([0.7], device=DEV), d)
+        outs.append((acc.clone(), d[:, :C_].float().clone()))
+    (a0, d0), (a1, d1) = outs
+    assert float(a0[1]) == float(a1[1]) == float((label == 1).sum())
+    assert abs(float(a0[0]) - float(a1[0])) < 2e-3 * max(1.0, abs(float(a1[0])))
+    assert rel(d0, d1) < (1e-4 if dtype == torch.float32 else 8e-3)
+
+
 def test_eltwise_colsum_gather():
     a, b = rnd(300, 1024), rnd(300, 1024, seed=1)
     for op in (_lib.ELT_ADD, _lib.ELT_MUL, _lib.ELT_RELU, _lib.ELT_DRELU, _lib.ELT_GELU, _lib.ELT_DGELU):

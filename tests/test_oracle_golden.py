@@ -33,13 +33,15 @@ def test_oracle_forward_matches_reference(name):
     for i, n in enumerate(g["layer_ids"]):
         assert torch.allclose(taps["layers_t"][n], g["layers_t"][i], atol=ATOL), (name, "t", n)
         assert torch.allclose(taps["layers_v"][n], g["layers_v"][i], atol=ATOL), (name, "v", n)
-    assert torch.allclose(taps["pooled_t"], g["pooled_t"], atol=ATOL)
-    assert torch.allclose(taps["pooled_v"], g["pooled_v"], atol=ATOL)
+    for key in ("pooled_t", "pooled_v"):
+        if g[key] is not None:
+            assert torch.allclose(taps[key], g[key], atol=ATOL)
     k = g["mlm_logits"].shape[-1]
     assert torch.allclose(taps["mlm_logits"][..., :k], g["mlm_logits"], atol=1e-4)
     k = g["img_logits"].shape[-1]
-    assert torch.allclose(taps["img_logits.0"][..., :k], g["img_logits"], atol=1e-4)
-    assert torch.allclose(taps["itm_logits"], g["itm_logits"], atol=ATOL)
+    assert torch.allclose(taps["img_logits." + g.get("img_target", "0")][..., :k], g["img_logits"], atol=1e-4)
+    if g["itm_logits"] is not None:
+        assert torch.allclose(taps["itm_logits"], g["itm_logits"], atol=ATOL)
     for mine, ref in zip(losses, g["losses"]):
         assert abs(float(mine) - ref) < 1e-4 * max(1.0, abs(ref)), (name, float(mine), ref)
 

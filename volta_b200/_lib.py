@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libvolta_b200.so")
 
 F32, BF16 = 0, 1
 GEMM_AUTO, GEMM_TC, GEMM_SIMT = 0, 1, 2
+REGION_XENT, REGION_MSE, REGION_HUBER = 0, 1, 2
 ATTN_AUTO, ATTN_MMA, ATTN_SIMT = 0, 1, 2
 (EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_DROP_RES, EPI_MUL, EPI_ADD, EPI_DRELU, EPI_ACCUM,
  EPI_BIAS_ADD) = range(10)
@@ -64,6 +65,8 @@ SIGNATURES = {
     "vb_xent_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp]),
     "vb_xent_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "vb_kl_fwd": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp, _i32, _vp]),
+    "vb_region_loss_fwd": (_i32, [_i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "vb_region_loss_bwd": (_i32, [_i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _i32, _vp]),
     "vb_kl_bwd": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp, _vp, _i32, _vp]),
     "vb_loss_finalize": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "vb_eltwise": (_i32, [_i32, _vp, _i32, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _f, _f, _u64, _u64, _vp]),

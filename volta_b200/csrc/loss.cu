@@ -162,6 +162,82 @@ kl_bwd_kernel(const T* __restrict__ logits, int64_t ld, int per, int per_ld, int
     d[c] = from_f<T>(g * (__expf(to_f<T>(x[c]) - l) * ts - t[c]));
 }
 
+// The other masked-region criteria of volta/losses.py, over the same row mapping as kl_1601:
+//   VB_REGION_XENT : confidence-weighted cross-entropy against a hard label - xent_1600 / xent_400 (with conf,
+//                    :87-107) and xent_1601 (conf == NULL, :125-133):  weight * sum_{label==1} CE_r * conf_r / max(#,1)
+//   VB_REGION_MSE / VB_REGION_HUBER : feature regression - mse_2048 (:25-33) / huber_2048 (:110-122); the caller
+//                    passes weight / C so that the shared denominator max(#label==1, 1) gives the reference's
+//                    mean over masked regions AND feature dimensions.
+// `add_count`: only one of the criteria of a step accumulates the region count (they share the denominator).
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+region_fwd_kernel(int kind, const T* __restrict__ logits, int64_t ld, int per, int per_ld, int skip,
+                  const int64_t* __restrict__ label, const int64_t* __restrict__ tgt_idx, const float* __restrict__ conf,
+                  const float* __restrict__ tgt_vec, int64_t ld_t, int C, float weight, float* __restrict__ lse_out,
+                  float* __restrict__ loss_sum, float* __restrict__ count, int add_count, bool vec_ok) {
+  __shared__ float sh[THREADS / 32];
+  const int64_t r = blockIdx.x;
+  if (label[r] != 1) {
+    if (threadIdx.x == 0 && lse_out) lse_out[r] = 0.f;
+    return;
+  }
+  const T* x = logits + ((r / per) * per_ld + (r % per) + skip) * ld;
+  float s = 0.f;
+  if (kind == VB_REGION_XENT) {
+    const float lse = row_lse<T>(x, C, vec_ok, sh);
+    const int64_t t = tgt_idx[r];
+    if (threadIdx.x == 0) {
+      lse_out[r] = lse;
+      s = (lse - to_f<T>(x[t])) * (conf ? conf[r] : 1.f);
+    }
+  } else {
+    const float* t = tgt_vec + r * ld_t;
+    for (int c = threadIdx.x; c < C; c += THREADS) {
+      const float d = to_f<T>(x[c]) - t[c];
+      const float a = fabsf(d);
+      s += (kind == VB_REGION_MSE) ? d * d : (a < 1.f ? 0.5f * d * d : a - 0.5f);   // SmoothL1Loss, beta = 1
+    }
+    s = block_sum(s, sh);
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(loss_sum, weight * s);
+    if (add_count) atomicAdd(count, 1.0f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+region_bwd_kernel(int kind, const T* __restrict__ logits, int64_t ld, int per, int per_ld, int skip,
+                  const int64_t* __restrict__ label, const int64_t* __restrict__ tgt_idx, const float* __restrict__ conf,
+                  const float* __restrict__ tgt_vec, int64_t ld_t, int C, float weight, const float* __restrict__ lse,
+                  const float* __restrict__ count, const float* __restrict__ dloss, T* __restrict__ dlogits) {
+  const int64_t lr = blockIdx.x;
+  const int64_t b = lr / per_ld;
+  const int within = (int)(lr % per_ld) - skip;
+  const bool is_pred = within >= 0 && within < per;
+  const int64_t r = b * per + within;
+  const bool live = is_pred && label[r] == 1;
+  T* d = dlogits + lr * ld;
+  if (!live) {
+    for (int c = threadIdx.x; c < C; c += THREADS) d[c] = from_f<T>(0.f);
+    return;
+  }
+  const T* x = logits + lr * ld;
+  const float g = weight * (*dloss) / fmaxf(*count, 1.0f);
+  if (kind == VB_REGION_XENT) {
+    const float gc = g * (conf ? conf[r] : 1.f), l = lse[r];
+    const int64_t t = tgt_idx[r];
+    for (int c = threadIdx.x; c < C; c += THREADS)
+      d[c] = from_f<T>(gc * (__expf(to_f<T>(x[c]) - l) - (c == t ? 1.f : 0.f)));
+  } else {
+    const float* t = tgt_vec + r * ld_t;
+    for (int c = threadIdx.x; c < C; c += THREADS) {
+      const float e = to_f<T>(x[c]) - t[c];
+      d[c] = from_f<T>(g * ((kind == VB_REGION_MSE) ? 2.f * e : fminf(fmaxf(e, -1.f), 1.f)));
+    }
+  }
+}
+
 __global__ void finalize_kernel(const float* __restrict__ loss_sum, const float* __restrict__ count, float* __restrict__ out, int n) {
   const int i = threadIdx.x;
   if (i < n) out[i] = loss_sum[i] / fmaxf(count[i], 1.0f);
@@ -239,6 +315,49 @@ int vb_kl_bwd(const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32
     kl_bwd_kernel<float><<<(unsigned)logit_rows, THREADS, 0, (cudaStream_t)stream>>>(
         (const float*)logits, ld, per, per_ld, skip, label, target, C, weight, lse, count, dloss, (float*)dlogits);
   return vb::check_launch("kl_bwd_kernel");
+}
+
+int vb_region_loss_fwd(int32_t kind, const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32_t skip,
+                       const int64_t* label, const int64_t* tgt_idx, const float* conf, const float* tgt_vec, int64_t ld_t,
+                       int64_t rows, int32_t C, float weight, float* lse, float* loss_sum, float* count, int32_t add_count,
+                       int32_t dtype, void* stream) {
+  VB_REQUIRE(logits && label && loss_sum && count && C > 0 && ld >= C && per > 0 && per_ld >= per + skip, VB_ERR_ARG,
+             "region_loss_fwd: bad arguments");
+  VB_REQUIRE(kind == VB_REGION_XENT ? (tgt_idx && lse) : ((kind == VB_REGION_MSE || kind == VB_REGION_HUBER) && tgt_vec && ld_t >= C),
+             VB_ERR_ARG, "region_loss_fwd: kind %d lacks its target", kind);
+  if (rows == 0) return 0;
+  using namespace vb::loss;
+  if (dtype == VB_BF16)
+    region_fwd_kernel<vb::bf16><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
+        kind, (const vb::bf16*)logits, ld, per, per_ld, skip, label, tgt_idx, conf, tgt_vec, ld_t, C, weight, lse, loss_sum, count,
+        add_count, row_vec_ok<vb::bf16>(logits, ld));
+  else
+    region_fwd_kernel<float><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
+        kind, (const float*)logits, ld, per, per_ld, skip, label, tgt_idx, conf, tgt_vec, ld_t, C, weight, lse, loss_sum, count,
+        add_count, row_vec_ok<float>(logits, ld));
+  return vb::check_launch("region_fwd_kernel");
+}
+
+int vb_region_loss_bwd(int32_t kind, const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32_t skip,
+                       const int64_t* label, const int64_t* tgt_idx, const float* conf, const float* tgt_vec, int64_t ld_t,
+                       int64_t rows, int32_t C, float weight, const float* lse, const float* count, const float* dloss,
+                       void* dlogits, int32_t dtype, void* stream) {
+  VB_REQUIRE(logits && label && count && dloss && dlogits && C > 0 && ld >= C && per > 0 && per_ld >= per + skip, VB_ERR_ARG,
+             "region_loss_bwd: bad arguments");
+  VB_REQUIRE(kind == VB_REGION_XENT ? (tgt_idx && lse) : ((kind == VB_REGION_MSE || kind == VB_REGION_HUBER) && tgt_vec),
+             VB_ERR_ARG, "region_loss_bwd: kind %d lacks its target", kind);
+  if (rows == 0) return 0;
+  using namespace vb::loss;
+  const int64_t logit_rows = (rows / per) * per_ld;
+  if (dtype == VB_BF16)
+    region_bwd_kernel<vb::bf16><<<(unsigned)logit_rows, THREADS, 0, (cudaStream_t)stream>>>(
+        kind, (const vb::bf16*)logits, ld, per, per_ld, skip, label, tgt_idx, conf, tgt_vec, ld_t, C, weight, lse, count, dloss,
+        (vb::bf16*)dlogits);
+  else
+    region_bwd_kernel<float><<<(unsigned)logit_rows, THREADS, 0, (cudaStream_t)stream>>>(
+        kind, (const float*)logits, ld, per, per_ld, skip, label, tgt_idx, conf, tgt_vec, ld_t, C, weight, lse, count, dloss,
+        (float*)dlogits);
+  return vb::check_launch("region_bwd_kernel");
 }
 
 int vb_loss_finalize(const float* loss_sum, const float* count, float* out, int32_t n, void* stream) {

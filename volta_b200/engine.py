@@ -759,22 +759,50 @@ def heads_fwd(rt, model, x, pooled_t, pooled_v, labels, want_logits=False):
         _count()
         s["mlm_loss"] = (lab, lse)
     if labels.get("image_label") is not None:
+        # masked-region criteria (reference: volta/encoders.py:1079-1087 + volta/losses.py); they share the denominator
+        # max(#label==1, 1), so all accumulate into one (sum, count) pair and exactly one of them counts the regions
+        per = labels["image_label"].shape[1]
+        skip = 1 if cfg.add_global_imgfeat == "first" else 0
+        lab = labels["image_label"].reshape(-1).to(torch.int64).contiguous()
+        s["img_losses"] = []
         for ix, w in cfg.visual_target_weights.items():
             if w <= 0:
                 continue
-            if ix != "0":
-                raise NotImplementedError("visual target %s (%s) has no device criterion yet; the shipped ctrl_* "
-                                          "configs use target '0' (kl_1601)" % (ix, ix))
-            if labels.get("image_cls") is None:
-                continue
-            per = labels["image_label"].shape[1]
-            skip = 0 if cfg.add_global_imgfeat != "first" else 1
-            lab = labels["image_label"].reshape(-1).to(torch.int64).contiguous()
-            tgt = labels["image_cls"].reshape(-1, labels["image_cls"].shape[-1]).float().contiguous()
+            n_cls = pre_vis_targets[ix]
+            rec = None
+            if ix == "0":
+                if labels.get("image_cls") is None:
+                    continue
+                tgt = labels["image_cls"].reshape(-1, labels["image_cls"].shape[-1]).float().contiguous()
+                rec = dict(kind="kl", tgt=tgt, w=w)
+            elif ix in ("3", "4", "6"):
+                names = {"3": ("obj_labels", "obj_confs"), "4": ("attr_labels", "attr_confs"), "6": ("obj_labels", None)}[ix]
+                if labels.get(names[0]) is None or (names[1] is not None and labels.get(names[1]) is None):
+                    continue
+                conf = labels[names[1]].reshape(-1).float().contiguous() if names[1] else None
+                rec = dict(kind=_lib.REGION_XENT, idx=labels[names[0]].reshape(-1).to(torch.int64).contiguous(), conf=conf, vec=None, w=w)
+            elif ix in ("1", "5"):
+                if labels.get("image_feat") is None:
+                    continue
+                if skip != 0 or labels["image_feat"].shape[1] != per:
+                    raise ValueError("feature-regression targets need as many regions as predictions (no global feature), "
+                                     "as in the reference (volta/losses.py:25-33)")
+                vec = labels["image_feat"].reshape(-1, n_cls).float().contiguous()
+                rec = dict(kind=_lib.REGION_MSE if ix == "1" else _lib.REGION_HUBER, idx=None, conf=None, vec=vec, w=w / n_cls)
+            else:
+                raise NotImplementedError("visual target 2 (nce_2048, volta/losses.py:36-84) draws its negatives with the host "
+                                          "RNG inside the criterion; it is not on the device path")
             lse = rt.empty(lab.numel(), dtype=torch.float32)
-            ops.kl_fwd(img_logits[ix], per, rt.V, skip, lab, tgt, pre_vis_targets[ix], w, lse, sums[1:2], sums[5:6])
+            first = not s["img_losses"]
+            if rec["kind"] == "kl":
+                # kl_fwd always counts: make it the counting criterion by running it first
+                ops.kl_fwd(img_logits[ix], per, rt.V, skip, lab, rec["tgt"], n_cls, w, lse, sums[1:2], sums[5:6] if first else rt.zeros(1, dtype=torch.float32))
+            else:
+                ops.region_loss_fwd(rec["kind"], img_logits[ix], per, rt.V, skip, lab, rec["idx"], rec["conf"], rec["vec"], n_cls,
+                                    rec["w"], lse, sums[1:2], sums[5:6], first)
             _count()
-            s["img_loss"] = (ix, per, skip, lab, tgt, w, lse)
+            rec.update(ix=ix, per=per, skip=skip, lab=lab, lse=lse, n_cls=n_cls)
+            s["img_losses"].append(rec)
     if labels.get("itm") is not None and itm_logits is not None:
         lab = labels["itm"].reshape(-1).to(torch.int64).contiguous()
         lse = rt.empty(rt.B, dtype=torch.float32)
@@ -807,16 +835,23 @@ def heads_bwd(rt, model, s, dlosses, x):
         _transform_bwd(rt, cls.predictions.transform, dhn, s["mlm_tr"], dx.t)
     else:
         ops.fill(dx.t, 0)
-    # --- MRM
+    # --- MRM: every active criterion back-propagates through its own decoder into the shared transform output
     hv, img_logits = s["img"]
-    if "img_loss" in s:
-        ix, per, skip, lab, tgt, w, lse = s["img_loss"]
-        lg = img_logits[ix]
-        n_cls = pre_vis_targets[ix]
-        ops.kl_bwd(lg, per, rt.V, skip, lab, tgt, n_cls, w, lse, sums[5:6], dlosses[1:2], lg)  # in place
-        _count()
-        dec = cls.imagePredictions.decoder_dict[ix]
-        dhv = linear_bwd(rt, hv, lg[:, :n_cls], dec)
+    if s.get("img_losses"):
+        dhv = None
+        for rec in s["img_losses"]:
+            ix, lg, n_cls = rec["ix"], img_logits[rec["ix"]], rec["n_cls"]
+            if rec["kind"] == "kl":
+                ops.kl_bwd(lg, rec["per"], rt.V, rec["skip"], rec["lab"], rec["tgt"], n_cls, rec["w"], rec["lse"], sums[5:6], dlosses[1:2], lg)
+            else:
+                ops.region_loss_bwd(rec["kind"], lg, rec["per"], rt.V, rec["skip"], rec["lab"], rec["idx"], rec["conf"], rec["vec"], n_cls,
+                                    rec["w"], rec["lse"], sums[5:6], dlosses[1:2], lg)  # in place
+            _count()
+            dec = cls.imagePredictions.decoder_dict[ix]
+            if dhv is None:
+                dhv = linear_bwd(rt, hv, lg[:, :n_cls], dec)
+            else:
+                linear_bwd(rt, hv, lg[:, :n_cls], dec, dx_epilogue=EPI_ADD, dx_out=dhv, aux_in=dhv)
         _transform_bwd(rt, cls.imagePredictions.transform, dhv, s["img_tr"], dx.v)
     else:
         ops.fill(dx.v, 0)
@@ -862,13 +897,15 @@ def _check_inputs(input_txt, input_imgs, image_loc):
 class _PretrainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, model, args):
-        (ids, feat, loc, seg, mask_t, mask_v, mlm_labels, image_label, image_cls, itm_label) = args
+        (ids, feat, loc, seg, mask_t, mask_v, mlm_labels, image_label, image_cls, itm_label, obj_labels, obj_confs,
+         attr_labels, attr_confs) = args
         B, T = ids.shape
         V = feat.shape[1]
         rt = Runtime(model, ids.device, B, T, V, model.training, grad=anchor is not None)
         seg = torch.zeros_like(ids) if seg is None else seg
         x, pt, pv, _, s_bert = bert_fwd(rt, model.bert, ids.contiguous(), feat.contiguous(), loc, seg.contiguous(), mask_t, mask_v)
-        labels = dict(mlm=mlm_labels, image_label=image_label, image_cls=image_cls, itm=itm_label)
+        labels = dict(mlm=mlm_labels, image_label=image_label, image_cls=image_cls, itm=itm_label, obj_labels=obj_labels,
+                      obj_confs=obj_confs, attr_labels=attr_labels, attr_confs=attr_confs, image_feat=feat)
         losses, logits, s_heads = heads_fwd(rt, model, x, pt, pv, labels)
         ctx.rt, ctx.model, ctx.s_bert, ctx.s_heads, ctx.x = rt, model, s_bert, s_heads, x
         ctx.logits = logits
@@ -973,7 +1010,7 @@ def pretraining_forward(model, input_ids, image_feat, image_loc, token_type_ids,
         raise NotImplementedError("attention probabilities are never materialised on this path "
                                   "(output_all_attention_masks / config.visualization)")
     args = (input_ids, image_feat, image_loc, token_type_ids, attention_mask, image_attention_mask, masked_lm_labels,
-            image_label, image_cls, next_sentence_label)
+            image_label, image_cls, next_sentence_label, obj_labels, obj_confs, attr_labels, attr_confs)
     no_labels = masked_lm_labels is None and image_label is None and next_sentence_label is None
     if no_labels:
         with torch.no_grad():

@@ -52,7 +52,8 @@ class GraphedPretrainStep:
     # ------------------------------------------------------------------------------------------ capture
     def _capture(self):
         model = self.model
-        (ids, feat, loc, seg, mask_t, mask_v, mlm_labels, image_label, image_cls, itm_label) = self.static_in
+        (ids, feat, loc, seg, mask_t, mask_v, mlm_labels, image_label, image_cls, itm_label, obj_labels, obj_confs,
+         attr_labels, attr_confs) = self.static_in
         B, T = ids.shape
         V = feat.shape[1]
         store = engine.model_store(model)
@@ -72,7 +73,8 @@ class GraphedPretrainStep:
                 rt.quiet = True
                 seg_ = torch.zeros_like(ids) if seg is None else seg
                 x, pt, pv, _, s_bert = engine.bert_fwd(rt, model.bert, ids, feat, loc, seg_, mask_t, mask_v)
-                labels = dict(mlm=mlm_labels, image_label=image_label, image_cls=image_cls, itm=itm_label)
+                labels = dict(mlm=mlm_labels, image_label=image_label, image_cls=image_cls, itm=itm_label, obj_labels=obj_labels,
+                              obj_confs=obj_confs, attr_labels=attr_labels, attr_confs=attr_confs, image_feat=feat)
                 losses, _, s_heads = engine.heads_fwd(rt, model, x, pt, pv, labels)
                 g.capture_end()
                 self.fwd_graph, self.losses = g, losses

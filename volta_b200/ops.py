@@ -241,6 +241,29 @@ def kl_bwd(logits, per, per_ld, skip, label, target, C_, weight, lse, count, dlo
               _stream())
 
 
+def region_loss_fwd(kind, logits, per, per_ld, skip, label, tgt_idx, conf, tgt_vec, C_, weight, lse, loss_sum, count, add_count):
+    _, _, ld = _rows2d(logits)
+    rows = label.numel()
+    assert label.dtype == torch.int64 and (tgt_idx is None or tgt_idx.dtype == torch.int64)
+    assert conf is None or (conf.dtype == torch.float32 and conf.is_contiguous())
+    ld_t = 0
+    if tgt_vec is not None:
+        assert tgt_vec.dtype == torch.float32
+        _, _, ld_t = _rows2d(tgt_vec)
+    _lib.call("vb_region_loss_fwd", kind, logits.data_ptr(), ld, per, per_ld, skip, label.data_ptr(), _ptr(tgt_idx), _ptr(conf),
+              _ptr(tgt_vec), ld_t, rows, C_, float(weight), _ptr(lse), loss_sum.data_ptr(), count.data_ptr(), int(add_count),
+              dt(logits), _stream())
+
+
+def region_loss_bwd(kind, logits, per, per_ld, skip, label, tgt_idx, conf, tgt_vec, C_, weight, lse, count, dloss, dlogits):
+    _, _, ld = _rows2d(logits)
+    rows = label.numel()
+    ld_t = _rows2d(tgt_vec)[2] if tgt_vec is not None else 0
+    _lib.call("vb_region_loss_bwd", kind, logits.data_ptr(), ld, per, per_ld, skip, label.data_ptr(), _ptr(tgt_idx), _ptr(conf),
+              _ptr(tgt_vec), ld_t, rows, C_, float(weight), _ptr(lse), count.data_ptr(), dloss.data_ptr(), dlogits.data_ptr(),
+              dt(logits), _stream())
+
+
 def loss_finalize(loss_sum, count, out):
     _lib.call("vb_loss_finalize", loss_sum.data_ptr(), count.data_ptr(), out.data_ptr(), out.numel(), _stream())
     return out

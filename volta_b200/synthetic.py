@@ -12,8 +12,14 @@ import torch
 
 
 def pretraining_batch(batch, seq_len, num_regions, *, vocab_size=30522, feat_dim=2048, num_locs=5,
-                      num_classes=1601, seed=1234, full_length=False, global_first=True):
-    """Returns a dict of CPU tensors.  `num_regions` counts the global row (V)."""
+                      num_classes=1601, seed=1234, full_length=False, global_first=True, global_last=False,
+                      detector_labels=False):
+    """Returns a dict of CPU tensors.  `num_regions` counts the global row (V).
+    global_last: the global feature is the LAST row (`add_global_imgfeat: "last"`, vl-bert_base.json).
+    detector_labels: also returns hard object / attribute labels with confidences (the targets of xent_1600 / xent_400 /
+    xent_1601, volta/losses.py:87-133), drawn from a separate generator so the other fields do not change."""
+    if global_last:
+        global_first = True
     g = torch.Generator().manual_seed(seed)
     B, T, V = batch, seq_len, num_regions
     n_det = V - 1 if global_first else V
@@ -59,11 +65,20 @@ def pretraining_batch(batch, seq_len, num_regions, *, vocab_size=30522, feat_dim
     else:
         image_mask = det_mask
 
-    return dict(
+    if global_last:  # rotate the global row to the end
+        feat = torch.cat([feat[:, 1:], feat[:, :1]], dim=1)
+        loc = torch.cat([loc[:, 1:], loc[:, :1]], dim=1)
+        image_mask = torch.cat([image_mask[:, 1:], image_mask[:, :1]], dim=1)
+    out = dict(
         input_ids=ids, image_feat=feat.contiguous(), image_loc=loc.contiguous(), segment_ids=segment_ids,
         input_mask=input_mask, image_mask=image_mask, lm_label_ids=lm_label_ids,
         image_label=image_label, image_cls=image_cls.contiguous(), is_match=is_match,
     )
+    if detector_labels:
+        g2 = torch.Generator().manual_seed(seed + 7919)
+        out.update(obj_labels=torch.randint(0, 1600, (B, n_det), generator=g2), obj_confs=torch.rand(B, n_det, generator=g2),
+                   attr_labels=torch.randint(0, 400, (B, n_det), generator=g2), attr_confs=torch.rand(B, n_det, generator=g2))
+    return out
 
 
 def retrieval_batch(num_pairs, seq_len, num_regions, *, vocab_size=30522, feat_dim=2048, num_locs=5, seed=4321):
