@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-optimizer-leg", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     return ap.parse_args()
 
@@ -288,6 +289,26 @@ def main():
         e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                "ms_per_step": ms_e2e}
 
+    # optimizer-included step (reported next to the headline, which is the path alone): the
+    # reference's clip_grad_norm_(5.0) + AdamW with one group per parameter + zero_grad, through volta_b200.optim.FusedAdamW
+    with_opt = None
+    if not args.no_optimizer_leg:
+        from volta_b200.optim import FusedAdamW
+        no_decay = ("bias", "LayerNorm.bias", "LayerNorm.weight")
+        groups = [{"params": [p], "lr": 1e-4, "weight_decay": 0.0 if any(nd in n for nd in no_decay) else 0.01}
+                  for n, p in model.named_parameters()]
+        opt = FusedAdamW(groups, lr=1e-4, betas=(0.9, 0.999), eps=1e-6, model=model, max_grad_norm=5.0)
+
+        def step_opt():
+            opt.zero_grad()
+            l = runner(*batch_args(resident))
+            (l[0] + l[1] + l[2]).sum().backward()
+            opt.step()
+        ms_opt, _, _ = timed(step_opt, args.steps, 2)
+        with_opt = {"value": B * world / (ms_opt / 1e3), "unit": "samples/s", "ms_per_step": ms_opt,
+                    "what": "fwd + bwd + clip_grad_norm(5.0) + AdamW (one group per parameter) + zero_grad"}
+        del opt
+
     # roofline leg: one instrumented EAGER step (the timed legs replay CUDA graphs, whose kernels cannot be bracketed
     # one by one).  Every GEMM launch of the step is re-issued 5x back to back between two CUDA events on the launching
     # stream (vb_gemm_bench) - device time per launch without host gaps, operands as L2-warm as in the real step.
@@ -332,6 +353,8 @@ def main():
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if e2e is not None:
         line["e2e"] = e2e
+    if with_opt is not None:
+        line["with_optimizer"] = with_opt
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"], _ = cpu_reference(args, 3, 1)
     if rank == 0:

@@ -288,6 +288,16 @@ int vb_vlbert_prep(const float* feat, const float* mask_emb, void* out, int64_t 
 int vb_vlbert_index(const int64_t* ids, int32_t B, int32_t T, int32_t K, int64_t* tpos, int64_t* opos, int64_t* text_end,
                     int64_t* last_row, void* stream);
 int vb_batched_colsum(const void* a, int32_t dtype, int64_t batch, int64_t rows, int64_t cols, float* out, void* stream);
+/* ---- optimizer step over the flat buffers (the step right after the path) ---------------------------
+ * vb_sumsq      : *out += sum x[i]^2   (global gradient norm for torch.nn.utils.clip_grad_norm_, train_concap.py:305-307)
+ * vb_adamw_flat : pytorch_transformers.AdamW (train_concap.py:227; correct_bias folded into the per-group step size) over
+ *                 n fp32 parameters p with gradients g and moments m, v; also writes the bf16 operand copy p16 (or NULL).
+ *                 chunk_group[i] = hyper-parameter group of elements [64 i, 64 i + 64), 0xFFFF = not optimised;
+ *                 group_hp[g] = {lr, weight_decay, step_size = lr*sqrt(1-b2^t)/(1-b1^t), active != 0} (fp32 x 4).
+ *                 sumsq != NULL and max_norm > 0: gradients are scaled by min(1, max_norm / (sqrt(*sumsq) + 1e-6)). */
+int vb_sumsq(const float* x, int64_t n, float* out, void* stream);
+int vb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
+                  const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream);
 /* L2-flush helper for benchmarks: writes `bytes` to buf. */
 int vb_fill(void* buf, int64_t bytes, int32_t value, void* stream);
 

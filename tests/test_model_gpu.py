@@ -169,32 +169,14 @@ def test_cuda_graph_replay_matches_eager_steps():
             assert rel_l2(gg[k], ge[k]) < 2e-2 or float(ge[k].norm()) < 1e-6, k
 
 
-def _adamw(named, state, lr, step, clip=5.0, betas=(0.9, 0.999), eps=1e-6, wd=0.01):
-    """pytorch_transformers.AdamW as called by the reference (train_concap.py:199-227, 305-313): global-norm clip,
-    bias-corrected Adam, decoupled weight decay except on biases / LayerNorm.  Restated here because the package is
-    not in the image; the SAME code drives the oracle and the CUDA model."""
-    grads = [p.grad for _, p in named if p.grad is not None]
-    total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).item()
-    scale = min(1.0, clip / (total + 1e-6))
-    for name, p in named:
-        if p.grad is None:
-            continue
-        g = p.grad * scale
-        m, v = state.setdefault(name, (torch.zeros_like(p), torch.zeros_like(p)))
-        m.mul_(betas[0]).add_(g, alpha=1 - betas[0])
-        v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
-        step_size = lr * (1 - betas[1] ** step) ** 0.5 / (1 - betas[0] ** step)
-        with torch.no_grad():
-            p.addcdiv_(m, v.sqrt().add_(eps), value=-step_size)
-            if not any(nd in name for nd in ("bias", "LayerNorm.bias", "LayerNorm.weight")):
-                p.add_(p, alpha=-lr * wd)
+from adamw_ref import adamw_step as _adamw  # noqa: E402  (the same restated optimizer drives oracle and CUDA model)
 
 
 @pytest.mark.parametrize("precision,steps,mean_tol,max_tol", [("fp32", 40, 5e-4, 3e-3), ("bf16", 200, 1.5e-2, 8e-2)])
 def test_loss_curve_tracks_the_oracle(precision, steps, mean_tol, max_tol):
     """BASELINE.json: 'the loss curve over 200 steps tracking the reference'.  mini ctrl_vilbert (full 36-sub-layer
-    schedule), four synthetic batches cycled (so there is something to fit), dropout off (its RNG stream cannot be shared), the restated AdamW +
-    warm-up/linear-decay schedule on both sides.  The CUDA side runs through the module API (CUDA graphs included)."""
+    schedule), four synthetic batches cycled (so there is something to fit), dropout off (its RNG stream cannot be shared), the restated AdamW
+    (tests/adamw_ref.py) + warm-up/linear-decay schedule on both sides.  The CUDA side runs through the module API (CUDA graphs included)."""
     from volta_b200.synthetic import pretraining_batch
     g, cfg, _ = load_case("mini_ctrl_vilbert")
     model = volta_b200.BertForVLPreTraining(cfg)

@@ -76,6 +76,8 @@ SIGNATURES = {
     "vb_multi_cast_bf16": (_i32, [_vp, _i32, _i64, _vp]),
     "vb_box_sincos": (_i32, [_vp, _i32, _i32, _vp, _i64, _i64, _i32, _vp]),
     "vb_fill": (_i32, [_vp, _i64, _i32, _vp]),
+    "vb_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
+    "vb_adamw_flat": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _f, _f, _f, _vp, _f, _vp]),
     "vb_vlbert_prep": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "vb_vlbert_index": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vb_batched_colsum": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp]),

@@ -315,6 +315,20 @@ def box_sincos(boxes, dim, out):
     return out
 
 
+def sumsq(x, out):
+    assert x.dtype == torch.float32 and out.dtype == torch.float32 and x.is_contiguous()
+    _lib.call("vb_sumsq", x.data_ptr(), x.numel(), out.data_ptr(), _stream())
+    return out
+
+
+def adamw_flat(p, g, m, v, p16, chunk_group, group_hp, beta1, beta2, eps, sumsq_buf=None, max_norm=0.0):
+    assert p.dtype == g.dtype == m.dtype == v.dtype == torch.float32 and chunk_group.dtype == torch.int16
+    assert group_hp.dtype == torch.float32 and group_hp.shape[-1] == 4 and chunk_group.numel() * 64 == p.numel()
+    _lib.call("vb_adamw_flat", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p16), p.numel(),
+              chunk_group.data_ptr(), group_hp.data_ptr(), float(beta1), float(beta2), float(eps), _ptr(sumsq_buf),
+              float(max_norm), _stream())
+
+
 def fill(buf, value=0):
     _lib.call("vb_fill", buf.data_ptr(), buf.numel() * buf.element_size(), int(value), _stream())
 
