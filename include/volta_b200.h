@@ -42,7 +42,7 @@ extern "C" {
 #define VB_ERR_WORKSPACE (-4)
 
 /* ---- library ---------------------------------------------------------- */
-int vb_version(void);                 /* ABI version (major*1000+minor) */
+int vb_version(void);                 /* ABI version (major*1000+minor); 1002: vb_gemm_args grew B2 / bias2 / split_M */
 const char* vb_last_error(void);      /* thread-local, never NULL */
 /* 0 if the current device is sm_100 (B200); VB_ERR_DEVICE otherwise. */
 int vb_device_check(void);
@@ -108,6 +108,13 @@ typedef struct vb_gemm_args {
   uint64_t seed, offset; /* counter-hash RNG stream for the dropout mask: element index = m*N+n */
   int32_t split_k;       /* ACCUM only: 0 = auto */
   int32_t reserved;
+  /* Row-split launch (tcgen05 back-end only): rows [0, split_M) use B / bias, rows [split_M, M) use B2 / bias2 (same
+   * shape, pitch and layout as B).  One launch then serves the text rows and the vision rows of a two-stream sub-layer
+   * whose hidden states share one buffer (different nn.Linear weights per stream, volta/encoders.py:204-217).
+   * split_M must be a multiple of 256; 0 / B2 == NULL = ordinary GEMM. */
+  const void* B2;
+  const float* bias2;
+  int64_t split_M;
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);

@@ -24,7 +24,14 @@ def _dgelu(x):
 
 
 def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
-         dropout_p=0.0, seed=0, offset=0, backend=0, split_k=0, M=None, N=None, K=None):
+         dropout_p=0.0, seed=0, offset=0, backend=0, split_k=0, M=None, N=None, K=None, b2=None, bias2=None, split_M=0):
+    if b2 is not None:   # row-split launch = two ordinary GEMMs over the two row ranges
+        assert a_kmajor and epilogue != _lib.EPI_ACCUM
+        kw = dict(a_kmajor=a_kmajor, b_kmajor=b_kmajor, epilogue=epilogue, dropout_p=dropout_p, N=N, K=K)
+        for rows, bb_, bias_ in ((slice(0, split_M), b, bias), (slice(split_M, None), b2, bias2 if bias2 is not None else bias)):
+            gemm(a[rows], bb_, out[rows], bias=bias_, aux_in=None if aux_in is None else aux_in[rows],
+                 aux_out=None if aux_out is None else aux_out[rows], **kw)
+        return out
     A = a.float() if a_kmajor else a.float().t()
     B = b.float() if b_kmajor else b.float().t()
     M = A.shape[0] if M is None else M

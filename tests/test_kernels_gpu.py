@@ -102,6 +102,29 @@ def test_gemm_tc_every_tile_configuration(tile, monkeypatch):
             assert rel(dW, 1.0 + dy.float().t() @ a.float()) < 2e-3, (tile, M, N, K, "wgrad")
 
 
+@pytest.mark.parametrize("tile", ["auto", "192x1", "192x2", "256x2"])
+def test_gemm_row_split_launch(tile, monkeypatch):
+    """One launch, two weight matrices: rows below split_M use (B, bias), the rest (B2, bias2) - the text and vision
+    rows of a two-stream sub-layer; forward (K-major B) and dgrad (MN-major B) layouts."""
+    if tile != "auto":
+        monkeypatch.setenv("VOLTA_B200_GEMM_TILE", tile)
+    M, split, N, K = 1300, 512, 776, 320
+    a = rnd(M, K)
+    w1, w2 = rnd(N, K, scale=0.05), rnd(N, K, scale=0.05, seed=1)
+    b1, b2 = rnd(N, dtype=torch.float32), rnd(N, dtype=torch.float32, seed=2)
+    res = rnd(M, N, seed=3)
+    out = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a, w1, out, epilogue=_lib.EPI_BIAS_ADD, bias=b1, aux_in=res, backend=_lib.GEMM_TC, b2=w2, bias2=b2, split_M=split)
+    ref = torch.cat([a[:split].float() @ w1.float().t() + b1, a[split:].float() @ w2.float().t() + b2]) + res.float()
+    assert rel(out.float(), ref) < 6e-3
+    if tile != "192x2":
+        w1t, w2t = w1.t().contiguous(), w2.t().contiguous()   # [K, N]: MN-major B
+        out2 = torch.zeros(M, N, dtype=torch.bfloat16, device=DEV)
+        ops.gemm(a, w1t, out2, a_kmajor=True, b_kmajor=False, backend=_lib.GEMM_TC, b2=w2t, split_M=split)
+        ref2 = torch.cat([a[:split].float() @ w1.float().t(), a[split:].float() @ w2.float().t()])
+        assert rel(out2.float(), ref2) < 6e-3
+
+
 def test_gemm_tc_strided_rows_and_inplace_add():
     """The pooler reads row 0 of every sample through lda = T*H and adds its dgrad in place through ldd."""
     B, T, H, P = 64, 12, 256, 512

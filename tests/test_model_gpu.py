@@ -135,6 +135,52 @@ def test_train_mode_dropout_runs_and_is_reproducible_in_backward():
     assert abs(float(l3[0]) - g["losses"][0]) < 3e-2 * g["losses"][0]
 
 
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+def test_row_split_launches_match_per_stream_launches(dropout, monkeypatch):
+    """B*T = 256: the two-stream sub-layers run row-split GEMMs (one launch for the text and the vision rows).  Against
+    the per-stream launches: same losses / gradients without dropout; with dropout the masks are indexed differently,
+    so only the forward/backward mask consistency (finite, deterministic under a fixed seed) and the loss level are checked."""
+    from volta_b200.synthetic import pretraining_batch
+    g, cfg, _ = load_case("mini_ctrl_vilbert")
+    for k in ("hidden_dropout_prob", "attention_probs_dropout_prob", "v_hidden_dropout_prob", "v_attention_probs_dropout_prob"):
+        setattr(cfg, k, dropout)
+    b = pretraining_batch(32, 8, 9, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
+    d = {k: v.cuda() for k, v in b.items()}
+    runs = {}
+    for split in ("1", "0"):
+        monkeypatch.setenv("VOLTA_B200_ROW_SPLIT", split)
+        model = volta_b200.BertForVLPreTraining(cfg)
+        model.load_state_dict(seeded_state_dict(model.state_dict(), seed=0))
+        model.train().cuda()
+        model._use_cuda_graphs = False
+        out = []
+        for rep in range(2):
+            model.zero_grad(set_to_none=True)
+            torch.manual_seed(5)
+            n0 = engine_launches()
+            l = _losses(model, d)
+            (l[0] + l[1] + l[2]).sum().backward()
+            out.append(([float(x) for x in l], {k: p.grad.clone() for k, p in model.named_parameters()}, engine_launches() - n0))
+        runs[split] = out
+    (l1, g1, n1), (l1b, g1b, _) = runs["1"]
+    (l0, g0, n0), _ = runs["0"]
+    assert n1 < n0 - 50, (n1, n0)                     # the split plan really merged launches
+    assert l1 == l1b                                  # same seed -> same masks -> same losses
+    for k in g1:
+        assert torch.isfinite(g1[k]).all()
+        assert rel_l2(g1b[k], g1[k]) < 1e-2 or float(g1[k].norm()) < 1e-6, k
+    for a, c in zip(l1, l0):
+        assert abs(a - c) < (2e-3 if dropout == 0.0 else 0.15) * max(1.0, abs(c)), (l1, l0)
+    if dropout == 0.0:
+        for k in g1:
+            assert rel_l2(g1[k], g0[k]) < 3e-2 or float(g0[k].norm()) < 1e-6, k
+
+
+def engine_launches():
+    from volta_b200 import engine
+    return engine.launch_count
+
+
 def test_cuda_graph_replay_matches_eager_steps():
     """The captured forward/backward graphs (volta_b200/graphs.py) must reproduce the eager path step by step: same
     per-step seeds -> same dropout masks -> same losses; gradients equal up to the order of fp32 atomics; weight

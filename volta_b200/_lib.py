@@ -26,7 +26,8 @@ class GemmArgs(C.Structure):
                 ("lda", _i64), ("ldb", _i64), ("ldd", _i64), ("ab_dtype", _i32), ("d_dtype", _i32),
                 ("a_kmajor", _i32), ("b_kmajor", _i32), ("epilogue", _i32), ("backend", _i32),
                 ("bias", _vp), ("aux_in", _vp), ("aux_out", _vp), ("ld_aux", _i64), ("alpha", _f),
-                ("dropout_p", _f), ("seed", _u64), ("offset", _u64), ("split_k", _i32), ("reserved", _i32)]
+                ("dropout_p", _f), ("seed", _u64), ("offset", _u64), ("split_k", _i32), ("reserved", _i32),
+                ("B2", _vp), ("bias2", _vp), ("split_M", _i64)]
 
 
 class AttnArgs(C.Structure):

@@ -118,6 +118,7 @@ int fill_epi_params(const vb_gemm_args& a, EpiParams& p) {
 }
 
 int gemm_simt_launch(const vb_gemm_args& a, cudaStream_t stream) {
+  VB_REQUIRE(a.B2 == nullptr || a.split_M <= 0, VB_ERR_UNSUPPORTED, "gemm: row-split launches need the tcgen05 back-end");
   EpiParams p;
   int rc = fill_epi_params(a, p);
   if (rc) return rc;

@@ -20,6 +20,10 @@ bool gemm_tc_supported(const vb_gemm_args& a, const char** why) {
   if (a.epilogue == VB_EPI_BIAS_GELU && (!aligned16(a.aux_out) || (a.ld_aux * esz) % 16 != 0)) return fail("aux_out alignment");
   if (epi_uses_bias(a.epilogue) && !aligned16(a.bias)) return fail("bias alignment");
   if (a.epilogue == VB_EPI_ACCUM && a.d_dtype != VB_F32) return fail("ACCUM needs fp32 D");
+  if (a.B2 != nullptr && a.split_M > 0) {
+    if (a.epilogue == VB_EPI_ACCUM) return fail("row-split launches are for forward / dgrad GEMMs");
+    if ((a.split_M % 256) != 0 || a.split_M >= a.M || !aligned16(a.B2)) return fail("split_M must be a multiple of 256 below M, B2 16-byte aligned");
+  }
   return true;
 }
 

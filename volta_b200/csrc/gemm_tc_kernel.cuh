@@ -25,6 +25,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <climits>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
@@ -73,6 +75,8 @@ struct Params {
   int32_t kb_total, kb_per_split, split_k;
   int32_t a_kmajor, b_kmajor;
   uint32_t idesc;
+  int32_t split_m_blk;   // tiles with m_blk >= split_m_blk take the second B operand / bias (row-split launch); INT_MAX = none
+  const float* bias2;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -473,7 +477,8 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
 
 template <int BN, int EPI, int CG, typename OutT>
 __global__ void __launch_bounds__(128 + 32 * epi_warps<EPI, OutT>(), 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Params p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmB2, const Params p) {
   constexpr int NUM_EPI_WARPS = epi_warps<EPI, OutT>();
   using C = Cfg<BN, CG, NUM_EPI_WARPS>;
   extern __shared__ uint8_t smem_raw[];
@@ -503,6 +508,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmB2);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -533,6 +539,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
       const int m0 = (m_blk * CG + (int)rank) * BM;
       const int n0 = n_blk * BN + (int)rank * (int)C::B_ROWS;
+      const CUtensorMap* mapB = (m_blk >= p.split_m_blk) ? &tmB2 : &tmB;   // row-split launch: second stream's weights
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -554,10 +561,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < BM / 64; ++j) load(smem_a(stage) + j * MN_BLOCK_BYTES, &tmA, m0 + j * 64, kb * BK);
         }
         if (p.b_kmajor) {
-          load(smem_b(stage), &tmB, kb * BK, n0);
+          load(smem_b(stage), mapB, kb * BK, n0);
         } else {
 #pragma unroll
-          for (int j = 0; j < (int)C::B_ROWS / 64; ++j) load(smem_b(stage) + j * MN_BLOCK_BYTES, &tmB, n0 + j * 64, kb * BK);
+          for (int j = 0; j < (int)C::B_ROWS / 64; ++j) load(smem_b(stage) + j * MN_BLOCK_BYTES, mapB, n0 + j * 64, kb * BK);
         }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
@@ -606,9 +613,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // accumulator stage; the named barrier also guarantees nobody still reads the buffer of tile it-2.
       float* bias_cur = bias_smem + as * BN;
       if constexpr (EPI == VB_EPI_BIAS || EPI == VB_EPI_BIAS_GELU || EPI == VB_EPI_BIAS_RELU || EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_BIAS_ADD) {
+        const float* bias_g = (m_blk >= p.split_m_blk) ? p.bias2 : p.epi.bias;
         for (int j = threadIdx.x - EPI_WARP0 * 32; j < BN; j += NUM_EPI_WARPS * 32) {
           const int64_t n = (int64_t)n_blk * BN + j;
-          bias_cur[j] = n < p.epi.N ? __ldg(p.epi.bias + n) : 0.f;
+          bias_cur[j] = n < p.epi.N ? __ldg(bias_g + n) : 0.f;
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
@@ -729,6 +737,17 @@ static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
   if (a.b_kmajor) rc = make_map(&tmB, a.B, a.N, a.K, a.ldb, (int)C::B_ROWS);
   else rc = make_map(&tmB, a.B, a.K, a.N, a.ldb, BK);
   if (rc) return rc;
+  CUtensorMap tmB2 = tmB;
+  p.split_m_blk = INT32_MAX;
+  p.bias2 = p.epi.bias;
+  if (a.B2 != nullptr && a.split_M > 0 && a.split_M < a.M) {
+    VB_REQUIRE(a.split_M % (BM * CG) == 0, VB_ERR_ARG, "gemm: split_M=%lld is not a multiple of the %d-row tile", (long long)a.split_M, BM * CG);
+    if (a.b_kmajor) rc = make_map(&tmB2, a.B2, a.N, a.K, a.ldb, (int)C::B_ROWS);
+    else rc = make_map(&tmB2, a.B2, a.K, a.N, a.ldb, BK);
+    if (rc) return rc;
+    p.split_m_blk = (int32_t)(a.split_M / (BM * CG));
+    p.bias2 = a.bias2 ? a.bias2 : p.epi.bias;
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -753,7 +772,7 @@ static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
     cfg.numAttrs = 2;
   }
   cfg.attrs = attr;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, CG, OutT>, tmA, tmB, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, CG, OutT>, tmA, tmB, tmB2, p);
   VB_REQUIRE(le == cudaSuccess, (int)le, "gemm_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   return check_launch("gemm_tc_kernel");
 }
@@ -786,6 +805,7 @@ static int launch_epi(const vb_gemm_args& a, cudaStream_t stream) {
       continue;
     }
     if (o.cg == 2 && (a.M <= 128 || (sms % 2) != 0)) continue;
+    if (a.B2 != nullptr && a.split_M > 0 && (a.split_M % (128 * o.cg)) != 0) continue;   // row split must fall on a tile edge
     if (o.bn > 128 && a.N <= 128 && o.cg == 1) continue;
     const int64_t tiles = ceil_div(a.M, 128 * o.cg) * ceil_div(a.N, o.bn);
     const int64_t rounds = ceil_div(tiles, sms / o.cg);

@@ -136,9 +136,15 @@ def model_store(model):
 # ====================================================================================================
 # building blocks (forward returns outputs + a `saved` record; backward consumes it)
 # ====================================================================================================
-def linear_fwd(rt, x, lin, epilogue=EPI_BIAS, out=None, **kw):
-    """y = x W^T + b through vb_gemm; W may be several stacked Linears (fused QKV)."""
-    lins = lin if isinstance(lin, (list, tuple)) else [lin]
+def _lins(lin):
+    return lin if isinstance(lin, (list, tuple)) else [lin]
+
+
+def linear_fwd(rt, x, lin, epilogue=EPI_BIAS, out=None, lin2=None, split=0, **kw):
+    """y = x W^T + b through vb_gemm; W may be several stacked Linears (fused QKV).
+    lin2 / split: row-split launch - rows [0, split) use `lin`, rows [split, M) use `lin2` (the text and the vision
+    rows of a two-stream sub-layer that share one hidden-state buffer)."""
+    lins = _lins(lin)
     W = rt.cw(*[l.weight for l in lins])
     b = rt.w32(*[l.bias for l in lins]) if lins[0].bias is not None else None
     rows = x.shape[0]
@@ -146,23 +152,32 @@ def linear_fwd(rt, x, lin, epilogue=EPI_BIAS, out=None, **kw):
         out = rt.empty(rows, W.shape[0])
     if b is None and epilogue == EPI_BIAS:
         epilogue = EPI_NONE
+    if lin2 is not None:
+        l2 = _lins(lin2)
+        kw.update(b2=rt.cw(*[l.weight for l in l2]), bias2=rt.w32(*[l.bias for l in l2]) if b is not None else None, split_M=split)
     rt.gemm(x, W, out, epilogue=epilogue, bias=b, **kw)
     return out
 
 
-def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, bias_done=False, **kw):
-    """dW += dy^T x (fp32, accumulated into the flat gradient buffer), db += colsum(dy), dx = dy W (+epilogue)."""
-    lins = lin if isinstance(lin, (list, tuple)) else [lin]
-    dW = rt.g32(*[l.weight for l in lins])
-    rt.gemm(dy, x, dW, a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)
-    if lins[0].bias is not None and not bias_done:
-        ops.colsum(dy, rt.g32(*[l.bias for l in lins]))
-        _count()
+def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, bias_done=False, lin2=None, split=0, **kw):
+    """dW += dy^T x (fp32, accumulated into the flat gradient buffer), db += colsum(dy), dx = dy W (+epilogue).
+    lin2 / split: the rows [split, M) belong to a second Linear - two weight-gradient launches over the two row ranges,
+    ONE row-split launch for dx."""
+    parts = [(lin, x, dy)] if lin2 is None else [(lin, x[:split], dy[:split]), (lin2, x[split:], dy[split:])]
+    for l_, x_, dy_ in parts:
+        lins = _lins(l_)
+        rt.gemm(dy_, x_, rt.g32(*[l.weight for l in lins]), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)
+        if lins[0].bias is not None and not bias_done:
+            ops.colsum(dy_, rt.g32(*[l.bias for l in lins]))
+            _count()
     if not need_dx:
         return None
+    lins = _lins(lin)
     W = rt.cw(*[l.weight for l in lins])
     if dx_out is None:
         dx_out = rt.empty(dy.shape[0], W.shape[1])
+    if lin2 is not None:
+        kw.update(b2=rt.cw(*[l.weight for l in _lins(lin2)]), split_M=split)
     rt.gemm(dy, W, dx_out, a_kmajor=True, b_kmajor=False, epilogue=dx_epilogue, **kw)
     return dx_out
 
@@ -176,10 +191,10 @@ def ln_fwd(rt, x, ln, y=None, out_scale=1.0, accum=False, save=True):
     return y, (mean, rstd)
 
 
-def ln_bwd(rt, dy, x, stats, ln, out_scale=1.0, dx=None, dx_drop=None, p=0.0, seed=0, dbias=None):
+def ln_bwd(rt, dy, x, stats, ln, out_scale=1.0, dx=None, dx_drop=None, p=0.0, seed=0, dbias=None, offset=0):
     dx = rt.empty(*x.shape) if dx is None else dx
     ops.layernorm_bwd(dy, x, stats[0], stats[1], rt.w32(ln.weight), dx, rt.g32(ln.weight), rt.g32(ln.bias), out_scale,
-                      dx_drop, p, seed, 0, dbias)
+                      dx_drop, p, seed, offset, dbias)
     _count()
     return dx
 
@@ -208,6 +223,42 @@ def out_block_bwd(rt, dy, saved, dense, ln, dh_epilogue=EPI_NONE, dh_aux=None):
     ln_bwd(rt, dy, u, stats, ln, dx=du, dx_drop=du_drop, p=p, seed=seed, dbias=rt.g32(dense.bias))
     dz = du_drop if p > 0 else du
     dh = linear_bwd(rt, h, dz, dense, dx_epilogue=dh_epilogue, bias_done=True, aux_in=dh_aux)
+    return du, dh
+
+
+# ---- the same tail for BOTH streams of a two-stream sub-layer in one row-split GEMM ------------------------------
+def split_ok(rt, x, p_t, p_v, *lin_pairs):
+    """Can the text and vision rows of this sub-layer share row-split GEMM launches?  They must live in one buffer,
+    the text rows must end on a 256-row tile edge, the streams must use equally shaped Linears and one dropout rate."""
+    if x.all is None or rt.precision != "bf16" or rt.gemm_backend == _lib.GEMM_SIMT or os.environ.get("VOLTA_B200_ROW_SPLIT", "1") == "0":
+        return False
+    if rt.Mt % 256 != 0 or rt.Mv == 0 or p_t != p_v:
+        return False
+    return all(a.weight.shape == b.weight.shape and (a.bias is None) == (b.bias is None) for a, b in lin_pairs)
+
+
+def out_block_fwd2(rt, h, x, dense_t, ln_t, dense_v, ln_v, p, y):
+    seed = rt.seed() if p > 0 else 0
+    Mt = rt.Mt
+    u = linear_fwd(rt, h, dense_t, epilogue=EPI_BIAS_DROP_RES, aux_in=x, dropout_p=p, seed=seed, lin2=dense_v, split=Mt)
+    _, st_t = ln_fwd(rt, u[:Mt], ln_t, y=y[:Mt])
+    _, st_v = ln_fwd(rt, u[Mt:], ln_v, y=y[Mt:])
+    return (h, u, (st_t, st_v), p, seed)
+
+
+def out_block_bwd2(rt, dy, saved, dense_t, ln_t, dense_v, ln_v, dh_epilogue=EPI_NONE, dh_aux=None):
+    h, u, (st_t, st_v), p, seed = saved
+    Mt, H = rt.Mt, u.shape[1]
+    du = rt.empty(*u.shape)
+    du_drop = rt.empty(*u.shape) if p > 0 else None
+    dd = (lambda a: None if a is None else a)
+    # the dropout mask of the row-split GEMM is indexed by the JOINT row: the vision half starts at element Mt*H
+    ln_bwd(rt, dy[:Mt], u[:Mt], st_t, ln_t, dx=du[:Mt], dx_drop=dd(du_drop[:Mt] if p > 0 else None), p=p, seed=seed,
+           dbias=rt.g32(dense_t.bias))
+    ln_bwd(rt, dy[Mt:], u[Mt:], st_v, ln_v, dx=du[Mt:], dx_drop=dd(du_drop[Mt:] if p > 0 else None), p=p, seed=seed,
+           dbias=rt.g32(dense_v.bias), offset=Mt * H)
+    dz = du_drop if p > 0 else du
+    dh = linear_bwd(rt, h, dz, dense_t, dx_epilogue=dh_epilogue, bias_done=True, aux_in=dh_aux, lin2=dense_v, split=Mt)
     return du, dh
 
 
@@ -244,9 +295,16 @@ def attention_fwd(rt, layer, x, masks):
     A_t, A_v = sa.all_head_size, sa.v_all_head_size
     joint = groups == ["all"]
     qkv, ctx = {}, {}
-    if joint:
-        q_all = linear_fwd(rt, x.all, [sa.query, sa.key, sa.value])
+    split = (not joint and sa.has_text and sa.has_vision and A_t == A_v and
+             split_ok(rt, x, rt.p(so.dropout.p), rt.p(so.v_dropout.p), (sa.query, sa.v_query), (sa.key, sa.v_key),
+                      (sa.value, sa.v_value), (so.dense, so.v_dense)))
+    if joint or split:
+        # one GEMM over all rows: shared weights (joint) or a row-split launch with each stream's own weights
+        q_all = linear_fwd(rt, x.all, [sa.query, sa.key, sa.value],
+                           lin2=[sa.v_query, sa.v_key, sa.v_value] if split else None, split=rt.Mt)
         qkv["t"], qkv["v"] = q_all[:rt.Mt], q_all[rt.Mt:]
+        if split:
+            qkv["all"] = q_all
         c_all = rt.empty(rt.Mt + rt.Mv, A_t)
         ctx["t"], ctx["v"], ctx["all"] = c_all[:rt.Mt], c_all[rt.Mt:], c_all
     else:
@@ -283,6 +341,9 @@ def attention_fwd(rt, layer, x, masks):
     saved_out = {}
     if joint:
         saved_out["all"] = out_block_fwd(rt, ctx["all"], x.all, so.dense, so.LayerNorm, rt.p(so.dropout.p), y.all)
+    elif split:
+        saved_out["split"] = out_block_fwd2(rt, ctx["all"], x.all, so.dense, so.LayerNorm, so.v_dense, so.v_LayerNorm,
+                                            rt.p(so.dropout.p), y.all)
     else:
         if y is None:  # only one stream is touched: the other passes through unchanged (encoders.py:380-396)
             y = Pair(rt.empty(*x.t.shape) if sa.has_text else x.t, rt.empty(*x.v.shape) if sa.has_vision else x.v, None)
@@ -291,7 +352,7 @@ def attention_fwd(rt, layer, x, masks):
         if sa.has_vision:
             saved_out["v"] = out_block_fwd(rt, ctx["v"], x.v, so.v_dense, so.v_LayerNorm, rt.p(so.v_dropout.p), y.v)
     saved = dict(x=x, qkv=qkv, ctx=ctx, lse=(lse_t, lse_v), calls=calls, seed=seed, p=(p_t, p_v), out=saved_out,
-                 joint=joint, masks=masks)
+                 joint=joint, split=split, masks=masks)
     return y, saved
 
 
@@ -303,13 +364,16 @@ def attention_bwd(rt, layer, dy, s):
     if s["joint"]:
         du_all, dc_all = out_block_bwd(rt, dy.all, s["out"]["all"], so.dense, so.LayerNorm)
         du["all"], dctx["t"], dctx["v"] = du_all, dc_all[:rt.Mt], dc_all[rt.Mt:]
+    elif s["split"]:
+        du_all, dc_all = out_block_bwd2(rt, dy.all, s["out"]["split"], so.dense, so.LayerNorm, so.v_dense, so.v_LayerNorm)
+        du["all"], dctx["t"], dctx["v"] = du_all, dc_all[:rt.Mt], dc_all[rt.Mt:]
     else:
         if sa.has_text:
             du["t"], dctx["t"] = out_block_bwd(rt, dy.t, s["out"]["t"], so.dense, so.LayerNorm)
         if sa.has_vision:
             du["v"], dctx["v"] = out_block_bwd(rt, dy.v, s["out"]["v"], so.v_dense, so.v_LayerNorm)
     dqkv = {}
-    if s["joint"]:
+    if s["joint"] or s["split"]:
         dq_all = rt.empty(rt.Mt + rt.Mv, qkv["t"].shape[1])
         dqkv["t"], dqkv["v"], dqkv["all"] = dq_all[:rt.Mt], dq_all[rt.Mt:], dq_all
     else:
@@ -324,8 +388,9 @@ def attention_bwd(rt, layer, dy, s):
                           dqkv_t=dqkv.get("t") if qt is not None else None, dqkv_v=dqkv.get("v") if qv is not None else None)
         _count()
     # dx = dqkv . Wqkv + du   (the residual gradient is folded into the dgrad epilogue)
-    if s["joint"]:
-        dx_all = linear_bwd(rt, x.all, dqkv["all"], [sa.query, sa.key, sa.value], dx_epilogue=EPI_ADD, aux_in=du["all"])
+    if s["joint"] or s["split"]:
+        dx_all = linear_bwd(rt, x.all, dqkv["all"], [sa.query, sa.key, sa.value], dx_epilogue=EPI_ADD, aux_in=du["all"],
+                            lin2=[sa.v_query, sa.v_key, sa.v_value] if s["split"] else None, split=rt.Mt)
         return Pair(dx_all[:rt.Mt], dx_all[rt.Mt:], dx_all)
     dx = _grad_pair_like(rt, x)
     if sa.has_text:
@@ -347,22 +412,29 @@ def _act_epilogues(name):
     raise NotImplementedError("hidden_act=%r: the shipped configs use 'gelu'; 'relu' is supported, 'swish' is not" % (name,))
 
 
-def _ffn_stream_fwd(rt, x, inter, dense2, ln, p, y, act):
+def _ffn_stream_fwd(rt, x, inter, dense2, ln, p, y, act, second=None):
+    """second = (inter_v, dense2_v, ln_v): both streams in row-split launches over the joint buffer."""
     epi_f, _ = _act_epilogues(act)
     I = inter.weight.shape[0]
     h = rt.empty(x.shape[0], I)
+    sp = dict(lin2=second[0], split=rt.Mt) if second else {}
     if epi_f == EPI_BIAS_GELU:
         pre = rt.empty(x.shape[0], I)
-        linear_fwd(rt, x, inter, epilogue=EPI_BIAS_GELU, out=h, aux_out=pre)
+        linear_fwd(rt, x, inter, epilogue=EPI_BIAS_GELU, out=h, aux_out=pre, **sp)
     else:
-        linear_fwd(rt, x, inter, epilogue=EPI_BIAS_RELU, out=h)
+        linear_fwd(rt, x, inter, epilogue=EPI_BIAS_RELU, out=h, **sp)
         pre = h  # relu'(pre) = (h > 0)
+    if second:
+        return (x, pre, out_block_fwd2(rt, h, x, dense2, ln, second[1], second[2], p, y))
     return (x, pre, out_block_fwd(rt, h, x, dense2, ln, p, y))
 
 
-def _ffn_stream_bwd(rt, dy, saved, inter, dense2, ln, act, dx_out=None):
+def _ffn_stream_bwd(rt, dy, saved, inter, dense2, ln, act, dx_out=None, second=None):
     x, pre, out_saved = saved
     _, epi_b = _act_epilogues(act)
+    if second:
+        du, dpre = out_block_bwd2(rt, dy, out_saved, dense2, ln, second[1], second[2], dh_epilogue=epi_b, dh_aux=pre)
+        return linear_bwd(rt, x, dpre, inter, dx_epilogue=EPI_ADD, aux_in=du, dx_out=dx_out, lin2=second[0], split=rt.Mt)
     du, dpre = out_block_bwd(rt, dy, out_saved, dense2, ln, dh_epilogue=epi_b, dh_aux=pre)
     return linear_bwd(rt, x, dpre, inter, dx_epilogue=EPI_ADD, aux_in=du, dx_out=dx_out)
 
@@ -374,6 +446,11 @@ def ffn_fwd(rt, layer, x):
     if groups == ["all"]:
         y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
         saved["all"] = _ffn_stream_fwd(rt, x.all, it.dense, out.dense, out.LayerNorm, rt.p(out.dropout.p), y.all, it.hidden_act)
+    elif (it.has_language and it.has_vision and it.hidden_act == it.v_hidden_act and
+          split_ok(rt, x, rt.p(out.dropout.p), rt.p(out.v_dropout.p), (it.dense, it.v_dense), (out.dense, out.v_dense))):
+        y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
+        saved["split"] = _ffn_stream_fwd(rt, x.all, it.dense, out.dense, out.LayerNorm, rt.p(out.dropout.p), y.all, it.hidden_act,
+                                         second=(it.v_dense, out.v_dense, out.v_LayerNorm))
     else:
         if it.has_language and it.has_vision:
             y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
@@ -390,6 +467,10 @@ def ffn_bwd(rt, layer, dy, saved):
     it, out = layer.intermediate, layer.output
     if "all" in saved:
         dx = _ffn_stream_bwd(rt, dy.all, saved["all"], it.dense, out.dense, out.LayerNorm, it.hidden_act)
+        return Pair(dx[:rt.Mt], dx[rt.Mt:], dx)
+    if "split" in saved:
+        dx = _ffn_stream_bwd(rt, dy.all, saved["split"], it.dense, out.dense, out.LayerNorm, it.hidden_act,
+                             second=(it.v_dense, out.v_dense, out.v_LayerNorm))
         return Pair(dx[:rt.Mt], dx[rt.Mt:], dx)
     dx = _grad_pair_like(rt, saved["x"])
     if "t" in saved:

@@ -48,7 +48,8 @@ def require_cuda(*ts):
 
 # --------------------------------------------------------------------------- GEMM
 def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
-         dropout_p=0.0, seed=0, offset=0, backend=_lib.GEMM_AUTO, split_k=0, M=None, N=None, K=None):
+         dropout_p=0.0, seed=0, offset=0, backend=_lib.GEMM_AUTO, split_k=0, M=None, N=None, K=None, b2=None, bias2=None,
+         split_M=0):
     """out[M,N] = epilogue(opA . opB^T); see vb_gemm in include/volta_b200.h."""
     require_cuda(a, b, out)
     ar, ac, lda = _rows2d(a)
@@ -79,6 +80,9 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bia
             _, _, ld_aux = _rows2d(x)
     g.aux_in, g.aux_out, g.ld_aux = _ptr(aux_in), _ptr(aux_out), ld_aux
     g.alpha, g.dropout_p, g.seed, g.offset, g.split_k = 1.0, float(dropout_p), int(seed), int(offset), int(split_k)
+    if b2 is not None:   # row-split launch: rows >= split_M use b2 / bias2
+        assert b2.shape == b.shape and b2.stride() == b.stride() and b2.dtype == b.dtype and 0 < split_M < M
+        g.B2, g.bias2, g.split_M = b2.data_ptr(), _ptr(bias2), int(split_M)
     _lib.call("vb_gemm", C.byref(g), _stream())
     if GEMM_BENCH is not None:  # bench.py: device time of this launch, repeated back to back (no host gaps)
         ms = C.c_float(0.0)
