@@ -165,7 +165,7 @@ def test_row_split_launches_match_per_stream_launches(dropout, monkeypatch):
     (l1, g1, n1), (l1b, g1b, _) = runs["1"]
     (l0, g0, n0), _ = runs["0"]
     assert n1 < n0 - 50, (n1, n0)                     # the split plan really merged launches
-    assert l1 == l1b                                  # same seed -> same masks -> same losses
+    assert all(abs(a - c) < 1e-5 * max(1.0, abs(a)) for a, c in zip(l1, l1b))   # same seed -> same masks (loss sums use fp32 atomics)
     for k in g1:
         assert torch.isfinite(g1[k]).all()
         assert rel_l2(g1b[k], g1[k]) < 1e-2 or float(g1[k].norm()) < 1e-6, k
