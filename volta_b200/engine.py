@@ -136,6 +136,17 @@ def model_store(model):
 # ====================================================================================================
 # building blocks (forward returns outputs + a `saved` record; backward consumes it)
 # ====================================================================================================
+_SIDE_STREAMS = {}
+_SIDE_STREAMS_ON = os.environ.get("VOLTA_B200_SIDE_STREAM", "1") != "0"
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def _lins(lin):
     return lin if isinstance(lin, (list, tuple)) else [lin]
 
@@ -164,13 +175,26 @@ def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, 
     lin2 / split: the rows [split, M) belong to a second Linear - two weight-gradient launches over the two row ranges,
     ONE row-split launch for dx."""
     parts = [(lin, x, dy)] if lin2 is None else [(lin, x[:split], dy[:split]), (lin2, x[split:], dy[split:])]
+    # The bias gradients (column sums of dy) run on a side stream next to the weight-gradient / input-gradient GEMMs of
+    # the same Linear: the wgrad kernel leaves registers and shared memory for one small block per SM, and both read dy
+    # from L2.  The side stream joins before this function returns (dy may be freed by the caller afterwards).
+    side = None
+    if _lins(lin)[0].bias is not None and not bias_done and dy.shape[0] >= 1024 and _SIDE_STREAMS_ON and dy.is_cuda:
+        side = _side_stream(rt.device)
+        side.wait_stream(torch.cuda.current_stream(rt.device))
+        with torch.cuda.stream(side):
+            for l_, x_, dy_ in parts:
+                ops.colsum(dy_, rt.g32(*[l.bias for l in _lins(l_)]))
+                _count()
     for l_, x_, dy_ in parts:
         lins = _lins(l_)
         rt.gemm(dy_, x_, rt.g32(*[l.weight for l in lins]), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)
-        if lins[0].bias is not None and not bias_done:
+        if lins[0].bias is not None and not bias_done and side is None:
             ops.colsum(dy_, rt.g32(*[l.bias for l in lins]))
             _count()
     if not need_dx:
+        if side is not None:
+            torch.cuda.current_stream(rt.device).wait_stream(side)
         return None
     lins = _lins(lin)
     W = rt.cw(*[l.weight for l in lins])
@@ -179,6 +203,8 @@ def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, 
     if lin2 is not None:
         kw.update(b2=rt.cw(*[l.weight for l in _lins(lin2)]), split_M=split)
     rt.gemm(dy, W, dx_out, a_kmajor=True, b_kmajor=False, epilogue=dx_epilogue, **kw)
+    if side is not None:
+        torch.cuda.current_stream(rt.device).wait_stream(side)
     return dx_out
 
 
