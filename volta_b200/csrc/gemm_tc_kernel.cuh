@@ -371,7 +371,8 @@ __device__ __forceinline__ void red_tile(const uint8_t* stg, float* g, int64_t l
 template <typename OutT, int BN, int EPI, bool INTERIOR, int NUM_EPI_GROUPS>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, uint8_t* stg, int64_t m0, int64_t nb0,
                                            int lane, int group, const float* bias_s, const CUtensorMap* mapD,
-                                           const CUtensorMap* mapAuxOut) {
+                                           const CUtensorMap* mapAuxOut, const CUtensorMap* mapAuxIn, uint32_t aux_bar,
+                                           uint32_t& aux_phase) {
   using S = Stg<OutT>;
   constexpr bool TMA_OUT = sizeof(OutT) == 2 && EPI != VB_EPI_ACCUM;
   const int swz = (lane >> 1) & 3;                       // 64B-swizzle term of this lane's row
@@ -392,25 +393,35 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
   uint64_t seed = 0;
   if constexpr (EPI == VB_EPI_BIAS_DROP_RES) seed = effective_seed(p.seed, p.seed_ptr);
   uint4 pre[S::ITERS];
-  if constexpr (use_aux) {
+  if constexpr (use_aux && TMA_OUT) {
+    // residual / activation-derivative chunks arrive by TMA (32 x 32 box, zero fill outside the matrix) into the aux buffer;
+    // the load of chunk c+1 is issued as soon as chunk c has been read out of it
+    if (lane == 0 && nb0 + group * S::CW < p.N) {
+      mbar_expect_tx(aux_bar, STG_BUF_BYTES);
+      tma_load_2d(smem_u32(abuf), mapAuxIn, aux_bar, (int32_t)(nb0 + group * S::CW), (int32_t)m0);
+    }
+  } else if constexpr (use_aux) {
     if (nb0 + group * S::CW < p.N) S::template load_regs<INTERIOR>(pre, aux, p.ld_aux, m0, nb0 + group * S::CW, p.M, p.N, lane);
   }
+  uint4 auxr[S::VPR];
 #pragma unroll 1
   for (int c = group; c < NCH; c += NUM_EPI_GROUPS) {
     const int64_t n0 = nb0 + c * S::CW;
     if (n0 >= p.N) break;  // warp-uniform
     uint32_t raw[32];
     tmem_ld32(tmem_acc + (uint32_t)(c * S::CW), raw);
-    if constexpr (use_aux) {
-      if constexpr (TMA_OUT) {
+    if constexpr (use_aux && TMA_OUT) {
+      mbar_wait(aux_bar, aux_phase);
+      aux_phase ^= 1u;
 #pragma unroll
-        for (int i = 0; i < S::ITERS; ++i) {             // coalesced rows -> dense swizzled rows of the aux buffer
-          const int row = i * S::RPI + lane / S::VPR, v = lane % S::VPR;
-          *reinterpret_cast<uint4*>(abuf + row * 64 + ((v ^ ((row >> 1) & 3)) << 4)) = pre[i];
-        }
-      } else {
-        S::regs_to_stage(pre, stg, lane);
+      for (int v = 0; v < S::VPR; ++v) auxr[v] = *reinterpret_cast<const uint4*>(abuf + lane * 64 + ((v ^ swz) << 4));
+      __syncwarp();                                      // every lane has read its row: the buffer may be refilled
+      if (lane == 0 && c + NUM_EPI_GROUPS < NCH && n0 + NUM_EPI_GROUPS * S::CW < p.N) {
+        mbar_expect_tx(aux_bar, STG_BUF_BYTES);
+        tma_load_2d(smem_u32(abuf), mapAuxIn, aux_bar, (int32_t)(n0 + NUM_EPI_GROUPS * S::CW), (int32_t)m0);
       }
+    } else if constexpr (use_aux) {
+      S::regs_to_stage(pre, stg, lane);
       __syncwarp();
       // prefetch the next chunk's residual / derivative tile while this chunk is processed
       if (c + NUM_EPI_GROUPS < NCH && n0 + NUM_EPI_GROUPS * S::CW < p.N)
@@ -435,7 +446,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
       }
       if constexpr (use_aux) {
         uint4 rawx;
-        if constexpr (TMA_OUT) rawx = *reinterpret_cast<const uint4*>(abuf + lane * 64 + ((v ^ swz) << 4));
+        if constexpr (TMA_OUT) rawx = auxr[v];
         else rawx = *reinterpret_cast<const uint4*>(my_row + v * 16);
         const OutT* t = reinterpret_cast<const OutT*>(&rawx);
 #pragma unroll
@@ -546,7 +557,7 @@ template <int BN, int EPI, int CG, typename OutT>
 __global__ void __launch_bounds__(128 + 32 * epi_warps<EPI, OutT>(), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmD,
-               const __grid_constant__ CUtensorMap tmAux, const Params p) {
+               const __grid_constant__ CUtensorMap tmAux, const __grid_constant__ CUtensorMap tmAuxIn, const Params p) {
   constexpr int NUM_EPI_WARPS = epi_warps<EPI, OutT>();
   using C = Cfg<BN, CG, NUM_EPI_WARPS>;
   extern __shared__ uint8_t smem_raw[];
@@ -562,6 +573,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
+  auto aux_bar = [&](int w) { return bars + 8u * (2 * C::STAGES + 5 + w); };   // one per epilogue warp: aux-chunk TMA loads
   auto smem_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
 
@@ -579,10 +591,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB2);
     tma_prefetch_desc(&tmD);
     tma_prefetch_desc(&tmAux);
+    tma_prefetch_desc(&tmAuxIn);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG * NUM_EPI_WARPS); }
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(aux_bar(w), 1);
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -674,6 +688,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = (warp - EPI_WARP0) & 3;    // == warp % 4: TMEM lane quarter this warp may access
     const int group = (warp - EPI_WARP0) >> 2;  // which share of the 32-column chunks
     uint8_t* stg = stg_base + (warp - EPI_WARP0) * STG_WARP_BYTES;
+    const uint32_t my_aux_bar = aux_bar(warp - EPI_WARP0);
+    uint32_t aux_phase = 0;
     int it = 0;
     for (int64_t w = first; w < total_work; w += step, ++it) {
       const int64_t tile = w / p.split_k;
@@ -698,8 +714,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t nb0 = (int64_t)n_blk * BN;
         const bool interior = m0 + 32 <= p.epi.M && nb0 + BN <= p.epi.N;  // warp-uniform
         // OutT is a kernel template parameter: one epilogue body per kernel (code size, register allocation)
-        if (interior) epilogue_tile<OutT, BN, EPI, true, NUM_EPI_WARPS / 4>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux);
-        else epilogue_tile<OutT, BN, EPI, false, NUM_EPI_WARPS / 4>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux);
+        if (interior) epilogue_tile<OutT, BN, EPI, true, NUM_EPI_WARPS / 4>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase);
+        else epilogue_tile<OutT, BN, EPI, false, NUM_EPI_WARPS / 4>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -844,6 +860,8 @@ static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
     tmAux = tmD;
     if (EPI == VB_EPI_BIAS_GELU && (rc = make_out_map(&tmAux, a.aux_out, a.M, a.N, a.ld_aux))) return rc;
   }
+  CUtensorMap tmAuxIn = tmD;
+  if (sizeof(OutT) == 2 && epi_uses_aux_in(EPI) && (rc = make_out_map(&tmAuxIn, a.aux_in, a.M, a.N, a.ld_aux))) return rc;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -868,7 +886,7 @@ static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
     cfg.numAttrs = 2;
   }
   cfg.attrs = attr;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, CG, OutT>, tmA, tmB, tmB2, tmD, tmAux, p);
+  cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, CG, OutT>, tmA, tmB, tmB2, tmD, tmAux, tmAuxIn, p);
   VB_REQUIRE(le == cudaSuccess, (int)le, "gemm_tc_kernel: launch failed: %s", cudaGetErrorString(le));
   return check_launch("gemm_tc_kernel");
 }
