@@ -80,11 +80,15 @@ def test_gemm_wgrad_accumulate(backend, M, N, K, split):
     assert rel(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("clc", ["0", "1"])
 @pytest.mark.parametrize("tile", ["128x1", "192x1", "192x2", "256x2"])
-def test_gemm_tc_every_tile_configuration(tile, monkeypatch):
+def test_gemm_tc_every_tile_configuration(tile, clc, monkeypatch):
     """Each instantiation of the tcgen05 kernel (tile width x CTA-group size) on all three operand layouts, ragged
-    edges, several persistent rounds and split-K; CTA pairs (x2) run the cta_group::2 protocol."""
+    edges, several persistent rounds and split-K; CTA pairs (x2) run the cta_group::2 protocol.  clc=1: work items
+    handed out by cluster launch control (one cluster per item, resident clusters cancel and take over the rest)
+    instead of the static persistent stride."""
     monkeypatch.setenv("VOLTA_B200_GEMM_TILE", tile)
+    monkeypatch.setenv("VOLTA_B200_GEMM_CLC", clc)
     for (M, N, K) in [(300, 776, 328), (9472, 1536, 256), (129, 200, 64)]:
         a, w, bias = rnd(M, K), rnd(N, K, scale=0.05), rnd(N, dtype=torch.float32)
         res = rnd(M, N, seed=2)

@@ -62,7 +62,7 @@ template <int BN, int CG, int EW> struct Cfg {
   static constexpr uint32_t TMEM_COLS = (BN <= 128) ? 256 : 512;    // 2 accumulator stages, power of two
   static constexpr int NUM_THREADS = 128 + EW * 32;
   static constexpr size_t FIXED_BYTES = 1024 /*align slack*/ + EW * 6144 /*epilogue staging*/ +
-                                        2 * BN * 4 /*bias*/ + 256 /*barriers*/;
+                                        2 * BN * 4 /*bias*/ + 384 /*barriers, work-queue responses*/;
   static constexpr int STAGES_FIT = (int)((227 * 1024 - FIXED_BYTES) / STAGE_BYTES);
   static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;    // CG1: 5 / 4 / 3,  CG2: 7 / 6 / 5 stages
   static_assert(STAGES >= 3, "operand ring too shallow");
@@ -77,6 +77,7 @@ struct Params {
   uint32_t idesc;
   int32_t split_m_blk;   // tiles with m_blk >= split_m_blk take the second B operand / bias (row-split launch); INT_MAX = none
   const float* bias2;
+  int32_t clc;           // 1: work items come from cluster launch control (grid = one cluster per work item); 0: static stride
 };
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -144,6 +145,36 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+// ---- cluster launch control: a running cluster asks the hardware for the grid index of a cluster that has not been
+// launched yet and does its work itself (dynamic persistent scheduling without a global counter).  The 16-byte answer
+// is written to `resp` (with MULTICAST: at the same offset in every CTA of the cluster) and counted on `bar` (ditto).
+template <bool MULTICAST>
+__device__ __forceinline__ void clc_try_cancel(uint32_t resp, uint32_t bar) {
+  if constexpr (MULTICAST)
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+                 ::"r"(resp), "r"(bar) : "memory");
+  else
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.b128 [%0], [%1];"
+                 ::"r"(resp), "r"(bar) : "memory");
+}
+// true + blockIdx.x of the first CTA of the cancelled cluster, or false when nothing was left to cancel
+__device__ __forceinline__ bool clc_read(uint32_t resp, uint32_t& ctaid_x) {
+  uint32_t ok, x = 0, y = 0, z = 0;
+  asm volatile(
+      "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+      "ld.shared.b128 r, [%4];\n\t"
+      "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+      "selp.u32 %3, 1, 0, p1;\n\t"
+      "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid.v4.b32.b128 {%0, %1, %2, _}, r;\n\t}"
+      : "+r"(x), "+r"(y), "+r"(z), "=r"(ok)
+      : "r"(resp)
+      : "memory");
+  ctaid_x = x;
+  return ok != 0;
 }
 // TMA load of a CTA-pair kernel: data lands in THIS CTA's shared memory, completion is counted on `bar`, a
 // shared::cluster address that may name the leader CTA's barrier.
@@ -574,6 +605,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * C::STAGES + 2 + s); };
   const uint32_t tmem_slot = bars + 8u * (2 * C::STAGES + 4);
   auto aux_bar = [&](int w) { return bars + 8u * (2 * C::STAGES + 5 + w); };   // one per epilogue warp: aux-chunk TMA loads
+  auto clc_full = [&](int s) { return bars + 8u * (2 * C::STAGES + 13 + s); };  // work queue: answer s has landed
+  auto clc_empty = [&](int s) { return bars + 8u * (2 * C::STAGES + 15 + s); }; // (leader's copy) every reader is done with answer s
+  auto clc_resp = [&](int s) { return bars + 8u * (2 * C::STAGES + 18) + 16u * s; };
   auto smem_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
 
@@ -597,6 +631,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG * NUM_EPI_WARPS); }
     for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(aux_bar(w), 1);
+    // readers of a work-queue answer besides the leader's producer thread (which issues the queries): per CTA the
+    // epilogue warps + one of {MMA thread (leader), producer thread (peer)}
+    for (int s = 0; s < 2; ++s) { mbar_init(clc_full(s), 1); mbar_init(clc_empty(s), CG * (NUM_EPI_WARPS + 1)); }
     fence_barrier_init();
     fence_proxy_async();
   }
@@ -613,11 +650,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int64_t tiles = (int64_t)p.num_m_blocks * p.num_n_blocks;   // tiles of (CG*128) x BN
   const int64_t total_work = tiles * p.split_k;
   const int64_t first = blockIdx.x / CG, step = gridDim.x / CG;     // one work item per CTA (pair) at a time
+  // Work items.  Static mode: first, first + step, ... (grid = resident CTAs).  Cluster-launch-control mode (p.clc): the
+  // grid has one cluster per work item; a resident cluster does its own item, then keeps cancelling clusters that have
+  // not started and does theirs.  SMs held by another kernel (a collective, a side-stream reduction) then simply take
+  // no part, instead of delaying a fixed share of the tiles until they are free.  The leader's producer thread issues
+  // query q when it STARTS loading an item (at most one in flight, none after a failed one), everyone else reads
+  // answer q from slot q & 1 and releases it on the leader's clc_empty barrier.
+  auto next_work = [&](int64_t& w, int& q, bool arrive, bool whole_warp) -> bool {
+    if (!p.clc) { w += step; return w < total_work; }
+    const int slot = q & 1; const uint32_t par = (uint32_t)(q >> 1) & 1u; ++q;
+    mbar_wait(clc_full(slot), par);
+    uint32_t x;
+    const bool ok = clc_read(clc_resp(slot), x);
+    fence_proxy_async();   // our generic-proxy read is ordered before the async-proxy write of a later answer
+    if (whole_warp) __syncwarp();   // every lane has read before lane 0 releases the slot
+    if (arrive) {
+      if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(clc_empty(slot), 0)); else mbar_arrive(clc_empty(slot));
+    }
+    w = (int64_t)(x / CG);
+    return ok;
+  };
 
   if (warp == 0 && lane == 0) {
     // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====================
     int stage = 0; uint32_t phase = 0;
-    for (int64_t w = first; w < total_work; w += step) {
+    int q = 0;
+    for (int64_t w = first;;) {
+      if (p.clc && rank == 0) {
+        const int slot = q & 1; const uint32_t par = (uint32_t)(q >> 1) & 1u;
+        mbar_wait(clc_empty(slot), par ^ 1u);
+        mbar_expect_tx(clc_full(slot), 16);
+        if constexpr (CG == 2) mbar_expect_tx_cluster(mapa_shared(clc_full(slot), 1), 16);
+        clc_try_cancel<CG == 2>(clc_resp(slot), clc_full(slot));
+      }
       const int split = (int)(w % p.split_k);
       const int64_t tile = w / p.split_k;
       const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
@@ -652,13 +717,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (!next_work(w, q, rank != 0, false)) break;
     }
   } else if (warp == 1 && lane == 0 && rank == 0) {
     // ===================== MMA issuer (leader CTA only) =====================
     int stage = 0; uint32_t phase = 0; int it = 0;
     const uint32_t a_step = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);  // bytes per UMMA_K step
     const uint32_t b_step = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
-    for (int64_t w = first; w < total_work; w += step, ++it) {
+    int q = 0;
+    for (int64_t w = first;; ++it) {
       const int split = (int)(w % p.split_k);
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -682,6 +749,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       // accumulator ready for the epilogue warps (of both CTAs)
       if constexpr (CG == 2) umma_commit_cg2(tfull_bar(as)); else umma_commit(tfull_bar(as));
+      if (!next_work(w, q, true, false)) break;
     }
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue (every CTA drains its own 128 x BN accumulator) =====================
@@ -690,8 +758,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* stg = stg_base + (warp - EPI_WARP0) * STG_WARP_BYTES;
     const uint32_t my_aux_bar = aux_bar(warp - EPI_WARP0);
     uint32_t aux_phase = 0;
-    int it = 0;
-    for (int64_t w = first; w < total_work; w += step, ++it) {
+    int it = 0, q = 0;
+    for (int64_t w = first;; ++it) {
       const int64_t tile = w / p.split_k;
       const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
@@ -708,6 +776,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       asm volatile("bar.sync 1, %0;" ::"n"(NUM_EPI_WARPS * 32) : "memory");
       mbar_wait(tfull_bar(as), aphase);
       tcgen05_fence_after();
+      // the answer for the next item was requested when this item's loads began: it is there by now, take it (and
+      // release the slot) before the long part
+      int64_t w_next = w;
+      const bool more = next_work(w_next, q, lane == 0, true);
       const int64_t m0 = ((int64_t)m_blk * CG + rank) * BM + ew * 32;
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
       if (m0 < p.epi.M) {  // warp-uniform
@@ -723,6 +795,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (CG == 2) mbar_arrive_cluster(mapa_shared(tempty_bar(as), 0));  // the leader's MMA thread waits for both CTAs
         else mbar_arrive(tempty_bar(as));
       }
+      if (!more) break;
+      w = w_next;
     }
     if constexpr (sizeof(OutT) == 2 && EPI != VB_EPI_ACCUM) {
       if (lane == 0) bulk_wait_all();   // outstanding TMA stores must finish before the staging memory goes away
@@ -784,6 +858,11 @@ inline int make_out_map(CUtensorMap* map, const void* base, int64_t rows, int64_
   VB_REQUIRE(r == CUDA_SUCCESS, VB_ERR_ARG, "cuTensorMapEncodeTiled (output) failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
              (long long)rows, (long long)cols, (long long)ld);
   return 0;
+}
+
+inline bool use_clc() {
+  const char* e = getenv("VOLTA_B200_GEMM_CLC");   // read per launch: tests switch it
+  return e && e[0] == '1';
 }
 
 inline int sm_count() {
@@ -870,7 +949,13 @@ static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
     attr_set = true;
   }
   const int64_t work = tiles * p.split_k;
-  const int grid = (int)std::min<int64_t>(work, units) * CG;
+  // default: classic persistent grid with a static stride.  VOLTA_B200_GEMM_CLC=1: cluster launch control - one cluster
+  // per work item, resident clusters take over the ones not yet launched.  Measured (B200): 2-5 us slower per GEMM
+  // in isolation (qkv 35.5 vs 31.8 us), equal inside the single-GPU step, 0.25 ms/step SLOWER with the NCCL
+  // all-reduce running next to the backward (19.1 vs 18.85 ms at 2 GPUs) - so the collective does not starve
+  // statically assigned tiles, and the static grid stays the default.
+  p.clc = (use_clc() && work * CG < (int64_t)INT32_MAX) ? 1 : 0;
+  const int grid = (int)(p.clc ? work : std::min<int64_t>(work, units)) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(C::NUM_THREADS);

@@ -110,7 +110,7 @@ class DistributedDataParallel(torch.nn.Module):
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised (init_process_group(backend='nccl'))")
         self.module = module
-        self.message_size = int(message_size)
+        self.message_size = int(float(os.environ.get("VOLTA_B200_DDP_MESSAGE_SIZE", message_size)))
         self.delay_allreduce = bool(delay_allreduce)
         self.group = group
         self.world_size = dist.get_world_size(group)
