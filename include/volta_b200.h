@@ -115,6 +115,13 @@ typedef struct vb_gemm_args {
   const void* B2;
   const float* bias2;
   int64_t split_M;
+  /* Device-side extents (NULL = none): int32 values in device memory, written by an earlier kernel of the stream
+   * (vb_compact_plan).  Only rows [0, *m_limit) of A / D and reduction indices [0, *k_limit) hold data: output tiles
+   * and k-blocks entirely beyond them are skipped, so the cost follows the device-side count while the launch
+   * (grid, pointers, CUDA-graph node) stays static.  The tcgen05 back-end works in whole 256-row tiles / 64-deep
+   * k-blocks: the caller keeps the operands zero from the limit up to the next multiple of 256. */
+  const int32_t* m_limit;
+  const int32_t* k_limit;
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
@@ -220,15 +227,18 @@ int vb_box_project_bwd(const float* loc, int32_t nl, const void* dout, int64_t l
  *   (volta/encoders.py:1030, 1095-1109).  logits [rows, ld] in `dtype`, C classes, labels int64.
  *   Writes per-row lse (fp32), loss_sum and count (fp32 scalars, ACCUMULATED - zero them first).
  * vb_xent_bwd: dlogits = (softmax - onehot) * (*dloss) / max(count,1) on non-ignored rows, 0 elsewhere.
+ *   row_limit (both; NULL = none): device-side int32 row count - rows at or beyond *row_limit are not touched
+ *   (the compacted masked-LM rows, see vb_compact_plan).
  * vb_kl_fwd / vb_kl_bwd: the `kl_1601` criterion (volta/losses.py:16-22):
  *   sum_{label==1} KL(target || softmax(pred)) / max(#label==1, 1) * weight; target fp32 [rows, C].
  *   `row_map`: pred row r reads logits row row_map_base(r) = (r / per) * per_ld + r % per + skip, so the
  *   global-feature row is skipped in place (encoders.py:1085) without a copy.
  */
 int vb_xent_fwd(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C, float* lse,
-                float* loss_sum, float* count, int32_t dtype, void* stream);
+                float* loss_sum, float* count, const int32_t* row_limit, int32_t dtype, void* stream);
 int vb_xent_bwd(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C, const float* lse,
-                const float* count, const float* dloss, void* dlogits, int32_t dtype, void* stream);
+                const float* count, const float* dloss, void* dlogits, const int32_t* row_limit, int32_t dtype,
+                void* stream);
 int vb_kl_fwd(const void* logits, int64_t ld, int32_t per, int32_t per_ld, int32_t skip, const int64_t* label,
               const float* target, int64_t rows, int32_t C, float weight, float* lse, float* loss_sum,
               float* count, int32_t dtype, void* stream);
@@ -270,8 +280,28 @@ int vb_loss_finalize(const float* loss_sum, const float* count, float* out, int3
 int vb_eltwise(int32_t op, const void* a, int32_t a_dtype, int64_t lda, const void* b, int32_t b_dtype,
                int64_t ldb, void* out, int32_t out_dtype, int64_t ldo, int64_t rows, int64_t cols,
                float alpha, float p, uint64_t seed, uint64_t offset, void* stream);
-/* out[c] += sum_r a[r,c]   (fp32 out, atomic accumulate; bias gradients) */
-int vb_colsum(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t cols, float* out, void* stream);
+/* out[c] += sum_r a[r,c]   (fp32 out, atomic accumulate; bias gradients).  row_limit: optional device-side int32
+ * row count (rows at or beyond *row_limit are not read), NULL = all `rows`. */
+int vb_colsum(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t cols, float* out,
+              const int32_t* row_limit, void* stream);
+
+/* ---- row compaction with a device-side count (masked-LM head) ----------
+ * The reference computes vocabulary logits for all B*T positions (volta/encoders.py:686-696, 772) and
+ * CrossEntropyLoss(ignore_index=-1) (encoders.py:1030, 1095-1099) discards the ~90 % that carry no label.  Packing the
+ * labelled rows first and giving the count to the kernels as a DEVICE value (vb_gemm_args::m_limit / k_limit,
+ * row_limit above) gives the same loss and gradients for a tenth of the decoder work, with static launches.
+ * vb_compact_plan: one pass over labels[rows] (int64; label >= 0 = keep, order preserved):
+ *   limits[0] = count, limits[1] = min(rows, count rounded up to `pad`);  src_index[i] = source row of compact row i
+ *   (-1 beyond count);  pos[r] = compact row of source row r or -1;  labels_c[i] = label of compact row i (-1 beyond).
+ * vb_compact_gather: dst[i,:] = src[src_index[i],:] for i < limits[0], zeros for limits[0] <= i < limits[1], rows
+ *   beyond limits[1] are left untouched (never read by the limited kernels).
+ * vb_compact_scatter: dst[r,:] = pos[r] >= 0 ? src_c[pos[r],:] : 0 for every r < rows (the gather's adjoint). */
+int vb_compact_plan(const int64_t* labels, int64_t rows, int32_t pad, int32_t* limits, int32_t* src_index, int32_t* pos,
+                    int64_t* labels_c, void* stream);
+int vb_compact_gather(const void* src, int64_t ld_src, const int32_t* src_index, const int32_t* limits, void* dst,
+                      int64_t ld_dst, int64_t rows, int32_t cols, int32_t dtype, void* stream);
+int vb_compact_scatter(const void* src_c, int64_t ld_src, const int32_t* pos, void* dst, int64_t ld_dst, int64_t rows,
+                       int32_t cols, int32_t dtype, void* stream);
 /* out[r,:] = a[idx[r],:] (gather rows; idx int64) and its scatter-add adjoint */
 int vb_gather_rows(const void* a, int64_t lda, const int64_t* idx, void* out, int64_t ldo, int64_t rows,
                    int64_t cols, int32_t dtype, void* stream);

@@ -24,7 +24,21 @@ def _dgelu(x):
 
 
 def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
-         dropout_p=0.0, seed=0, offset=0, backend=0, split_k=0, M=None, N=None, K=None, b2=None, bias2=None, split_M=0):
+         dropout_p=0.0, seed=0, offset=0, backend=0, split_k=0, M=None, N=None, K=None, b2=None, bias2=None, split_M=0,
+         m_limit=None, k_limit=None):
+    if m_limit is not None or k_limit is not None:   # device-side extents: only that many rows / reduction elements exist
+        A0 = a if a_kmajor else a.t()
+        B0 = b if b_kmajor else b.t()
+        M = A0.shape[0] if M is None else M
+        K = A0.shape[1] if K is None else K
+        if m_limit is not None:
+            M = min(M, int(m_limit[0]))
+        if k_limit is not None:
+            K = min(K, int(k_limit[0]))
+        if M == 0 or K == 0:
+            return out
+        return gemm(a, b, out, a_kmajor=a_kmajor, b_kmajor=b_kmajor, epilogue=epilogue, bias=bias, aux_in=aux_in, aux_out=aux_out,
+                    dropout_p=dropout_p, M=M, N=N, K=K)
     if b2 is not None:   # row-split launch = two ordinary GEMMs over the two row ranges
         assert a_kmajor and epilogue != _lib.EPI_ACCUM
         kw = dict(a_kmajor=a_kmajor, b_kmajor=b_kmajor, epilogue=epilogue, dropout_p=dropout_p, N=N, K=K)
@@ -205,7 +219,10 @@ def box_project_bwd(loc, dout, dW, db):
         db += d.sum(0)
 
 
-def xent_fwd(logits, labels, C_, lse, loss_sum, count):
+def xent_fwd(logits, labels, C_, lse, loss_sum, count, row_limit=None):
+    if row_limit is not None:
+        n = int(row_limit[0])
+        logits, labels, lse = logits[:n], labels[:n], lse[:n]
     x = logits[:, :C_].float()
     live = labels >= 0
     l = torch.logsumexp(x, -1)
@@ -215,13 +232,16 @@ def xent_fwd(logits, labels, C_, lse, loss_sum, count):
     count += live.sum()
 
 
-def xent_bwd(logits, labels, C_, lse, count, dloss, dlogits):
+def xent_bwd(logits, labels, C_, lse, count, dloss, dlogits, row_limit=None):
+    if row_limit is not None:
+        n = int(row_limit[0])
+        logits, labels, lse, dlogits = logits[:n], labels[:n], lse[:n], dlogits[:n]
     x = logits[:, :C_].float()
     live = (labels >= 0)[:, None]
     g = dloss / count.clamp(min=1.0)
     p = torch.exp(x - lse[:, None])
     onehot = F.one_hot(labels.clamp(min=0), C_).float()
-    dlogits[:, :C_] = ((p - onehot) * g * live).to(dlogits.dtype)
+    dlogits[:, :C_] = torch.where(live, (p - onehot) * g, torch.zeros_like(p)).to(dlogits.dtype)
 
 
 def _kl_rows(per, per_ld, skip, rows, device=None):
@@ -323,9 +343,42 @@ def eltwise(op, a, out, b=None, alpha=1.0, p=0.0, seed=0, offset=0):
     return out
 
 
-def colsum(a, out):
-    out[:a.shape[-1]] += a.float().reshape(-1, a.shape[-1]).sum(0)
+def colsum(a, out, row_limit=None):
+    a2 = a.reshape(-1, a.shape[-1])
+    if row_limit is not None:
+        a2 = a2[:int(row_limit[0])]
+    out[:a.shape[-1]] += a2.float().sum(0)
     return out
+
+
+def compact_plan(labels, pad, limits, src_index, pos, labels_c):
+    rows = labels.numel()
+    keep = (labels >= 0).nonzero()[:, 0]
+    n = keep.numel()
+    limits[0] = n
+    limits[1] = min(rows, (n + pad - 1) // pad * pad)
+    src_index[:rows] = -1
+    src_index[:n] = keep.to(torch.int32)
+    pos[:rows] = -1
+    pos[keep] = torch.arange(n, dtype=torch.int32)
+    labels_c[:rows] = -1
+    labels_c[:n] = labels[keep]
+
+
+def compact_gather(src, src_index, limits, dst):
+    n, npad = int(limits[0]), int(limits[1])
+    dst[:n] = src[src_index[:n].long()]
+    dst[n:npad] = 0
+    return dst
+
+
+def compact_scatter(src_c, pos, dst):
+    rows = dst.shape[0]
+    p = pos[:rows].long()
+    dst.zero_()
+    live = p >= 0
+    dst[live] = src_c[p[live]]
+    return dst
 
 
 def gather_rows(a, idx, out):
@@ -388,7 +441,8 @@ def fill(buf, value=0):
 
 _NAMES = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "embed_gather_fwd",
           "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd", "region_loss_fwd", "region_loss_bwd",
-          "loss_finalize", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill"]
+          "loss_finalize", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill",
+          "compact_plan", "compact_gather", "compact_scatter"]
 
 
 def install(monkeypatch):

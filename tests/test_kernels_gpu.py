@@ -129,6 +129,89 @@ def test_gemm_row_split_launch(tile, monkeypatch):
         assert rel(out2.float(), ref2) < 6e-3
 
 
+@pytest.mark.parametrize("backend", ["tc", "simt"])
+@pytest.mark.parametrize("count", [0, 1, 300, 777, 1300])
+def test_gemm_device_side_extents(backend, count):
+    """m_limit / k_limit: the row count lives in device memory (compacted masked-LM rows); tiles / k-blocks beyond it are
+    not scheduled, rows below it match the plain GEMM, rows beyond the last touched tile keep their old contents."""
+    be = _lib.GEMM_TC if backend == "tc" else _lib.GEMM_SIMT
+    M, N, K = 1300, 776, 320
+    npad = min(M, (count + 255) // 256 * 256)
+    lim = torch.tensor([count, npad], dtype=torch.int32, device=DEV)
+    a, w, bias = rnd(M, K), rnd(N, K, scale=0.05), rnd(N, dtype=torch.float32)
+    a[count:] = 0                                   # the caller keeps the operands zero up to the padded count
+    out = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a, w, out, epilogue=_lib.EPI_BIAS, bias=bias, backend=be, m_limit=lim[0:1])
+    if count:
+        assert rel(out[:count].float(), a[:count].float() @ w.float().t() + bias) < 6e-3
+    assert bool((out[npad:] == 7.0).all()), "rows beyond the last scheduled tile were written"
+    # dgrad layout (MN-major B)
+    wt = w.t().contiguous()
+    out2 = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a, wt, out2, a_kmajor=True, b_kmajor=False, backend=be, m_limit=lim[0:1])
+    if count:
+        assert rel(out2[:count].float(), a[:count].float() @ w.float().t()) < 6e-3
+    assert bool((out2[npad:] == 7.0).all())
+    # wgrad: the reduction runs over the rows
+    dy = rnd(M, N, scale=0.5, seed=4)
+    dy[count:] = 0
+    dW = torch.ones(N, K, device=DEV)
+    ops.gemm(dy, a, dW, a_kmajor=False, b_kmajor=False, epilogue=_lib.EPI_ACCUM, backend=be, k_limit=lim[1:2])
+    ref = 1.0 + dy[:count].float().t() @ a[:count].float()
+    assert rel(dW, ref) < 2e-3
+
+
+def test_compact_plan_gather_scatter_and_limited_criterion():
+    """vb_compact_*: order-preserving packing of the labelled rows, exact; cross-entropy / column sums with a device-side
+    row count equal the full-size calls on the same rows."""
+    R, H, C = 3000, 768, 1000
+    g = torch.Generator().manual_seed(3)
+    labels = torch.where(torch.rand(R, generator=g) < 0.12, torch.randint(0, C, (R,), generator=g), torch.full((R,), -1)).to(DEV)
+    x = rnd(R, H)
+    lim = torch.zeros(2, dtype=torch.int32, device=DEV)
+    src, pos = torch.zeros(R, dtype=torch.int32, device=DEV), torch.zeros(R, dtype=torch.int32, device=DEV)
+    lab_c = torch.zeros(R, dtype=torch.int64, device=DEV)
+    ops.compact_plan(labels, 256, lim, src, pos, lab_c)
+    keep = (labels >= 0).nonzero()[:, 0]
+    n = keep.numel()
+    npad = (n + 255) // 256 * 256
+    assert lim.tolist() == [n, npad]
+    assert torch.equal(src[:n].long(), keep) and bool((src[n:] == -1).all())
+    assert torch.equal(lab_c[:n], labels[keep]) and bool((lab_c[n:] == -1).all())
+    assert torch.equal(pos[keep].long(), torch.arange(n, device=DEV)) and int((pos >= 0).sum()) == n
+    xc = torch.full((R, H), 5.0, dtype=torch.bfloat16, device=DEV)
+    ops.compact_gather(x, src, lim, xc)
+    assert torch.equal(xc[:n], x[keep]) and bool((xc[n:npad] == 0).all()) and bool((xc[npad:] == 5.0).all())
+    back = torch.full((R, H), 5.0, dtype=torch.bfloat16, device=DEV)
+    ops.compact_scatter(xc, pos, back)
+    ref = torch.zeros_like(x)
+    ref[keep] = x[keep]
+    assert torch.equal(back, ref)
+    # no labelled row at all
+    none = torch.full((R,), -1, dtype=torch.int64, device=DEV)
+    ops.compact_plan(none, 256, lim, src, pos, lab_c)
+    assert lim.tolist() == [0, 0] and bool((pos == -1).all())
+    # criterion + column sums on the packed rows
+    ops.compact_plan(labels, 256, lim, src, pos, lab_c)
+    logits = rnd(R, C, scale=2.0, seed=5)
+    lg_c = torch.zeros(R, C, dtype=torch.bfloat16, device=DEV)
+    ops.compact_gather(logits, src, lim, lg_c)
+    out = {}
+    for name, (lg, lb, rl_f, rl_b) in dict(full=(logits, labels, None, None), packed=(lg_c, lab_c, lim[0:1], lim[1:2])).items():
+        lse = torch.zeros(R, device=DEV)
+        sums = torch.zeros(2, device=DEV)
+        ops.xent_fwd(lg, lb, C, lse, sums[0:1], sums[1:2], row_limit=rl_f)
+        d = torch.full((R, C), 3.0, dtype=torch.bfloat16, device=DEV)
+        ops.xent_bwd(lg, lb, C, lse, sums[1:2], torch.ones(1, device=DEV), d, row_limit=rl_b)
+        cs = torch.zeros(C, device=DEV)
+        ops.colsum(d, cs, row_limit=rl_b)
+        out[name] = (sums.clone(), d, cs)
+    assert torch.allclose(out["full"][0], out["packed"][0], rtol=1e-5)
+    assert torch.equal(out["packed"][1][:n], out["full"][1][keep])
+    assert bool((out["packed"][1][n:npad] == 0).all()) and bool((out["packed"][1][npad:] == 3.0).all())
+    assert rel(out["packed"][2], out["full"][2]) < 1e-5
+
+
 def test_gemm_tc_strided_rows_and_inplace_add():
     """The pooler reads row 0 of every sample through lda = T*H and adds its dgrad in place through ldd."""
     B, T, H, P = 64, 12, 256, 512

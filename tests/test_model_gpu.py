@@ -181,6 +181,32 @@ def engine_launches():
     return engine.launch_count
 
 
+def test_masked_lm_rows_only_matches_all_positions_decoder(monkeypatch):
+    """The masked-LM head runs the decoder / criterion on the labelled rows only (device-side count).  Against the
+    all-positions decoder of the reference (volta/encoders.py:686-696): same losses, same gradients for every parameter."""
+    from volta_b200 import engine
+    from volta_b200.synthetic import pretraining_batch
+    g, cfg, _ = load_case("mini_ctrl_vilbert")
+    b = pretraining_batch(32, 8, 9, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
+    d = {k: v.cuda() for k, v in b.items()}
+    runs = {}
+    for compact in (True, False):
+        monkeypatch.setattr(engine, "MLM_COMPACT", compact)
+        model = volta_b200.BertForVLPreTraining(cfg)
+        model.load_state_dict(seeded_state_dict(model.state_dict(), seed=0))
+        model.eval().cuda()
+        model._use_cuda_graphs = False
+        l = _losses(model, d)
+        (l[0] + l[1] + l[2]).sum().backward()
+        runs[compact] = ([float(x) for x in l], {k: p.grad.clone() for k, p in model.named_parameters()})
+    (l1, g1), (l0, g0) = runs[True], runs[False]
+    assert all(abs(a - c) < 2e-3 * max(1.0, abs(a)) for a, c in zip(l1, l0)), (l1, l0)
+    for k in g1:
+        den = float(g0[k].norm())
+        if den > 1e-6:
+            assert float((g1[k] - g0[k]).norm()) / den < 3e-2, k
+
+
 def test_cuda_graph_replay_matches_eager_steps():
     """The captured forward/backward graphs (volta_b200/graphs.py) must reproduce the eager path step by step: same
     per-step seeds -> same dropout masks -> same losses; gradients equal up to the order of fp32 atomics; weight

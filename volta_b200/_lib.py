@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
                 ("a_kmajor", _i32), ("b_kmajor", _i32), ("epilogue", _i32), ("backend", _i32),
                 ("bias", _vp), ("aux_in", _vp), ("aux_out", _vp), ("ld_aux", _i64), ("alpha", _f),
                 ("dropout_p", _f), ("seed", _u64), ("offset", _u64), ("split_k", _i32), ("reserved", _i32),
-                ("B2", _vp), ("bias2", _vp), ("split_M", _i64)]
+                ("B2", _vp), ("bias2", _vp), ("split_M", _i64), ("m_limit", _vp), ("k_limit", _vp)]
 
 
 class AttnArgs(C.Structure):
@@ -63,15 +63,18 @@ SIGNATURES = {
     "vb_colsum_by_key": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),
     "vb_box_project_fwd": (_i32, [_vp, _i32, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "vb_box_project_bwd": (_i32, [_vp, _i32, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp]),
-    "vb_xent_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp]),
-    "vb_xent_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "vb_xent_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "vb_xent_bwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "vb_kl_fwd": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp, _i32, _vp]),
     "vb_region_loss_fwd": (_i32, [_i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f, _vp, _vp, _vp, _i32, _i32, _vp]),
     "vb_region_loss_bwd": (_i32, [_i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _i32, _vp]),
     "vb_kl_bwd": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp, _vp, _i32, _vp]),
     "vb_loss_finalize": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "vb_eltwise": (_i32, [_i32, _vp, _i32, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _f, _f, _u64, _u64, _vp]),
-    "vb_colsum": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp]),
+    "vb_colsum": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "vb_compact_plan": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vb_compact_gather": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
+    "vb_compact_scatter": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "vb_gather_rows": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "vb_scatter_rows_add": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "vb_multi_cast_bf16": (_i32, [_vp, _i32, _i64, _vp]),

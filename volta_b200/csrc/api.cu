@@ -35,7 +35,7 @@ int check_launch(const char* what) {
 
 extern "C" {
 
-int vb_version(void) { return 1002; }
+int vb_version(void) { return 1003; }
 
 int vb_set_gemm_sm_limit(int32_t sms) {
   vb::g_gemm_sm_limit = sms > 0 ? sms : 0;

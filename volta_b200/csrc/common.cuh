@@ -45,11 +45,13 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t v) {
 // 16-byte aligned for the vector path; callers check and fall back to `load8_scalar`.
 template <typename T> struct Vec8;
 template <> struct Vec8<bf16> {
-  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) {
-    uint4 r = *reinterpret_cast<const uint4*>(p);
+  typedef uint4 Raw;   // 8 packed elements: keep a prefetched vector in 4 registers until it is needed
+  static __device__ __forceinline__ Raw load_raw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
     float2 a = unpack_bf16x2(r.x), b = unpack_bf16x2(r.y), c = unpack_bf16x2(r.z), d = unpack_bf16x2(r.w);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
   }
+  static __device__ __forceinline__ void load(const bf16* p, float (&v)[8]) { unpack(load_raw(p), v); }
   static __device__ __forceinline__ void store(bf16* p, const float (&v)[8]) {
     uint4 r;
     r.x = pack_bf16x2(v[0], v[1]); r.y = pack_bf16x2(v[2], v[3]);
@@ -58,10 +60,16 @@ template <> struct Vec8<bf16> {
   }
 };
 template <> struct Vec8<float> {
-  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) {
-    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  struct Raw { float4 a, b; };
+  static __device__ __forceinline__ Raw load_raw(const float* p) {
+    Raw r;
+    r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4);
+    return r;
   }
+  static __device__ __forceinline__ void unpack(const Raw& r, float (&v)[8]) {
+    v[0] = r.a.x; v[1] = r.a.y; v[2] = r.a.z; v[3] = r.a.w; v[4] = r.b.x; v[5] = r.b.y; v[6] = r.b.z; v[7] = r.b.w;
+  }
+  static __device__ __forceinline__ void load(const float* p, float (&v)[8]) { unpack(load_raw(p), v); }
   static __device__ __forceinline__ void store(float* p, const float (&v)[8]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);

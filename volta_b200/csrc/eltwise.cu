@@ -87,11 +87,14 @@ eltwise_vec_kernel(int op, const TA* __restrict__ a, int64_t lda, const TA* __re
 // column sums: block handles a 32-column strip x a slab of rows; lanes walk columns (coalesced), warps walk rows.
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t cols, float* __restrict__ out, int64_t rows_per_block) {
+colsum_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t cols, float* __restrict__ out, int64_t rows_per_block,
+              const int32_t* __restrict__ row_limit) {
   __shared__ float part[8][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + lane;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  if (row_limit) rows = min(rows, (int64_t)*row_limit);   // device-side row count
+  if (r0 >= rows) return;
   const int64_t r1 = min(rows, r0 + rows_per_block);
   float s = 0.f;
   if (c < cols)
@@ -111,12 +114,15 @@ colsum_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t cols, 
 // the slab's rows with 4 loads in flight each; partials meet in shared memory, one atomicAdd per column and block.
 template <typename T>
 __global__ void __launch_bounds__(256)
-colsum_vec_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t cols, float* __restrict__ out, int64_t rows_per_block) {
+colsum_vec_kernel(const T* __restrict__ a, int64_t lda, int64_t rows, int64_t cols, float* __restrict__ out, int64_t rows_per_block,
+                  const int32_t* __restrict__ row_limit) {
   pdl_enter();
   __shared__ float part[8][32][9];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t c = ((int64_t)blockIdx.x * 32 + lane) * 8;
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  if (row_limit) rows = min(rows, (int64_t)*row_limit);
+  if (r0 >= rows) return;
   const int64_t r1 = min(rows, r0 + rows_per_block);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (c < cols) {
@@ -248,7 +254,8 @@ int vb_eltwise(int32_t op, const void* a, int32_t a_dtype, int64_t lda, const vo
   return vb::check_launch("eltwise_kernel");
 }
 
-int vb_colsum(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t cols, float* out, void* stream) {
+int vb_colsum(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t cols, float* out, const int32_t* row_limit,
+              void* stream) {
   VB_REQUIRE(a && out, VB_ERR_ARG, "colsum: null pointer");
   if (rows * cols == 0) return 0;
   const int64_t es = dtype == VB_BF16 ? 2 : 4;
@@ -259,9 +266,9 @@ int vb_colsum(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t c
     slabs = vb::ceil_div(rows, rpb);
     dim3 grid((unsigned)strips, (unsigned)slabs);
     if (dtype == VB_BF16)
-      vb::launch_pdl(vb::elt::colsum_vec_kernel<vb::bf16>, grid, dim3(256), 0, (cudaStream_t)stream, (const vb::bf16*)a, lda, rows, cols, out, rpb);
+      vb::launch_pdl(vb::elt::colsum_vec_kernel<vb::bf16>, grid, dim3(256), 0, (cudaStream_t)stream, (const vb::bf16*)a, lda, rows, cols, out, rpb, row_limit);
     else
-      vb::launch_pdl(vb::elt::colsum_vec_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)a, lda, rows, cols, out, rpb);
+      vb::launch_pdl(vb::elt::colsum_vec_kernel<float>, grid, dim3(256), 0, (cudaStream_t)stream, (const float*)a, lda, rows, cols, out, rpb, row_limit);
     (void)es;
     return vb::check_launch("colsum_vec_kernel");
   }
@@ -271,9 +278,9 @@ int vb_colsum(const void* a, int32_t dtype, int64_t lda, int64_t rows, int64_t c
   slabs = vb::ceil_div(rows, rpb);
   dim3 grid((unsigned)strips, (unsigned)slabs);
   if (dtype == VB_BF16)
-    vb::elt::colsum_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const vb::bf16*)a, lda, rows, cols, out, rpb);
+    vb::elt::colsum_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const vb::bf16*)a, lda, rows, cols, out, rpb, row_limit);
   else
-    vb::elt::colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, rows, cols, out, rpb);
+    vb::elt::colsum_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)a, lda, rows, cols, out, rpb, row_limit);
   return vb::check_launch("colsum_kernel");
 }
 

@@ -78,6 +78,10 @@ struct Params {
   int32_t split_m_blk;   // tiles with m_blk >= split_m_blk take the second B operand / bias (row-split launch); INT_MAX = none
   const float* bias2;
   int32_t clc;           // 1: work items come from cluster launch control (grid = one cluster per work item); 0: static stride
+  // Device-side extents (vb_gemm_args::m_limit / k_limit): only the first *m_limit rows of the output / the first
+  // *k_limit elements of the reduction hold data; whole tiles / k-blocks beyond them are not scheduled.
+  const int32_t* m_limit;
+  const int32_t* k_limit;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -647,8 +651,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int64_t tiles = (int64_t)p.num_m_blocks * p.num_n_blocks;   // tiles of (CG*128) x BN
-  const int64_t total_work = tiles * p.split_k;
+  int num_m_blocks = p.num_m_blocks, kb_total = p.kb_total, split_k = p.split_k;
+  if (p.m_limit) num_m_blocks = min(num_m_blocks, (max(*p.m_limit, 0) + BM * CG - 1) / (BM * CG));
+  if (p.k_limit) {
+    kb_total = min(kb_total, (max(*p.k_limit, 0) + BK - 1) / BK);
+    split_k = (kb_total + p.kb_per_split - 1) / p.kb_per_split;   // trailing slices are empty: not scheduled at all
+  }
+  const int64_t tiles = (int64_t)num_m_blocks * p.num_n_blocks;   // tiles of (CG*128) x BN
+  const int64_t total_work = tiles * split_k;
   const int64_t first = blockIdx.x / CG, step = gridDim.x / CG;     // one work item per CTA (pair) at a time
   // Work items.  Static mode: first, first + step, ... (grid = resident CTAs).  Cluster-launch-control mode (p.clc): the
   // grid has one cluster per work item; a resident cluster does its own item, then keeps cancelling clusters that have
@@ -675,7 +685,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer (every CTA loads its own A rows and its share of B) =====================
     int stage = 0; uint32_t phase = 0;
     int q = 0;
-    for (int64_t w = first;;) {
+    if (first < total_work) for (int64_t w = first;;) {
       if (p.clc && rank == 0) {
         const int slot = q & 1; const uint32_t par = (uint32_t)(q >> 1) & 1u;
         mbar_wait(clc_empty(slot), par ^ 1u);
@@ -683,14 +693,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (CG == 2) mbar_expect_tx_cluster(mapa_shared(clc_full(slot), 1), 16);
         clc_try_cancel<CG == 2>(clc_resp(slot), clc_full(slot));
       }
-      const int split = (int)(w % p.split_k);
-      const int64_t tile = w / p.split_k;
+      const int split = (int)(w % split_k);
+      const int64_t tile = w / split_k;
       const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
       const int m0 = (m_blk * CG + (int)rank) * BM;
       const int n0 = n_blk * BN + (int)rank * (int)C::B_ROWS;
       const CUtensorMap* mapB = (m_blk >= p.split_m_blk) ? &tmB2 : &tmB;   // row-split launch: second stream's weights
       const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const int kb1 = min(kb_total, kb0 + p.kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         uint32_t fb = full_bar(stage);
@@ -725,10 +735,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t a_step = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);  // bytes per UMMA_K step
     const uint32_t b_step = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
     int q = 0;
-    for (int64_t w = first;; ++it) {
-      const int split = (int)(w % p.split_k);
+    if (first < total_work) for (int64_t w = first;; ++it) {
+      const int split = (int)(w % split_k);
       const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      const int kb1 = min(kb_total, kb0 + p.kb_per_split);
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tcgen05_fence_after();
@@ -759,8 +769,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t my_aux_bar = aux_bar(warp - EPI_WARP0);
     uint32_t aux_phase = 0;
     int it = 0, q = 0;
-    for (int64_t w = first;; ++it) {
-      const int64_t tile = w / p.split_k;
+    if (first < total_work) for (int64_t w = first;; ++it) {
+      const int64_t tile = w / split_k;
       const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
       // Stage this tile's bias slice in shared memory while the MMAs are still running.  Double buffered by
@@ -954,7 +964,9 @@ static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
   // in isolation (qkv 35.5 vs 31.8 us), equal inside the single-GPU step, 0.25 ms/step SLOWER with the NCCL
   // all-reduce running next to the backward (19.1 vs 18.85 ms at 2 GPUs) - so the collective does not starve
   // statically assigned tiles, and the static grid stays the default.
-  p.clc = (use_clc() && work * CG < (int64_t)INT32_MAX) ? 1 : 0;
+  p.m_limit = a.m_limit;
+  p.k_limit = a.k_limit;
+  p.clc = (use_clc() && work * CG < (int64_t)INT32_MAX && !a.m_limit && !a.k_limit) ? 1 : 0;
   const int grid = (int)(p.clc ? work : std::min<int64_t>(work, units)) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);

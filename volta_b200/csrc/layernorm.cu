@@ -80,48 +80,68 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
               const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int H, float out_scale,
               T* __restrict__ dx_drop, uint32_t drop_thresh, float drop_scale, uint64_t seed_in, uint64_t offset,
-              float* __restrict__ dbias, const uint64_t* __restrict__ seed_ptr) {
+              float* __restrict__ dbias, const uint64_t* __restrict__ seed_ptr, int early_fetch) {
   pdl_enter();
   const uint64_t seed = effective_seed(seed_in, seed_ptr);
-  extern __shared__ __align__(16) float red[];  // [3 or 2][WARPS][H]
+  extern __shared__ __align__(16) float red[];  // [3 or 2][WARPS][H] partial sums, then gamma [H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
   const int64_t total_warps = (int64_t)gridDim.x * WARPS;
   float* sg = red + warp * H;
   float* sb = red + (WARPS + warp) * H;
   float* sx = red + (2 * WARPS + warp) * H;
-  float gm[NV][8];
+  float* sgam = red + (EXTRA ? 3 : 2) * WARPS * H;   // gamma, shared by the block (frees 8*NV registers per thread)
+  for (int c = threadIdx.x * 4; c < H; c += WARPS * 32 * 4)
+    *reinterpret_cast<float4*>(sgam + c) = *reinterpret_cast<const float4*>(gamma + c);
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int c = (lane + 32 * i) * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) gm[i][j] = 0.f;
     if (c < H) {
-      Vec8<float>::load(gamma + c, gm[i]);
       const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       Vec8<float>::store(sg + c, z);
       Vec8<float>::store(sb + c, z);
       if constexpr (EXTRA) Vec8<float>::store(sx + c, z);
     }
   }
-  for (int64_t row = warp_global; row < rows; row += total_warps) {
-    const float mu = mean[row], rs = rstd[row];
+  __syncthreads();
+  // Software pipeline over the rows of this warp: the (still packed) dy / x vectors of the NEXT row are requested
+  // before the current row is processed, so the HBM latency of a row hides under the ~1000 instructions of the
+  // previous one instead of stalling all warps of the SM in the same phase.
+  using Raw = typename Vec8<T>::Raw;
+  Raw nd[NV], nx[NV];
+  float nmu = 0.f, nrs = 0.f;
+  auto fetch = [&](int64_t r) {
+    nmu = mean[r]; nrs = rstd[r];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < H) {
+        nd[i] = Vec8<T>::load_raw(dy + r * H + c);
+        nx[i] = Vec8<T>::load_raw(x + r * H + c);
+      }
+    }
+  };
+  int64_t row = warp_global;
+  if (row < rows) fetch(row);
+  for (; row < rows; row += total_warps) {
+    const float mu = nmu, rs = nrs;
     float xh[NV][8], g[NV][8];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + 32 * i) * 8;
       if (c < H) {
-        float d[8], xv[8], a8[8], b8[8];
-        Vec8<T>::load(dy + row * H + c, d);
-        Vec8<T>::load(x + row * H + c, xv);
+        float d[8], xv[8], a8[8], b8[8], gm[8];
+        Vec8<T>::unpack(nd[i], d);
+        Vec8<T>::unpack(nx[i], xv);
+        Vec8<float>::load(sgam + c, gm);
         Vec8<float>::load(sg + c, a8);
         Vec8<float>::load(sb + c, b8);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float dyo = d[j] * out_scale;
           xh[i][j] = (xv[j] - mu) * rs;
-          g[i][j] = dyo * gm[i][j];
+          g[i][j] = dyo * gm[j];
           c1 += g[i][j];
           c2 += g[i][j] * xh[i][j];
           a8[j] = fmaf(dyo, xh[i][j], a8[j]);
@@ -134,6 +154,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
         for (int j = 0; j < 8; ++j) { xh[i][j] = 0.f; g[i][j] = 0.f; }
       }
     }
+    if (early_fetch && row + total_warps < rows) fetch(row + total_warps);   // nd / nx are dead here: reuse them for the next row
     c1 = warp_sum(c1) / (float)H;
     c2 = warp_sum(c2) / (float)H;
 #pragma unroll
@@ -168,6 +189,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
         }
       }
     }
+    if (!early_fetch && row + total_warps < rows) fetch(row + total_warps);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < H; c += WARPS * 32) {
@@ -217,16 +239,18 @@ static int bwd_dispatch(const void* dy, const void* x, const float* mean, const 
   if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   // enough rows per warp to amortise the column reduction, enough blocks to fill the machine
   int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), (int64_t)sms * 2);  // two resident blocks per SM
-  const size_t smem = (size_t)(extra ? 3 : 2) * WARPS * H * sizeof(float);
+  const size_t smem = ((size_t)(extra ? 3 : 2) * WARPS + 1) * H * sizeof(float);
   const uint32_t thresh = dx_drop ? dropout_thresh(p) : 0u;
   const float scale = 1.f / (1.f - p);
+  const char* ef = getenv("VOLTA_B200_LN_EARLY_FETCH");
+  const int early = (ef && ef[0] == '0') ? 0 : 1;
 #define VB_LN_BWD(NV_, EX_)                                                                                      \
   do {                                                                                                           \
     if (smem > 48 * 1024)                                                                                        \
       cudaFuncSetAttribute(ln_bwd_kernel<T, NV_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     launch_pdl(ln_bwd_kernel<T, NV_, EX_>, dim3((unsigned)grid), dim3(WARPS * 32), smem, st,                    \
         (const T*)dy, (const T*)x, mean, rstd, gamma, (T*)dx, dgamma, dbeta, rows, H, out_scale, (T*)dx_drop,    \
-        thresh, scale, seed, offset, dbias, seed_pointer());                                                                     \
+        thresh, scale, seed, offset, dbias, seed_pointer(), early);                                                                     \
   } while (0)
 #define VB_LN_BWD2(NV_) do { if (extra) VB_LN_BWD(NV_, true); else VB_LN_BWD(NV_, false); } while (0)
   switch (nv) {

@@ -58,9 +58,11 @@ __device__ __forceinline__ float row_lse(const T* __restrict__ x, int C, bool ve
 template <typename T>
 __global__ void __launch_bounds__(THREADS)
 xent_fwd_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels, int C,
-                float* __restrict__ lse_out, float* __restrict__ loss_sum, float* __restrict__ count, bool vec_ok) {
+                float* __restrict__ lse_out, float* __restrict__ loss_sum, float* __restrict__ count, bool vec_ok,
+                const int32_t* __restrict__ row_limit) {
   __shared__ float sh[THREADS / 32];
   const int64_t r = blockIdx.x;
+  if (row_limit && r >= *row_limit) return;   // device-side row count (compacted rows): nothing beyond it exists
   const int64_t lab = labels[r];
   if (lab < 0 || lab >= C) {  // ignore_index = -1
     if (threadIdx.x == 0) lse_out[r] = 0.f;
@@ -79,8 +81,9 @@ template <typename T>
 __global__ void __launch_bounds__(THREADS)
 xent_bwd_kernel(const T* __restrict__ logits, int64_t ld, const int64_t* __restrict__ labels, int C,
                 const float* __restrict__ lse, const float* __restrict__ count, const float* __restrict__ dloss,
-                T* __restrict__ dlogits, bool vec_ok) {
+                T* __restrict__ dlogits, bool vec_ok, const int32_t* __restrict__ row_limit) {
   const int64_t r = blockIdx.x;
+  if (row_limit && r >= *row_limit) return;
   const int64_t lab = labels[r];
   const T* x = logits + r * ld;
   T* d = dlogits + r * ld;
@@ -253,32 +256,32 @@ template <typename T> static bool row_vec_ok(const void* p, int64_t ld) {
 extern "C" {
 
 int vb_xent_fwd(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C, float* lse,
-                float* loss_sum, float* count, int32_t dtype, void* stream) {
+                float* loss_sum, float* count, const int32_t* row_limit, int32_t dtype, void* stream) {
   VB_REQUIRE(logits && labels && lse && loss_sum && count && C > 0 && ld >= C, VB_ERR_ARG, "xent_fwd: bad arguments");
   if (rows == 0) return 0;
   using namespace vb::loss;
   if (dtype == VB_BF16)
     xent_fwd_kernel<vb::bf16><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
-        (const vb::bf16*)logits, ld, labels, C, lse, loss_sum, count, row_vec_ok<vb::bf16>(logits, ld));
+        (const vb::bf16*)logits, ld, labels, C, lse, loss_sum, count, row_vec_ok<vb::bf16>(logits, ld), row_limit);
   else
     xent_fwd_kernel<float><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
-        (const float*)logits, ld, labels, C, lse, loss_sum, count, row_vec_ok<float>(logits, ld));
+        (const float*)logits, ld, labels, C, lse, loss_sum, count, row_vec_ok<float>(logits, ld), row_limit);
   return vb::check_launch("xent_fwd_kernel");
 }
 
 int vb_xent_bwd(const void* logits, int64_t ld, const int64_t* labels, int64_t rows, int32_t C, const float* lse,
-                const float* count, const float* dloss, void* dlogits, int32_t dtype, void* stream) {
+                const float* count, const float* dloss, void* dlogits, const int32_t* row_limit, int32_t dtype, void* stream) {
   VB_REQUIRE(logits && labels && lse && count && dloss && dlogits && C > 0 && ld >= C, VB_ERR_ARG, "xent_bwd: bad arguments");
   if (rows == 0) return 0;
   using namespace vb::loss;
   if (dtype == VB_BF16)
     xent_bwd_kernel<vb::bf16><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
         (const vb::bf16*)logits, ld, labels, C, lse, count, dloss, (vb::bf16*)dlogits,
-        row_vec_ok<vb::bf16>(logits, ld) && row_vec_ok<vb::bf16>(dlogits, ld));
+        row_vec_ok<vb::bf16>(logits, ld) && row_vec_ok<vb::bf16>(dlogits, ld), row_limit);
   else
     xent_bwd_kernel<float><<<(unsigned)rows, THREADS, 0, (cudaStream_t)stream>>>(
         (const float*)logits, ld, labels, C, lse, count, dloss, (float*)dlogits,
-        row_vec_ok<float>(logits, ld) && row_vec_ok<float>(dlogits, ld));
+        row_vec_ok<float>(logits, ld) && row_vec_ok<float>(dlogits, ld), row_limit);
   return vb::check_launch("xent_bwd_kernel");
 }
 

@@ -136,6 +136,8 @@ def model_store(model):
 # ====================================================================================================
 # building blocks (forward returns outputs + a `saved` record; backward consumes it)
 # ====================================================================================================
+# Masked-LM decoder on the labelled rows only (heads_fwd); VOLTA_B200_MLM_COMPACT=0 restores the all-positions decoder.
+MLM_COMPACT = os.environ.get("VOLTA_B200_MLM_COMPACT", "1") != "0"
 _SIDE_STREAMS = {}
 _SIDE_STREAMS_ON = os.environ.get("VOLTA_B200_SIDE_STREAM", "1") != "0"
 
@@ -823,8 +825,26 @@ def heads_fwd(rt, model, x, pooled_t, pooled_v, labels, want_logits=False):
     E = rt.cw(cls.predictions.decoder.weight)
     ldv = _pad8(V_)
     mlm_logits = rt.empty(rt.Mt, ldv)
-    rt.gemm(hn, E, mlm_logits, epilogue=EPI_BIAS, bias=rt.w32(cls.predictions.bias), N=V_)
+    cmp_ = None
+    if MLM_COMPACT and not want_logits and labels.get("mlm") is not None:
+        # The loss ignores every position whose label is -1 (CrossEntropyLoss(ignore_index=-1), reference:
+        # volta/encoders.py:1030, 1095-1099) - ~90 % of the B*T rows.  Pack the labelled rows first and run the decoder /
+        # criterion on `count` rows; the count stays on the device (static launches, CUDA-graph friendly).  Same loss,
+        # same gradients as the reference's all-positions decoder (:686-696).
+        lab_full = labels["mlm"].reshape(-1).to(torch.int64).contiguous()
+        limits = rt.empty(2, dtype=torch.int32)          # [count, count rounded up to 256]
+        src_index, pos = rt.empty(rt.Mt, dtype=torch.int32), rt.empty(rt.Mt, dtype=torch.int32)
+        lab_c = rt.empty(rt.Mt, dtype=torch.int64)
+        ops.compact_plan(lab_full, 256, limits, src_index, pos, lab_c)
+        hc = rt.empty(rt.Mt, hn.shape[1])
+        ops.compact_gather(hn, src_index, limits, hc)
+        _count(2)
+        rt.gemm(hc, E, mlm_logits, epilogue=EPI_BIAS, bias=rt.w32(cls.predictions.bias), N=V_, m_limit=limits[0:1])
+        cmp_ = (limits, pos, lab_c, hc)
+    else:
+        rt.gemm(hn, E, mlm_logits, epilogue=EPI_BIAS, bias=rt.w32(cls.predictions.bias), N=V_)
     s["mlm"] = (hn, mlm_logits)
+    s["mlm_compact"] = cmp_
     # --- ITM
     itm_logits, pooled = None, None
     fm = cfg.fusion_method
@@ -860,9 +880,13 @@ def heads_fwd(rt, model, x, pooled_t, pooled_v, labels, want_logits=False):
     losses = rt.empty(4, dtype=torch.float32)
     s["sums"] = sums
     if labels.get("mlm") is not None:
-        lab = labels["mlm"].reshape(-1).to(torch.int64).contiguous()
         lse = rt.empty(rt.Mt, dtype=torch.float32)
-        ops.xent_fwd(mlm_logits, lab, V_, lse, sums[0:1], sums[4:5])
+        if cmp_ is not None:
+            lab = cmp_[2]
+            ops.xent_fwd(mlm_logits, lab, V_, lse, sums[0:1], sums[4:5], row_limit=cmp_[0][0:1])
+        else:
+            lab = labels["mlm"].reshape(-1).to(torch.int64).contiguous()
+            ops.xent_fwd(mlm_logits, lab, V_, lse, sums[0:1], sums[4:5])
         _count()
         s["mlm_loss"] = (lab, lse)
     if labels.get("image_label") is not None:
@@ -930,15 +954,26 @@ def heads_bwd(rt, model, s, dlosses, x):
     hn, mlm_logits = s["mlm"]
     if "mlm_loss" in s:
         lab, lse = s["mlm_loss"]
-        ops.xent_bwd(mlm_logits, lab, cfg.vocab_size, lse, sums[4:5], dlosses[0:1], mlm_logits)  # in place
-        _count()
-        dlog = mlm_logits[:, :cfg.vocab_size]
+        cmp_ = s.get("mlm_compact")
         E = cls.predictions.decoder
-        rt.gemm(dlog, hn, rt.g32(E.weight), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)
-        ops.colsum(dlog, rt.g32(cls.predictions.bias))
-        _count()
+        dlog = mlm_logits[:, :cfg.vocab_size]
         dhn = rt.empty(*hn.shape)
-        rt.gemm(dlog, rt.cw(E.weight), dhn, a_kmajor=True, b_kmajor=False)
+        if cmp_ is not None:
+            limits, pos, _, hc = cmp_
+            n, npad = limits[0:1], limits[1:2]     # rows [count, npad) are zero rows: they complete the last tile / k-block
+            ops.xent_bwd(mlm_logits, lab, cfg.vocab_size, lse, sums[4:5], dlosses[0:1], mlm_logits, row_limit=npad)  # in place
+            rt.gemm(dlog, hc, rt.g32(E.weight), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, k_limit=npad)
+            ops.colsum(dlog, rt.g32(cls.predictions.bias), row_limit=npad)
+            dhc = rt.empty(*hn.shape)
+            rt.gemm(dlog, rt.cw(E.weight), dhc, a_kmajor=True, b_kmajor=False, m_limit=n)
+            ops.compact_scatter(dhc, pos, dhn)
+            _count(3)
+        else:
+            ops.xent_bwd(mlm_logits, lab, cfg.vocab_size, lse, sums[4:5], dlosses[0:1], mlm_logits)  # in place
+            rt.gemm(dlog, hn, rt.g32(E.weight), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)
+            ops.colsum(dlog, rt.g32(cls.predictions.bias))
+            _count(2)
+            rt.gemm(dlog, rt.cw(E.weight), dhn, a_kmajor=True, b_kmajor=False)
         _transform_bwd(rt, cls.predictions.transform, dhn, s["mlm_tr"], dx.t)
     else:
         ops.fill(dx.t, 0)

@@ -49,8 +49,9 @@ def require_cuda(*ts):
 # --------------------------------------------------------------------------- GEMM
 def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
          dropout_p=0.0, seed=0, offset=0, backend=_lib.GEMM_AUTO, split_k=0, M=None, N=None, K=None, b2=None, bias2=None,
-         split_M=0):
-    """out[M,N] = epilogue(opA . opB^T); see vb_gemm in include/volta_b200.h."""
+         split_M=0, m_limit=None, k_limit=None):
+    """out[M,N] = epilogue(opA . opB^T); see vb_gemm in include/volta_b200.h.  m_limit / k_limit: int32 device tensors
+    (one element) holding the number of rows / reduction elements that carry data (see vb_compact_plan)."""
     require_cuda(a, b, out)
     ar, ac, lda = _rows2d(a)
     br, bc, ldb = _rows2d(b)
@@ -83,11 +84,17 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bia
     if b2 is not None:   # row-split launch: rows >= split_M use b2 / bias2
         assert b2.shape == b.shape and b2.stride() == b.stride() and b2.dtype == b.dtype and 0 < split_M < M
         g.B2, g.bias2, g.split_M = b2.data_ptr(), _ptr(bias2), int(split_M)
+    for name, lim in (("m_limit", m_limit), ("k_limit", k_limit)):
+        if lim is not None:
+            assert lim.dtype == torch.int32 and lim.is_cuda and lim.numel() >= 1
+            setattr(g, name, lim.data_ptr())
     _lib.call("vb_gemm", C.byref(g), _stream())
     if GEMM_BENCH is not None:  # bench.py: device time of this launch, repeated back to back (no host gaps)
         ms = C.c_float(0.0)
         _lib.call("vb_gemm_bench", C.byref(g), _stream(), 5, C.byref(ms))
-        GEMM_BENCH.append((2.0 * M * N * K, ms.value, _lib.load().vb_gemm_backend(C.byref(g)) == _lib.GEMM_TC,
+        Me = M if m_limit is None else min(M, int(m_limit[0].item()))   # executed extents of a device-limited launch
+        Ke = K if k_limit is None else min(K, int(k_limit[0].item()))
+        GEMM_BENCH.append((2.0 * Me * N * Ke, ms.value, _lib.load().vb_gemm_backend(C.byref(g)) == _lib.GEMM_TC,
                            "M%d N%d K%d a%d b%d epi%d" % (M, N, K, a_kmajor, b_kmajor, epilogue)))
     return out
 
@@ -215,18 +222,51 @@ def box_project_bwd(loc, dout, dW, db):
 
 
 # --------------------------------------------------------------------------- losses
-def xent_fwd(logits, labels, C_, lse, loss_sum, count):
+def _limit_ptr(lim):
+    if lim is None:
+        return None
+    assert lim.dtype == torch.int32 and lim.is_cuda and lim.numel() >= 1
+    return lim.data_ptr()
+
+
+def xent_fwd(logits, labels, C_, lse, loss_sum, count, row_limit=None):
     rows, _, ld = _rows2d(logits)
     assert labels.dtype == torch.int64 and labels.numel() == rows
     _lib.call("vb_xent_fwd", logits.data_ptr(), ld, labels.data_ptr(), rows, C_, lse.data_ptr(), loss_sum.data_ptr(),
-              count.data_ptr(), dt(logits), _stream())
+              count.data_ptr(), _limit_ptr(row_limit), dt(logits), _stream())
 
 
-def xent_bwd(logits, labels, C_, lse, count, dloss, dlogits):
+def xent_bwd(logits, labels, C_, lse, count, dloss, dlogits, row_limit=None):
     rows, _, ld = _rows2d(logits)
     assert _rows2d(dlogits)[2] == ld
     _lib.call("vb_xent_bwd", logits.data_ptr(), ld, labels.data_ptr(), rows, C_, lse.data_ptr(), count.data_ptr(),
-              dloss.data_ptr(), dlogits.data_ptr(), dt(logits), _stream())
+              dloss.data_ptr(), dlogits.data_ptr(), _limit_ptr(row_limit), dt(logits), _stream())
+
+
+def compact_plan(labels, pad, limits, src_index, pos, labels_c):
+    """Order-preserving compaction plan of the rows with label >= 0 (vb_compact_plan)."""
+    rows = labels.numel()
+    assert labels.dtype == torch.int64 and labels_c.dtype == torch.int64 and labels_c.numel() >= rows
+    for t_ in (limits, src_index, pos):
+        assert t_.dtype == torch.int32
+    assert limits.numel() >= 2 and src_index.numel() >= rows and pos.numel() >= rows
+    _lib.call("vb_compact_plan", labels.data_ptr(), rows, int(pad), limits.data_ptr(), src_index.data_ptr(), pos.data_ptr(),
+              labels_c.data_ptr(), _stream())
+
+
+def compact_gather(src, src_index, limits, dst):
+    rows, cols, ld_dst = _rows2d(dst)
+    _lib.call("vb_compact_gather", src.data_ptr(), _rows2d(src)[2], src_index.data_ptr(), limits.data_ptr(), dst.data_ptr(),
+              ld_dst, rows, cols, dt(src), _stream())
+    return dst
+
+
+def compact_scatter(src_c, pos, dst):
+    rows, cols, ld_dst = _rows2d(dst)
+    assert pos.numel() >= rows
+    _lib.call("vb_compact_scatter", src_c.data_ptr(), _rows2d(src_c)[2], pos.data_ptr(), dst.data_ptr(), ld_dst, rows, cols,
+              dt(src_c), _stream())
+    return dst
 
 
 def kl_fwd(logits, per, per_ld, skip, label, target, C_, weight, lse, loss_sum, count):
@@ -284,10 +324,10 @@ def eltwise(op, a, out, b=None, alpha=1.0, p=0.0, seed=0, offset=0):
     return out
 
 
-def colsum(a, out):
+def colsum(a, out, row_limit=None):
     rows, cols, lda = _rows2d(a)
     assert out.dtype == torch.float32 and out.numel() >= cols
-    _lib.call("vb_colsum", a.data_ptr(), dt(a), lda, rows, cols, out.data_ptr(), _stream())
+    _lib.call("vb_colsum", a.data_ptr(), dt(a), lda, rows, cols, out.data_ptr(), _limit_ptr(row_limit), _stream())
     return out
 
 
