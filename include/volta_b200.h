@@ -192,10 +192,17 @@ typedef struct vb_attn_args {
   uint64_t seed, offset;
   int32_t backend;                    /* VB_ATTN_AUTO | VB_ATTN_MMA (bf16 tensor-core path) | VB_ATTN_SIMT */
   int32_t reserved;
+  /* Optional [B] int32 per stream (NULL = none), from vb_mask_lengths: positions at or beyond len[b] are padding.  The
+   * tensor-core back-end then skips whole 16-row tiles of padding: as keys their softmax weight is exactly 0 (additive
+   * -10000 underflows), as queries nothing reads them (their context / dQ rows are written as zeros, the reference
+   * leaves finite garbage there).  Masked positions below the length are handled by the additive mask as usual. */
+  const int32_t* len_t; const int32_t* len_v;
 } vb_attn_args;
 
 int vb_attention_fwd(const vb_attn_args* args, void* stream);
 int vb_attention_bwd(const vb_attn_args* args, void* stream);
+/* len[b] = 1 + index of the last position with mask[b, j] != 0, or 0 if the sample has none. */
+int vb_mask_lengths(const int32_t* mask, int32_t B, int32_t L, int32_t* len, void* stream);
 
 /* ---- embeddings -------------------------------------------------------
  * vb_embed_gather_fwd: out[r,:] = (accum? out[r,:] : 0) + sum_j table_j[idx_j[r], :]  for up to 4

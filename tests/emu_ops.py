@@ -161,8 +161,14 @@ def attention_fwd(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, L
         ldst.copy_(lse)
 
 
+def mask_lengths(mask, out):
+    idx = torch.arange(1, mask.shape[1] + 1, dtype=torch.int32)
+    out.copy_(((mask != 0).to(torch.int32) * idx).max(1).values)
+    return out
+
+
 def attention_bwd(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, Lv, heads, d, pair_mask, p_t, p_v,
-                  seed, backend, dctx_t=None, dctx_v=None, dqkv_t=None, dqkv_v=None):
+                  seed, backend, dctx_t=None, dctx_v=None, dqkv_t=None, dqkv_v=None, **kw):
     leaves = {}
     with torch.enable_grad():
         a = qkv_t.detach().float().requires_grad_(True) if qkv_t is not None else None
@@ -442,7 +448,7 @@ def fill(buf, value=0):
 _NAMES = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "embed_gather_fwd",
           "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd", "region_loss_fwd", "region_loss_bwd",
           "loss_finalize", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill",
-          "compact_plan", "compact_gather", "compact_scatter"]
+          "compact_plan", "compact_gather", "compact_scatter", "mask_lengths"]
 
 
 def install(monkeypatch):

@@ -351,6 +351,59 @@ def test_attention_fwd_bwd(backend, B, Lt, Lv, heads, d, pm):
             assert rel(got.float(), ref.float()) < 2e-2
 
 
+@pytest.mark.parametrize("B,Lt,Lv,heads,d,pm", [(4, 36, 37, 12, 64, 1), (4, 36, 37, 12, 64, 9), (4, 36, 37, 12, 64, 6),
+                                                (4, 36, 37, 12, 64, 15), (4, 30, 101, 8, 128, 6), (4, 56, 80, 4, 64, 15)])
+def test_attention_skips_trailing_padding(B, Lt, Lv, heads, d, pm):
+    """vb_attn_args::len_*: tiles of trailing padding are skipped.  Valid rows must match the full computation (masked
+    keys have weight exactly 0), padded query rows come out as zeros, gradients of valid rows are unchanged when the
+    upstream gradient of the padded rows is zero (nothing downstream reads them); a hole in the mask below the length
+    still goes through the additive mask."""
+    dtype = torch.bfloat16
+    qt, qv, _, _, A = _attn_inputs(B, Lt, Lv, heads, d, pm, dtype)
+    lens_t = torch.tensor([Lt, 5, 17, 0][:B])
+    lens_v = torch.tensor([3, Lv, 0, 20][:B])
+    mt = (torch.arange(Lt)[None] < lens_t[:, None]).int()
+    mv = (torch.arange(Lv)[None] < lens_v[:, None]).int()
+    mt[0, 2] = 0                      # holes below the length
+    mv[1, 1] = 0
+    mt, mv = mt.to(DEV), mv.to(DEV)
+    lt_dev = ops.mask_lengths(mt, torch.zeros(B, dtype=torch.int32, device=DEV))
+    lv_dev = ops.mask_lengths(mv, torch.zeros(B, dtype=torch.int32, device=DEV))
+    assert lt_dev.tolist() == lens_t.tolist() and lv_dev.tolist() == lens_v.tolist()
+    tq, vq = bool(pm & 3), bool(pm & 12)
+    has_t, has_v = qt is not None, qv is not None
+    vt = (torch.arange(Lt)[None] < lens_t[:, None]).reshape(-1).to(DEV)   # rows below the length (holes included)
+    vv = (torch.arange(Lv)[None] < lens_v[:, None]).reshape(-1).to(DEV)
+    # samples with no valid position are computed in full: treat all their rows as valid
+    vt = vt | (lens_t == 0).repeat_interleave(Lt).to(DEV)
+    vv = vv | (lens_v == 0).repeat_interleave(Lv).to(DEV)
+    dct = rnd(B * Lt, A, dtype=dtype, seed=7) * vt[:, None] if tq else None
+    dcv = rnd(B * Lv, A, dtype=dtype, seed=8) * vv[:, None] if vq else None
+    res = {}
+    for name, (l_t, l_v) in dict(full=(None, None), skip=(lt_dev, lv_dev)).items():
+        ct = torch.full((B * Lt, A), 3.0, dtype=dtype, device=DEV) if tq else None
+        cv = torch.full((B * Lv, A), 3.0, dtype=dtype, device=DEV) if vq else None
+        lt, lv = torch.zeros(B, heads, Lt, device=DEV), torch.zeros(B, heads, Lv, device=DEV)
+        args = (qt, qv, mt if has_t else None, mv if has_v else None)
+        ops.attention_fwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, _lib.ATTN_MMA, len_t=l_t, len_v=l_v)
+        dqt = torch.full_like(qt, 7.0) if has_t else None
+        dqv = torch.full_like(qv, 7.0) if has_v else None
+        ops.attention_bwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, _lib.ATTN_MMA, dctx_t=dct, dctx_v=dcv,
+                          dqkv_t=dqt, dqkv_v=dqv, len_t=l_t, len_v=l_v)
+        res[name] = (ct, cv, dqt, dqv)
+    for i, valid in ((0, vt), (1, vv)):
+        full, skip = res["full"][i], res["skip"][i]
+        if full is not None:
+            assert rel(skip[valid].float(), full[valid].float()) < 2e-3
+            assert bool((skip[~valid] == 0).all()), "padded query rows must be written as zeros"
+        fullg, skipg = res["full"][2 + i], res["skip"][2 + i]
+        if fullg is not None:
+            assert torch.isfinite(skipg.float()).all()
+            assert rel(skipg[valid].float(), fullg[valid].float()) < 5e-3
+            if bool((~valid).any()):
+                assert float(skipg[~valid].float().abs().max()) == 0.0
+
+
 def test_attention_simt_fp32_exact():
     B, Lt, Lv, heads, d, pm = 2, 12, 9, 2, 32, 15
     qt, qv, mt, mv, A = _attn_inputs(B, Lt, Lv, heads, d, pm, torch.float32)

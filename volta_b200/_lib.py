@@ -36,7 +36,7 @@ class AttnArgs(C.Structure):
                 ("dctx_t", _vp), ("dctx_v", _vp), ("dqkv_t", _vp), ("dqkv_v", _vp),
                 ("B", _i32), ("Lt", _i32), ("Lv", _i32), ("heads", _i32), ("d", _i32), ("pair_mask", _i32),
                 ("dtype", _i32), ("scale", _f), ("dropout_p_t", _f), ("dropout_p_v", _f), ("seed", _u64),
-                ("offset", _u64), ("backend", _i32), ("reserved", _i32)]
+                ("offset", _u64), ("backend", _i32), ("reserved", _i32), ("len_t", _vp), ("len_v", _vp)]
 
 
 class CastItem(C.Structure):
@@ -72,6 +72,7 @@ SIGNATURES = {
     "vb_loss_finalize": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "vb_eltwise": (_i32, [_i32, _vp, _i32, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _f, _f, _u64, _u64, _vp]),
     "vb_colsum": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "vb_mask_lengths": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "vb_compact_plan": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vb_compact_gather": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),
     "vb_compact_scatter": (_i32, [_vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),

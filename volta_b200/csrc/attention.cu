@@ -32,7 +32,22 @@ struct P {
   uint64_t seed;             // seed + offset
   const uint64_t* seed_ptr;  // see vb_set_seed_pointer
   int ngroups;               // MMA back-end: independent (query set, key set) groups per (sample, head)
+  const int32_t* len[2];     // optional [B] per stream: 1 + index of the last position whose mask is set (vb_mask_lengths)
 };
+
+// Effective length of stream s in sample b: positions at or beyond it are padding for every head and every layer - as
+// keys they have softmax weight exactly 0 (additive -10000, encoders.py:983-991; exp underflows to 0 in fp32 and bf16),
+// as queries nothing downstream reads them (SURVEY.md 8a' item 3) - so whole 16-row tiles beyond it are neither loaded
+// nor multiplied; their outputs are written as zeros.  Masked positions BELOW the length (arbitrary masks) take the
+// ordinary path.  A sample with no valid position at all (len 0) is computed in full, like the reference does.
+__device__ __forceinline__ int eff_len(const P& p, int s, int b) {
+  int L = p.L[s];
+  if (p.len[s] != nullptr) {
+    const int v = p.len[s][b];
+    if (v > 0 && v < L) L = v;
+  }
+  return L;
+}
 
 __host__ __device__ __forceinline__ bool pair_on(int pair_mask, int qs, int ks) { return (pair_mask >> (qs * 2 + ks)) & 1; }
 
@@ -420,14 +435,15 @@ mma_fwd_kernel(P p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gq = lane >> 2, tq = lane & 3;
 
+  const int Le[2] = {p.L[0] ? eff_len(p, 0, b) : 0, p.L[1] ? eff_len(p, 1, b) : 0};
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const bf16* base = reinterpret_cast<const bf16*>(p.qkv[s]) + (int64_t)b * p.L[s] * p.ld[s] + h * D;
-    if (g.qrows[s]) load_seg<D>(Qs + (s ? g.qrows[0] : 0) * TL::PITCH, base, p.ld[s], p.L[s], g.qrows[s]);
+    if (g.qrows[s]) load_seg<D>(Qs + (s ? g.qrows[0] : 0) * TL::PITCH, base, p.ld[s], Le[s], g.qrows[s]);
     if (g.krows[s]) {
       const int off = s ? g.krows[0] : 0;
-      load_seg<D>(Ks + off * TL::PITCH, base + p.A, p.ld[s], p.L[s], g.krows[s]);
-      load_seg<D>(Vs + off * TL::PITCH, base + 2 * p.A, p.ld[s], p.L[s], g.krows[s]);
+      load_seg<D>(Ks + off * TL::PITCH, base + p.A, p.ld[s], Le[s], g.krows[s]);
+      load_seg<D>(Vs + off * TL::PITCH, base + 2 * p.A, p.ld[s], Le[s], g.krows[s]);
       load_madd(madd + off, p.mask[s] + (int64_t)b * p.L[s], p.L[s], g.krows[s]);
     }
   }
@@ -438,12 +454,19 @@ mma_fwd_kernel(P p) {
   const int qt = warp;
   const int qs = (qt * 16 < g.qrows[0]) ? 0 : 1;
   const int jq0 = qt * 16 - (qs ? g.qrows[0] : 0);  // first row of this tile inside its stream
+  if (jq0 >= Le[qs]) {
+    // padding-only query tile: its Q rows were zero-filled by the loader - they are the zero context rows to store
+    const bf16* zrows = Qs + qt * 16 * TL::PITCH;
+    store_rows16<D>(zrows, reinterpret_cast<bf16*>(p.ctx[qs]) + (int64_t)b * p.L[qs] * p.ld_ctx[qs] + h * D, p.ld_ctx[qs], jq0, p.L[qs]);
+    if (lane < 16 && jq0 + lane < p.L[qs]) p.lse[qs][((int64_t)b * p.heads + h) * p.L[qs] + jq0 + lane] = 0.f;
+    return;
+  }
   // key n-tiles (8 keys) this query stream attends: enabled key streams, rows below their length
   uint32_t ntmask = 0;
 #pragma unroll
   for (int ks = 0; ks < 2; ++ks)
     if (g.krows[ks] && pair_on(p.pair_mask, qs, ks))
-      ntmask |= ((1u << ((p.L[ks] + 7) >> 3)) - 1u) << ((ks ? g.krows[0] : 0) >> 3);
+      ntmask |= ((1u << ((Le[ks] + 7) >> 3)) - 1u) << ((ks ? g.krows[0] : 0) >> 3);
   const float sc2 = p.scale * 1.4426950408889634f;
 
   float s[2 * NKB][4];
@@ -496,8 +519,8 @@ mma_fwd_kernel(P p) {
   for (int r = 0; r < 2; ++r) {
     sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
     sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
-    osc[r] = p.keep_scale[qs] / sum[r];
     const int j = jq0 + gq + r * 8;
+    osc[r] = j < Le[qs] ? p.keep_scale[qs] / sum[r] : 0.f;   // padding rows of a partly valid tile: zeros, like whole padding tiles
     if (tq == 0 && j < p.L[qs]) p.lse[qs][((int64_t)b * p.heads + h) * p.L[qs] + j] = (mx[r] + __log2f(sum[r])) * 0.6931471805599453f;
   }
   const uint32_t thresh = p.thresh[qs];
@@ -577,14 +600,15 @@ mma_bwd_kernel(P p) {
   const int gq = lane >> 2, tq = lane & 3;
   const int Ltot = p.L[0] + p.L[1];
 
+  const int Le[2] = {p.L[0] ? eff_len(p, 0, b) : 0, p.L[1] ? eff_len(p, 1, b) : 0};
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const bf16* base = reinterpret_cast<const bf16*>(p.qkv[s]) + (int64_t)b * p.L[s] * p.ld[s] + h * D;
-    if (g.qrows[s]) load_seg<D>(Qs + (s ? g.qrows[0] : 0) * TL::PITCH, base, p.ld[s], p.L[s], g.qrows[s]);
+    if (g.qrows[s]) load_seg<D>(Qs + (s ? g.qrows[0] : 0) * TL::PITCH, base, p.ld[s], Le[s], g.qrows[s]);
     if (g.krows[s]) {
       const int off = s ? g.krows[0] : 0;
-      load_seg<D>(Ks + off * TL::PITCH, base + p.A, p.ld[s], p.L[s], g.krows[s]);
-      load_seg<D>(Vs + off * TL::PITCH, base + 2 * p.A, p.ld[s], p.L[s], g.krows[s]);
+      load_seg<D>(Ks + off * TL::PITCH, base + p.A, p.ld[s], Le[s], g.krows[s]);
+      load_seg<D>(Vs + off * TL::PITCH, base + 2 * p.A, p.ld[s], Le[s], g.krows[s]);
       load_madd(madd + off, p.mask[s] + (int64_t)b * p.L[s], p.L[s], g.krows[s]);
     }
   }
@@ -594,10 +618,10 @@ mma_bwd_kernel(P p) {
     if (!g.qrows[s]) continue;
     const int off = s ? g.qrows[0] : 0;
     const int64_t head0 = (int64_t)b * p.L[s] * p.ld_ctx[s] + h * D;
-    load_seg<D>(dOs + off * TL::PITCH, reinterpret_cast<const bf16*>(p.dctx[s]) + head0, p.ld_ctx[s], p.L[s], g.qrows[s]);
-    load_seg<D>(Os + off * TL::PITCH, reinterpret_cast<const bf16*>(p.ctx[s]) + head0, p.ld_ctx[s], p.L[s], g.qrows[s]);
+    load_seg<D>(dOs + off * TL::PITCH, reinterpret_cast<const bf16*>(p.dctx[s]) + head0, p.ld_ctx[s], Le[s], g.qrows[s]);
+    load_seg<D>(Os + off * TL::PITCH, reinterpret_cast<const bf16*>(p.ctx[s]) + head0, p.ld_ctx[s], Le[s], g.qrows[s]);
     for (int r = threadIdx.x; r < g.qrows[s]; r += blockDim.x) {
-      lse2[off + r] = r < p.L[s] ? p.lse[s][((int64_t)b * p.heads + h) * p.L[s] + r] * 1.4426950408889634f : INFINITY;
+      lse2[off + r] = r < Le[s] ? p.lse[s][((int64_t)b * p.heads + h) * p.L[s] + r] * 1.4426950408889634f : INFINITY;
       rowt[off + r] = attn_rowterm(seed_eff, ((uint32_t)b * p.heads + h) * Ltot + (s ? p.L[0] : 0) + r);
     }
   }
@@ -638,10 +662,12 @@ mma_bwd_kernel(P p) {
     const int hshl = (gq & 1) ? 0 : 16;  // keys jk0+gq and jk0+gq+8 have the parity of gq: which half of the pair hash
     const uint32_t thr_hi[2] = {p.thresh[0] << 16, p.thresh[1] << 16};
     const float kscs[2] = {p.keep_scale[0], p.keep_scale[1]};
+    const bool k_live = jk0 < Le[ks];   // a padding-only key tile gets dK = dV = 0 (stored below)
 #pragma unroll 1
-    for (int qb = 0; qb * 16 < g.RQ; ++qb) {
+    for (int qb = 0; k_live && qb * 16 < g.RQ; ++qb) {
       const int qs = (qb * 16 < g.qrows[0]) ? 0 : 1;
       if (!pair_on(p.pair_mask, qs, ks)) continue;
+      if (qb * 16 - (qs ? g.qrows[0] : 0) >= Le[qs]) continue;   // padding-only query tile: P = 0, nothing to add
       const uint32_t thr = qs ? thr_hi[1] : thr_hi[0];   // (r16 < thresh)  <=>  ((h << hshl) < thresh << 16)
       const float ksc = qs ? kscs[1] : kscs[0];
       float st[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dpt[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -719,8 +745,11 @@ mma_bwd_kernel(P p) {
     float dq[D / 8][4];
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) { dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f; }
-    for (int kt = 0; kt * 16 < g.RK; ++kt) {
-      if (!pair_on(p.pair_mask, qs, (kt * 16 < g.krows[0]) ? 0 : 1)) continue;
+    const bool q_live = jq0 < Le[qs];
+    for (int kt = 0; q_live && kt * 16 < g.RK; ++kt) {
+      const int ks = (kt * 16 < g.krows[0]) ? 0 : 1;
+      if (!pair_on(p.pair_mask, qs, ks)) continue;
+      if (kt * 16 - (ks ? g.krows[0] : 0) >= Le[ks]) continue;   // that dS^T tile was never written
       uint32_t a[4];
       TL::load_at(dSt, SP, qt * 16, kt * 16, a);
 #pragma unroll
@@ -795,6 +824,8 @@ static int fill(const vb_attn_args& a, P& p, bool bwd) {
   p.keep_scale[1] = 1.f / (1.f - a.dropout_p_v);
   p.seed = a.seed + a.offset;
   p.seed_ptr = seed_pointer();
+  p.len[0] = p.qkv[0] ? a.len_t : nullptr;
+  p.len[1] = p.qkv[1] ? a.len_v : nullptr;
   return 0;
 }
 
@@ -900,7 +931,30 @@ static int run(const vb_attn_args& a, cudaStream_t st, bool bwd) {
 }  // namespace attn
 }  // namespace vb
 
+namespace vb {
+namespace attn {
+// len[b] = 1 + index of the last position of sample b whose mask is set (0 if none): one warp per sample
+__global__ void __launch_bounds__(256)
+mask_len_kernel(const int32_t* __restrict__ mask, int B, int L, int32_t* __restrict__ len) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= B) return;
+  int last = 0;
+  for (int j = lane; j < L; j += 32)
+    if (mask[(int64_t)b * L + j] != 0) last = j + 1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  if (lane == 0) len[b] = last;
+}
+}  // namespace attn
+}  // namespace vb
+
 extern "C" {
+int vb_mask_lengths(const int32_t* mask, int32_t B, int32_t L, int32_t* len, void* stream) {
+  VB_REQUIRE(mask && len && B > 0 && L > 0, VB_ERR_ARG, "mask_lengths: bad arguments");
+  vb::attn::mask_len_kernel<<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(mask, B, L, len);
+  return vb::check_launch("mask_len_kernel");
+}
 int vb_attention_fwd(const vb_attn_args* a, void* stream) {
   VB_REQUIRE(a != nullptr, VB_ERR_ARG, "attention_fwd: null args");
   return vb::attn::run(*a, (cudaStream_t)stream, false);

@@ -138,6 +138,8 @@ def model_store(model):
 # ====================================================================================================
 # Masked-LM decoder on the labelled rows only (heads_fwd); VOLTA_B200_MLM_COMPACT=0 restores the all-positions decoder.
 MLM_COMPACT = os.environ.get("VOLTA_B200_MLM_COMPACT", "1") != "0"
+# Attention skips 16-row tiles of trailing padding (vb_attn_args::len_*); VOLTA_B200_SKIP_PADDING=0 computes them.
+SKIP_PADDING = os.environ.get("VOLTA_B200_SKIP_PADDING", "1") != "0"
 _SIDE_STREAMS = {}
 _SIDE_STREAMS_ON = os.environ.get("VOLTA_B200_SIDE_STREAM", "1") != "0"
 
@@ -363,7 +365,8 @@ def attention_fwd(rt, layer, x, masks):
     for pm, qt, qv, h_, d_ in calls:
         ops.attention_fwd(qt, qv, masks[0] if qt is not None else None, masks[1] if qv is not None else None,
                           ctx.get("t") if qt is not None else None, ctx.get("v") if qv is not None else None,
-                          lse_t, lse_v, rt.B, rt.T, rt.V, h_, d_, pm, p_t, p_v, seed, rt.attn_backend)
+                          lse_t, lse_v, rt.B, rt.T, rt.V, h_, d_, pm, p_t, p_v, seed, rt.attn_backend,
+                          len_t=getattr(rt, "lens", (None, None))[0], len_v=getattr(rt, "lens", (None, None))[1])
         _count()
     y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1]) if (sa.has_text and sa.has_vision) else None
     saved_out = {}
@@ -380,7 +383,7 @@ def attention_fwd(rt, layer, x, masks):
         if sa.has_vision:
             saved_out["v"] = out_block_fwd(rt, ctx["v"], x.v, so.v_dense, so.v_LayerNorm, rt.p(so.v_dropout.p), y.v)
     saved = dict(x=x, qkv=qkv, ctx=ctx, lse=(lse_t, lse_v), calls=calls, seed=seed, p=(p_t, p_v), out=saved_out,
-                 joint=joint, split=split, masks=masks)
+                 joint=joint, split=split, masks=masks, lens=getattr(rt, "lens", (None, None)))
     return y, saved
 
 
@@ -413,7 +416,8 @@ def attention_bwd(rt, layer, dy, s):
                           ctx.get("t") if qt is not None else None, ctx.get("v") if qv is not None else None,
                           lse_t, lse_v, rt.B, rt.T, rt.V, h_, d_, pm, s["p"][0], s["p"][1], s["seed"], rt.attn_backend,
                           dctx_t=dctx.get("t") if qt is not None else None, dctx_v=dctx.get("v") if qv is not None else None,
-                          dqkv_t=dqkv.get("t") if qt is not None else None, dqkv_v=dqkv.get("v") if qv is not None else None)
+                          dqkv_t=dqkv.get("t") if qt is not None else None, dqkv_v=dqkv.get("v") if qv is not None else None,
+                          len_t=s["lens"][0], len_v=s["lens"][1])
         _count()
     # dx = dqkv . Wqkv + du   (the residual gradient is folded into the dgrad epilogue)
     if s["joint"] or s["split"]:
@@ -728,6 +732,11 @@ def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
     cfg = bert.config
     x, s_emb = embeddings_fwd(rt, bert, ids, feat, loc, seg)
     masks = (_int_mask(rt, mask_t, rt.B, rt.T), _int_mask(rt, mask_v, rt.B, rt.V))
+    rt.lens = (None, None)
+    if SKIP_PADDING:
+        # per-sample valid lengths, once per forward: the attention kernels skip whole tiles of trailing padding
+        rt.lens = tuple(ops.mask_lengths(m, rt.empty(rt.B, dtype=torch.int32)) for m in masks)
+        _count(2)
     tape, layers = [], []
     for n, layer in enumerate(bert.encoder.layer):
         if bert.encoder.num2type[n] == "attn":

@@ -141,7 +141,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, out_scale=1.0, dx
 
 # --------------------------------------------------------------------------- attention
 def _attn_args(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, Lv, heads, d, pair_mask, p_t, p_v,
-               seed, backend, dctx_t=None, dctx_v=None, dqkv_t=None, dqkv_v=None):
+               seed, backend, dctx_t=None, dctx_v=None, dqkv_t=None, dqkv_v=None, len_t=None, len_v=None):
     a = _lib.AttnArgs()
     ref = qkv_t if qkv_t is not None else qkv_v
     require_cuda(ref)
@@ -160,7 +160,17 @@ def _attn_args(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, 
     a.dtype = dt(ref)
     a.scale = 1.0 / (d ** 0.5)
     a.dropout_p_t, a.dropout_p_v, a.seed, a.offset, a.backend = float(p_t), float(p_v), int(seed), 0, backend
+    for ln in (len_t, len_v):
+        assert ln is None or (ln.dtype == torch.int32 and ln.numel() >= B)
+    a.len_t, a.len_v = _ptr(len_t if qkv_t is not None else None), _ptr(len_v if qkv_v is not None else None)
     return a
+
+
+def mask_lengths(mask, out):
+    """out[b] = 1 + index of the last set position of mask[b, :] (int32 [B, L]); 0 for an all-zero row."""
+    assert mask.dtype == torch.int32 and mask.dim() == 2 and mask.is_contiguous() and out.dtype == torch.int32
+    _lib.call("vb_mask_lengths", mask.data_ptr(), mask.shape[0], mask.shape[1], out.data_ptr(), _stream())
+    return out
 
 
 def attention_fwd(*args, **kw):
