@@ -145,14 +145,27 @@ int vb_gemm_backend(const vb_gemm_args* args);
  *   Optional fused extras for the residual blocks:
  *     dx_drop  = dx * dropmask / (1-p)  (mask regenerated from seed/offset, index = row*H+col)
  *     dbias   += column sums of (dx_drop if given else dx)
+ *
+ * seqs (optional, NULL = every row is computed): which rows are TRAILING PADDING of their sample.  Rows [0, rows_a)
+ *   are samples of L_a rows each with valid length len_a[sample] (int32, device; from vb_mask_lengths), rows
+ *   [rows_a, rows) samples of L_b rows with len_b (NULL = none) - the text rows and the vision rows of a joint buffer.
+ *   A row at or beyond its sample's length (length 0 = sample computed in full) is written as zeros (y / dx / dx_drop;
+ *   mean = rstd = 0) and neither read nor accumulated: the reference computes such rows but nothing reads them
+ *   (SURVEY.md 8a' item 3) and their gradient is exactly zero, so every valid row and every parameter gradient is
+ *   unchanged.  Ignored when accum != 0.
  */
+typedef struct vb_row_seqs {
+  const int32_t* len_a; int32_t L_a; int64_t rows_a;
+  const int32_t* len_b; int32_t L_b;
+} vb_row_seqs;
+
 int vb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                     int64_t rows, int32_t H, float eps, float out_scale, int32_t accum, int32_t dtype,
-                     void* stream);
+                     int64_t rows, int32_t H, float eps, float out_scale, int32_t accum, const vb_row_seqs* seqs,
+                     int32_t dtype, void* stream);
 int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                      void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t H, float out_scale,
                      void* dx_drop, float dropout_p, uint64_t seed, uint64_t offset, float* dbias,
-                     int32_t dtype, void* stream);
+                     const vb_row_seqs* seqs, int32_t dtype, void* stream);
 
 /* ---- gated attention --------------------------------------------------
  * Replaces BertGatedSelfAttention.forward after the Q/K/V projections

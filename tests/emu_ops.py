@@ -85,7 +85,35 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bia
     return out
 
 
-def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=1.0, accum=False):
+def _dead_rows(seqs, rows):
+    """Rows that are trailing padding of their sample (vb_row_seqs); None = no row is skipped."""
+    if seqs is None:
+        return None
+    len_a, L_a, rows_a, len_b, L_b = seqs
+    parts = []
+    for ln, L, n in ((len_a, L_a, rows_a), (len_b, L_b, rows - rows_a)):
+        if n == 0:
+            continue
+        if ln is None:
+            parts.append(torch.zeros(n, dtype=torch.bool))
+            continue
+        j = torch.arange(n) % L
+        v = ln[:n // L].repeat_interleave(L)
+        parts.append((v > 0) & (j >= v))
+    return torch.cat(parts)
+
+
+def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=1.0, accum=False, seqs=None):
+    dead = None if accum else _dead_rows(seqs, x.shape[0])
+    if dead is not None:
+        y2, m2, r2 = torch.empty_like(y), torch.empty(x.shape[0]), torch.empty(x.shape[0])
+        layernorm_fwd(x, gamma, beta, y2, m2, r2, eps, out_scale, accum)
+        y.copy_(torch.where(dead[:, None], torch.zeros_like(y2), y2))
+        if mean is not None:
+            mean.copy_(torch.where(dead, torch.zeros_like(m2), m2))
+        if rstd is not None:
+            rstd.copy_(torch.where(dead, torch.zeros_like(r2), r2))
+        return y
     xf = x.float()
     mu = xf.mean(-1, keepdim=True)
     var = (xf - mu).pow(2).mean(-1, keepdim=True)
@@ -102,8 +130,12 @@ def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, out_scale=1.0, dx_drop=None, dropout_p=0.0, seed=0,
-                  offset=0, dbias=None):
+                  offset=0, dbias=None, seqs=None):
     assert dropout_p == 0.0
+    dead = _dead_rows(seqs, x.shape[0])
+    if dead is not None:   # skipped rows: no contribution, zero dx
+        dy = torch.where(dead[:, None], torch.zeros_like(dy), dy)
+        x = torch.where(dead[:, None], torch.zeros_like(x), x)
     dyo = dy.float() * out_scale
     xh = (x.float() - mean[:, None]) * rstd[:, None]
     g = dyo * gamma

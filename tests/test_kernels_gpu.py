@@ -284,6 +284,40 @@ def test_layernorm_fwd_bwd(H, dtype):
         assert rel(got, ref) < max(tol, 1e-4)
 
 
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+def test_layernorm_skips_trailing_padding_rows(dropout):
+    """vb_row_seqs: rows at or beyond their sample's valid length are written as zeros and contribute nothing; every
+    other row and every column sum is bit-identical to the call without the skip on inputs whose dy is zero there."""
+    B, T, V, H = 9, 36, 37, 768
+    rows = B * (T + V)
+    g = torch.Generator().manual_seed(1)
+    len_t = torch.randint(0, T + 1, (B,), generator=g, dtype=torch.int32)
+    len_v = torch.randint(0, V + 1, (B,), generator=g, dtype=torch.int32)
+    len_t[0], len_v[1] = 0, 0                      # length 0 = the sample is computed in full
+    live_t = (torch.arange(T)[None] < len_t[:, None]) | (len_t[:, None] == 0)
+    live_v = (torch.arange(V)[None] < len_v[:, None]) | (len_v[:, None] == 0)
+    live = torch.cat([live_t.reshape(-1), live_v.reshape(-1)]).to(DEV)
+    x = rnd(rows, H, scale=2.0)
+    dy = rnd(rows, H, seed=1) * live[:, None]      # gradients of padded rows are exactly zero in the model
+    gamma, beta = 1 + rnd(H, dtype=torch.float32, scale=0.1), rnd(H, dtype=torch.float32, scale=0.1)
+    seqs = (len_t.to(DEV), T, B * T, len_v.to(DEV), V)
+    out = {}
+    for name, sq in dict(full=None, skip=seqs).items():
+        y = torch.full_like(x, 5.0)
+        mean, rstd = torch.zeros(rows, device=DEV), torch.zeros(rows, device=DEV)
+        ops.layernorm_fwd(x, gamma, beta, y, mean, rstd, seqs=sq)
+        dx, dxd = torch.full_like(x, 5.0), torch.full_like(x, 5.0)
+        dg, db, dbias = torch.zeros(H, device=DEV), torch.zeros(H, device=DEV), torch.zeros(H, device=DEV)
+        ops.layernorm_bwd(dy, x, mean, rstd, gamma, dx, dg, db, dx_drop=dxd if dropout else None, dropout_p=dropout, seed=3,
+                          dbias=dbias, seqs=sq)
+        out[name] = (y, dx, dxd, dg, db, dbias)
+    for i in range(3 if dropout else 2):
+        assert torch.equal(out["skip"][i][live], out["full"][i][live])
+        assert bool((out["skip"][i][~live] == 0).all())
+    for i in (3, 4, 5):
+        assert rel(out["skip"][i], out["full"][i]) < 1e-5   # fp32 atomics: order only
+
+
 def test_layernorm_scale_accumulate():
     rows, H = 300, 768
     a, b = rnd(rows, H), rnd(rows, H, seed=1)

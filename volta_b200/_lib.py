@@ -39,6 +39,10 @@ class AttnArgs(C.Structure):
                 ("offset", _u64), ("backend", _i32), ("reserved", _i32), ("len_t", _vp), ("len_v", _vp)]
 
 
+class RowSeqs(C.Structure):
+    _fields_ = [("len_a", _vp), ("L_a", _i32), ("rows_a", _i64), ("len_b", _vp), ("L_b", _i32)]
+
+
 class CastItem(C.Structure):
     _fields_ = [("src", _vp), ("dst", _vp), ("n", _i64)]
 
@@ -54,8 +58,8 @@ SIGNATURES = {
     "vb_gemm": (_i32, [C.POINTER(GemmArgs), _vp]),
     "vb_gemm_backend": (_i32, [C.POINTER(GemmArgs)]),
     "vb_gemm_bench": (_i32, [C.POINTER(GemmArgs), _vp, _i32, C.POINTER(C.c_float)]),
-    "vb_layernorm_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _i32, _i32, _vp]),
-    "vb_layernorm_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _vp, _f, _u64, _u64, _vp, _i32, _vp]),
+    "vb_layernorm_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _i32, _vp, _i32, _vp]),
+    "vb_layernorm_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _vp, _f, _u64, _u64, _vp, _vp, _i32, _vp]),
     "vb_attention_fwd": (_i32, [C.POINTER(AttnArgs), _vp]),
     "vb_attention_bwd": (_i32, [C.POINTER(AttnArgs), _vp]),
     "vb_embed_gather_fwd": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i32, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),

@@ -11,15 +11,50 @@ namespace ln {
 
 constexpr int WARPS = 8;
 
+// vb_row_seqs by value: which rows are trailing padding of their sample.  Such rows are zeros on output and contribute
+// nothing: as attention keys they are masked (weight exactly 0), as queries the attention kernel skips them
+// (vb_attn_args::len_*), their gradients are exactly zero, and no loss reads them - so every VALID row is bit-identical
+// with and without the skip, and the kernel saves the read of a third of the rows.
+struct Seqs {
+  const int32_t* len_a; int32_t L_a; int64_t rows_a;
+  const int32_t* len_b; int32_t L_b;
+};
+__device__ __forceinline__ bool row_dead(const Seqs& q, int64_t row) {
+  if (q.len_a == nullptr) return false;
+  const int32_t* len = q.len_a;
+  int L = q.L_a;
+  int64_t r = row;
+  if (row >= q.rows_a) {
+    if (q.len_b == nullptr) return false;
+    len = q.len_b; L = q.L_b; r = row - q.rows_a;
+  }
+  const int64_t b = r / L;
+  const int v = len[b];
+  return v > 0 && (int)(r - b * L) >= v;
+}
+
 template <typename T, int NV>
 __global__ void __launch_bounds__(WARPS * 32)
 ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int H,
-              float eps, float out_scale, int accum) {
+              float eps, float out_scale, int accum, Seqs seqs) {
   pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
   if (row >= rows) return;
+  if (!accum && row_dead(seqs, row)) {   // trailing padding of its sample: zeros, nothing read
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = 0.f;
+      if (rstd_out) rstd_out[row] = 0.f;
+    }
+    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (lane + 32 * i) * 8;
+      if (c < H) Vec8<T>::store(y + row * H + c, z);
+    }
+    return;
+  }
   const T* xr = x + row * H;
   float v[NV][8];
   float s = 0.f;
@@ -80,7 +115,7 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
               const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int H, float out_scale,
               T* __restrict__ dx_drop, uint32_t drop_thresh, float drop_scale, uint64_t seed_in, uint64_t offset,
-              float* __restrict__ dbias, const uint64_t* __restrict__ seed_ptr, int early_fetch) {
+              float* __restrict__ dbias, const uint64_t* __restrict__ seed_ptr, int early_fetch, Seqs seqs) {
   pdl_enter();
   const uint64_t seed = effective_seed(seed_in, seed_ptr);
   extern __shared__ __align__(16) float red[];  // [3 or 2][WARPS][H] partial sums, then gamma [H]
@@ -110,7 +145,10 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
   using Raw = typename Vec8<T>::Raw;
   Raw nd[NV], nx[NV];
   float nmu = 0.f, nrs = 0.f;
+  bool ndead = false;
   auto fetch = [&](int64_t r) {
+    ndead = row_dead(seqs, r);
+    if (ndead) return;
     nmu = mean[r]; nrs = rstd[r];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -124,6 +162,21 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
   int64_t row = warp_global;
   if (row < rows) fetch(row);
   for (; row < rows; row += total_warps) {
+    if (ndead) {   // trailing padding: dy is exactly zero there, so are dx and every partial sum
+      if (row + total_warps < rows) fetch(row + total_warps);
+      const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = (lane + 32 * i) * 8;
+        if (c < H) {
+          Vec8<T>::store(dx + row * H + c, z);
+          if constexpr (EXTRA) {
+            if (dx_drop != nullptr) Vec8<T>::store(dx_drop + row * H + c, z);
+          }
+        }
+      }
+      continue;
+    }
     const float mu = nmu, rs = nrs;
     float xh[NV][8], g[NV][8];
     float c1 = 0.f, c2 = 0.f;
@@ -210,12 +263,12 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
 
 template <typename T>
 static int fwd_dispatch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                        int64_t rows, int H, float eps, float out_scale, int accum, cudaStream_t st) {
+                        int64_t rows, int H, float eps, float out_scale, int accum, Seqs seqs, cudaStream_t st) {
   const int nv = (H + 255) / 256;
   const unsigned grid = (unsigned)ceil_div(rows, WARPS);
 #define VB_LN_FWD(NV_)                                                                                             \
   launch_pdl(ln_fwd_kernel<T, NV_>, dim3(grid), dim3(WARPS * 32), 0, st, (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, H, \
-             eps, out_scale, accum)
+             eps, out_scale, accum, seqs)
   switch (nv) {
     case 1: VB_LN_FWD(1); break;
     case 2: VB_LN_FWD(2); break;
@@ -232,7 +285,7 @@ static int fwd_dispatch(const void* x, const float* gamma, const float* beta, vo
 template <typename T>
 static int bwd_dispatch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                         void* dx, float* dgamma, float* dbeta, int64_t rows, int H, float out_scale, void* dx_drop,
-                        float p, uint64_t seed, uint64_t offset, float* dbias, cudaStream_t st) {
+                        float p, uint64_t seed, uint64_t offset, float* dbias, Seqs seqs, cudaStream_t st) {
   const int nv = (H + 255) / 256;
   const bool extra = (dx_drop != nullptr) || (dbias != nullptr);
   static int sms = 0;
@@ -250,7 +303,7 @@ static int bwd_dispatch(const void* dy, const void* x, const float* mean, const 
       cudaFuncSetAttribute(ln_bwd_kernel<T, NV_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     launch_pdl(ln_bwd_kernel<T, NV_, EX_>, dim3((unsigned)grid), dim3(WARPS * 32), smem, st,                    \
         (const T*)dy, (const T*)x, mean, rstd, gamma, (T*)dx, dgamma, dbeta, rows, H, out_scale, (T*)dx_drop,    \
-        thresh, scale, seed, offset, dbias, seed_pointer(), early);                                                                     \
+        thresh, scale, seed, offset, dbias, seed_pointer(), early, seqs);                                                                     \
   } while (0)
 #define VB_LN_BWD2(NV_) do { if (extra) VB_LN_BWD(NV_, true); else VB_LN_BWD(NV_, false); } while (0)
   switch (nv) {
@@ -267,27 +320,38 @@ static int bwd_dispatch(const void* dy, const void* x, const float* mean, const 
   return check_launch("ln_bwd_kernel");
 }
 
+static Seqs make_seqs(const vb_row_seqs* q) {
+  Seqs s = {nullptr, 1, 0, nullptr, 1};
+  if (q != nullptr && q->len_a != nullptr && q->L_a > 0) {
+    s.len_a = q->len_a; s.L_a = q->L_a; s.rows_a = q->rows_a;
+    if (q->len_b != nullptr && q->L_b > 0) { s.len_b = q->len_b; s.L_b = q->L_b; }
+  }
+  return s;
+}
+
 }  // namespace ln
 }  // namespace vb
 
 extern "C" {
 
 int vb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                     int64_t rows, int32_t H, float eps, float out_scale, int32_t accum, int32_t dtype, void* stream) {
+                     int64_t rows, int32_t H, float eps, float out_scale, int32_t accum, const vb_row_seqs* seqs, int32_t dtype,
+                     void* stream) {
   VB_REQUIRE(x && gamma && beta && y, VB_ERR_ARG, "layernorm_fwd: null pointer");
   VB_REQUIRE(rows >= 0 && H > 0 && H % 8 == 0, VB_ERR_ARG, "layernorm_fwd: H=%d must be a positive multiple of 8", H);
   VB_REQUIRE(vb::aligned16(x) && vb::aligned16(y) && vb::aligned16(gamma) && vb::aligned16(beta), VB_ERR_ARG,
              "layernorm_fwd: pointers must be 16-byte aligned");
   if (rows == 0) return 0;
   if (dtype == VB_BF16)
-    return vb::ln::fwd_dispatch<vb::bf16>(x, gamma, beta, y, mean, rstd, rows, H, eps, out_scale, accum, (cudaStream_t)stream);
+    return vb::ln::fwd_dispatch<vb::bf16>(x, gamma, beta, y, mean, rstd, rows, H, eps, out_scale, accum, vb::ln::make_seqs(seqs), (cudaStream_t)stream);
   VB_REQUIRE(dtype == VB_F32, VB_ERR_ARG, "layernorm_fwd: bad dtype %d", dtype);
-  return vb::ln::fwd_dispatch<float>(x, gamma, beta, y, mean, rstd, rows, H, eps, out_scale, accum, (cudaStream_t)stream);
+  return vb::ln::fwd_dispatch<float>(x, gamma, beta, y, mean, rstd, rows, H, eps, out_scale, accum, vb::ln::make_seqs(seqs), (cudaStream_t)stream);
 }
 
 int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                      float* dgamma, float* dbeta, int64_t rows, int32_t H, float out_scale, void* dx_drop,
-                     float dropout_p, uint64_t seed, uint64_t offset, float* dbias, int32_t dtype, void* stream) {
+                     float dropout_p, uint64_t seed, uint64_t offset, float* dbias, const vb_row_seqs* seqs, int32_t dtype,
+                     void* stream) {
   VB_REQUIRE(dy && x && mean && rstd && gamma && dx, VB_ERR_ARG, "layernorm_bwd: null pointer");
   VB_REQUIRE(rows >= 0 && H > 0 && H % 8 == 0, VB_ERR_ARG, "layernorm_bwd: H=%d must be a positive multiple of 8", H);
   VB_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, VB_ERR_ARG, "layernorm_bwd: dropout_p out of range");
@@ -297,10 +361,10 @@ int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const flo
   if (dropout_p == 0.f) dx_drop = nullptr;
   if (dtype == VB_BF16)
     return vb::ln::bwd_dispatch<vb::bf16>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, H, out_scale, dx_drop,
-                                          dropout_p, seed, offset, dbias, (cudaStream_t)stream);
+                                          dropout_p, seed, offset, dbias, vb::ln::make_seqs(seqs), (cudaStream_t)stream);
   VB_REQUIRE(dtype == VB_F32, VB_ERR_ARG, "layernorm_bwd: bad dtype %d", dtype);
   return vb::ln::bwd_dispatch<float>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, H, out_scale, dx_drop,
-                                     dropout_p, seed, offset, dbias, (cudaStream_t)stream);
+                                     dropout_p, seed, offset, dbias, vb::ln::make_seqs(seqs), (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -116,6 +116,17 @@ class Runtime:
         return self.store.g32(*ps)
 
     # kernels with launch accounting
+    def seqs(self, st):
+        """vb_row_seqs tuple for the rows of stream st ('t', 'v', 'all' = text rows then vision rows), or None."""
+        lens = getattr(self, "lens", (None, None))
+        if st is None or lens[0] is None or lens[1] is None or not SKIP_PADDING_LN:
+            return None
+        if st == "t":
+            return (lens[0], self.T, self.Mt, None, 0)
+        if st == "v":
+            return (lens[1], self.V, self.Mv, None, 0)
+        return (lens[0], self.T, self.Mt, lens[1], self.V)
+
     def gemm(self, a, b, out, **k):
         _count()
         k.setdefault("backend", self.gemm_backend)
@@ -140,6 +151,7 @@ def model_store(model):
 MLM_COMPACT = os.environ.get("VOLTA_B200_MLM_COMPACT", "1") != "0"
 # Attention skips 16-row tiles of trailing padding (vb_attn_args::len_*); VOLTA_B200_SKIP_PADDING=0 computes them.
 SKIP_PADDING = os.environ.get("VOLTA_B200_SKIP_PADDING", "1") != "0"
+SKIP_PADDING_LN = os.environ.get("VOLTA_B200_SKIP_PADDING_LN", "1") != "0"   # the residual-block LayerNorms skip them too
 _SIDE_STREAMS = {}
 _SIDE_STREAMS_ON = os.environ.get("VOLTA_B200_SIDE_STREAM", "1") != "0"
 
@@ -212,19 +224,19 @@ def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, 
     return dx_out
 
 
-def ln_fwd(rt, x, ln, y=None, out_scale=1.0, accum=False, save=True):
+def ln_fwd(rt, x, ln, y=None, out_scale=1.0, accum=False, save=True, seqs=None):
     y = rt.empty(*x.shape) if y is None else y
     mean = rt.empty(x.shape[0], dtype=torch.float32) if save else None
     rstd = rt.empty(x.shape[0], dtype=torch.float32) if save else None
-    ops.layernorm_fwd(x, rt.w32(ln.weight), rt.w32(ln.bias), y, mean, rstd, LN_EPS, out_scale, accum)
+    ops.layernorm_fwd(x, rt.w32(ln.weight), rt.w32(ln.bias), y, mean, rstd, LN_EPS, out_scale, accum, seqs=seqs)
     _count()
     return y, (mean, rstd)
 
 
-def ln_bwd(rt, dy, x, stats, ln, out_scale=1.0, dx=None, dx_drop=None, p=0.0, seed=0, dbias=None, offset=0):
+def ln_bwd(rt, dy, x, stats, ln, out_scale=1.0, dx=None, dx_drop=None, p=0.0, seed=0, dbias=None, offset=0, seqs=None):
     dx = rt.empty(*x.shape) if dx is None else dx
     ops.layernorm_bwd(dy, x, stats[0], stats[1], rt.w32(ln.weight), dx, rt.g32(ln.weight), rt.g32(ln.bias), out_scale,
-                      dx_drop, p, seed, offset, dbias)
+                      dx_drop, p, seed, offset, dbias, seqs=seqs)
     _count()
     return dx
 
@@ -238,19 +250,21 @@ def dropout_(rt, x, p, seed):
 
 
 # ---- residual block tail:  u = dropout(dense(h)) + x ;  y = LN(u) -------------------------------------
-def out_block_fwd(rt, h, x, dense, ln, p, y):
+def out_block_fwd(rt, h, x, dense, ln, p, y, st=None):
+    """st: which stream's rows these are ('t' / 'v' / 'all'): the LayerNorm skips their trailing-padding rows."""
     seed = rt.seed() if p > 0 else 0
     u = linear_fwd(rt, h, dense, epilogue=EPI_BIAS_DROP_RES, aux_in=x, dropout_p=p, seed=seed)
-    _, stats = ln_fwd(rt, u, ln, y=y)
-    return (h, u, stats, p, seed)
+    sq = rt.seqs(st)
+    _, stats = ln_fwd(rt, u, ln, y=y, seqs=sq)
+    return (h, u, stats, p, seed, sq)
 
 
 def out_block_bwd(rt, dy, saved, dense, ln, dh_epilogue=EPI_NONE, dh_aux=None):
     """Returns (du, dh): du is the gradient of the residual input, dh = dense-input gradient (+epilogue)."""
-    h, u, stats, p, seed = saved
+    h, u, stats, p, seed, sq = saved
     du = rt.empty(*u.shape)
     du_drop = rt.empty(*u.shape) if p > 0 else None
-    ln_bwd(rt, dy, u, stats, ln, dx=du, dx_drop=du_drop, p=p, seed=seed, dbias=rt.g32(dense.bias))
+    ln_bwd(rt, dy, u, stats, ln, dx=du, dx_drop=du_drop, p=p, seed=seed, dbias=rt.g32(dense.bias), seqs=sq)
     dz = du_drop if p > 0 else du
     dh = linear_bwd(rt, h, dz, dense, dx_epilogue=dh_epilogue, bias_done=True, aux_in=dh_aux)
     return du, dh
@@ -271,22 +285,22 @@ def out_block_fwd2(rt, h, x, dense_t, ln_t, dense_v, ln_v, p, y):
     seed = rt.seed() if p > 0 else 0
     Mt = rt.Mt
     u = linear_fwd(rt, h, dense_t, epilogue=EPI_BIAS_DROP_RES, aux_in=x, dropout_p=p, seed=seed, lin2=dense_v, split=Mt)
-    _, st_t = ln_fwd(rt, u[:Mt], ln_t, y=y[:Mt])
-    _, st_v = ln_fwd(rt, u[Mt:], ln_v, y=y[Mt:])
-    return (h, u, (st_t, st_v), p, seed)
+    _, st_t = ln_fwd(rt, u[:Mt], ln_t, y=y[:Mt], seqs=rt.seqs("t"))
+    _, st_v = ln_fwd(rt, u[Mt:], ln_v, y=y[Mt:], seqs=rt.seqs("v"))
+    return (h, u, (st_t, st_v), p, seed, (rt.seqs("t"), rt.seqs("v")))
 
 
 def out_block_bwd2(rt, dy, saved, dense_t, ln_t, dense_v, ln_v, dh_epilogue=EPI_NONE, dh_aux=None):
-    h, u, (st_t, st_v), p, seed = saved
+    h, u, (st_t, st_v), p, seed, (sq_t, sq_v) = saved
     Mt, H = rt.Mt, u.shape[1]
     du = rt.empty(*u.shape)
     du_drop = rt.empty(*u.shape) if p > 0 else None
     dd = (lambda a: None if a is None else a)
     # the dropout mask of the row-split GEMM is indexed by the JOINT row: the vision half starts at element Mt*H
     ln_bwd(rt, dy[:Mt], u[:Mt], st_t, ln_t, dx=du[:Mt], dx_drop=dd(du_drop[:Mt] if p > 0 else None), p=p, seed=seed,
-           dbias=rt.g32(dense_t.bias))
+           dbias=rt.g32(dense_t.bias), seqs=sq_t)
     ln_bwd(rt, dy[Mt:], u[Mt:], st_v, ln_v, dx=du[Mt:], dx_drop=dd(du_drop[Mt:] if p > 0 else None), p=p, seed=seed,
-           dbias=rt.g32(dense_v.bias), offset=Mt * H)
+           dbias=rt.g32(dense_v.bias), offset=Mt * H, seqs=sq_v)
     dz = du_drop if p > 0 else du
     dh = linear_bwd(rt, h, dz, dense_t, dx_epilogue=dh_epilogue, bias_done=True, aux_in=dh_aux, lin2=dense_v, split=Mt)
     return du, dh
@@ -371,7 +385,7 @@ def attention_fwd(rt, layer, x, masks):
     y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1]) if (sa.has_text and sa.has_vision) else None
     saved_out = {}
     if joint:
-        saved_out["all"] = out_block_fwd(rt, ctx["all"], x.all, so.dense, so.LayerNorm, rt.p(so.dropout.p), y.all)
+        saved_out["all"] = out_block_fwd(rt, ctx["all"], x.all, so.dense, so.LayerNorm, rt.p(so.dropout.p), y.all, st="all")
     elif split:
         saved_out["split"] = out_block_fwd2(rt, ctx["all"], x.all, so.dense, so.LayerNorm, so.v_dense, so.v_LayerNorm,
                                             rt.p(so.dropout.p), y.all)
@@ -379,9 +393,9 @@ def attention_fwd(rt, layer, x, masks):
         if y is None:  # only one stream is touched: the other passes through unchanged (encoders.py:380-396)
             y = Pair(rt.empty(*x.t.shape) if sa.has_text else x.t, rt.empty(*x.v.shape) if sa.has_vision else x.v, None)
         if sa.has_text:
-            saved_out["t"] = out_block_fwd(rt, ctx["t"], x.t, so.dense, so.LayerNorm, rt.p(so.dropout.p), y.t)
+            saved_out["t"] = out_block_fwd(rt, ctx["t"], x.t, so.dense, so.LayerNorm, rt.p(so.dropout.p), y.t, st="t")
         if sa.has_vision:
-            saved_out["v"] = out_block_fwd(rt, ctx["v"], x.v, so.v_dense, so.v_LayerNorm, rt.p(so.v_dropout.p), y.v)
+            saved_out["v"] = out_block_fwd(rt, ctx["v"], x.v, so.v_dense, so.v_LayerNorm, rt.p(so.v_dropout.p), y.v, st="v")
     saved = dict(x=x, qkv=qkv, ctx=ctx, lse=(lse_t, lse_v), calls=calls, seed=seed, p=(p_t, p_v), out=saved_out,
                  joint=joint, split=split, masks=masks, lens=getattr(rt, "lens", (None, None)))
     return y, saved
@@ -444,7 +458,7 @@ def _act_epilogues(name):
     raise NotImplementedError("hidden_act=%r: the shipped configs use 'gelu'; 'relu' is supported, 'swish' is not" % (name,))
 
 
-def _ffn_stream_fwd(rt, x, inter, dense2, ln, p, y, act, second=None):
+def _ffn_stream_fwd(rt, x, inter, dense2, ln, p, y, act, second=None, st=None):
     """second = (inter_v, dense2_v, ln_v): both streams in row-split launches over the joint buffer."""
     epi_f, _ = _act_epilogues(act)
     I = inter.weight.shape[0]
@@ -458,7 +472,7 @@ def _ffn_stream_fwd(rt, x, inter, dense2, ln, p, y, act, second=None):
         pre = h  # relu'(pre) = (h > 0)
     if second:
         return (x, pre, out_block_fwd2(rt, h, x, dense2, ln, second[1], second[2], p, y))
-    return (x, pre, out_block_fwd(rt, h, x, dense2, ln, p, y))
+    return (x, pre, out_block_fwd(rt, h, x, dense2, ln, p, y, st=st))
 
 
 def _ffn_stream_bwd(rt, dy, saved, inter, dense2, ln, act, dx_out=None, second=None):
@@ -477,7 +491,7 @@ def ffn_fwd(rt, layer, x):
     saved = {"x": x}
     if groups == ["all"]:
         y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
-        saved["all"] = _ffn_stream_fwd(rt, x.all, it.dense, out.dense, out.LayerNorm, rt.p(out.dropout.p), y.all, it.hidden_act)
+        saved["all"] = _ffn_stream_fwd(rt, x.all, it.dense, out.dense, out.LayerNorm, rt.p(out.dropout.p), y.all, it.hidden_act, st="all")
     elif (it.has_language and it.has_vision and it.hidden_act == it.v_hidden_act and
           split_ok(rt, x, rt.p(out.dropout.p), rt.p(out.v_dropout.p), (it.dense, it.v_dense), (out.dense, out.v_dense))):
         y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
@@ -489,9 +503,9 @@ def ffn_fwd(rt, layer, x):
         else:
             y = Pair(rt.empty(*x.t.shape) if it.has_language else x.t, rt.empty(*x.v.shape) if it.has_vision else x.v, None)
         if it.has_language:
-            saved["t"] = _ffn_stream_fwd(rt, x.t, it.dense, out.dense, out.LayerNorm, rt.p(out.dropout.p), y.t, it.hidden_act)
+            saved["t"] = _ffn_stream_fwd(rt, x.t, it.dense, out.dense, out.LayerNorm, rt.p(out.dropout.p), y.t, it.hidden_act, st="t")
         if it.has_vision:
-            saved["v"] = _ffn_stream_fwd(rt, x.v, it.v_dense, out.v_dense, out.v_LayerNorm, rt.p(out.v_dropout.p), y.v, it.v_hidden_act)
+            saved["v"] = _ffn_stream_fwd(rt, x.v, it.v_dense, out.v_dense, out.v_LayerNorm, rt.p(out.v_dropout.p), y.v, it.v_hidden_act, st="v")
     return y, saved
 
 

@@ -119,23 +119,39 @@ def gemm_backend(a, b, out, **kw):
 
 
 # --------------------------------------------------------------------------- LayerNorm
-def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=1.0, accum=False):
+def _row_seqs(seqs, rows):
+    """seqs = (len_a, L_a, rows_a, len_b, L_b) or None -> vb_row_seqs (trailing-padding rows are skipped)."""
+    if seqs is None:
+        return None
+    len_a, L_a, rows_a, len_b, L_b = seqs
+    assert len_a.dtype == torch.int32 and rows_a <= rows and rows_a % L_a == 0 and len_a.numel() >= rows_a // L_a
+    q = _lib.RowSeqs()
+    q.len_a, q.L_a, q.rows_a = len_a.data_ptr(), int(L_a), int(rows_a)
+    if len_b is not None and rows > rows_a:
+        assert len_b.dtype == torch.int32 and (rows - rows_a) % L_b == 0 and len_b.numel() >= (rows - rows_a) // L_b
+        q.len_b, q.L_b = len_b.data_ptr(), int(L_b)
+    else:
+        assert rows == rows_a
+    return C.byref(q)
+
+
+def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=1.0, accum=False, seqs=None):
     require_cuda(x, y)
     rows, H, ld = _rows2d(x)
     assert ld == H and _rows2d(y)[2] == H, "LayerNorm rows must be dense"
     _lib.call("vb_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(mean), _ptr(rstd),
-              rows, H, eps, out_scale, int(accum), dt(x), _stream())
+              rows, H, eps, out_scale, int(accum), _row_seqs(seqs, rows), dt(x), _stream())
     return y
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, out_scale=1.0, dx_drop=None, dropout_p=0.0, seed=0,
-                  offset=0, dbias=None):
+                  offset=0, dbias=None, seqs=None):
     require_cuda(dy, x, dx)
     rows, H, ld = _rows2d(x)
     assert ld == H
     _lib.call("vb_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
               dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), rows, H, out_scale, _ptr(dx_drop), float(dropout_p), int(seed),
-              int(offset), _ptr(dbias), dt(x), _stream())
+              int(offset), _ptr(dbias), _row_seqs(seqs, rows), dt(x), _stream())
     return dx
 
 
