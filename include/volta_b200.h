@@ -122,6 +122,11 @@ typedef struct vb_gemm_args {
    * k-blocks: the caller keeps the operands zero from the limit up to the next multiple of 256. */
   const int32_t* m_limit;
   const int32_t* k_limit;
+  /* Two row segments with their own counts: rows [0, limit_seg_M) are limited by *m_limit, rows [limit_seg_M, M) by
+   * *m_limit2 (counted from limit_seg_M) - the packed text rows and the packed vision rows of a joint buffer.
+   * limit_seg_M = 0: one segment.  Must be a multiple of 256 for the tcgen05 back-end. */
+  const int32_t* m_limit2;
+  int64_t limit_seg_M;
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
@@ -210,6 +215,10 @@ typedef struct vb_attn_args {
    * -10000 underflows), as queries nothing reads them (their context / dQ rows are written as zeros, the reference
    * leaves finite garbage there).  Masked positions below the length are handled by the additive mask as usual. */
   const int32_t* len_t; const int32_t* len_v;
+  /* Optional [B] int32 per stream (needs len_*; tensor-core back-end only): the qkv / ctx / dctx / dqkv buffers of that
+   * stream are PACKED - sample b owns rows [cu[b], cu[b] + len[b]) instead of [b*L, (b+1)*L).  Masks and lse keep
+   * their [B, L] / [B, heads, L] layout. */
+  const int32_t* cu_t; const int32_t* cu_v;
 } vb_attn_args;
 
 int vb_attention_fwd(const vb_attn_args* args, void* stream);
@@ -322,6 +331,10 @@ int vb_compact_gather(const void* src, int64_t ld_src, const int32_t* src_index,
                       int64_t ld_dst, int64_t rows, int32_t cols, int32_t dtype, void* stream);
 int vb_compact_scatter(const void* src_c, int64_t ld_src, const int32_t* pos, void* dst, int64_t ld_dst, int64_t rows,
                        int32_t cols, int32_t dtype, void* stream);
+/* Zero rows [row_offset + *row_begin, row_offset + *row_end) of buf (device-side bounds, at most max_rows rows): the
+ * tail between a packed row count and its 256-row padding, which the tile-granular GEMMs read. */
+int vb_zero_rows(void* buf, int64_t ld, int32_t cols, const int32_t* row_begin, const int32_t* row_end, int64_t row_offset,
+                 int32_t max_rows, int32_t dtype, void* stream);
 /* out[r,:] = a[idx[r],:] (gather rows; idx int64) and its scatter-add adjoint */
 int vb_gather_rows(const void* a, int64_t lda, const int64_t* idx, void* out, int64_t ldo, int64_t rows,
                    int64_t cols, int32_t dtype, void* stream);

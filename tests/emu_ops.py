@@ -25,7 +25,16 @@ def _dgelu(x):
 
 def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
          dropout_p=0.0, seed=0, offset=0, backend=0, split_k=0, M=None, N=None, K=None, b2=None, bias2=None, split_M=0,
-         m_limit=None, k_limit=None):
+         m_limit=None, k_limit=None, m_limit2=None, limit_seg_M=0):
+    if limit_seg_M:      # two row segments with their own device-side counts (and, in a row-split launch, weights)
+        assert a_kmajor and epilogue != _lib.EPI_ACCUM and (b2 is None or split_M == limit_seg_M)
+        sg = limit_seg_M
+        kw = dict(a_kmajor=a_kmajor, b_kmajor=b_kmajor, epilogue=epilogue, dropout_p=dropout_p, N=N, K=K)
+        for rows, bb_, bias_, lim in ((slice(0, sg), b, bias, m_limit),
+                                     (slice(sg, None), b if b2 is None else b2, bias if (b2 is None or bias2 is None) else bias2, m_limit2)):
+            gemm(a[rows], bb_, out[rows], bias=bias_, aux_in=None if aux_in is None else aux_in[rows],
+                 aux_out=None if aux_out is None else aux_out[rows], m_limit=lim, **kw)
+        return out
     if m_limit is not None or k_limit is not None:   # device-side extents: only that many rows / reduction elements exist
         A0 = a if a_kmajor else a.t()
         B0 = b if b_kmajor else b.t()
@@ -410,6 +419,11 @@ def compact_gather(src, src_index, limits, dst):
     return dst
 
 
+def zero_rows(buf, row_begin, row_end, row_offset=0, max_rows=256):
+    buf[row_offset + int(row_begin[0]):row_offset + int(row_end[0])] = 0
+    return buf
+
+
 def compact_scatter(src_c, pos, dst):
     rows = dst.shape[0]
     p = pos[:rows].long()
@@ -480,7 +494,7 @@ def fill(buf, value=0):
 _NAMES = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "embed_gather_fwd",
           "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd", "region_loss_fwd", "region_loss_bwd",
           "loss_finalize", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill",
-          "compact_plan", "compact_gather", "compact_scatter", "mask_lengths"]
+          "compact_plan", "compact_gather", "compact_scatter", "mask_lengths", "zero_rows"]
 
 
 def install(monkeypatch):

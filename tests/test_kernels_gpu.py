@@ -161,6 +161,53 @@ def test_gemm_device_side_extents(backend, count):
     assert rel(dW, ref) < 2e-3
 
 
+@pytest.mark.parametrize("backend", ["tc", "simt"])
+@pytest.mark.parametrize("na,nb,split", [(300, 700, True), (0, 5, False), (1024, 0, True), (513, 1500, False)])
+def test_gemm_two_row_segments_with_device_counts(backend, na, nb, split):
+    """m_limit / m_limit2 / limit_seg_M: packed text rows [0, na) and packed vision rows [seg, seg + nb) of a joint
+    buffer, optionally with per-segment weights (row-split launch).  Rows below the counts match the plain GEMM; rows
+    beyond the last scheduled tile of a segment are not written."""
+    be = _lib.GEMM_TC if backend == "tc" else _lib.GEMM_SIMT
+    seg, M, N, K = 1024, 1024 + 1536, 776, 320
+    lim = torch.tensor([na, nb], dtype=torch.int32, device=DEV)
+    a = rnd(M, K)
+    a[na:seg] = 0
+    a[seg + nb:] = 0
+    w1, w2 = rnd(N, K, scale=0.05), rnd(N, K, scale=0.05, seed=1)
+    b1, b2 = rnd(N, dtype=torch.float32), rnd(N, dtype=torch.float32, seed=2)
+    out = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=DEV)
+    kw = dict(b2=w2, bias2=b2, split_M=seg) if split else {}
+    if split and backend == "simt":
+        pytest.skip("row-split launches are a tcgen05 feature")
+    ops.gemm(a, w1, out, epilogue=_lib.EPI_BIAS, bias=b1, backend=be, m_limit=lim[0:1], m_limit2=lim[1:2], limit_seg_M=seg, **kw)
+    wb, bb = (w2, b2) if split else (w1, b1)
+    if na:
+        assert rel(out[:na].float(), a[:na].float() @ w1.float().t() + b1) < 6e-3
+    if nb:
+        assert rel(out[seg:seg + nb].float(), a[seg:seg + nb].float() @ wb.float().t() + bb) < 6e-3
+    pa, pb = (na + 255) // 256 * 256, (nb + 255) // 256 * 256
+    assert bool((out[pa:seg] == 7.0).all()) and bool((out[seg + pb:] == 7.0).all())
+    # dgrad layout
+    w1t = w1.t().contiguous()
+    out2 = torch.full((M, N), 7.0, dtype=torch.bfloat16, device=DEV)
+    kw2 = dict(b2=w2.t().contiguous(), split_M=seg) if split else {}
+    ops.gemm(a, w1t, out2, a_kmajor=True, b_kmajor=False, backend=be, m_limit=lim[0:1], m_limit2=lim[1:2], limit_seg_M=seg, **kw2)
+    if na:
+        assert rel(out2[:na].float(), a[:na].float() @ w1.float().t()) < 6e-3
+    if nb:
+        assert rel(out2[seg:seg + nb].float(), a[seg:seg + nb].float() @ wb.float().t()) < 6e-3
+    assert bool((out2[pa:seg] == 7.0).all()) and bool((out2[seg + pb:] == 7.0).all())
+
+
+def test_zero_rows_device_bounds():
+    buf = torch.full((700, 776), 3.0, dtype=torch.bfloat16, device=DEV)
+    lim = torch.tensor([301, 512], dtype=torch.int32, device=DEV)
+    ops.zero_rows(buf[100:], lim[0:1], lim[1:2])
+    ref = torch.full_like(buf, 3.0)
+    ref[401:612] = 0
+    assert torch.equal(buf, ref)
+
+
 def test_compact_plan_gather_scatter_and_limited_criterion():
     """vb_compact_*: order-preserving packing of the labelled rows, exact; cross-entropy / column sums with a device-side
     row count equal the full-size calls on the same rows."""
@@ -436,6 +483,64 @@ def test_attention_skips_trailing_padding(B, Lt, Lv, heads, d, pm):
             assert rel(skipg[valid].float(), fullg[valid].float()) < 5e-3
             if bool((~valid).any()):
                 assert float(skipg[~valid].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,Lt,Lv,heads,d,pm", [(4, 36, 37, 12, 64, 1), (4, 36, 37, 12, 64, 9), (4, 36, 37, 12, 64, 6),
+                                                (4, 30, 101, 8, 128, 6), (4, 56, 80, 4, 64, 15)])
+def test_attention_on_packed_rows(B, Lt, Lv, heads, d, pm):
+    """vb_attn_args::cu_*: sample b owns rows [cu[b], cu[b] + len[b]) of the qkv / ctx / dctx / dqkv buffers.  Against the
+    padded layout with the same lengths: identical context rows and gradients for every valid position; rows beyond
+    the packed count are not touched."""
+    dtype = torch.bfloat16
+    qt, qv, _, _, A = _attn_inputs(B, Lt, Lv, heads, d, pm, dtype)
+    lens = {"t": torch.tensor([Lt, 5, 17, 9][:B]), "v": torch.tensor([3, Lv, 11, 20][:B])}
+    L = {"t": Lt, "v": Lv}
+    mask, ldev, cu, keep, n = {}, {}, {}, {}, {}
+    for k in "tv":
+        m = (torch.arange(L[k])[None] < lens[k][:, None]).int()
+        if k == "t":
+            m[0, 2] = 0                       # a hole below the length stays a (masked) row of the packed sample
+        mask[k] = m.to(DEV)
+        ldev[k] = lens[k].to(torch.int32).to(DEV)
+        cu[k] = (torch.cumsum(lens[k], 0) - lens[k]).to(torch.int32).to(DEV)
+        keep[k] = (torch.arange(L[k])[None] < lens[k][:, None]).reshape(-1).to(DEV)
+        n[k] = int(lens[k].sum())
+    tq, vq = bool(pm & 3), bool(pm & 12)
+    q = {"t": qt, "v": qv}
+    dctx = {"t": rnd(B * Lt, A, dtype=dtype, seed=7) if tq else None, "v": rnd(B * Lv, A, dtype=dtype, seed=8) if vq else None}
+
+    def pack(x, k):
+        if x is None:
+            return None
+        y = torch.full_like(x, 9.0)
+        y[:n[k]] = x[keep[k]]
+        return y
+    res = {}
+    for name in ("padded", "packed"):
+        pk = name == "packed"
+        qq = {k: (pack(q[k], k) if pk else q[k]) for k in "tv"}
+        dc = {k: (pack(dctx[k], k) if pk else dctx[k]) for k in "tv"}
+        ct = torch.full((B * Lt, A), 3.0, dtype=dtype, device=DEV) if tq else None
+        cv = torch.full((B * Lv, A), 3.0, dtype=dtype, device=DEV) if vq else None
+        lt, lv = torch.zeros(B, heads, Lt, device=DEV), torch.zeros(B, heads, Lv, device=DEV)
+        args = (qq["t"], qq["v"], mask["t"] if qt is not None else None, mask["v"] if qv is not None else None)
+        kw = dict(len_t=ldev["t"], len_v=ldev["v"])
+        if pk:
+            kw.update(cu_t=cu["t"], cu_v=cu["v"])
+        ops.attention_fwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, _lib.ATTN_MMA, **kw)
+        dqt = torch.full_like(qt, 7.0) if qt is not None else None
+        dqv = torch.full_like(qv, 7.0) if qv is not None else None
+        ops.attention_bwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, _lib.ATTN_MMA, dctx_t=dc["t"], dctx_v=dc["v"],
+                          dqkv_t=dqt, dqkv_v=dqv, **kw)
+        res[name] = dict(t=(ct, dqt), v=(cv, dqv))
+    for k in "tv":
+        for i in (0, 1):
+            a, b = res["padded"][k][i], res["packed"][k][i]
+            if a is None:
+                continue
+            assert torch.equal(b[:n[k]], a[keep[k]]), (k, i)
+            fill = 3.0 if i == 0 else 7.0
+            assert bool((b[n[k]:] == fill).all()), "rows beyond the packed count were written"
 
 
 def test_attention_simt_fp32_exact():

@@ -181,6 +181,50 @@ def engine_launches():
     return engine.launch_count
 
 
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+def test_packed_rows_match_padded_layout(dropout, monkeypatch):
+    """Between the embeddings and the heads the valid rows are packed (device-side counts).  Against the padded layout:
+    same losses and parameter gradients without dropout; with dropout (masks are indexed by the packed row) finite,
+    reproducible under a fixed seed, and at the same loss level."""
+    from volta_b200 import engine
+    from volta_b200.synthetic import pretraining_batch
+    g, cfg, _ = load_case("mini_ctrl_vilbert")
+    for k in ("hidden_dropout_prob", "attention_probs_dropout_prob", "v_hidden_dropout_prob", "v_attention_probs_dropout_prob"):
+        setattr(cfg, k, dropout)
+    b = pretraining_batch(32, 8, 9, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
+    d = {k: v.cuda() for k, v in b.items()}
+    runs = {}
+    for packed in (True, False):
+        monkeypatch.setattr(engine, "PACK_ROWS", packed)
+        model = volta_b200.BertForVLPreTraining(cfg)
+        model.load_state_dict(seeded_state_dict(model.state_dict(), seed=0))
+        model.train().cuda()
+        model._use_cuda_graphs = False
+        out = []
+        for rep in range(2):
+            model.zero_grad(set_to_none=True)
+            torch.manual_seed(5)
+            n0 = engine_launches()
+            l = _losses(model, d)
+            (l[0] + l[1] + l[2]).sum().backward()
+            out.append(([float(x) for x in l], {k: p.grad.clone() for k, p in model.named_parameters()}, engine_launches() - n0))
+        runs[packed] = out
+    (l1, g1, n1), (l1b, g1b, _) = runs[True]
+    (l0, g0, n0), _ = runs[False]
+    assert n1 > n0, "the packed plan adds its gather / scatter / zero-row launches: was it taken?"
+    assert all(abs(a - c) < 1e-5 * max(1.0, abs(a)) for a, c in zip(l1, l1b))
+    for k in g1:
+        assert torch.isfinite(g1[k]).all(), k
+    if dropout == 0.0:
+        assert all(abs(a - c) < 2e-3 * max(1.0, abs(a)) for a, c in zip(l1, l0)), (l1, l0)
+        for k in g1:
+            den = float(g0[k].norm())
+            if den > 1e-6:
+                assert float((g1[k] - g0[k]).norm()) / den < 3e-2, k
+    else:
+        assert all(abs(a - c) < 0.1 * max(1.0, abs(c)) for a, c in zip(l1, l0)), (l1, l0)
+
+
 def test_masked_lm_rows_only_matches_all_positions_decoder(monkeypatch):
     """The masked-LM head runs the decoder / criterion on the labelled rows only (device-side count).  Against the
     all-positions decoder of the reference (volta/encoders.py:686-696): same losses, same gradients for every parameter."""

@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
                 ("a_kmajor", _i32), ("b_kmajor", _i32), ("epilogue", _i32), ("backend", _i32),
                 ("bias", _vp), ("aux_in", _vp), ("aux_out", _vp), ("ld_aux", _i64), ("alpha", _f),
                 ("dropout_p", _f), ("seed", _u64), ("offset", _u64), ("split_k", _i32), ("reserved", _i32),
-                ("B2", _vp), ("bias2", _vp), ("split_M", _i64), ("m_limit", _vp), ("k_limit", _vp)]
+                ("B2", _vp), ("bias2", _vp), ("split_M", _i64), ("m_limit", _vp), ("k_limit", _vp), ("m_limit2", _vp), ("limit_seg_M", _i64)]
 
 
 class AttnArgs(C.Structure):
@@ -36,7 +36,7 @@ class AttnArgs(C.Structure):
                 ("dctx_t", _vp), ("dctx_v", _vp), ("dqkv_t", _vp), ("dqkv_v", _vp),
                 ("B", _i32), ("Lt", _i32), ("Lv", _i32), ("heads", _i32), ("d", _i32), ("pair_mask", _i32),
                 ("dtype", _i32), ("scale", _f), ("dropout_p_t", _f), ("dropout_p_v", _f), ("seed", _u64),
-                ("offset", _u64), ("backend", _i32), ("reserved", _i32), ("len_t", _vp), ("len_v", _vp)]
+                ("offset", _u64), ("backend", _i32), ("reserved", _i32), ("len_t", _vp), ("len_v", _vp), ("cu_t", _vp), ("cu_v", _vp)]
 
 
 class RowSeqs(C.Structure):
@@ -76,6 +76,7 @@ SIGNATURES = {
     "vb_loss_finalize": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "vb_eltwise": (_i32, [_i32, _vp, _i32, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _f, _f, _u64, _u64, _vp]),
     "vb_colsum": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "vb_zero_rows": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
     "vb_mask_lengths": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "vb_compact_plan": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vb_compact_gather": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),

@@ -33,6 +33,7 @@ struct P {
   const uint64_t* seed_ptr;  // see vb_set_seed_pointer
   int ngroups;               // MMA back-end: independent (query set, key set) groups per (sample, head)
   const int32_t* len[2];     // optional [B] per stream: 1 + index of the last position whose mask is set (vb_mask_lengths)
+  const int32_t* cu[2];      // optional [B] per stream: PACKED rows - sample b owns rows [cu[b], cu[b] + len[b]) of the buffers
 };
 
 // Effective length of stream s in sample b: positions at or beyond it are padding for every head and every layer - as
@@ -44,6 +45,7 @@ __device__ __forceinline__ int eff_len(const P& p, int s, int b) {
   int L = p.L[s];
   if (p.len[s] != nullptr) {
     const int v = p.len[s][b];
+    if (p.cu[s] != nullptr) return min(max(v, 0), L);   // packed buffers hold exactly len[b] rows of this sample
     if (v > 0 && v < L) L = v;
   }
   return L;
@@ -436,9 +438,12 @@ mma_fwd_kernel(P p) {
   const int gq = lane >> 2, tq = lane & 3;
 
   const int Le[2] = {p.L[0] ? eff_len(p, 0, b) : 0, p.L[1] ? eff_len(p, 1, b) : 0};
+  // first buffer row of this sample and how many of its rows exist there (packed: the valid ones only)
+  const int64_t row0[2] = {p.cu[0] ? (int64_t)p.cu[0][b] : (int64_t)b * p.L[0], p.cu[1] ? (int64_t)p.cu[1][b] : (int64_t)b * p.L[1]};
+  const int Ls[2] = {p.cu[0] ? Le[0] : p.L[0], p.cu[1] ? Le[1] : p.L[1]};
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    const bf16* base = reinterpret_cast<const bf16*>(p.qkv[s]) + (int64_t)b * p.L[s] * p.ld[s] + h * D;
+    const bf16* base = reinterpret_cast<const bf16*>(p.qkv[s]) + row0[s] * p.ld[s] + h * D;
     if (g.qrows[s]) load_seg<D>(Qs + (s ? g.qrows[0] : 0) * TL::PITCH, base, p.ld[s], Le[s], g.qrows[s]);
     if (g.krows[s]) {
       const int off = s ? g.krows[0] : 0;
@@ -457,7 +462,7 @@ mma_fwd_kernel(P p) {
   if (jq0 >= Le[qs]) {
     // padding-only query tile: its Q rows were zero-filled by the loader - they are the zero context rows to store
     const bf16* zrows = Qs + qt * 16 * TL::PITCH;
-    store_rows16<D>(zrows, reinterpret_cast<bf16*>(p.ctx[qs]) + (int64_t)b * p.L[qs] * p.ld_ctx[qs] + h * D, p.ld_ctx[qs], jq0, p.L[qs]);
+    store_rows16<D>(zrows, reinterpret_cast<bf16*>(p.ctx[qs]) + row0[qs] * p.ld_ctx[qs] + h * D, p.ld_ctx[qs], jq0, Ls[qs]);
     if (lane < 16 && jq0 + lane < p.L[qs]) p.lse[qs][((int64_t)b * p.heads + h) * p.L[qs] + jq0 + lane] = 0.f;
     return;
   }
@@ -520,7 +525,7 @@ mma_fwd_kernel(P p) {
     sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 1);
     sum[r] += __shfl_xor_sync(0xffffffffu, sum[r], 2);
     const int j = jq0 + gq + r * 8;
-    osc[r] = j < Le[qs] ? p.keep_scale[qs] / sum[r] : 0.f;   // padding rows of a partly valid tile: zeros, like whole padding tiles
+    osc[r] = (j < Le[qs] && sum[r] > 0.f) ? p.keep_scale[qs] / sum[r] : 0.f;   // padding rows of a partly valid tile: zeros, like whole padding tiles
     if (tq == 0 && j < p.L[qs]) p.lse[qs][((int64_t)b * p.heads + h) * p.L[qs] + j] = (mx[r] + __log2f(sum[r])) * 0.6931471805599453f;
   }
   const uint32_t thresh = p.thresh[qs];
@@ -569,7 +574,7 @@ mma_fwd_kernel(P p) {
   __syncwarp();
   frag_to_rows16<D>(mine, o, osc[0], osc[1]);
   __syncwarp();
-  store_rows16<D>(mine, reinterpret_cast<bf16*>(p.ctx[qs]) + (int64_t)b * p.L[qs] * p.ld_ctx[qs] + h * D, p.ld_ctx[qs], jq0, p.L[qs]);
+  store_rows16<D>(mine, reinterpret_cast<bf16*>(p.ctx[qs]) + row0[qs] * p.ld_ctx[qs] + h * D, p.ld_ctx[qs], jq0, Ls[qs]);
 }
 
 // ---------------------------------------------------------------------------------------------- backward
@@ -601,9 +606,11 @@ mma_bwd_kernel(P p) {
   const int Ltot = p.L[0] + p.L[1];
 
   const int Le[2] = {p.L[0] ? eff_len(p, 0, b) : 0, p.L[1] ? eff_len(p, 1, b) : 0};
+  const int64_t row0[2] = {p.cu[0] ? (int64_t)p.cu[0][b] : (int64_t)b * p.L[0], p.cu[1] ? (int64_t)p.cu[1][b] : (int64_t)b * p.L[1]};
+  const int Ls[2] = {p.cu[0] ? Le[0] : p.L[0], p.cu[1] ? Le[1] : p.L[1]};
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    const bf16* base = reinterpret_cast<const bf16*>(p.qkv[s]) + (int64_t)b * p.L[s] * p.ld[s] + h * D;
+    const bf16* base = reinterpret_cast<const bf16*>(p.qkv[s]) + row0[s] * p.ld[s] + h * D;
     if (g.qrows[s]) load_seg<D>(Qs + (s ? g.qrows[0] : 0) * TL::PITCH, base, p.ld[s], Le[s], g.qrows[s]);
     if (g.krows[s]) {
       const int off = s ? g.krows[0] : 0;
@@ -617,7 +624,7 @@ mma_bwd_kernel(P p) {
   for (int s = 0; s < 2; ++s) {
     if (!g.qrows[s]) continue;
     const int off = s ? g.qrows[0] : 0;
-    const int64_t head0 = (int64_t)b * p.L[s] * p.ld_ctx[s] + h * D;
+    const int64_t head0 = row0[s] * p.ld_ctx[s] + h * D;
     load_seg<D>(dOs + off * TL::PITCH, reinterpret_cast<const bf16*>(p.dctx[s]) + head0, p.ld_ctx[s], Le[s], g.qrows[s]);
     load_seg<D>(Os + off * TL::PITCH, reinterpret_cast<const bf16*>(p.ctx[s]) + head0, p.ld_ctx[s], Le[s], g.qrows[s]);
     for (int r = threadIdx.x; r < g.qrows[s]; r += blockDim.x) {
@@ -724,16 +731,16 @@ mma_bwd_kernel(P p) {
     // dV, then dK: staged in the warp's own (now dead) V rows - its K rows are still read by the dQ phase -
     // and stored as 16-byte coalesced rows
     if (p.dqkv[ks] != nullptr) {
-      bf16* dst = reinterpret_cast<bf16*>(p.dqkv[ks]) + (int64_t)b * p.L[ks] * p.ld[ks] + h * D;
+      bf16* dst = reinterpret_cast<bf16*>(p.dqkv[ks]) + row0[ks] * p.ld[ks] + h * D;
       bf16* mv = Vs + kt * 16 * TL::PITCH;
       __syncwarp();
       frag_to_rows16<D>(mv, dv, 1.f, 1.f);
       __syncwarp();
-      store_rows16<D>(mv, dst + 2 * p.A, p.ld[ks], jk0, p.L[ks]);
+      store_rows16<D>(mv, dst + 2 * p.A, p.ld[ks], jk0, Ls[ks]);
       __syncwarp();
       frag_to_rows16<D>(mv, dk, 1.f, 1.f);
       __syncwarp();
-      store_rows16<D>(mv, dst + p.A, p.ld[ks], jk0, p.L[ks]);
+      store_rows16<D>(mv, dst + p.A, p.ld[ks], jk0, Ls[ks]);
     }
   }
   __syncthreads();
@@ -764,21 +771,21 @@ mma_bwd_kernel(P p) {
       bf16* mine = Qs + qt * 16 * TL::PITCH;  // nobody reads Q after the barrier
       frag_to_rows16<D>(mine, dq, 1.f, 1.f);
       __syncwarp();
-      store_rows16<D>(mine, reinterpret_cast<bf16*>(p.dqkv[qs]) + (int64_t)b * p.L[qs] * p.ld[qs] + h * D, p.ld[qs], jq0, p.L[qs]);
+      store_rows16<D>(mine, reinterpret_cast<bf16*>(p.dqkv[qs]) + row0[qs] * p.ld[qs] + h * D, p.ld[qs], jq0, Ls[qs]);
     }
   }
   // streams that only supply keys (queries) get zero dQ (dK, dV)
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     if (p.dqkv[s] == nullptr) continue;
-    bf16* dst = reinterpret_cast<bf16*>(p.dqkv[s]) + (int64_t)b * p.L[s] * p.ld[s] + h * D;
+    bf16* dst = reinterpret_cast<bf16*>(p.dqkv[s]) + row0[s] * p.ld[s] + h * D;
     if (g.qrows[s]) {
     } else if (g.krows[s] && attn_groups(p.pair_mask) == 1) {
-      for (int e = threadIdx.x; e < p.L[s] * CH; e += blockDim.x)
+      for (int e = threadIdx.x; e < Ls[s] * CH; e += blockDim.x)
         *reinterpret_cast<uint4*>(dst + (int64_t)(e / CH) * p.ld[s] + (e % CH) * 8) = make_uint4(0u, 0u, 0u, 0u);
     }
     if (g.qrows[s] && !g.krows[s] && attn_groups(p.pair_mask) == 1) {
-      for (int e = threadIdx.x; e < p.L[s] * CH * 2; e += blockDim.x) {
+      for (int e = threadIdx.x; e < Ls[s] * CH * 2; e += blockDim.x) {
         const int r = e / (2 * CH), c = (e % (2 * CH)) * 8;  // K and V column blocks
         *reinterpret_cast<uint4*>(dst + (int64_t)r * p.ld[s] + p.A + (c / D) * p.A + (c % D)) = make_uint4(0u, 0u, 0u, 0u);
       }
@@ -826,6 +833,9 @@ static int fill(const vb_attn_args& a, P& p, bool bwd) {
   p.seed_ptr = seed_pointer();
   p.len[0] = p.qkv[0] ? a.len_t : nullptr;
   p.len[1] = p.qkv[1] ? a.len_v : nullptr;
+  p.cu[0] = p.qkv[0] ? a.cu_t : nullptr;
+  p.cu[1] = p.qkv[1] ? a.cu_v : nullptr;
+  VB_REQUIRE((!p.cu[0] || p.len[0]) && (!p.cu[1] || p.len[1]), VB_ERR_ARG, "attention: packed rows (cu_*) need the lengths (len_*)");
   return 0;
 }
 
@@ -883,6 +893,7 @@ static int run(const vb_attn_args& a, cudaStream_t st, bool bwd) {
   const bool can_mma = mma_ok(a, p, bwd, &why);
   VB_REQUIRE(a.backend != VB_ATTN_MMA || can_mma, VB_ERR_UNSUPPORTED, "attention: MMA back-end cannot run: %s", why);
   const bool use_mma = can_mma && a.backend != VB_ATTN_SIMT;
+  VB_REQUIRE(use_mma || (!p.cu[0] && !p.cu[1]), VB_ERR_UNSUPPORTED, "attention: packed rows (cu_*) need the tensor-core back-end");
   const unsigned grid = (unsigned)(a.B * a.heads);
   if (use_mma) {
     const LaunchGeo lg = launch_geo(p, a.d);

@@ -111,6 +111,23 @@ scatter_kernel(const T* __restrict__ src_c, int64_t ld_src, const int32_t* __res
   }
 }
 
+// rows [row_offset + *row_begin, row_offset + *row_end) := 0
+template <typename T>
+__global__ void __launch_bounds__(256)
+zero_rows_kernel(T* __restrict__ buf, int64_t ld, int cols, const int32_t* __restrict__ row_begin,
+                 const int32_t* __restrict__ row_end, int64_t row_offset, bool vec) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)*row_begin + (int64_t)blockIdx.x * 8 + warp;
+  if (r >= *row_end) return;
+  T* d = buf + (row_offset + r) * ld;
+  if (vec) {
+    constexpr int E = 16 / sizeof(T);
+    for (int c = lane * E; c < cols; c += 32 * E) *reinterpret_cast<uint4*>(d + c) = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    for (int c = lane; c < cols; c += 32) d[c] = from_f<T>(0.f);
+  }
+}
+
 template <typename T>
 static bool vec_ok(const void* a, int64_t lda, const void* b, int64_t ldb, int cols) {
   constexpr int E = 16 / sizeof(T);
@@ -158,6 +175,20 @@ int vb_compact_scatter(const void* src_c, int64_t ld_src, const int32_t* pos, vo
     scatter_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src_c, ld_src, pos, (float*)dst, ld_dst, rows, cols,
                                                                 vec_ok<float>(src_c, ld_src, dst, ld_dst, cols));
   return vb::check_launch("compact_scatter_kernel");
+}
+
+int vb_zero_rows(void* buf, int64_t ld, int32_t cols, const int32_t* row_begin, const int32_t* row_end, int64_t row_offset,
+                 int32_t max_rows, int32_t dtype, void* stream) {
+  VB_REQUIRE(buf && row_begin && row_end && cols > 0 && ld >= cols && max_rows > 0, VB_ERR_ARG, "zero_rows: bad arguments");
+  const unsigned grid = (unsigned)vb::ceil_div((int64_t)max_rows, 8);
+  using namespace vb::compact;
+  if (dtype == VB_BF16)
+    zero_rows_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((vb::bf16*)buf, ld, cols, row_begin, row_end, row_offset,
+                                                                     vec_ok<vb::bf16>(buf, ld, buf, ld, cols));
+  else
+    zero_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)buf, ld, cols, row_begin, row_end, row_offset,
+                                                                  vec_ok<float>(buf, ld, buf, ld, cols));
+  return vb::check_launch("zero_rows_kernel");
 }
 
 }  // extern "C"

@@ -16,14 +16,19 @@ struct Operand {
 template <typename T>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(Operand A, Operand B, int64_t M, int64_t N, int64_t K, EpiParams p, const int32_t* m_limit,
-                 const int32_t* k_limit) {
+                 const int32_t* k_limit, const int32_t* m_limit2, int64_t seg_M) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const T* a = reinterpret_cast<const T*>(A.ptr);
   const T* b = reinterpret_cast<const T*>(B.ptr);
   const int tid = threadIdx.x;
   const int64_t m0 = (int64_t)blockIdx.y * TM, n0 = (int64_t)blockIdx.x * TN;
-  if (m_limit && m0 >= *m_limit) return;            // device-side extents (vb_gemm_args::m_limit / k_limit)
+  // device-side extents (vb_gemm_args::m_limit / k_limit / m_limit2)
+  if (seg_M > 0 && m0 >= seg_M) {
+    if (m_limit2 && m0 - seg_M >= *m_limit2) return;
+  } else if (m_limit && m0 >= *m_limit) {
+    return;
+  }
   if (k_limit) K = min(K, (int64_t)max(*k_limit, 0));
   const int tx = tid & 15, ty = tid >> 4;
   float acc[4][4];
@@ -130,9 +135,9 @@ int gemm_simt_launch(const vb_gemm_args& a, cudaStream_t stream) {
   dim3 grid((unsigned)ceil_div(a.N, simt::TN), (unsigned)ceil_div(a.M, simt::TM));
   VB_REQUIRE(grid.y <= 65535u, VB_ERR_UNSUPPORTED, "gemm_simt: M too large (%lld)", (long long)a.M);
   if (a.ab_dtype == VB_BF16)
-    simt::gemm_simt_kernel<bf16><<<grid, 256, 0, stream>>>(A, B, a.M, a.N, a.K, p, a.m_limit, a.k_limit);
+    simt::gemm_simt_kernel<bf16><<<grid, 256, 0, stream>>>(A, B, a.M, a.N, a.K, p, a.m_limit, a.k_limit, a.m_limit2, (a.limit_seg_M > 0 && a.limit_seg_M < a.M) ? a.limit_seg_M : 0);
   else
-    simt::gemm_simt_kernel<float><<<grid, 256, 0, stream>>>(A, B, a.M, a.N, a.K, p, a.m_limit, a.k_limit);
+    simt::gemm_simt_kernel<float><<<grid, 256, 0, stream>>>(A, B, a.M, a.N, a.K, p, a.m_limit, a.k_limit, a.m_limit2, (a.limit_seg_M > 0 && a.limit_seg_M < a.M) ? a.limit_seg_M : 0);
   return check_launch("gemm_simt_kernel");
 }
 

@@ -82,6 +82,8 @@ struct Params {
   // *k_limit elements of the reduction hold data; whole tiles / k-blocks beyond them are not scheduled.
   const int32_t* m_limit;
   const int32_t* k_limit;
+  const int32_t* m_limit2;   // second row segment (rows >= seg_m_blk tiles): its own device-side row count
+  int32_t seg_m_blk;         // first tile row of the second segment; INT_MAX = one segment
 };
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -652,7 +654,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   int num_m_blocks = p.num_m_blocks, kb_total = p.kb_total, split_k = p.split_k;
-  if (p.m_limit) num_m_blocks = min(num_m_blocks, (max(*p.m_limit, 0) + BM * CG - 1) / (BM * CG));
+  // live tile rows: [0, live_a) of the first segment, then [seg_blk, seg_blk + live_b) of the second (packed text rows
+  // and packed vision rows of a joint buffer); the work list enumerates live tile rows only
+  const int seg_blk = min(p.seg_m_blk, num_m_blocks);
+  int live_a = seg_blk, live_b = num_m_blocks - seg_blk;
+  if (p.m_limit) live_a = min(live_a, (max(*p.m_limit, 0) + BM * CG - 1) / (BM * CG));
+  if (p.m_limit2) live_b = min(live_b, (max(*p.m_limit2, 0) + BM * CG - 1) / (BM * CG));
+  num_m_blocks = live_a + live_b;
+  auto m_of = [&](int m_idx) { return m_idx < live_a ? m_idx : seg_blk + (m_idx - live_a); };
   if (p.k_limit) {
     kb_total = min(kb_total, (max(*p.k_limit, 0) + BK - 1) / BK);
     split_k = (kb_total + p.kb_per_split - 1) / p.kb_per_split;   // trailing slices are empty: not scheduled at all
@@ -695,7 +704,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const int split = (int)(w % split_k);
       const int64_t tile = w / split_k;
-      const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
+      const int n_blk = (int)(tile % p.num_n_blocks), m_blk = m_of((int)(tile / p.num_n_blocks));
       const int m0 = (m_blk * CG + (int)rank) * BM;
       const int n0 = n_blk * BN + (int)rank * (int)C::B_ROWS;
       const CUtensorMap* mapB = (m_blk >= p.split_m_blk) ? &tmB2 : &tmB;   // row-split launch: second stream's weights
@@ -771,7 +780,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int it = 0, q = 0;
     if (first < total_work) for (int64_t w = first;; ++it) {
       const int64_t tile = w / split_k;
-      const int n_blk = (int)(tile % p.num_n_blocks), m_blk = (int)(tile / p.num_n_blocks);
+      const int n_blk = (int)(tile % p.num_n_blocks), m_blk = m_of((int)(tile / p.num_n_blocks));
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
       // Stage this tile's bias slice in shared memory while the MMAs are still running.  Double buffered by
       // accumulator stage; the named barrier also guarantees nobody still reads the buffer of tile it-2.
@@ -966,7 +975,15 @@ static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
   // statically assigned tiles, and the static grid stays the default.
   p.m_limit = a.m_limit;
   p.k_limit = a.k_limit;
-  p.clc = (use_clc() && work * CG < (int64_t)INT32_MAX && !a.m_limit && !a.k_limit) ? 1 : 0;
+  p.m_limit2 = nullptr;
+  p.seg_m_blk = INT32_MAX;
+  if (a.limit_seg_M > 0 && a.limit_seg_M < a.M) {
+    VB_REQUIRE(a.limit_seg_M % (BM * CG) == 0, VB_ERR_ARG, "gemm: limit_seg_M=%lld is not a multiple of the %d-row tile",
+               (long long)a.limit_seg_M, BM * CG);
+    p.seg_m_blk = (int32_t)(a.limit_seg_M / (BM * CG));
+    p.m_limit2 = a.m_limit2;
+  }
+  p.clc = (use_clc() && work * CG < (int64_t)INT32_MAX && !a.m_limit && !a.k_limit && !p.m_limit2) ? 1 : 0;
   const int grid = (int)(p.clc ? work : std::min<int64_t>(work, units)) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -1017,6 +1034,7 @@ static int launch_epi(const vb_gemm_args& a, cudaStream_t stream) {
     }
     if (o.cg == 2 && (a.M <= 128 || (sms % 2) != 0)) continue;
     if (a.B2 != nullptr && a.split_M > 0 && (a.split_M % (128 * o.cg)) != 0) continue;   // row split must fall on a tile edge
+    if (a.limit_seg_M > 0 && (a.limit_seg_M % (128 * o.cg)) != 0) continue;
     if (o.bn > 128 && a.N <= 128 && o.cg == 1) continue;
     const int64_t tiles = ceil_div(a.M, 128 * o.cg) * ceil_div(a.N, o.bn);
     const int64_t rounds = ceil_div(tiles, sms / o.cg);

@@ -118,6 +118,14 @@ class Runtime:
     # kernels with launch accounting
     def seqs(self, st):
         """vb_row_seqs tuple for the rows of stream st ('t', 'v', 'all' = text rows then vision rows), or None."""
+        if st is not None and getattr(self, "pack_on", False):
+            # packed rows: each stream is ONE run of `count` valid rows followed by unused rows
+            pk = self.pack
+            if st == "t":
+                return (pk.lim_t[0:1], self.Mt, self.Mt, None, 0)
+            if st == "v":
+                return (pk.lim_v[0:1], self.Mv, self.Mv, None, 0)
+            return (pk.lim_t[0:1], self.Mt, self.Mt, pk.lim_v[0:1], self.Mv)
         lens = getattr(self, "lens", (None, None))
         if st is None or lens[0] is None or lens[1] is None or not SKIP_PADDING_LN:
             return None
@@ -127,9 +135,27 @@ class Runtime:
             return (lens[1], self.V, self.Mv, None, 0)
         return (lens[0], self.T, self.Mt, lens[1], self.V)
 
+    def row_limit(self, rows, padded=True):
+        """Packed rows: the device-side row count (int32[1]) of the stream whose buffer has `rows` rows, else None."""
+        if not getattr(self, "pack_on", False):
+            return None
+        pk = self.pack
+        lim = pk.lim_t if rows == self.Mt else pk.lim_v if rows == self.Mv else None
+        assert lim is not None, "packed rows: a buffer of %d rows belongs to neither stream" % rows
+        return lim[1:2] if padded else lim[0:1]
+
     def gemm(self, a, b, out, **k):
         _count()
         k.setdefault("backend", self.gemm_backend)
+        if getattr(self, "pack_on", False):
+            # Packed rows (bert_fwd): only the first `count` rows of each stream exist; the GEMM schedules whole tiles /
+            # k-blocks up to the count, the count stays on the device.
+            if k.get("epilogue") == EPI_ACCUM:          # weight gradient: the reduction runs over the rows
+                k["k_limit"] = self.row_limit(a.shape[0])
+            elif a.shape[0] == self.Mt + self.Mv:       # joint buffer: text segment, then vision segment
+                k.update(m_limit=self.pack.lim_t[0:1], m_limit2=self.pack.lim_v[0:1], limit_seg_M=self.Mt)
+            else:
+                k["m_limit"] = self.row_limit(a.shape[0], padded=False)
         return ops.gemm(a, b, out, **k)
 
 
@@ -200,13 +226,13 @@ def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, 
         side.wait_stream(torch.cuda.current_stream(rt.device))
         with torch.cuda.stream(side):
             for l_, x_, dy_ in parts:
-                ops.colsum(dy_, rt.g32(*[l.bias for l in _lins(l_)]))
+                ops.colsum(dy_, rt.g32(*[l.bias for l in _lins(l_)]), row_limit=rt.row_limit(dy_.shape[0]))
                 _count()
     for l_, x_, dy_ in parts:
         lins = _lins(l_)
         rt.gemm(dy_, x_, rt.g32(*[l.weight for l in lins]), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)
         if lins[0].bias is not None and not bias_done and side is None:
-            ops.colsum(dy_, rt.g32(*[l.bias for l in lins]))
+            ops.colsum(dy_, rt.g32(*[l.bias for l in lins]), row_limit=rt.row_limit(dy_.shape[0]))
             _count()
     if not need_dx:
         if side is not None:
@@ -380,8 +406,9 @@ def attention_fwd(rt, layer, x, masks):
         ops.attention_fwd(qt, qv, masks[0] if qt is not None else None, masks[1] if qv is not None else None,
                           ctx.get("t") if qt is not None else None, ctx.get("v") if qv is not None else None,
                           lse_t, lse_v, rt.B, rt.T, rt.V, h_, d_, pm, p_t, p_v, seed, rt.attn_backend,
-                          len_t=getattr(rt, "lens", (None, None))[0], len_v=getattr(rt, "lens", (None, None))[1])
+                          len_t=getattr(rt, "lens", (None, None))[0], len_v=getattr(rt, "lens", (None, None))[1], **_pack_cu(rt))
         _count()
+    _zero_pad_rows(rt, ctx)
     y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1]) if (sa.has_text and sa.has_vision) else None
     saved_out = {}
     if joint:
@@ -431,8 +458,9 @@ def attention_bwd(rt, layer, dy, s):
                           lse_t, lse_v, rt.B, rt.T, rt.V, h_, d_, pm, s["p"][0], s["p"][1], s["seed"], rt.attn_backend,
                           dctx_t=dctx.get("t") if qt is not None else None, dctx_v=dctx.get("v") if qv is not None else None,
                           dqkv_t=dqkv.get("t") if qt is not None else None, dqkv_v=dqkv.get("v") if qv is not None else None,
-                          len_t=s["lens"][0], len_v=s["lens"][1])
+                          len_t=s["lens"][0], len_v=s["lens"][1], **_pack_cu(rt))
         _count()
+    _zero_pad_rows(rt, dqkv)
     # dx = dqkv . Wqkv + du   (the residual gradient is folded into the dgrad epilogue)
     if s["joint"] or s["split"]:
         dx_all = linear_bwd(rt, x.all, dqkv["all"], [sa.query, sa.key, sa.value], dx_epilogue=EPI_ADD, aux_in=du["all"],
@@ -742,6 +770,90 @@ def _pool_bwd(rt, pooler, dpooled, pooled, a, dx, L):
     linear_bwd(rt, a, dpre, pooler.dense, dx_epilogue=EPI_ADD, dx_out=rows0, aux_in=rows0)
 
 
+# ---- packed rows ----------------------------------------------------------------------------------------------------
+# The reference computes every padded position (SURVEY.md 8a' item 3: finite garbage nothing reads).  Between the
+# embeddings and the heads the valid rows of each stream are PACKED to the front of its buffer: the GEMMs schedule only
+# the tiles below the device-side count (vb_gemm_args::m_limit / m_limit2 / k_limit), the attention kernels address
+# sample b at cu[b] (vb_attn_args::cu_*), the LayerNorms stop at the count (vb_row_seqs).  Valid rows, losses and
+# parameter gradients are what the padded layout gives; shapes, launches and CUDA graphs stay static.
+PACK_ROWS = os.environ.get("VOLTA_B200_PACK_ROWS", "1") != "0"
+
+
+class _Pack:
+    pass
+
+
+def _pack_supported(rt, bert, keep_layers):
+    if not (PACK_ROWS and SKIP_PADDING) or keep_layers or rt.precision != "bf16":
+        return False
+    if rt.gemm_backend == _lib.GEMM_SIMT or rt.attn_backend == _lib.ATTN_SIMT or not torch.cuda.is_available():
+        return False
+    if rt.Mt % 256 != 0 or rt.Mt == rt.Mv or rt.Mv == 0 or rt.T > 160 or rt.V > 160:
+        return False
+    if bert.config.fusion_method == "vl-bert_vqa":
+        return False
+    for n, layer in enumerate(bert.encoder.layer):
+        if bert.encoder.num2type[n] == "attn":
+            sa = layer.attention_self
+            if sa.share_layer or (sa.has_text and sa.attention_head_size not in (64, 128)) or \
+                    (sa.has_vision and sa.v_attention_head_size not in (64, 128)):
+                return False
+        elif layer.intermediate.share_layer:
+            return False
+    return True
+
+
+def _make_pack(rt):
+    """Packing plan of both streams from the per-sample lengths (rows below the length are kept, holes included)."""
+    pk = _Pack()
+    for tag, ln, L in (("t", rt.lens[0], rt.T), ("v", rt.lens[1], rt.V)):
+        rows = rt.B * L
+        keep = (torch.arange(L, device=rt.device, dtype=torch.int32)[None, :] < ln[:, None]).reshape(-1)
+        keys = keep.to(torch.int64) - 1                                  # 0 = keep, -1 = drop
+        lim = rt.empty(2, dtype=torch.int32)
+        src, pos = rt.empty(rows, dtype=torch.int32), rt.empty(rows, dtype=torch.int32)
+        ops.compact_plan(keys, 256, lim, src, pos, rt.empty(rows, dtype=torch.int64))
+        cu = (torch.cumsum(ln, 0, dtype=torch.int32) - ln).contiguous()  # first packed row of every sample
+        setattr(pk, "lim_" + tag, lim); setattr(pk, "src_" + tag, src); setattr(pk, "pos_" + tag, pos); setattr(pk, "cu_" + tag, cu)
+        _count()
+    return pk
+
+
+def _pack_pair(rt, x):
+    pk = rt.pack
+    y = Pair.alloc(rt, x.t.shape[0], x.t.shape[1], x.v.shape[0], x.v.shape[1])
+    ops.compact_gather(x.t, pk.src_t, pk.lim_t, y.t)
+    ops.compact_gather(x.v, pk.src_v, pk.lim_v, y.v)
+    _count(2)
+    return y
+
+
+def _unpack_pair(rt, x):
+    pk = rt.pack
+    y = Pair.alloc(rt, x.t.shape[0], x.t.shape[1], x.v.shape[0], x.v.shape[1])
+    ops.compact_scatter(x.t, pk.pos_t, y.t)
+    ops.compact_scatter(x.v, pk.pos_v, y.v)
+    _count(2)
+    return y
+
+
+def _pack_cu(rt):
+    if not getattr(rt, "pack_on", False):
+        return {}
+    return dict(cu_t=rt.pack.cu_t, cu_v=rt.pack.cu_v)
+
+
+def _zero_pad_rows(rt, bufs):
+    """Rows between a stream's count and its 256-row padding are read by the tile-granular weight-gradient GEMMs: the
+    attention kernels write per sample, so those rows of their outputs are zeroed here."""
+    if not getattr(rt, "pack_on", False):
+        return
+    for tag, lim in (("t", rt.pack.lim_t), ("v", rt.pack.lim_v)):
+        if bufs.get(tag) is not None:
+            ops.zero_rows(bufs[tag], lim[0:1], lim[1:2])
+            _count()
+
+
 def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
     cfg = bert.config
     x, s_emb = embeddings_fwd(rt, bert, ids, feat, loc, seg)
@@ -751,6 +863,11 @@ def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
         # per-sample valid lengths, once per forward: the attention kernels skip whole tiles of trailing padding
         rt.lens = tuple(ops.mask_lengths(m, rt.empty(rt.B, dtype=torch.int32)) for m in masks)
         _count(2)
+    rt.pack, rt.pack_on = None, False
+    if _pack_supported(rt, bert, keep_layers):
+        rt.pack = _make_pack(rt)
+        x = _pack_pair(rt, x)
+        rt.pack_on = True
     tape, layers = [], []
     for n, layer in enumerate(bert.encoder.layer):
         if bert.encoder.num2type[n] == "attn":
@@ -760,6 +877,9 @@ def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
         tape.append(saved if rt.grad_enabled else None)
         if keep_layers:
             layers.append(x)
+    if rt.pack is not None:
+        rt.pack_on = False
+        x = _unpack_pair(rt, x)
     pooled_t = pooled_v = None
     s_pool = {}
     fm = cfg.fusion_method
@@ -776,7 +896,7 @@ def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
     if fm not in ("none", "text", "vl-bert_vqa"):
         pooled_v, a = _pool_fwd(rt, bert.v_pooler, x.v, rt.V)
         s_pool["v"] = (pooled_v, a, None)
-    return x, pooled_t, pooled_v, layers, dict(emb=s_emb, tape=tape, pool=s_pool, x=x)
+    return x, pooled_t, pooled_v, layers, dict(emb=s_emb, tape=tape, pool=s_pool, x=x, pack=rt.pack, lens=rt.lens)
 
 
 def bert_bwd(rt, bert, s, dx, dpooled_t, dpooled_v):
@@ -796,6 +916,11 @@ def bert_bwd(rt, bert, s, dx, dpooled_t, dpooled_v):
         _pool_bwd(rt, bert.v_pooler, dpooled_v, pooled, a, dx.v, rt.V)
     if hasattr(bert, "t_pooler"):
         _notify_progress(rt, bert.t_pooler)
+    rt.pack, rt.pack_on = s.get("pack"), False
+    if rt.pack is not None:       # the encoder ran on packed rows: so does its backward
+        rt.lens = s["lens"]
+        dx = _pack_pair(rt, dx)
+        rt.pack_on = True
     for n in range(len(bert.encoder.layer) - 1, -1, -1):
         layer = bert.encoder.layer[n]
         if bert.encoder.num2type[n] == "attn":
@@ -804,6 +929,9 @@ def bert_bwd(rt, bert, s, dx, dpooled_t, dpooled_v):
             dx = ffn_bwd(rt, layer, dx, s["tape"][n])
         s["tape"][n] = None  # free activations as the backward retires them
         _notify_progress(rt, layer)
+    if rt.pack is not None:
+        rt.pack_on = False
+        dx = _unpack_pair(rt, dx)
     embeddings_bwd(rt, bert, dx, s["emb"])
 
 

@@ -49,7 +49,7 @@ def require_cuda(*ts):
 # --------------------------------------------------------------------------- GEMM
 def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
          dropout_p=0.0, seed=0, offset=0, backend=_lib.GEMM_AUTO, split_k=0, M=None, N=None, K=None, b2=None, bias2=None,
-         split_M=0, m_limit=None, k_limit=None):
+         split_M=0, m_limit=None, k_limit=None, m_limit2=None, limit_seg_M=0):
     """out[M,N] = epilogue(opA . opB^T); see vb_gemm in include/volta_b200.h.  m_limit / k_limit: int32 device tensors
     (one element) holding the number of rows / reduction elements that carry data (see vb_compact_plan)."""
     require_cuda(a, b, out)
@@ -84,15 +84,18 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bia
     if b2 is not None:   # row-split launch: rows >= split_M use b2 / bias2
         assert b2.shape == b.shape and b2.stride() == b.stride() and b2.dtype == b.dtype and 0 < split_M < M
         g.B2, g.bias2, g.split_M = b2.data_ptr(), _ptr(bias2), int(split_M)
-    for name, lim in (("m_limit", m_limit), ("k_limit", k_limit)):
+    for name, lim in (("m_limit", m_limit), ("k_limit", k_limit), ("m_limit2", m_limit2)):
         if lim is not None:
             assert lim.dtype == torch.int32 and lim.is_cuda and lim.numel() >= 1
             setattr(g, name, lim.data_ptr())
+    g.limit_seg_M = int(limit_seg_M)
     _lib.call("vb_gemm", C.byref(g), _stream())
     if GEMM_BENCH is not None:  # bench.py: device time of this launch, repeated back to back (no host gaps)
         ms = C.c_float(0.0)
         _lib.call("vb_gemm_bench", C.byref(g), _stream(), 5, C.byref(ms))
         Me = M if m_limit is None else min(M, int(m_limit[0].item()))   # executed extents of a device-limited launch
+        if limit_seg_M:
+            Me = min(limit_seg_M, Me) + (M - limit_seg_M if m_limit2 is None else min(M - limit_seg_M, int(m_limit2[0].item())))
         Ke = K if k_limit is None else min(K, int(k_limit[0].item()))
         GEMM_BENCH.append((2.0 * Me * N * Ke, ms.value, _lib.load().vb_gemm_backend(C.byref(g)) == _lib.GEMM_TC,
                            "M%d N%d K%d a%d b%d epi%d" % (M, N, K, a_kmajor, b_kmajor, epilogue)))
@@ -157,7 +160,7 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, out_scale=1.0, dx
 
 # --------------------------------------------------------------------------- attention
 def _attn_args(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, Lv, heads, d, pair_mask, p_t, p_v,
-               seed, backend, dctx_t=None, dctx_v=None, dqkv_t=None, dqkv_v=None, len_t=None, len_v=None):
+               seed, backend, dctx_t=None, dctx_v=None, dqkv_t=None, dqkv_v=None, len_t=None, len_v=None, cu_t=None, cu_v=None):
     a = _lib.AttnArgs()
     ref = qkv_t if qkv_t is not None else qkv_v
     require_cuda(ref)
@@ -179,7 +182,18 @@ def _attn_args(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, 
     for ln in (len_t, len_v):
         assert ln is None or (ln.dtype == torch.int32 and ln.numel() >= B)
     a.len_t, a.len_v = _ptr(len_t if qkv_t is not None else None), _ptr(len_v if qkv_v is not None else None)
+    for cu in (cu_t, cu_v):
+        assert cu is None or (cu.dtype == torch.int32 and cu.numel() >= B)
+    a.cu_t, a.cu_v = _ptr(cu_t if qkv_t is not None else None), _ptr(cu_v if qkv_v is not None else None)
     return a
+
+
+def zero_rows(buf, row_begin, row_end, row_offset=0, max_rows=256):
+    """buf[row_offset + *row_begin : row_offset + *row_end] = 0 with device-side bounds (int32 tensors)."""
+    _, cols, ld = _rows2d(buf)
+    _lib.call("vb_zero_rows", buf.data_ptr(), ld, cols, row_begin.data_ptr(), row_end.data_ptr(), int(row_offset), int(max_rows),
+              dt(buf), _stream())
+    return buf
 
 
 def mask_lengths(mask, out):
