@@ -18,6 +18,7 @@ The first call with a new signature runs eagerly (it fills the host-side caches 
 attributes); the second call captures.  A forward issued while the previous forward's backward is still pending, or
 any call without labels / without grad, takes the eager path.
 """
+import gc
 import os
 
 import torch
@@ -64,11 +65,16 @@ class GraphedPretrainStep:
         stream = torch.cuda.Stream(device=self.device)
         stream.wait_stream(torch.cuda.current_stream(self.device))
         lib.vb_set_seed_pointer(self.seed_dev.data_ptr())
+        # Nothing may free device memory or destroy a graph while the capture runs: collect dead objects now (models of
+        # earlier calls hold graphs in reference cycles) and keep the cyclic collector off until the capture has ended.
+        gc.collect()
+        gc_was_on = gc.isenabled()
+        gc.disable()
         try:
             with torch.cuda.stream(stream):
                 n0 = engine.launch_count
                 g = torch.cuda.CUDAGraph()
-                g.capture_begin(pool=pool)
+                g.capture_begin(pool=pool, capture_error_mode="thread_local")
                 rt = Runtime(model, self.device, B, T, V, model.training, grad=True, seed_base=0)
                 rt.quiet = True
                 seg_ = torch.zeros_like(ids) if seg is None else seg
@@ -84,14 +90,14 @@ class GraphedPretrainStep:
                 n0 = engine.launch_count
                 cut = engine.progress_cut_fn(model)
                 state = {"g": torch.cuda.CUDAGraph()}
-                state["g"].capture_begin(pool=pool)
+                state["g"].capture_begin(pool=pool, capture_error_mode="thread_local")
 
                 def on_progress(frontier):
                     if cut is not None and cut(frontier):
                         state["g"].capture_end()
                         self.bwd_segments.append((state["g"], frontier))
                         state["g"] = torch.cuda.CUDAGraph()
-                        state["g"].capture_begin(pool=pool)
+                        state["g"].capture_begin(pool=pool, capture_error_mode="thread_local")
                 rt.quiet = False
                 rt.progress_override = on_progress
                 with engine.backward_sm_limit(model):   # grid sizes are baked into the captured launches
@@ -104,6 +110,8 @@ class GraphedPretrainStep:
                 engine.launch_count -= self.n_fwd + self.n_bwd  # capture launches nothing; replays are counted
         finally:
             lib.vb_set_seed_pointer(None)
+            if gc_was_on:
+                gc.enable()
         torch.cuda.current_stream(self.device).wait_stream(stream)
         self._keep = (rt, s_bert, s_heads, x)  # activations live in the graphs' private pool
         self._ptrs = self._store_ptrs()
