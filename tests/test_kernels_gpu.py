@@ -37,6 +37,19 @@ def test_gemm_forward_bias(backend, M, N, K):
     assert rel(out.float(), ref) < 6e-3
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("M,N,K", [(256, 2, 1024), (500, 1, 1024), (37, 8, 200)])
+def test_gemm_skinny_outputs(M, N, K, dtype):
+    """N <= 8 (ITM / retrieval logit heads): warp-per-row kernel behind the SIMT back-end."""
+    a, w, bias = rnd(M, K, dtype=dtype), rnd(N, K, dtype=dtype, scale=0.05), rnd(8, dtype=torch.float32)[:N]
+    out = torch.zeros(M, 8, dtype=dtype, device=DEV)[:, :N]
+    ops.gemm(a, w, out, epilogue=_lib.EPI_BIAS, bias=bias, backend=_lib.GEMM_AUTO)
+    assert rel(out.float(), a.float() @ w.float().t() + bias) < (6e-3 if dtype == torch.bfloat16 else 1e-5)
+    out2 = torch.zeros(M, 8, dtype=dtype, device=DEV)[:, :N]
+    ops.gemm(a, w, out2, backend=_lib.GEMM_SIMT)
+    assert rel(out2.float(), a.float() @ w.float().t()) < (6e-3 if dtype == torch.bfloat16 else 1e-5)
+
+
 @pytest.mark.parametrize("epi", ["none", "gelu", "relu", "res", "mul", "add", "drelu", "bias_add"])
 @pytest.mark.parametrize("odt", [torch.bfloat16, torch.float32])
 def test_gemm_tc_epilogues(epi, odt):

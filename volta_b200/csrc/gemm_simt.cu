@@ -125,11 +125,50 @@ int fill_epi_params(const vb_gemm_args& a, EpiParams& p) {
   return 0;
 }
 
+namespace simt {
+// N <= 8 output columns (the ITM / task logit heads: [B, 1024] x [2, 1024]^T): one warp per output row, the lanes
+// stride over K, all N dot products in registers.  The tiled kernel above would run such a problem on 4 blocks.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(const T* __restrict__ A, int64_t lda, const T* __restrict__ B, int64_t ldb, int64_t M, int N, int64_t K,
+                   EpiParams p) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m = (int64_t)blockIdx.x * 8 + warp;
+  if (m >= M) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t k = lane; k < K; k += 32) {
+    const float av = to_f<T>(A[m * lda + k]);
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n < N) acc[n] = fmaf(av, to_f<T>(B[n * ldb + k]), acc[n]);
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = warp_sum(acc[n]);
+  if (lane == 0) {
+    for (int n = 0; n < N; ++n) {
+      float pre = 0.f;
+      const float o = epilogue_scalar(p, acc[n], p.epilogue == VB_EPI_BIAS ? p.bias[n] : 0.f, 0.f, m, n, pre);
+      if (p.d_bf16) reinterpret_cast<bf16*>(p.D)[m * p.ldd + n] = from_f<bf16>(o);
+      else reinterpret_cast<float*>(p.D)[m * p.ldd + n] = o;
+    }
+  }
+}
+}  // namespace simt
+
 int gemm_simt_launch(const vb_gemm_args& a, cudaStream_t stream) {
   VB_REQUIRE(a.B2 == nullptr || a.split_M <= 0, VB_ERR_UNSUPPORTED, "gemm: row-split launches need the tcgen05 back-end");
   EpiParams p;
   int rc = fill_epi_params(a, p);
   if (rc) return rc;
+  if (a.N <= 8 && a.a_kmajor && a.b_kmajor && (a.epilogue == VB_EPI_NONE || a.epilogue == VB_EPI_BIAS) && !a.m_limit &&
+      !a.k_limit && !a.m_limit2) {
+    const unsigned grid = (unsigned)ceil_div(a.M, 8);
+    if (a.ab_dtype == VB_BF16)
+      simt::gemm_skinny_kernel<bf16><<<grid, 256, 0, stream>>>((const bf16*)a.A, a.lda, (const bf16*)a.B, a.ldb, a.M, (int)a.N, a.K, p);
+    else
+      simt::gemm_skinny_kernel<float><<<grid, 256, 0, stream>>>((const float*)a.A, a.lda, (const float*)a.B, a.ldb, a.M, (int)a.N, a.K, p);
+    return check_launch("gemm_skinny_kernel");
+  }
   simt::Operand A{a.A, a.a_kmajor ? a.lda : 1, a.a_kmajor ? 1 : a.lda};
   simt::Operand B{a.B, a.b_kmajor ? a.ldb : 1, a.b_kmajor ? 1 : a.ldb};
   dim3 grid((unsigned)ceil_div(a.N, simt::TN), (unsigned)ceil_div(a.M, simt::TM));

@@ -662,9 +662,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (p.m_limit2) live_b = min(live_b, (max(*p.m_limit2, 0) + BM * CG - 1) / (BM * CG));
   num_m_blocks = live_a + live_b;
   auto m_of = [&](int m_idx) { return m_idx < live_a ? m_idx : seg_blk + (m_idx - live_a); };
+  int kb_per_split = p.kb_per_split;
   if (p.k_limit) {
+    // keep the number of slices the host planned for the machine, shorten them evenly to the live reduction length
     kb_total = min(kb_total, (max(*p.k_limit, 0) + BK - 1) / BK);
-    split_k = (kb_total + p.kb_per_split - 1) / p.kb_per_split;   // trailing slices are empty: not scheduled at all
+    kb_per_split = max(1, (kb_total + p.split_k - 1) / p.split_k);
+    split_k = (kb_total + kb_per_split - 1) / kb_per_split;
   }
   const int64_t tiles = (int64_t)num_m_blocks * p.num_n_blocks;   // tiles of (CG*128) x BN
   const int64_t total_work = tiles * split_k;
@@ -708,8 +711,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (m_blk * CG + (int)rank) * BM;
       const int n0 = n_blk * BN + (int)rank * (int)C::B_ROWS;
       const CUtensorMap* mapB = (m_blk >= p.split_m_blk) ? &tmB2 : &tmB;   // row-split launch: second stream's weights
-      const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb_total, kb0 + kb_per_split);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         uint32_t fb = full_bar(stage);
@@ -746,8 +749,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int q = 0;
     if (first < total_work) for (int64_t w = first;; ++it) {
       const int split = (int)(w % split_k);
-      const int kb0 = split * p.kb_per_split;
-      const int kb1 = min(kb_total, kb0 + p.kb_per_split);
+      const int kb0 = split * kb_per_split;
+      const int kb1 = min(kb_total, kb0 + kb_per_split);
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tcgen05_fence_after();
