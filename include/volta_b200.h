@@ -164,13 +164,17 @@ typedef struct vb_row_seqs {
   const int32_t* len_b; int32_t L_b;
 } vb_row_seqs;
 
+/* gamma2 / beta2 / split_row (NULL / 0 = one LayerNorm): rows [split_row, rows) belong to a SECOND LayerNorm module -
+ * the vision rows of a joint text+vision buffer (volta/encoders.py:392 v_LayerNorm) - normalised by the same launch with
+ * their own affine parameters; the backward accumulates their dgamma2 / dbeta2 / dbias2 separately. */
 int vb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
                      int64_t rows, int32_t H, float eps, float out_scale, int32_t accum, const vb_row_seqs* seqs,
-                     int32_t dtype, void* stream);
+                     const float* gamma2, const float* beta2, int64_t split_row, int32_t dtype, void* stream);
 int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                      void* dx, float* dgamma, float* dbeta, int64_t rows, int32_t H, float out_scale,
                      void* dx_drop, float dropout_p, uint64_t seed, uint64_t offset, float* dbias,
-                     const vb_row_seqs* seqs, int32_t dtype, void* stream);
+                     const vb_row_seqs* seqs, const float* gamma2, float* dgamma2, float* dbeta2, float* dbias2,
+                     int64_t split_row, int32_t dtype, void* stream);
 
 /* ---- gated attention --------------------------------------------------
  * Replaces BertGatedSelfAttention.forward after the Q/K/V projections
@@ -332,9 +336,11 @@ int vb_compact_gather(const void* src, int64_t ld_src, const int32_t* src_index,
 int vb_compact_scatter(const void* src_c, int64_t ld_src, const int32_t* pos, void* dst, int64_t ld_dst, int64_t rows,
                        int32_t cols, int32_t dtype, void* stream);
 /* Zero rows [row_offset + *row_begin, row_offset + *row_end) of buf (device-side bounds, at most max_rows rows): the
- * tail between a packed row count and its 256-row padding, which the tile-granular GEMMs read. */
+ * tail between a packed row count and its 256-row padding, which the tile-granular GEMMs read.  An optional second
+ * range (row_begin2 / row_end2 / row_offset2, NULL = none) of the same buffer is cleared by the same launch. */
 int vb_zero_rows(void* buf, int64_t ld, int32_t cols, const int32_t* row_begin, const int32_t* row_end, int64_t row_offset,
-                 int32_t max_rows, int32_t dtype, void* stream);
+                 const int32_t* row_begin2, const int32_t* row_end2, int64_t row_offset2, int32_t max_rows, int32_t dtype,
+                 void* stream);
 /* out[r,:] = a[idx[r],:] (gather rows; idx int64) and its scatter-add adjoint */
 int vb_gather_rows(const void* a, int64_t lda, const int64_t* idx, void* out, int64_t ldo, int64_t rows,
                    int64_t cols, int32_t dtype, void* stream);

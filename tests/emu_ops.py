@@ -112,7 +112,26 @@ def _dead_rows(seqs, rows):
     return torch.cat(parts)
 
 
-def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=1.0, accum=False, seqs=None):
+def _seq_slice(seqs, lo, hi, rows):
+    """vb_row_seqs restricted to the row range [lo, hi) that starts a segment (emulation of two-stream launches)."""
+    if seqs is None:
+        return None
+    len_a, L_a, rows_a, len_b, L_b = seqs
+    if lo == 0:
+        assert hi == rows_a
+        return (len_a, L_a, rows_a, None, 0)
+    assert lo == rows_a
+    return None if len_b is None else (len_b, L_b, hi - lo, None, 0)
+
+
+def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=1.0, accum=False, seqs=None, second=None,
+                  split_row=0):
+    if second is not None and 0 < split_row < x.shape[0]:
+        rows = x.shape[0]
+        for lo, hi, g_, b_ in ((0, split_row, gamma, beta), (split_row, rows, second[0], second[1])):
+            layernorm_fwd(x[lo:hi], g_, b_, y[lo:hi], None if mean is None else mean[lo:hi], None if rstd is None else rstd[lo:hi],
+                          eps, out_scale, accum, _seq_slice(seqs, lo, hi, rows))
+        return y
     dead = None if accum else _dead_rows(seqs, x.shape[0])
     if dead is not None:
         y2, m2, r2 = torch.empty_like(y), torch.empty(x.shape[0]), torch.empty(x.shape[0])
@@ -139,8 +158,15 @@ def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, out_scale=1.0, dx_drop=None, dropout_p=0.0, seed=0,
-                  offset=0, dbias=None, seqs=None):
+                  offset=0, dbias=None, seqs=None, second=None, split_row=0):
     assert dropout_p == 0.0
+    if second is not None and 0 < split_row < x.shape[0]:
+        rows = x.shape[0]
+        g2, dg2, db2, dbi2 = second
+        for lo, hi, g_, dg_, db_, dbi_ in ((0, split_row, gamma, dgamma, dbeta, dbias), (split_row, rows, g2, dg2, db2, dbi2)):
+            layernorm_bwd(dy[lo:hi], x[lo:hi], mean[lo:hi], rstd[lo:hi], g_, dx[lo:hi], dg_, db_, out_scale, None, 0.0, 0, 0, dbi_,
+                          _seq_slice(seqs, lo, hi, rows))
+        return dx
     dead = _dead_rows(seqs, x.shape[0])
     if dead is not None:   # skipped rows: no contribution, zero dx
         dy = torch.where(dead[:, None], torch.zeros_like(dy), dy)
@@ -419,8 +445,10 @@ def compact_gather(src, src_index, limits, dst):
     return dst
 
 
-def zero_rows(buf, row_begin, row_end, row_offset=0, max_rows=256):
+def zero_rows(buf, row_begin, row_end, row_offset=0, max_rows=256, second=None):
     buf[row_offset + int(row_begin[0]):row_offset + int(row_end[0])] = 0
+    if second is not None:
+        buf[second[2] + int(second[0][0]):second[2] + int(second[1][0])] = 0
     return buf
 
 

@@ -219,6 +219,11 @@ def test_zero_rows_device_bounds():
     ref = torch.full_like(buf, 3.0)
     ref[401:612] = 0
     assert torch.equal(buf, ref)
+    lim2 = torch.tensor([5, 9], dtype=torch.int32, device=DEV)
+    ops.zero_rows(buf, lim2[0:1], lim2[1:2], second=(lim2[0:1], lim2[1:2], 650))   # two ranges, one launch
+    ref[5:9] = 0
+    ref[655:659] = 0
+    assert torch.equal(buf, ref)
 
 
 def test_compact_plan_gather_scatter_and_limited_criterion():
@@ -376,6 +381,38 @@ def test_layernorm_skips_trailing_padding_rows(dropout):
         assert bool((out["skip"][i][~live] == 0).all())
     for i in (3, 4, 5):
         assert rel(out["skip"][i], out["full"][i]) < 1e-5   # fp32 atomics: order only
+
+
+@pytest.mark.parametrize("dropout", [0.0, 0.1])
+def test_layernorm_two_streams_in_one_launch(dropout):
+    """gamma2 / split_row: the vision rows of a joint buffer are normalised by the same launch with their own module's
+    parameters; against two separate launches: identical rows, separate gradient sums (fp32 atomics: order only)."""
+    Mt, Mv, H = 512, 777, 768
+    rows = Mt + Mv
+    x, dy = rnd(rows, H, scale=2.0), rnd(rows, H, seed=1)
+    g1, b1 = 1 + rnd(H, dtype=torch.float32, scale=0.1), rnd(H, dtype=torch.float32, scale=0.1)
+    g2, b2 = 1 + rnd(H, dtype=torch.float32, scale=0.1, seed=2), rnd(H, dtype=torch.float32, scale=0.1, seed=3)
+
+    def run(merged):
+        y, dx, dxd = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        mean, rstd = torch.zeros(rows, device=DEV), torch.zeros(rows, device=DEV)
+        sums = [torch.zeros(H, device=DEV) for _ in range(6)]   # dg1, db1, dbias1, dg2, db2, dbias2
+        dd = dxd if dropout else None
+        if merged:
+            ops.layernorm_fwd(x, g1, b1, y, mean, rstd, second=(g2, b2), split_row=Mt)
+            ops.layernorm_bwd(dy, x, mean, rstd, g1, dx, sums[0], sums[1], dx_drop=dd, dropout_p=dropout, seed=3, dbias=sums[2],
+                              second=(g2, sums[3], sums[4], sums[5]), split_row=Mt)
+        else:
+            for lo, hi, g_, b_, k, off in ((0, Mt, g1, b1, 0, 0), (Mt, rows, g2, b2, 3, Mt * H)):
+                ops.layernorm_fwd(x[lo:hi], g_, b_, y[lo:hi], mean[lo:hi], rstd[lo:hi])
+                ops.layernorm_bwd(dy[lo:hi], x[lo:hi], mean[lo:hi], rstd[lo:hi], g_, dx[lo:hi], sums[k], sums[k + 1],
+                                  dx_drop=None if dd is None else dd[lo:hi], dropout_p=dropout, seed=3, offset=off, dbias=sums[k + 2])
+        return y, dx, (dxd if dropout else dx), sums
+    ya, dxa, dda, sa = run(True)
+    yb, dxb, ddb, sb = run(False)
+    assert torch.equal(ya, yb) and torch.equal(dxa, dxb) and torch.equal(dda, ddb)
+    for a, b in zip(sa, sb):
+        assert rel(a, b) < 1e-5
 
 
 def test_layernorm_scale_accumulate():

@@ -58,8 +58,8 @@ SIGNATURES = {
     "vb_gemm": (_i32, [C.POINTER(GemmArgs), _vp]),
     "vb_gemm_backend": (_i32, [C.POINTER(GemmArgs)]),
     "vb_gemm_bench": (_i32, [C.POINTER(GemmArgs), _vp, _i32, C.POINTER(C.c_float)]),
-    "vb_layernorm_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _i32, _vp, _i32, _vp]),
-    "vb_layernorm_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _vp, _f, _u64, _u64, _vp, _vp, _i32, _vp]),
+    "vb_layernorm_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _f, _i32, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "vb_layernorm_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _vp, _f, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "vb_attention_fwd": (_i32, [C.POINTER(AttnArgs), _vp]),
     "vb_attention_bwd": (_i32, [C.POINTER(AttnArgs), _vp]),
     "vb_embed_gather_fwd": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i32, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
@@ -76,7 +76,7 @@ SIGNATURES = {
     "vb_loss_finalize": (_i32, [_vp, _vp, _vp, _i32, _vp]),
     "vb_eltwise": (_i32, [_i32, _vp, _i32, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _f, _f, _u64, _u64, _vp]),
     "vb_colsum": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
-    "vb_zero_rows": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _i32, _i32, _vp]),
+    "vb_zero_rows": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp]),
     "vb_mask_lengths": (_i32, [_vp, _i32, _i32, _vp, _vp]),
     "vb_compact_plan": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vb_compact_gather": (_i32, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i32, _i32, _vp]),

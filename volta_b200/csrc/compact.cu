@@ -115,8 +115,10 @@ scatter_kernel(const T* __restrict__ src_c, int64_t ld_src, const int32_t* __res
 template <typename T>
 __global__ void __launch_bounds__(256)
 zero_rows_kernel(T* __restrict__ buf, int64_t ld, int cols, const int32_t* __restrict__ row_begin,
-                 const int32_t* __restrict__ row_end, int64_t row_offset, bool vec) {
+                 const int32_t* __restrict__ row_end, int64_t row_offset, const int32_t* __restrict__ row_begin2,
+                 const int32_t* __restrict__ row_end2, int64_t row_offset2, bool vec) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.y == 1) { row_begin = row_begin2; row_end = row_end2; row_offset = row_offset2; }   // second row range
   const int64_t r = (int64_t)*row_begin + (int64_t)blockIdx.x * 8 + warp;
   if (r >= *row_end) return;
   T* d = buf + (row_offset + r) * ld;
@@ -178,15 +180,19 @@ int vb_compact_scatter(const void* src_c, int64_t ld_src, const int32_t* pos, vo
 }
 
 int vb_zero_rows(void* buf, int64_t ld, int32_t cols, const int32_t* row_begin, const int32_t* row_end, int64_t row_offset,
-                 int32_t max_rows, int32_t dtype, void* stream) {
+                 const int32_t* row_begin2, const int32_t* row_end2, int64_t row_offset2, int32_t max_rows, int32_t dtype,
+                 void* stream) {
   VB_REQUIRE(buf && row_begin && row_end && cols > 0 && ld >= cols && max_rows > 0, VB_ERR_ARG, "zero_rows: bad arguments");
-  const unsigned grid = (unsigned)vb::ceil_div((int64_t)max_rows, 8);
+  VB_REQUIRE((row_begin2 == nullptr) == (row_end2 == nullptr), VB_ERR_ARG, "zero_rows: second range needs both bounds");
+  const dim3 grid((unsigned)vb::ceil_div((int64_t)max_rows, 8), row_begin2 ? 2u : 1u);
   using namespace vb::compact;
   if (dtype == VB_BF16)
     zero_rows_kernel<vb::bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((vb::bf16*)buf, ld, cols, row_begin, row_end, row_offset,
+                                                                     row_begin2, row_end2, row_offset2,
                                                                      vec_ok<vb::bf16>(buf, ld, buf, ld, cols));
   else
     zero_rows_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((float*)buf, ld, cols, row_begin, row_end, row_offset,
+                                                                  row_begin2, row_end2, row_offset2,
                                                                   vec_ok<float>(buf, ld, buf, ld, cols));
   return vb::check_launch("zero_rows_kernel");
 }

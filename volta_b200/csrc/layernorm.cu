@@ -37,11 +37,13 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(WARPS * 32)
 ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
               T* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out, int64_t rows, int H,
-              float eps, float out_scale, int accum, Seqs seqs) {
+              float eps, float out_scale, int accum, Seqs seqs, const float* __restrict__ gamma2,
+              const float* __restrict__ beta2, int64_t split_row) {
   pdl_enter();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * WARPS + warp;
   if (row >= rows) return;
+  if (row >= split_row) { gamma = gamma2; beta = beta2; }   // second stream of a joint buffer: its own affine parameters
   if (!accum && row_dead(seqs, row)) {   // trailing padding of its sample: zeros, nothing read
     if (lane == 0) {
       if (mean_out) mean_out[row] = 0.f;
@@ -115,13 +117,27 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
               const float* __restrict__ rstd, const float* __restrict__ gamma, T* __restrict__ dx,
               float* __restrict__ dgamma, float* __restrict__ dbeta, int64_t rows, int H, float out_scale,
               T* __restrict__ dx_drop, uint32_t drop_thresh, float drop_scale, uint64_t seed_in, uint64_t offset,
-              float* __restrict__ dbias, const uint64_t* __restrict__ seed_ptr, int early_fetch, Seqs seqs) {
+              float* __restrict__ dbias, const uint64_t* __restrict__ seed_ptr, int early_fetch, Seqs seqs,
+              const float* __restrict__ gamma2, float* __restrict__ dgamma2, float* __restrict__ dbeta2,
+              float* __restrict__ dbias2, int64_t split_row, int blocks_a) {
   pdl_enter();
   const uint64_t seed = effective_seed(seed_in, seed_ptr);
   extern __shared__ __align__(16) float red[];  // [3 or 2][WARPS][H] partial sums, then gamma [H]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
-  const int64_t total_warps = (int64_t)gridDim.x * WARPS;
+  // Two streams in one launch (rows [0, split_row) and [split_row, rows) with their own gamma and gradient sums): the
+  // first blocks_a blocks walk the first range, the others the second, so a block's column sums belong to one stream.
+  int64_t row_begin = 0, row_end = rows;
+  int blk = blockIdx.x, nblk = gridDim.x;
+  if (split_row < rows) {
+    if (blk < blocks_a) { row_end = split_row; nblk = blocks_a; }
+    else {
+      row_begin = split_row; blk -= blocks_a; nblk -= blocks_a;
+      gamma = gamma2; dgamma = dgamma2; dbeta = dbeta2; dbias = dbias2;
+    }
+  }
+  const int64_t warp_global = row_begin + (int64_t)blk * WARPS + warp;
+  const int64_t total_warps = (int64_t)nblk * WARPS;
+  rows = row_end;
   float* sg = red + warp * H;
   float* sb = red + (WARPS + warp) * H;
   float* sx = red + (2 * WARPS + warp) * H;
@@ -263,12 +279,13 @@ ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __
 
 template <typename T>
 static int fwd_dispatch(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                        int64_t rows, int H, float eps, float out_scale, int accum, Seqs seqs, cudaStream_t st) {
+                        int64_t rows, int H, float eps, float out_scale, int accum, Seqs seqs, const float* gamma2,
+                        const float* beta2, int64_t split_row, cudaStream_t st) {
   const int nv = (H + 255) / 256;
   const unsigned grid = (unsigned)ceil_div(rows, WARPS);
 #define VB_LN_FWD(NV_)                                                                                             \
   launch_pdl(ln_fwd_kernel<T, NV_>, dim3(grid), dim3(WARPS * 32), 0, st, (const T*)x, gamma, beta, (T*)y, mean, rstd, rows, H, \
-             eps, out_scale, accum, seqs)
+             eps, out_scale, accum, seqs, gamma2, beta2, split_row)
   switch (nv) {
     case 1: VB_LN_FWD(1); break;
     case 2: VB_LN_FWD(2); break;
@@ -285,13 +302,19 @@ static int fwd_dispatch(const void* x, const float* gamma, const float* beta, vo
 template <typename T>
 static int bwd_dispatch(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
                         void* dx, float* dgamma, float* dbeta, int64_t rows, int H, float out_scale, void* dx_drop,
-                        float p, uint64_t seed, uint64_t offset, float* dbias, Seqs seqs, cudaStream_t st) {
+                        float p, uint64_t seed, uint64_t offset, float* dbias, Seqs seqs, const float* gamma2,
+                        float* dgamma2, float* dbeta2, float* dbias2, int64_t split_row, cudaStream_t st) {
   const int nv = (H + 255) / 256;
   const bool extra = (dx_drop != nullptr) || (dbias != nullptr);
   static int sms = 0;
   if (!sms) { int dev; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
   // enough rows per warp to amortise the column reduction, enough blocks to fill the machine
   int64_t grid = std::min<int64_t>(ceil_div(rows, WARPS), (int64_t)sms * 2);  // two resident blocks per SM
+  int blocks_a = (int)grid;
+  if (split_row < rows) {   // blocks in proportion to the two row ranges, at least one each
+    grid = std::max<int64_t>(grid, 2);
+    blocks_a = (int)std::min<int64_t>(grid - 1, std::max<int64_t>(1, (grid * split_row + rows / 2) / rows));
+  }
   const size_t smem = ((size_t)(extra ? 3 : 2) * WARPS + 1) * H * sizeof(float);
   const uint32_t thresh = dx_drop ? dropout_thresh(p) : 0u;
   const float scale = 1.f / (1.f - p);
@@ -303,7 +326,8 @@ static int bwd_dispatch(const void* dy, const void* x, const float* mean, const 
       cudaFuncSetAttribute(ln_bwd_kernel<T, NV_, EX_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
     launch_pdl(ln_bwd_kernel<T, NV_, EX_>, dim3((unsigned)grid), dim3(WARPS * 32), smem, st,                    \
         (const T*)dy, (const T*)x, mean, rstd, gamma, (T*)dx, dgamma, dbeta, rows, H, out_scale, (T*)dx_drop,    \
-        thresh, scale, seed, offset, dbias, seed_pointer(), early, seqs);                                                                     \
+        thresh, scale, seed, offset, dbias, seed_pointer(), early, seqs, gamma2, dgamma2, dbeta2, dbias2,  \
+        split_row, blocks_a);                                                                     \
   } while (0)
 #define VB_LN_BWD2(NV_) do { if (extra) VB_LN_BWD(NV_, true); else VB_LN_BWD(NV_, false); } while (0)
   switch (nv) {
@@ -335,22 +359,24 @@ static Seqs make_seqs(const vb_row_seqs* q) {
 extern "C" {
 
 int vb_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
-                     int64_t rows, int32_t H, float eps, float out_scale, int32_t accum, const vb_row_seqs* seqs, int32_t dtype,
-                     void* stream) {
+                     int64_t rows, int32_t H, float eps, float out_scale, int32_t accum, const vb_row_seqs* seqs,
+                     const float* gamma2, const float* beta2, int64_t split_row, int32_t dtype, void* stream) {
   VB_REQUIRE(x && gamma && beta && y, VB_ERR_ARG, "layernorm_fwd: null pointer");
   VB_REQUIRE(rows >= 0 && H > 0 && H % 8 == 0, VB_ERR_ARG, "layernorm_fwd: H=%d must be a positive multiple of 8", H);
   VB_REQUIRE(vb::aligned16(x) && vb::aligned16(y) && vb::aligned16(gamma) && vb::aligned16(beta), VB_ERR_ARG,
              "layernorm_fwd: pointers must be 16-byte aligned");
   if (rows == 0) return 0;
+  if (!gamma2 || !beta2 || split_row <= 0 || split_row >= rows) { split_row = rows; gamma2 = gamma; beta2 = beta; }
   if (dtype == VB_BF16)
-    return vb::ln::fwd_dispatch<vb::bf16>(x, gamma, beta, y, mean, rstd, rows, H, eps, out_scale, accum, vb::ln::make_seqs(seqs), (cudaStream_t)stream);
+    return vb::ln::fwd_dispatch<vb::bf16>(x, gamma, beta, y, mean, rstd, rows, H, eps, out_scale, accum, vb::ln::make_seqs(seqs), gamma2, beta2, split_row, (cudaStream_t)stream);
   VB_REQUIRE(dtype == VB_F32, VB_ERR_ARG, "layernorm_fwd: bad dtype %d", dtype);
-  return vb::ln::fwd_dispatch<float>(x, gamma, beta, y, mean, rstd, rows, H, eps, out_scale, accum, vb::ln::make_seqs(seqs), (cudaStream_t)stream);
+  return vb::ln::fwd_dispatch<float>(x, gamma, beta, y, mean, rstd, rows, H, eps, out_scale, accum, vb::ln::make_seqs(seqs), gamma2, beta2, split_row, (cudaStream_t)stream);
 }
 
 int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
                      float* dgamma, float* dbeta, int64_t rows, int32_t H, float out_scale, void* dx_drop,
-                     float dropout_p, uint64_t seed, uint64_t offset, float* dbias, const vb_row_seqs* seqs, int32_t dtype,
+                     float dropout_p, uint64_t seed, uint64_t offset, float* dbias, const vb_row_seqs* seqs,
+                     const float* gamma2, float* dgamma2, float* dbeta2, float* dbias2, int64_t split_row, int32_t dtype,
                      void* stream) {
   VB_REQUIRE(dy && x && mean && rstd && gamma && dx, VB_ERR_ARG, "layernorm_bwd: null pointer");
   VB_REQUIRE(rows >= 0 && H > 0 && H % 8 == 0, VB_ERR_ARG, "layernorm_bwd: H=%d must be a positive multiple of 8", H);
@@ -358,13 +384,14 @@ int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const flo
   VB_REQUIRE(vb::aligned16(dy) && vb::aligned16(x) && vb::aligned16(dx) && vb::aligned16(gamma) &&
                  (!dx_drop || vb::aligned16(dx_drop)), VB_ERR_ARG, "layernorm_bwd: pointers must be 16-byte aligned");
   if (rows == 0) return 0;
+  if (!gamma2 || split_row <= 0 || split_row >= rows) split_row = rows;
   if (dropout_p == 0.f) dx_drop = nullptr;
   if (dtype == VB_BF16)
     return vb::ln::bwd_dispatch<vb::bf16>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, H, out_scale, dx_drop,
-                                          dropout_p, seed, offset, dbias, vb::ln::make_seqs(seqs), (cudaStream_t)stream);
+                                          dropout_p, seed, offset, dbias, vb::ln::make_seqs(seqs), gamma2, dgamma2, dbeta2, dbias2, split_row, (cudaStream_t)stream);
   VB_REQUIRE(dtype == VB_F32, VB_ERR_ARG, "layernorm_bwd: bad dtype %d", dtype);
   return vb::ln::bwd_dispatch<float>(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, rows, H, out_scale, dx_drop,
-                                     dropout_p, seed, offset, dbias, vb::ln::make_seqs(seqs), (cudaStream_t)stream);
+                                     dropout_p, seed, offset, dbias, vb::ln::make_seqs(seqs), gamma2, dgamma2, dbeta2, dbias2, split_row, (cudaStream_t)stream);
 }
 
 }  // extern "C"

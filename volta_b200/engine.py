@@ -311,22 +311,25 @@ def out_block_fwd2(rt, h, x, dense_t, ln_t, dense_v, ln_v, p, y):
     seed = rt.seed() if p > 0 else 0
     Mt = rt.Mt
     u = linear_fwd(rt, h, dense_t, epilogue=EPI_BIAS_DROP_RES, aux_in=x, dropout_p=p, seed=seed, lin2=dense_v, split=Mt)
-    _, st_t = ln_fwd(rt, u[:Mt], ln_t, y=y[:Mt], seqs=rt.seqs("t"))
-    _, st_v = ln_fwd(rt, u[Mt:], ln_v, y=y[Mt:], seqs=rt.seqs("v"))
-    return (h, u, (st_t, st_v), p, seed, (rt.seqs("t"), rt.seqs("v")))
+    # one LayerNorm launch for both streams: rows [Mt, ...) take the vision module's gamma / beta
+    sq = rt.seqs("all")
+    mean, rstd = rt.empty(u.shape[0], dtype=torch.float32), rt.empty(u.shape[0], dtype=torch.float32)
+    ops.layernorm_fwd(u, rt.w32(ln_t.weight), rt.w32(ln_t.bias), y, mean, rstd, LN_EPS, seqs=sq,
+                      second=(rt.w32(ln_v.weight), rt.w32(ln_v.bias)), split_row=Mt)
+    _count()
+    return (h, u, (mean, rstd), p, seed, sq)
 
 
 def out_block_bwd2(rt, dy, saved, dense_t, ln_t, dense_v, ln_v, dh_epilogue=EPI_NONE, dh_aux=None):
-    h, u, (st_t, st_v), p, seed, (sq_t, sq_v) = saved
+    h, u, (mean, rstd), p, seed, sq = saved
     Mt, H = rt.Mt, u.shape[1]
     du = rt.empty(*u.shape)
     du_drop = rt.empty(*u.shape) if p > 0 else None
-    dd = (lambda a: None if a is None else a)
-    # the dropout mask of the row-split GEMM is indexed by the JOINT row: the vision half starts at element Mt*H
-    ln_bwd(rt, dy[:Mt], u[:Mt], st_t, ln_t, dx=du[:Mt], dx_drop=dd(du_drop[:Mt] if p > 0 else None), p=p, seed=seed,
-           dbias=rt.g32(dense_t.bias), seqs=sq_t)
-    ln_bwd(rt, dy[Mt:], u[Mt:], st_v, ln_v, dx=du[Mt:], dx_drop=dd(du_drop[Mt:] if p > 0 else None), p=p, seed=seed,
-           dbias=rt.g32(dense_v.bias), offset=Mt * H, seqs=sq_v)
+    # one launch for both streams; the dropout mask of the row-split GEMM is indexed by the JOINT row, as here
+    ops.layernorm_bwd(dy, u, mean, rstd, rt.w32(ln_t.weight), du, rt.g32(ln_t.weight), rt.g32(ln_t.bias), 1.0, du_drop, p, seed, 0,
+                      rt.g32(dense_t.bias), seqs=sq,
+                      second=(rt.w32(ln_v.weight), rt.g32(ln_v.weight), rt.g32(ln_v.bias), rt.g32(dense_v.bias)), split_row=Mt)
+    _count()
     dz = du_drop if p > 0 else du
     dh = linear_bwd(rt, h, dz, dense_t, dx_epilogue=dh_epilogue, bias_done=True, aux_in=dh_aux, lin2=dense_v, split=Mt)
     return du, dh
@@ -444,13 +447,17 @@ def attention_bwd(rt, layer, dy, s):
             du["t"], dctx["t"] = out_block_bwd(rt, dy.t, s["out"]["t"], so.dense, so.LayerNorm)
         if sa.has_vision:
             du["v"], dctx["v"] = out_block_bwd(rt, dy.v, s["out"]["v"], so.v_dense, so.v_LayerNorm)
-    dqkv = {}
+    dqkv, to_clear = {}, {}
     if s["joint"] or s["split"]:
-        dq_all = rt.empty(rt.Mt + rt.Mv, qkv["t"].shape[1])
+        dq_all, fresh = _dqkv_buffer(rt, rt.Mt + rt.Mv, qkv["t"].shape[1])
         dqkv["t"], dqkv["v"], dqkv["all"] = dq_all[:rt.Mt], dq_all[rt.Mt:], dq_all
+        if fresh:
+            to_clear["all"] = dq_all
     else:
         for k in qkv:
-            dqkv[k] = rt.empty(*qkv[k].shape)
+            dqkv[k], fresh = _dqkv_buffer(rt, *qkv[k].shape)
+            if fresh:
+                to_clear[k] = dqkv[k]
     lse_t, lse_v = s["lse"]
     for pm, qt, qv, h_, d_ in s["calls"]:
         ops.attention_bwd(qt, qv, s["masks"][0] if qt is not None else None, s["masks"][1] if qv is not None else None,
@@ -460,7 +467,7 @@ def attention_bwd(rt, layer, dy, s):
                           dqkv_t=dqkv.get("t") if qt is not None else None, dqkv_v=dqkv.get("v") if qv is not None else None,
                           len_t=s["lens"][0], len_v=s["lens"][1], **_pack_cu(rt))
         _count()
-    _zero_pad_rows(rt, dqkv)
+    _zero_pad_rows(rt, to_clear)
     # dx = dqkv . Wqkv + du   (the residual gradient is folded into the dgrad epilogue)
     if s["joint"] or s["split"]:
         dx_all = linear_bwd(rt, x.all, dqkv["all"], [sa.query, sa.key, sa.value], dx_epilogue=EPI_ADD, aux_in=du["all"],
@@ -837,6 +844,19 @@ def _unpack_pair(rt, x):
     return y
 
 
+def _dqkv_buffer(rt, rows, cols):
+    """Gradient buffer of the fused Q/K/V projection.  On packed rows ONE buffer serves every sub-layer of a backward
+    (each consumes it before the next one writes): the attention kernels write whole samples, so the tail between the
+    count and its padding, cleared once, stays zero.  Returns (buffer, needs_its_tail_cleared)."""
+    if not getattr(rt, "pack_on", False):
+        return rt.empty(rows, cols), True
+    cache = rt.pack.__dict__.setdefault("dq_cache", {})
+    if (rows, cols) in cache:
+        return cache[(rows, cols)], False
+    cache[(rows, cols)] = rt.empty(rows, cols)
+    return cache[(rows, cols)], True
+
+
 def _pack_cu(rt):
     if not getattr(rt, "pack_on", False):
         return {}
@@ -848,7 +868,12 @@ def _zero_pad_rows(rt, bufs):
     attention kernels write per sample, so those rows of their outputs are zeroed here."""
     if not getattr(rt, "pack_on", False):
         return
-    for tag, lim in (("t", rt.pack.lim_t), ("v", rt.pack.lim_v)):
+    lt, lv = rt.pack.lim_t, rt.pack.lim_v
+    if bufs.get("all") is not None:      # both streams live in one buffer: one launch clears both tails
+        ops.zero_rows(bufs["all"], lt[0:1], lt[1:2], second=(lv[0:1], lv[1:2], rt.Mt))
+        _count()
+        return
+    for tag, lim in (("t", lt), ("v", lv)):
         if bufs.get(tag) is not None:
             ops.zero_rows(bufs[tag], lim[0:1], lim[1:2])
             _count()
@@ -1115,10 +1140,14 @@ def heads_bwd(rt, model, s, dlosses, x):
             ops.xent_bwd(mlm_logits, lab, cfg.vocab_size, lse, sums[4:5], dlosses[0:1], mlm_logits, row_limit=npad)  # in place
             rt.gemm(dlog, hc, rt.g32(E.weight), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, k_limit=npad)
             ops.colsum(dlog, rt.g32(cls.predictions.bias), row_limit=npad)
+            # d(hidden) = dlogits . E over K = 30522 with only ~count/256 x 3 output tiles: split the reduction (fp32
+            # accumulate) so the whole machine works on it, then round to the activation dtype
+            dhc32 = rt.zeros(*hn.shape, dtype=torch.float32)
+            rt.gemm(dlog, rt.cw(E.weight), dhc32, a_kmajor=True, b_kmajor=False, epilogue=EPI_ACCUM, split_k=16, m_limit=n)
             dhc = rt.empty(*hn.shape)
-            rt.gemm(dlog, rt.cw(E.weight), dhc, a_kmajor=True, b_kmajor=False, m_limit=n)
+            ops.eltwise(ELT_COPY, dhc32, dhc)
             ops.compact_scatter(dhc, pos, dhn)
-            _count(3)
+            _count(4)
         else:
             ops.xent_bwd(mlm_logits, lab, cfg.vocab_size, lse, sums[4:5], dlosses[0:1], mlm_logits)  # in place
             rt.gemm(dlog, hn, rt.g32(E.weight), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)

@@ -138,23 +138,28 @@ def _row_seqs(seqs, rows):
     return C.byref(q)
 
 
-def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=1.0, accum=False, seqs=None):
+def layernorm_fwd(x, gamma, beta, y, mean=None, rstd=None, eps=1e-12, out_scale=1.0, accum=False, seqs=None,
+                  second=None, split_row=0):
+    """second = (gamma2, beta2): rows [split_row, rows) are normalised with the second module's parameters."""
     require_cuda(x, y)
     rows, H, ld = _rows2d(x)
     assert ld == H and _rows2d(y)[2] == H, "LayerNorm rows must be dense"
+    g2, b2 = (second[0].data_ptr(), second[1].data_ptr()) if second is not None else (None, None)
     _lib.call("vb_layernorm_fwd", x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), _ptr(mean), _ptr(rstd),
-              rows, H, eps, out_scale, int(accum), _row_seqs(seqs, rows), dt(x), _stream())
+              rows, H, eps, out_scale, int(accum), _row_seqs(seqs, rows), g2, b2, int(split_row), dt(x), _stream())
     return y
 
 
 def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, out_scale=1.0, dx_drop=None, dropout_p=0.0, seed=0,
-                  offset=0, dbias=None, seqs=None):
+                  offset=0, dbias=None, seqs=None, second=None, split_row=0):
+    """second = (gamma2, dgamma2, dbeta2, dbias2 or None): the rows [split_row, rows) belong to a second LayerNorm."""
     require_cuda(dy, x, dx)
     rows, H, ld = _rows2d(x)
     assert ld == H
+    g2, dg2, db2, dbi2 = (_ptr(t) for t in second) if second is not None else (None, None, None, None)
     _lib.call("vb_layernorm_bwd", dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
               dx.data_ptr(), _ptr(dgamma), _ptr(dbeta), rows, H, out_scale, _ptr(dx_drop), float(dropout_p), int(seed),
-              int(offset), _ptr(dbias), _row_seqs(seqs, rows), dt(x), _stream())
+              int(offset), _ptr(dbias), _row_seqs(seqs, rows), g2, dg2, db2, dbi2, int(split_row), dt(x), _stream())
     return dx
 
 
@@ -188,11 +193,13 @@ def _attn_args(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, 
     return a
 
 
-def zero_rows(buf, row_begin, row_end, row_offset=0, max_rows=256):
-    """buf[row_offset + *row_begin : row_offset + *row_end] = 0 with device-side bounds (int32 tensors)."""
+def zero_rows(buf, row_begin, row_end, row_offset=0, max_rows=256, second=None):
+    """buf[row_offset + *row_begin : row_offset + *row_end] = 0 with device-side bounds (int32 tensors);
+    second = (row_begin2, row_end2, row_offset2): another range of the same buffer in the same launch."""
     _, cols, ld = _rows2d(buf)
-    _lib.call("vb_zero_rows", buf.data_ptr(), ld, cols, row_begin.data_ptr(), row_end.data_ptr(), int(row_offset), int(max_rows),
-              dt(buf), _stream())
+    b2, e2, o2 = (second[0].data_ptr(), second[1].data_ptr(), int(second[2])) if second is not None else (None, None, 0)
+    _lib.call("vb_zero_rows", buf.data_ptr(), ld, cols, row_begin.data_ptr(), row_end.data_ptr(), int(row_offset), b2, e2, o2,
+              int(max_rows), dt(buf), _stream())
     return buf
 
 
