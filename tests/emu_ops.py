@@ -41,7 +41,7 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bia
         M = A0.shape[0] if M is None else M
         K = A0.shape[1] if K is None else K
         if m_limit is not None:
-            M = min(M, int(m_limit[0]))
+            M = min(M, (int(m_limit[0]) + 255) // 256 * 256)   # whole 256-row tiles, like the kernels
         if k_limit is not None:
             K = min(K, int(k_limit[0]))
         if M == 0 or K == 0:

@@ -22,9 +22,13 @@ def _build(name):
     return g, cfg, b, model, state
 
 
-@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("name", CASES + ["mini_ctrl_vilbert+img_compact"])
 def test_engine_forward_backward_matches_oracle(name, monkeypatch):
     emu_ops.install(monkeypatch)
+    if name.endswith("+img_compact"):     # the optional compaction of the masked-region head (engine.IMG_COMPACT)
+        from volta_b200 import engine
+        monkeypatch.setattr(engine, "IMG_COMPACT", True)
+        name = name.split("+")[0]
     g, cfg, b, model, state = _build(name)
     losses = model(b["input_ids"], b["image_feat"], b["image_loc"], b["segment_ids"], b["input_mask"], b["image_mask"],
                    b["lm_label_ids"], b["image_label"], b["image_cls"], b.get("obj_labels"), b.get("obj_confs"), b.get("attr_labels"),

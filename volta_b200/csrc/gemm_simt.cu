@@ -24,9 +24,10 @@ gemm_simt_kernel(Operand A, Operand B, int64_t M, int64_t N, int64_t K, EpiParam
   const int tid = threadIdx.x;
   const int64_t m0 = (int64_t)blockIdx.y * TM, n0 = (int64_t)blockIdx.x * TN;
   // device-side extents (vb_gemm_args::m_limit / k_limit / m_limit2)
+  // (whole 256-row groups, like the tcgen05 back-end: rows up to the padded count are computed from the zero rows there)
   if (seg_M > 0 && m0 >= seg_M) {
-    if (m_limit2 && m0 - seg_M >= *m_limit2) return;
-  } else if (m_limit && m0 >= *m_limit) {
+    if (m_limit2 && m0 - seg_M >= (((int64_t)*m_limit2 + 255) & ~(int64_t)255)) return;
+  } else if (m_limit && m0 >= (((int64_t)*m_limit + 255) & ~(int64_t)255)) {
     return;
   }
   if (k_limit) K = min(K, (int64_t)max(*k_limit, 0));

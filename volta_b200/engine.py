@@ -175,6 +175,10 @@ def model_store(model):
 # ====================================================================================================
 # Masked-LM decoder on the labelled rows only (heads_fwd); VOLTA_B200_MLM_COMPACT=0 restores the all-positions decoder.
 MLM_COMPACT = os.environ.get("VOLTA_B200_MLM_COMPACT", "1") != "0"
+# The same for the masked-region head (label == 1 rows).  Measured on B200 (A/B on one box, 30 steps each): 12.40 / 12.45
+# ms with it, 12.41 / 12.47 ms without - the head is small (0.5 % of the FLOPs) and the plan / gather / scatter launches
+# cost what the skipped rows save.  Off by default; VOLTA_B200_IMG_COMPACT=1 turns it on (covered by the CPU tests).
+IMG_COMPACT = os.environ.get("VOLTA_B200_IMG_COMPACT", "0") == "1"
 # Attention skips 16-row tiles of trailing padding (vb_attn_args::len_*); VOLTA_B200_SKIP_PADDING=0 computes them.
 SKIP_PADDING = os.environ.get("VOLTA_B200_SKIP_PADDING", "1") != "0"
 SKIP_PADDING_LN = os.environ.get("VOLTA_B200_SKIP_PADDING_LN", "1") != "0"   # the residual-block LayerNorms skip them too
@@ -212,11 +216,16 @@ def linear_fwd(rt, x, lin, epilogue=EPI_BIAS, out=None, lin2=None, split=0, **kw
     return out
 
 
-def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, bias_done=False, lin2=None, split=0, **kw):
+def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, bias_done=False, lin2=None, split=0, lim=None, **kw):
     """dW += dy^T x (fp32, accumulated into the flat gradient buffer), db += colsum(dy), dx = dy W (+epilogue).
     lin2 / split: the rows [split, M) belong to a second Linear - two weight-gradient launches over the two row ranges,
     ONE row-split launch for dx."""
     parts = [(lin, x, dy)] if lin2 is None else [(lin, x[:split], dy[:split]), (lin2, x[split:], dy[split:])]
+    # lim = int32 [count, count padded to 256] on the device (compacted head rows): only that many rows hold data
+    wl = dict(k_limit=lim[1:2]) if lim is not None else {}
+    rl = dict(row_limit=lim[1:2]) if lim is not None else {}
+    if lim is not None:
+        kw["m_limit"] = lim[0:1]
     # The bias gradients (column sums of dy) run on a side stream next to the weight-gradient / input-gradient GEMMs of
     # the same Linear: the wgrad kernel leaves registers and shared memory for one small block per SM, and both read dy
     # from L2.  The side stream joins before this function returns (dy may be freed by the caller afterwards).
@@ -226,13 +235,13 @@ def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, 
         side.wait_stream(torch.cuda.current_stream(rt.device))
         with torch.cuda.stream(side):
             for l_, x_, dy_ in parts:
-                ops.colsum(dy_, rt.g32(*[l.bias for l in _lins(l_)]), row_limit=rt.row_limit(dy_.shape[0]))
+                ops.colsum(dy_, rt.g32(*[l.bias for l in _lins(l_)]), **(rl or dict(row_limit=rt.row_limit(dy_.shape[0]))))
                 _count()
     for l_, x_, dy_ in parts:
         lins = _lins(l_)
-        rt.gemm(dy_, x_, rt.g32(*[l.weight for l in lins]), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM)
+        rt.gemm(dy_, x_, rt.g32(*[l.weight for l in lins]), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, **wl)
         if lins[0].bias is not None and not bias_done and side is None:
-            ops.colsum(dy_, rt.g32(*[l.bias for l in lins]), row_limit=rt.row_limit(dy_.shape[0]))
+            ops.colsum(dy_, rt.g32(*[l.bias for l in lins]), **(rl or dict(row_limit=rt.row_limit(dy_.shape[0]))))
             _count()
     if not need_dx:
         if side is not None:
@@ -963,32 +972,40 @@ def bert_bwd(rt, bert, s, dx, dpooled_t, dpooled_v):
 # ====================================================================================================
 # pre-training heads + losses
 # ====================================================================================================
-def _transform_fwd(rt, tr, x, has_ln=True):
+def _lim_seqs(lim, rows):
+    """vb_row_seqs for a buffer whose first lim[0] rows hold data (compacted head rows)."""
+    return None if lim is None else (lim[0:1], rows, rows, None, 0)
+
+
+def _transform_fwd(rt, tr, x, has_ln=True, lim=None):
+    """lim: int32 [count, padded count] on the device - only the first `count` rows of x hold data."""
     epi_f, _ = _act_epilogues(tr.hidden_act)
     H = tr.dense.weight.shape[0]
     h, pre = rt.empty(x.shape[0], H), rt.empty(x.shape[0], H)
+    ml = dict(m_limit=lim[0:1]) if lim is not None else {}
     if epi_f == EPI_BIAS_GELU:
-        linear_fwd(rt, x, tr.dense, epilogue=EPI_BIAS_GELU, out=h, aux_out=pre)
+        linear_fwd(rt, x, tr.dense, epilogue=EPI_BIAS_GELU, out=h, aux_out=pre, **ml)
     else:
-        linear_fwd(rt, x, tr.dense, epilogue=EPI_BIAS_RELU, out=h)
+        linear_fwd(rt, x, tr.dense, epilogue=EPI_BIAS_RELU, out=h, **ml)
         pre = h
     if not has_ln:
         return h, (x, pre, h, None)
-    y, stats = ln_fwd(rt, h, tr.LayerNorm)
+    y, stats = ln_fwd(rt, h, tr.LayerNorm, seqs=_lim_seqs(lim, x.shape[0]))
     return y, (x, pre, h, stats)
 
 
-def _transform_bwd(rt, tr, dy, saved, dx_out, accumulate_dx=False):
+def _transform_bwd(rt, tr, dy, saved, dx_out, accumulate_dx=False, lim=None):
     x, pre, h, stats = saved
     _, epi_b = _act_epilogues(tr.hidden_act)
-    dh = ln_bwd(rt, dy, h, stats, tr.LayerNorm) if stats is not None else dy
+    assert lim is None or stats is not None     # the LayerNorm backward is what zeroes the rows beyond the count
+    dh = ln_bwd(rt, dy, h, stats, tr.LayerNorm, seqs=_lim_seqs(lim, h.shape[0])) if stats is not None else dy
     dpre = rt.empty(*dh.shape)
     ops.eltwise(ELT_MUL if epi_b == EPI_MUL else ELT_DRELU, dh, dpre, b=pre)
     _count()
     if accumulate_dx:
-        linear_bwd(rt, x, dpre, tr.dense, dx_epilogue=EPI_ADD, dx_out=dx_out, aux_in=dx_out)
+        linear_bwd(rt, x, dpre, tr.dense, dx_epilogue=EPI_ADD, dx_out=dx_out, aux_in=dx_out, lim=lim)
     else:
-        linear_bwd(rt, x, dpre, tr.dense, dx_out=dx_out)
+        linear_bwd(rt, x, dpre, tr.dense, dx_out=dx_out, lim=lim)
 
 
 def heads_fwd(rt, model, x, pooled_t, pooled_v, labels, want_logits=False):
@@ -997,7 +1014,6 @@ def heads_fwd(rt, model, x, pooled_t, pooled_v, labels, want_logits=False):
     s = {}
     V_, C_ = cfg.vocab_size, None
     # --- MLM: transform -> tied decoder
-    hn, s["mlm_tr"] = _transform_fwd(rt, cls.predictions.transform, x.t)
     E = rt.cw(cls.predictions.decoder.weight)
     ldv = _pad8(V_)
     mlm_logits = rt.empty(rt.Mt, ldv)
@@ -1012,12 +1028,14 @@ def heads_fwd(rt, model, x, pooled_t, pooled_v, labels, want_logits=False):
         src_index, pos = rt.empty(rt.Mt, dtype=torch.int32), rt.empty(rt.Mt, dtype=torch.int32)
         lab_c = rt.empty(rt.Mt, dtype=torch.int64)
         ops.compact_plan(lab_full, 256, limits, src_index, pos, lab_c)
-        hc = rt.empty(rt.Mt, hn.shape[1])
-        ops.compact_gather(hn, src_index, limits, hc)
+        xc = rt.empty(rt.Mt, x.t.shape[1])
+        ops.compact_gather(x.t, src_index, limits, xc)
         _count(2)
-        rt.gemm(hc, E, mlm_logits, epilogue=EPI_BIAS, bias=rt.w32(cls.predictions.bias), N=V_, m_limit=limits[0:1])
-        cmp_ = (limits, pos, lab_c, hc)
+        hn, s["mlm_tr"] = _transform_fwd(rt, cls.predictions.transform, xc, lim=limits)   # transform of the labelled rows only
+        rt.gemm(hn, E, mlm_logits, epilogue=EPI_BIAS, bias=rt.w32(cls.predictions.bias), N=V_, m_limit=limits[0:1])
+        cmp_ = (limits, pos, lab_c)
     else:
+        hn, s["mlm_tr"] = _transform_fwd(rt, cls.predictions.transform, x.t)
         rt.gemm(hn, E, mlm_logits, epilogue=EPI_BIAS, bias=rt.w32(cls.predictions.bias), N=V_)
     s["mlm"] = (hn, mlm_logits)
     s["mlm_compact"] = cmp_
@@ -1043,14 +1061,44 @@ def heads_fwd(rt, model, x, pooled_t, pooled_v, labels, want_logits=False):
         s["itm"] = (pooled, itm_logits, pooled_t, pooled_v)
     # --- MRM
     ip = cls.imagePredictions
-    hv, s["img_tr"] = _transform_fwd(rt, ip.transform, x.v, has_ln=ip.transform.has_ln)
     img_logits = {}
-    for ix, dec in ip.decoder_dict.items():
+    img_cmp = None
+    active = [ix for ix, w in cfg.visual_target_weights.items() if w > 0]
+    if (MLM_COMPACT and IMG_COMPACT and not want_logits and active == ["0"] and "0" in ip.decoder_dict and ip.transform.has_ln and
+            labels.get("image_label") is not None and labels.get("image_cls") is not None):
+        # Masked-region head on the masked regions only (label == 1; kl_1601 ignores the rest, volta/losses.py:16-22):
+        # the same compaction as the masked-LM head, over the region index r = b*per + j <-> hidden row b*V + j + skip.
+        per = labels["image_label"].shape[1]
+        skip = 1 if cfg.add_global_imgfeat == "first" else 0
+        R = rt.B * per
+        keys = (labels["image_label"].reshape(-1) == 1).to(torch.int64) - 1
+        lim = rt.empty(2, dtype=torch.int32)
+        src_r, pos_r = rt.empty(R, dtype=torch.int32), rt.empty(R, dtype=torch.int32)
+        ops.compact_plan(keys.contiguous(), 256, lim, src_r, pos_r, rt.empty(R, dtype=torch.int64))
+        src_h = (src_r + torch.div(src_r, per, rounding_mode="floor") * (rt.V - per) + skip).to(torch.int32)
+        xc = rt.empty(R, x.v.shape[1])
+        ops.compact_gather(x.v, src_h, lim, xc)
+        hv, s["img_tr"] = _transform_fwd(rt, ip.transform, xc, lim=lim)
+        dec = ip.decoder_dict["0"]
         n_cls = dec.weight.shape[0]
-        lg = rt.empty(rt.Mv, _pad8(n_cls))
-        linear_fwd(rt, hv, dec, out=lg, N=n_cls)
-        img_logits[ix] = lg
+        lg = rt.empty(R, _pad8(n_cls))
+        linear_fwd(rt, hv, dec, out=lg, N=n_cls, m_limit=lim[0:1])
+        tgt = labels["image_cls"].reshape(-1, labels["image_cls"].shape[-1]).float().contiguous()
+        tgt_c = rt.empty(R, tgt.shape[1], dtype=torch.float32)
+        ops.compact_gather(tgt, src_r, lim, tgt_c)
+        lab_c = (torch.arange(R, device=rt.device, dtype=torch.int32) < lim[0:1]).to(torch.int64) * 2 - 1   # 1 below the count, else -1
+        _count(3)
+        img_logits["0"] = lg
+        img_cmp = dict(lim=lim, pos_r=pos_r, per=per, skip=skip, R=R, lab_c=lab_c, tgt_c=tgt_c)
+    else:
+        hv, s["img_tr"] = _transform_fwd(rt, ip.transform, x.v, has_ln=ip.transform.has_ln)
+        for ix, dec in ip.decoder_dict.items():
+            n_cls = dec.weight.shape[0]
+            lg = rt.empty(rt.Mv, _pad8(n_cls))
+            linear_fwd(rt, hv, dec, out=lg, N=n_cls)
+            img_logits[ix] = lg
     s["img"] = (hv, img_logits)
+    s["img_compact"] = img_cmp
     # --- criteria
     sums = rt.zeros(8, dtype=torch.float32)  # [sum_mlm, sum_img, sum_itm, -, cnt_mlm, cnt_img, cnt_itm, -]
     losses = rt.empty(4, dtype=torch.float32)
@@ -1101,6 +1149,13 @@ def heads_fwd(rt, model, x, pooled_t, pooled_v, labels, want_logits=False):
                                           "RNG inside the criterion; it is not on the device path")
             lse = rt.empty(lab.numel(), dtype=torch.float32)
             first = not s["img_losses"]
+            if img_cmp is not None:      # compacted rows: prediction row r is logits row r
+                R = img_cmp["R"]
+                ops.kl_fwd(img_logits[ix], R, R, 0, img_cmp["lab_c"], img_cmp["tgt_c"], n_cls, w, lse, sums[1:2], sums[5:6])
+                _count()
+                rec.update(ix=ix, per=R, per_ld=R, skip=0, lab=img_cmp["lab_c"], tgt=img_cmp["tgt_c"], lse=lse, n_cls=n_cls)
+                s["img_losses"].append(rec)
+                continue
             if rec["kind"] == "kl":
                 # kl_fwd always counts: make it the counting criterion by running it first
                 ops.kl_fwd(img_logits[ix], per, rt.V, skip, lab, rec["tgt"], n_cls, w, lse, sums[1:2], sums[5:6] if first else rt.zeros(1, dtype=torch.float32))
@@ -1135,18 +1190,19 @@ def heads_bwd(rt, model, s, dlosses, x):
         dlog = mlm_logits[:, :cfg.vocab_size]
         dhn = rt.empty(*hn.shape)
         if cmp_ is not None:
-            limits, pos, _, hc = cmp_
+            limits, pos, _ = cmp_
             n, npad = limits[0:1], limits[1:2]     # rows [count, npad) are zero rows: they complete the last tile / k-block
             ops.xent_bwd(mlm_logits, lab, cfg.vocab_size, lse, sums[4:5], dlosses[0:1], mlm_logits, row_limit=npad)  # in place
-            rt.gemm(dlog, hc, rt.g32(E.weight), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, k_limit=npad)
+            rt.gemm(dlog, hn, rt.g32(E.weight), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, k_limit=npad)
             ops.colsum(dlog, rt.g32(cls.predictions.bias), row_limit=npad)
             # d(hidden) = dlogits . E over K = 30522 with only ~count/256 x 3 output tiles: split the reduction (fp32
             # accumulate) so the whole machine works on it, then round to the activation dtype
             dhc32 = rt.zeros(*hn.shape, dtype=torch.float32)
             rt.gemm(dlog, rt.cw(E.weight), dhc32, a_kmajor=True, b_kmajor=False, epilogue=EPI_ACCUM, split_k=16, m_limit=n)
-            dhc = rt.empty(*hn.shape)
-            ops.eltwise(ELT_COPY, dhc32, dhc)
-            ops.compact_scatter(dhc, pos, dhn)
+            ops.eltwise(ELT_COPY, dhc32, dhn)
+            dxc = rt.empty(*dx.t.shape)
+            _transform_bwd(rt, cls.predictions.transform, dhn, s["mlm_tr"], dxc, lim=limits)
+            ops.compact_scatter(dxc, pos, dx.t)
             _count(4)
         else:
             ops.xent_bwd(mlm_logits, lab, cfg.vocab_size, lse, sums[4:5], dlosses[0:1], mlm_logits)  # in place
@@ -1154,7 +1210,7 @@ def heads_bwd(rt, model, s, dlosses, x):
             ops.colsum(dlog, rt.g32(cls.predictions.bias))
             _count(2)
             rt.gemm(dlog, rt.cw(E.weight), dhn, a_kmajor=True, b_kmajor=False)
-        _transform_bwd(rt, cls.predictions.transform, dhn, s["mlm_tr"], dx.t)
+            _transform_bwd(rt, cls.predictions.transform, dhn, s["mlm_tr"], dx.t)
     else:
         ops.fill(dx.t, 0)
     # --- MRM: every active criterion back-propagates through its own decoder into the shared transform output
@@ -1164,17 +1220,28 @@ def heads_bwd(rt, model, s, dlosses, x):
         for rec in s["img_losses"]:
             ix, lg, n_cls = rec["ix"], img_logits[rec["ix"]], rec["n_cls"]
             if rec["kind"] == "kl":
-                ops.kl_bwd(lg, rec["per"], rt.V, rec["skip"], rec["lab"], rec["tgt"], n_cls, rec["w"], rec["lse"], sums[5:6], dlosses[1:2], lg)
+                ops.kl_bwd(lg, rec["per"], rec.get("per_ld", rt.V), rec["skip"], rec["lab"], rec["tgt"], n_cls, rec["w"], rec["lse"], sums[5:6],
+                           dlosses[1:2], lg)
             else:
                 ops.region_loss_bwd(rec["kind"], lg, rec["per"], rt.V, rec["skip"], rec["lab"], rec["idx"], rec["conf"], rec["vec"], n_cls,
                                     rec["w"], rec["lse"], sums[5:6], dlosses[1:2], lg)  # in place
             _count()
             dec = cls.imagePredictions.decoder_dict[ix]
+            lim = s["img_compact"]["lim"] if s.get("img_compact") else None
             if dhv is None:
-                dhv = linear_bwd(rt, hv, lg[:, :n_cls], dec)
+                dhv = linear_bwd(rt, hv, lg[:, :n_cls], dec, lim=lim)
             else:
-                linear_bwd(rt, hv, lg[:, :n_cls], dec, dx_epilogue=EPI_ADD, dx_out=dhv, aux_in=dhv)
-        _transform_bwd(rt, cls.imagePredictions.transform, dhv, s["img_tr"], dx.v)
+                linear_bwd(rt, hv, lg[:, :n_cls], dec, dx_epilogue=EPI_ADD, dx_out=dhv, aux_in=dhv, lim=lim)
+        if s.get("img_compact"):
+            ic = s["img_compact"]
+            dxc = rt.empty(ic["R"], dx.v.shape[1])
+            _transform_bwd(rt, cls.imagePredictions.transform, dhv, s["img_tr"], dxc, lim=ic["lim"])
+            pos_h = torch.full((rt.B, rt.V), -1, dtype=torch.int32, device=rt.device)
+            pos_h[:, ic["skip"]:ic["skip"] + ic["per"]] = ic["pos_r"].view(rt.B, ic["per"])
+            ops.compact_scatter(dxc, pos_h.reshape(-1), dx.v)
+            _count()
+        else:
+            _transform_bwd(rt, cls.imagePredictions.transform, dhv, s["img_tr"], dx.v)
     else:
         ops.fill(dx.v, 0)
     # --- ITM
