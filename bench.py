@@ -252,8 +252,8 @@ def main():
             upload()
         d, ev = pending.pop(0)
         torch.cuda.current_stream().wait_event(ev)
+        l = step(d)                                # enqueue this step first: the GPU never waits for the host's copy calls
         upload()                                   # next step's batch travels while this step runs
-        l = step(d)
         losses_host.copy_(torch.cat([x.detach().reshape(1) for x in l]), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the loss every step (train_concap.py:316-318)
         return l
