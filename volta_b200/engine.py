@@ -804,7 +804,7 @@ def _pack_supported(rt, bert, keep_layers):
         return False
     if rt.gemm_backend == _lib.GEMM_SIMT or rt.attn_backend == _lib.ATTN_SIMT or not torch.cuda.is_available():
         return False
-    if rt.Mt % 256 != 0 or rt.Mt == rt.Mv or rt.Mv == 0 or rt.T > 160 or rt.V > 160:
+    if rt.Mt % 256 != 0 or rt.Mt == rt.Mv or rt.Mv == 0 or rt.T + rt.V > 160:   # 160: what one tensor-core attention block holds
         return False
     if bert.config.fusion_method == "vl-bert_vqa":
         return False
