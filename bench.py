@@ -12,7 +12,9 @@ the bucketed gradient all-reduce overlapped with the backward.  The optimizer is
 
   value     samples/s with the batch already resident in HBM when the timed region starts
   e2e       the same metric through the module API with HOST (pinned) buffers: every step copies its batch
-            host->device and reads the three losses back
+            host->device (on a copy stream, while the previous step computes) and reads its three losses back; the
+            losses are final after the forward, so their read-back is queued before the backward and the host blocks
+            on it - not on the backward - before it queues the next step (all work is inside the timed region)
   roofline  dominant kernel = the tcgen05 GEMM: algorithmic FLOPs (2*M*N*K per launch) / CUDA-event time of
             every GEMM launch in an instrumented step, against the measured sustained bf16 peak
   cpu_baseline / --impl reference: the oracle port of the reference (oracle/volta_oracle.py, fp32, train mode)
@@ -205,6 +207,7 @@ def main():
     if world > 1:
         if os.environ.get("VOLTA_B200_NCCL_CTAS"):  # experiments with VOLTA_B200_DDP_RESERVE_SMS (parallel.py)
             os.environ.setdefault("NCCL_MAX_CTAS", os.environ["VOLTA_B200_NCCL_CTAS"])
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version banner must not share stdout with the JSON line
         dist.init_process_group(backend="nccl", device_id=dev)
 
     cfg = make_cfg(args)
@@ -235,6 +238,7 @@ def main():
     # batch i+1 is issued on a copy stream while step i computes (what a prefetching loader does; the reference's
     # loop does `batch.cuda(non_blocking=True)`, train_concap.py:273); the step waits on the upload's event.
     copy_stream = torch.cuda.Stream(device=dev)
+    loss_ready = torch.cuda.Event()
     pending = []
 
     def upload():
@@ -252,10 +256,15 @@ def main():
             upload()
         d, ev = pending.pop(0)
         torch.cuda.current_stream().wait_event(ev)
-        l = step(d)                                # enqueue this step first: the GPU never waits for the host's copy calls
-        upload()                                   # next step's batch travels while this step runs
+        model.zero_grad(set_to_none=True)
+        l = runner(*batch_args(d))
+        # the losses are final once the forward has run: their device->host copy is queued before the backward, so the
+        # host can read them (every step, as train_concap.py:316-318 does) while the backward is still executing
         losses_host.copy_(torch.cat([x.detach().reshape(1) for x in l]), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller reads the loss every step (train_concap.py:316-318)
+        loss_ready.record()
+        (l[0] + l[1] + l[2]).sum().backward()
+        upload()                                   # next step's batch travels while this step runs
+        loss_ready.synchronize()                   # the caller holds this step's three losses from here on
         return l
 
     def barrier():
