@@ -218,13 +218,34 @@ def _attn_forward_math(qkv_t, qkv_v, mask_t, mask_v, B, Lt, Lv, heads, d, pair_m
     return out
 
 
+def _unpack_rows(x, cu, lens, B, L):
+    """Packed rows (vb_attn_args::cu_*: sample b at [cu[b], cu[b] + len[b])) -> the padded [B*L, C] layout, zeros elsewhere."""
+    if x is None or cu is None:
+        return x
+    out = torch.zeros(B * L, x.shape[1], dtype=x.dtype)
+    for b in range(B):
+        n, c0 = int(lens[b]), int(cu[b])
+        out[b * L:b * L + n] = x[c0:c0 + n]
+    return out
+
+
+def _pack_rows_into(src, dst, cu, lens, B, L):
+    for b in range(B):
+        n, c0 = int(lens[b]), int(cu[b])
+        dst[c0:c0 + n] = src[b * L:b * L + n].to(dst.dtype)
+
+
 def attention_fwd(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, Lv, heads, d, pair_mask, p_t, p_v,
-                  seed, backend, **kw):
+                  seed, backend, len_t=None, len_v=None, cu_t=None, cu_v=None, **kw):
     assert p_t == 0.0 and p_v == 0.0
-    out = _attn_forward_math(qkv_t, qkv_v, mask_t, mask_v, B, Lt, Lv, heads, d, pair_mask)
+    out = _attn_forward_math(_unpack_rows(qkv_t, cu_t, len_t, B, Lt), _unpack_rows(qkv_v, cu_v, len_v, B, Lv), mask_t, mask_v,
+                             B, Lt, Lv, heads, d, pair_mask)
     for qs, (ctx, lse) in out.items():
-        dst, ldst = (ctx_t, lse_t) if qs == 0 else (ctx_v, lse_v)
-        dst.copy_(ctx.to(dst.dtype))
+        dst, ldst, cu, ln, L = (ctx_t, lse_t, cu_t, len_t, Lt) if qs == 0 else (ctx_v, lse_v, cu_v, len_v, Lv)
+        if cu is None:
+            dst.copy_(ctx.to(dst.dtype))
+        else:
+            _pack_rows_into(ctx, dst, cu, ln, B, L)
         ldst.copy_(lse)
 
 
@@ -235,8 +256,10 @@ def mask_lengths(mask, out):
 
 
 def attention_bwd(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, Lt, Lv, heads, d, pair_mask, p_t, p_v,
-                  seed, backend, dctx_t=None, dctx_v=None, dqkv_t=None, dqkv_v=None, **kw):
-    leaves = {}
+                  seed, backend, dctx_t=None, dctx_v=None, dqkv_t=None, dqkv_v=None, len_t=None, len_v=None, cu_t=None,
+                  cu_v=None, **kw):
+    qkv_t, dctx_t = _unpack_rows(qkv_t, cu_t, len_t, B, Lt), _unpack_rows(dctx_t, cu_t, len_t, B, Lt)
+    qkv_v, dctx_v = _unpack_rows(qkv_v, cu_v, len_v, B, Lv), _unpack_rows(dctx_v, cu_v, len_v, B, Lv)
     with torch.enable_grad():
         a = qkv_t.detach().float().requires_grad_(True) if qkv_t is not None else None
         b = qkv_v.detach().float().requires_grad_(True) if qkv_v is not None else None
@@ -246,10 +269,14 @@ def attention_bwd(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, L
             g = dctx_t if qs == 0 else dctx_v
             tot = tot + (ctx * g.float()).sum()
         tot.backward()
-    if a is not None:
-        dqkv_t.copy_((a.grad if a.grad is not None else torch.zeros_like(a)).to(dqkv_t.dtype))
-    if b is not None:
-        dqkv_v.copy_((b.grad if b.grad is not None else torch.zeros_like(b)).to(dqkv_v.dtype))
+    for leaf, dst, cu, ln, L in ((a, dqkv_t, cu_t, len_t, Lt), (b, dqkv_v, cu_v, len_v, Lv)):
+        if leaf is None:
+            continue
+        g = leaf.grad if leaf.grad is not None else torch.zeros_like(leaf)
+        if cu is None:
+            dst.copy_(g.to(dst.dtype))
+        else:
+            _pack_rows_into(g, dst, cu, ln, B, L)
 
 
 def embed_gather_fwd(tables, idx, const_rows, out, accum=False):

@@ -97,3 +97,36 @@ def test_row_split_launch_plan_matches_oracle(name, monkeypatch):
         assert float((got - ref).norm()) < 2e-3 * max(float(ref.norm()), 1e-6), (name, key)
     assert any(taken) == (name != "mini_vilbert"), taken   # vilbert_base: the streams differ in width - never split
     assert real is not forced
+
+
+def test_packed_rows_plan_matches_oracle(monkeypatch):
+    """engine.bert_fwd packs the valid rows of both streams between the embeddings and the heads (device-side counts for
+    the GEMMs / LayerNorms, per-sample offsets for the attention).  The plan needs the tensor-core kernels on the device;
+    here it is forced on under the emulation - the host logic (packing plan, limits, zero-row invariant, un-packing) must
+    reproduce the oracle's losses and every parameter gradient on a batch whose text rows end on a 256-row boundary."""
+    from volta_b200 import engine
+    from volta_b200.synthetic import pretraining_batch
+    emu_ops.install(monkeypatch)
+    taken = []
+
+    def forced(rt, bert, keep_layers):
+        ok = not keep_layers and rt.Mt % 256 == 0 and rt.Mt != rt.Mv
+        taken.append(ok)
+        return ok
+    monkeypatch.setattr(engine, "_pack_supported", forced)
+    g, cfg, _, model, state = _build("mini_ctrl_vilbert")
+    b = pretraining_batch(32, 8, 9, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
+    losses = model(b["input_ids"], b["image_feat"], b["image_loc"], b["segment_ids"], b["input_mask"], b["image_mask"],
+                   b["lm_label_ids"], b["image_label"], b["image_cls"], None, None, None, None, None, b["is_match"])
+    assert taken and all(taken)
+    (losses[0] + losses[1] + losses[2]).sum().backward()
+    P = O.params_from_state_dict(state, requires_grad=True)
+    ref = O.pretraining_losses(P, cfg, b)
+    for mine, r in zip(losses, ref):
+        assert abs(float(mine) - float(r)) < 2e-4 * max(1.0, abs(float(r))), (float(mine), float(r))
+    sum(ref).backward()
+    for key, p in model.named_parameters():
+        rg = P[key].grad if P[key].grad is not None else torch.zeros_like(P[key])
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        err = float((got - rg).norm()) / max(float(rg.norm()), 1e-6)
+        assert err < 2e-3, (key, err)
