@@ -374,6 +374,23 @@ int vb_batched_colsum(const void* a, int32_t dtype, int64_t batch, int64_t rows,
 int vb_sumsq(const float* x, int64_t n, float* out, void* stream);
 int vb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
                   const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream);
+/* ---- input pipeline: region batch assembly on the device ------------------------------------
+ * vb_region_batch replaces the per-batch numpy work of the reference's Conceptual-Captions loader between the detector
+ * output and the model call: box area + normalisation (volta/datasets/concept_cap_dataset.py:450-461), zeroing of the
+ * regions picked for prediction and exclusion of the regions overlapping them from the mean (IoU > 0.4, :31-68,
+ * :661-690), padding mask / labels (:562-568), and the mean-pooled global feature with its box and mask
+ * (ConceptCapLoaderTrain.__iter__, :237-264; the same layout _image_features_reader.py:102-113 builds for the tasks).
+ *   raw_feat [B,R,F] in_dtype (fp32 as stored, or bf16 to halve the upload); raw_box [B,R,4] fp32 PIXELS x1,y1,x2,y2;
+ *   image_hw [B,2] fp32 (h, w); num_boxes [B]; sel [B,R]: 0 = untouched, 1 = predicted + features zeroed, 2 = predicted,
+ *   features kept (the host's random draws, :669-686).  Rows at or beyond num_boxes[b] are never read (treated as 0).
+ *   global_pos: 0 none, 1 first, 2 last (config.add_global_imgfeat);  V = R + (global_pos != 0).
+ *   Outputs: feat [B,V,F] out_dtype; loc [B,V,num_locs] fp32 (num_locs 4 or 5); mask [B,V] int64; label [B,R] int64
+ *   (1 / -1); count [B] int32 = divisor of the global feature (regions not excluded, padded rows included, min 1).
+ * fp32 outputs are bit-identical to the reference's numpy arithmetic (same operation order, round-to-nearest). */
+int vb_region_batch(const void* raw_feat, int32_t in_dtype, const float* raw_box, const float* image_hw,
+                    const int32_t* num_boxes, const uint8_t* sel, int32_t B, int32_t R, int32_t F, int32_t num_locs,
+                    int32_t global_pos, void* feat, int32_t out_dtype, float* loc, int64_t* mask, int64_t* label,
+                    int32_t* count, void* stream);
 /* L2-flush helper for benchmarks: writes `bytes` to buf. */
 int vb_fill(void* buf, int64_t bytes, int32_t value, void* stream);
 

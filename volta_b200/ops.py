@@ -443,3 +443,19 @@ def batched_colsum(a, batch, rows, cols, out):
     assert a.is_contiguous() and out.dtype == torch.float32 and out.numel() == batch * cols
     _lib.call("vb_batched_colsum", a.data_ptr(), dt(a), batch, rows, cols, out.data_ptr(), _stream())
     return out
+
+
+def region_batch(raw_feat, raw_box, image_hw, num_boxes, sel, global_pos, feat, loc, mask, label, count):
+    """Region batch assembly (vb_region_batch): detector output -> image_feat / image_loc / image_mask / image_label."""
+    require_cuda(raw_feat, raw_box, image_hw, num_boxes, sel, feat, loc, mask, label, count)
+    B, R, F = raw_feat.shape
+    for t in (raw_feat, raw_box, image_hw, num_boxes, sel, feat, loc, mask, label, count):
+        assert t.is_contiguous()
+    assert raw_box.shape == (B, R, 4) and raw_box.dtype == torch.float32 and image_hw.shape == (B, 2)
+    assert image_hw.dtype == torch.float32 and num_boxes.dtype == torch.int32 and sel.dtype == torch.uint8
+    V = R + (1 if global_pos else 0)
+    assert feat.shape == (B, V, F) and loc.shape[:2] == (B, V) and mask.shape == (B, V) and label.shape == (B, R)
+    assert loc.dtype == torch.float32 and mask.dtype == torch.int64 and label.dtype == torch.int64 and count.dtype == torch.int32
+    _lib.call("vb_region_batch", raw_feat.data_ptr(), dt(raw_feat), raw_box.data_ptr(), image_hw.data_ptr(),
+              num_boxes.data_ptr(), sel.data_ptr(), B, R, F, loc.shape[2], global_pos, feat.data_ptr(), dt(feat),
+              loc.data_ptr(), mask.data_ptr(), label.data_ptr(), count.data_ptr(), _stream())

@@ -81,6 +81,39 @@ def pretraining_batch(batch, seq_len, num_regions, *, vocab_size=30522, feat_dim
     return out
 
 
+def raw_region_batch(batch, region_len, *, feat_dim=2048, seed=2468, full=True):
+    """Detector output BEFORE the loader touched it (what `BertPreprocessBatch.__call__` receives per sample,
+    volta/datasets/concept_cap_dataset.py:429-431, stacked over the batch): pooled features (post-ReLU, fp32), boxes
+    in PIXELS (x1, y1, x2, y2), image (h, w), box count, and `sel` - which regions the masking draw of
+    `random_region` (:661-690) picked: 0 = untouched, 1 = predicted and zeroed, 2 = predicted, features kept.
+    Boxes are drawn around a few centres so that IoU > 0.4 overlaps (the exclusion rule of :679) really occur.
+    full=False: ragged box counts (rows beyond the count are zero, as the loader pads them, :435-446)."""
+    g = torch.Generator().manual_seed(seed)
+    B, R = batch, region_len
+    hw = torch.stack([torch.randint(240, 801, (B,), generator=g), torch.randint(320, 1025, (B,), generator=g)], 1).float()
+    h, w = hw[:, :1], hw[:, 1:]
+    nbox = torch.full((B,), R, dtype=torch.int32) if full else \
+        torch.randint(max(1, R // 3), R + 1, (B,), generator=g).to(torch.int32)
+    live = torch.arange(R).unsqueeze(0) < nbox.unsqueeze(1)
+    feat = torch.relu(torch.randn(B, R, feat_dim, generator=g)) * live.unsqueeze(-1)
+    n_centres = max(2, R // 4)
+    cx = torch.rand(B, n_centres, generator=g)
+    cy = torch.rand(B, n_centres, generator=g)
+    which = torch.randint(0, n_centres, (B, R), generator=g)
+    bx = (cx.gather(1, which) + 0.04 * torch.randn(B, R, generator=g)).clamp(0.05, 0.95) * w
+    by = (cy.gather(1, which) + 0.04 * torch.randn(B, R, generator=g)).clamp(0.05, 0.95) * h
+    bw = (0.1 + 0.3 * torch.rand(B, R, generator=g)) * w
+    bh = (0.1 + 0.3 * torch.rand(B, R, generator=g)) * h
+    x1 = (bx - bw / 2).clamp(min=0.0)
+    y1 = (by - bh / 2).clamp(min=0.0)
+    x2 = torch.minimum(bx + bw / 2, w - 1)
+    y2 = torch.minimum(by + bh / 2, h - 1)
+    box = torch.stack([x1, y1, x2, y2], -1) * live.unsqueeze(-1)
+    u = torch.rand(B, R, generator=g)
+    sel = torch.where(u < 0.15 * 0.9, 1, torch.where(u < 0.15, 2, 0)).to(torch.uint8) * live.to(torch.uint8)
+    return dict(raw_feat=feat.contiguous(), raw_box=box.contiguous(), image_hw=hw, num_boxes=nbox, sel=sel)
+
+
 def retrieval_batch(num_pairs, seq_len, num_regions, *, vocab_size=30522, feat_dim=2048, num_locs=5, seed=4321):
     """One caption repeated against `num_pairs` candidate images (`eval_retrieval.py:172-191`)."""
     b = pretraining_batch(num_pairs, seq_len, num_regions, vocab_size=vocab_size, feat_dim=feat_dim,
