@@ -41,6 +41,20 @@ def _worker(rank, world, port, out):
             # 640..1000 (360 >= 200) closes first, then 400..640 (240), then 100..400 (300); finish() flushes 0..100
             assert b.ranges == [(640, 1000), (400, 640), (100, 400), (0, 100)], b.ranges
             assert n == 4
+        # bf16 wire (allreduce_dtype=torch.bfloat16 / VOLTA_B200_DDP_BF16=1): same buckets, values rounded to bf16 once
+        # before the sum; the fp32 buffer receives the averaged result
+        gen = torch.Generator().manual_seed(7)
+        base = torch.randn(total, generator=gen)
+        flat = base * (rank + 1)
+        b = GradBucketer(flat, bounds, message_size=200, wire_dtype=torch.bfloat16)
+        for frontier in (900, 640, 400, 250, 100):
+            b.advance(frontier)
+        assert b.finish() == 4 and b.ranges == [(640, 1000), (400, 640), (100, 400), (0, 100)]
+        expect = sum((base * (r + 1)).bfloat16().float() for r in range(world)) / world
+        assert flat.dtype == torch.float32
+        assert torch.allclose(flat, expect, rtol=2 ** -7, atol=1e-6), (flat - expect).abs().max()
+        exact = base * sum(r + 1 for r in range(world)) / world
+        assert torch.allclose(flat, exact, rtol=2 ** -6, atol=1e-6)
         out.put((rank, "ok"))
     except Exception as e:  # noqa
         out.put((rank, repr(e)))

@@ -130,4 +130,5 @@ def test_assembled_batch_feeds_the_model_like_the_host_assembled_one():
                         text["lm_label_ids"].cuda(), label, text["image_cls"].cuda(), None, None, None, None, None,
                         text["is_match"].cuda())
         losses.append([float(x) for x in out[:3]])
-    assert losses[0] == losses[1], losses
+    for a, b in zip(*losses):   # the loss sums use fp32 atomics: last-bit run-to-run differences
+        assert abs(a - b) <= 2e-6 * abs(b), losses

@@ -128,7 +128,7 @@ feat_kernel(const TIn* __restrict__ raw, const int32_t* __restrict__ num_boxes, 
   const TIn* src = raw + (int64_t)b * R * F + c;
   TOut* dst = out + ((int64_t)b * V + off) * F + c;
   float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-  constexpr int U = 4;
+  constexpr int U = 6;   // loads in flight per thread (36 regions = 6 rounds)
   for (int r0 = 0; r0 < R; r0 += U) {
     float4 v[U];
 #pragma unroll

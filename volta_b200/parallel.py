@@ -23,6 +23,17 @@ import torch.distributed as dist
 from . import engine
 
 
+def _convert(src, dst):
+    """dst = src in dst's dtype (fp32 <-> bf16), on the current stream: vb_eltwise on the GPU; torch on CPU tensors
+    (the gloo tests of the host logic)."""
+    if src.is_cuda:
+        from . import ops
+        from ._lib import ELT_COPY
+        ops.eltwise(ELT_COPY, src.view(1, -1), dst.view(1, -1))
+    else:
+        dst.copy_(src)
+
+
 class GradBucketer:
     """Slices a flat gradient buffer into buckets that close as the backward frontier moves towards offset 0.
 
@@ -31,8 +42,14 @@ class GradBucketer:
     least `message_size` elements is all-reduced asynchronously.  `finish()` flushes the rest and waits.
     Pure host logic + torch.distributed: works with gloo on CPU tensors (tests) and NCCL on CUDA."""
 
-    def __init__(self, flat_grad, boundaries, message_size=10_000_000, group=None, average=True):
+    def __init__(self, flat_grad, boundaries, message_size=10_000_000, group=None, average=True, wire_dtype=None):
         self.flat = flat_grad
+        # Optional reduced-precision wire format (SURVEY.md 8e "bf16 or fp32 buckets"; apex reduces half-precision
+        # gradients in their own dtype unless allreduce_always_fp32 is set, distributed.py:442-456): the bucket is cast
+        # into `wire` when it closes, the collective moves half the bytes, the result is cast back in finish().
+        self.wire = None
+        if wire_dtype is not None and wire_dtype != flat_grad.dtype:
+            self.wire = torch.empty(flat_grad.numel(), dtype=wire_dtype, device=flat_grad.device)
         self.total = flat_grad.numel()
         self.boundaries = sorted(set(b for b in boundaries if 0 < b < self.total))
         self.message_size = int(message_size)
@@ -52,9 +69,13 @@ class GradBucketer:
         if hi <= lo:
             return
         chunk = self.flat[lo:hi]
+        sent = chunk
+        if self.wire is not None:
+            sent = self.wire[lo:hi]
+            _convert(chunk, sent)
         op = dist.ReduceOp.AVG if self._native_avg else dist.ReduceOp.SUM
-        work = dist.all_reduce(chunk, op=op, group=self.group, async_op=True)
-        self.works.append((work, chunk))
+        work = dist.all_reduce(sent, op=op, group=self.group, async_op=True)
+        self.works.append((work, chunk, sent))
         self.ranges.append((lo, hi))
         self.hi = lo
 
@@ -92,8 +113,10 @@ class GradBucketer:
 
     def finish(self):
         self._issue(0, self.hi)
-        for work, chunk in self.works:
+        for work, chunk, sent in self.works:
             work.wait()
+            if sent is not chunk:
+                _convert(sent, chunk)
             if self.average and not self._native_avg:
                 chunk.div_(self.world)
         n = len(self.works)
@@ -105,7 +128,7 @@ class DistributedDataParallel(torch.nn.Module):
     """`DistributedDataParallel(model, delay_allreduce=False, message_size=1e7)` as in the reference's call
     (train_concap.py:253).  The wrapped model must be one of volta_b200's models on a CUDA device."""
 
-    def __init__(self, module, message_size=10_000_000, delay_allreduce=False, group=None, **unused):
+    def __init__(self, module, message_size=10_000_000, delay_allreduce=False, group=None, allreduce_dtype=None, **unused):
         super().__init__()
         if not dist.is_initialized():
             raise RuntimeError("torch.distributed is not initialised (init_process_group(backend='nccl'))")
@@ -114,6 +137,14 @@ class DistributedDataParallel(torch.nn.Module):
         self.delay_allreduce = bool(delay_allreduce)
         self.group = group
         self.world_size = dist.get_world_size(group)
+        # allreduce_dtype=torch.bfloat16 (or VOLTA_B200_DDP_BF16=1): gradients cross NVLink as bf16 - half the 968 MB of
+        # ctrl_vilbert per step; each element is rounded once before and the sum once per hop.  Off by default: the
+        # fp32 wire is what the parity tests pin.
+        if allreduce_dtype is None and os.environ.get("VOLTA_B200_DDP_BF16", "0") == "1":
+            allreduce_dtype = torch.bfloat16
+        if allreduce_dtype not in (None, torch.float32, torch.bfloat16):
+            raise ValueError("allreduce_dtype must be None, torch.float32 or torch.bfloat16")
+        self.allreduce_dtype = allreduce_dtype
         self._bucketer = None
         self.last_num_buckets = 0
         self._broadcast_params()
@@ -150,7 +181,8 @@ class DistributedDataParallel(torch.nn.Module):
     def _ensure_bucketer(self):
         store = engine.model_store(self.module)
         if self._bucketer is None or self._bucketer.flat.data_ptr() != store.grad32.data_ptr():
-            self._bucketer = GradBucketer(store.grad32, self._boundaries(store), self.message_size, self.group)
+            self._bucketer = GradBucketer(store.grad32, self._boundaries(store), self.message_size, self.group,
+                                          wire_dtype=self.allreduce_dtype)
         return self._bucketer
 
     def _on_progress(self, frontier_offset):
