@@ -391,6 +391,17 @@ int vb_region_batch(const void* raw_feat, int32_t in_dtype, const float* raw_box
                     const int32_t* num_boxes, const uint8_t* sel, int32_t B, int32_t R, int32_t F, int32_t num_locs,
                     int32_t global_pos, void* feat, int32_t out_dtype, float* loc, int64_t* mask, int64_t* label,
                     int32_t* count, void* stream);
+/* ---- retrieval ranking on the device -------------------------------------------------------
+ * vb_retrieval_ranks replaces the per-caption / per-image numpy argsorts of eval_retrieval.py over its score and target
+ * matrices (scores [C,I] fp32, pitch ld; targets [C,I] uint8, 1 = matching pair, pitch ld_t).  The place of an element
+ * in a descending sort is the number of elements that beat it; equal scores keep index order (numpy's default argsort
+ * leaves that case unspecified).
+ *   axis 0 (image retrieval, eval_retrieval.py:201-208): rank[c] = place of the FIRST matching image of caption c in
+ *          its row, I if it has none (:166);  topk (or NULL) [C,k] int32 = first k images of the row's descending order
+ *          (:222, k = 20), -1 beyond I.
+ *   axis 1 (text retrieval, :248-256): rank[i] = best place of a matching caption in column i, C if there is none. */
+int vb_retrieval_ranks(const float* scores, int64_t ld, const uint8_t* targets, int64_t ld_t, int32_t C, int32_t I,
+                       int32_t axis, int32_t* rank, int32_t* topk, int32_t k, void* stream);
 /* L2-flush helper for benchmarks: writes `bytes` to buf. */
 int vb_fill(void* buf, int64_t bytes, int32_t value, void* stream);
 

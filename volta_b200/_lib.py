@@ -91,6 +91,7 @@ SIGNATURES = {
     "vb_vlbert_prep": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "vb_vlbert_index": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vb_batched_colsum": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp]),
+    "vb_retrieval_ranks": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32, _vp]),
     "vb_region_batch": (_i32, [_vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
 }
 

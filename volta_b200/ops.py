@@ -459,3 +459,18 @@ def region_batch(raw_feat, raw_box, image_hw, num_boxes, sel, global_pos, feat, 
     _lib.call("vb_region_batch", raw_feat.data_ptr(), dt(raw_feat), raw_box.data_ptr(), image_hw.data_ptr(),
               num_boxes.data_ptr(), sel.data_ptr(), B, R, F, loc.shape[2], global_pos, feat.data_ptr(), dt(feat),
               loc.data_ptr(), mask.data_ptr(), label.data_ptr(), count.data_ptr(), _stream())
+
+
+def retrieval_ranks(scores, targets, axis, rank, topk=None):
+    """vb_retrieval_ranks: places of the matching pairs in the descending order of every row (axis 0) / column (axis 1)."""
+    require_cuda(scores, targets, rank, topk)
+    C, I = scores.shape
+    assert scores.dtype == torch.float32 and targets.dtype == torch.uint8 and targets.shape == (C, I)
+    assert scores.stride(1) == 1 and targets.stride(1) == 1
+    assert rank.dtype == torch.int32 and rank.is_contiguous() and rank.numel() == (C if axis == 0 else I)
+    k = 0
+    if topk is not None:
+        assert topk.dtype == torch.int32 and topk.is_contiguous() and topk.shape[0] == C
+        k = topk.shape[1]
+    _lib.call("vb_retrieval_ranks", scores.data_ptr(), scores.stride(0), targets.data_ptr(), targets.stride(0), C, I, axis,
+              rank.data_ptr(), _ptr(topk), k, _stream())

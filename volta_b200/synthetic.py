@@ -123,6 +123,22 @@ def retrieval_batch(num_pairs, seq_len, num_regions, *, vocab_size=30522, feat_d
     return {k: b[k] for k in ("input_ids", "image_feat", "image_loc", "segment_ids", "input_mask", "image_mask")}
 
 
+def retrieval_case(num_captions, num_images, seed=0):
+    """Score / target matrices in the layout of eval_retrieval.py:164-165: caption c belongs to image
+    c // (num_captions // num_images) (Flickr30k: 5 captions per image); scores are distinct fp32 values with the matching
+    pair pushed up, so ranks spread over the first few dozen places."""
+    g = torch.Generator().manual_seed(seed)
+    C, I = num_captions, num_images
+    per = max(1, C // I)
+    owner = (torch.arange(C) // per).clamp(max=I - 1)
+    targets = torch.zeros(C, I, dtype=torch.uint8)
+    targets[torch.arange(C), owner] = 1
+    scores = torch.randperm(C * I, generator=g).float().reshape(C, I) / (C * I) * 8.0 - 4.0   # distinct values
+    boost = torch.rand(C, generator=g) * 6.0
+    scores[torch.arange(C), owner] += boost
+    return scores.contiguous(), targets
+
+
 def seeded_state_dict(reference_state, seed=0, std=0.02):
     """Deterministic weights for parity tests: N(0, std) for matrices / embeddings,
     N(1, std) for LayerNorm weights, N(0, std) for biases, drawn key by key in
