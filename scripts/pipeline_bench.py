@@ -1,6 +1,6 @@
 """Region batch assembly (vb_region_batch) at the Conceptual-Captions batch shape: B=256, 36 regions x 2048-d.
 
-    python scripts/pipeline_bench.py [--batch 256] [--iters 50] [--cpu-batches 3]
+    python scripts/pipeline_bench.py [--batch 256] [--iters 50] [--cpu-batches 3] [--once]
 
 Prints ONE JSON line:
   kernel     : device-resident detector output (a pool of batches larger than the 126 MB L2 rotates), CUDA events around
@@ -28,6 +28,7 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--regions", type=int, default=36)
 ap.add_argument("--iters", type=int, default=50)
 ap.add_argument("--cpu-batches", type=int, default=3)
+ap.add_argument("--once", action="store_true", help="one eager launch per dtype combination on a cold batch (the command ncu profiles)")
 args = ap.parse_args()
 
 B, R, F = args.batch, args.regions, 2048
@@ -42,6 +43,17 @@ KEYS = ("raw_feat", "raw_box", "image_hw", "num_boxes", "sel")
 raws = [raw_region_batch(B, R, seed=10 + i, full=False) for i in range(POOL)]
 out = {"op": "vb_region_batch", "workload": "B=%d, %d regions x %d-d + global first, ragged box counts" % (B, R, F),
        "hbm_peak_gbs": peak, "pool": "%d batches rotate (%.0f MB of fp32 features, > L2)" % (POOL, POOL * B * R * F * 4 / 1e6)}
+
+
+if args.once:
+    for k, (in_dt, out_dt) in enumerate(((torch.float32, torch.bfloat16), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.float32))):
+        asm = RegionBatchAssembler(R, F, 5, "first", out_dtype=out_dt)
+        d = {key: v.to(dev) for key, v in raws[k].items()}
+        d["raw_feat"] = d["raw_feat"].to(in_dt)
+        torch.cuda.synchronize()
+        asm(**{key: d[key] for key in KEYS})
+        torch.cuda.synchronize()
+    sys.exit(0)
 
 
 def timed(fn, iters):

@@ -17,7 +17,7 @@ namespace pipeline {
 
 constexpr int THREADS = 128;
 constexpr int MAX_REGIONS = 1024;
-constexpr int U = 6;   // row loads in flight per thread (36 regions = 6 rounds)
+constexpr int U = 12;  // row loads in flight per thread (36 regions = 3 rounds): the per-thread chain is latency-bound
 
 // W consecutive elements <-> W floats; W = 16 bytes of the INPUT type, so every load is a 16-byte vector.
 template <typename T, int W> struct Pack;
@@ -71,13 +71,11 @@ region_batch_kernel(const TIn* __restrict__ raw, const float* __restrict__ raw_b
   const int b = blockIdx.y, t = threadIdx.x;
   const int nb = max(0, min(num_boxes[b], R));
   const int V = R + (global_pos != 0 ? 1 : 0), off = global_pos == 1 ? 1 : 0;
-  for (int j = t; j < R; j += THREADS) {
-    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < nb) bx = *reinterpret_cast<const float4*>(raw_box + ((int64_t)b * R + j) * 4);
-    box_s[j] = bx;
-    area_s[j] = __fmul_rn(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
-    sel_s[j] = j < nb ? sel[(int64_t)b * R + j] : (uint8_t)0;
-  }
+  // the picks decide which rows are read at all; the boxes are only needed after the feature pass - request this
+  // thread's first box now, park it in a register, and fill shared memory once the feature loads have been issued
+  for (int j = t; j < R; j += THREADS) sel_s[j] = j < nb ? sel[(int64_t)b * R + j] : (uint8_t)0;
+  float4 box0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (t < nb) box0 = *reinterpret_cast<const float4*>(raw_box + ((int64_t)b * R + t) * 4);
   __syncthreads();
 
   // ---- features: copy / zero the rows, running sum ----
@@ -108,6 +106,17 @@ region_batch_kernel(const TIn* __restrict__ raw, const float* __restrict__ raw_b
       }
     }
   }
+
+  for (int j = t; j < R; j += THREADS) {
+    float4 bx = box0;
+    if (j != t) {
+      bx = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < nb) bx = *reinterpret_cast<const float4*>(raw_box + ((int64_t)b * R + j) * 4);
+    }
+    box_s[j] = bx;
+    area_s[j] = __fmul_rn(__fadd_rn(__fsub_rn(bx.z, bx.x), 1.f), __fadd_rn(__fsub_rn(bx.w, bx.y), 1.f));
+  }
+  __syncthreads();
 
   // ---- region j leaves the mean's divisor when it overlaps (IoU > 0.4) any picked region, itself included ----
   int32_t mine = 0;

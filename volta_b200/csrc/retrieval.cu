@@ -98,26 +98,50 @@ row_rank_kernel(const float* __restrict__ scores, int64_t ld, const uint8_t* __r
   }
 }
 
-// One thread per image column (adjacent threads read adjacent columns): the best-placed matching caption.
-__global__ void __launch_bounds__(THREADS)
+// Image columns: a block owns 32 adjacent columns (a warp reads 128 contiguous bytes of a row) and splits the captions
+// over its 32 warps; per column the best-placed matching caption is reduced through shared memory, then the captions
+// that beat it are counted the same way.
+constexpr int COL_ROWS = 32;
+__global__ void __launch_bounds__(32 * COL_ROWS)
 col_rank_kernel(const float* __restrict__ scores, int64_t ld, const uint8_t* __restrict__ targets, int64_t ld_t, int C, int I,
                 int32_t* __restrict__ rank) {
-  const int i = blockIdx.x * THREADS + threadIdx.x;
-  if (i >= I) return;
+  __shared__ float s_best[COL_ROWS][33];
+  __shared__ int s_idx[COL_ROWS][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * 32 + tx;
+  const bool live = i < I;
   float bs = 0.f;
   int bc = C;
-  for (int c = 0; c < C; ++c) {
-    if (targets[(int64_t)c * ld_t + i] == 1) {
-      const float v = scores[(int64_t)c * ld + i];
-      if (bc == C || before(v, c, bs, bc)) { bs = v; bc = c; }
+  if (live) {
+    for (int c = ty; c < C; c += COL_ROWS) {
+      if (targets[(int64_t)c * ld_t + i] == 1) {
+        const float v = scores[(int64_t)c * ld + i];
+        if (bc == C || before(v, c, bs, bc)) { bs = v; bc = c; }
+      }
     }
   }
-  int r = C;
-  if (bc < C) {
-    r = 0;
-    for (int c = 0; c < C; ++c) r += before(scores[(int64_t)c * ld + i], c, bs, bc) ? 1 : 0;
+  s_best[ty][tx] = bs;
+  s_idx[ty][tx] = bc;
+  __syncthreads();
+  bs = s_best[0][tx]; bc = s_idx[0][tx];
+#pragma unroll 4
+  for (int k = 1; k < COL_ROWS; ++k) {
+    const float os = s_best[k][tx];
+    const int oc = s_idx[k][tx];
+    if (oc != C && (bc == C || before(os, oc, bs, bc))) { bs = os; bc = oc; }
   }
-  rank[i] = r;
+  __syncthreads();
+  int beats = 0;
+  if (live && bc < C)
+    for (int c = ty; c < C; c += COL_ROWS) beats += before(scores[(int64_t)c * ld + i], c, bs, bc) ? 1 : 0;
+  s_idx[ty][tx] = beats;
+  __syncthreads();
+  if (ty == 0 && live) {
+    int r = 0;
+#pragma unroll 4
+    for (int k = 0; k < COL_ROWS; ++k) r += s_idx[k][tx];
+    rank[i] = bc < C ? r : C;
+  }
 }
 
 }  // namespace retrieval
@@ -137,7 +161,7 @@ extern "C" int vb_retrieval_ranks(const float* scores, int64_t ld, const uint8_t
   if (axis == 0)
     retrieval::row_rank_kernel<<<C, retrieval::THREADS, 0, st>>>(scores, ld, targets, ld_t, I, rank, topk, k);
   else
-    retrieval::col_rank_kernel<<<(unsigned)ceil_div(I, retrieval::THREADS), retrieval::THREADS, 0, st>>>(scores, ld, targets,
-                                                                                                        ld_t, C, I, rank);
+    retrieval::col_rank_kernel<<<(unsigned)ceil_div(I, 32), dim3(32, retrieval::COL_ROWS), 0, st>>>(scores, ld, targets, ld_t, C, I,
+                                                                                                   rank);
   return check_launch("vb_retrieval_ranks");
 }
