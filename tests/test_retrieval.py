@@ -40,8 +40,76 @@ def test_host_metrics_equal_the_reference_formulas(golden):
 
 def test_ranker_refuses_to_run_without_a_device():
     from volta_b200.retrieval import RetrievalRanker
+    rk = RetrievalRanker(10, 2, device="cpu")          # buffers may live anywhere; ranking may not
     with pytest.raises(RuntimeError):
-        RetrievalRanker(10, 2, device="cpu")
+        rk.image_retrieval()
+    with pytest.raises(RuntimeError):
+        rk.text_retrieval()
+
+
+class _FakeTasksModel(torch.nn.Module):
+    """Stands in for BertForVLTasks in the host-logic test: the 'logit' of a pair is a fixed function of its inputs."""
+
+    def forward(self, question, features, spatials, task, segment_ids, input_mask, image_mask):
+        return (features.sum((1, 2)).view(-1, 1) + question[:, :1].float() * 0.001, None, None, None)
+
+
+def _retrieval_batches(C, I, chunk):
+    g = torch.Generator().manual_seed(17)
+    feats = torch.randn(I, 3, 4, generator=g)
+    out = []
+    for c in range(C):
+        for part in range(I // chunk):
+            sl = slice(part * chunk, (part + 1) * chunk)
+            target = (torch.arange(I)[sl] == c % I).long().view(1, chunk)
+            out.append((feats[sl].unsqueeze(0), torch.zeros(1, chunk, 3, 5), torch.ones(1, chunk, 3), torch.full((1, 6), c),
+                        torch.ones(1, 6), torch.zeros(1, 6), target, torch.tensor(c), torch.tensor(part)))
+    return out
+
+
+def _sharded_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from volta_b200.retrieval import RetrievalRanker, evaluate_retrieval
+        C, I, chunk = 9, 8, 4
+        batches = _retrieval_batches(C, I, chunk)
+        rk = evaluate_retrieval(_FakeTasksModel(), "TASK8", batches, RetrievalRanker(C, I, "cpu", chunk=chunk), "cpu")
+        mine = sum(rk.owns(k) for k in range(len(batches)))
+        assert mine in (len(batches) // world, len(batches) // world + 1)
+        out.put((rank, rk.score_matrix.clone(), rk.target_matrix.clone()))
+    except Exception as e:  # noqa
+        out.put((rank, repr(e), None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_evaluation_rebuilds_the_single_process_matrices_gloo():
+    """Two gloo ranks score disjoint halves of the (caption x chunk) grid; after merge() both hold exactly the matrices
+    one process computes alone."""
+    import socket
+    import torch.multiprocessing as mp
+    from volta_b200.retrieval import RetrievalRanker, evaluate_retrieval
+    C, I, chunk = 9, 8, 4
+    single = evaluate_retrieval(_FakeTasksModel(), "TASK8", _retrieval_batches(C, I, chunk),
+                                RetrievalRanker(C, I, "cpu", chunk=chunk), "cpu")
+    assert int(single.target_matrix.sum()) == C
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, scores, targets in results:
+        assert targets is not None, scores
+        assert torch.equal(scores, single.score_matrix) and torch.equal(targets, single.target_matrix)
 
 
 # ----------------------------------------------------------------------------------------------- GPU

@@ -12,6 +12,7 @@ Ties between scores keep index order (the reference's unstable argsort leaves th
 """
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import ops
 
@@ -30,9 +31,9 @@ class RetrievalRanker:
     ranks, top20, metrics = ranker.image_retrieval();  ranks_t, metrics_t = ranker.text_retrieval()"""
 
     def __init__(self, num_captions=5000, num_images=1000, device="cuda", chunk=500, topk=20):
+        # the matrices are buffers (any device: the bookkeeping and the cross-rank merge are plumbing); RANKING has no
+        # CPU path - image_retrieval() / text_retrieval() raise unless the buffers live on a CUDA device
         device = torch.device(device)
-        if device.type != "cuda":
-            raise RuntimeError("volta_b200.retrieval has no CPU path: a CUDA (sm_100a) device is required")
         self.C, self.I, self.chunk, self.topk = int(num_captions), int(num_images), int(chunk), int(topk)
         self.score_matrix = torch.zeros(self.C, self.I, dtype=torch.float32, device=device)
         self.target_matrix = torch.zeros(self.C, self.I, dtype=torch.uint8, device=device)
@@ -50,8 +51,33 @@ class RetrievalRanker:
         self.score_matrix.copy_(scores.to(self.score_matrix.device, non_blocking=True))
         self.target_matrix.copy_((targets == 1).to(self.target_matrix.device, non_blocking=True))
 
+    # ---- data parallel evaluation (retrieval row) -------------------------------------------------
+    def owns(self, step, rank=None, world=None):
+        """Work item `step` (the i-th batch of the evaluation loop, eval_retrieval.py:168: one caption against one chunk
+        of 500 images) belongs to rank step % world.  The reference runs the loop on ONE GPU (:150-152 rejects more);
+        here every rank scores its share of the (caption x chunk) grid with its own model replica - no collective on the
+        data path."""
+        if world is None:
+            world = dist.get_world_size() if dist.is_initialized() else 1
+        if rank is None:
+            rank = dist.get_rank() if dist.is_initialized() else 0
+        return int(step) % world == rank
+
+    def merge(self, group=None):
+        """One exchange at the end: every pair was scored by exactly one rank and is zero elsewhere, so a SUM of the
+        score matrices (x + 0 is exact) and a MAX of the target matrices reproduce the single-GPU matrices on every
+        rank (20 MB + 5 MB for Flickr30k)."""
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.score_matrix, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(self.target_matrix, op=dist.ReduceOp.MAX, group=group)
+
+    def _require_device(self):
+        if not self.score_matrix.is_cuda:
+            raise RuntimeError("volta_b200.retrieval has no CPU path: ranking needs the matrices on a CUDA (sm_100a) device")
+
     def image_retrieval(self, num_captions=None):
         """Rank of the first matching image for captions [0, num_captions) (the running print of :210-220 uses a prefix)."""
+        self._require_device()
         C = self.C if num_captions is None else int(num_captions)
         rank = torch.empty(C, dtype=torch.int32, device=self.score_matrix.device)
         top = torch.empty(C, self.topk, dtype=torch.int32, device=self.score_matrix.device)
@@ -60,7 +86,29 @@ class RetrievalRanker:
         return ranks, top.cpu().numpy(), recall_metrics(ranks)
 
     def text_retrieval(self):
+        self._require_device()
         rank = torch.empty(self.I, dtype=torch.int32, device=self.score_matrix.device)
         ops.retrieval_ranks(self.score_matrix, self.target_matrix, 1, rank)
         ranks = rank.cpu().numpy()
         return ranks, recall_metrics(ranks)
+
+
+def evaluate_retrieval(model, task, batches, ranker, device, group=None):
+    """The evaluation loop of eval_retrieval.py:168-198 over `batches` (tuples as RetrievalDatasetVal yields them:
+    features, spatials, image_mask, question, input_mask, segment_ids, target, caption_idx, image_idx), sharded over the
+    ranks of `group` by batch index, merged once at the end.  `model` is a BertForVLTasks replica in eval mode; returns
+    the ranker (matrices complete on every rank)."""
+    with torch.no_grad():
+        for step, batch in enumerate(batches):
+            if not ranker.owns(step, None if group is None else dist.get_rank(group),
+                               None if group is None else dist.get_world_size(group)):
+                continue
+            batch = tuple(t.to(device, non_blocking=True) for t in batch)
+            features, spatials, image_mask, question, input_mask, segment_ids, target, caption_idx, image_idx = batch
+            features, spatials, image_mask = features.squeeze(0), spatials.squeeze(0), image_mask.squeeze(0)
+            n = features.size(0)
+            question, segment_ids, input_mask = question.repeat(n, 1), segment_ids.repeat(n, 1), input_mask.repeat(n, 1)
+            vil_logit = model(question, features, spatials, task, segment_ids, input_mask, image_mask)[0]
+            ranker.update(caption_idx, image_idx, vil_logit, target)
+    ranker.merge(group)
+    return ranker
