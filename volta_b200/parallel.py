@@ -186,7 +186,7 @@ class DistributedDataParallel(torch.nn.Module):
         return self._bucketer
 
     def _on_progress(self, frontier_offset):
-        if self.delay_allreduce or self.world_size == 1 or not torch.is_grad_enabled() and False:
+        if self.delay_allreduce or self.world_size == 1:
             return
         b = self._ensure_bucketer()
         if b.hi == b.total and not b.works:
