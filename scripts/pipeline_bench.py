@@ -28,6 +28,7 @@ ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--regions", type=int, default=36)
 ap.add_argument("--iters", type=int, default=50)
 ap.add_argument("--cpu-batches", type=int, default=3)
+ap.add_argument("--kernel-only", action="store_true", help="device time only (no host-buffer leg, no CPU baseline)")
 ap.add_argument("--once", action="store_true", help="one eager launch per dtype combination on a cold batch (the command ncu profiles)")
 args = ap.parse_args()
 
@@ -93,11 +94,17 @@ for in_dt, out_dt, tag in ((torch.float32, torch.bfloat16, "fp32->bf16"), (torch
     host_ms = timed(lambda i: asm(**{k: devs[i % POOL][k] for k in KEYS}), args.iters)
     out["kernel " + tag] = {"us": ms * 1e3, "algorithmic_bytes": nbytes, "gbs": nbytes / ms / 1e6, "frac_of_hbm_peak": nbytes / ms / 1e6 / peak,
                             "samples_per_s": B / ms * 1e3, "us_per_call_through_the_python_class": host_ms * 1e3}
+    if args.kernel_only:
+        continue
     pinned = [{k: v.pin_memory() for k, v in r.items()} for r in raws]
     for p in pinned:
         p["raw_feat"] = p["raw_feat"].to(in_dt).pin_memory()
     ms = timed(lambda i: asm(device=dev, **{k: pinned[i % POOL][k] for k in ("raw_feat", "raw_box", "image_hw", "num_boxes", "sel")}), args.iters)
     out["e2e " + tag] = {"ms": ms, "samples_per_s": B / ms * 1e3, "h2d_bytes": B * R * F * esz_in + B * R * 17 + B * 12}
+
+if args.kernel_only:
+    print(json.dumps(out))
+    sys.exit(0)
 
 from oracle.pipeline_oracle import assemble_region_batch  # noqa: E402  (timed CPU baseline only)
 

@@ -80,7 +80,7 @@ def test_kernel_equals_the_reference_loader_bit_for_bit(name, golden_dir):
 @pytest.mark.gpu
 @pytest.mark.parametrize("B,R,F,full,add_global,num_locs", [
     (5, 36, 2048, False, "first", 5), (3, 100, 2048, False, "last", 5), (2, 7, 40, False, "first", 4),
-    (1, 1, 8, True, "first", 5), (4, 12, 1024, False, "none", 5), (256, 36, 2048, True, "first", 5)])
+    (1, 1, 8, True, "first", 5), (3, 9, 30, False, "first", 5), (4, 12, 1024, False, "none", 5), (256, 36, 2048, True, "first", 5)])
 def test_kernel_equals_the_oracle(B, R, F, full, add_global, num_locs):
     raw = raw_region_batch(B, R, feat_dim=F, seed=100 + B + R, full=full)
     feat, loc, mask, label, count = _device_run(raw, raw["sel"], num_locs, add_global, torch.float32)

@@ -17,7 +17,7 @@ namespace pipeline {
 
 constexpr int THREADS = 128;
 constexpr int MAX_REGIONS = 1024;
-constexpr int U = 12;  // row loads in flight per thread (36 regions = 3 rounds): the per-thread chain is latency-bound
+constexpr int U = 10;  // row loads in flight per thread: the per-thread chain is latency-bound; 10 keeps the fp32 kernels at 72 registers (one wave)
 
 // W consecutive elements <-> W floats; W = 16 bytes of the INPUT type, so every load is a 16-byte vector.
 template <typename T, int W> struct Pack;
@@ -53,13 +53,14 @@ template <typename T> struct Pack<T, 1> {
   static __device__ __forceinline__ void store(T* p, const float (&v)[1]) { *p = from_f<T>(v[0]); }
 };
 
-// ONE launch, grid (column groups, samples).  A thread owns W columns of one sample and walks the regions: copy (or
-// zero) the row, add it to the running sum in the reference's order.  While those loads are in flight nothing else is
+// ONE launch, grid (column groups, samples).  A thread owns W columns of one sample and walks the live regions (a
+// block-wide list built once): copy the row, add it to the running sum in the reference's order; the other rows are
+// written as zeros (adding them would not change the sum).  While those loads are in flight nothing else is
 // needed; the divisor of the mean (regions that do not overlap a picked one) is computed by the block afterwards from
 // the sample's boxes in shared memory, and the block of the first column group also writes the sample's boxes, mask
 // and labels.  Rows that are zeroed or beyond the box count are not read.
 template <typename TIn, typename TOut, int W>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, W == 4 ? 7 : 4)   // fp32 input: 1024 blocks at B = 256 stay ONE wave on 148 SMs
 region_batch_kernel(const TIn* __restrict__ raw, const float* __restrict__ raw_box, const float* __restrict__ image_hw,
                     const int32_t* __restrict__ num_boxes, const uint8_t* __restrict__ sel, int R, int F, int num_locs,
                     int global_pos, TOut* __restrict__ out, float* __restrict__ loc, int64_t* __restrict__ mask,
@@ -67,7 +68,9 @@ region_batch_kernel(const TIn* __restrict__ raw, const float* __restrict__ raw_b
   __shared__ float4 box_s[MAX_REGIONS];
   __shared__ float area_s[MAX_REGIONS];
   __shared__ uint8_t sel_s[MAX_REGIONS];
+  __shared__ uint16_t rows_s[MAX_REGIONS];
   __shared__ int32_t warp_cnt[THREADS / 32];
+  __shared__ int32_t n_live_s;
   const int b = blockIdx.y, t = threadIdx.x;
   const int nb = max(0, min(num_boxes[b], R));
   const int V = R + (global_pos != 0 ? 1 : 0), off = global_pos == 1 ? 1 : 0;
@@ -77,8 +80,28 @@ region_batch_kernel(const TIn* __restrict__ raw, const float* __restrict__ raw_b
   float4 box0 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (t < nb) box0 = *reinterpret_cast<const float4*>(raw_box + ((int64_t)b * R + t) * 4);
   __syncthreads();
+  // row lists (warp 0, ballot compaction, ascending): `rows_s[0, n_live)` are read and summed, the rows from the end
+  // of the array downwards (`rows_s[R-1-k]`, k < R - n_live) are written as zeros - the feature loop then carries no
+  // per-row decisions
+  if (t < 32) {
+    int n_l = 0, n_d = 0;
+    for (int base = 0; base < R; base += 32) {
+      const int j = base + t;
+      const bool in = j < R;
+      const bool lv = in && j < nb && sel_s[j] != 1;
+      const unsigned ml = __ballot_sync(0xffffffffu, lv), md = __ballot_sync(0xffffffffu, in && !lv);
+      const unsigned below = (1u << t) - 1u;
+      if (lv) rows_s[n_l + __popc(ml & below)] = (uint16_t)j;
+      else if (in) rows_s[R - 1 - (n_d + __popc(md & below))] = (uint16_t)j;
+      n_l += __popc(ml);
+      n_d += __popc(md);
+    }
+    if (t == 0) n_live_s = n_l;
+  }
+  __syncthreads();
+  const int n_live = n_live_s;
 
-  // ---- features: copy / zero the rows, running sum ----
+  // ---- features: copy the live rows with a running sum (the reference's order), zero the others ----
   const int c = (blockIdx.x * THREADS + t) * W;
   const bool active = c < F;
   float sum[W];
@@ -87,24 +110,36 @@ region_batch_kernel(const TIn* __restrict__ raw, const float* __restrict__ raw_b
   if (active) {
     const TIn* src = raw + (int64_t)b * R * F + c;
     TOut* dst = out + ((int64_t)b * V + off) * F + c;
-    for (int r0 = 0; r0 < R; r0 += U) {
+    int k0 = 0;
+    for (; k0 + U <= n_live; k0 += U) {            // full rounds: U loads in flight, no predicates
       float v[U][W];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int r = r0 + u;
-#pragma unroll
-        for (int w = 0; w < W; ++w) v[u][w] = 0.f;
-        if (r < nb && sel_s[r] != 1) Pack<TIn, W>::load(src + (int64_t)r * F, v[u]);
-      }
+      for (int u = 0; u < U; ++u) Pack<TIn, W>::load(src + (int64_t)rows_s[k0 + u] * F, v[u]);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int r = r0 + u;
-        if (r >= R) break;
 #pragma unroll
         for (int w = 0; w < W; ++w) sum[w] = __fadd_rn(sum[w], v[u][w]);
-        Pack<TOut, W>::store(dst + (int64_t)r * F, v[u]);
+        Pack<TOut, W>::store(dst + (int64_t)rows_s[k0 + u] * F, v[u]);
       }
     }
+    if (k0 < n_live) {                             // last, partial round
+      float v[U][W];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (k0 + u < n_live) Pack<TIn, W>::load(src + (int64_t)rows_s[k0 + u] * F, v[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k0 + u < n_live) {
+#pragma unroll
+          for (int w = 0; w < W; ++w) sum[w] = __fadd_rn(sum[w], v[u][w]);
+          Pack<TOut, W>::store(dst + (int64_t)rows_s[k0 + u] * F, v[u]);
+        }
+      }
+    }
+    float zero[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) zero[w] = 0.f;
+    for (int k = n_live; k < R; ++k) Pack<TOut, W>::store(dst + (int64_t)rows_s[k] * F, zero);
   }
 
   for (int j = t; j < R; j += THREADS) {
