@@ -99,11 +99,15 @@ def test_row_split_launch_plan_matches_oracle(name, monkeypatch):
     assert real is not forced
 
 
-def test_packed_rows_plan_matches_oracle(monkeypatch):
+@pytest.mark.parametrize("name", ["mini_ctrl_vilbert", "mini_ctrl_lxmert", "mini_ctrl_visualbert", "mini_ctrl_uniter",
+                                  "mini_ctrl_vlbert"])
+def test_packed_rows_plan_matches_oracle(name, monkeypatch):
     """engine.bert_fwd packs the valid rows of both streams between the embeddings and the heads (device-side counts for
     the GEMMs / LayerNorms, per-sample offsets for the attention).  The plan needs the tensor-core kernels on the device;
     here it is forced on under the emulation - the host logic (packing plan, limits, zero-row invariant, un-packing) must
-    reproduce the oracle's losses and every parameter gradient on a batch whose text rows end on a 256-row boundary."""
+    reproduce the oracle's losses and every parameter gradient on a batch whose text rows end on a 256-row boundary.
+    ctrl_lxmert / the single-stream families have SHARED sub-layers (one GEMM over the joint buffer: two runs of valid
+    rows, weight and bias gradients reduced per run) - the plan behind VOLTA_B200_PACK_SHARED=1."""
     from volta_b200 import engine
     from volta_b200.synthetic import pretraining_batch
     emu_ops.install(monkeypatch)
@@ -114,7 +118,7 @@ def test_packed_rows_plan_matches_oracle(monkeypatch):
         taken.append(ok)
         return ok
     monkeypatch.setattr(engine, "_pack_supported", forced)
-    g, cfg, _, model, state = _build("mini_ctrl_vilbert")
+    g, cfg, _, model, state = _build(name)
     b = pretraining_batch(32, 8, 9, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
     losses = model(b["input_ids"], b["image_feat"], b["image_loc"], b["segment_ids"], b["input_mask"], b["image_mask"],
                    b["lm_label_ids"], b["image_label"], b["image_cls"], None, None, None, None, None, b["is_match"])
@@ -129,4 +133,4 @@ def test_packed_rows_plan_matches_oracle(monkeypatch):
         rg = P[key].grad if P[key].grad is not None else torch.zeros_like(P[key])
         got = p.grad if p.grad is not None else torch.zeros_like(p)
         err = float((got - rg).norm()) / max(float(rg.norm()), 1e-6)
-        assert err < 2e-3, (key, err)
+        assert err < 2e-3, (name, key, err)

@@ -225,6 +225,39 @@ def test_packed_rows_match_padded_layout(dropout, monkeypatch):
         assert all(abs(a - c) < 0.1 * max(1.0, abs(c)) for a, c in zip(l1, l0)), (l1, l0)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("VOLTA_B200_PACK_SHARED") != "1",
+                    reason="packed rows for shared sub-layers are opt-in until measured on a B200 (VOLTA_B200_PACK_SHARED=1)")
+@pytest.mark.parametrize("name", ["mini_ctrl_lxmert", "mini_ctrl_visualbert", "mini_ctrl_uniter"])
+def test_packed_rows_with_shared_sublayers_match_padded_layout(name, monkeypatch):
+    """ctrl_lxmert's cross layers and every layer of the single-stream models share their weights between the streams:
+    one GEMM over the joint buffer with two runs of valid rows.  Same losses and parameter gradients as the padded
+    layout (the host plan is checked against the oracle on CPU: test_engine_emulated.py)."""
+    from volta_b200 import engine
+    from volta_b200.synthetic import pretraining_batch
+    g, cfg, _ = load_case(name)
+    b = pretraining_batch(32, 8, 9, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
+    d = {k: v.cuda() for k, v in b.items()}
+    runs = {}
+    for packed in (True, False):
+        monkeypatch.setattr(engine, "PACK_ROWS", packed)
+        monkeypatch.setattr(engine, "PACK_SHARED", packed)
+        model = volta_b200.BertForVLPreTraining(cfg)
+        model.load_state_dict(seeded_state_dict(model.state_dict(), seed=0))
+        model.eval().cuda()
+        model._use_cuda_graphs = False
+        n0 = engine_launches()
+        l = _losses(model, d)
+        (l[0] + l[1] + l[2]).sum().backward()
+        runs[packed] = ([float(x) for x in l], {k: p.grad.clone() for k, p in model.named_parameters()}, engine_launches() - n0)
+    (l1, g1, n1), (l0, g0, n0) = runs[True], runs[False]
+    assert n1 > n0, "the packed plan adds its gather / scatter / zero-row launches: was it taken?"
+    assert all(abs(a - c) < 2e-3 * max(1.0, abs(a)) for a, c in zip(l1, l0)), (l1, l0)
+    for k in g1:
+        den = float(g0[k].norm())
+        if den > 1e-6:
+            assert float((g1[k] - g0[k]).norm()) / den < 3e-2, k
+
+
 def test_masked_lm_rows_only_matches_all_positions_decoder(monkeypatch):
     """The masked-LM head runs the decoder / criterion on the labelled rows only (device-side count).  Against the
     all-positions decoder of the reference (volta/encoders.py:686-696): same losses, same gradients for every parameter."""

@@ -221,6 +221,10 @@ def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, 
     lin2 / split: the rows [split, M) belong to a second Linear - two weight-gradient launches over the two row ranges,
     ONE row-split launch for dx."""
     parts = [(lin, x, dy)] if lin2 is None else [(lin, x[:split], dy[:split]), (lin2, x[split:], dy[split:])]
+    if lin2 is None and getattr(rt, "pack_on", False) and dy.shape[0] == rt.Mt + rt.Mv and lim is None:
+        # packed rows, shared weights over the joint buffer: each stream is its own run of valid rows, so the reduction
+        # of the weight gradient (and of the bias gradient) runs per stream, both accumulating into the same parameter
+        parts = [(lin, x[:rt.Mt], dy[:rt.Mt]), (lin, x[rt.Mt:], dy[rt.Mt:])]
     # lim = int32 [count, count padded to 256] on the device (compacted head rows): only that many rows hold data
     wl = dict(k_limit=lim[1:2]) if lim is not None else {}
     rl = dict(row_limit=lim[1:2]) if lim is not None else {}
@@ -793,6 +797,11 @@ def _pool_bwd(rt, pooler, dpooled, pooled, a, dx, L):
 # sample b at cu[b] (vb_attn_args::cu_*), the LayerNorms stop at the count (vb_row_seqs).  Valid rows, losses and
 # parameter gradients are what the padded layout gives; shapes, launches and CUDA graphs stay static.
 PACK_ROWS = os.environ.get("VOLTA_B200_PACK_ROWS", "1") != "0"
+# Shared sub-layers (ctrl_lxmert's cross layers; every layer of the single-stream models) run ONE GEMM over the joint
+# buffer: packed, it holds two runs of valid rows (vb_gemm_args::m_limit / m_limit2 / limit_seg_M forward and dgrad;
+# the weight / bias gradients reduce per run, linear_bwd).  The host plan reproduces the oracle under the emulation for
+# every family (tests/test_engine_emulated.py); it has not run on a B200 yet, so it is opt-in until measured.
+PACK_SHARED = os.environ.get("VOLTA_B200_PACK_SHARED", "0") == "1"
 
 
 class _Pack:
@@ -811,10 +820,10 @@ def _pack_supported(rt, bert, keep_layers):
     for n, layer in enumerate(bert.encoder.layer):
         if bert.encoder.num2type[n] == "attn":
             sa = layer.attention_self
-            if sa.share_layer or (sa.has_text and sa.attention_head_size not in (64, 128)) or \
+            if (sa.share_layer and not PACK_SHARED) or (sa.has_text and sa.attention_head_size not in (64, 128)) or \
                     (sa.has_vision and sa.v_attention_head_size not in (64, 128)):
                 return False
-        elif layer.intermediate.share_layer:
+        elif layer.intermediate.share_layer and not PACK_SHARED:
             return False
     return True
 
