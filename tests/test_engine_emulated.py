@@ -99,27 +99,31 @@ def test_row_split_launch_plan_matches_oracle(name, monkeypatch):
     assert real is not forced
 
 
-@pytest.mark.parametrize("name", ["mini_ctrl_vilbert", "mini_ctrl_lxmert", "mini_ctrl_visualbert", "mini_ctrl_uniter",
-                                  "mini_ctrl_vlbert"])
-def test_packed_rows_plan_matches_oracle(name, monkeypatch):
+@pytest.mark.parametrize("name,shape", [("mini_ctrl_vilbert", (32, 8, 9)), ("mini_ctrl_lxmert", (32, 8, 9)),
+                                        ("mini_ctrl_visualbert", (32, 8, 9)), ("mini_ctrl_uniter", (32, 8, 9)),
+                                        ("mini_ctrl_vlbert", (32, 8, 9)), ("mini_ctrl_vilbert", (30, 8, 9)),
+                                        ("mini_ctrl_lxmert", (37, 7, 8)), ("mini_ctrl_visualbert", (30, 8, 9))])
+def test_packed_rows_plan_matches_oracle(name, shape, monkeypatch):
     """engine.bert_fwd packs the valid rows of both streams between the embeddings and the heads (device-side counts for
     the GEMMs / LayerNorms, per-sample offsets for the attention).  The plan needs the tensor-core kernels on the device;
     here it is forced on under the emulation - the host logic (packing plan, limits, zero-row invariant, un-packing) must
     reproduce the oracle's losses and every parameter gradient on a batch whose text rows end on a 256-row boundary.
     ctrl_lxmert / the single-stream families have SHARED sub-layers (one GEMM over the joint buffer: two runs of valid
-    rows, weight and bias gradients reduced per run) - the plan behind VOLTA_B200_PACK_SHARED=1."""
+    rows, weight and bias gradients reduced per run) - the plan behind VOLTA_B200_PACK_SHARED=1.  Shapes whose B*T is not a
+    multiple of 256 (30 x 8, 37 x 7) pad the text segment of the packed buffers to the next tile edge
+    (VOLTA_B200_PACK_ANY_ROWS=1)."""
     from volta_b200 import engine
     from volta_b200.synthetic import pretraining_batch
     emu_ops.install(monkeypatch)
     taken = []
 
     def forced(rt, bert, keep_layers):
-        ok = not keep_layers and rt.Mt % 256 == 0 and rt.Mt != rt.Mv
+        ok = not keep_layers and engine._pad256(rt.Mt) != rt.Mv
         taken.append(ok)
         return ok
     monkeypatch.setattr(engine, "_pack_supported", forced)
     g, cfg, _, model, state = _build(name)
-    b = pretraining_batch(32, 8, 9, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
+    b = pretraining_batch(*shape, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
     losses = model(b["input_ids"], b["image_feat"], b["image_loc"], b["segment_ids"], b["input_mask"], b["image_mask"],
                    b["lm_label_ids"], b["image_label"], b["image_cls"], None, None, None, None, None, b["is_match"])
     assert taken and all(taken)

@@ -227,20 +227,24 @@ def test_packed_rows_match_padded_layout(dropout, monkeypatch):
 
 @pytest.mark.skipif(__import__("os").environ.get("VOLTA_B200_PACK_SHARED") != "1",
                     reason="packed rows for shared sub-layers are opt-in until measured on a B200 (VOLTA_B200_PACK_SHARED=1)")
-@pytest.mark.parametrize("name", ["mini_ctrl_lxmert", "mini_ctrl_visualbert", "mini_ctrl_uniter"])
-def test_packed_rows_with_shared_sublayers_match_padded_layout(name, monkeypatch):
+@pytest.mark.parametrize("name,shape", [("mini_ctrl_lxmert", (32, 8, 9)), ("mini_ctrl_visualbert", (32, 8, 9)),
+                                        ("mini_ctrl_uniter", (32, 8, 9)), ("mini_ctrl_vilbert", (30, 8, 9)),
+                                        ("mini_ctrl_lxmert", (37, 7, 8))])
+def test_packed_rows_with_shared_sublayers_match_padded_layout(name, shape, monkeypatch):
     """ctrl_lxmert's cross layers and every layer of the single-stream models share their weights between the streams:
     one GEMM over the joint buffer with two runs of valid rows.  Same losses and parameter gradients as the padded
-    layout (the host plan is checked against the oracle on CPU: test_engine_emulated.py)."""
+    layout (the host plan is checked against the oracle on CPU: test_engine_emulated.py).  30 x 8 and 37 x 7 text rows do
+    not end on a 256-row edge: the packed buffers pad their text segment (VOLTA_B200_PACK_ANY_ROWS)."""
     from volta_b200 import engine
     from volta_b200.synthetic import pretraining_batch
     g, cfg, _ = load_case(name)
-    b = pretraining_batch(32, 8, 9, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
+    b = pretraining_batch(*shape, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
     d = {k: v.cuda() for k, v in b.items()}
     runs = {}
     for packed in (True, False):
         monkeypatch.setattr(engine, "PACK_ROWS", packed)
         monkeypatch.setattr(engine, "PACK_SHARED", packed)
+        monkeypatch.setattr(engine, "PACK_ANY_ROWS", packed)
         model = volta_b200.BertForVLPreTraining(cfg)
         model.load_state_dict(seeded_state_dict(model.state_dict(), seed=0))
         model.eval().cuda()

@@ -802,6 +802,15 @@ PACK_ROWS = os.environ.get("VOLTA_B200_PACK_ROWS", "1") != "0"
 # the weight / bias gradients reduce per run, linear_bwd).  The host plan reproduces the oracle under the emulation for
 # every family (tests/test_engine_emulated.py); it has not run on a B200 yet, so it is opt-in until measured.
 PACK_SHARED = os.environ.get("VOLTA_B200_PACK_SHARED", "0") == "1"
+# The vision rows of a joint buffer must start on a 256-row tile edge.  When B*T is not a multiple of 256 (the reference
+# recipe: global batch 256 over 8 GPUs = 32 x 36 rows) the packed region can pad the TEXT segment of its buffers up to the
+# next edge (rt.Mt grows for the duration of the packed encoder; the padding rows are dropped rows of the plan, kept zero
+# like every row between a count and its tile edge).  Same status as PACK_SHARED: checked under the emulation, opt-in.
+PACK_ANY_ROWS = os.environ.get("VOLTA_B200_PACK_ANY_ROWS", "0") == "1"
+
+
+def _pad256(n):
+    return (n + 255) // 256 * 256
 
 
 class _Pack:
@@ -813,8 +822,8 @@ def _pack_supported(rt, bert, keep_layers):
         return False
     if rt.gemm_backend == _lib.GEMM_SIMT or rt.attn_backend == _lib.ATTN_SIMT or not torch.cuda.is_available():
         return False
-    if rt.Mt % 256 != 0 or rt.Mt == rt.Mv or rt.Mv == 0 or rt.T + rt.V > 160:   # 160: what one tensor-core attention block holds
-        return False
+    if (rt.Mt % 256 != 0 and not PACK_ANY_ROWS) or _pad256(rt.Mt) == rt.Mv or rt.Mv == 0 or rt.T + rt.V > 160:
+        return False                                                   # 160: what one tensor-core attention block holds
     if bert.config.fusion_method == "vl-bert_vqa":
         return False
     for n, layer in enumerate(bert.encoder.layer):
@@ -835,6 +844,9 @@ def _make_pack(rt):
         rows = rt.B * L
         keep = (torch.arange(L, device=rt.device, dtype=torch.int32)[None, :] < ln[:, None]).reshape(-1)
         keys = keep.to(torch.int64) - 1                                  # 0 = keep, -1 = drop
+        if tag == "t" and rows % 256 != 0:                               # text segment padded to the next tile edge
+            keys = torch.cat([keys, torch.full((_pad256(rows) - rows,), -1, dtype=torch.int64, device=rt.device)])
+            rows = _pad256(rows)
         lim = rt.empty(2, dtype=torch.int32)
         src, pos = rt.empty(rows, dtype=torch.int32), rt.empty(rows, dtype=torch.int32)
         ops.compact_plan(keys, 256, lim, src, pos, rt.empty(rows, dtype=torch.int64))
@@ -845,17 +857,29 @@ def _make_pack(rt):
 
 
 def _pack_pair(rt, x):
+    """Valid rows of both streams to the front of their segment; the text segment has rt.Mt rows (B*T, or B*T padded to a
+    256-row edge - _enter_packed)."""
     pk = rt.pack
-    y = Pair.alloc(rt, x.t.shape[0], x.t.shape[1], x.v.shape[0], x.v.shape[1])
+    y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
     ops.compact_gather(x.t, pk.src_t, pk.lim_t, y.t)
     ops.compact_gather(x.v, pk.src_v, pk.lim_v, y.v)
     _count(2)
     return y
 
 
+def _enter_packed(rt):
+    rt.rows_t = rt.Mt
+    rt.Mt = _pad256(rt.Mt)
+
+
+def _leave_packed(rt):
+    rt.pack_on = False
+    rt.Mt = rt.rows_t
+
+
 def _unpack_pair(rt, x):
     pk = rt.pack
-    y = Pair.alloc(rt, x.t.shape[0], x.t.shape[1], x.v.shape[0], x.v.shape[1])
+    y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1])
     ops.compact_scatter(x.t, pk.pos_t, y.t)
     ops.compact_scatter(x.v, pk.pos_v, y.v)
     _count(2)
@@ -909,6 +933,7 @@ def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
     rt.pack, rt.pack_on = None, False
     if _pack_supported(rt, bert, keep_layers):
         rt.pack = _make_pack(rt)
+        _enter_packed(rt)
         x = _pack_pair(rt, x)
         rt.pack_on = True
     tape, layers = [], []
@@ -921,7 +946,7 @@ def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
         if keep_layers:
             layers.append(x)
     if rt.pack is not None:
-        rt.pack_on = False
+        _leave_packed(rt)
         x = _unpack_pair(rt, x)
     pooled_t = pooled_v = None
     s_pool = {}
@@ -962,6 +987,7 @@ def bert_bwd(rt, bert, s, dx, dpooled_t, dpooled_v):
     rt.pack, rt.pack_on = s.get("pack"), False
     if rt.pack is not None:       # the encoder ran on packed rows: so does its backward
         rt.lens = s["lens"]
+        _enter_packed(rt)
         dx = _pack_pair(rt, dx)
         rt.pack_on = True
     for n in range(len(bert.encoder.layer) - 1, -1, -1):
@@ -973,7 +999,7 @@ def bert_bwd(rt, bert, s, dx, dpooled_t, dpooled_v):
         s["tape"][n] = None  # free activations as the backward retires them
         _notify_progress(rt, layer)
     if rt.pack is not None:
-        rt.pack_on = False
+        _leave_packed(rt)
         dx = _unpack_pair(rt, dx)
     embeddings_bwd(rt, bert, dx, s["emb"])
 
