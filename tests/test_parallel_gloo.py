@@ -73,3 +73,79 @@ def test_bucketed_allreduce_two_ranks_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The wrapper itself: volta_b200.parallel.DistributedDataParallel around a model whose C ABI is emulated in PyTorch
+# (tests/emu_ops.py) - parameter broadcast, progress hooks of the hand-written backward, bucket cuts, final flush.
+def _ddp_build():
+    import volta_b200
+    from golden_util import load_case
+    from volta_b200.synthetic import seeded_state_dict
+    g, cfg, _ = load_case("mini_ctrl_vilbert")
+    model = volta_b200.BertForVLPreTraining(cfg)
+    model.load_state_dict(seeded_state_dict(model.state_dict(), seed=0))
+    model.set_precision("fp32").eval()
+    return cfg, model
+
+
+def _ddp_step(model, cfg, seed):
+    from volta_b200.synthetic import pretraining_batch
+    b = pretraining_batch(4, 8, 9, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=seed)
+    model.zero_grad(set_to_none=True)
+    l = model(b["input_ids"], b["image_feat"], b["image_loc"], b["segment_ids"], b["input_mask"], b["image_mask"],
+              b["lm_label_ids"], b["image_label"], b["image_cls"], None, None, None, None, None, b["is_match"])
+    (l[0] + l[1] + l[2]).sum().backward()
+    return {k: p.grad.clone() for k, p in model.named_parameters()}
+
+
+def _ddp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import emu_ops
+        emu_ops.install(pytest.MonkeyPatch())
+        from volta_b200.parallel import DistributedDataParallel
+        cfg, ref_model = _ddp_build()
+        singles = [_ddp_step(ref_model, cfg, 100 + r) for r in range(world)]      # what each rank computes alone
+        report = {}
+        for wire in (None, torch.bfloat16):
+            cfg, model = _ddp_build()
+            if rank == 1:
+                with torch.no_grad():
+                    for p in model.parameters():
+                        p.add_(1.0)                     # the broadcast from rank 0 must overwrite this
+            ddp = DistributedDataParallel(model, message_size=200_000, allreduce_dtype=wire)
+            grads = _ddp_step(ddp, cfg, 100 + rank)
+            worst = 0.0
+            for k, got in grads.items():
+                expect = sum(s[k[len("module."):]] for s in singles) / world
+                worst = max(worst, float((got - expect).norm()) / max(float(expect.norm()), 1e-9))
+            report[str(wire)] = (worst, ddp.last_num_buckets)
+        out.put((rank, report))
+    except Exception:  # noqa
+        import traceback
+        out.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ddp_wrapper_over_the_emulated_engine_two_ranks_gloo():
+    """Every parameter gradient after backward() through the wrapper equals the mean of the two ranks' own gradients
+    (exactly with the fp32 wire, to bf16 rounding with allreduce_dtype=torch.bfloat16); the backward closed several
+    buckets on the way (apex: delay_allreduce=False, message_size)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, report in results:
+        assert isinstance(report, dict), report
+        worst, buckets = report["None"]
+        assert worst < 1e-6 and buckets > 2, (rank, report)
+        worst16, buckets16 = report["torch.bfloat16"]
+        assert worst16 < 1e-2 and buckets16 == buckets, (rank, report)
