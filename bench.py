@@ -52,6 +52,10 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--raw-input", default="", choices=["", "fp32", "bf16"],
+                    help="e2e leg: upload the RAW detector output (features in this dtype, pixel boxes, image sizes, the "
+                         "masking draws) and assemble image_feat / image_loc / image_mask / image_label on the device "
+                         "(volta_b200.pipeline.RegionBatchAssembler) inside the timed step")
     ap.add_argument("--no-optimizer-leg", action="store_true")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     return ap.parse_args()
@@ -251,11 +255,29 @@ def main():
             v.record_stream(main)
         pending.append((d, ev))
 
+    asm = None
+    if args.raw_input:
+        # the loader-side leg of SURVEY.md 8f rank 2: what travels is the detector output as stored, the batch is assembled
+        # on the device; image_feat stays fp32 so that the step replays the graph captured for the resident batch
+        from volta_b200.pipeline import RegionBatchAssembler
+        from volta_b200.synthetic import raw_region_batch
+        raw = raw_region_batch(B, V - 1, seed=4321 + rank, full=False)
+        if args.raw_input == "bf16":
+            raw["raw_feat"] = raw["raw_feat"].to(torch.bfloat16)
+        for k in ("image_feat", "image_loc", "image_mask", "image_label"):
+            del pinned[k]
+        pinned.update({k: v.pin_memory() for k, v in raw.items()})
+        h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+        asm = RegionBatchAssembler(V - 1, 2048, 5, "first", out_dtype=torch.float32)
+
     def step_e2e():
         if not pending:
             upload()
         d, ev = pending.pop(0)
         torch.cuda.current_stream().wait_event(ev)
+        if asm is not None:
+            feat, loc, mask, label, _ = asm(d["raw_feat"], d["raw_box"], d["image_hw"], d["num_boxes"], d["sel"])
+            d = dict(d, image_feat=feat, image_loc=loc, image_mask=mask, image_label=label)
         model.zero_grad(set_to_none=True)
         l = runner(*batch_args(d))
         # the losses are final once the forward has run: their device->host copy is queued before the backward, so the
@@ -301,6 +323,8 @@ def main():
         ms_e2e, _, _ = timed(step_e2e, args.steps, 2)
         e2e = {"value": B * world / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 12,
                "ms_per_step": ms_e2e}
+        if asm is not None:
+            e2e["input"] = "raw detector output (%s features), assembled on the device by vb_region_batch" % args.raw_input
 
     # optimizer-included step (reported next to the headline, which is the path alone): the
     # reference's clip_grad_norm_(5.0) + AdamW with one group per parameter + zero_grad, through volta_b200.optim.FusedAdamW
