@@ -379,7 +379,8 @@ int vb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, int64
  * output and the model call: box area + normalisation (volta/datasets/concept_cap_dataset.py:450-461), zeroing of the
  * regions picked for prediction and exclusion of the regions overlapping them from the mean (IoU > 0.4, :31-68,
  * :661-690), padding mask / labels (:562-568), and the mean-pooled global feature with its box and mask
- * (ConceptCapLoaderTrain.__iter__, :237-264; the same layout _image_features_reader.py:102-113 builds for the tasks).
+ * (ConceptCapLoaderTrain.__iter__, :237-264).  The task datasets' reader (_image_features_reader.py:102-113) builds the
+ * same layout but divides by the BOX count: identical when no region is picked and every sample has R boxes.
  *   raw_feat [B,R,F] in_dtype (fp32 as stored, or bf16 to halve the upload); raw_box [B,R,4] fp32 PIXELS x1,y1,x2,y2;
  *   image_hw [B,2] fp32 (h, w); num_boxes [B]; sel [B,R]: 0 = untouched, 1 = predicted + features zeroed, 2 = predicted,
  *   features kept (the host's random draws, :669-686).  Rows at or beyond num_boxes[b] are never read (treated as 0).

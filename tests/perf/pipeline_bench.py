@@ -1,8 +1,8 @@
 """Region batch assembly (vb_region_batch) at the Conceptual-Captions batch shape: B=256, 36 regions x 2048-d.
 
-    python scripts/pipeline_bench.py [--batch 256] [--iters 50] [--cpu-batches 3] [--once]
+    python tests/perf/pipeline_bench.py [--batch 256] [--iters 50] [--cpu-batches 3] [--once]
 
-Prints ONE JSON line:
+Lives under tests/ because its CPU-baseline leg times the oracle (test infrastructure).  Prints ONE JSON line:
   kernel     : device-resident detector output (a pool of batches larger than the 126 MB L2 rotates), CUDA events around
                a replayed CUDA graph of 20 back-to-back calls; algorithmic bytes = features read once (fp32 or bf16) + image_feat written once
                (+ boxes, masks, labels) -> GB/s against MEASURED_PEAKS.json hbm_gbs;
@@ -16,7 +16,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 

@@ -1,8 +1,8 @@
 """Retrieval ranking (vb_retrieval_ranks) on the reference's Flickr30k evaluation layout: 5000 captions x 1000 images.
 
-    python scripts/retrieval_bench.py
+    python tests/perf/retrieval_bench.py
 
-Prints ONE JSON line: device time of the row pass (+ top-20) and the column pass (CUDA events, 20 launches each;
+Lives under tests/ because its CPU-baseline leg times the oracle (test infrastructure).  Prints ONE JSON line: device time of the row pass (+ top-20) and the column pass (CUDA events, 20 launches each;
 algorithmic bytes = the 20 MB score matrix + the 5 MB target matrix read once per pass), and the same ranking done the
 reference's way - numpy argsort per row / column - by the oracle on one host core (the timed CPU baseline only)."""
 import json
@@ -10,7 +10,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import torch
 
