@@ -15,7 +15,8 @@ Parity status: PINNED.  `tests/golden/make_golden_pipeline.py` runs the UNMODIFI
 `msgpack_numpy` imports, a toy tokenizer) on seeded detector outputs and commits their outputs under
 `tests/golden/pipeline_*.pt`; `tests/test_pipeline.py` checks this file against them BIT FOR BIT.
 
-Nothing in `volta_b200/` imports this module; only `tests/` may.
+Nothing in `volta_b200/` imports this module; only `tests/` (incl. the timed CPU-baseline leg of `tests/perf/`) and
+`__graft_entry__.smoke()` may.
 """
 import numpy as np
 

@@ -10,7 +10,8 @@ Parity status: PINNED for distinct scores - `tests/golden/make_golden_retrieval.
 statements (read from /root/reference/eval_retrieval.py, lines cited above) on seeded matrices and commits the ranks
 under `tests/golden/retrieval_ranks.pt`; `tests/test_retrieval.py` checks this file against them exactly.
 
-Nothing in `volta_b200/` imports this module; only `tests/` may.
+Nothing in `volta_b200/` imports this module; only `tests/` (incl. the timed CPU-baseline leg of `tests/perf/`) and
+`__graft_entry__.smoke()` may.
 """
 import numpy as np
 
