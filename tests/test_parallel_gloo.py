@@ -149,3 +149,45 @@ def test_ddp_wrapper_over_the_emulated_engine_two_ranks_gloo():
         assert worst < 1e-6 and buckets > 2, (rank, report)
         worst16, buckets16 = report["torch.bfloat16"]
         assert worst16 < 1e-2 and buckets16 == buckets, (rank, report)
+
+
+def test_bucketer_tiles_the_buffer_for_any_frontier_sequence():
+    """Property (seeded random cases, one-rank gloo group): whatever the boundaries, message size and order of frontier
+    notifications, the issued ranges tile [0, total) exactly once from the end of the buffer towards offset 0, every
+    range but the flush reaches the message size, and simulate() - what the CUDA-graph executor cuts the backward by -
+    predicts exactly the notifications that issue a collective."""
+    import random
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()), RANK="0", WORLD_SIZE="1")
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        from volta_b200.parallel import GradBucketer
+        rnd = random.Random(1234)
+        for case in range(60):
+            total = rnd.randint(50, 5000)
+            bounds = sorted(set(rnd.randint(0, total) for _ in range(rnd.randint(0, 25))))
+            msg = rnd.choice([1, 10, 100, 1000, 10 ** 7])
+            flat = torch.arange(total, dtype=torch.float32)
+            b = GradBucketer(flat, bounds, message_size=msg, wire_dtype=rnd.choice([None, torch.bfloat16]))
+            cut = b.simulate()
+            frontiers = sorted((rnd.randint(0, total) for _ in range(rnd.randint(1, 30))), reverse=True)
+            if rnd.random() < 0.5:
+                frontiers.append(0)
+            for f in frontiers:
+                before = len(b.ranges)
+                predicted = cut(f)
+                b.advance(f)
+                assert predicted == (len(b.ranges) > before), (case, f)
+                assert all(lo >= f for lo, hi in b.ranges), (case, f, b.ranges)   # nothing below the frontier is sent
+            n = b.finish()
+            assert n == len(b.ranges)
+            hi = total
+            for lo, h in b.ranges:
+                assert h == hi and lo < h, (case, b.ranges)
+                hi = lo
+            assert hi == 0, (case, b.ranges)
+            for lo, h in b.ranges[:-1]:
+                assert h - lo >= msg or lo == 0, (case, msg, b.ranges)
+            assert torch.equal(flat, torch.arange(total, dtype=torch.float32).bfloat16().float() if b.wire is not None
+                               else torch.arange(total, dtype=torch.float32))
+    finally:
+        dist.destroy_process_group()
