@@ -93,6 +93,14 @@ def test_kernel_equals_the_oracle(B, R, F, full, add_global, num_locs):
 
 
 @pytest.mark.gpu
+def test_empty_batch_returns_empty_outputs():
+    raw = raw_region_batch(2, 8, feat_dim=16)
+    raw = {k: v[:0] for k, v in raw.items()}
+    feat, loc, mask, label, count = _device_run(raw, raw["sel"], 5, "first", torch.float32)
+    assert feat.shape == (0, 9, 16) and loc.shape == (0, 9, 5) and mask.shape == (0, 9) and label.shape == (0, 8) and count.numel() == 0
+
+
+@pytest.mark.gpu
 def test_bf16_output_is_the_rounded_fp32_result_and_bf16_upload_is_accepted():
     raw = raw_region_batch(6, 36, seed=5, full=False)
     o_feat = torch.from_numpy(_oracle(raw, raw["sel"], 5, "first")[0])

@@ -70,6 +70,8 @@ class RegionBatchAssembler:
         mask = torch.empty(B, V, dtype=torch.int64, device=device)
         label = torch.empty(B, R, dtype=torch.int64, device=device)
         count = torch.empty(B, dtype=torch.int32, device=device)
+        if B == 0:        # an empty batch has nothing to assemble (and no buffers to point at)
+            return feat, loc, mask, label, count
         with torch.cuda.device(device):
             ops.region_batch(raw_feat, raw_box, image_hw, num_boxes, sel, self.global_pos, feat, loc, mask, label, count)
         return feat, loc, mask, label, count
