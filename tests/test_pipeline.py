@@ -95,8 +95,10 @@ def test_kernel_equals_the_oracle(B, R, F, full, add_global, num_locs):
 @pytest.mark.gpu
 def test_empty_batch_returns_empty_outputs():
     raw = raw_region_batch(2, 8, feat_dim=16)
-    raw = {k: v[:0] for k, v in raw.items()}
-    feat, loc, mask, label, count = _device_run(raw, raw["sel"], 5, "first", torch.float32)
+    from volta_b200.pipeline import RegionBatchAssembler
+    raw = {k: v[:0].cuda() for k, v in raw.items()}
+    asm = RegionBatchAssembler(8, feature_size=16, out_dtype=torch.float32)
+    feat, loc, mask, label, count = asm(raw["raw_feat"], raw["raw_box"], raw["image_hw"], raw["num_boxes"], raw["sel"])
     assert feat.shape == (0, 9, 16) and loc.shape == (0, 9, 5) and mask.shape == (0, 9) and label.shape == (0, 8) and count.numel() == 0
 
 
