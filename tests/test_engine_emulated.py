@@ -138,3 +138,40 @@ def test_packed_rows_plan_matches_oracle(name, shape, monkeypatch):
         got = p.grad if p.grad is not None else torch.zeros_like(p)
         err = float((got - rg).norm()) / max(float(rg.norm()), 1e-6)
         assert err < 2e-3, (name, key, err)
+
+
+def _tasks_cases():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_tasks
+    return make_golden_tasks
+
+
+@pytest.mark.parametrize("name", ["tasks_mini_ctrl_vilbert", "tasks_mini_ctrl_visualbert"])
+def test_task_heads_host_logic_matches_reference(name, monkeypatch):
+    """engine.tasks_forward (fusion of the pooled outputs, every head type, V-logit masking) with the C ABI emulated:
+    predictions equal the unmodified reference's (tests/golden/tasks_*.pt), and a task loss back-propagates into every
+    parameter the prediction depends on (fine-tuning goes through the same hand-written backward)."""
+    import os
+    from golden_util import ROOT
+    mk = _tasks_cases()
+    emu_ops.install(monkeypatch)
+    g = torch.load(os.path.join(ROOT, "tests", "golden", name + ".pt"), weights_only=False)
+    cfg = volta_b200.BertConfig.from_dict(g["config"])
+    model = volta_b200.BertForVLTasks(cfg, g["task_cfg"], g["tasks"])
+    model.load_state_dict(seeded_state_dict(model.state_dict(), seed=0))
+    model.set_precision("fp32").eval()
+    b = mk.case_batch(name)
+    for t in g["tasks"]:
+        model.zero_grad(set_to_none=True)
+        vil, _, _, _ = model(b["input_ids"], b["image_feat"], b["image_loc"], t, b["segment_ids"], b["input_mask"], b["image_mask"])
+        ref = g["pred"][t]
+        got = vil.detach().float().reshape(ref.shape)
+        keep = ref > -5000.0
+        assert torch.equal(keep, got > -5000.0), (name, t)
+        assert float((got[keep] - ref[keep]).norm() / ref[keep].norm().clamp(min=1e-6)) < 2e-4, (name, t)
+        (vil.float().reshape(ref.shape) * keep).sum().backward()
+        touched = [k for k, p in model.named_parameters() if p.grad is not None and float(p.grad.abs().sum()) > 0]
+        assert any(k.startswith("bert.encoder.layer.0.") for k in touched), (name, t)
+        assert any(k.startswith("clfs_dict.%s." % t) for k in touched), (name, t, [k for k in touched if "clfs" in k])
