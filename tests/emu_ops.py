@@ -546,10 +546,37 @@ def fill(buf, value=0):
     buf.zero_()
 
 
+def sumsq(x, out):
+    out += (x.double() ** 2).sum().float()
+    return out
+
+
+def adamw_flat(p, g, m, v, p16, chunk_group, group_hp, beta1, beta2, eps, sumsq_buf=None, max_norm=0.0):
+    """vb_adamw_flat as documented in include/volta_b200.h: chunk_group[i] = hyper-parameter group of elements
+    [64 i, 64 i + 64) (-1 = not optimised), group_hp[g] = (lr, weight_decay, step_size, active)."""
+    coef = 1.0
+    if sumsq_buf is not None and max_norm > 0:
+        coef = min(1.0, max_norm / (float(sumsq_buf.sqrt()) + 1e-6))
+    grp = chunk_group.to(torch.int64).repeat_interleave(64)
+    live = grp >= 0
+    hp = group_hp[grp.clamp(min=0)]
+    live = live & (hp[:, 3] != 0)
+    gg = g * coef
+    m_new = beta1 * m + (1 - beta1) * gg
+    v_new = beta2 * v + (1 - beta2) * gg * gg
+    x = p - hp[:, 2] * m_new / (v_new.sqrt() + eps)
+    x = torch.where(hp[:, 1] > 0, x - hp[:, 0] * hp[:, 1] * x, x)
+    m.copy_(torch.where(live, m_new, m))
+    v.copy_(torch.where(live, v_new, v))
+    p.copy_(torch.where(live, x, p))
+    if p16 is not None:
+        p16.copy_(torch.where(live, x, p16.float()).to(p16.dtype))
+
+
 _NAMES = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "embed_gather_fwd",
           "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd", "region_loss_fwd", "region_loss_bwd",
           "loss_finalize", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill",
-          "compact_plan", "compact_gather", "compact_scatter", "mask_lengths", "zero_rows"]
+          "compact_plan", "compact_gather", "compact_scatter", "mask_lengths", "zero_rows", "sumsq", "adamw_flat"]
 
 
 def install(monkeypatch):
