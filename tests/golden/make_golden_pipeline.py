@@ -31,6 +31,8 @@ CASES = {
     "pipeline_last_r8": (3, 8, "last", 5, 12, 6),
     "pipeline_first_r36": (2, 36, "first", 5, 13, 7),
     "pipeline_locs4_r12": (3, 12, "first", 4, 14, 8),
+    # visualization=True: random_region / random_word never mask (:625, :672) - no picked region, divisor = region_len
+    "pipeline_nomask_r10": (3, 10, "first", 5, 15, 9),
 }
 
 
@@ -77,11 +79,11 @@ class FakeFlow:
         return 1
 
 
-def run_reference(mod, raw, region_len, add_global, num_locs, py_seed):
+def run_reference(mod, raw, region_len, add_global, num_locs, py_seed, visualization=False):
     pp = object.__new__(mod.BertPreprocessBatch)           # the constructor only reads the caption file
     pp.split, pp.seq_len, pp.region_len = "Train", 16, region_len
     pp.tokenizer, pp.num_caps, pp.captions = ToyTokenizer(), 1, ["a caption"]
-    pp.visualization, pp.objective, pp.bert_model, pp.num_locs = False, 2, "bert-base-uncased", num_locs
+    pp.visualization, pp.objective, pp.bert_model, pp.num_locs = visualization, 2, "bert-base-uncased", num_locs
     random.seed(py_seed)
     np.random.seed(py_seed)
     B = raw["raw_feat"].shape[0]
@@ -107,11 +109,12 @@ def main():
     mod = load_reference_module()
     for name, (B, R, add_global, num_locs, seed, py_seed) in CASES.items():
         raw = raw_region_batch(B, R, seed=seed, full=True)   # the reference needs num_boxes == region_len (:679 broadcast)
-        feat, loc, mask, label = run_reference(mod, raw, R, add_global, num_locs, py_seed)
+        nomask = "nomask" in name
+        feat, loc, mask, label = run_reference(mod, raw, R, add_global, num_locs, py_seed, visualization=nomask)
         body = feat[:, 1:] if add_global == "first" else feat[:, :-1]
         zeroed = (body == 0).all(-1) & (raw["raw_feat"] != 0).any(-1)
         sel = torch.where(label == 1, torch.where(zeroed, 1, 2), 0).to(torch.uint8)
-        assert int((sel != 0).sum()) > 0, "no region was masked - pick another seed"
+        assert (int((sel != 0).sum()) > 0) != nomask, "masking does not match the case - pick another seed"
         torch.save(dict(case=(B, R, add_global, num_locs, seed), sel=sel, image_feat=feat, image_loc=loc,
                         image_mask=mask, image_label=label), os.path.join(HERE, name + ".pt"))
         print(name, tuple(feat.shape), "masked:", int((sel == 1).sum()), "kept:", int((sel == 2).sum()))

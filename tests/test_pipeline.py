@@ -10,7 +10,7 @@ import torch
 from oracle.pipeline_oracle import assemble_region_batch
 from volta_b200.synthetic import raw_region_batch
 
-GOLDEN = ["pipeline_first_r8", "pipeline_last_r8", "pipeline_first_r36", "pipeline_locs4_r12"]
+GOLDEN = ["pipeline_first_r8", "pipeline_last_r8", "pipeline_first_r36", "pipeline_locs4_r12", "pipeline_nomask_r10"]
 
 
 def _load(golden_dir, name):
