@@ -26,7 +26,3 @@ def load_case(name):
 def rel_l2(a, b):
     a, b = a.double(), b.double()
     return float((a - b).norm() / b.norm().clamp(min=1e-30))
-
-
-def state_template_from_keys(keys, shapes_from):
-    raise NotImplementedError

@@ -417,6 +417,9 @@ class BertForVLTasks(BertPreTrainedModel):
     def __init__(self, config, task_cfg, task_ids, dropout_prob=0.1):
         super().__init__(config)
         self.bert = BertModel(config)
+        # one flat parameter store for encoder + task heads: the data-parallel hooks and FusedAdamW are keyed by the store's
+        # model (this object); head gradients (written by autograd) enter the flat gradient buffer in prepare_grads
+        self.bert.__dict__["_engine_parent"] = weakref.ref(self)
         self.dropout = nn.Dropout(dropout_prob)
         self.config, self.task_cfg = config, task_cfg
         task2clf = {}
@@ -442,6 +445,11 @@ class BertForVLTasks(BertPreTrainedModel):
         self.clfs_dict = nn.ModuleDict(task2clf)
         self.fusion_method = config.fusion_method
         self.apply(self.init_weights)
+
+    def _engine_written(self):
+        """Parameters whose gradients the engine's hand-written backward writes (the rest - the task heads - get theirs
+        from autograd and stay `None` when a step does not use them, as in the reference)."""
+        return list(self.bert.parameters())
 
     def forward(self, input_txt, input_imgs, image_loc, task_id, token_type_ids=None, attention_mask=None,
                 image_attention_mask=None, output_all_encoded_layers=False, output_all_attention_masks=False):

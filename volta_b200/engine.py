@@ -243,7 +243,8 @@ def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, 
                 _count()
     for l_, x_, dy_ in parts:
         lins = _lins(l_)
-        rt.gemm(dy_, x_, rt.g32(*[l.weight for l in lins]), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, **wl)
+        if any(l.weight.requires_grad for l in lins):   # frozen Linears (fixed_layers / freeze_layers): no weight gradient
+            rt.gemm(dy_, x_, rt.g32(*[l.weight for l in lins]), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, **wl)
         if lins[0].bias is not None and not bias_done and side is None:
             ops.colsum(dy_, rt.g32(*[l.bias for l in lins]), **(rl or dict(row_limit=rt.row_limit(dy_.shape[0]))))
             _count()
@@ -1421,7 +1422,9 @@ def register_grad_ready_hook(model, fn):
 
 
 def _notify_grads_ready(model):
-    fn = _GRAD_HOOKS.get(id(model))
+    """Hooks are keyed by the model that owns the flat store (the object the data-parallel wrapper wraps): a BertModel
+    inside BertForVLPreTraining / BertForVLTasks resolves to its parent."""
+    fn = _GRAD_HOOKS.get(id(model_store(model).model))
     if fn is not None:
         fn()
 

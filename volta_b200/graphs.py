@@ -118,7 +118,8 @@ class GraphedPretrainStep:
 
     def _store_ptrs(self):
         st = engine.model_store(self.model)
-        return tuple(None if t is None else t.data_ptr() for t in (st.flat32, st.flat16, st.grad32))
+        ptrs = tuple(None if t is None else t.data_ptr() for t in (st.flat32, st.flat16, st.grad32, st._trash))
+        return ptrs + (tuple(p.requires_grad for p in st.params),)   # freezing a layer re-routes its gradient writes
 
     def valid(self):
         """The graphs hold raw pointers into the flat parameter / gradient buffers."""

@@ -34,6 +34,7 @@ class FusedAdamW(torch.optim.Optimizer):
         if model is None:
             raise ValueError("FusedAdamW needs model= (the volta_b200 model whose flat store holds these parameters)")
         self.model = model
+        self._writes_bf16_operands = True     # store.py: this optimizer's step leaves the bf16 operand copy fresh
         self.max_grad_norm = float(max_grad_norm)
         b = {tuple(g["betas"]) for g in self.param_groups}
         e = {float(g["eps"]) for g in self.param_groups}
@@ -67,8 +68,8 @@ class FusedAdamW(torch.optim.Optimizer):
         m = torch.zeros(store.total, dtype=torch.float32, device=dev)
         v = torch.zeros(store.total, dtype=torch.float32, device=dev)
         old = self._layout
-        self._layout = dict(key=key, chunk_group=chunk_group.to(dev), m=m, v=v, sumsq=torch.zeros(1, dtype=torch.float32, device=dev),
-                            steps=[0] * len(self.param_groups))
+        self._layout = dict(key=key, chunk_group=chunk_group.to(dev), chunk_group_host=chunk_group, none_sig=None, active=None,
+                            m=m, v=v, sumsq=torch.zeros(1, dtype=torch.float32, device=dev), steps=[0] * len(self.param_groups))
         for group in self.param_groups:          # per-parameter state as views, for state_dict() compatibility
             for p in group["params"]:
                 off, n = store.offsets[id(p)]
@@ -101,13 +102,45 @@ class FusedAdamW(torch.optim.Optimizer):
             with torch.enable_grad():
                 loss = closure()
         store = self._ensure()
-        if store.grad32 is None:
-            return loss  # no backward has run yet
         lay = self._layout
+        # Parameters without a gradient are skipped, as torch optimizers do (`if p.grad is None: continue`: task heads a
+        # step did not use keep their weights, moments and step count).  Gradients that autograd produced outside the flat
+        # buffer (a head whose encoder backward did not run) are adopted first.
+        base = None if store.grad32 is None else store.grad32.data_ptr()
+        none_sig, foreign = [], False
+        for group in self.param_groups:
+            for p in group["params"]:
+                g = p.grad
+                none_sig.append(g is None)
+                if g is not None and (base is None or g.data_ptr() != base + 4 * store.offsets[id(p)][0]):
+                    foreign = True
+        if all(none_sig):
+            return loss  # no backward has run since the gradients were cleared: nothing to do, as in torch
+        if foreign:
+            store.prepare_grads()
+        none_sig = tuple(none_sig)
+        if none_sig != lay["none_sig"]:
+            lay["none_sig"] = none_sig
+            if any(none_sig):
+                active = lay["chunk_group_host"].clone()
+                it = iter(none_sig)
+                for group in self.param_groups:
+                    for p in group["params"]:
+                        if next(it):
+                            off, n = store.offsets[id(p)]
+                            active[off // 64:(off + n + 63) // 64] = -1
+                lay["active"] = active.to(store.flat32.device)
+            else:
+                lay["active"] = lay["chunk_group"]
         beta1, beta2 = self.param_groups[0]["betas"]
         eps = self.param_groups[0]["eps"]
         rows = []
+        it = iter(none_sig)
         for gi, group in enumerate(self.param_groups):
+            live = [not next(it) for _ in group["params"]]
+            if not any(live):
+                rows.append((0.0, 0.0, 0.0, 1.0))   # no parameter of this group has a gradient: its chunks are masked out
+                continue
             lay["steps"][gi] += 1
             t = lay["steps"][gi]
             lr = float(group["lr"])
@@ -115,8 +148,9 @@ class FusedAdamW(torch.optim.Optimizer):
             if group.get("correct_bias", True):
                 step_size = lr * (1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t)
             rows.append((lr, float(group["weight_decay"]), step_size, 1.0))
-            for p in group["params"]:
-                self.state[p]["step"] = t
+            for p, on in zip(group["params"], live):
+                if on:
+                    self.state[p]["step"] = t
         hp = torch.tensor(rows, dtype=torch.float32)
         hp_dev = hp.to(store.flat32.device, non_blocking=True)
         sumsq = None
@@ -125,7 +159,7 @@ class FusedAdamW(torch.optim.Optimizer):
             sumsq.zero_()
             ops.sumsq(store.grad32, sumsq)
         p16 = store.flat16 if store.precision == "bf16" else None
-        ops.adamw_flat(store.flat32, store.grad32, lay["m"], lay["v"], p16, lay["chunk_group"], hp_dev, beta1, beta2, eps,
+        ops.adamw_flat(store.flat32, store.grad32, lay["m"], lay["v"], p16, lay["active"], hp_dev, beta1, beta2, eps,
                        sumsq, self.max_grad_norm)
         engine._count(2 if sumsq is not None else 1)
         return loss

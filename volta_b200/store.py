@@ -15,6 +15,27 @@ import torch
 
 from . import ops
 
+# ---- staleness of the bf16 operand copy ------------------------------------------------------------------------------
+# `p._version` sees in-place updates made through the parameter itself (`with no_grad(): p.add_()`), NOT updates made
+# through `p.data` - which is how the reference's optimizers write (pytorch_transformers.AdamW: `p.data.addcdiv_`;
+# volta/optimization.py RAdam: `p.data.copy_`, call sites train_task.py:222-234).  Every `torch.optim.Optimizer.step`
+# therefore bumps a global epoch through torch's optimizer post-step hook, and a store re-casts its operands when the
+# epoch moved since its last cast.  FusedAdamW writes the bf16 copy itself and does not bump it.  Edits made neither
+# through the parameter nor by an optimizer (`p.data.mul_()` by hand) need `store.refresh()`.
+_OPT_EPOCH = [0]
+
+
+def _on_optimizer_step(optimizer, args, kwargs):
+    if not getattr(optimizer, "_writes_bf16_operands", False):
+        _OPT_EPOCH[0] += 1
+
+
+try:
+    from torch.optim.optimizer import register_optimizer_step_post_hook
+    register_optimizer_step_post_hook(_on_optimizer_step)
+except ImportError:  # pragma: no cover - torch < 2.0: fall back to re-casting after every backward
+    register_optimizer_step_post_hook = None
+
 ALIGN = 64  # elements: every group starts on a 256-byte boundary (TMA wants 16 B, 128 B keeps sectors whole)
 
 
@@ -29,6 +50,8 @@ class ParamStore:
         self.total = 0
         self._sig = None
         self.precision = None
+        self._backwards = 0    # backwards run on this store (the fallback staleness signal without the optimizer hook)
+        self._trash = None     # where the gradients of frozen parameters are written (never read)
 
     # ---- layout -------------------------------------------------------------------------
     def _layout(self):
@@ -48,6 +71,7 @@ class ParamStore:
             seen.update(id(m) for m in members)
         off = 0
         self.offsets, self.params = {}, []
+        self.groups = order
         for members in order:
             off = (off + ALIGN - 1) // ALIGN * ALIGN
             for p in members:
@@ -85,7 +109,8 @@ class ParamStore:
         if precision != self.precision:
             self.precision, self._sig = precision, None
         if precision == "bf16":
-            sig = sum(p._version for p in self.params)
+            sig = (sum(p._version for p in self.params), _OPT_EPOCH[0],
+                   self._backwards if register_optimizer_step_post_hook is None else 0)
             if self.flat16 is None:
                 self.flat16 = torch.empty(self.total, dtype=torch.bfloat16, device=device)
                 self._sig = None
@@ -118,6 +143,16 @@ class ParamStore:
         return self._view(self.flat32, ps)
 
     def g32(self, *ps):
+        """Gradient view of one parameter / several consecutive ones.  Frozen parameters (requires_grad False:
+        config.fixed_layers, volta/train_utils.py:250-255 freeze_layers) get a scratch view instead: the kernels still
+        write, nothing reads, and their slice of grad32 stays zero - so the flat gradient norm (optim.py) and the
+        all-reduced buckets hold exactly what `clip_grad_norm_(model.parameters())` / apex DDP see in the reference."""
+        if not any(p.requires_grad for p in ps):
+            n = sum(p.numel() for p in ps)
+            if self._trash is None or self._trash.numel() < n:   # sized in prepare_grads; only reached by out-of-band freezes
+                self._trash = torch.empty(n, dtype=torch.float32, device=self.flat32.device)
+            lead = sum(p.shape[0] for p in ps)
+            return self._trash[:n].view((lead,) + tuple(ps[0].shape[1:]))
         return self._view(self.grad32, ps)
 
     # ---- gradients ----------------------------------------------------------------------
@@ -125,6 +160,12 @@ class ParamStore:
         """Attach `p.grad` views into grad32; zero what is not being accumulated into."""
         if self.grad32 is None:
             self.grad32 = torch.empty(self.total, dtype=torch.float32, device=self.flat32.device)
+        self._backwards += 1
+        frozen = [sum(p.numel() for p in g) for g in self.groups if not any(p.requires_grad for p in g)]
+        if frozen and (self._trash is None or self._trash.numel() < max(frozen)):
+            self._trash = torch.empty(max(frozen), dtype=torch.float32, device=self.flat32.device)
+        written = getattr(self.model, "_engine_written", None)
+        written = None if written is None else {id(p) for p in written()}
         base = self.grad32.data_ptr()
         ours, missing, foreign = [], [], []
         for p in self.params:
@@ -146,7 +187,8 @@ class ParamStore:
             view = self.grad32[off:off + n].view(p.shape)
             if zero_each:
                 view.zero_()
-            if p.requires_grad:
+            # parameters outside the engine's backward (task heads a step does not use) keep grad None, as in the reference
+            if p.requires_grad and (written is None or id(p) in written):
                 p.grad = view
         for p in foreign:
             off, n = self.offsets[id(p)]
