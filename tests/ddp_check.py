@@ -1,0 +1,105 @@
+"""Multi-rank numerical check of volta_b200.parallel.DistributedDataParallel on real GPUs (launched by torchrun; the
+pytest wrapper is tests/test_parallel_gpu.py::test_ddp_gradients_equal_mean_of_single_rank_gradients).
+
+Pattern: the reference's apex/tests/distributed/DDP/ddp_race_condition_test.py:29-69 - several iterations, the gradients
+after backward() are checked against a value known in closed form, which catches stream-ordering races between the
+all-reduce stream and the compute stream.  Here the closed form is: every rank holds, for EVERY parameter, the mean over
+ranks of the gradient each rank's batch gives on its own (computed on the same GPU by an un-wrapped twin of the model).
+The wrapped model runs the default path: full-width ctrl_vilbert_base, CUDA-graph replay, backward cut into segments at
+the bucket boundaries, buckets all-reduced on NCCL's stream while the remaining segments run.
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/ddp_check.py
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    import contextlib
+    import volta_b200
+    from volta_b200.config import named_config
+    from volta_b200.parallel import DistributedDataParallel
+    from volta_b200.synthetic import pretraining_batch, seeded_state_dict
+    world, rank, local = int(os.environ["WORLD_SIZE"]), int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    dist.init_process_group("nccl", device_id=dev)
+    iters = int(os.environ.get("DDP_CHECK_ITERS", "10"))
+    B, T, V = int(os.environ.get("DDP_CHECK_BATCH", "64")), 36, 37
+    name = os.environ.get("DDP_CHECK_MODEL", "ctrl_vilbert_base")
+    wire = torch.bfloat16 if os.environ.get("DDP_CHECK_WIRE") == "bf16" else None
+    cfg = named_config(name, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, v_hidden_dropout_prob=0.0,
+                       v_attention_probs_dropout_prob=0.0)
+
+    def build(seed):
+        with contextlib.redirect_stdout(sys.stderr):
+            m = volta_b200.BertForVLPreTraining(cfg)
+        m.load_state_dict(seeded_state_dict(m.state_dict(), seed=seed))
+        m.cls.dropout.p = 0.0
+        return m.train().to(dev)
+
+    twin = build(0)
+    twin._use_cuda_graphs = False
+    model = build(0 if rank == 0 else 99)          # the wrapper's broadcast from rank 0 must make the ranks equal
+    ddp = DistributedDataParallel(model, allreduce_dtype=wire)
+
+    def args_of(d):
+        return (d["input_ids"], d["image_feat"], d["image_loc"], d["segment_ids"], d["input_mask"], d["image_mask"],
+                d["lm_label_ids"], d["image_label"], d["image_cls"], None, None, None, None, None, d["is_match"])
+
+    def grads_of(m, runner, seed):
+        d = {k: v.to(dev) for k, v in pretraining_batch(B, T, V, seed=seed).items()}
+        m.zero_grad(set_to_none=True)
+        l = runner(*args_of(d))
+        (l[0] + l[1] + l[2]).sum().backward()
+        torch.cuda.synchronize()
+        from volta_b200 import engine
+        return engine.model_store(m).grad32.clone(), [float(x) for x in l]
+
+    from volta_b200 import engine
+    worst_all, replays, buckets = 0.0, 0, 0
+    tol = 2e-2 if wire is not None else 2e-4
+    for it in range(iters):
+        got, _ = grads_of(model, ddp, 1000 + 10 * it + rank)
+        expect = None
+        for r in range(world):
+            g, _ = grads_of(twin, twin, 1000 + 10 * it + r)
+            expect = g if expect is None else expect + g
+        expect /= world
+        store = engine.model_store(model)
+        worst = 0.0
+        total = float(expect.norm())
+        for key, p in model.named_parameters():
+            off, n = store.offsets[id(p)]
+            a, e = got[off:off + n], expect[off:off + n]
+            worst = max(worst, float((a - e).norm()) / max(float(e.norm()), 1e-3 * total))
+        # every rank must hold bit-identical gradients after the all-reduce
+        mine = got.double().sum().reshape(1)
+        both = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(both, mine)
+        assert all(float(b) == float(both[0]) for b in both), ("ranks disagree after the all-reduce", it, [float(b) for b in both])
+        assert worst < tol, ("gradient != mean of the single-rank gradients", it, worst)
+        worst_all = max(worst_all, worst)
+        buckets = ddp.last_num_buckets
+    steps = [s for s in model._graph_steps.values() if not isinstance(s, str)]
+    replays = steps[0].replays if steps else 0
+    segs = len(steps[0].bwd_segments) if steps else 0
+    assert replays >= iters - 2 and segs >= 2, ("the CUDA-graph path with a segmented backward was not taken", replays, segs)
+    if rank == 0:
+        print(json.dumps({"ddp_check": "ok", "world": world, "model": name, "per_rank_batch": B, "iterations": iters,
+                          "wire": "bf16" if wire is not None else "fp32", "worst_rel_l2_vs_mean_of_single_rank": worst_all,
+                          "tolerance": tol, "buckets_per_step": buckets, "graph_replays": replays, "backward_segments": segs}), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,3 +35,32 @@ def test_bucketer_wire_formats_on_one_rank_nccl():
             assert torch.equal(flat, expect)
     finally:
         dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wire", ["fp32", "bf16"])
+def test_ddp_gradients_equal_mean_of_single_rank_gradients(wire):
+    """>= 2 real ranks over NCCL (self-skips on a one-GPU box): tests/ddp_check.py under torchrun - 10 iterations of the
+    graph-replayed, bucket-overlapped backward; every parameter gradient equals the mean of the single-rank gradients
+    (apex/tests/distributed/DDP/ddp_race_condition_test.py:29-69 is the pattern)."""
+    import json
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DDP_CHECK_WIRE=wire)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "ddp_check.py")],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    rep = json.loads(line)
+    assert rep["ddp_check"] == "ok" and rep["buckets_per_step"] >= 2 and rep["backward_segments"] >= 2, rep
+    print(line)

@@ -142,3 +142,43 @@ def test_assembled_batch_feeds_the_model_like_the_host_assembled_one():
         losses.append([float(x) for x in out[:3]])
     for a, b in zip(*losses):   # the loss sums use fp32 atomics: last-bit run-to-run differences
         assert abs(a - b) <= 2e-6 * abs(b), losses
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pinned,wire", [(False, None), (True, torch.bfloat16)])
+def test_prefetching_loader_yields_the_assembled_batches_in_order(pinned, wire):
+    """PrefetchingRegionLoader (two slots, staging thread, copy stream): every yielded batch equals the direct assembly
+    of the same host batch, in order, while the consumer still holds the previous one; device buffers are reused (a slot's
+    addresses repeat every `depth` batches); pass-through tensors arrive unchanged."""
+    from volta_b200.pipeline import PrefetchingRegionLoader, RegionBatchAssembler
+    from volta_b200.synthetic import pretraining_batch
+    B, R, F, n = 16, 36, 256, 7
+    dev = torch.device("cuda:0")
+    host = []
+    for i in range(n):
+        raw = raw_region_batch(B, R, feat_dim=F, seed=300 + i, full=False)
+        text = pretraining_batch(B, 12, R + 1, feat_dim=F, seed=400 + i)
+        hb = {k: raw[k] for k in ("raw_feat", "raw_box", "image_hw", "num_boxes", "sel")}
+        hb.update(input_ids=text["input_ids"], image_cls=text["image_cls"], is_match=text["is_match"])
+        host.append({k: (v.pin_memory() if pinned else v) for k, v in hb.items()})
+    asm = RegionBatchAssembler(R, feature_size=F, num_locs=5, add_global_imgfeat="first", out_dtype=torch.bfloat16)
+    loader = PrefetchingRegionLoader(iter(host), asm, dev, depth=2, wire_dtype=wire)
+    seen, ptrs, held = 0, [], None
+    for i, batch in enumerate(loader):
+        hb = host[i]
+        rf = hb["raw_feat"] if wire is None else hb["raw_feat"].to(wire)
+        feat, loc, mask, label, count = asm(rf.cuda(), hb["raw_box"].cuda(), hb["image_hw"].cuda(), hb["num_boxes"].cuda(), hb["sel"].cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(batch["image_feat"], feat) and torch.equal(batch["image_loc"], loc)
+        assert torch.equal(batch["image_mask"], mask) and torch.equal(batch["image_label"], label)
+        assert torch.equal(batch["num_regions"], count)
+        for k in ("input_ids", "image_cls", "is_match"):
+            assert torch.equal(batch[k].cpu(), hb[k]), k
+        if held is not None:       # the previous batch is still intact while this one has been staged
+            assert torch.equal(held[0], held[1])
+        held = (batch["image_feat"], feat)
+        ptrs.append(batch["image_feat"].data_ptr())
+        seen += 1
+    assert seen == n
+    assert len(set(ptrs)) == 2 and ptrs[0] == ptrs[2] == ptrs[4] and ptrs[1] == ptrs[3]
+    assert loader.h2d_bytes > 0

@@ -37,6 +37,12 @@ def _count(n=1):
     launch_count += n
 
 
+# What the last forward's launch plan did (tests assert that the plan they mean to check was the one taken):
+# packed = encoder ran on packed rows; row_split = sub-layers whose two streams shared row-split GEMM launches;
+# joint = shared sub-layers run as one GEMM over both streams; mlm_compact = masked-LM head on the labelled rows only.
+last_plan = {}
+
+
 def _pad8(n):
     return (n + 7) // 8 * 8
 
@@ -937,12 +943,16 @@ def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
         _enter_packed(rt)
         x = _pack_pair(rt, x)
         rt.pack_on = True
+    last_plan.clear()
+    last_plan.update(packed=rt.pack is not None, row_split=0, joint=0, mlm_compact=False, rows_t=rt.Mt, rows_v=rt.Mv)
     tape, layers = [], []
     for n, layer in enumerate(bert.encoder.layer):
         if bert.encoder.num2type[n] == "attn":
             x, saved = attention_fwd(rt, layer, x, masks)
         else:
             x, saved = ffn_fwd(rt, layer, x)
+        last_plan["row_split"] += int(bool(saved.get("split")))
+        last_plan["joint"] += int(bool(saved.get("joint") or saved.get("all")))
         tape.append(saved if rt.grad_enabled else None)
         if keep_layers:
             layers.append(x)
@@ -1070,6 +1080,7 @@ def heads_fwd(rt, model, x, pooled_t, pooled_v, labels, want_logits=False):
         hn, s["mlm_tr"] = _transform_fwd(rt, cls.predictions.transform, xc, lim=limits)   # transform of the labelled rows only
         rt.gemm(hn, E, mlm_logits, epilogue=EPI_BIAS, bias=rt.w32(cls.predictions.bias), N=V_, m_limit=limits[0:1])
         cmp_ = (limits, pos, lab_c)
+        last_plan["mlm_compact"] = True
     else:
         hn, s["mlm_tr"] = _transform_fwd(rt, cls.predictions.transform, x.t)
         rt.gemm(hn, E, mlm_logits, epilogue=EPI_BIAS, bias=rt.w32(cls.predictions.bias), N=V_)

@@ -48,7 +48,9 @@ class GraphedPretrainStep:
         self.fwd_graph = None
         self.bwd_segments = []   # [(graph, frontier offset or None)]
         self.n_fwd = self.n_bwd = 0
+        self.replays = 0         # completed forward+backward replays (tests assert the graph path was the one measured)
         self._capture()
+        self.plan = dict(engine.last_plan)
 
     # ------------------------------------------------------------------------------------------ capture
     def _capture(self):
@@ -149,6 +151,7 @@ class GraphedPretrainStep:
             if frontier is not None and hook is not None:
                 hook(frontier)
         engine.launch_count += self.n_bwd
+        self.replays += 1
         self.pending = False
         engine._notify_grads_ready(model)
 
