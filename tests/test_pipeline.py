@@ -163,22 +163,26 @@ def test_prefetching_loader_yields_the_assembled_batches_in_order(pinned, wire):
         host.append({k: (v.pin_memory() if pinned else v) for k, v in hb.items()})
     asm = RegionBatchAssembler(R, feature_size=F, num_locs=5, add_global_imgfeat="first", out_dtype=torch.bfloat16)
     loader = PrefetchingRegionLoader(iter(host), asm, dev, depth=2, wire_dtype=wire)
-    seen, ptrs, held = 0, [], None
+    # The consumer never synchronises inside the loop: it queues a delay and then a read of the batch on its stream, and
+    # asks for the next batch right away.  A slot may only be overwritten after that queued read has run (the `left`
+    # event), and a batch may only be read after its upload + assembly have finished (the `ready` event).
+    ptrs, reads = [], []
     for i, batch in enumerate(loader):
+        torch.cuda._sleep(5_000_000)
+        reads.append({k: batch[k].clone() for k in ("image_feat", "image_loc", "image_mask", "image_label", "num_regions",
+                                                     "input_ids", "image_cls", "is_match")})
+        ptrs.append(batch["image_feat"].data_ptr())
+    torch.cuda.synchronize()
+    assert len(reads) == n
+    for i, got in enumerate(reads):
         hb = host[i]
         rf = hb["raw_feat"] if wire is None else hb["raw_feat"].to(wire)
         feat, loc, mask, label, count = asm(rf.cuda(), hb["raw_box"].cuda(), hb["image_hw"].cuda(), hb["num_boxes"].cuda(), hb["sel"].cuda())
         torch.cuda.synchronize()
-        assert torch.equal(batch["image_feat"], feat) and torch.equal(batch["image_loc"], loc)
-        assert torch.equal(batch["image_mask"], mask) and torch.equal(batch["image_label"], label)
-        assert torch.equal(batch["num_regions"], count)
+        assert torch.equal(got["image_feat"], feat) and torch.equal(got["image_loc"], loc), i
+        assert torch.equal(got["image_mask"], mask) and torch.equal(got["image_label"], label), i
+        assert torch.equal(got["num_regions"], count), i
         for k in ("input_ids", "image_cls", "is_match"):
-            assert torch.equal(batch[k].cpu(), hb[k]), k
-        if held is not None:       # the previous batch is still intact while this one has been staged
-            assert torch.equal(held[0], held[1])
-        held = (batch["image_feat"], feat)
-        ptrs.append(batch["image_feat"].data_ptr())
-        seen += 1
-    assert seen == n
+            assert torch.equal(got[k].cpu(), hb[k]), (i, k)
     assert len(set(ptrs)) == 2 and ptrs[0] == ptrs[2] == ptrs[4] and ptrs[1] == ptrs[3]
     assert loader.h2d_bytes > 0

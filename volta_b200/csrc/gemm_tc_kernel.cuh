@@ -658,8 +658,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // and packed vision rows of a joint buffer); the work list enumerates live tile rows only
   const int seg_blk = min(p.seg_m_blk, num_m_blocks);
   int live_a = seg_blk, live_b = num_m_blocks - seg_blk;
-  if (p.m_limit) live_a = min(live_a, (max(*p.m_limit, 0) + BM * CG - 1) / (BM * CG));
-  if (p.m_limit2) live_b = min(live_b, (max(*p.m_limit2, 0) + BM * CG - 1) / (BM * CG));
+  // contract (vb_gemm_args::m_limit): rows are produced in whole 256-row groups whatever the tile height - a 128-row
+  // (CG = 1) tile grid must not stop at the first 128 rows, the consumers reduce up to the count padded to 256
+  auto live_tiles = [](int lim) { return (((max(lim, 0) + 255) & ~255) + BM * CG - 1) / (BM * CG); };
+  if (p.m_limit) live_a = min(live_a, live_tiles(*p.m_limit));
+  if (p.m_limit2) live_b = min(live_b, live_tiles(*p.m_limit2));
   num_m_blocks = live_a + live_b;
   auto m_of = [&](int m_idx) { return m_idx < live_a ? m_idx : seg_blk + (m_idx - live_a); };
   int kb_per_split = p.kb_per_split;

@@ -806,14 +806,15 @@ def _pool_bwd(rt, pooler, dpooled, pooled, a, dx, L):
 PACK_ROWS = os.environ.get("VOLTA_B200_PACK_ROWS", "1") != "0"
 # Shared sub-layers (ctrl_lxmert's cross layers; every layer of the single-stream models) run ONE GEMM over the joint
 # buffer: packed, it holds two runs of valid rows (vb_gemm_args::m_limit / m_limit2 / limit_seg_M forward and dgrad;
-# the weight / bias gradients reduce per run, linear_bwd).  The host plan reproduces the oracle under the emulation for
-# every family (tests/test_engine_emulated.py); it has not run on a B200 yet, so it is opt-in until measured.
-PACK_SHARED = os.environ.get("VOLTA_B200_PACK_SHARED", "0") == "1"
+# the weight / bias gradients reduce per run, linear_bwd).  Measured on a B200 (B=256, round 2): ctrl_visualbert_base
+# 19.95 k -> 24.6 k samples/s, ctrl_lxmert 17.1 k -> 21.6 k.  VOLTA_B200_PACK_SHARED=0 switches it off.
+PACK_SHARED = os.environ.get("VOLTA_B200_PACK_SHARED", "1") != "0"
 # The vision rows of a joint buffer must start on a 256-row tile edge.  When B*T is not a multiple of 256 (the reference
-# recipe: global batch 256 over 8 GPUs = 32 x 36 rows) the packed region can pad the TEXT segment of its buffers up to the
-# next edge (rt.Mt grows for the duration of the packed encoder; the padding rows are dropped rows of the plan, kept zero
-# like every row between a count and its tile edge).  Same status as PACK_SHARED: checked under the emulation, opt-in.
-PACK_ANY_ROWS = os.environ.get("VOLTA_B200_PACK_ANY_ROWS", "0") == "1"
+# recipe: global batch 256 over 8 GPUs = 32 x 36 rows; BASELINE.json configs[0]: batch 8) the packed region pads the
+# TEXT segment of its buffers up to the next edge (rt.Mt grows for the duration of the packed encoder; the padding rows
+# are dropped rows of the plan, kept zero like every row between a count and its tile edge).  Measured (B=32, T=38):
+# 4.92 k -> 5.61 k samples/s.  VOLTA_B200_PACK_ANY_ROWS=0 switches it off.
+PACK_ANY_ROWS = os.environ.get("VOLTA_B200_PACK_ANY_ROWS", "1") != "0"
 
 
 def _pad256(n):

@@ -93,13 +93,14 @@ class RetrievalRanker:
         return ranks, recall_metrics(ranks)
 
 
-def evaluate_retrieval(model, task, batches, ranker, device, group=None):
+def evaluate_retrieval(model, task, batches, ranker, device, group=None, start=0, merge=True):
     """The evaluation loop of eval_retrieval.py:168-198 over `batches` (tuples as RetrievalDatasetVal yields them:
     features, spatials, image_mask, question, input_mask, segment_ids, target, caption_idx, image_idx), sharded over the
     ranks of `group` by batch index, merged once at the end.  `model` is a BertForVLTasks replica in eval mode; returns
-    the ranker (matrices complete on every rank)."""
+    the ranker (matrices complete on every rank).  `start`: index of the first batch in the whole evaluation (a resumed or
+    chunked loop); `merge=False` leaves the cross-rank merge to a later `ranker.merge()`."""
     with torch.no_grad():
-        for step, batch in enumerate(batches):
+        for step, batch in enumerate(batches, start):
             if not ranker.owns(step, None if group is None else dist.get_rank(group),
                                None if group is None else dist.get_world_size(group)):
                 continue
@@ -110,5 +111,6 @@ def evaluate_retrieval(model, task, batches, ranker, device, group=None):
             question, segment_ids, input_mask = question.repeat(n, 1), segment_ids.repeat(n, 1), input_mask.repeat(n, 1)
             vil_logit = model(question, features, spatials, task, segment_ids, input_mask, image_mask)[0]
             ranker.update(caption_idx, image_idx, vil_logit, target)
-    ranker.merge(group)
+    if merge:
+        ranker.merge(group)
     return ranker
