@@ -388,7 +388,14 @@ def main_pretrain(args):
     # ---- e2e: the loader-side public API feeds the model from pinned host memory, every step ------------------------
     e2e = None
     if not args.no_e2e:
-        raw = raw_region_batch(B, V - 1, seed=4321 + rank, full=args.full_length)
+        # the same box counts as the resident batch, so that both legs run the same number of valid rows
+        raw = raw_region_batch(B, V - 1, seed=4321 + rank, full=True)
+        nb = (host["image_mask"].sum(1) - 1).to(torch.int32)
+        live = torch.arange(V - 1).unsqueeze(0) < nb.unsqueeze(1)
+        raw["raw_feat"] = raw["raw_feat"] * live.unsqueeze(-1)
+        raw["raw_box"] = raw["raw_box"] * live.unsqueeze(-1)
+        raw["sel"] = raw["sel"] * live.to(raw["sel"].dtype)
+        raw["num_boxes"] = nb
         if args.raw_input == "bf16":
             raw["raw_feat"] = raw["raw_feat"].to(torch.bfloat16)
         hb = {k: v for k, v in host.items() if k not in ("image_feat", "image_loc", "image_mask", "image_label")}

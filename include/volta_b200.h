@@ -127,6 +127,14 @@ typedef struct vb_gemm_args {
    * limit_seg_M = 0: one segment.  Must be a multiple of 256 for the tcgen05 back-end. */
   const int32_t* m_limit2;
   int64_t limit_seg_M;
+  /* Two reduction segments (VB_EPI_ACCUM on the tcgen05 back-end: the weight gradients of the text and the vision
+   * Linear of a two-stream sub-layer whose rows share one buffer, in ONE launch): reduction indices [0, k_seg)
+   * accumulate into D, indices [k_seg, K) into D2 (same shape and pitch as D; D2 == D for shared weights).  k_limit
+   * bounds the first segment, k_limit2 the second (counted from k_seg).  k_seg must be a multiple of 64;
+   * k_seg = 0 / D2 == NULL: one segment. */
+  void* D2;
+  const int32_t* k_limit2;
+  int64_t k_seg;
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);
@@ -403,6 +411,20 @@ int vb_region_batch(const void* raw_feat, int32_t in_dtype, const float* raw_box
  *   axis 1 (text retrieval, :248-256): rank[i] = best place of a matching caption in column i, C if there is none. */
 int vb_retrieval_ranks(const float* scores, int64_t ld, const uint8_t* targets, int64_t ld_t, int32_t C, int32_t I,
                        int32_t axis, int32_t* rank, int32_t* topk, int32_t k, void* stream);
+/* ---- gradient all-reduce over NVLink / NVSwitch (replaces the per-bucket NCCL call of
+ * apex/apex/parallel/distributed.py:449-454: dist.all_reduce(flat_bucket) + mul_(1/world)) --------------------------
+ * In-place all-reduce (sum, then * scale) of elements [offset, offset + count) of a SYMMETRIC fp32 buffer: the same
+ * allocation on every rank, peer-mapped.  buffer_ptrs_dev / signal_pad_ptrs_dev: device arrays [world] of the buffer /
+ * signal-pad base addresses on every rank as seen from this rank (torch.distributed._symmetric_memory supplies them);
+ * multicast_ptr: the NVSwitch multicast address of the buffer, or 0.  With a multicast address every rank reduces its
+ * 1/world slice inside the switch (multimem.ld_reduce) and broadcasts it (multimem.st); without one it sums its slice
+ * over peer loads and stores the result to every peer.  The kernel takes no shared memory and 128 threads per block, so
+ * its blocks share SMs with the persistent GEMM kernels of the backward.  EVERY rank must issue the same sequence of
+ * calls (same offset, count, blocks); bytes [4096, vb_allreduce_pad_bytes()) of the signal pads belong to this kernel
+ * and must be zero at the first call.  offset and count are multiples of 4; blocks <= 32 (0 = default). */
+int vb_allreduce_f32(const uint64_t* buffer_ptrs_dev, uint64_t multicast_ptr, const uint64_t* signal_pad_ptrs_dev,
+                     int32_t rank, int32_t world, int64_t offset, int64_t count, float scale, int32_t blocks, void* stream);
+int vb_allreduce_pad_bytes(void);
 /* L2-flush helper for benchmarks: writes `bytes` to buf. */
 int vb_fill(void* buf, int64_t bytes, int32_t value, void* stream);
 

@@ -6,6 +6,7 @@ import torch
 
 import emu_ops
 import volta_b200
+from volta_b200 import ops as ops_mod
 from golden_util import MINI_CASES, load_case, rel_l2
 from oracle import volta_oracle as O
 from volta_b200.synthetic import seeded_state_dict
@@ -122,12 +123,22 @@ def test_packed_rows_plan_matches_oracle(name, shape, monkeypatch):
         taken.append(ok)
         return ok
     monkeypatch.setattr(engine, "_pack_supported", forced)
+    monkeypatch.setattr(engine, "PLAN_EMULATED", True)   # row-split GEMMs and two-segment weight-gradient launches (vb_gemm_args::k_seg / D2)
+    grouped = []
+    real_gemm = ops_mod.gemm
+
+    def spy(*a, **k):
+        if k.get("out2") is not None:
+            grouped.append(k["k_seg"])
+        return real_gemm(*a, **k)
+    monkeypatch.setattr(ops_mod, "gemm", spy)
     g, cfg, _, model, state = _build(name)
     b = pretraining_batch(*shape, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=11)
     losses = model(b["input_ids"], b["image_feat"], b["image_loc"], b["segment_ids"], b["input_mask"], b["image_mask"],
                    b["lm_label_ids"], b["image_label"], b["image_cls"], None, None, None, None, None, b["is_match"])
     assert taken and all(taken)
     (losses[0] + losses[1] + losses[2]).sum().backward()
+    assert len(grouped) >= 10 and all(k % 256 == 0 for k in grouped), grouped[:4]   # the grouped plan was taken
     P = O.params_from_state_dict(state, requires_grad=True)
     ref = O.pretraining_losses(P, cfg, b)
     for mine, r in zip(losses, ref):

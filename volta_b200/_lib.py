@@ -27,7 +27,8 @@ class GemmArgs(C.Structure):
                 ("a_kmajor", _i32), ("b_kmajor", _i32), ("epilogue", _i32), ("backend", _i32),
                 ("bias", _vp), ("aux_in", _vp), ("aux_out", _vp), ("ld_aux", _i64), ("alpha", _f),
                 ("dropout_p", _f), ("seed", _u64), ("offset", _u64), ("split_k", _i32), ("reserved", _i32),
-                ("B2", _vp), ("bias2", _vp), ("split_M", _i64), ("m_limit", _vp), ("k_limit", _vp), ("m_limit2", _vp), ("limit_seg_M", _i64)]
+                ("B2", _vp), ("bias2", _vp), ("split_M", _i64), ("m_limit", _vp), ("k_limit", _vp), ("m_limit2", _vp), ("limit_seg_M", _i64),
+                ("D2", _vp), ("k_limit2", _vp), ("k_seg", _i64)]
 
 
 class AttnArgs(C.Structure):
@@ -87,6 +88,8 @@ SIGNATURES = {
     "vb_box_sincos": (_i32, [_vp, _i32, _i32, _vp, _i64, _i64, _i32, _vp]),
     "vb_fill": (_i32, [_vp, _i64, _i32, _vp]),
     "vb_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
+    "vb_allreduce_f32": (_i32, [_vp, _u64, _vp, _i32, _i32, _i64, _i64, _f, _i32, _vp]),
+    "vb_allreduce_pad_bytes": (_i32, []),
     "vb_adamw_flat": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _f, _f, _f, _vp, _f, _vp]),
     "vb_vlbert_prep": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "vb_vlbert_index": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -102,6 +102,8 @@ int vb_gemm(const vb_gemm_args* a, void* stream) {
   VB_REQUIRE(a->d_dtype == VB_F32 || a->d_dtype == VB_BF16, VB_ERR_ARG, "vb_gemm: bad d_dtype %d", a->d_dtype);
   const int be = vb_gemm_backend(a);
   if (be == VB_GEMM_TC) return vb::gemm_tc_launch(*a, (cudaStream_t)stream);
+  VB_REQUIRE(a->D2 == nullptr || a->k_seg <= 0, VB_ERR_UNSUPPORTED,
+             "vb_gemm: two reduction segments (k_seg / D2) need the tcgen05 back-end (bf16 operands, aligned pitches)");
   return vb::gemm_simt_launch(*a, (cudaStream_t)stream);
 }
 

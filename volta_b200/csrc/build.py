@@ -13,7 +13,7 @@ PKG = os.path.dirname(HERE)
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(PKG, "libvolta_b200.so")
 SOURCES = ["api.cu", "gemm_tc.cu", "gemm_tc_inst_a.cu", "gemm_tc_inst_b.cu", "gemm_tc_inst_c.cu", "gemm_tc_inst_d.cu",
-           "gemm_tc_inst_e.cu", "gemm_simt.cu", "layernorm.cu", "attention.cu", "embed.cu", "loss.cu", "eltwise.cu", "optim.cu", "compact.cu", "pipeline.cu", "retrieval.cu"]
+           "gemm_tc_inst_e.cu", "gemm_simt.cu", "layernorm.cu", "attention.cu", "embed.cu", "loss.cu", "eltwise.cu", "optim.cu", "compact.cu", "pipeline.cu", "retrieval.cu", "allreduce.cu"]
 HEADERS = ["common.cuh", "gemm_common.cuh", "gemm_tc_kernel.cuh", os.path.join("..", "..", "include", "volta_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]

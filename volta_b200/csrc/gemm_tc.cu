@@ -24,6 +24,10 @@ bool gemm_tc_supported(const vb_gemm_args& a, const char** why) {
     if (a.epilogue == VB_EPI_ACCUM) return fail("row-split launches are for forward / dgrad GEMMs");
     if ((a.split_M % 256) != 0 || a.split_M >= a.M || !aligned16(a.B2)) return fail("split_M must be a multiple of 256 below M, B2 16-byte aligned");
   }
+  if (a.D2 != nullptr && a.k_seg > 0) {
+    if (a.epilogue != VB_EPI_ACCUM) return fail("two reduction segments (k_seg / D2) are for ACCUM (weight-gradient) GEMMs");
+    if ((a.k_seg % 64) != 0 || a.k_seg >= a.K || !aligned16(a.D2)) return fail("k_seg must be a multiple of 64 below K, D2 16-byte aligned");
+  }
   return true;
 }
 

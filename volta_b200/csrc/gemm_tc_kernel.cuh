@@ -84,6 +84,11 @@ struct Params {
   const int32_t* k_limit;
   const int32_t* m_limit2;   // second row segment (rows >= seg_m_blk tiles): its own device-side row count
   int32_t seg_m_blk;         // first tile row of the second segment; INT_MAX = one segment
+  // Two reduction segments (ACCUM): k-blocks [0, kseg_kb) accumulate into epi.D, k-blocks [kseg_kb, kb_total) into D2
+  // (vb_gemm_args::k_seg / D2 / k_limit2); kseg_kb = 0: one segment.
+  float* D2;
+  const int32_t* k_limit2;
+  int32_t kseg_kb;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------
@@ -406,7 +411,7 @@ __device__ __forceinline__ void red_tile(const uint8_t* stg, float* g, int64_t l
 // waits until the store that last used it has read it (bulk_wait_read).  Measured on the GELU GEMM: the LDS + STG
 // store path it replaces cost 12.5 of 58.5 us.  fp32 outputs keep the padded staging + per-thread vector stores.
 template <typename OutT, int BN, int EPI, bool INTERIOR, int NUM_EPI_GROUPS>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_acc, uint8_t* stg, int64_t m0, int64_t nb0,
+__device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, uint32_t tmem_acc, uint8_t* stg, int64_t m0, int64_t nb0,
                                            int lane, int group, const float* bias_s, const CUtensorMap* mapD,
                                            const CUtensorMap* mapAuxOut, const CUtensorMap* mapAuxIn, uint32_t aux_bar,
                                            uint32_t& aux_phase) {
@@ -570,7 +575,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
     }
     __syncwarp();
     if constexpr (EPI == VB_EPI_ACCUM) {
-      if constexpr (sizeof(OutT) == 4) red_tile<INTERIOR>(stg, reinterpret_cast<float*>(p.D), p.ldd, m0, n0, p.M, p.N, lane);
+      if constexpr (sizeof(OutT) == 4) red_tile<INTERIOR>(stg, reinterpret_cast<float*>(d_out), p.ldd, m0, n0, p.M, p.N, lane);
     } else {
       if constexpr (EPI == VB_EPI_BIAS_GELU) {
         S::template store_tile<INTERIOR>(stg, reinterpret_cast<OutT*>(p.aux_out), p.ld_aux, m0, n0, p.M, p.N, lane);
@@ -584,7 +589,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, uint32_t tmem_
         }
         __syncwarp();
       }
-      S::template store_tile<INTERIOR>(stg, reinterpret_cast<OutT*>(p.D), p.ldd, m0, n0, p.M, p.N, lane);
+      S::template store_tile<INTERIOR>(stg, reinterpret_cast<OutT*>(d_out), p.ldd, m0, n0, p.M, p.N, lane);
     }
     __syncwarp();
   }
@@ -666,12 +671,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   num_m_blocks = live_a + live_b;
   auto m_of = [&](int m_idx) { return m_idx < live_a ? m_idx : seg_blk + (m_idx - live_a); };
   int kb_per_split = p.kb_per_split;
-  if (p.k_limit) {
+  // reduction segments: A = k-blocks [0, kbA) -> D, B = k-blocks [kbB0, kbB0 + kbB) -> D2 (one segment: kbB = 0)
+  int kbA = kb_total, kbB0 = 0, kbB = 0;
+  if (p.kseg_kb > 0) { kbA = min(p.kseg_kb, kb_total); kbB0 = kbA; kbB = kb_total - kbA; }
+  if (p.k_limit) kbA = min(kbA, (max(*p.k_limit, 0) + BK - 1) / BK);
+  if (p.k_limit2) kbB = min(kbB, (max(*p.k_limit2, 0) + BK - 1) / BK);
+  int splitA = split_k;
+  if (p.k_limit || p.kseg_kb > 0) {
     // keep the number of slices the host planned for the machine, shorten them evenly to the live reduction length
-    kb_total = min(kb_total, (max(*p.k_limit, 0) + BK - 1) / BK);
-    kb_per_split = max(1, (kb_total + p.split_k - 1) / p.split_k);
-    split_k = (kb_total + kb_per_split - 1) / kb_per_split;
+    kb_per_split = max(1, (kbA + kbB + p.split_k - 1) / p.split_k);
+    splitA = (kbA + kb_per_split - 1) / kb_per_split;
+    split_k = splitA + (kbB + kb_per_split - 1) / kb_per_split;
   }
+  kb_total = kbA;
+  // k-block range [kb0, kb1) and output segment of slice `split` of a tile
+  auto slice_of = [&](int split, int& kb0, int& kb1) -> bool {
+    if (split < splitA) { kb0 = split * kb_per_split; kb1 = min(kbA, kb0 + kb_per_split); return false; }
+    kb0 = kbB0 + (split - splitA) * kb_per_split; kb1 = min(kbB0 + kbB, kb0 + kb_per_split); return true;
+  };
   const int64_t tiles = (int64_t)num_m_blocks * p.num_n_blocks;   // tiles of (CG*128) x BN
   const int64_t total_work = tiles * split_k;
   const int64_t first = blockIdx.x / CG, step = gridDim.x / CG;     // one work item per CTA (pair) at a time
@@ -714,8 +731,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (m_blk * CG + (int)rank) * BM;
       const int n0 = n_blk * BN + (int)rank * (int)C::B_ROWS;
       const CUtensorMap* mapB = (m_blk >= p.split_m_blk) ? &tmB2 : &tmB;   // row-split launch: second stream's weights
-      const int kb0 = split * kb_per_split;
-      const int kb1 = min(kb_total, kb0 + kb_per_split);
+      int kb0, kb1;
+      slice_of(split, kb0, kb1);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
         uint32_t fb = full_bar(stage);
@@ -752,8 +769,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int q = 0;
     if (first < total_work) for (int64_t w = first;; ++it) {
       const int split = (int)(w % split_k);
-      const int kb0 = split * kb_per_split;
-      const int kb1 = min(kb_total, kb0 + kb_per_split);
+      int kb0, kb1;
+      slice_of(split, kb0, kb1);
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(tempty_bar(as), aphase ^ 1u);
       tcgen05_fence_after();
@@ -807,12 +824,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool more = next_work(w_next, q, lane == 0, true);
       const int64_t m0 = ((int64_t)m_blk * CG + rank) * BM + ew * 32;
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+      void* d_out = p.epi.D;
+      if constexpr (EPI == VB_EPI_ACCUM) {
+        int kb0_, kb1_;
+        if (slice_of((int)(w % split_k), kb0_, kb1_)) d_out = p.D2;   // second reduction segment: the other stream's gradient
+      }
       if (m0 < p.epi.M) {  // warp-uniform
         const int64_t nb0 = (int64_t)n_blk * BN;
         const bool interior = m0 + 32 <= p.epi.M && nb0 + BN <= p.epi.N;  // warp-uniform
         // OutT is a kernel template parameter: one epilogue body per kernel (code size, register allocation)
-        if (interior) epilogue_tile<OutT, BN, EPI, true, NUM_EPI_WARPS / 4>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase);
-        else epilogue_tile<OutT, BN, EPI, false, NUM_EPI_WARPS / 4>(p.epi, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase);
+        if (interior) epilogue_tile<OutT, BN, EPI, true, NUM_EPI_WARPS / 4>(p.epi, d_out, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase);
+        else epilogue_tile<OutT, BN, EPI, false, NUM_EPI_WARPS / 4>(p.epi, d_out, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -989,7 +1011,13 @@ static int launch_t(const vb_gemm_args& a, cudaStream_t stream) {
     p.seg_m_blk = (int32_t)(a.limit_seg_M / (BM * CG));
     p.m_limit2 = a.m_limit2;
   }
-  p.clc = (use_clc() && work * CG < (int64_t)INT32_MAX && !a.m_limit && !a.k_limit && !p.m_limit2) ? 1 : 0;
+  p.D2 = nullptr; p.k_limit2 = nullptr; p.kseg_kb = 0;
+  if (EPI == VB_EPI_ACCUM && a.D2 != nullptr && a.k_seg > 0 && a.k_seg < a.K) {
+    p.D2 = reinterpret_cast<float*>(a.D2);
+    p.k_limit2 = a.k_limit2;
+    p.kseg_kb = (int32_t)(a.k_seg / BK);
+  }
+  p.clc = (use_clc() && work * CG < (int64_t)INT32_MAX && !a.m_limit && !a.k_limit && !p.m_limit2 && !p.kseg_kb) ? 1 : 0;
   const int grid = (int)(p.clc ? work : std::min<int64_t>(work, units)) * CG;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);

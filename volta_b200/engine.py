@@ -188,6 +188,11 @@ IMG_COMPACT = os.environ.get("VOLTA_B200_IMG_COMPACT", "0") == "1"
 # Attention skips 16-row tiles of trailing padding (vb_attn_args::len_*); VOLTA_B200_SKIP_PADDING=0 computes them.
 SKIP_PADDING = os.environ.get("VOLTA_B200_SKIP_PADDING", "1") != "0"
 SKIP_PADDING_LN = os.environ.get("VOLTA_B200_SKIP_PADDING_LN", "1") != "0"   # the residual-block LayerNorms skip them too
+# The weight gradients of the two streams of a sub-layer run as one launch with two reduction segments (linear_bwd)
+WGRAD_GROUP = os.environ.get("VOLTA_B200_WGRAD_GROUP", "1") != "0"
+PLAN_EMULATED = False   # tests/test_engine_emulated.py: take the tensor-core launch plan (row-split / grouped launches) under the CPU emulation of the C ABI
+# The memset of the flat gradient buffer runs on a side stream under the forward (store.prezero_grads)
+PREZERO_GRADS = os.environ.get("VOLTA_B200_PREZERO_GRADS", "1") != "0"
 _SIDE_STREAMS = {}
 _SIDE_STREAMS_ON = os.environ.get("VOLTA_B200_SIDE_STREAM", "1") != "0"
 
@@ -247,9 +252,23 @@ def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, 
             for l_, x_, dy_ in parts:
                 ops.colsum(dy_, rt.g32(*[l.bias for l in _lins(l_)]), **(rl or dict(row_limit=rt.row_limit(dy_.shape[0]))))
                 _count()
+    # Both row ranges of a joint buffer in ONE weight-gradient launch (vb_gemm_args::k_seg / D2): the reduction over the
+    # text rows accumulates into the first Linear's gradient, the reduction over the vision rows into the second's (the
+    # same one for shared weights) - half the launches, and the slices of both fill the machine together.
+    tc_ok = (rt.precision == "bf16" and rt.gemm_backend != _lib.GEMM_SIMT and dy.is_cuda) or PLAN_EMULATED
+    grouped = (len(parts) == 2 and WGRAD_GROUP and lim is None and tc_ok and parts[0][2].shape[0] % 64 == 0 and
+               all(l.weight.requires_grad for pt in parts for l in _lins(pt[0])))
+    if grouped:
+        seg = parts[0][2].shape[0]
+        kl = {}
+        if getattr(rt, "pack_on", False):
+            kl = dict(k_limit=rt.row_limit(seg), k_limit2=rt.row_limit(dy.shape[0] - seg))
+        _count()
+        ops.gemm(dy, x, rt.g32(*[l.weight for l in _lins(parts[0][0])]), out2=rt.g32(*[l.weight for l in _lins(parts[1][0])]),
+                 k_seg=seg, a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, backend=rt.gemm_backend, **kl)
     for l_, x_, dy_ in parts:
         lins = _lins(l_)
-        if any(l.weight.requires_grad for l in lins):   # frozen Linears (fixed_layers / freeze_layers): no weight gradient
+        if not grouped and any(l.weight.requires_grad for l in lins):   # frozen Linears (fixed_layers / freeze_layers): no weight gradient
             rt.gemm(dy_, x_, rt.g32(*[l.weight for l in lins]), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, **wl)
         if lins[0].bias is not None and not bias_done and side is None:
             ops.colsum(dy_, rt.g32(*[l.bias for l in lins]), **(rl or dict(row_limit=rt.row_limit(dy_.shape[0]))))
@@ -320,7 +339,8 @@ def out_block_bwd(rt, dy, saved, dense, ln, dh_epilogue=EPI_NONE, dh_aux=None):
 def split_ok(rt, x, p_t, p_v, *lin_pairs):
     """Can the text and vision rows of this sub-layer share row-split GEMM launches?  They must live in one buffer,
     the text rows must end on a 256-row tile edge, the streams must use equally shaped Linears and one dropout rate."""
-    if x.all is None or rt.precision != "bf16" or rt.gemm_backend == _lib.GEMM_SIMT or os.environ.get("VOLTA_B200_ROW_SPLIT", "1") == "0":
+    tc = (rt.precision == "bf16" and rt.gemm_backend != _lib.GEMM_SIMT) or PLAN_EMULATED
+    if x.all is None or not tc or os.environ.get("VOLTA_B200_ROW_SPLIT", "1") == "0":
         return False
     if rt.Mt % 256 != 0 or rt.Mv == 0 or p_t != p_v:
         return False
@@ -1339,6 +1359,8 @@ class _PretrainFn(torch.autograd.Function):
         B, T = ids.shape
         V = feat.shape[1]
         rt = Runtime(model, ids.device, B, T, V, model.training, grad=anchor is not None)
+        if anchor is not None and PREZERO_GRADS:
+            rt.store.prezero_grads()
         seg = torch.zeros_like(ids) if seg is None else seg
         x, pt, pv, _, s_bert = bert_fwd(rt, model.bert, ids.contiguous(), feat.contiguous(), loc, seg.contiguous(), mask_t, mask_v)
         labels = dict(mlm=mlm_labels, image_label=image_label, image_cls=image_cls, itm=itm_label, obj_labels=obj_labels,

@@ -134,6 +134,8 @@ class GraphedPretrainStep:
             if dst is not None and src is not dst:
                 dst.copy_(src, non_blocking=True)
         self.seed_dev.copy_(torch.tensor([seed], dtype=torch.int64))
+        if engine.PREZERO_GRADS:
+            engine.model_store(self.model).prezero_grads()
         self.fwd_graph.replay()
         engine.launch_count += self.n_fwd
         self.pending = True

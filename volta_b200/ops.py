@@ -49,7 +49,7 @@ def require_cuda(*ts):
 # --------------------------------------------------------------------------- GEMM
 def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
          dropout_p=0.0, seed=0, offset=0, backend=_lib.GEMM_AUTO, split_k=0, M=None, N=None, K=None, b2=None, bias2=None,
-         split_M=0, m_limit=None, k_limit=None, m_limit2=None, limit_seg_M=0):
+         split_M=0, m_limit=None, k_limit=None, m_limit2=None, limit_seg_M=0, out2=None, k_seg=0, k_limit2=None):
     """out[M,N] = epilogue(opA . opB^T); see vb_gemm in include/volta_b200.h.  m_limit / k_limit: int32 device tensors
     (one element) holding the number of rows / reduction elements that carry data (see vb_compact_plan)."""
     require_cuda(a, b, out)
@@ -89,6 +89,13 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bia
             assert lim.dtype == torch.int32 and lim.is_cuda and lim.numel() >= 1
             setattr(g, name, lim.data_ptr())
     g.limit_seg_M = int(limit_seg_M)
+    if out2 is not None:   # two reduction segments (weight gradients of two streams in one launch): [0, k_seg) -> out, [k_seg, K) -> out2
+        assert epilogue == _lib.EPI_ACCUM and 0 < k_seg < K and k_seg % 64 == 0
+        assert out2.dtype == out.dtype and out2.shape == out.shape and out2.stride() == out.stride()
+        g.D2, g.k_seg = out2.data_ptr(), int(k_seg)
+        if k_limit2 is not None:
+            assert k_limit2.dtype == torch.int32 and k_limit2.is_cuda
+            g.k_limit2 = k_limit2.data_ptr()
     _lib.call("vb_gemm", C.byref(g), _stream())
     if GEMM_BENCH is not None:  # bench.py: device time of this launch, repeated back to back (no host gaps)
         ms = C.c_float(0.0)
@@ -96,7 +103,11 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bia
         Me = M if m_limit is None else min(M, int(m_limit[0].item()))   # executed extents of a device-limited launch
         if limit_seg_M:
             Me = min(limit_seg_M, Me) + (M - limit_seg_M if m_limit2 is None else min(M - limit_seg_M, int(m_limit2[0].item())))
-        Ke = K if k_limit is None else min(K, int(k_limit[0].item()))
+        if out2 is not None:
+            Ke = (k_seg if k_limit is None else min(k_seg, int(k_limit[0].item()))) + \
+                 (K - k_seg if k_limit2 is None else min(K - k_seg, int(k_limit2[0].item())))
+        else:
+            Ke = K if k_limit is None else min(K, int(k_limit[0].item()))
         GEMM_BENCH.append((2.0 * Me * N * Ke, ms.value, _lib.load().vb_gemm_backend(C.byref(g)) == _lib.GEMM_TC,
                            "M%d N%d K%d a%d b%d epi%d" % (M, N, K, a_kmajor, b_kmajor, epilogue)))
     return out

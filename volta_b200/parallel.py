@@ -34,6 +34,54 @@ def _convert(src, dst):
         dst.copy_(src)
 
 
+class SwitchAllReduce:
+    """The flat fp32 gradient buffer in SYMMETRIC memory (the same allocation on every rank, peer-mapped and bound to an
+    NVSwitch multicast address by torch.distributed._symmetric_memory - plumbing), reduced by this library's own kernel
+    `vb_allreduce_f32` (csrc/allreduce.cu): in-switch reduction with multimem.ld_reduce / multimem.st, no shared memory,
+    so its blocks are co-resident with the backward's persistent GEMM CTAs instead of displacing them.  One launch per
+    bucket on a high-priority communication stream; `wait()` joins it into the current stream."""
+
+    def __init__(self, numel, device, group=None, blocks=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        pg = group if group is not None else dist.distributed_c10d._get_default_group()
+        need = int(_lib.load().vb_allreduce_pad_bytes())
+        if symm_mem.get_signal_pad_size() < need:
+            symm_mem.set_signal_pad_size(need)
+        self.buf = symm_mem.empty(numel, dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, pg)
+        self.rank, self.world = int(self.hdl.rank), int(self.hdl.world_size)
+        self.multicast = int(self.hdl.multicast_ptr or 0)
+        if os.environ.get("VOLTA_B200_DDP_MULTICAST", "1") == "0":
+            self.multicast = 0
+        self.buffer_ptrs_dev = int(self.hdl.buffer_ptrs_dev)
+        self.signal_pad_ptrs_dev = int(self.hdl.signal_pad_ptrs_dev)
+        self.blocks = int(blocks if blocks is not None else os.environ.get("VOLTA_B200_DDP_BLOCKS", "16"))
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
+        self.device = device
+        self.launches = 0
+        # our flag region of the signal pad starts zeroed on every rank before anyone launches
+        pad = self.hdl.get_signal_pad(self.rank, (need // 4,), dtype=torch.int32)
+        pad[1024:].zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(group=pg)
+
+    @property
+    def kind(self):
+        return "nvswitch multimem" if self.multicast else "peer pointers (two-shot)"
+
+    def allreduce(self, lo, hi, scale):
+        from . import _lib
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)                       # the bucket's gradients are final in stream order
+        _lib.call("vb_allreduce_f32", self.buffer_ptrs_dev, self.multicast, self.signal_pad_ptrs_dev, self.rank, self.world,
+                  int(lo), int(hi - lo), float(scale), self.blocks, self.stream.cuda_stream)
+        self.launches += 1
+
+    def wait(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
+
 class GradBucketer:
     """Slices a flat gradient buffer into buckets that close as the backward frontier moves towards offset 0.
 
@@ -42,14 +90,16 @@ class GradBucketer:
     least `message_size` elements is all-reduced asynchronously.  `finish()` flushes the rest and waits.
     Pure host logic + torch.distributed: works with gloo on CPU tensors (tests) and NCCL on CUDA."""
 
-    def __init__(self, flat_grad, boundaries, message_size=10_000_000, group=None, average=True, wire_dtype=None):
+    def __init__(self, flat_grad, boundaries, message_size=10_000_000, group=None, average=True, wire_dtype=None, wire_buffer=None,
+                 reducer=None):
         self.flat = flat_grad
+        self.reducer = reducer    # SwitchAllReduce over the same buffer: buckets go through vb_allreduce_f32 instead of NCCL
         # Optional reduced-precision wire format (SURVEY.md 8e "bf16 or fp32 buckets"; apex reduces half-precision
         # gradients in their own dtype unless allreduce_always_fp32 is set, distributed.py:442-456): the bucket is cast
         # into `wire` when it closes, the collective moves half the bytes, the result is cast back in finish().
         self.wire = None
         if wire_dtype is not None and wire_dtype != flat_grad.dtype:
-            self.wire = torch.empty(flat_grad.numel(), dtype=wire_dtype, device=flat_grad.device)
+            self.wire = wire_buffer if wire_buffer is not None else torch.empty(flat_grad.numel(), dtype=wire_dtype, device=flat_grad.device)
         self.total = flat_grad.numel()
         self.boundaries = sorted(set(b for b in boundaries if 0 < b < self.total))
         self.message_size = int(message_size)
@@ -67,6 +117,12 @@ class GradBucketer:
 
     def _issue(self, lo, hi):
         if hi <= lo:
+            return
+        if self.reducer is not None:
+            self.reducer.allreduce(lo, hi, 1.0 / self.world if self.average else 1.0)
+            self.works.append((None, None, None))
+            self.ranges.append((lo, hi))
+            self.hi = lo
             return
         chunk = self.flat[lo:hi]
         sent = chunk
@@ -113,6 +169,11 @@ class GradBucketer:
 
     def finish(self):
         self._issue(0, self.hi)
+        if self.reducer is not None:
+            self.reducer.wait()
+            n = len(self.works)
+            self.works = []
+            return n
         for work, chunk, sent in self.works:
             work.wait()
             if sent is not chunk:
@@ -148,6 +209,8 @@ class DistributedDataParallel(torch.nn.Module):
         self._bucketer = None
         self.last_num_buckets = 0
         self._broadcast_params()
+        self._reducer = self._make_switch_allreduce()
+        self.registered = False if self._reducer is not None else self._register_gradient_buffer()
         engine.register_progress_hook(module, self._on_progress, self._make_cut_fn)
         # Optional: leave SMs to NCCL while the backward runs (the persistent GEMM assigns tiles to its blocks statically,
         # so a block displaced by an all-reduce block holds its tiles back).  Measured on 8 B200 (30 steps, B=256/GPU):
@@ -169,6 +232,55 @@ class DistributedDataParallel(torch.nn.Module):
         dist.broadcast(store.flat32, 0, group=self.group)
         store.refresh()
 
+    def _make_switch_allreduce(self):
+        """VOLTA_B200_DDP_ALLREDUCE = "switch" (default on CUDA with the fp32 wire): the gradient buffer lives in symmetric
+        memory and buckets are reduced by vb_allreduce_f32; "nccl": torch.distributed all_reduce.  Falls back to NCCL
+        (with a warning) when symmetric memory cannot be set up."""
+        mode = os.environ.get("VOLTA_B200_DDP_ALLREDUCE", "switch")
+        if (self.world_size == 1 or mode != "switch" or self.allreduce_dtype not in (None, torch.float32) or
+                not torch.cuda.is_available() or dist.get_backend(self.group) != "nccl"):
+            return None
+        store = engine.model_store(self.module)
+        if store.grad32 is not None or not store.flat32.is_cuda:
+            return None
+        try:
+            red = SwitchAllReduce(store.total, store.flat32.device, self.group)
+        except Exception as e:
+            import warnings
+            warnings.warn("volta_b200 DDP: symmetric-memory all-reduce unavailable (%r); using NCCL" % (e,))
+            return None
+        store.grad32 = red.buf
+        return red
+
+    def _register_gradient_buffer(self):
+        """NCCL user-buffer registration of the flat gradient buffer (one registration for every bucket, since a bucket is a
+        slice of it): the buffer is allocated by NCCL's own allocator (ncclMemAlloc through torch's MemPool) and the pool is
+        registered with the communicator, so the NVLink-SHARP (NVLS) all-reduce reads and writes it in place - no staging
+        copies through NCCL's internal buffers, fewer SMs taken from the backward GEMMs.  VOLTA_B200_DDP_REGISTER=0 keeps
+        a plain allocation.  Returns True when the registration took place."""
+        if self.world_size == 1 or os.environ.get("VOLTA_B200_DDP_REGISTER", "1") == "0" or not torch.cuda.is_available():
+            return False
+        store = engine.model_store(self.module)
+        if store.grad32 is not None or not store.flat32.is_cuda or dist.get_backend(self.group) != "nccl":
+            return False
+        try:
+            pg = self.group if self.group is not None else dist.distributed_c10d._get_default_group()
+            backend = pg._get_backend(store.flat32.device)
+            pool = torch.cuda.MemPool(backend.mem_allocator)
+            with torch.cuda.use_mem_pool(pool):
+                grad32 = torch.empty(store.total, dtype=torch.float32, device=store.flat32.device)
+                wire = None
+                if self.allreduce_dtype not in (None, torch.float32):
+                    wire = torch.empty(store.total, dtype=self.allreduce_dtype, device=store.flat32.device)
+            backend.register_mem_pool(pool)
+        except Exception as e:  # older torch / NCCL: plain buffers work, only slower
+            import warnings
+            warnings.warn("volta_b200 DDP: NCCL buffer registration unavailable (%s); using unregistered buffers" % (e,))
+            return False
+        store.grad32 = grad32
+        self._pool, self._wire = pool, wire   # the pool must outlive the buffers
+        return True
+
     def _boundaries(self, store):
         """Offsets where a sub-layer's parameters start: legal bucket ends."""
         bounds = set()
@@ -182,7 +294,9 @@ class DistributedDataParallel(torch.nn.Module):
         store = engine.model_store(self.module)
         if self._bucketer is None or self._bucketer.flat.data_ptr() != store.grad32.data_ptr():
             self._bucketer = GradBucketer(store.grad32, self._boundaries(store), self.message_size, self.group,
-                                          wire_dtype=self.allreduce_dtype)
+                                          wire_dtype=self.allreduce_dtype, wire_buffer=getattr(self, "_wire", None),
+                                          reducer=self._reducer if (self._reducer is not None and
+                                                                    self._reducer.buf.data_ptr() == store.grad32.data_ptr()) else None)
         return self._bucketer
 
     def _on_progress(self, frontier_offset):
