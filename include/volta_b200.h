@@ -421,7 +421,7 @@ int vb_retrieval_ranks(const float* scores, int64_t ld, const uint8_t* targets, 
  * over peer loads and stores the result to every peer.  The kernel takes no shared memory and 128 threads per block, so
  * its blocks share SMs with the persistent GEMM kernels of the backward.  EVERY rank must issue the same sequence of
  * calls (same offset, count, blocks); bytes [4096, vb_allreduce_pad_bytes()) of the signal pads belong to this kernel
- * and must be zero at the first call.  offset and count are multiples of 4; blocks <= 32 (0 = default). */
+ * and must be zero at the first call.  offset and count are multiples of 4; blocks <= 304 (0 = one per SM). */
 int vb_allreduce_f32(const uint64_t* buffer_ptrs_dev, uint64_t multicast_ptr, const uint64_t* signal_pad_ptrs_dev,
                      int32_t rank, int32_t world, int64_t offset, int64_t count, float scale, int32_t blocks, void* stream);
 int vb_allreduce_pad_bytes(void);

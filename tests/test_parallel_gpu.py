@@ -64,3 +64,29 @@ def test_ddp_gradients_equal_mean_of_single_rank_gradients(wire):
     rep = json.loads(line)
     assert rep["ddp_check"] == "ok" and rep["buckets_per_step"] >= 2 and rep["backward_segments"] >= 2, rep
     print(line)
+
+
+@pytest.mark.gpu
+def test_switch_allreduce_exact():
+    """vb_allreduce_f32 alone on >= 2 real GPUs: tests/allreduce_check.py under torchrun - integer-valued data, random
+    bucket offsets / sizes, multicast and peer-pointer modes, a matmul load on the main stream; every result exact."""
+    import json
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", "allreduce_check.py")],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    assert json.loads(line)["allreduce_check"] == "ok"
+    print(line)

@@ -24,7 +24,7 @@ namespace vb {
 namespace ar {
 
 constexpr int THREADS = 128;
-constexpr int MAX_BLOCKS = 32;
+constexpr int MAX_BLOCKS = 304;   // up to two blocks per SM
 constexpr int MAX_WORLD = 16;
 constexpr int PAD_OFFSET_BYTES = 4096;   // our flags live in [4096, 4096 + MAX_BLOCKS * MAX_WORLD * 4) of the signal pad
 
@@ -83,7 +83,9 @@ __device__ __forceinline__ void st_sys(float* p, float4 v) {
   asm volatile("st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-template <bool MULTICAST>
+// U = independent 16-byte vectors in flight per thread: 4 next to the backward GEMMs (40 registers: a block fits beside a
+// GEMM CTA), 8 for the last bucket of a step, which runs alone and is latency-bound on the NVLink round trip.
+template <bool MULTICAST, int U>
 __global__ void __launch_bounds__(THREADS)
 allreduce_kernel(const Args a) {
   // every rank's gradients of this bucket are final (written by kernels that precede this launch in their streams)
@@ -92,7 +94,6 @@ allreduce_kernel(const Args a) {
   const int64_t per = (n4 + a.world - 1) / a.world;
   const int64_t v0 = min(n4, (int64_t)a.rank * per), v1 = min(n4, v0 + per);   // this rank's slice
   const int64_t stride = (int64_t)gridDim.x * THREADS;
-  constexpr int U = 4;                                           // independent vectors in flight per thread
   int64_t i = v0 + (int64_t)blockIdx.x * THREADS + threadIdx.x;
   if constexpr (MULTICAST) {
     float* mc = reinterpret_cast<float*>(a.multicast_ptr) + a.offset;
@@ -142,9 +143,14 @@ int vb_allreduce_f32(const uint64_t* buffer_ptrs_dev, uint64_t multicast_ptr, co
   Args a;
   a.buffer_ptrs = buffer_ptrs_dev; a.multicast_ptr = multicast_ptr; a.signal_pad_ptrs = signal_pad_ptrs_dev;
   a.rank = rank; a.world = world; a.offset = offset; a.count = count; a.scale = scale;
-  const int grid = std::max(1, std::min(blocks > 0 ? blocks : 16, MAX_BLOCKS));
-  if (multicast_ptr != 0) allreduce_kernel<true><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
-  else allreduce_kernel<false><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
+  const int grid = std::max(1, std::min(blocks > 0 ? blocks : 148, MAX_BLOCKS));
+  const bool deep = blocks > 148;   // the caller asks for more than one block per SM: nothing else is running
+  if (multicast_ptr != 0) {
+    if (deep) allreduce_kernel<true, 8><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
+    else allreduce_kernel<true, 4><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
+  } else {
+    allreduce_kernel<false, 4><<<grid, THREADS, 0, (cudaStream_t)stream>>>(a);
+  }
   return vb::check_launch("allreduce_kernel");
 }
 

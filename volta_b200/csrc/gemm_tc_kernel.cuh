@@ -680,6 +680,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (p.k_limit || p.kseg_kb > 0) {
     // keep the number of slices the host planned for the machine, shorten them evenly to the live reduction length
     kb_per_split = max(1, (kbA + kbB + p.split_k - 1) / p.split_k);
+    // two segments round up separately: stay within the number of slices the host planned (one more slice than CTA pairs
+    // would cost a whole extra round)
+    while (kbB > 0 && kb_per_split < kbA + kbB &&
+           (kbA + kb_per_split - 1) / kb_per_split + (kbB + kb_per_split - 1) / kb_per_split > p.split_k) ++kb_per_split;
     splitA = (kbA + kb_per_split - 1) / kb_per_split;
     split_k = splitA + (kbB + kb_per_split - 1) / kb_per_split;
   }

@@ -54,9 +54,16 @@ class SwitchAllReduce:
         self.multicast = int(self.hdl.multicast_ptr or 0)
         if os.environ.get("VOLTA_B200_DDP_MULTICAST", "1") == "0":
             self.multicast = 0
-        self.buffer_ptrs_dev = int(self.hdl.buffer_ptrs_dev)
+        # the tensor may sit at an offset inside its (symmetric) allocation: the same offset on every rank
+        delta = self.buf.data_ptr() - int(self.hdl.buffer_ptrs[self.rank])
+        assert 0 <= delta < (1 << 40), "unexpected symmetric-memory layout"
+        self._ptr_table = torch.tensor([int(p) + delta for p in self.hdl.buffer_ptrs], dtype=torch.int64, device=device)
+        self.buffer_ptrs_dev = self._ptr_table.data_ptr()
+        if self.multicast:
+            self.multicast += delta
         self.signal_pad_ptrs_dev = int(self.hdl.signal_pad_ptrs_dev)
-        self.blocks = int(blocks if blocks is not None else os.environ.get("VOLTA_B200_DDP_BLOCKS", "16"))
+        self.blocks = int(blocks if blocks is not None else os.environ.get("VOLTA_B200_DDP_BLOCKS", "64"))
+        self.blocks_alone = int(os.environ.get("VOLTA_B200_DDP_BLOCKS_ALONE", "296"))
         self.stream = torch.cuda.Stream(device=device, priority=-1)
         self.device = device
         self.launches = 0
@@ -70,12 +77,14 @@ class SwitchAllReduce:
     def kind(self):
         return "nvswitch multimem" if self.multicast else "peer pointers (two-shot)"
 
-    def allreduce(self, lo, hi, scale):
+    def allreduce(self, lo, hi, scale, alone=False):
+        """alone=True: nothing else will run next to this launch (the last bucket of a step) - two blocks per SM, twice the
+        loads in flight; every rank must make the same choice."""
         from . import _lib
         cur = torch.cuda.current_stream(self.device)
         self.stream.wait_stream(cur)                       # the bucket's gradients are final in stream order
         _lib.call("vb_allreduce_f32", self.buffer_ptrs_dev, self.multicast, self.signal_pad_ptrs_dev, self.rank, self.world,
-                  int(lo), int(hi - lo), float(scale), self.blocks, self.stream.cuda_stream)
+                  int(lo), int(hi - lo), float(scale), self.blocks_alone if alone else self.blocks, self.stream.cuda_stream)
         self.launches += 1
 
     def wait(self):
@@ -119,7 +128,7 @@ class GradBucketer:
         if hi <= lo:
             return
         if self.reducer is not None:
-            self.reducer.allreduce(lo, hi, 1.0 / self.world if self.average else 1.0)
+            self.reducer.allreduce(lo, hi, 1.0 / self.world if self.average else 1.0, alone=(lo == 0))
             self.works.append((None, None, None))
             self.ranges.append((lo, hi))
             self.hi = lo
