@@ -122,7 +122,15 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def end(self):
+        self.t1 = time.perf_counter()
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi is started before the warm-up (it needs a few hundred ms to produce its
+        first line - longer than a short timed region), only samples that arrive after this mark are summarised."""
+        self.t0 = time.perf_counter()
 
     def __exit__(self, *a):
         if self.proc is not None:
@@ -134,7 +142,12 @@ class ClockSampler:
 
     def summary(self):
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t0 = getattr(self, "t0", 0.0)
+        t1 = getattr(self, "t1", float("inf")) + 0.05
+        rows = [r for ts, r in self.rows if t0 <= ts <= t1]
+        if not rows and self.rows:          # region shorter than the sampling period: the sample taken closest to it
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + min(t1, t0 + 60.0))))[1]]
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -297,17 +310,19 @@ class Harness:
     def timed(self, fn, steps, warmup):
         from volta_b200 import engine
         torch = self.torch
-        for _ in range(warmup):
-            fn()
-        self.barrier()
-        n0 = engine.launch_count
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         with ClockSampler(self.local) as cs:
+            for _ in range(warmup):
+                fn()
+            self.barrier()
+            n0 = engine.launch_count
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            cs.mark()
             e0.record()
             for _ in range(steps):
                 fn()
             e1.record()
             self.barrier()
+            cs.end()
         ms = e0.elapsed_time(e1)
         if self.world > 1:
             t = torch.tensor([ms], device=self.dev)

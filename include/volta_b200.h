@@ -203,6 +203,7 @@ int vb_layernorm_bwd(const void* dy, const void* x, const float* mean, const flo
 #define VB_ATTN_AUTO 0
 #define VB_ATTN_MMA 1
 #define VB_ATTN_SIMT 2
+#define VB_ATTN_TC 3    /* forward on the tcgen05 / TMEM / TMA kernel (bf16, d 64|128, <= 128 rows per sample); backward = VB_ATTN_MMA */
 
 typedef struct vb_attn_args {
   const void* qkv_t; const void* qkv_v;
@@ -220,7 +221,7 @@ typedef struct vb_attn_args {
   float scale;                        /* 1/sqrt(d) */
   float dropout_p_t, dropout_p_v;     /* text-query rows / vision-query rows */
   uint64_t seed, offset;
-  int32_t backend;                    /* VB_ATTN_AUTO | VB_ATTN_MMA (bf16 tensor-core path) | VB_ATTN_SIMT */
+  int32_t backend;                    /* VB_ATTN_AUTO | VB_ATTN_MMA (warp-level mma.sync) | VB_ATTN_SIMT | VB_ATTN_TC */
   int32_t reserved;
   /* Optional [B] int32 per stream (NULL = none), from vb_mask_lengths: positions at or beyond len[b] are padding.  The
    * tensor-core back-end then skips whole 16-row tiles of padding: as keys their softmax weight is exactly 0 (additive

@@ -440,18 +440,22 @@ def _attn_inputs(B, Lt, Lv, heads, d, pm, dtype):
     has_t, has_v = bool(pm & 7), bool(pm & 14)
     qt = rnd(B * Lt, 3 * A, dtype=dtype, scale=0.7) if has_t else None
     qv = rnd(B * Lv, 3 * A, dtype=dtype, scale=0.7, seed=1) if has_v else None
-    mt = (torch.arange(Lt)[None] < torch.tensor([Lt, max(3, Lt // 2), Lt - 1][:B])[:, None]).int().to(DEV)
-    mv = (torch.arange(Lv)[None] < torch.tensor([Lv - 2, Lv, max(2, Lv // 3)][:B])[:, None]).int().to(DEV)
+    lt = ([Lt, max(3, Lt // 2), Lt - 1] * ((B + 2) // 3))[:B]
+    lv = ([Lv - 2, Lv, max(2, Lv // 3)] * ((B + 2) // 3))[:B]
+    mt = (torch.arange(Lt)[None] < torch.tensor(lt)[:, None]).int().to(DEV)
+    mv = (torch.arange(Lv)[None] < torch.tensor(lv)[:, None]).int().to(DEV)
     return qt, qv, mt, mv, A
 
 
-@pytest.mark.parametrize("backend", ["mma", "simt"])
-@pytest.mark.parametrize("B,Lt,Lv,heads,d,pm", ATTN_CASES)
+@pytest.mark.parametrize("backend", ["tc", "mma", "simt"])
+@pytest.mark.parametrize("B,Lt,Lv,heads,d,pm", ATTN_CASES + [(7, 36, 37, 12, 64, 6), (9, 20, 25, 4, 64, 15), (5, 30, 101, 8, 128, 15)])
 def test_attention_fwd_bwd(backend, B, Lt, Lv, heads, d, pm):
+    """backend "tc": forward on the tcgen05 / TMEM / TMA kernel (several samples per 128-row tile), backward on the
+    warp-level kernel from the lse the tcgen05 forward saved."""
     dtype = torch.bfloat16
     qt, qv, mt, mv, A = _attn_inputs(B, Lt, Lv, heads, d, pm, dtype)
     tq, vq = bool(pm & 3), bool(pm & 12)
-    be = _lib.ATTN_MMA if backend == "mma" else _lib.ATTN_SIMT
+    be = {"mma": _lib.ATTN_MMA, "simt": _lib.ATTN_SIMT, "tc": _lib.ATTN_TC}[backend]
 
     def bufs():
         return (torch.zeros(B * Lt, A, dtype=dtype, device=DEV) if tq else None,
@@ -484,7 +488,8 @@ def test_attention_fwd_bwd(backend, B, Lt, Lv, heads, d, pm):
 
 @pytest.mark.parametrize("B,Lt,Lv,heads,d,pm", [(4, 36, 37, 12, 64, 1), (4, 36, 37, 12, 64, 9), (4, 36, 37, 12, 64, 6),
                                                 (4, 36, 37, 12, 64, 15), (4, 30, 101, 8, 128, 6), (4, 56, 80, 4, 64, 15)])
-def test_attention_skips_trailing_padding(B, Lt, Lv, heads, d, pm):
+@pytest.mark.parametrize("fwd_backend", ["mma", "tc"])
+def test_attention_skips_trailing_padding(fwd_backend, B, Lt, Lv, heads, d, pm):
     """vb_attn_args::len_*: tiles of trailing padding are skipped.  Valid rows must match the full computation (masked
     keys have weight exactly 0), padded query rows come out as zeros, gradients of valid rows are unchanged when the
     upstream gradient of the padded rows is zero (nothing downstream reads them); a hole in the mask below the length
@@ -516,7 +521,8 @@ def test_attention_skips_trailing_padding(B, Lt, Lv, heads, d, pm):
         cv = torch.full((B * Lv, A), 3.0, dtype=dtype, device=DEV) if vq else None
         lt, lv = torch.zeros(B, heads, Lt, device=DEV), torch.zeros(B, heads, Lv, device=DEV)
         args = (qt, qv, mt if has_t else None, mv if has_v else None)
-        ops.attention_fwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, _lib.ATTN_MMA, len_t=l_t, len_v=l_v)
+        ops.attention_fwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0,
+                          _lib.ATTN_TC if fwd_backend == "tc" else _lib.ATTN_MMA, len_t=l_t, len_v=l_v)
         dqt = torch.full_like(qt, 7.0) if has_t else None
         dqv = torch.full_like(qv, 7.0) if has_v else None
         ops.attention_bwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, _lib.ATTN_MMA, dctx_t=dct, dctx_v=dcv,
@@ -537,7 +543,8 @@ def test_attention_skips_trailing_padding(B, Lt, Lv, heads, d, pm):
 
 @pytest.mark.parametrize("B,Lt,Lv,heads,d,pm", [(4, 36, 37, 12, 64, 1), (4, 36, 37, 12, 64, 9), (4, 36, 37, 12, 64, 6),
                                                 (4, 30, 101, 8, 128, 6), (4, 56, 80, 4, 64, 15)])
-def test_attention_on_packed_rows(B, Lt, Lv, heads, d, pm):
+@pytest.mark.parametrize("fwd_backend", ["mma", "tc"])
+def test_attention_on_packed_rows(fwd_backend, B, Lt, Lv, heads, d, pm):
     """vb_attn_args::cu_*: sample b owns rows [cu[b], cu[b] + len[b]) of the qkv / ctx / dctx / dqkv buffers.  Against the
     padded layout with the same lengths: identical context rows and gradients for every valid position; rows beyond
     the packed count are not touched."""
@@ -577,7 +584,7 @@ def test_attention_on_packed_rows(B, Lt, Lv, heads, d, pm):
         kw = dict(len_t=ldev["t"], len_v=ldev["v"])
         if pk:
             kw.update(cu_t=cu["t"], cu_v=cu["v"])
-        ops.attention_fwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, _lib.ATTN_MMA, **kw)
+        ops.attention_fwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, _lib.ATTN_TC if fwd_backend == "tc" else _lib.ATTN_MMA, **kw)
         dqt = torch.full_like(qt, 7.0) if qt is not None else None
         dqv = torch.full_like(qv, 7.0) if qv is not None else None
         ops.attention_bwd(*args, ct, cv, lt, lv, B, Lt, Lv, heads, d, pm, 0.0, 0.0, 0, _lib.ATTN_MMA, dctx_t=dc["t"], dctx_v=dc["v"],

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libvolta_b200.so")
 F32, BF16 = 0, 1
 GEMM_AUTO, GEMM_TC, GEMM_SIMT = 0, 1, 2
 REGION_XENT, REGION_MSE, REGION_HUBER = 0, 1, 2
-ATTN_AUTO, ATTN_MMA, ATTN_SIMT = 0, 1, 2
+ATTN_AUTO, ATTN_MMA, ATTN_SIMT, ATTN_TC = 0, 1, 2, 3
 (EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_DROP_RES, EPI_MUL, EPI_ADD, EPI_DRELU, EPI_ACCUM,
  EPI_BIAS_ADD) = range(10)
 (ELT_COPY, ELT_ADD, ELT_MUL, ELT_RELU, ELT_DRELU, ELT_GELU, ELT_DGELU, ELT_SCALE, ELT_DROPOUT, ELT_AXPY) = range(10)

@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "gemm_tc_kernel.cuh"   // PTX wrappers (mbarrier, TMA, tcgen05) shared with the GEMM
 
 namespace vb {
 namespace attn {
@@ -793,6 +794,353 @@ mma_bwd_kernel(P p) {
   }
 }
 
+
+// =====================================================================================
+// tcgen05 back-end (forward): S = Q K^T and O = P V on the 5th-generation tensor cores, accumulators in TMEM,
+// operands brought in by TMA.
+//
+// A (sample, head) of this model is 20-101 rows - a quarter of the 128-row tcgen05 tile.  But consecutive samples are
+// consecutive ROWS of the [rows, 3A] Q/K/V buffer (packed or not), so ONE 128-row TMA box at (row of the first sample,
+// column of head h) brings in the Q (or K, or V) rows of G = floor(128 / L) samples at once.  The CTA computes the whole
+// 128 x 128 score block of those G samples per key stream with d/16 MMAs, and the softmax - one thread per query row,
+// reading its row of S straight out of TMEM - keeps only the columns of its own sample (block-diagonal) before P goes
+// back to shared memory (bf16, the K-major swizzled layout the MMA reads) for O = P V.  Masked keys, the joint softmax
+// over [text keys | vision keys], the dropout hash, the saved row log-sum-exp and the zero rows of padding queries are
+// those of the warp-level kernel above, so the backward (which recomputes P from lse) is unchanged.
+// One CTA = (group of G samples, head, query stream): 128 threads, thread 0 also issues the TMA loads and the MMAs.
+// =====================================================================================
+namespace tcf {
+using namespace vb::tc;
+
+constexpr int MAXG = 8;
+constexpr int TILE = 128;
+
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes) {
+  // cute::UMMA::SmemDescriptor, SWIZZLE_128B: start address, leading-dimension byte offset, stride byte offset 1024
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) | ((uint64_t)(1024u >> 4) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+struct Meta {
+  int qoff[MAXG], qspan[MAXG], qlen[MAXG];   // tile rows of sample s: [qoff, qoff + qspan); valid queries: the first qlen
+  int koff[2][MAXG], klen[2][MAXG];          // tile columns (per key stream) of the valid keys of sample s
+  int kend[2];                               // last key column + 1 per key stream
+  int G;
+};
+
+template <int D, int NKS>
+__global__ void __launch_bounds__(128)
+attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const P p, const int G,
+                   const int qs_mask) {
+  extern __shared__ uint8_t smraw[];
+  constexpr uint32_t TILE_BYTES = TILE * D * 2;                 // one 128-row operand tile: D/64 k-blocks of 16 KB
+  constexpr uint32_t P_BYTES = 2u * 16384u;                     // 128 rows x 128 key columns, bf16 (two 64-column k-blocks)
+  constexpr uint32_t QK_BYTES = (1 + NKS) * TILE_BYTES;
+  constexpr uint32_t QKP_BYTES = QK_BYTES > NKS * P_BYTES ? QK_BYTES : NKS * P_BYTES;   // P reuses the Q / K tiles
+  const uint32_t base = (smem_u32(smraw) + 1023u) & ~1023u;
+  const uint32_t sQ = base, sK0 = base + TILE_BYTES, sV0 = base + QKP_BYTES, sP0 = base;
+  uint8_t* gen = smraw + (base - smem_u32(smraw));              // generic pointer to the aligned base
+  uint8_t* tail = gen + QKP_BYTES + NKS * TILE_BYTES;
+  float* madd = reinterpret_cast<float*>(tail);                 // [2][128]
+  Meta* meta = reinterpret_cast<Meta*>(tail + 1024);
+  const uint32_t bars = base + QKP_BYTES + NKS * TILE_BYTES + 1024 + 512;
+  const uint32_t bar_tma = bars, bar_mma = bars + 8, tmem_slot = bars + 16;
+
+  const int t = threadIdx.x, warp = t >> 5;
+  // which query stream this CTA serves (blockIdx.y-th set bit of qs_mask)
+  int qs = (qs_mask & 1) ? 0 : 1;
+  if (blockIdx.y == 1) qs = 1;
+  const int grp = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  const int b0 = grp * G;
+  const int nG = min(G, p.B - b0);
+  const bool ks_on[2] = {pair_on(p.pair_mask, qs, 0) && p.qkv[0] != nullptr, pair_on(p.pair_mask, qs, 1) && p.qkv[1] != nullptr};
+
+  if (t == 0) {
+    mbar_init(bar_tma, 1);
+    mbar_init(bar_mma, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+    tma_prefetch_desc(&map0);
+    tma_prefetch_desc(&map1);
+  }
+  if (warp == 0) tmem_alloc<NKS * 128, 1>(tmem_slot);
+  // ---- sample geometry of this group
+  __shared__ int64_t base_row[2];
+  if (t < 2) {
+    const int st = t;
+    int64_t r0 = 0;
+    if (p.qkv[st] != nullptr) r0 = p.cu[st] ? (int64_t)p.cu[st][b0] : (int64_t)b0 * p.L[st];
+    base_row[st] = r0;
+  }
+  if (t == 0) meta->G = nG;
+  __syncthreads();
+  if (t < nG) {
+    const int b = b0 + t;
+    for (int st = 0; st < 2; ++st) {
+      if (p.qkv[st] == nullptr) { if (st == qs) { meta->qoff[t] = 0; meta->qspan[t] = 0; meta->qlen[t] = 0; } meta->koff[st][t] = 0; meta->klen[st][t] = 0; continue; }
+      const int Le = eff_len(p, st, b);
+      const int64_t r0 = p.cu[st] ? (int64_t)p.cu[st][b] : (int64_t)b * p.L[st];
+      const int off = (int)(r0 - base_row[st]);
+      if (st == qs) { meta->qoff[t] = off; meta->qspan[t] = p.cu[st] ? Le : p.L[st]; meta->qlen[t] = Le; }
+      meta->koff[st][t] = off; meta->klen[st][t] = ks_on[st] ? Le : 0;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (t < 2) {
+    int e = 0;
+    for (int s_ = 0; s_ < nG; ++s_) e = max(e, meta->koff[t][s_] + meta->klen[t][s_]);
+    meta->kend[t] = ks_on[t] ? min(e, TILE) : 0;
+  }
+  // ---- TMA: Q tile of the query stream, K and V tiles of every enabled key stream
+  if (t == 0) {
+    int nks = (ks_on[0] ? 1 : 0) + (ks_on[1] ? 1 : 0);
+    mbar_expect_tx(bar_tma, (1 + 2 * nks) * TILE_BYTES);
+    const CUtensorMap* mq = qs ? &map1 : &map0;
+#pragma unroll
+    for (int kb = 0; kb < D / 64; ++kb) tma_load_2d(sQ + kb * 16384, mq, bar_tma, h * D + kb * 64, (int32_t)base_row[qs]);
+    int slot = 0;
+    for (int ks = 0; ks < 2; ++ks) {
+      if (!ks_on[ks]) continue;
+      const CUtensorMap* mk = ks ? &map1 : &map0;
+#pragma unroll
+      for (int kb = 0; kb < D / 64; ++kb) {
+        tma_load_2d(sK0 + slot * TILE_BYTES + kb * 16384, mk, bar_tma, p.A + h * D + kb * 64, (int32_t)base_row[ks]);
+        tma_load_2d(sV0 + slot * TILE_BYTES + kb * 16384, mk, bar_tma, 2 * p.A + h * D + kb * 64, (int32_t)base_row[ks]);
+      }
+      ++slot;
+    }
+  }
+  __syncthreads();   // kend visible
+  // additive key masks (log2 domain) per tile column, while the loads are in flight
+  for (int ks = 0; ks < 2; ++ks) {
+    float v = -INFINITY;
+    if (ks_on[ks]) {
+      for (int s_ = 0; s_ < nG; ++s_) {
+        const int j = t - meta->koff[ks][s_];
+        if (j >= 0 && j < meta->klen[ks][s_]) v = p.mask[ks][(int64_t)(b0 + s_) * p.L[ks] + j] ? 0.f : -14426.950408889634f;
+      }
+    }
+    madd[ks * TILE + t] = v;
+  }
+  __syncthreads();   // every thread reads other threads' mask entries
+  mbar_wait(bar_tma, 0);
+  // V rows between the last valid key and the end of its 16-key MMA step may be memory nobody wrote: zero them
+  {
+    int slot = 0;
+    for (int ks = 0; ks < 2; ++ks) {
+      if (!ks_on[ks]) continue;
+      const int e0 = meta->kend[ks], e1 = min(TILE, (e0 + 15) & ~15);
+      for (int i = t; i < (e1 - e0) * (D / 64) * 8; i += 128) {
+        const int row = e0 + i / ((D / 64) * 8), rem = i % ((D / 64) * 8), kb = rem / 8, c16 = rem % 8;
+        *reinterpret_cast<uint4*>(gen + (sV0 - base) + slot * TILE_BYTES + kb * 16384 + row * 128 + c16 * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      ++slot;
+    }
+  }
+  // ---- S = Q K^T per key stream (thread 0), accumulators at TMEM columns [ks_slot * 128, +128)
+  if (t == 0) {
+    tcgen05_fence_after();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int slot = 0;
+    for (int ks = 0; ks < 2; ++ks) {
+      if (!ks_on[ks]) continue;
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        const uint32_t off = (kk / 4) * 16384 + (kk % 4) * 32;
+        umma_bf16(tmem_base + slot * 128, smem_desc(sQ + off, 16), smem_desc(sK0 + slot * TILE_BYTES + off, 16), idesc, kk > 0 ? 1u : 0u);
+      }
+      ++slot;
+    }
+    umma_commit(bar_mma);
+  }
+  // ---- softmax: thread t = query row t of the tile
+  int sidx = -1;
+  for (int s_ = 0; s_ < nG; ++s_)
+    if (t >= meta->qoff[s_] && t < meta->qoff[s_] + meta->qspan[s_]) sidx = s_;
+  const int jq = sidx >= 0 ? t - meta->qoff[sidx] : 0;
+  const bool row_valid = sidx >= 0 && jq < meta->qlen[sidx];
+  int c0[2] = {0, 0}, c1[2] = {0, 0};
+  if (row_valid) {
+    for (int ks = 0; ks < 2; ++ks) { c0[ks] = meta->koff[ks][sidx]; c1[ks] = min(TILE, c0[ks] + meta->klen[ks][sidx]); }
+  }
+  const float sc2 = p.scale * 1.4426950408889634f;
+  mbar_wait(bar_mma, 0);
+  tcgen05_fence_after();
+  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+  float mx = -INFINITY;
+  {
+    int slot = 0;
+    for (int ks = 0; ks < 2; ++ks) {
+      if (!ks_on[ks]) continue;
+      const int nch = (meta->kend[ks] + 31) >> 5;
+      for (int ch = 0; ch < nch; ++ch) {
+        uint32_t raw[32];
+        tmem_ld32(trow + slot * 128 + ch * 32, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int col = ch * 32 + j;
+          if (col >= c0[ks] && col < c1[ks]) mx = fmaxf(mx, fmaf(__uint_as_float(raw[j]), sc2, madd[ks * TILE + col]));
+        }
+      }
+      ++slot;
+    }
+  }
+  if (mx == -INFINITY) mx = 0.f;
+  float sum = 0.f;
+  const uint32_t thresh = p.thresh[qs];
+  const uint64_t seed_eff = effective_seed(p.seed, p.seed_ptr);
+  const int Ltot = p.L[0] + p.L[1];
+  const uint32_t rt = attn_rowterm(seed_eff, ((uint32_t)(b0 + max(sidx, 0)) * p.heads + h) * Ltot + (qs ? p.L[0] : 0) + jq);
+  {
+    int slot = 0;
+    for (int ks = 0; ks < 2; ++ks) {
+      if (!ks_on[ks]) continue;
+      const int nch = (((meta->kend[ks] + 15) & ~15) + 31) >> 5;   // every column the P V MMAs will read gets written
+      uint8_t* prow = gen + (sP0 - base) + slot * P_BYTES + (t >> 3) * 1024 + (t & 7) * 128;
+      for (int ch = 0; ch < nch; ++ch) {
+        uint32_t raw[32];
+        tmem_ld32(trow + slot * 128 + ch * 32, raw);
+        tmem_ld_wait();
+        uint32_t packed[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float pr[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int col = ch * 32 + j + u;
+            float v = 0.f;
+            if (col >= c0[ks] && col < c1[ks]) {
+              v = ex2f(fmaf(__uint_as_float(raw[j + u]), sc2, madd[ks * TILE + col]) - mx);
+              sum += v;
+              if (thresh) {
+                const int jk = col - c0[ks];
+                const uint32_t hsh = attn_mix(rt ^ attn_colterm(seed_eff, ks, jk));
+                if (((jk & 1) ? (hsh >> 16) : (hsh & 0xFFFFu)) < thresh) v = 0.f;
+              }
+            }
+            pr[u] = v;
+          }
+          packed[j >> 1] = pack_bf16x2(pr[0], pr[1]);
+        }
+        // 32 columns = 4 chunks of 16 bytes in k-block (ch / 2), 128B-swizzled: chunk index ^= row % 8
+        uint8_t* kbp = prow + (ch >> 1) * 16384;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int c16 = ((ch & 1) * 4 + q4) ^ (t & 7);
+          *reinterpret_cast<uint4*>(kbp + c16 * 16) = make_uint4(packed[q4 * 4], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
+        }
+      }
+      ++slot;
+    }
+  }
+  // every thread's reads of S and writes of P (and of the zeroed V rows) are done before the second MMA overwrites S with O
+  tcgen05_fence_before();
+  fence_proxy_async();
+  __syncthreads();
+  if (t == 0) {
+    tcgen05_fence_after();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((uint32_t)(D >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    int slot = 0;
+    bool first = true;
+    for (int ks = 0; ks < 2; ++ks) {
+      if (!ks_on[ks]) continue;
+      const int nk16 = (meta->kend[ks] + 15) >> 4;
+      for (int k16 = 0; k16 < nk16; ++k16) {
+        const uint64_t adesc = smem_desc(sP0 + slot * P_BYTES + (k16 / 4) * 16384 + (k16 % 4) * 32, 16);
+        const uint64_t bdesc = smem_desc(sV0 + slot * TILE_BYTES + k16 * 2048, 16384);
+        umma_bf16(tmem_base, adesc, bdesc, idesc, first ? 0u : 1u);
+        first = false;
+      }
+      ++slot;
+    }
+    umma_commit(bar_mma);
+  }
+  // ---- epilogue: O row / sum -> bf16 -> ctx; row log-sum-exp
+  const float osc = (row_valid && sum > 0.f) ? p.keep_scale[qs] / sum : 0.f;
+  if (sidx >= 0 && jq < p.L[qs])
+    p.lse[qs][((int64_t)(b0 + sidx) * p.heads + h) * p.L[qs] + jq] = row_valid ? (mx + __log2f(sum)) * 0.6931471805599453f : 0.f;
+  mbar_wait(bar_mma, 1);
+  tcgen05_fence_after();
+  const bool any_keys = (meta->kend[0] + meta->kend[1]) > 0;
+  bf16* out = reinterpret_cast<bf16*>(p.ctx[qs]) + (base_row[qs] + t) * p.ld_ctx[qs] + h * D;
+#pragma unroll
+  for (int ch = 0; ch < D / 32; ++ch) {
+    uint32_t raw[32];
+    tmem_ld32(trow + ch * 32, raw);     // warp-collective: every lane takes part, only rows of a sample are stored
+    tmem_ld_wait();
+    if (sidx >= 0) {
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        uint32_t o4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float a0 = any_keys ? __uint_as_float(raw[v * 8 + 2 * u]) * osc : 0.f;
+          const float a1 = any_keys ? __uint_as_float(raw[v * 8 + 2 * u + 1]) * osc : 0.f;
+          o4[u] = pack_bf16x2(osc != 0.f ? a0 : 0.f, osc != 0.f ? a1 : 0.f);
+        }
+        *reinterpret_cast<uint4*>(out + ch * 32 + v * 8) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<NKS * 128, 1>(tmem_base);
+  }
+}
+
+template <int D, int NKS> static size_t smem_bytes() {
+  const size_t tile = (size_t)TILE * D * 2, pb = 2 * 16384;
+  const size_t qk = (1 + NKS) * tile, qkp = qk > NKS * pb ? qk : NKS * pb;
+  return 1024 + qkp + NKS * tile + 1024 + 512 + 64;
+}
+
+// Can the tcgen05 forward run this call?  Every stream's sample must fit a 128-row tile.
+static bool ok(const vb_attn_args& a, const P& p) {
+  if (a.dtype != VB_BF16 || (a.d != 64 && a.d != 128)) return false;
+  for (int s = 0; s < 2; ++s) {
+    if (!p.qkv[s]) continue;
+    if (p.L[s] > TILE || !aligned16(p.qkv[s]) || (p.ld[s] % 8) != 0) return false;
+    if (p.ctx[s] && (!aligned16(p.ctx[s]) || (p.ld_ctx[s] % 8) != 0)) return false;
+  }
+  return true;
+}
+
+static int launch(const vb_attn_args& a, const P& p, cudaStream_t st) {
+  const int Lmax = std::max(p.L[0], p.L[1]);
+  const int G = std::max(1, std::min(MAXG, TILE / Lmax));
+  const int qs_mask = ((p.pair_mask & 3) ? 1 : 0) | ((p.pair_mask & 12) ? 2 : 0);
+  const int nq = (qs_mask == 3) ? 2 : 1;
+  int nks = 1;
+  for (int qs = 0; qs < 2; ++qs)
+    if ((qs_mask >> qs) & 1) nks = std::max(nks, (pair_on(p.pair_mask, qs, 0) ? 1 : 0) + (pair_on(p.pair_mask, qs, 1) ? 1 : 0));
+  CUtensorMap maps[2];
+  for (int s = 0; s < 2; ++s) {
+    const int o = p.qkv[s] ? s : 1 - s;   // an absent stream gets a valid (unused) descriptor
+    int rc = vb::tc::make_map(&maps[s], p.qkv[o], (int64_t)p.B * p.L[o], 3 * (int64_t)p.A, p.ld[o], TILE);
+    if (rc) return rc;
+  }
+  const dim3 grid((unsigned)(((p.B + G - 1) / G) * p.heads), (unsigned)nq);
+#define VB_ATC(D_, N_)                                                                                         \
+  do {                                                                                                         \
+    const size_t sm = smem_bytes<D_, N_>();                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_fwd_kernel<D_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+    VB_REQUIRE(e == cudaSuccess, (int)e, "attention (tcgen05): cannot reserve %zu bytes of shared memory", sm); \
+    attn_tc_fwd_kernel<D_, N_><<<grid, 128, sm, st>>>(maps[0], maps[1], p, G, qs_mask);                        \
+  } while (0)
+  if (a.d == 64) { if (nks == 1) VB_ATC(64, 1); else VB_ATC(64, 2); }
+  else { if (nks == 1) VB_ATC(128, 1); else VB_ATC(128, 2); }
+#undef VB_ATC
+  return check_launch("attention attn_tc_fwd_kernel");
+}
+}  // namespace tcf
+
 // ---- host ----------------------------------------------------------------------------
 static int fill(const vb_attn_args& a, P& p, bool bwd) {
   VB_REQUIRE(a.B > 0 && a.heads > 0 && a.d > 0, VB_ERR_ARG, "attention: bad sizes B=%d heads=%d d=%d", a.B, a.heads, a.d);
@@ -895,6 +1243,13 @@ static int run(const vb_attn_args& a, cudaStream_t st, bool bwd) {
   const bool use_mma = can_mma && a.backend != VB_ATTN_SIMT;
   VB_REQUIRE(use_mma || (!p.cu[0] && !p.cu[1]), VB_ERR_UNSUPPORTED, "attention: packed rows (cu_*) need the tensor-core back-end");
   const unsigned grid = (unsigned)(a.B * a.heads);
+  // forward on the tcgen05 / TMEM / TMA kernel (VB_ATTN_TC, or AUTO unless VOLTA_B200_ATTN_TC=0); the backward keeps
+  // the warp-level kernel, which recomputes P from the same lse / dropout hash
+  if (!bwd && a.backend != VB_ATTN_SIMT && a.backend != VB_ATTN_MMA && tcf::ok(a, p)) {
+    const char* e = getenv("VOLTA_B200_ATTN_TC");
+    if (a.backend == VB_ATTN_TC || !(e && e[0] == '0')) return tcf::launch(a, p, st);
+  }
+  VB_REQUIRE(a.backend != VB_ATTN_TC || bwd, VB_ERR_UNSUPPORTED, "attention: tcgen05 back-end cannot run this call (bf16, d 64/128, <= 128 rows per sample)");
   if (use_mma) {
     const LaunchGeo lg = launch_geo(p, a.d);
     const dim3 g2(grid, (unsigned)p.ngroups);

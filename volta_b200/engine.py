@@ -84,7 +84,7 @@ class Runtime:
         self._site = 0
         self.gemm_backend = {"auto": _lib.GEMM_AUTO, "tc": _lib.GEMM_TC, "simt": _lib.GEMM_SIMT}[
             os.environ.get("VOLTA_B200_GEMM", "auto")]
-        self.attn_backend = {"auto": _lib.ATTN_AUTO, "mma": _lib.ATTN_MMA, "simt": _lib.ATTN_SIMT}[
+        self.attn_backend = {"auto": _lib.ATTN_AUTO, "mma": _lib.ATTN_MMA, "simt": _lib.ATTN_SIMT, "tc": _lib.ATTN_TC}[
             os.environ.get("VOLTA_B200_ATTN", "auto")]
         if self.precision == "fp32":
             self.gemm_backend, self.attn_backend = _lib.GEMM_SIMT, _lib.ATTN_SIMT
