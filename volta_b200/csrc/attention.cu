@@ -963,31 +963,54 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
     if (t >= meta->qoff[s_] && t < meta->qoff[s_] + meta->qspan[s_]) sidx = s_;
   const int jq = sidx >= 0 ? t - meta->qoff[sidx] : 0;
   const bool row_valid = sidx >= 0 && jq < meta->qlen[sidx];
-  int c0[2] = {0, 0}, c1[2] = {0, 0};
-  if (row_valid) {
-    for (int ks = 0; ks < 2; ++ks) { c0[ks] = meta->koff[ks][sidx]; c1[ks] = min(TILE, c0[ks] + meta->klen[ks][sidx]); }
+  // key slots of this CTA (compile-time indexed: no local-memory arrays): slot -> key stream, this row's column range
+  // [lo, lo + n) inside the slot, the columns the P V MMAs read (kend rounded up to 16)
+  int slot_ks[NKS], lo[NKS], n[NKS], kend16[NKS];
+  {
+    int sl = 0;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      if (ks_on[ks] && sl < NKS) {
+        slot_ks[sl] = ks;
+        lo[sl] = row_valid ? meta->koff[ks][sidx] : 0;
+        n[sl] = row_valid ? min(TILE - lo[sl], meta->klen[ks][sidx]) : 0;
+        kend16[sl] = min(TILE, (meta->kend[ks] + 15) & ~15);
+        ++sl;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NKS; ++q)
+      if (q >= sl) { slot_ks[q] = 0; lo[q] = 0; n[q] = 0; kend16[q] = 0; }
+  }
+  // 32-column chunks this WARP needs per slot: the union of its 32 rows' ranges (consecutive rows belong to consecutive
+  // samples, so the union is short); chunks outside it hold no probability of these rows and are written as zeros
+  int ch0[NKS], ch1[NKS];
+#pragma unroll
+  for (int q = 0; q < NKS; ++q) {
+    const int a0 = __reduce_min_sync(0xffffffffu, n[q] > 0 ? lo[q] : TILE);
+    const int a1 = __reduce_max_sync(0xffffffffu, n[q] > 0 ? lo[q] + n[q] : 0);
+    ch0[q] = a0 >> 5;
+    ch1[q] = (a1 + 31) >> 5;          // empty when a1 == 0
+    if (a1 == 0) ch0[q] = 0;
   }
   const float sc2 = p.scale * 1.4426950408889634f;
   mbar_wait(bar_mma, 0);
   tcgen05_fence_after();
   const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
   float mx = -INFINITY;
-  {
-    int slot = 0;
-    for (int ks = 0; ks < 2; ++ks) {
-      if (!ks_on[ks]) continue;
-      const int nch = (meta->kend[ks] + 31) >> 5;
-      for (int ch = 0; ch < nch; ++ch) {
-        uint32_t raw[32];
-        tmem_ld32(trow + slot * 128 + ch * 32, raw);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = ch * 32 + j;
-          if (col >= c0[ks] && col < c1[ks]) mx = fmaxf(mx, fmaf(__uint_as_float(raw[j]), sc2, madd[ks * TILE + col]));
-        }
+  for (int q = 0; q < NKS; ++q) {
+    const float* md = madd + slot_ks[q] * TILE;
+    for (int ch = ch0[q]; ch < ch1[q]; ++ch) {
+      uint32_t raw[32];
+      tmem_ld32(trow + q * 128 + ch * 32, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int col = ch * 32 + j;
+        const float v = fmaf(__uint_as_float(raw[j]), sc2, md[col]);
+        mx = fmaxf(mx, ((unsigned)(col - lo[q]) < (unsigned)n[q]) ? v : -INFINITY);
       }
-      ++slot;
     }
   }
   if (mx == -INFINITY) mx = 0.f;
@@ -996,46 +1019,46 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map0, const __grid_consta
   const uint64_t seed_eff = effective_seed(p.seed, p.seed_ptr);
   const int Ltot = p.L[0] + p.L[1];
   const uint32_t rt = attn_rowterm(seed_eff, ((uint32_t)(b0 + max(sidx, 0)) * p.heads + h) * Ltot + (qs ? p.L[0] : 0) + jq);
-  {
-    int slot = 0;
-    for (int ks = 0; ks < 2; ++ks) {
-      if (!ks_on[ks]) continue;
-      const int nch = (((meta->kend[ks] + 15) & ~15) + 31) >> 5;   // every column the P V MMAs will read gets written
-      uint8_t* prow = gen + (sP0 - base) + slot * P_BYTES + (t >> 3) * 1024 + (t & 7) * 128;
-      for (int ch = 0; ch < nch; ++ch) {
+#pragma unroll
+  for (int q = 0; q < NKS; ++q) {
+    const float* md = madd + slot_ks[q] * TILE;
+    uint8_t* prow = gen + (sP0 - base) + q * P_BYTES + (t >> 3) * 1024 + (t & 7) * 128;
+    const int nch = (kend16[q] + 31) >> 5;             // every column the P V MMAs will read gets written
+    for (int ch = 0; ch < nch; ++ch) {
+      uint32_t packed[16];
+      if (ch >= ch0[q] && ch < ch1[q]) {               // warp-uniform
         uint32_t raw[32];
-        tmem_ld32(trow + slot * 128 + ch * 32, raw);
+        tmem_ld32(trow + q * 128 + ch * 32, raw);
         tmem_ld_wait();
-        uint32_t packed[16];
+        float pr[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float pr[2];
+        for (int j = 0; j < 32; ++j) {
+          const int col = ch * 32 + j;
+          const float e = ex2f(fmaf(__uint_as_float(raw[j]), sc2, md[col]) - mx);
+          pr[j] = ((unsigned)(col - lo[q]) < (unsigned)n[q]) ? e : 0.f;
+          sum += pr[j];
+        }
+        if (thresh) {                                  // uniform: dropout on the probabilities of this query stream
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int col = ch * 32 + j + u;
-            float v = 0.f;
-            if (col >= c0[ks] && col < c1[ks]) {
-              v = ex2f(fmaf(__uint_as_float(raw[j + u]), sc2, madd[ks * TILE + col]) - mx);
-              sum += v;
-              if (thresh) {
-                const int jk = col - c0[ks];
-                const uint32_t hsh = attn_mix(rt ^ attn_colterm(seed_eff, ks, jk));
-                if (((jk & 1) ? (hsh >> 16) : (hsh & 0xFFFFu)) < thresh) v = 0.f;
-              }
-            }
-            pr[u] = v;
+          for (int j = 0; j < 32; ++j) {
+            const int jk = ch * 32 + j - lo[q];
+            const uint32_t hsh = attn_mix(rt ^ attn_colterm(seed_eff, slot_ks[q], jk));
+            if (((jk & 1) ? (hsh >> 16) : (hsh & 0xFFFFu)) < thresh) pr[j] = 0.f;
           }
-          packed[j >> 1] = pack_bf16x2(pr[0], pr[1]);
         }
-        // 32 columns = 4 chunks of 16 bytes in k-block (ch / 2), 128B-swizzled: chunk index ^= row % 8
-        uint8_t* kbp = prow + (ch >> 1) * 16384;
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int c16 = ((ch & 1) * 4 + q4) ^ (t & 7);
-          *reinterpret_cast<uint4*>(kbp + c16 * 16) = make_uint4(packed[q4 * 4], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
-        }
+        for (int j = 0; j < 32; j += 2) packed[j >> 1] = pack_bf16x2(pr[j], pr[j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) packed[j] = 0u;
       }
-      ++slot;
+      // 32 columns = 4 chunks of 16 bytes in k-block (ch / 2), 128B-swizzled: chunk index ^= row % 8
+      uint8_t* kbp = prow + (ch >> 1) * 16384;
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int c16 = ((ch & 1) * 4 + q4) ^ (t & 7);
+        *reinterpret_cast<uint4*>(kbp + c16 * 16) = make_uint4(packed[q4 * 4], packed[q4 * 4 + 1], packed[q4 * 4 + 2], packed[q4 * 4 + 3]);
+      }
     }
   }
   // every thread's reads of S and writes of P (and of the zeroed V rows) are done before the second MMA overwrites S with O
@@ -1245,9 +1268,15 @@ static int run(const vb_attn_args& a, cudaStream_t st, bool bwd) {
   const unsigned grid = (unsigned)(a.B * a.heads);
   // forward on the tcgen05 / TMEM / TMA kernel (VB_ATTN_TC, or AUTO unless VOLTA_B200_ATTN_TC=0); the backward keeps
   // the warp-level kernel, which recomputes P from the same lse / dropout hash
+  // Measured (B200, isolated launches): at 30 x 101 rows and d = 128 (vilbert_base retrieval) it is the faster one; at
+  // the 36/37-row pre-training shapes three samples share a tile, each thread's softmax walks columns of other samples,
+  // and the warp-level kernel (scores kept in mma fragments) stays ahead - AUTO therefore takes it only when one sample
+  // fills more than half a tile.  VOLTA_B200_ATTN_TC=1 forces it wherever it can run, =0 never.
   if (!bwd && a.backend != VB_ATTN_SIMT && a.backend != VB_ATTN_MMA && tcf::ok(a, p)) {
     const char* e = getenv("VOLTA_B200_ATTN_TC");
-    if (a.backend == VB_ATTN_TC || !(e && e[0] == '0')) return tcf::launch(a, p, st);
+    const bool force = a.backend == VB_ATTN_TC || (e && e[0] == '1');
+    const bool never = a.backend != VB_ATTN_TC && e && e[0] == '0';
+    if (force || (!never && std::max(p.L[0], p.L[1]) > tcf::TILE / 2)) return tcf::launch(a, p, st);
   }
   VB_REQUIRE(a.backend != VB_ATTN_TC || bwd, VB_ERR_UNSUPPORTED, "attention: tcgen05 back-end cannot run this call (bf16, d 64/128, <= 128 rows per sample)");
   if (use_mma) {
