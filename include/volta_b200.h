@@ -135,6 +135,9 @@ typedef struct vb_gemm_args {
   void* D2;
   const int32_t* k_limit2;
   int64_t k_seg;
+  /* Host-side estimate of the rows a device-limited launch (m_limit / m_limit2) will really produce, 0 = unknown.  It only
+   * steers the tile choice (how many tiles of which width fill the SMs in how many rounds); results do not depend on it. */
+  int64_t m_hint;
 } vb_gemm_args;
 
 int vb_gemm(const vb_gemm_args* args, void* stream);

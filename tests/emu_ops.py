@@ -25,7 +25,7 @@ def _dgelu(x):
 
 def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
          dropout_p=0.0, seed=0, offset=0, backend=0, split_k=0, M=None, N=None, K=None, b2=None, bias2=None, split_M=0,
-         m_limit=None, k_limit=None, m_limit2=None, limit_seg_M=0, out2=None, k_seg=0, k_limit2=None):
+         m_limit=None, k_limit=None, m_limit2=None, limit_seg_M=0, out2=None, k_seg=0, k_limit2=None, m_hint=0):
     if out2 is not None:   # two reduction segments: rows [0, k_seg) of the (MN-major) operands -> out, rows [k_seg, K) -> out2
         assert epilogue == _lib.EPI_ACCUM and not a_kmajor and not b_kmajor and k_seg % 64 == 0
         gemm(a[:k_seg], b[:k_seg], out, a_kmajor=False, b_kmajor=False, epilogue=epilogue, k_limit=k_limit)

@@ -28,7 +28,7 @@ class GemmArgs(C.Structure):
                 ("bias", _vp), ("aux_in", _vp), ("aux_out", _vp), ("ld_aux", _i64), ("alpha", _f),
                 ("dropout_p", _f), ("seed", _u64), ("offset", _u64), ("split_k", _i32), ("reserved", _i32),
                 ("B2", _vp), ("bias2", _vp), ("split_M", _i64), ("m_limit", _vp), ("k_limit", _vp), ("m_limit2", _vp), ("limit_seg_M", _i64),
-                ("D2", _vp), ("k_limit2", _vp), ("k_seg", _i64)]
+                ("D2", _vp), ("k_limit2", _vp), ("k_seg", _i64), ("m_hint", _i64)]
 
 
 class AttnArgs(C.Structure):

@@ -1074,7 +1074,9 @@ static int launch_epi(const vb_gemm_args& a, cudaStream_t stream) {
     if (a.B2 != nullptr && a.split_M > 0 && (a.split_M % (128 * o.cg)) != 0) continue;   // row split must fall on a tile edge
     if (a.limit_seg_M > 0 && (a.limit_seg_M % (128 * o.cg)) != 0) continue;
     if (o.bn > 128 && a.N <= 128 && o.cg == 1) continue;
-    const int64_t tiles = ceil_div(a.M, 128 * o.cg) * ceil_div(a.N, o.bn);
+    // rows that will really be produced: the caller's estimate of the device-side count when there is one
+    const int64_t Mlive = (a.m_hint > 0 && (a.m_limit || a.m_limit2)) ? std::min<int64_t>(a.m_hint, a.M) : a.M;
+    const int64_t tiles = ceil_div(Mlive, 128 * o.cg) * ceil_div(a.N, o.bn);
     const int64_t rounds = ceil_div(tiles, sms / o.cg);
     const double per_kb = std::max(2.0 * o.bn, (16384.0 + 128.0 * o.bn / o.cg) / 44.0);
     double cost = (double)rounds * per_kb;

@@ -89,6 +89,9 @@ class Runtime:
         if self.precision == "fp32":
             self.gemm_backend, self.attn_backend = _lib.GEMM_SIMT, _lib.ATTN_SIMT
         self.store.ensure(device, self.precision)
+        # (valid text rows, valid vision rows) of a recent batch of this shape - see graphs.py; steers GEMM tile choices only
+        h = getattr(self.store, "row_hint", None)
+        self.row_hint = tuple(h[3:]) if (h is not None and tuple(h[:3]) == (B, T, V)) else None
 
     def empty(self, *shape, dtype=None):
         return torch.empty(shape, dtype=dtype or self.cdtype, device=self.device)
@@ -160,8 +163,12 @@ class Runtime:
                 k["k_limit"] = self.row_limit(a.shape[0])
             elif a.shape[0] == self.Mt + self.Mv:       # joint buffer: text segment, then vision segment
                 k.update(m_limit=self.pack.lim_t[0:1], m_limit2=self.pack.lim_v[0:1], limit_seg_M=self.Mt)
+                if self.row_hint:
+                    k["m_hint"] = _pad256(self.row_hint[0]) + _pad256(self.row_hint[1])
             else:
                 k["m_limit"] = self.row_limit(a.shape[0], padded=False)
+                if self.row_hint:
+                    k["m_hint"] = _pad256(self.row_hint[0] if a.shape[0] == self.Mt else self.row_hint[1])
         return ops.gemm(a, b, out, **k)
 
 

@@ -62,6 +62,12 @@ class GraphedPretrainStep:
         store = engine.model_store(model)
         store.ensure(self.device, model.precision)
         store.prepare_grads()           # grad32 must exist (and keep its address) before it is baked into the graph
+        # The packed plan schedules GEMM tiles up to device-side row counts, but the tile WIDTH is a launch-time choice
+        # that is baked into the graph: give the cost model the valid-row counts of this batch (one host read at capture
+        # time, never during replays) - later batches of the same shape have similar counts.
+        ht = int((mask_t != 0).sum()) if mask_t is not None else B * T
+        hv = int((mask_v != 0).sum()) if mask_v is not None else B * V
+        store.row_hint = (B, T, V, max(ht, 1), max(hv, 1))
         lib = _lib.load()
         pool = torch.cuda.graph_pool_handle()
         stream = torch.cuda.Stream(device=self.device)

@@ -49,7 +49,7 @@ def require_cuda(*ts):
 # --------------------------------------------------------------------------- GEMM
 def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bias=None, aux_in=None, aux_out=None,
          dropout_p=0.0, seed=0, offset=0, backend=_lib.GEMM_AUTO, split_k=0, M=None, N=None, K=None, b2=None, bias2=None,
-         split_M=0, m_limit=None, k_limit=None, m_limit2=None, limit_seg_M=0, out2=None, k_seg=0, k_limit2=None):
+         split_M=0, m_limit=None, k_limit=None, m_limit2=None, limit_seg_M=0, out2=None, k_seg=0, k_limit2=None, m_hint=0):
     """out[M,N] = epilogue(opA . opB^T); see vb_gemm in include/volta_b200.h.  m_limit / k_limit: int32 device tensors
     (one element) holding the number of rows / reduction elements that carry data (see vb_compact_plan)."""
     require_cuda(a, b, out)
@@ -89,6 +89,7 @@ def gemm(a, b, out, *, a_kmajor=True, b_kmajor=True, epilogue=_lib.EPI_NONE, bia
             assert lim.dtype == torch.int32 and lim.is_cuda and lim.numel() >= 1
             setattr(g, name, lim.data_ptr())
     g.limit_seg_M = int(limit_seg_M)
+    g.m_hint = int(m_hint)
     if out2 is not None:   # two reduction segments (weight gradients of two streams in one launch): [0, k_seg) -> out, [k_seg, K) -> out2
         assert epilogue == _lib.EPI_ACCUM and 0 < k_seg < K and k_seg % 64 == 0
         assert out2.dtype == out.dtype and out2.shape == out.shape and out2.stride() == out.stride()
