@@ -321,6 +321,8 @@ int vb_loss_finalize(const float* loss_sum, const float* count, float* out, int3
 #define VB_ELT_SCALE 7     /* out = a * alpha                                            */
 #define VB_ELT_DROPOUT 8   /* out = a * mask / (1-p)      (counter hash, index = element) */
 #define VB_ELT_AXPY 9      /* out = out + alpha * a                                      */
+#define VB_ELT_SWISH 10    /* out = a * sigmoid(a)        (ACT2FN["swish"], volta/encoders.py:153-157) */
+#define VB_ELT_DSWISH 11   /* out = swish'(a)             (saved next to the activation, multiplied in by the backward GEMM) */
 /* 2-D strided element-wise op over [rows, cols]; a/b/out may have different dtypes. */
 int vb_eltwise(int32_t op, const void* a, int32_t a_dtype, int64_t lda, const void* b, int32_t b_dtype,
                int64_t ldb, void* out, int32_t out_dtype, int64_t ldo, int64_t rows, int64_t cols,

@@ -435,6 +435,11 @@ def eltwise(op, a, out, b=None, alpha=1.0, p=0.0, seed=0, offset=0):
         r = _gelu(af)
     elif op == E.ELT_DGELU:
         r = af * _dgelu(bf)
+    elif op == E.ELT_SWISH:
+        r = af * torch.sigmoid(af)
+    elif op == E.ELT_DSWISH:
+        sg = torch.sigmoid(af)
+        r = sg * (1.0 + af * (1.0 - sg))
     elif op == E.ELT_SCALE:
         r = af * alpha
     elif op == E.ELT_DROPOUT:

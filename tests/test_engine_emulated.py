@@ -186,3 +186,27 @@ def test_task_heads_host_logic_matches_reference(name, monkeypatch):
         touched = [k for k, p in model.named_parameters() if p.grad is not None and float(p.grad.abs().sum()) > 0]
         assert any(k.startswith("bert.encoder.layer.0.") for k in touched), (name, t)
         assert any(k.startswith("clfs_dict.%s." % t) for k in touched), (name, t, [k for k in touched if "clfs" in k])
+
+
+@pytest.mark.parametrize("act", ["swish", "relu"])
+def test_other_activations_match_oracle(act, monkeypatch):
+    """hidden_act / v_hidden_act in {relu, swish} (ACT2FN, volta/encoders.py:157; no shipped config uses them): losses and
+    every parameter gradient against the oracle, which applies the same table."""
+    emu_ops.install(monkeypatch)
+    g, cfg, b = load_case("mini_ctrl_vilbert")
+    cfg.hidden_act = cfg.v_hidden_act = act
+    model = volta_b200.BertForVLPreTraining(cfg)
+    state = seeded_state_dict(model.state_dict(), seed=0)
+    model.load_state_dict(state)
+    model.set_precision("fp32").eval()
+    losses = model(b["input_ids"], b["image_feat"], b["image_loc"], b["segment_ids"], b["input_mask"], b["image_mask"],
+                   b["lm_label_ids"], b["image_label"], b["image_cls"], None, None, None, None, None, b["is_match"])
+    (losses[0] + losses[1] + losses[2]).sum().backward()
+    P = O.params_from_state_dict(state, requires_grad=True)
+    ref = O.fwd_bwd(P, cfg, b)
+    for mine, r in zip(losses, ref):
+        assert abs(float(mine) - r) < 2e-4 * max(1.0, abs(r)), (act, float(mine), r)
+    for key, p in model.named_parameters():
+        rg = P[key].grad if P[key].grad is not None else torch.zeros_like(P[key])
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        assert float((got - rg).norm()) / max(float(rg.norm()), 1e-6) < 2e-3, (act, key)

@@ -750,7 +750,7 @@ def test_region_criteria(dtype, kind, C_, skip, with_conf):
 
 def test_eltwise_colsum_gather():
     a, b = rnd(300, 1024), rnd(300, 1024, seed=1)
-    for op in (_lib.ELT_ADD, _lib.ELT_MUL, _lib.ELT_RELU, _lib.ELT_DRELU, _lib.ELT_GELU, _lib.ELT_DGELU):
+    for op in (_lib.ELT_ADD, _lib.ELT_MUL, _lib.ELT_RELU, _lib.ELT_DRELU, _lib.ELT_GELU, _lib.ELT_DGELU, _lib.ELT_SWISH, _lib.ELT_DSWISH):
         o, r = torch.empty_like(a), torch.empty_like(a)
         ops.eltwise(op, a, o, b=b)
         emu_ops.eltwise(op, a, r, b=b)

@@ -16,7 +16,8 @@ REGION_XENT, REGION_MSE, REGION_HUBER = 0, 1, 2
 ATTN_AUTO, ATTN_MMA, ATTN_SIMT, ATTN_TC = 0, 1, 2, 3
 (EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_RELU, EPI_BIAS_DROP_RES, EPI_MUL, EPI_ADD, EPI_DRELU, EPI_ACCUM,
  EPI_BIAS_ADD) = range(10)
-(ELT_COPY, ELT_ADD, ELT_MUL, ELT_RELU, ELT_DRELU, ELT_GELU, ELT_DGELU, ELT_SCALE, ELT_DROPOUT, ELT_AXPY) = range(10)
+(ELT_COPY, ELT_ADD, ELT_MUL, ELT_RELU, ELT_DRELU, ELT_GELU, ELT_DGELU, ELT_SCALE, ELT_DROPOUT, ELT_AXPY, ELT_SWISH,
+ ELT_DSWISH) = range(12)
 
 _vp, _i32, _i64, _u64, _f = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
 

@@ -26,6 +26,8 @@ __device__ __forceinline__ float apply(int op, float a, float b, float o, float 
     case VB_ELT_SCALE: return a * alpha;
     case VB_ELT_DROPOUT: return keep ? a * scale : 0.f;
     case VB_ELT_AXPY: return o + alpha * a;
+    case VB_ELT_SWISH: return a / (1.f + __expf(-a));                               // x * sigmoid(x), volta/encoders.py:153-154
+    case VB_ELT_DSWISH: { const float sg = 1.f / (1.f + __expf(-a)); return sg * (1.f + a * (1.f - sg)); }   // d/dx of the above
     default: return a;
   }
 }
@@ -225,7 +227,7 @@ extern "C" {
 int vb_eltwise(int32_t op, const void* a, int32_t a_dtype, int64_t lda, const void* b, int32_t b_dtype, int64_t ldb,
                void* out, int32_t out_dtype, int64_t ldo, int64_t rows, int64_t cols, float alpha, float p, uint64_t seed,
                uint64_t offset, void* stream) {
-  VB_REQUIRE(op >= VB_ELT_COPY && op <= VB_ELT_AXPY, VB_ERR_ARG, "eltwise: bad op %d", op);
+  VB_REQUIRE(op >= VB_ELT_COPY && op <= VB_ELT_DSWISH, VB_ERR_ARG, "eltwise: bad op %d", op);
   VB_REQUIRE(a && out, VB_ERR_ARG, "eltwise: null pointer");
   const bool needs_b = (op == VB_ELT_ADD || op == VB_ELT_MUL || op == VB_ELT_DRELU || op == VB_ELT_DGELU);
   VB_REQUIRE(!needs_b || b, VB_ERR_ARG, "eltwise: op %d needs a second operand", op);

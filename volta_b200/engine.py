@@ -537,21 +537,35 @@ def _act_epilogues(name):
         return EPI_BIAS_GELU, EPI_MUL  # the forward epilogue saves gelu'(x); the backward epilogue multiplies by it
     if name == "relu":
         return EPI_BIAS_RELU, EPI_DRELU
-    raise NotImplementedError("hidden_act=%r: the shipped configs use 'gelu'; 'relu' is supported, 'swish' is not" % (name,))
+    if name == "swish":
+        # no shipped config uses it (ACT2FN, volta/encoders.py:157): the Linear runs with the plain bias epilogue and two
+        # element-wise passes form x*sigmoid(x) and its derivative; the backward multiplies the derivative in like GELU's
+        return "swish", EPI_MUL
+    raise ValueError("hidden_act=%r is not one of gelu / relu / swish (volta/encoders.py:157)" % (name,))
+
+
+def _act_linear_fwd(rt, x, lin, act, h, pre, **kw):
+    """h = act(x W^T + b); pre = what the backward epilogue needs (the derivative for gelu / swish; h itself for relu)."""
+    epi_f, _ = _act_epilogues(act)
+    if epi_f == EPI_BIAS_GELU:
+        linear_fwd(rt, x, lin, epilogue=EPI_BIAS_GELU, out=h, aux_out=pre, **kw)
+        return pre
+    if epi_f == "swish":
+        linear_fwd(rt, x, lin, epilogue=EPI_BIAS, out=pre, **kw)      # pre-activation, then activation / derivative in place
+        ops.eltwise(_lib.ELT_SWISH, pre, h)
+        ops.eltwise(_lib.ELT_DSWISH, pre, pre)
+        _count(2)
+        return pre
+    linear_fwd(rt, x, lin, epilogue=EPI_BIAS_RELU, out=h, **kw)
+    return h  # relu'(pre) = (h > 0)
 
 
 def _ffn_stream_fwd(rt, x, inter, dense2, ln, p, y, act, second=None, st=None):
     """second = (inter_v, dense2_v, ln_v): both streams in row-split launches over the joint buffer."""
-    epi_f, _ = _act_epilogues(act)
     I = inter.weight.shape[0]
     h = rt.empty(x.shape[0], I)
     sp = dict(lin2=second[0], split=rt.Mt) if second else {}
-    if epi_f == EPI_BIAS_GELU:
-        pre = rt.empty(x.shape[0], I)
-        linear_fwd(rt, x, inter, epilogue=EPI_BIAS_GELU, out=h, aux_out=pre, **sp)
-    else:
-        linear_fwd(rt, x, inter, epilogue=EPI_BIAS_RELU, out=h, **sp)
-        pre = h  # relu'(pre) = (h > 0)
+    pre = _act_linear_fwd(rt, x, inter, act, h, rt.empty(x.shape[0], I) if act != "relu" else None, **sp)
     if second:
         return (x, pre, out_block_fwd2(rt, h, x, dense2, ln, second[1], second[2], p, y))
     return (x, pre, out_block_fwd(rt, h, x, dense2, ln, p, y, st=st))
@@ -1053,15 +1067,10 @@ def _lim_seqs(lim, rows):
 
 def _transform_fwd(rt, tr, x, has_ln=True, lim=None):
     """lim: int32 [count, padded count] on the device - only the first `count` rows of x hold data."""
-    epi_f, _ = _act_epilogues(tr.hidden_act)
     H = tr.dense.weight.shape[0]
-    h, pre = rt.empty(x.shape[0], H), rt.empty(x.shape[0], H)
+    h = rt.empty(x.shape[0], H)
     ml = dict(m_limit=lim[0:1]) if lim is not None else {}
-    if epi_f == EPI_BIAS_GELU:
-        linear_fwd(rt, x, tr.dense, epilogue=EPI_BIAS_GELU, out=h, aux_out=pre, **ml)
-    else:
-        linear_fwd(rt, x, tr.dense, epilogue=EPI_BIAS_RELU, out=h, **ml)
-        pre = h
+    pre = _act_linear_fwd(rt, x, tr.dense, tr.hidden_act, h, rt.empty(x.shape[0], H) if tr.hidden_act != "relu" else None, **ml)
     if not has_ln:
         return h, (x, pre, h, None)
     y, stats = ln_fwd(rt, h, tr.LayerNorm, seqs=_lim_seqs(lim, x.shape[0]))
