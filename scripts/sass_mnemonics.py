@@ -1,6 +1,6 @@
 """Static SASS evidence for every kernel of libvolta_b200.so: per kernel (demangled), the count of the mnemonics that
 tell which hardware path it uses - tcgen05 MMA (UTCHMMA), TMA loads / stores (UTMALDG / UTMASTG), TMEM reads (LDTM),
-warp-level tensor cores (HMMA), cp.async (LDGSTS), ldmatrix (LDSM), 16-byte global accesses, reductions, shuffles.
+warp-level tensor cores (HMMA), NVSwitch multimem loads (LDGMC), cp.async (LDGSTS), ldmatrix (LDSM), 16-byte global accesses, reductions, shuffles.
 
     python scripts/sass_mnemonics.py > profiles/r02_sass_mnemonics.txt
 """
@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BUILD = os.path.join(ROOT, "volta_b200", "csrc", "_build")
-KEYS = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "LDTM", "UTCATOMSWS", "HMMA", "LDSM", "LDGSTS", "LDG.E.128", "STG.E.128",
+KEYS = ["UTCHMMA", "UTCBAR", "UTMALDG", "UTMASTG", "LDTM", "UTCATOMSWS", "LDGMC", "HMMA", "LDSM", "LDGSTS", "LDG.E.128", "STG.E.128",
         "LDS.128", "STS.128", "RED", "ATOM", "SHFL", "MUFU", "SYNCS", "BAR"]
 
 

@@ -110,9 +110,9 @@ def test_gradients_match_oracle_per_parameter(name, precision):
             worst = max(worst, (rel_err, key))
         if err > ptol * max(float(ref.norm()), 2e-3 * total_ref):
             bad.append((key, err, float(ref.norm())))
-    print("GRADTOL %s %s worst %.4f (%s) pooler %.4f (%s)" % (name, precision, worst[0], worst[1], worst_pool[0], worst_pool[1]))
         if name.startswith("mini") and precision == "fp32":
             assert abs(float(got.double().norm()) - g["grad_norm"][key]) <= 5e-3 * max(g["grad_norm"][key], 2e-3 * total_ref)
+    print("GRADTOL %s %s worst %.4f (%s) pooler %.4f (%s)" % (name, precision, worst[0], worst[1], worst_pool[0], worst_pool[1]))
     assert not bad, (name, precision, bad[:8], len(bad))
 
 
