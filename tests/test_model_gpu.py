@@ -94,7 +94,11 @@ def test_gradients_match_oracle_per_parameter(name, precision):
     # bf16: rounding noise accumulates over 24-36 sub-layers of backward (the reference's own bf16 run drifts
     # 1.6 % forward); ReLU-gated pooler weights additionally flip units whose pre-activation is
     # within bf16 resolution of zero, so they get a looser bound.  The fp32 mode pins the arithmetic at 2e-3.
-    tol = 2e-3 if precision == "fp32" else 1e-1
+    # Observed on the B200 (round 2, GRADTOL lines of this test), bf16, worst non-pooler tensor: full-width model 0.042;
+    # the H = 128 / batch 2-3 mini models 0.016-0.095 (uniter's region projection: a 2-sample batch) - the full-width
+    # default plan is pinned tighter, at 6e-2 per tensor and 4e-2 for the whole gradient, in test_default_plan_gpu.py.
+    # Pooler weights: 0.07-0.42 (mini_lxmert t_pooler).
+    tol = 2e-3 if precision == "fp32" else (6e-2 if name.startswith("full") else 1e-1)
     total_ref = sum(float(v.grad.norm()) ** 2 for v in {id(v): v for v in P.values()}.values() if v.grad is not None) ** 0.5
     bad, worst, worst_pool = [], (0.0, None), (0.0, None)
     for key, p in model.named_parameters():
