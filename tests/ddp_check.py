@@ -36,6 +36,7 @@ def main():
     B, T, V = int(os.environ.get("DDP_CHECK_BATCH", "64")), 36, 37
     name = os.environ.get("DDP_CHECK_MODEL", "ctrl_vilbert_base")
     wire = torch.bfloat16 if os.environ.get("DDP_CHECK_WIRE") == "bf16" else None
+    precision = os.environ.get("DDP_CHECK_PRECISION", "bf16")   # "fp32": the validation-mode kernels - a run is reproducible to ~1e-6
     cfg = named_config(name, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, v_hidden_dropout_prob=0.0,
                        v_attention_probs_dropout_prob=0.0)
 
@@ -44,7 +45,7 @@ def main():
             m = volta_b200.BertForVLPreTraining(cfg)
         m.load_state_dict(seeded_state_dict(m.state_dict(), seed=seed))
         m.cls.dropout.p = 0.0
-        return m.train().to(dev)
+        return m.set_precision(precision).train().to(dev)
 
     twin = build(0)
     twin._use_cuda_graphs = False
@@ -65,8 +66,16 @@ def main():
         return engine.model_store(m).grad32.clone(), [float(x) for x in l]
 
     from volta_b200 import engine
-    worst_all, replays, buckets = 0.0, 0, 0
-    tol = 2e-2 if wire is not None else 1e-2   # two runs of the same step differ by ~1e-3: fp32 atomics reorder sums that are then rounded to bf16
+    worst_all, whole_all, replays, buckets = 0.0, 0.0, 0, 0
+    # bf16 kernels: two runs of the SAME step differ (fp32 atomics reorder sums that are then rounded to bf16, and the
+    # softmax backward amplifies that in the small key / query weight gradients: 0.004-0.014 observed per tensor), so the
+    # per-tensor bound is 5e-2 with the denominator floored at 1 % of the whole gradient and the whole gradient is held
+    # to 1e-2; a bucket reduced too early or twice is an O(1) error in every tensor of the bucket.  fp32 validation mode:
+    # reproducible to ~1e-6, held to 1e-4 - that run is the sharp race detector.
+    if precision == "fp32":
+        tol, floor, whole_tol = 1e-4, 1e-3, 1e-5
+    else:
+        tol, floor, whole_tol = (5e-2, 1e-2, 2e-2) if wire is not None else (5e-2, 1e-2, 1e-2)
     for it in range(iters):
         got, _ = grads_of(model, ddp, 1000 + 10 * it + rank)
         expect = None
@@ -80,7 +89,7 @@ def main():
         for key, p in model.named_parameters():
             off, n = store.offsets[id(p)]
             a, e = got[off:off + n], expect[off:off + n]
-            err = float((a - e).norm()) / max(float(e.norm()), 1e-3 * total)
+            err = float((a - e).norm()) / max(float(e.norm()), floor * total)
             if err > worst:
                 worst, worst_key = err, (key, off, n, float(e.norm()), float((a - e).abs().max()), int(((a - e).abs() > 1e-3 * e.abs().max()).sum()))
         # every rank must hold bit-identical gradients after the all-reduce
@@ -89,7 +98,9 @@ def main():
         dist.all_gather(both, mine)
         assert all(float(b) == float(both[0]) for b in both), ("ranks disagree after the all-reduce", it, [float(b) for b in both])
         assert worst < tol, ("gradient != mean of the single-rank gradients", it, worst, worst_key)
-        worst_all = max(worst_all, worst)
+        whole = float((got - expect).norm()) / total
+        assert whole < whole_tol, ("whole gradient != mean of the single-rank gradients", it, whole)
+        worst_all, whole_all = max(worst_all, worst), max(whole_all, whole)
         buckets = ddp.last_num_buckets
     steps = [s for s in model._graph_steps.values() if not isinstance(s, str)]
     replays = steps[0].replays if steps else 0
@@ -98,8 +109,8 @@ def main():
     if rank == 0:
         print(json.dumps({"ddp_check": "ok", "world": world, "model": name, "per_rank_batch": B, "iterations": iters,
                           "wire": "bf16" if wire is not None else "fp32",
-                          "allreduce": ("vb_allreduce_f32 over " + ddp._reducer.kind) if ddp._reducer is not None else "nccl", "worst_rel_l2_vs_mean_of_single_rank": worst_all,
-                          "tolerance": tol, "buckets_per_step": buckets, "graph_replays": replays, "backward_segments": segs}), flush=True)
+                          "allreduce": ("vb_allreduce_f32 over " + ddp._reducer.kind) if ddp._reducer is not None else "nccl", "precision": precision, "worst_rel_l2_vs_mean_of_single_rank": worst_all,
+                          "tolerance": tol, "whole_gradient_rel_l2": whole_all, "whole_tolerance": whole_tol, "buckets_per_step": buckets, "graph_replays": replays, "backward_segments": segs}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

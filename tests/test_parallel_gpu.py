@@ -38,8 +38,8 @@ def test_bucketer_wire_formats_on_one_rank_nccl():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("wire", ["fp32", "bf16"])
-def test_ddp_gradients_equal_mean_of_single_rank_gradients(wire):
+@pytest.mark.parametrize("wire,precision", [("fp32", "bf16"), ("bf16", "bf16"), ("fp32", "fp32")])
+def test_ddp_gradients_equal_mean_of_single_rank_gradients(wire, precision):
     """>= 2 real ranks over NCCL (self-skips on a one-GPU box): tests/ddp_check.py under torchrun - 10 iterations of the
     graph-replayed, bucket-overlapped backward; every parameter gradient equals the mean of the single-rank gradients
     (apex/tests/distributed/DDP/ddp_race_condition_test.py:29-69 is the pattern)."""
@@ -53,7 +53,9 @@ def test_ddp_gradients_equal_mean_of_single_rank_gradients(wire):
     port = s.getsockname()[1]
     s.close()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, DDP_CHECK_WIRE=wire)
+    env = dict(os.environ, DDP_CHECK_WIRE=wire, DDP_CHECK_PRECISION=precision)
+    if precision == "fp32":    # SIMT validation kernels: a smaller batch and fewer iterations keep the run short
+        env.update(DDP_CHECK_BATCH="8", DDP_CHECK_ITERS="5")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
