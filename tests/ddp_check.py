@@ -75,7 +75,7 @@ def main():
     if precision == "fp32":
         tol, floor, whole_tol = 1e-4, 1e-3, 1e-5
     else:
-        tol, floor, whole_tol = (5e-2, 1e-2, 2e-2) if wire is not None else (5e-2, 1e-2, 1e-2)
+        tol, floor, whole_tol = (5e-2, 1e-2, 3e-2) if wire is not None else (5e-2, 1e-2, 2e-2)   # observed whole: 0.004 (2 ranks) - 0.008 (8 ranks)
     for it in range(iters):
         got, _ = grads_of(model, ddp, 1000 + 10 * it + rank)
         expect = None
