@@ -238,6 +238,10 @@ typedef struct vb_attn_args {
 } vb_attn_args;
 
 int vb_attention_fwd(const vb_attn_args* args, void* stream);
+/* Attention probabilities for inspection (config.visualization + output_all_attention_masks, volta/encoders.py:342-356):
+ * probs_t fp32 [B, heads, Lt, Lt+Lv], probs_v fp32 [B, heads, Lv, Lt+Lv] (text keys first; zero columns for a key stream
+ * the row does not attend), joint softmax, no dropout; ctx / lse of args are ignored.  Padded layout only. */
+int vb_attention_probs(const vb_attn_args* args, float* probs_t, float* probs_v, void* stream);
 int vb_attention_bwd(const vb_attn_args* args, void* stream);
 /* len[b] = 1 + index of the last position with mask[b, j] != 0, or 0 if the sample has none. */
 int vb_mask_lengths(const int32_t* mask, int32_t B, int32_t L, int32_t* len, void* stream);

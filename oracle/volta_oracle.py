@@ -233,11 +233,17 @@ def attention_sublayer(P, cfg, n, xt, xv, mt, mv, train=False, taps=None):
         return out.transpose(1, 2).reshape(B, L, h * d), pr
 
     ot, ov = xt, xv
+    if taps is not None:     # a stream the sub-layer does not touch: every slot None (encoders.py:343-354)
+        taps["attn_t.%d" % n], taps["attn_v.%d" % n] = (dict(intra_attn=None, inter_attn=None, queries=None, keys=None) for _ in range(2))
     if text:
         segs = ([(kt, vt_, mt)] if has["tt"] else []) + ([(kv, vv_, mv)] if has["tv"] else [])
         ctx, pr = attend(qt, segs, cfg.attention_probs_dropout_prob)
         if taps is not None:
             taps["ctx_t.%d" % n] = ctx
+            # what BertGatedSelfAttention returns with config.visualization (encoders.py:342-348): intra = own-modality block
+            nt = kt.shape[2] if has["tt"] else 0
+            taps["attn_t.%d" % n] = {"intra_attn": pr[..., :nt] if has["tt"] else None, "inter_attn": pr[..., nt:] if has["tv"] else None,
+                                     "queries": qt, "keys": kt}
         d = _drop(linear(ctx, P, pre + "attention_output.dense"), cfg.hidden_dropout_prob, train)
         ot = layer_norm(d + xt, P[pre + "attention_output.LayerNorm.weight"], P[pre + "attention_output.LayerNorm.bias"])
     if vision:
@@ -245,6 +251,9 @@ def attention_sublayer(P, cfg, n, xt, xv, mt, mv, train=False, taps=None):
         ctx, pr = attend(qv, segs, cfg.v_attention_probs_dropout_prob)
         if taps is not None:
             taps["ctx_v.%d" % n] = ctx
+            nt = kt.shape[2] if has["vt"] else 0       # vision rows: [vt | vv] (encoders.py:300-306, 349-354)
+            taps["attn_v.%d" % n] = {"intra_attn": pr[..., nt:] if has["vv"] else None, "inter_attn": pr[..., :nt] if has["vt"] else None,
+                                     "queries": qv, "keys": kv}
         d = _drop(linear(ctx, P, pre + "attention_output.v_dense"), cfg.v_hidden_dropout_prob, train)
         ov = layer_norm(d + xv, P[pre + "attention_output.v_LayerNorm.weight"], P[pre + "attention_output.v_LayerNorm.bias"])
     return ot, ov

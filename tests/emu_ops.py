@@ -254,6 +254,26 @@ def attention_fwd(qkv_t, qkv_v, mask_t, mask_v, ctx_t, ctx_v, lse_t, lse_v, B, L
         ldst.copy_(lse)
 
 
+def attention_probs(qkv_t, qkv_v, mask_t, mask_v, probs_t, probs_v, B, Lt, Lv, heads, d, pair_mask):
+    A, streams, madd = _attn_core(qkv_t, qkv_v, mask_t, mask_v, B, Lt, Lv, heads, d, pair_mask)
+    off = {0: 0, 1: Lt if qkv_t is not None else 0}
+    for qs, out in ((0, probs_t), (1, probs_v)):
+        if out is None or qs not in streams:
+            continue
+        segs = [ks for ks in streams if (pair_mask >> (qs * 2 + ks)) & 1]
+        out.zero_()
+        if not segs:
+            continue
+        q = streams[qs][0]
+        sc = torch.cat([q @ streams[ks][1].transpose(-1, -2) / math.sqrt(d) + madd[ks][:, None, None, :] for ks in segs], -1)
+        p = torch.softmax(sc, -1)
+        o = 0
+        for ks in segs:
+            n = streams[ks][1].shape[2]
+            out[..., off[ks]:off[ks] + n] = p[..., o:o + n]
+            o += n
+
+
 def mask_lengths(mask, out):
     idx = torch.arange(1, mask.shape[1] + 1, dtype=torch.int32)
     out.copy_(((mask != 0).to(torch.int32) * idx).max(1).values)
@@ -585,7 +605,7 @@ def adamw_flat(p, g, m, v, p16, chunk_group, group_hp, beta1, beta2, eps, sumsq_
 
 _NAMES = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "embed_gather_fwd",
           "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd", "region_loss_fwd", "region_loss_bwd",
-          "loss_finalize", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill",
+          "loss_finalize", "attention_probs", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill",
           "compact_plan", "compact_gather", "compact_scatter", "mask_lengths", "zero_rows", "sumsq", "adamw_flat"]
 
 

@@ -486,6 +486,35 @@ def test_attention_fwd_bwd(backend, B, Lt, Lv, heads, d, pm):
             assert rel(got.float(), ref.float()) < 2e-2
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,Lt,Lv,heads,d,pm", [(3, 36, 37, 12, 64, 1), (3, 36, 37, 12, 64, 8), (3, 36, 37, 12, 64, 6),
+                                                (3, 36, 37, 12, 64, 15), (2, 30, 101, 8, 128, 15), (5, 10, 7, 2, 64, 9)])
+def test_attention_probs(dtype, B, Lt, Lv, heads, d, pm):
+    """vb_attention_probs (the data of config.visualization): rows sum to 1 over the enabled key streams, masked keys
+    get 0, values match softmax(QK^T/sqrt(d) + mask) of the emulation."""
+    qt, qv, mt, mv, A = _attn_inputs(B, Lt, Lv, heads, d, pm, dtype)
+    wt, wv = (Lt if qt is not None else 0), (Lv if qv is not None else 0)
+    tq, vq = bool(pm & 3), bool(pm & 12)
+
+    def bufs():
+        return (torch.full((B, heads, Lt, wt + wv), 7.0, device=DEV) if tq else None,
+                torch.full((B, heads, Lv, wt + wv), 7.0, device=DEV) if vq else None)
+    args = (qt, qv, mt if qt is not None else None, mv if qv is not None else None)
+    pt, pv = bufs()
+    rt_, rv_ = bufs()
+    ops.attention_probs(*args, pt, pv, B, Lt, Lv, heads, d, pm)
+    emu_ops.attention_probs(*args, rt_, rv_, B, Lt, Lv, heads, d, pm)
+    for got, ref in ((pt, rt_), (pv, rv_)):
+        if got is None:
+            continue
+        assert torch.allclose(got, ref, atol=2e-6 if dtype == torch.float32 else 2e-3), float((got - ref).abs().max())
+        assert torch.allclose(got.sum(-1), torch.ones_like(got[..., 0]), atol=1e-5)
+        for off, m, on in ((0, mt, wt), (wt, mv, wv)):
+            if on:
+                dead = (m == 0)[:, None, None, :].expand(B, heads, got.shape[2], m.shape[1])
+                assert float(got[..., off:off + m.shape[1]][dead].abs().max() if dead.any() else 0.0) == 0.0
+
+
 @pytest.mark.parametrize("B,Lt,Lv,heads,d,pm", [(4, 36, 37, 12, 64, 1), (4, 36, 37, 12, 64, 9), (4, 36, 37, 12, 64, 6),
                                                 (4, 36, 37, 12, 64, 15), (4, 30, 101, 8, 128, 6), (4, 56, 80, 4, 64, 15)])
 @pytest.mark.parametrize("fwd_backend", ["mma", "tc"])

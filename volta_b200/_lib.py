@@ -64,6 +64,7 @@ SIGNATURES = {
     "vb_layernorm_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _f, _vp, _f, _u64, _u64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "vb_attention_fwd": (_i32, [C.POINTER(AttnArgs), _vp]),
     "vb_attention_bwd": (_i32, [C.POINTER(AttnArgs), _vp]),
+    "vb_attention_probs": (_i32, [C.POINTER(AttnArgs), _vp, _vp, _vp]),
     "vb_embed_gather_fwd": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), _i32, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
     "vb_embed_gather_bwd": (_i32, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i64), _i32, _vp, _i64, _i64, _i32, _i32, _vp]),
     "vb_colsum_by_key": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _i32, _vp, _vp]),

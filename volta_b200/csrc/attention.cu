@@ -795,6 +795,52 @@ mma_bwd_kernel(P p) {
 }
 
 
+// Attention probabilities on request (config.visualization + output_all_attention_masks, volta/encoders.py:342-356,
+// 873-875): the path never materialises P, so this separate kernel recomputes it for inspection - one warp per query row,
+// joint softmax over the enabled key streams, no dropout (the reference's visualisation is read in eval mode).
+// out[qs]: fp32 [B, heads, L[qs], L[0] + L[1]], text keys first; columns of a key stream the row does not attend are 0.
+template <typename T>
+__global__ void __launch_bounds__(128)
+simt_probs_kernel(P p, float* out_t, float* out_v) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qs = blockIdx.y;
+  float* out = qs ? out_v : out_t;
+  const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+  if (p.qkv[qs] == nullptr || out == nullptr) return;
+  const int Ltot = p.L[0] + p.L[1];
+  float* qbuf = sm + warp * (p.d + Ltot);
+  float* pbuf = qbuf + p.d;
+  const T* Q = reinterpret_cast<const T*>(p.qkv[qs]);
+  for (int i = warp; i < p.L[qs]; i += 4) {
+    const int64_t qrow = (int64_t)b * p.L[qs] + i;
+    for (int dd = lane; dd < p.d; dd += 32) qbuf[dd] = to_f<T>(Q[qrow * p.ld[qs] + h * p.d + dd]);
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int kg = lane; kg < Ltot; kg += 32) {
+      const int ks = kg < p.L[0] ? 0 : 1;
+      const int j = ks ? kg - p.L[0] : kg;
+      float s = -INFINITY;
+      if (pair_on(p.pair_mask, qs, ks) && p.qkv[ks] != nullptr) {
+        const T* K = reinterpret_cast<const T*>(p.qkv[ks]) + ((int64_t)b * p.L[ks] + j) * p.ld[ks] + p.A + h * p.d;
+        float acc = 0.f;
+        for (int dd = 0; dd < p.d; ++dd) acc = fmaf(qbuf[dd], to_f<T>(K[dd]), acc);
+        s = acc * p.scale + (p.mask[ks][(int64_t)b * p.L[ks] + j] ? 0.f : -10000.0f);
+      }
+      pbuf[kg] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    if (mx == -INFINITY) mx = 0.f;
+    float sum = 0.f;
+    for (int kg = lane; kg < Ltot; kg += 32) sum += __expf(pbuf[kg] - mx);
+    sum = warp_sum(sum);
+    float* orow = out + (((int64_t)b * p.heads + h) * p.L[qs] + i) * Ltot;
+    for (int kg = lane; kg < Ltot; kg += 32) orow[kg] = sum > 0.f ? __expf(pbuf[kg] - mx) / sum : 0.f;
+    __syncwarp();
+  }
+}
+
 // =====================================================================================
 // tcgen05 back-end (forward): S = Q K^T and O = P V on the 5th-generation tensor cores, accumulators in TMEM,
 // operands brought in by TMA.
@@ -1353,6 +1399,27 @@ int vb_mask_lengths(const int32_t* mask, int32_t B, int32_t L, int32_t* len, voi
 int vb_attention_fwd(const vb_attn_args* a, void* stream) {
   VB_REQUIRE(a != nullptr, VB_ERR_ARG, "attention_fwd: null args");
   return vb::attn::run(*a, (cudaStream_t)stream, false);
+}
+int vb_attention_probs(const vb_attn_args* a, float* probs_t, float* probs_v, void* stream) {
+  VB_REQUIRE(a != nullptr, VB_ERR_ARG, "attention_probs: null args");
+  VB_REQUIRE(a->cu_t == nullptr && a->cu_v == nullptr, VB_ERR_UNSUPPORTED, "attention_probs: padded layout only (no cu_*)");
+  vb_attn_args b = *a;
+  float dummy = 0.f;          // fill() insists on ctx / lse for query streams: this entry point writes neither
+  if (!b.ctx_t) b.ctx_t = &dummy;
+  if (!b.ctx_v) b.ctx_v = &dummy;
+  if (!b.lse_t) b.lse_t = &dummy;
+  if (!b.lse_v) b.lse_v = &dummy;
+  vb::attn::P p;
+  int rc = vb::attn::fill(b, p, false);
+  if (rc) return rc;
+  VB_REQUIRE(a->d <= 256, VB_ERR_UNSUPPORTED, "attention_probs: head size %d > 256", a->d);
+  VB_REQUIRE((!(a->pair_mask & 3) || probs_t) && (!(a->pair_mask & 12) || probs_v), VB_ERR_ARG, "attention_probs: output missing for a query stream");
+  const int Ltot = p.L[0] + p.L[1];
+  const size_t smem = 4 * (size_t)(a->d + Ltot) * sizeof(float);
+  const dim3 grid((unsigned)(a->B * a->heads), 2);
+  if (a->dtype == VB_BF16) vb::attn::simt_probs_kernel<vb::bf16><<<grid, 128, smem, (cudaStream_t)stream>>>(p, probs_t, probs_v);
+  else vb::attn::simt_probs_kernel<float><<<grid, 128, smem, (cudaStream_t)stream>>>(p, probs_t, probs_v);
+  return vb::check_launch("attention simt_probs_kernel");
 }
 int vb_attention_bwd(const vb_attn_args* a, void* stream) {
   VB_REQUIRE(a != nullptr, VB_ERR_ARG, "attention_bwd: null args");

@@ -459,6 +459,8 @@ def attention_fwd(rt, layer, x, masks):
                           len_t=getattr(rt, "lens", (None, None))[0], len_v=getattr(rt, "lens", (None, None))[1], **_pack_cu(rt))
         _count()
     _zero_pad_rows(rt, ctx)
+    if getattr(rt, "attn_taps", None) is not None:
+        rt.attn_taps.append(_attention_data(rt, sa, qkv, masks) if sa.visualization else (None, None))
     y = Pair.alloc(rt, rt.Mt, x.t.shape[1], rt.Mv, x.v.shape[1]) if (sa.has_text and sa.has_vision) else None
     saved_out = {}
     if joint:
@@ -476,6 +478,49 @@ def attention_fwd(rt, layer, x, masks):
     saved = dict(x=x, qkv=qkv, ctx=ctx, lse=(lse_t, lse_v), calls=calls, seed=seed, p=(p_t, p_v), out=saved_out,
                  joint=joint, split=split, masks=masks, lens=getattr(rt, "lens", (None, None)))
     return y, saved
+
+
+def _attention_data(rt, sa, qkv, masks):
+    """(t_attn_data, v_attn_data) of BertGatedSelfAttention with config.visualization (volta/encoders.py:342-356): the
+    probabilities of the enabled (query stream, key stream) blocks after the joint softmax (eval semantics: no dropout),
+    queries and keys as [B, heads, L, d].  The fused kernels never materialise P; vb_attention_probs recomputes it."""
+    B, T, V = rt.B, rt.T, rt.V
+    Lt, Lv = (T if "t" in qkv else 0), (V if "v" in qkv else 0)
+    heads = sa.num_attention_heads if sa.has_text else sa.v_num_attention_heads
+    d = sa.attention_head_size if sa.has_text else sa.v_attention_head_size
+    same = (not (sa.has_text and sa.has_vision)) or (sa.num_attention_heads == sa.v_num_attention_heads and
+                                                      sa.attention_head_size == sa.v_attention_head_size)
+    out = {}
+    calls = [(sa.pair_mask, qkv.get("t"), qkv.get("v"), heads, d)] if same else \
+        [(1, qkv["t"], None, sa.num_attention_heads, sa.attention_head_size),
+         (8, None, qkv["v"], sa.v_num_attention_heads, sa.v_attention_head_size)]
+    for pm, qt, qv, h_, d_ in calls:
+        # a stream no enabled pair touches has no columns (vb_attention_probs: text uses tt|tv|vt, vision tv|vt|vv)
+        lt, lv = (T if (qt is not None and pm & 7) else 0), (V if (qv is not None and pm & 14) else 0)
+        pt = rt.empty(B, h_, T, lt + lv, dtype=torch.float32) if (qt is not None and pm & 3) else None
+        pv = rt.empty(B, h_, V, lt + lv, dtype=torch.float32) if (qv is not None and pm & 12) else None
+        ops.attention_probs(qt, qv, masks[0] if qt is not None else None, masks[1] if qv is not None else None, pt, pv,
+                            B, T, V, h_, d_, pm)
+        _count()
+        if pt is not None:
+            out["t"] = (pt, lt, h_, d_)
+        if pv is not None:
+            out["v"] = (pv, lt, h_, d_)
+
+    def heads_view(q, L, h_, d_, which):
+        A = h_ * d_
+        return q[:, which * A:(which + 1) * A].reshape(B, L, h_, d_).permute(0, 2, 1, 3)
+    # both dicts always exist; a stream the sub-layer does not touch has None in every slot (encoders.py:343-354)
+    t_data, v_data = (dict(intra_attn=None, inter_attn=None, queries=None, keys=None) for _ in range(2))
+    if sa.has_text:
+        pt, lt, h_, d_ = out["t"]
+        t_data = {"intra_attn": pt[..., :lt] if sa.has_tt else None, "inter_attn": pt[..., lt:] if sa.has_tv else None,
+                  "queries": heads_view(qkv["t"], T, h_, d_, 0), "keys": heads_view(qkv["t"], T, h_, d_, 1)}
+    if sa.has_vision:
+        pv, lt, h_, d_ = out["v"]
+        v_data = {"intra_attn": pv[..., lt:] if sa.has_vv else None, "inter_attn": pv[..., :lt] if sa.has_vt else None,
+                  "queries": heads_view(qkv["v"], V, h_, d_, 0), "keys": heads_view(qkv["v"], V, h_, d_, 1)}
+    return t_data, v_data
 
 
 def attention_bwd(rt, layer, dy, s):
@@ -970,8 +1015,9 @@ def _zero_pad_rows(rt, bufs):
             _count()
 
 
-def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
+def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False, want_attn=False):
     cfg = bert.config
+    rt.attn_taps = [] if want_attn else None
     x, s_emb = embeddings_fwd(rt, bert, ids, feat, loc, seg)
     masks = (_int_mask(rt, mask_t, rt.B, rt.T), _int_mask(rt, mask_v, rt.B, rt.V))
     rt.lens = (None, None)
@@ -980,7 +1026,7 @@ def bert_fwd(rt, bert, ids, feat, loc, seg, mask_t, mask_v, keep_layers=False):
         rt.lens = tuple(ops.mask_lengths(m, rt.empty(rt.B, dtype=torch.int32)) for m in masks)
         _count(2)
     rt.pack, rt.pack_on = None, False
-    if _pack_supported(rt, bert, keep_layers):
+    if _pack_supported(rt, bert, keep_layers or want_attn):     # attention data are [B, heads, L, L]: padded layout
         rt.pack = _make_pack(rt)
         _enter_packed(rt)
         x = _pack_pair(rt, x)
@@ -1483,9 +1529,6 @@ def pretraining_forward(model, input_ids, image_feat, image_loc, token_type_ids,
                         masked_lm_labels, image_label, image_cls, obj_labels, obj_confs, attr_labels, attr_confs,
                         image_attrs, next_sentence_label, output_all_attention_masks):
     _check_inputs(input_ids, image_feat, image_loc)
-    if output_all_attention_masks:
-        raise NotImplementedError("attention probabilities are never materialised on this path "
-                                  "(output_all_attention_masks / config.visualization)")
     args = (input_ids, image_feat, image_loc, token_type_ids, attention_mask, image_attention_mask, masked_lm_labels,
             image_label, image_cls, next_sentence_label, obj_labels, obj_confs, attr_labels, attr_confs)
     no_labels = masked_lm_labels is None and image_label is None and next_sentence_label is None
@@ -1495,11 +1538,14 @@ def pretraining_forward(model, input_ids, image_feat, image_loc, token_type_ids,
             rt = Runtime(model, input_ids.device, B, T, image_feat.shape[1], model.training)
             seg = torch.zeros_like(input_ids) if token_type_ids is None else token_type_ids
             x, pt, pv, _, _ = bert_fwd(rt, model.bert, input_ids.contiguous(), image_feat.contiguous(), image_loc,
-                                       seg.contiguous(), attention_mask, image_attention_mask)
+                                       seg.contiguous(), attention_mask, image_attention_mask,
+                                       want_attn=bool(output_all_attention_masks))
             _, (mlm, img, itm, pooled), _ = heads_fwd(rt, model, x, pt, pv, {})
         V_ = model.config.vocab_size
         img = {ix: v.view(B, -1, v.shape[-1])[..., :pre_vis_targets[ix]].float() for ix, v in img.items()}
-        return (mlm.view(B, T, -1)[..., :V_].float(), img, None if itm is None else itm.float(), None,
+        # the reference returns ([], []) when no attention data were requested (encoders.py:865-875, 1114)
+        attn = ([a for a, _ in rt.attn_taps], [b for _, b in rt.attn_taps]) if output_all_attention_masks else ([], [])
+        return (mlm.view(B, T, -1)[..., :V_].float(), img, None if itm is None else itm.float(), attn,
                 None if pooled is None else pooled.float())
     anchor = _anchor(model) if torch.is_grad_enabled() else None
     if anchor is None:
@@ -1516,13 +1562,15 @@ class _BertFn(torch.autograd.Function):
     """BertModel alone: differentiable w.r.t. parameters through (seq_t, seq_v, pooled_t, pooled_v)."""
 
     @staticmethod
-    def forward(ctx, anchor, model, args, keep_layers):
+    def forward(ctx, anchor, model, args, keep_layers, attn_holder=None):
         ids, feat, loc, seg, mask_t, mask_v = args
         B, T = ids.shape
         rt = Runtime(model, ids.device, B, T, feat.shape[1], model.training, grad=anchor is not None)
         seg = torch.zeros_like(ids) if seg is None else seg
         x, pt, pv, layers, s = bert_fwd(rt, model, ids.contiguous(), feat.contiguous(), loc, seg.contiguous(), mask_t, mask_v,
-                                        keep_layers=keep_layers)
+                                        keep_layers=keep_layers, want_attn=attn_holder is not None)
+        if attn_holder is not None:      # attention data for inspection: not differentiable, handed over on the side
+            attn_holder["taps"] = rt.attn_taps
         ctx.rt, ctx.model, ctx.s = rt, model, s
         ctx.n_layers = len(layers)
         outs = [x.t.view(B, T, -1), x.v.view(B, rt.V, -1)]
@@ -1556,18 +1604,19 @@ class _BertFn(torch.autograd.Function):
         bert_bwd(rt, model, s, dx, conv(g_pt, ctx.has_pool[0]), conv(g_pv, ctx.has_pool[1]))
         _notify_grads_ready(model)
         ctx.s = None
-        return None, None, None, None
+        return None, None, None, None, None
 
 
-def _run_bert(model, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, keep_layers):
+def _run_bert(model, input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask, keep_layers,
+              attn_holder=None):
     _check_inputs(input_txt, input_imgs, image_loc)
     args = (input_txt, input_imgs, image_loc, token_type_ids, attention_mask, image_attention_mask)
     anchor = _anchor(model) if torch.is_grad_enabled() else None
     if anchor is None:
         with torch.no_grad():
-            outs = _BertFn.apply(None, model, args, keep_layers)
+            outs = _BertFn.apply(None, model, args, keep_layers, attn_holder)
     else:
-        outs = _BertFn.apply(anchor, model, args, keep_layers)
+        outs = _BertFn.apply(anchor, model, args, keep_layers, attn_holder)
     cfg = model.config
     seq_t, seq_v = outs[0], outs[1]
     pt = outs[2] if cfg.fusion_method != "none" else None
@@ -1580,13 +1629,15 @@ def bert_model_forward(model, input_txt, input_imgs, image_loc, token_type_ids, 
                        output_all_encoded_layers, output_all_attention_masks):
     """BertModel.forward contract (reference: volta/encoders.py:954-1017).  Hidden states come back in the
     compute dtype (bf16 unless the fp32 validation mode is on)."""
-    if output_all_attention_masks:
-        raise NotImplementedError("attention probabilities are never materialised on this path")
+    holder = {} if output_all_attention_masks else None
     seq_t, seq_v, pt, pv, layers = _run_bert(model, input_txt, input_imgs, image_loc, token_type_ids, attention_mask,
-                                             image_attention_mask, output_all_encoded_layers)
+                                             image_attention_mask, output_all_encoded_layers, holder)
+    # per attention sub-layer: the (t_attn_data, v_attn_data) dicts of the reference when config.visualization is set,
+    # None otherwise (encoders.py:342-356, 873-875); ([], []) when not requested
+    attn = ([a for a, _ in holder["taps"]], [b for _, b in holder["taps"]]) if holder is not None else ([], [])
     if output_all_encoded_layers:
-        return list(layers[0::2]), list(layers[1::2]), pt, pv, ([], [])
-    return seq_t, seq_v, pt, pv, ([], [])
+        return list(layers[0::2]), list(layers[1::2]), pt, pv, attn
+    return seq_t, seq_v, pt, pv, attn
 
 
 # ====================================================================================================

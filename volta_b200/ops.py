@@ -227,6 +227,15 @@ def attention_fwd(*args, **kw):
     _lib.call("vb_attention_fwd", C.byref(a), _stream())
 
 
+def attention_probs(qkv_t, qkv_v, mask_t, mask_v, probs_t, probs_v, B, Lt, Lv, heads, d, pair_mask):
+    """vb_attention_probs: the probabilities the fused kernels never materialise, for inspection (visualization).
+    probs_t fp32 [B, heads, Lt, Lt+Lv] / probs_v fp32 [B, heads, Lv, Lt+Lv] (None for a stream without queries)."""
+    a = _attn_args(qkv_t, qkv_v, mask_t, mask_v, None, None, None, None, B, Lt, Lv, heads, d, pair_mask, 0.0, 0.0, 0, _lib.ATTN_SIMT)
+    for t in (probs_t, probs_v):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda)
+    _lib.call("vb_attention_probs", C.byref(a), _ptr(probs_t), _ptr(probs_v), _stream())
+
+
 def attention_bwd(*args, **kw):
     a = _attn_args(*args, **kw)
     _lib.call("vb_attention_bwd", C.byref(a), _stream())
