@@ -581,9 +581,10 @@ def sumsq(x, out):
     return out
 
 
-def adamw_flat(p, g, m, v, p16, chunk_group, group_hp, beta1, beta2, eps, sumsq_buf=None, max_norm=0.0):
-    """vb_adamw_flat as documented in include/volta_b200.h: chunk_group[i] = hyper-parameter group of elements
-    [64 i, 64 i + 64) (-1 = not optimised), group_hp[g] = (lr, weight_decay, step_size, active)."""
+def adamw_flat(p, g, m, v, p16, chunk_group, group_hp, beta1, beta2, eps, sumsq_buf=None, max_norm=0.0, rule="adamw"):
+    """vb_adamw_flat / vb_radam_flat as documented in include/volta_b200.h: chunk_group[i] = hyper-parameter group of
+    elements [64 i, 64 i + 64) (-1 = not optimised), group_hp[g] = (lr, weight_decay, step_size, active) for "adamw",
+    (wd * lr, rectified, step_size, active) for "radam"."""
     coef = 1.0
     if sumsq_buf is not None and max_norm > 0:
         coef = min(1.0, max_norm / (float(sumsq_buf.sqrt()) + 1e-6))
@@ -594,8 +595,12 @@ def adamw_flat(p, g, m, v, p16, chunk_group, group_hp, beta1, beta2, eps, sumsq_
     gg = g * coef
     m_new = beta1 * m + (1 - beta1) * gg
     v_new = beta2 * v + (1 - beta2) * gg * gg
-    x = p - hp[:, 2] * m_new / (v_new.sqrt() + eps)
-    x = torch.where(hp[:, 1] > 0, x - hp[:, 0] * hp[:, 1] * x, x)
+    if rule == "adamw":
+        x = p - hp[:, 2] * m_new / (v_new.sqrt() + eps)
+        x = torch.where(hp[:, 1] > 0, x - hp[:, 0] * hp[:, 1] * x, x)
+    else:
+        x = p - hp[:, 0] * p
+        x = torch.where(hp[:, 1] != 0, x - hp[:, 2] * m_new / (v_new.sqrt() + eps), x - hp[:, 2] * m_new)
     m.copy_(torch.where(live, m_new, m))
     v.copy_(torch.where(live, v_new, v))
     p.copy_(torch.where(live, x, p))

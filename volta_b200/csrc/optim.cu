@@ -36,6 +36,10 @@ sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
 }
 
 // group_hp[g] = {lr, weight_decay, step_size, active}; chunk_group[c] = group of elements [64c, 64c+64) or 0xFFFF (not optimised)
+// RULE 1 = RAdam as the reference ships it (volta/optimization.py:9-93, train_task.py:227-228): the moments as above, then
+//     p -= (wd lr) p ;   N_sma >= 5:  p -= step_size m / (sqrt(v) + eps)     else:  p -= step_size m
+// with group_hp[g] = {wd * lr, rectified (N_sma >= 5) ? 1 : 0, step_size, active}; the host forms N_sma and step_size.
+template <int RULE>
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ p16, int64_t n, const uint16_t* __restrict__ chunk_group, const float4* __restrict__ group_hp,
@@ -59,8 +63,14 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
       const float gg = gv[j] * coef;
       mv[j] = beta1 * mv[j] + (1.f - beta1) * gg;
       vv[j] = beta2 * vv[j] + (1.f - beta2) * gg * gg;
-      float x = pv[j] - hp.z * mv[j] / (sqrtf(vv[j]) + eps);
-      if (hp.y > 0.f) x -= hp.x * hp.y * x;
+      float x = pv[j];
+      if constexpr (RULE == 0) {
+        x -= hp.z * mv[j] / (sqrtf(vv[j]) + eps);
+        if (hp.y > 0.f) x -= hp.x * hp.y * x;
+      } else {
+        if (hp.x != 0.f) x -= hp.x * x;
+        x -= hp.y != 0.f ? hp.z * mv[j] / (sqrtf(vv[j]) + eps) : hp.z * mv[j];
+      }
       pv[j] = x;
     }
     Vec8<float>::store(p + e, pv);
@@ -83,18 +93,33 @@ int vb_sumsq(const float* x, int64_t n, float* out, void* stream) {
   return vb::check_launch("sumsq_kernel");
 }
 
-int vb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
-                  const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream) {
+static int adam_flat(int rule, float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
+                     const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream) {
   VB_REQUIRE(p && g && m && v && chunk_group && group_hp, VB_ERR_ARG, "adamw_flat: null pointer");
   VB_REQUIRE(n % vb::optim::CHUNK == 0, VB_ERR_ARG, "adamw_flat: n must be a multiple of 64 (flat store alignment)");
   VB_REQUIRE(vb::aligned16(p) && vb::aligned16(g) && vb::aligned16(m) && vb::aligned16(v) && vb::aligned16(group_hp) &&
                  (!p16 || vb::aligned16(p16)), VB_ERR_ARG, "adamw_flat: buffers must be 16-byte aligned");
   if (n == 0) return 0;
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(vb::ceil_div(n / 8, 256), 148 * 16));
-  vb::optim::adamw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (vb::bf16*)p16, n, chunk_group,
-                                                                   reinterpret_cast<const float4*>(group_hp), beta1, beta2, eps,
-                                                                   sumsq, max_norm);
+  if (rule == 0)
+    vb::optim::adamw_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (vb::bf16*)p16, n, chunk_group,
+                                                                        reinterpret_cast<const float4*>(group_hp), beta1, beta2,
+                                                                        eps, sumsq, max_norm);
+  else
+    vb::optim::adamw_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (vb::bf16*)p16, n, chunk_group,
+                                                                        reinterpret_cast<const float4*>(group_hp), beta1, beta2,
+                                                                        eps, sumsq, max_norm);
   return vb::check_launch("adamw_kernel");
+}
+
+int vb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
+                  const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream) {
+  return adam_flat(0, p, g, m, v, p16, n, chunk_group, group_hp, beta1, beta2, eps, sumsq, max_norm, stream);
+}
+
+int vb_radam_flat(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
+                  const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream) {
+  return adam_flat(1, p, g, m, v, p16, n, chunk_group, group_hp, beta1, beta2, eps, sumsq, max_norm, stream);
 }
 
 }  // extern "C"

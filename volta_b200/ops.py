@@ -433,10 +433,12 @@ def sumsq(x, out):
     return out
 
 
-def adamw_flat(p, g, m, v, p16, chunk_group, group_hp, beta1, beta2, eps, sumsq_buf=None, max_norm=0.0):
+def adamw_flat(p, g, m, v, p16, chunk_group, group_hp, beta1, beta2, eps, sumsq_buf=None, max_norm=0.0, rule="adamw"):
+    """rule "adamw": vb_adamw_flat, group_hp rows {lr, wd, step_size, active};  "radam": vb_radam_flat, rows
+    {wd * lr, rectified, step_size, active}."""
     assert p.dtype == g.dtype == m.dtype == v.dtype == torch.float32 and chunk_group.dtype == torch.int16
     assert group_hp.dtype == torch.float32 and group_hp.shape[-1] == 4 and chunk_group.numel() * 64 == p.numel()
-    _lib.call("vb_adamw_flat", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p16), p.numel(),
+    _lib.call({"adamw": "vb_adamw_flat", "radam": "vb_radam_flat"}[rule], p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _ptr(p16), p.numel(),
               chunk_group.data_ptr(), group_hp.data_ptr(), float(beta1), float(beta2), float(eps), _ptr(sumsq_buf),
               float(max_norm), _stream())
 

@@ -11,7 +11,9 @@ of group dicts, so `WarmupLinearSchedule` / any LR scheduler that edits `group["
 copy of the weights is written by the same kernel, so the next forward does not need the fp32 -> bf16 refresh pass.
 
 pytorch_transformers 1.1.0 is not installed (requirements.txt:39): its update rule is restated in
-csrc/optim.cu and pinned by tests against a plain PyTorch restatement of the same published algorithm.
+csrc/optim.cu and pinned by tests against a plain PyTorch restatement of the same published algorithm.  `FusedRAdam`
+is the optimizer the reference ships itself (volta/optimization.py:9-93) on the same buffers, pinned by trajectories of
+the unmodified class (tests/golden/make_golden_radam.py).
 """
 import torch
 
@@ -143,11 +145,7 @@ class FusedAdamW(torch.optim.Optimizer):
                 continue
             lay["steps"][gi] += 1
             t = lay["steps"][gi]
-            lr = float(group["lr"])
-            step_size = lr
-            if group.get("correct_bias", True):
-                step_size = lr * (1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t)
-            rows.append((lr, float(group["weight_decay"]), step_size, 1.0))
+            rows.append(self._group_row(group, t, beta1, beta2))
             for p, on in zip(group["params"], live):
                 if on:
                     self.state[p]["step"] = t
@@ -160,13 +158,65 @@ class FusedAdamW(torch.optim.Optimizer):
             ops.sumsq(store.grad32, sumsq)
         p16 = store.flat16 if store.precision == "bf16" else None
         ops.adamw_flat(store.flat32, store.grad32, lay["m"], lay["v"], p16, lay["active"], hp_dev, beta1, beta2, eps,
-                       sumsq, self.max_grad_norm)
+                       sumsq, self.max_grad_norm, rule=self._rule)
         engine._count(2 if sumsq is not None else 1)
         return loss
+
+    _rule = "adamw"
+
+    def _group_row(self, group, t, beta1, beta2):
+        """(lr, weight_decay, step_size, active) of vb_adamw_flat for a group at its step t."""
+        lr = float(group["lr"])
+        step_size = lr
+        if group.get("correct_bias", True):
+            step_size = lr * (1.0 - beta2 ** t) ** 0.5 / (1.0 - beta1 ** t)
+        return (lr, float(group["weight_decay"]), step_size, 1.0)
 
     def grad_norm(self):
         """Global gradient norm of the last clipped step (device tensor; reading it synchronises)."""
         return None if self._layout is None else self._layout["sumsq"].sqrt()
+
+
+class FusedRAdam(FusedAdamW):
+    """The reference's own `RAdam` (volta/optimization.py:9-93; `train_task.py --optim RAdam`, :227-228) over the flat
+    buffers: same constructor contract (`RAdam(optimizer_grouped_parameters, lr=base_lr)`, defaults betas (0.9, 0.999),
+    eps 1e-8, weight_decay 0), same `state_dict()` entries (`step`, `exp_avg`, `exp_avg_sq`), one `vb_radam_flat` launch.
+
+    The host forms what the reference forms per parameter: the length of the approximated SMA N_sma(t) and the step size
+    (:52-81), weight decay `p += -wd * lr * p` BEFORE the update (:83-84).  It also keeps the reference's ten-slot
+    `buffer` (:12, 52-81): a step size is computed once per step count `t` - with the learning rate of the FIRST group
+    that reaches `t` - and reused by every later group at the same `t`, whatever its own learning rate (groups with
+    different learning rates therefore share the first one's step size; their weight decay uses their own).  That is
+    the reference's behaviour and the golden vectors (tests/golden/make_golden_radam.py, made by running the unmodified
+    class) contain it."""
+
+    _rule = "radam"
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0, model=None, max_grad_norm=0.0):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, model=model,
+                         max_grad_norm=max_grad_norm)
+        for g in self.param_groups:
+            g.pop("correct_bias", None)         # the reference's defaults: lr, betas, eps, weight_decay
+        self.defaults.pop("correct_bias", None)
+        self.buffer = [[None, None, None] for _ in range(10)]
+
+    def _group_row(self, group, t, beta1, beta2):
+        buffered = self.buffer[int(t % 10)]
+        if t == buffered[0]:
+            n_sma, step_size = buffered[1], buffered[2]
+        else:
+            buffered[0] = t
+            beta2_t = beta2 ** t
+            n_sma_max = 2 / (1 - beta2) - 1
+            n_sma = n_sma_max - 2 * t * beta2_t / (1 - beta2_t)
+            buffered[1] = n_sma
+            if n_sma >= 5:
+                step_size = (group["lr"] * ((1 - beta2_t) * (n_sma - 4) / (n_sma_max - 4) * (n_sma - 2) / n_sma * n_sma_max /
+                                            (n_sma_max - 2)) ** 0.5 / (1 - beta1 ** t))
+            else:
+                step_size = group["lr"] / (1 - beta1 ** t)
+            buffered[2] = step_size
+        return (float(group["weight_decay"]) * float(group["lr"]), 1.0 if n_sma >= 5 else 0.0, float(step_size), 1.0)
 
 
 def clip_grad_norm_(model, max_norm):

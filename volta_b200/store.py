@@ -112,7 +112,10 @@ class ParamStore:
             for p in self.params:
                 off, n = self.offsets[id(p)]
                 p.data = flat[off:off + n].view(p.shape)
-                p.grad = None
+                # gradients that exist already (an optimizer step before the first forward, accumulation across a
+                # re-layout) stay: they are foreign tensors now and prepare_grads() adopts them into the new grad32
+                if p.grad is not None and p.grad.device != flat.device:
+                    p.grad = None
             self.flat32 = flat
             self.grad32 = None
             self.flat16 = None
