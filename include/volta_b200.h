@@ -388,16 +388,18 @@ int vb_batched_colsum(const void* a, int32_t dtype, int64_t batch, int64_t rows,
  *                 n fp32 parameters p with gradients g and moments m, v; also writes the bf16 operand copy p16 (or NULL).
  *                 chunk_group[i] = hyper-parameter group of elements [64 i, 64 i + 64), 0xFFFF = not optimised;
  *                 group_hp[g] = {lr, weight_decay, step_size = lr*sqrt(1-b2^t)/(1-b1^t), active != 0} (fp32 x 4).
- *                 sumsq != NULL and max_norm > 0: gradients are scaled by min(1, max_norm / (sqrt(*sumsq) + 1e-6)). */
+ *                 sumsq != NULL and max_norm > 0: gradients are scaled by min(1, max_norm / (sqrt(*sumsq) + 1e-6)).
+ *                 beta1 / beta2 are doubles: the kernel uses (float)beta and (float)(1.0 - beta), the two fp32 scalars the
+ *                 reference's Python expressions `mul_(beta)` / `add_(1 - beta, grad)` produce. */
 int vb_sumsq(const float* x, int64_t n, float* out, void* stream);
 int vb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
-                  const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream);
+                  const float* group_hp, double beta1, double beta2, float eps, const float* sumsq, float max_norm, void* stream);
 /* vb_radam_flat : the reference's own RAdam (volta/optimization.py:9-93; train_task.py:227-228 `--optim RAdam`), same
  *                 buffers and chunk table:  m, v as above;  p -= (wd lr) p;  then  p -= step_size m / (sqrt(v) + eps)  when the
  *                 variance is rectifiable (N_sma >= 5, :66-81)  or  p -= step_size m  (:83, 91).
  *                 group_hp[g] = {weight_decay * lr, N_sma >= 5 ? 1 : 0, step_size, active != 0}. */
 int vb_radam_flat(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
-                  const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream);
+                  const float* group_hp, double beta1, double beta2, float eps, const float* sumsq, float max_norm, void* stream);
 /* ---- input pipeline: region batch assembly on the device ------------------------------------
  * vb_region_batch replaces the per-batch numpy work of the reference's Conceptual-Captions loader between the detector
  * output and the model call: box area + normalisation (volta/datasets/concept_cap_dataset.py:450-461), zeroing of the

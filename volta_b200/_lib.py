@@ -92,8 +92,8 @@ SIGNATURES = {
     "vb_sumsq": (_i32, [_vp, _i64, _vp, _vp]),
     "vb_allreduce_f32": (_i32, [_vp, _u64, _vp, _i32, _i32, _i64, _i64, _f, _i32, _vp]),
     "vb_allreduce_pad_bytes": (_i32, []),
-    "vb_adamw_flat": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _f, _f, _f, _vp, _f, _vp]),
-    "vb_radam_flat": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _f, _f, _f, _vp, _f, _vp]),
+    "vb_adamw_flat": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, C.c_double, C.c_double, _f, _vp, _f, _vp]),
+    "vb_radam_flat": (_i32, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, C.c_double, C.c_double, _f, _vp, _f, _vp]),
     "vb_vlbert_prep": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _vp]),
     "vb_vlbert_index": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vb_batched_colsum": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp]),

@@ -43,7 +43,7 @@ template <int RULE>
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
              bf16* __restrict__ p16, int64_t n, const uint16_t* __restrict__ chunk_group, const float4* __restrict__ group_hp,
-             float beta1, float beta2, float eps, const float* __restrict__ sumsq, float max_norm) {
+             float beta1, float beta2, float omb1, float omb2, float eps, const float* __restrict__ sumsq, float max_norm) {
   float coef = 1.f;
   if (sumsq != nullptr && max_norm > 0.f) coef = fminf(1.f, max_norm / (sqrtf(*sumsq) + 1e-6f));  // clip_grad_norm_
   const int64_t n8 = n >> 3;
@@ -61,8 +61,8 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float gg = gv[j] * coef;
-      mv[j] = beta1 * mv[j] + (1.f - beta1) * gg;
-      vv[j] = beta2 * vv[j] + (1.f - beta2) * gg * gg;
+      mv[j] = beta1 * mv[j] + omb1 * gg;          // omb = 1 - beta formed in double on the host, as the reference's
+      vv[j] = beta2 * vv[j] + omb2 * gg * gg;     // Python scalars are (1.f - 0.999f is off by 5e-5 relative)
       float x = pv[j];
       if constexpr (RULE == 0) {
         x -= hp.z * mv[j] / (sqrtf(vv[j]) + eps);
@@ -94,7 +94,7 @@ int vb_sumsq(const float* x, int64_t n, float* out, void* stream) {
 }
 
 static int adam_flat(int rule, float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
-                     const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream) {
+                     const float* group_hp, double beta1, double beta2, float eps, const float* sumsq, float max_norm, void* stream) {
   VB_REQUIRE(p && g && m && v && chunk_group && group_hp, VB_ERR_ARG, "adamw_flat: null pointer");
   VB_REQUIRE(n % vb::optim::CHUNK == 0, VB_ERR_ARG, "adamw_flat: n must be a multiple of 64 (flat store alignment)");
   VB_REQUIRE(vb::aligned16(p) && vb::aligned16(g) && vb::aligned16(m) && vb::aligned16(v) && vb::aligned16(group_hp) &&
@@ -103,22 +103,24 @@ static int adam_flat(int rule, float* p, const float* g, float* m, float* v, voi
   const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(vb::ceil_div(n / 8, 256), 148 * 16));
   if (rule == 0)
     vb::optim::adamw_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (vb::bf16*)p16, n, chunk_group,
-                                                                        reinterpret_cast<const float4*>(group_hp), beta1, beta2,
-                                                                        eps, sumsq, max_norm);
+                                                                        reinterpret_cast<const float4*>(group_hp), (float)beta1,
+                                                                        (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), eps,
+                                                                        sumsq, max_norm);
   else
     vb::optim::adamw_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (vb::bf16*)p16, n, chunk_group,
-                                                                        reinterpret_cast<const float4*>(group_hp), beta1, beta2,
-                                                                        eps, sumsq, max_norm);
+                                                                        reinterpret_cast<const float4*>(group_hp), (float)beta1,
+                                                                        (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), eps,
+                                                                        sumsq, max_norm);
   return vb::check_launch("adamw_kernel");
 }
 
 int vb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
-                  const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream) {
+                  const float* group_hp, double beta1, double beta2, float eps, const float* sumsq, float max_norm, void* stream) {
   return adam_flat(0, p, g, m, v, p16, n, chunk_group, group_hp, beta1, beta2, eps, sumsq, max_norm, stream);
 }
 
 int vb_radam_flat(float* p, const float* g, float* m, float* v, void* p16, int64_t n, const uint16_t* chunk_group,
-                  const float* group_hp, float beta1, float beta2, float eps, const float* sumsq, float max_norm, void* stream) {
+                  const float* group_hp, double beta1, double beta2, float eps, const float* sumsq, float max_norm, void* stream) {
   return adam_flat(1, p, g, m, v, p16, n, chunk_group, group_hp, beta1, beta2, eps, sumsq, max_norm, stream);
 }
 

@@ -197,6 +197,10 @@ SKIP_PADDING = os.environ.get("VOLTA_B200_SKIP_PADDING", "1") != "0"
 SKIP_PADDING_LN = os.environ.get("VOLTA_B200_SKIP_PADDING_LN", "1") != "0"   # the residual-block LayerNorms skip them too
 # The weight gradients of the two streams of a sub-layer run as one launch with two reduction segments (linear_bwd)
 WGRAD_GROUP = os.environ.get("VOLTA_B200_WGRAD_GROUP", "1") != "0"
+# Weight-gradient GEMM on the side stream next to the input-gradient GEMM of the same Linear: -1 = auto (on below 2560
+# rows, where neither GEMM fills the machine: 5.53 -> 5.41 ms/step at 32 samples per GPU; off above: 12.32 -> 12.38 ms at
+# 256), 0 = never, 1 = issued before the dgrad, 2 = after it
+WGRAD_SIDE = int(os.environ.get("VOLTA_B200_WGRAD_SIDE", "-1"))
 PLAN_EMULATED = False   # tests/test_engine_emulated.py: take the tensor-core launch plan (row-split / grouped launches) under the CPU emulation of the C ABI
 # The memset of the flat gradient buffer runs on a side stream under the forward (store.prezero_grads)
 PREZERO_GRADS = os.environ.get("VOLTA_B200_PREZERO_GRADS", "1") != "0"
@@ -252,34 +256,47 @@ def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, 
     # the same Linear: the wgrad kernel leaves registers and shared memory for one small block per SM, and both read dy
     # from L2.  The side stream joins before this function returns (dy may be freed by the caller afterwards).
     side = None
-    if _lins(lin)[0].bias is not None and not bias_done and dy.shape[0] >= 1024 and _SIDE_STREAMS_ON and dy.is_cuda:
+    big = dy.shape[0] >= 1024 and _SIDE_STREAMS_ON and dy.is_cuda
+    if _lins(lin)[0].bias is not None and not bias_done and big:
         side = _side_stream(rt.device)
         side.wait_stream(torch.cuda.current_stream(rt.device))
         with torch.cuda.stream(side):
             for l_, x_, dy_ in parts:
                 ops.colsum(dy_, rt.g32(*[l.bias for l in _lins(l_)]), **(rl or dict(row_limit=rt.row_limit(dy_.shape[0]))))
                 _count()
+    # the weight-gradient GEMM on the side stream as well (WGRAD_SIDE): its CTAs and the input-gradient GEMM's fill each
+    # other's prologue / tail when neither fills the machine
+    wside = (WGRAD_SIDE if WGRAD_SIDE >= 0 else (2 if dy.shape[0] < 2560 else 0)) if (big and need_dx) else 0
+    if wside and side is None:
+        side = _side_stream(rt.device)
+        side.wait_stream(torch.cuda.current_stream(rt.device))
     # Both row ranges of a joint buffer in ONE weight-gradient launch (vb_gemm_args::k_seg / D2): the reduction over the
     # text rows accumulates into the first Linear's gradient, the reduction over the vision rows into the second's (the
     # same one for shared weights) - half the launches, and the slices of both fill the machine together.
     tc_ok = (rt.precision == "bf16" and rt.gemm_backend != _lib.GEMM_SIMT and dy.is_cuda) or PLAN_EMULATED
     grouped = (len(parts) == 2 and WGRAD_GROUP and lim is None and tc_ok and parts[0][2].shape[0] % 64 == 0 and
                all(l.weight.requires_grad for pt in parts for l in _lins(pt[0])))
-    if grouped:
-        seg = parts[0][2].shape[0]
-        kl = {}
-        if getattr(rt, "pack_on", False):
-            kl = dict(k_limit=rt.row_limit(seg), k_limit2=rt.row_limit(dy.shape[0] - seg))
-        _count()
-        ops.gemm(dy, x, rt.g32(*[l.weight for l in _lins(parts[0][0])]), out2=rt.g32(*[l.weight for l in _lins(parts[1][0])]),
-                 k_seg=seg, a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, backend=rt.gemm_backend, **kl)
-    for l_, x_, dy_ in parts:
-        lins = _lins(l_)
-        if not grouped and any(l.weight.requires_grad for l in lins):   # frozen Linears (fixed_layers / freeze_layers): no weight gradient
-            rt.gemm(dy_, x_, rt.g32(*[l.weight for l in lins]), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, **wl)
-        if lins[0].bias is not None and not bias_done and side is None:
-            ops.colsum(dy_, rt.g32(*[l.bias for l in lins]), **(rl or dict(row_limit=rt.row_limit(dy_.shape[0]))))
+    def weight_grads():
+        if grouped:
+            seg = parts[0][2].shape[0]
+            kl = {}
+            if getattr(rt, "pack_on", False):
+                kl = dict(k_limit=rt.row_limit(seg), k_limit2=rt.row_limit(dy.shape[0] - seg))
             _count()
+            ops.gemm(dy, x, rt.g32(*[l.weight for l in _lins(parts[0][0])]), out2=rt.g32(*[l.weight for l in _lins(parts[1][0])]),
+                     k_seg=seg, a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, backend=rt.gemm_backend, **kl)
+        for l_, x_, dy_ in parts:
+            lins = _lins(l_)
+            if not grouped and any(l.weight.requires_grad for l in lins):   # frozen Linears (fixed_layers / freeze_layers): no weight gradient
+                rt.gemm(dy_, x_, rt.g32(*[l.weight for l in lins]), a_kmajor=False, b_kmajor=False, epilogue=EPI_ACCUM, **wl)
+            if lins[0].bias is not None and not bias_done and side is None:
+                ops.colsum(dy_, rt.g32(*[l.bias for l in lins]), **(rl or dict(row_limit=rt.row_limit(dy_.shape[0]))))
+                _count()
+    if wside == 1:
+        with torch.cuda.stream(side):
+            weight_grads()
+    elif wside == 0:
+        weight_grads()
     if not need_dx:
         if side is not None:
             torch.cuda.current_stream(rt.device).wait_stream(side)
@@ -291,6 +308,9 @@ def linear_bwd(rt, x, dy, lin, need_dx=True, dx_epilogue=EPI_NONE, dx_out=None, 
     if lin2 is not None:
         kw.update(b2=rt.cw(*[l.weight for l in _lins(lin2)]), split_M=split)
     rt.gemm(dy, W, dx_out, a_kmajor=True, b_kmajor=False, epilogue=dx_epilogue, **kw)
+    if wside == 2:
+        with torch.cuda.stream(side):
+            weight_grads()
     if side is not None:
         torch.cuda.current_stream(rt.device).wait_stream(side)
     return dx_out
