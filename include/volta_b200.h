@@ -313,6 +313,21 @@ int vb_region_loss_bwd(int32_t kind, const void* logits, int64_t ld, int32_t per
                        int64_t rows, int32_t C, float weight, const float* lse, const float* count, const float* dloss,
                        void* dlogits, int32_t dtype, void* stream);
 int vb_loss_finalize(const float* loss_sum, const float* count, float* out, int32_t n, void* stream);
+/* ---- task criteria (volta/task_utils.py:24-27 LossMap, used at :103-137 and :237-282) -----------
+ * vb_bce_logits_fwd : nn.BCEWithLogitsLoss over logits [rows, C] (bf16 / fp32, row stride ld) and fp32 targets:
+ *                     row_loss[r] = sum_c max(x,0) - x t + log(1 + exp(-|x|));  *loss_out = scale * sum_r row_loss[r]
+ *                     (scale = 1 / (rows * C) is reduction="mean"; deterministic: no atomics).
+ * vb_bce_logits_bwd : dlogits = (sigmoid(x) - t) * (*dloss) * scale.
+ * vb_argmax_pick    : arg[r] = argmax_c logits[r, c] (first of equal maxima), pick[r] = labels[r, arg[r]] (labels NULL:
+ *                     the maximum itself) - `torch.max(logits, 1)` + the one-hot product of compute_score_with_logits
+ *                     (:429-434), `preds` / `select_idx` of the VL-logit / V-logit branches (:113-121).  arg or pick may be NULL.
+ * The CrossEntropyLoss entry of LossMap is vb_xent_fwd / vb_xent_bwd (negative labels ignored, mean over the rest). */
+int vb_bce_logits_fwd(const void* logits, int64_t ld, const float* target, int64_t ld_t, int64_t rows, int32_t C,
+                      float* row_loss, float scale, float* loss_out, int32_t dtype, void* stream);
+int vb_bce_logits_bwd(const void* logits, int64_t ld, const float* target, int64_t ld_t, int64_t rows, int32_t C,
+                      const float* dloss, float scale, void* dlogits, int64_t ld_d, int32_t dtype, void* stream);
+int vb_argmax_pick(const void* logits, int64_t ld, const float* labels, int64_t ld_l, int64_t rows, int32_t C, int64_t* arg,
+                   float* pick, int32_t dtype, void* stream);
 
 /* ---- element-wise / reductions (glue that the reference issues as ATen ops) */
 #define VB_ELT_COPY 0      /* out = a                     (also dtype conversion)       */

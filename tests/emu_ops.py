@@ -432,6 +432,30 @@ def region_loss_bwd(kind, logits, per, per_ld, skip, label, tgt_idx, conf, tgt_v
     dlogits[:, :C_] = full.to(dlogits.dtype)
 
 
+def bce_logits_fwd(logits, target, row_loss, scale, loss_out):
+    """vb_bce_logits_fwd as documented in include/volta_b200.h."""
+    x = logits.float()
+    l = x.clamp(min=0) - x * target + torch.log1p(torch.exp(-x.abs()))
+    row_loss[:x.shape[0]] = l.sum(1)
+    loss_out[0] = row_loss[:x.shape[0]].sum() * scale
+    return loss_out
+
+
+def bce_logits_bwd(logits, target, dloss, scale, dlogits):
+    dlogits.copy_(((torch.sigmoid(logits.float()) - target) * dloss * scale).to(dlogits.dtype))
+    return dlogits
+
+
+def argmax_pick(logits, labels=None, arg=None, pick=None):
+    x = logits.float()
+    a = x.argmax(1)          # first of equal maxima
+    if arg is not None:
+        arg.copy_(a)
+    if pick is not None:
+        pick.copy_((labels if labels is not None else x).gather(1, a[:, None])[:, 0])
+    return arg, pick
+
+
 def loss_finalize(loss_sum, count, out):
     out.copy_(loss_sum / count.clamp(min=1.0))
     return out
@@ -610,7 +634,7 @@ def adamw_flat(p, g, m, v, p16, chunk_group, group_hp, beta1, beta2, eps, sumsq_
 
 _NAMES = ["gemm", "layernorm_fwd", "layernorm_bwd", "attention_fwd", "attention_bwd", "embed_gather_fwd",
           "embed_gather_bwd", "box_project_fwd", "box_project_bwd", "xent_fwd", "xent_bwd", "kl_fwd", "kl_bwd", "region_loss_fwd", "region_loss_bwd",
-          "loss_finalize", "attention_probs", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill",
+          "loss_finalize", "bce_logits_fwd", "bce_logits_bwd", "argmax_pick", "attention_probs", "eltwise", "colsum", "colsum_by_key", "vlbert_prep", "vlbert_index", "batched_colsum", "gather_rows", "scatter_rows_add", "cast_bf16", "box_sincos", "fill",
           "compact_plan", "compact_gather", "compact_scatter", "mask_lengths", "zero_rows", "sumsq", "adamw_flat"]
 
 

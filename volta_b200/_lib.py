@@ -77,6 +77,9 @@ SIGNATURES = {
     "vb_region_loss_bwd": (_i32, [_i32, _vp, _i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64, _i64, _i32, _f, _vp, _vp, _vp, _vp, _i32, _vp]),
     "vb_kl_bwd": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i64, _i32, _f, _vp, _vp, _vp, _vp, _i32, _vp]),
     "vb_loss_finalize": (_i32, [_vp, _vp, _vp, _i32, _vp]),
+    "vb_bce_logits_fwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _f, _vp, _i32, _vp]),
+    "vb_bce_logits_bwd": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _f, _vp, _i64, _i32, _vp]),
+    "vb_argmax_pick": (_i32, [_vp, _i64, _vp, _i64, _i64, _i32, _vp, _vp, _i32, _vp]),
     "vb_eltwise": (_i32, [_i32, _vp, _i32, _i64, _vp, _i32, _i64, _vp, _i32, _i64, _i64, _i64, _f, _f, _u64, _u64, _vp]),
     "vb_colsum": (_i32, [_vp, _i32, _i64, _i64, _i64, _vp, _vp, _vp]),
     "vb_zero_rows": (_i32, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _i64, _i32, _i32, _vp]),

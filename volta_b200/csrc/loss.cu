@@ -241,6 +241,86 @@ region_bwd_kernel(int kind, const T* __restrict__ logits, int64_t ld, int per, i
   }
 }
 
+// ---- task criteria (volta/task_utils.py:24-27 LossMap; used at :103-137 and :237-282) -------------------------------
+// BCEWithLogitsLoss(reduction="mean") over a [rows, C] logit matrix with fp32 soft targets (VQA / GQA answer scores,
+// RefCOCO region scores):  l = max(x, 0) - x t + log(1 + exp(-|x|))  - the stable form PyTorch evaluates.
+// One block per row writes the row's partial sum; a single block adds the partial sums in a fixed order (deterministic,
+// no atomics) and scales:  loss = scale * sum  (scale = 1 / (rows C) for "mean").
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+bce_fwd_kernel(const T* __restrict__ logits, int64_t ld, const float* __restrict__ target, int64_t ld_t, int C,
+               float* __restrict__ row_loss) {
+  __shared__ float sh[THREADS / 32];
+  const int64_t r = blockIdx.x;
+  const T* x = logits + r * ld;
+  const float* t = target + r * ld_t;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < C; c += THREADS) {
+    const float v = to_f<T>(x[c]);
+    s += fmaxf(v, 0.f) - v * t[c] + log1pf(__expf(-fabsf(v)));
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) row_loss[r] = s;
+}
+__global__ void __launch_bounds__(THREADS)
+sum_rows_kernel(const float* __restrict__ row_loss, int64_t rows, float scale, float* __restrict__ out) {
+  __shared__ float sh[THREADS / 32];
+  float s = 0.f;
+  for (int64_t r = threadIdx.x; r < rows; r += THREADS) s += row_loss[r];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = s * scale;
+}
+// dx = (sigmoid(x) - t) * dloss * scale
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+bce_bwd_kernel(const T* __restrict__ logits, int64_t ld, const float* __restrict__ target, int64_t ld_t, int C,
+               const float* __restrict__ dloss, float scale, T* __restrict__ dlogits, int64_t ld_d) {
+  const int64_t r = blockIdx.x;
+  const T* x = logits + r * ld;
+  const float* t = target + r * ld_t;
+  T* d = dlogits + r * ld_d;
+  const float g = (*dloss) * scale;
+  for (int c = threadIdx.x; c < C; c += THREADS) {
+    const float v = to_f<T>(x[c]);
+    const float e = __expf(-fabsf(v));
+    const float sg = v >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+    d[c] = from_f<T>((sg - t[c]) * g);
+  }
+}
+// Row-wise argmax (the smallest index among equal maxima) and the label at that position: `torch.max(logits, 1)[1]`
+// followed by the one-hot scatter * labels of compute_score_with_logits (volta/task_utils.py:429-434), and the
+// `preds` / `select_idx` of the VL-logit / V-logit branches (:113-114, :120-121).
+template <typename T>
+__global__ void __launch_bounds__(THREADS)
+argmax_pick_kernel(const T* __restrict__ logits, int64_t ld, const float* __restrict__ labels, int64_t ld_l, int C,
+                   int64_t* __restrict__ arg, float* __restrict__ pick) {
+  __shared__ float shv[THREADS / 32];
+  __shared__ int shi[THREADS / 32];
+  const int64_t r = blockIdx.x;
+  const T* x = logits + r * ld;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = threadIdx.x; c < C; c += THREADS) {
+    const float v = to_f<T>(x[c]);
+    if (bi == 0x7fffffff || v > best) { best = v; bi = c; }   // c increases: the first of equal maxima stays
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (oi != 0x7fffffff && (bi == 0x7fffffff || ov > best || (ov == best && oi < bi))) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { shv[threadIdx.x >> 5] = best; shi[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < THREADS / 32; ++w)
+      if (shi[w] != 0x7fffffff && (bi == 0x7fffffff || shv[w] > best || (shv[w] == best && shi[w] < bi))) { best = shv[w]; bi = shi[w]; }
+    if (bi == 0x7fffffff) bi = 0;
+    if (arg) arg[r] = bi;
+    if (pick) pick[r] = labels ? labels[r * ld_l + bi] : best;
+  }
+}
+
 __global__ void finalize_kernel(const float* __restrict__ loss_sum, const float* __restrict__ count, float* __restrict__ out, int n) {
   const int i = threadIdx.x;
   if (i < n) out[i] = loss_sum[i] / fmaxf(count[i], 1.0f);
@@ -361,6 +441,46 @@ int vb_region_loss_bwd(int32_t kind, const void* logits, int64_t ld, int32_t per
         kind, (const float*)logits, ld, per, per_ld, skip, label, tgt_idx, conf, tgt_vec, ld_t, C, weight, lse, count, dloss,
         (float*)dlogits);
   return vb::check_launch("region_bwd_kernel");
+}
+
+int vb_bce_logits_fwd(const void* logits, int64_t ld, const float* target, int64_t ld_t, int64_t rows, int32_t C,
+                      float* row_loss, float scale, float* loss_out, int32_t dtype, void* stream) {
+  VB_REQUIRE(logits && target && row_loss && loss_out && rows > 0 && C > 0, VB_ERR_ARG, "bce_logits_fwd: bad arguments");
+  VB_REQUIRE(ld >= C && ld_t >= C, VB_ERR_ARG, "bce_logits_fwd: leading dimension smaller than C");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB_BF16)
+    vb::loss::bce_fwd_kernel<vb::bf16><<<(unsigned)rows, vb::loss::THREADS, 0, st>>>((const vb::bf16*)logits, ld, target, ld_t, C, row_loss);
+  else if (dtype == VB_F32)
+    vb::loss::bce_fwd_kernel<float><<<(unsigned)rows, vb::loss::THREADS, 0, st>>>((const float*)logits, ld, target, ld_t, C, row_loss);
+  else { vb::set_error("bce_logits_fwd: bad dtype %d", dtype); return VB_ERR_ARG; }
+  vb::loss::sum_rows_kernel<<<1, vb::loss::THREADS, 0, st>>>(row_loss, rows, scale, loss_out);
+  return vb::check_launch("bce_fwd_kernel");
+}
+
+int vb_bce_logits_bwd(const void* logits, int64_t ld, const float* target, int64_t ld_t, int64_t rows, int32_t C,
+                      const float* dloss, float scale, void* dlogits, int64_t ld_d, int32_t dtype, void* stream) {
+  VB_REQUIRE(logits && target && dloss && dlogits && rows > 0 && C > 0, VB_ERR_ARG, "bce_logits_bwd: bad arguments");
+  VB_REQUIRE(ld >= C && ld_t >= C && ld_d >= C, VB_ERR_ARG, "bce_logits_bwd: leading dimension smaller than C");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB_BF16)
+    vb::loss::bce_bwd_kernel<vb::bf16><<<(unsigned)rows, vb::loss::THREADS, 0, st>>>((const vb::bf16*)logits, ld, target, ld_t, C, dloss, scale, (vb::bf16*)dlogits, ld_d);
+  else if (dtype == VB_F32)
+    vb::loss::bce_bwd_kernel<float><<<(unsigned)rows, vb::loss::THREADS, 0, st>>>((const float*)logits, ld, target, ld_t, C, dloss, scale, (float*)dlogits, ld_d);
+  else { vb::set_error("bce_logits_bwd: bad dtype %d", dtype); return VB_ERR_ARG; }
+  return vb::check_launch("bce_bwd_kernel");
+}
+
+int vb_argmax_pick(const void* logits, int64_t ld, const float* labels, int64_t ld_l, int64_t rows, int32_t C, int64_t* arg,
+                   float* pick, int32_t dtype, void* stream) {
+  VB_REQUIRE(logits && (arg || pick) && rows > 0 && C > 0, VB_ERR_ARG, "argmax_pick: bad arguments");
+  VB_REQUIRE(ld >= C && (!labels || ld_l >= C), VB_ERR_ARG, "argmax_pick: leading dimension smaller than C");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == VB_BF16)
+    vb::loss::argmax_pick_kernel<vb::bf16><<<(unsigned)rows, vb::loss::THREADS, 0, st>>>((const vb::bf16*)logits, ld, labels, ld_l, C, arg, pick);
+  else if (dtype == VB_F32)
+    vb::loss::argmax_pick_kernel<float><<<(unsigned)rows, vb::loss::THREADS, 0, st>>>((const float*)logits, ld, labels, ld_l, C, arg, pick);
+  else { vb::set_error("argmax_pick: bad dtype %d", dtype); return VB_ERR_ARG; }
+  return vb::check_launch("argmax_pick_kernel");
 }
 
 int vb_loss_finalize(const float* loss_sum, const float* count, float* out, int32_t n, void* stream) {

@@ -376,6 +376,36 @@ def region_loss_bwd(kind, logits, per, per_ld, skip, label, tgt_idx, conf, tgt_v
               dt(logits), _stream())
 
 
+def bce_logits_fwd(logits, target, row_loss, scale, loss_out):
+    """vb_bce_logits_fwd: logits [rows, C] (bf16 / fp32), target fp32 [rows, C]; loss_out[0] = scale * sum."""
+    rows, C_, ld = _rows2d(logits)
+    require_cuda(logits, target)
+    assert target.dtype == torch.float32 and _rows2d(target)[:2] == (rows, C_) and row_loss.numel() >= rows
+    _lib.call("vb_bce_logits_fwd", logits.data_ptr(), ld, target.data_ptr(), _rows2d(target)[2], rows, C_, row_loss.data_ptr(),
+              float(scale), loss_out.data_ptr(), dt(logits), _stream())
+    return loss_out
+
+
+def bce_logits_bwd(logits, target, dloss, scale, dlogits):
+    rows, C_, ld = _rows2d(logits)
+    require_cuda(logits, target, dlogits)
+    assert target.dtype == torch.float32 and dloss.dtype == torch.float32 and dlogits.dtype == logits.dtype
+    _lib.call("vb_bce_logits_bwd", logits.data_ptr(), ld, target.data_ptr(), _rows2d(target)[2], rows, C_, dloss.data_ptr(),
+              float(scale), dlogits.data_ptr(), _rows2d(dlogits)[2], dt(logits), _stream())
+    return dlogits
+
+
+def argmax_pick(logits, labels=None, arg=None, pick=None):
+    """vb_argmax_pick over the rows of logits [rows, C]: arg int64 [rows], pick fp32 [rows] (label at the argmax, or the max)."""
+    rows, C_, ld = _rows2d(logits)
+    require_cuda(logits)
+    assert labels is None or (labels.dtype == torch.float32 and _rows2d(labels)[:2] == (rows, C_))
+    assert (arg is None or arg.dtype == torch.int64) and (pick is None or pick.dtype == torch.float32)
+    _lib.call("vb_argmax_pick", logits.data_ptr(), ld, _ptr(labels), 0 if labels is None else _rows2d(labels)[2], rows, C_,
+              _ptr(arg), _ptr(pick), dt(logits), _stream())
+    return arg, pick
+
+
 def loss_finalize(loss_sum, count, out):
     _lib.call("vb_loss_finalize", loss_sum.data_ptr(), count.data_ptr(), out.data_ptr(), out.numel(), _stream())
     return out
