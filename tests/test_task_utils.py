@@ -120,3 +120,73 @@ def test_task_kernels_at_vqa_size_gpu():
     n0 = engine.launch_count
     TU.LossMap["BCEWithLogitLoss"](x.detach(), t)
     assert engine.launch_count - n0 == 2
+
+
+# ---- ForwardModelsTrain / ForwardModelsVal around a real BertForVLTasks -------------------------------------------------
+def _forward_models_case(device, precision, tol):
+    """`ForwardModelsTrain` / `ForwardModelsVal` with the mini ctrl_vilbert task model: the loss equals the reference
+    criterion applied to the UNMODIFIED reference's predictions (tests/golden/tasks_mini_ctrl_vilbert.pt), the score
+    its arg-max count, and the loss back-propagates into encoder and head."""
+    import copy
+    import volta_b200
+    import make_golden_tasks as MK
+    from volta_b200.synthetic import seeded_state_dict
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "tasks_mini_ctrl_vilbert.pt"), weights_only=False)
+    cfg = volta_b200.BertConfig.from_dict(g["config"])
+    task_cfg = copy.deepcopy(g["task_cfg"])
+    proc = {"TASK1": "normal", "TASK13": "normal", "TASK10": "normal", "TASK8": "retrieval"}
+    loss_of = {"TASK1": "BCEWithLogitLoss", "TASK13": "BCEWithLogitLoss", "TASK10": "BCEWithLogitLoss", "TASK8": "CrossEntropyLoss"}
+    model = volta_b200.BertForVLTasks(cfg, task_cfg, g["tasks"])
+    model.load_state_dict(seeded_state_dict(model.state_dict(), seed=0))
+    model.set_precision(precision).eval().to(device)
+    b = MK.case_batch("tasks_mini_ctrl_vilbert")
+    B = b["input_ids"].shape[0]
+    gen = torch.Generator().manual_seed(3)
+    for t in proc:
+        task_cfg[t].update(process=proc[t], loss=loss_of[t])
+        ref_pred = g["pred"][t]
+        feats, locs, vmask, ids, imask, seg = b["image_feat"], b["image_loc"], b["image_mask"], b["input_ids"], b["input_mask"], b["segment_ids"]
+        if t == "TASK8":       # one caption against B images: [1, B, ...] batch, class index target
+            feats, locs, vmask, ids, imask, seg = (x.unsqueeze(0) for x in (feats, locs, vmask, ids, imask, seg))
+            target = torch.tensor([2])
+            ref_loss = torch.nn.CrossEntropyLoss()(ref_pred.view(1, B), target)
+            ref_score = float((ref_pred.view(1, B).argmax(1) == target).sum())
+            bs = 1
+        elif t == "TASK10":
+            target = (torch.rand(B, ref_pred.shape[1], 1, generator=gen) > 0.6).float()
+            ref_loss = torch.nn.BCEWithLogitsLoss()(ref_pred, target) * target.size(1)
+            ref_score = float((target.squeeze(2).gather(1, ref_pred.argmax(1).view(-1, 1)) > 0.5).sum())
+            bs = B
+        else:
+            C = ref_pred.shape[1]
+            target = torch.zeros(B, C)
+            target[torch.arange(B), torch.randint(0, C, (B,), generator=gen)] = 1.0
+            ref_loss = torch.nn.BCEWithLogitsLoss()(ref_pred, target) * (C if t == "TASK1" else 1)
+            ref_score = float((torch.zeros(B, C).scatter_(1, ref_pred.argmax(1, keepdim=True), 1) * target).sum())
+            bs = B
+        batch = (feats, locs, vmask, ids, target, imask, seg, torch.arange(B))
+        criterion = TU.LoadLoss({"TASK" + t[4:]: task_cfg[t]}, t[4:])
+        model.zero_grad(set_to_none=True)
+        loss, score = TU.ForwardModelsTrain(cfg, task_cfg, device, t, batch, model, criterion)
+        assert abs(float(loss) - float(ref_loss)) <= tol * max(1.0, abs(float(ref_loss))), (t, float(loss), float(ref_loss))
+        if precision == "fp32":
+            assert abs(score - ref_score / bs) < 1e-6, (t, score, ref_score, bs)
+        loss.backward()
+        touched = [k for k, p in model.named_parameters() if p.grad is not None and float(p.grad.abs().sum()) > 0]
+        assert any(k.startswith("bert.encoder.layer.0.") for k in touched) and any(k.startswith("clfs_dict.%s." % t) for k in touched), t
+        vloss, vscore, vbs = TU.ForwardModelsVal(cfg, task_cfg, device, t, batch, model, criterion)
+        assert isinstance(vloss, float) and abs(vloss - float(ref_loss)) <= tol * max(1.0, abs(float(ref_loss))) and vbs == bs
+        if precision == "fp32":
+            assert vscore == ref_score
+
+
+def test_forward_models_train_val_emulated(monkeypatch):
+    emu_ops.install(monkeypatch)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)    # the batch transfer of :31 / :141, on a CPU-only box
+    _forward_models_case("cpu", "fp32", 2e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 3e-2)])
+def test_forward_models_train_val_gpu(precision, tol):
+    _forward_models_case("cuda", precision, tol)
