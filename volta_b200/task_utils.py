@@ -3,7 +3,7 @@ after the `BertForVLTasks` forward in `train_task.py` / `eval_task.py`:
 
   * `LossMap` / `LoadLoss`             (volta/task_utils.py:24-27, 284-287)
   * `compute_score_with_logits`        (:429-434)
-  * the per-task-type loss + score     (`ForwardModelsTrain` :236-282, `ForwardModelsVal` :102-137) -> `task_loss_and_score`
+  * the per-task-type loss + score     (`ForwardModelsTrain` :237-279, `ForwardModelsVal` :94-135)  -> `task_loss_and_score`
   * the per-"process" batch reshapes   (:148-233 / :36-94)                                         -> `expand_task_batch`
   * `ForwardModelsTrain` / `ForwardModelsVal` themselves, same signatures and returns.
 
@@ -123,94 +123,90 @@ def compute_score_with_logits(logits, labels):
     return pick.view(-1, 1)
 
 
+# task types whose criterion value is multiplied by the number of classes / regions (`loss.mean() * target.size(1)`)
+_TIMES_WIDTH = ("VL-classifier", "VL-classifier-GQA", "V-logit", "V-logit-mc")
+_TASK_TYPES = _TIMES_WIDTH + ("VL-logit", "VL-binary-classifier", "VL-tri-classifier")
+
+
 def task_loss_and_score(task_type, vil_prediction, target, criterion, batch_size, num_options=None, multi_choice_ids=None):
-    """The if / elif chain over `task_cfg[task_id]["type"]` (ForwardModelsTrain :236-280, ForwardModelsVal :102-135).
-    Returns (loss tensor, batch_score as a 0-dim device tensor = the number / sum of correct predictions, NOT yet divided
-    by the batch size)."""
-    if task_type in ("VL-classifier", "VL-classifier-GQA"):
-        loss = criterion(vil_prediction, target)
-        loss = loss.mean() * target.size(1)
-        score = compute_score_with_logits(vil_prediction, target).sum()
-    elif task_type == "VL-logit":
-        vil_logit = vil_prediction.view(batch_size, num_options)
-        loss = criterion(vil_logit, target)
-        preds, _ = _argmax_pick(vil_logit, want_pick=False)
-        score = (preds == target).sum()
-    elif task_type == "V-logit":
-        loss = criterion(vil_prediction, target)
-        loss = loss.mean() * target.size(1)
-        # select_idx = argmax over the regions; score = its target > 0.5 (:120-122)
-        _, sel = _argmax_pick(vil_prediction.squeeze(2), target.squeeze(2), want_arg=False)
-        score = (sel > 0.5).sum()
-    elif task_type == "V-logit-mc":
-        vision_logit = vil_prediction[:, 101:]  # the reference's own offset (:124, "FIXME from ViLBERT")
-        vision_logit = vision_logit.squeeze(2).gather(1, multi_choice_ids)
-        vision_logit = vision_logit.unsqueeze(2)
-        loss = criterion(vision_logit, target)
-        loss = loss.mean() * target.size(1)
-        preds, _ = _argmax_pick(vision_logit.squeeze(2), want_pick=False)
-        tgt, _ = _argmax_pick(target.squeeze(2), want_pick=False)
-        score = (preds == tgt).sum()
-    elif task_type in ("VL-binary-classifier", "VL-tri-classifier"):
-        loss = criterion(vil_prediction, target)
-        loss = loss.mean()
-        score = compute_score_with_logits(vil_prediction, target).sum()
-    else:
+    """Loss and score of one task type - the if / elif chain over `task_cfg[task_id]["type"]` (ForwardModelsTrain
+    :237-279, ForwardModelsVal :94-135).  Returns (loss tensor, score): score is a 0-dim device tensor, the number (or
+    label mass) of correct predictions, NOT yet divided by the batch size.
+      VL-logit                      : one of `num_options` candidates per example; class-index target; hit = arg-max == target
+      VL-classifier(-GQA), binary,
+      tri-classifier                : soft / one-hot label matrix; score = label at the arg-max class
+      V-logit                       : one logit per region; score = the arg-max region's target > 0.5
+      V-logit-mc                    : the logits of the listed regions (after the reference's offset 101, :124); hit = arg-max
+                                      of the prediction == arg-max of the target"""
+    if task_type not in _TASK_TYPES:
         raise KeyError("unknown task type %r" % (task_type,))
+    if task_type == "VL-logit":
+        logits = vil_prediction.view(batch_size, num_options)
+        return criterion(logits, target), (_argmax_pick(logits, want_pick=False)[0] == target).sum()
+    logits = vil_prediction
+    if task_type == "V-logit-mc":
+        logits = vil_prediction[:, 101:].squeeze(2).gather(1, multi_choice_ids).unsqueeze(2)
+    loss = criterion(logits, target).mean()
+    if task_type in _TIMES_WIDTH:
+        loss = loss * target.size(1)
+    if task_type == "V-logit":
+        score = (_argmax_pick(logits.squeeze(2), target.squeeze(2), want_arg=False)[1] > 0.5).sum()
+    elif task_type == "V-logit-mc":
+        score = (_argmax_pick(logits.squeeze(2), want_pick=False)[0] == _argmax_pick(target.squeeze(2), want_pick=False)[0]).sum()
+    else:
+        score = compute_score_with_logits(logits, target).sum()
     return loss, score
 
 
+def _per_option(x, n):
+    """[B, ...] -> [B * n, ...]: every sample repeated once per answer option (rows b*n .. b*n + n-1 are sample b)."""
+    return x.unsqueeze(1).expand(x.shape[0], n, *x.shape[1:]).reshape(x.shape[0] * n, *x.shape[1:])
+
+
+def _merge_options(x):
+    """[B, O, ...] -> [B * O, ...]."""
+    return x.reshape(x.shape[0] * x.shape[1], *x.shape[2:])
+
+
+def _split_pair(x):
+    """[B, 2 * V, ...] -> [2 * B, V, ...]: the two images of an NLVR2 example become consecutive samples."""
+    return x.reshape(x.shape[0] * 2, x.shape[1] // 2, *x.shape[2:])
+
+
 def expand_task_batch(process, config, features, spatials, image_mask, question, input_mask, segment_ids, target=None):
-    """The reshapes by `task_cfg[task_id]["process"]` (ForwardModelsTrain :148-233, ForwardModelsVal :36-94): views and
-    expands only.  Returns (features, spatials, image_mask, question, input_mask, segment_ids, target, batch_size, num_options)."""
+    """The batch layouts by `task_cfg[task_id]["process"]` (ForwardModelsTrain :148-233, ForwardModelsVal :36-94), as
+    views / expands of the loader's tensors.  Returns (features, spatials, image_mask, question, input_mask, segment_ids,
+    target, batch_size, num_options).
+      normal    : unchanged
+      expand    : O text options per image (VCR): image tensors repeated per option, text tensors [B, O, T] -> [B*O, T]
+      retrieval : O (caption, image) pairs per example: every tensor [B, O, ...] -> [B*O, ...]
+      nlvr      : two images per statement: image tensors [B, 2V, ...] -> [2B, V, ...], each text row duplicated
+      dialog    : R rounds x O options (VisDial); as in the reference the mask is expanded from [B, V] straight to four
+                  dimensions, which torch rejects - the call fails the same way."""
     batch_size = features.size(0)
     num_options = None
-    if process in ("dialog",):
-        max_num_bbox = features.size(1)
-        nround = question.size(1)
-        num_options = question.size(2)
-        rbatch_size = batch_size * nround
-        question = question.view(rbatch_size, question.size(2), question.size(3))
+    img, txt = (features, spatials, image_mask), (question, input_mask, segment_ids)
+    if process == "dialog":
+        nround, num_options = question.size(1), question.size(2)
         target = target.view(-1)
-        input_mask = input_mask.view(rbatch_size, input_mask.size(2), input_mask.size(3))
-        segment_ids = segment_ids.view(rbatch_size, segment_ids.size(2), segment_ids.size(3))
-        features = features.unsqueeze(1).unsqueeze(1).expand(batch_size, nround, num_options, max_num_bbox, config.v_feature_size) \
-            .contiguous().view(-1, max_num_bbox, config.v_feature_size)
-        spatials = spatials.unsqueeze(1).unsqueeze(1).expand(batch_size, nround, num_options, max_num_bbox, config.num_locs) \
-            .contiguous().view(-1, max_num_bbox, config.num_locs)
-        image_mask = image_mask.unsqueeze(1).expand(batch_size, nround, num_options, max_num_bbox).contiguous().view(-1, max_num_bbox)
-        question = question.view(-1, question.size(2))
-        input_mask = input_mask.view(-1, input_mask.size(2))
-        segment_ids = segment_ids.view(-1, segment_ids.size(2))
-        batch_size = rbatch_size
-    elif process in ("expand",):
-        max_num_bbox = features.size(1)
+        txt = tuple(_merge_options(_merge_options(t)) for t in txt)
+        features, spatials = (_per_option(x, nround * num_options) for x in (features, spatials))
+        image_mask = image_mask.unsqueeze(1).expand(batch_size, nround, num_options, image_mask.size(1))   # :172-177
+        img = (features, spatials, image_mask.reshape(-1, image_mask.size(-1)))
+        batch_size = batch_size * nround
+    elif process == "expand":
         num_options = question.size(1)
-        features = features.unsqueeze(1).expand(batch_size, num_options, max_num_bbox, config.v_feature_size) \
-            .contiguous().view(-1, max_num_bbox, config.v_feature_size)
-        spatials = spatials.unsqueeze(1).expand(batch_size, num_options, max_num_bbox, config.num_locs) \
-            .contiguous().view(-1, max_num_bbox, config.num_locs)
-        image_mask = image_mask.unsqueeze(1).expand(batch_size, num_options, max_num_bbox).contiguous().view(-1, max_num_bbox)
-        question = question.view(-1, question.size(2))
-        input_mask = input_mask.view(-1, input_mask.size(2))
-        segment_ids = segment_ids.view(-1, segment_ids.size(2))
-    elif process in ("retrieval",):
+        img = tuple(_per_option(x, num_options) for x in img)
+        txt = tuple(_merge_options(t) for t in txt)
+    elif process == "retrieval":
         num_options = question.size(1)
-        features = features.view(-1, features.size(2), features.size(3))
-        spatials = spatials.view(-1, spatials.size(2), spatials.size(3))
-        image_mask = image_mask.view(-1, image_mask.size(2))
-        question = question.view(-1, question.size(2))
-        input_mask = input_mask.view(-1, input_mask.size(2))
-        segment_ids = segment_ids.view(-1, segment_ids.size(2))
-    elif process in ("nlvr",):
+        img = tuple(_merge_options(x) for x in img)
+        txt = tuple(_merge_options(t) for t in txt)
+    elif process == "nlvr":
         num_options = question.size(1)
-        features = features.view(batch_size * 2, int(features.size(1) / 2), features.size(2))
-        spatials = spatials.view(batch_size * 2, int(spatials.size(1) / 2), spatials.size(2))
-        image_mask = image_mask.view(batch_size * 2, int(image_mask.size(1) / 2))
-        question = question.repeat(1, 2).view(batch_size * 2, int(question.size(1)))
-        input_mask = input_mask.repeat(1, 2).view(batch_size * 2, int(input_mask.size(1)))
-        segment_ids = segment_ids.repeat(1, 2).view(batch_size * 2, int(segment_ids.size(1)))
-    return features, spatials, image_mask, question, input_mask, segment_ids, target, batch_size, num_options
+        img = tuple(_split_pair(x) for x in img)
+        txt = tuple(t.repeat_interleave(2, dim=0) for t in txt)
+    return (*img, *txt, target, batch_size, num_options)
 
 
 def _forward(config, task_cfg, device, task_id, batch, model, criterion, train):
@@ -221,7 +217,7 @@ def _forward(config, task_cfg, device, task_id, batch, model, criterion, train):
     else:
         features, spatials, image_mask, question, target, input_mask, segment_ids, question_id = batch
     process = task_cfg[task_id]["process"]
-    if process in ("dialog",) and not train:
+    if process == "dialog" and not train:
         raise NotImplementedError("dialog process for validation")
     features, spatials, image_mask, question, input_mask, segment_ids, target, batch_size, num_options = expand_task_batch(
         process, config, features, spatials, image_mask, question, input_mask, segment_ids, target)
