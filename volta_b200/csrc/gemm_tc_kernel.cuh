@@ -410,20 +410,30 @@ __device__ __forceinline__ void red_tile(const uint8_t* stg, float* g, int64_t l
 // cp.async.bulk.tensor to D (and to aux_out for GELU) and the warp moves on; before a buffer is rewritten the lane
 // waits until the store that last used it has read it (bulk_wait_read).  Measured on the GELU GEMM: the LDS + STG
 // store path it replaces cost 12.5 of 58.5 us.  fp32 outputs keep the padded staging + per-thread vector stores.
+#ifndef VB_EPI_DEFER_WAIT
+#define VB_EPI_DEFER_WAIT 0   // measured: no gain (12.34 / 12.25 vs 12.29 / 12.32 ms per step), +24 registers; kept for the record
+#endif
 template <typename OutT, int BN, int EPI, bool INTERIOR, int NUM_EPI_GROUPS>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, uint32_t tmem_acc, uint8_t* stg, int64_t m0, int64_t nb0,
                                            int lane, int group, const float* bias_s, const CUtensorMap* mapD,
                                            const CUtensorMap* mapAuxOut, const CUtensorMap* mapAuxIn, uint32_t aux_bar,
-                                           uint32_t& aux_phase) {
+                                           uint32_t& aux_phase, int& ob_io) {
   using S = Stg<OutT>;
   constexpr bool TMA_OUT = sizeof(OutT) == 2 && EPI != VB_EPI_ACCUM;
   const int swz = (lane >> 1) & 3;                       // 64B-swizzle term of this lane's row
   uint8_t* const abuf = stg + 2 * STG_BUF_BYTES;         // aux_in staging (TMA_OUT layout)
+#if VB_EPI_DEFER_WAIT
+  // The two output buffers alternate over the whole life of the warp (ob_io persists from tile to tile): a buffer is
+  // rewritten two stores after it was handed to TMA, and the wait for that older store sits right BEFORE the rewrite -
+  // behind the tcgen05.ld and the math of the chunk - instead of right after the newer store was issued.
+  int ob = ob_io;
+#else
   int ob = 0;                                            // output buffer in use
   if constexpr (TMA_OUT) {
     if (lane == 0) bulk_wait_read<0>();                  // stores of the previous tile have drained their buffers
     __syncwarp();
   }
+#endif
   constexpr bool use_bias = EPI == VB_EPI_BIAS || EPI == VB_EPI_BIAS_GELU || EPI == VB_EPI_BIAS_RELU ||
                             EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_BIAS_ADD;
   constexpr bool use_aux = EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_MUL || EPI == VB_EPI_ADD ||
@@ -470,6 +480,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, u
         S::template load_regs<INTERIOR>(pre, aux, p.ld_aux, m0, n0 + NUM_EPI_GROUPS * S::CW, p.M, p.N, lane);
     }
     tmem_ld_wait();
+#if VB_EPI_DEFER_WAIT
+    uint4 packed[S::VPR];   // the chunk's first output, packed, until its staging buffer is known to be free
+#endif
     float acc[S::CW];
 #pragma unroll
     for (int j = 0; j < S::CW; ++j) acc[j] = __uint_as_float(raw[j]) * p.alpha;
@@ -539,21 +552,40 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, u
 #pragma unroll
         for (int j = 0; j < S::EV; ++j) o[j] = from_f<OutT>(acc[v * S::EV + j]);
       }
+#if VB_EPI_DEFER_WAIT
+      if constexpr (TMA_OUT) packed[v] = *reinterpret_cast<uint4*>(o);
+#else
       if constexpr (TMA_OUT) *reinterpret_cast<uint4*>(stg + ob * STG_BUF_BYTES + lane * 64 + ((v ^ swz) << 4)) = *reinterpret_cast<uint4*>(o);
+#endif
       else *reinterpret_cast<uint4*>(my_row + v * 16) = *reinterpret_cast<uint4*>(o);
     }
     if constexpr (TMA_OUT) {
       // first (or only) output of the chunk: gelu'(x) -> aux_out for GELU, the result -> D otherwise
+#if VB_EPI_DEFER_WAIT
+      if (lane == 0) bulk_wait_read<1>();   // the store before the previous one - the last user of buffer `ob` - has read it
+      __syncwarp();
+#pragma unroll
+      for (int v = 0; v < S::VPR; ++v)
+        *reinterpret_cast<uint4*>(stg + ob * STG_BUF_BYTES + lane * 64 + ((v ^ swz) << 4)) = packed[v];
+#endif
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
         tma_store_2d(EPI == VB_EPI_BIAS_GELU ? mapAuxOut : mapD, smem_u32(stg + ob * STG_BUF_BYTES), (int32_t)n0, (int32_t)m0);
         bulk_commit();
+#if !VB_EPI_DEFER_WAIT
         bulk_wait_read<1>();          // the OTHER buffer (store before this one) is free again
+#endif
       }
       ob ^= 1;
+#if !VB_EPI_DEFER_WAIT
       __syncwarp();
+#endif
       if constexpr (EPI == VB_EPI_BIAS_GELU) {
+#if VB_EPI_DEFER_WAIT
+        if (lane == 0) bulk_wait_read<1>();   // only the gelu' store just issued may still be reading (the other buffer)
+        __syncwarp();
+#endif
 #pragma unroll
         for (int v = 0; v < S::VPR; ++v) {
           OutT o[S::EV];
@@ -566,10 +598,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, u
         if (lane == 0) {
           tma_store_2d(mapD, smem_u32(stg + ob * STG_BUF_BYTES), (int32_t)n0, (int32_t)m0);
           bulk_commit();
+#if !VB_EPI_DEFER_WAIT
           bulk_wait_read<1>();
+#endif
         }
         ob ^= 1;
+#if !VB_EPI_DEFER_WAIT
         __syncwarp();
+#endif
       }
       continue;
     }
@@ -593,6 +629,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, u
     }
     __syncwarp();
   }
+  ob_io = ob;
 }
 
 template <int BN, int EPI, int CG, typename OutT>
@@ -804,6 +841,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* stg = stg_base + (warp - EPI_WARP0) * STG_WARP_BYTES;
     const uint32_t my_aux_bar = aux_bar(warp - EPI_WARP0);
     uint32_t aux_phase = 0;
+    int out_buf = 0;       // which of the warp's two TMA-store staging buffers the next store uses
     int it = 0, q = 0;
     if (first < total_work) for (int64_t w = first;; ++it) {
       const int64_t tile = w / split_k;
@@ -837,8 +875,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t nb0 = (int64_t)n_blk * BN;
         const bool interior = m0 + 32 <= p.epi.M && nb0 + BN <= p.epi.N;  // warp-uniform
         // OutT is a kernel template parameter: one epilogue body per kernel (code size, register allocation)
-        if (interior) epilogue_tile<OutT, BN, EPI, true, NUM_EPI_WARPS / 4>(p.epi, d_out, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase);
-        else epilogue_tile<OutT, BN, EPI, false, NUM_EPI_WARPS / 4>(p.epi, d_out, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase);
+        if (interior) epilogue_tile<OutT, BN, EPI, true, NUM_EPI_WARPS / 4>(p.epi, d_out, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase, out_buf);
+        else epilogue_tile<OutT, BN, EPI, false, NUM_EPI_WARPS / 4>(p.epi, d_out, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase, out_buf);
       }
       tcgen05_fence_before();
       __syncwarp();
