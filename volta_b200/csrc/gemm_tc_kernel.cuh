@@ -413,27 +413,51 @@ __device__ __forceinline__ void red_tile(const uint8_t* stg, float* g, int64_t l
 #ifndef VB_EPI_DEFER_WAIT
 #define VB_EPI_DEFER_WAIT 0   // measured: no gain (12.34 / 12.25 vs 12.29 / 12.32 ms per step), +24 registers; kept for the record
 #endif
+// Epilogues that read a second tensor (residual, activation derivative): the warp's three 2 KB buffers are used as ONE
+// output buffer + TWO aux buffers, so that the TMA loads of the aux chunks run two chunks ahead (the first two are
+// issued before the accumulator is even complete) instead of one; the single output buffer is rewritten only after a
+// wait placed behind the chunk's math (the store engine has long read it by then).
+#ifndef VB_EPI_AUX2
+#define VB_EPI_AUX2 1
+#endif
+template <typename OutT, int EPI> __host__ __device__ constexpr bool epi_aux2() {
+  return VB_EPI_AUX2 != 0 && sizeof(OutT) == 2 &&
+         (EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_MUL || EPI == VB_EPI_ADD || EPI == VB_EPI_DRELU || EPI == VB_EPI_BIAS_ADD);
+}
+// the first two aux chunks of a tile (this warp's share: chunks group, group + NUM_EPI_GROUPS): buffers 1 and 2, barriers 0 and 1
+template <typename OutT, int BN, int NUM_EPI_GROUPS>
+__device__ __forceinline__ void epilogue_aux_prefetch(const EpiParams& p, uint8_t* stg, int64_t m0, int64_t nb0, int lane, int group,
+                                                      const CUtensorMap* mapAuxIn, uint32_t aux_bar, uint32_t aux_bar2) {
+  using S = Stg<OutT>;
+  constexpr int NCH = BN / S::CW;
+  if (lane == 0) {
+    if (nb0 + group * S::CW < p.N) {
+      mbar_expect_tx(aux_bar, STG_BUF_BYTES);
+      tma_load_2d(smem_u32(stg + STG_BUF_BYTES), mapAuxIn, aux_bar, (int32_t)(nb0 + group * S::CW), (int32_t)m0);
+    }
+    if (group + NUM_EPI_GROUPS < NCH && nb0 + (group + NUM_EPI_GROUPS) * S::CW < p.N) {
+      mbar_expect_tx(aux_bar2, STG_BUF_BYTES);
+      tma_load_2d(smem_u32(stg + 2 * STG_BUF_BYTES), mapAuxIn, aux_bar2, (int32_t)(nb0 + (group + NUM_EPI_GROUPS) * S::CW), (int32_t)m0);
+    }
+  }
+}
 template <typename OutT, int BN, int EPI, bool INTERIOR, int NUM_EPI_GROUPS>
 __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, uint32_t tmem_acc, uint8_t* stg, int64_t m0, int64_t nb0,
                                            int lane, int group, const float* bias_s, const CUtensorMap* mapD,
                                            const CUtensorMap* mapAuxOut, const CUtensorMap* mapAuxIn, uint32_t aux_bar,
-                                           uint32_t& aux_phase, int& ob_io) {
+                                           uint32_t aux_bar2, uint32_t& aux_phase, int& ob_io) {
   using S = Stg<OutT>;
   constexpr bool TMA_OUT = sizeof(OutT) == 2 && EPI != VB_EPI_ACCUM;
+  constexpr bool DEFER = VB_EPI_DEFER_WAIT != 0;         // two output buffers alternating over the warp's whole life, wait before the rewrite
+  constexpr bool AUX2 = epi_aux2<OutT, EPI>();           // one output buffer (0), two aux buffers (1, 2)
+  constexpr bool REG_STAGE = TMA_OUT && (DEFER || AUX2); // the chunk's output waits in registers until its buffer is free
   const int swz = (lane >> 1) & 3;                       // 64B-swizzle term of this lane's row
-  uint8_t* const abuf = stg + 2 * STG_BUF_BYTES;         // aux_in staging (TMA_OUT layout)
-#if VB_EPI_DEFER_WAIT
-  // The two output buffers alternate over the whole life of the warp (ob_io persists from tile to tile): a buffer is
-  // rewritten two stores after it was handed to TMA, and the wait for that older store sits right BEFORE the rewrite -
-  // behind the tcgen05.ld and the math of the chunk - instead of right after the newer store was issued.
-  int ob = ob_io;
-#else
-  int ob = 0;                                            // output buffer in use
-  if constexpr (TMA_OUT) {
+  uint8_t* const abuf = stg + (AUX2 ? 1 : 2) * STG_BUF_BYTES;   // aux_in staging (TMA_OUT layout)
+  int ob = (DEFER && !AUX2) ? ob_io : 0;                 // output buffer in use
+  if constexpr (TMA_OUT && !REG_STAGE) {
     if (lane == 0) bulk_wait_read<0>();                  // stores of the previous tile have drained their buffers
     __syncwarp();
   }
-#endif
   constexpr bool use_bias = EPI == VB_EPI_BIAS || EPI == VB_EPI_BIAS_GELU || EPI == VB_EPI_BIAS_RELU ||
                             EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_BIAS_ADD;
   constexpr bool use_aux = EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_MUL || EPI == VB_EPI_ADD ||
@@ -445,7 +469,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, u
   uint64_t seed = 0;
   if constexpr (EPI == VB_EPI_BIAS_DROP_RES) seed = effective_seed(p.seed, p.seed_ptr);
   uint4 pre[S::ITERS];
-  if constexpr (use_aux && TMA_OUT) {
+  if constexpr (AUX2) {
+    // the first two aux chunks were requested by epilogue_aux_prefetch() before the accumulator was awaited
+  } else if constexpr (use_aux && TMA_OUT) {
     // residual / activation-derivative chunks arrive by TMA (32 x 32 box, zero fill outside the matrix) into the aux buffer;
     // the load of chunk c+1 is issued as soon as chunk c has been read out of it
     if (lane == 0 && nb0 + group * S::CW < p.N) {
@@ -456,13 +482,28 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, u
     if (nb0 + group * S::CW < p.N) S::template load_regs<INTERIOR>(pre, aux, p.ld_aux, m0, nb0 + group * S::CW, p.M, p.N, lane);
   }
   uint4 auxr[S::VPR];
+  int kchunk = 0;                                        // this warp's chunk counter inside the tile (AUX2: buffer / barrier parity)
 #pragma unroll 1
   for (int c = group; c < NCH; c += NUM_EPI_GROUPS) {
     const int64_t n0 = nb0 + c * S::CW;
     if (n0 >= p.N) break;  // warp-uniform
     uint32_t raw[32];
     tmem_ld32(tmem_acc + (uint32_t)(c * S::CW), raw);
-    if constexpr (use_aux && TMA_OUT) {
+    if constexpr (AUX2) {
+      const int which = kchunk & 1;
+      const uint32_t bar = which ? aux_bar2 : aux_bar;
+      uint8_t* const ab = abuf + which * STG_BUF_BYTES;
+      mbar_wait(bar, (aux_phase >> which) & 1u);
+      aux_phase ^= 1u << which;
+#pragma unroll
+      for (int v = 0; v < S::VPR; ++v) auxr[v] = *reinterpret_cast<const uint4*>(ab + lane * 64 + ((v ^ swz) << 4));
+      __syncwarp();                                      // every lane has read its row: the buffer may be refilled
+      if (lane == 0 && c + 2 * NUM_EPI_GROUPS < NCH && n0 + 2 * NUM_EPI_GROUPS * S::CW < p.N) {   // two chunks ahead
+        mbar_expect_tx(bar, STG_BUF_BYTES);
+        tma_load_2d(smem_u32(ab), mapAuxIn, bar, (int32_t)(n0 + 2 * NUM_EPI_GROUPS * S::CW), (int32_t)m0);
+      }
+      ++kchunk;
+    } else if constexpr (use_aux && TMA_OUT) {
       mbar_wait(aux_bar, aux_phase);
       aux_phase ^= 1u;
 #pragma unroll
@@ -480,9 +521,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, u
         S::template load_regs<INTERIOR>(pre, aux, p.ld_aux, m0, n0 + NUM_EPI_GROUPS * S::CW, p.M, p.N, lane);
     }
     tmem_ld_wait();
-#if VB_EPI_DEFER_WAIT
-    uint4 packed[S::VPR];   // the chunk's first output, packed, until its staging buffer is known to be free
-#endif
+    uint4 packed[S::VPR];   // REG_STAGE: the chunk's first output, packed, until its staging buffer is known to be free
     float acc[S::CW];
 #pragma unroll
     for (int j = 0; j < S::CW; ++j) acc[j] = __uint_as_float(raw[j]) * p.alpha;
@@ -552,40 +591,36 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, u
 #pragma unroll
         for (int j = 0; j < S::EV; ++j) o[j] = from_f<OutT>(acc[v * S::EV + j]);
       }
-#if VB_EPI_DEFER_WAIT
-      if constexpr (TMA_OUT) packed[v] = *reinterpret_cast<uint4*>(o);
-#else
-      if constexpr (TMA_OUT) *reinterpret_cast<uint4*>(stg + ob * STG_BUF_BYTES + lane * 64 + ((v ^ swz) << 4)) = *reinterpret_cast<uint4*>(o);
-#endif
+      if constexpr (REG_STAGE) packed[v] = *reinterpret_cast<uint4*>(o);
+      else if constexpr (TMA_OUT) *reinterpret_cast<uint4*>(stg + ob * STG_BUF_BYTES + lane * 64 + ((v ^ swz) << 4)) = *reinterpret_cast<uint4*>(o);
       else *reinterpret_cast<uint4*>(my_row + v * 16) = *reinterpret_cast<uint4*>(o);
     }
     if constexpr (TMA_OUT) {
       // first (or only) output of the chunk: gelu'(x) -> aux_out for GELU, the result -> D otherwise
-#if VB_EPI_DEFER_WAIT
-      if (lane == 0) bulk_wait_read<1>();   // the store before the previous one - the last user of buffer `ob` - has read it
-      __syncwarp();
+      if constexpr (REG_STAGE) {
+        if (lane == 0) {
+          if constexpr (AUX2) bulk_wait_read<0>();   // the one output buffer: the previous chunk's store has read it
+          else bulk_wait_read<1>();                  // the store before the previous one - the last user of buffer `ob`
+        }
+        __syncwarp();
 #pragma unroll
-      for (int v = 0; v < S::VPR; ++v)
-        *reinterpret_cast<uint4*>(stg + ob * STG_BUF_BYTES + lane * 64 + ((v ^ swz) << 4)) = packed[v];
-#endif
+        for (int v = 0; v < S::VPR; ++v)
+          *reinterpret_cast<uint4*>(stg + ob * STG_BUF_BYTES + lane * 64 + ((v ^ swz) << 4)) = packed[v];
+      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
         tma_store_2d(EPI == VB_EPI_BIAS_GELU ? mapAuxOut : mapD, smem_u32(stg + ob * STG_BUF_BYTES), (int32_t)n0, (int32_t)m0);
         bulk_commit();
-#if !VB_EPI_DEFER_WAIT
-        bulk_wait_read<1>();          // the OTHER buffer (store before this one) is free again
-#endif
+        if constexpr (!REG_STAGE) bulk_wait_read<1>();          // the OTHER buffer (store before this one) is free again
       }
-      ob ^= 1;
-#if !VB_EPI_DEFER_WAIT
-      __syncwarp();
-#endif
+      if constexpr (!AUX2) ob ^= 1;
+      if constexpr (!REG_STAGE) __syncwarp();
       if constexpr (EPI == VB_EPI_BIAS_GELU) {
-#if VB_EPI_DEFER_WAIT
-        if (lane == 0) bulk_wait_read<1>();   // only the gelu' store just issued may still be reading (the other buffer)
-        __syncwarp();
-#endif
+        if constexpr (REG_STAGE) {
+          if (lane == 0) bulk_wait_read<1>();   // only the gelu' store just issued may still be reading (the other buffer)
+          __syncwarp();
+        }
 #pragma unroll
         for (int v = 0; v < S::VPR; ++v) {
           OutT o[S::EV];
@@ -598,14 +633,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& p, void* d_out, u
         if (lane == 0) {
           tma_store_2d(mapD, smem_u32(stg + ob * STG_BUF_BYTES), (int32_t)n0, (int32_t)m0);
           bulk_commit();
-#if !VB_EPI_DEFER_WAIT
-          bulk_wait_read<1>();
-#endif
+          if constexpr (!REG_STAGE) bulk_wait_read<1>();
         }
         ob ^= 1;
-#if !VB_EPI_DEFER_WAIT
-        __syncwarp();
-#endif
+        if constexpr (!REG_STAGE) __syncwarp();
       }
       continue;
     }
@@ -656,6 +687,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto clc_full = [&](int s) { return bars + 8u * (2 * C::STAGES + 13 + s); };  // work queue: answer s has landed
   auto clc_empty = [&](int s) { return bars + 8u * (2 * C::STAGES + 15 + s); }; // (leader's copy) every reader is done with answer s
   auto clc_resp = [&](int s) { return bars + 8u * (2 * C::STAGES + 18) + 16u * s; };
+  auto aux_bar2 = [&](int w) { return bars + 8u * (2 * C::STAGES + 22 + w); };  // second aux-chunk barrier per epilogue warp (epi_aux2)
+  static_assert(8 * (2 * C::STAGES + 22 + NUM_EPI_WARPS) <= 384, "barrier area (Cfg::FIXED_BYTES) too small");
   auto smem_a = [&](int s) { return smem_base + s * C::STAGE_BYTES; };
   auto smem_b = [&](int s) { return smem_base + s * C::STAGE_BYTES + A_STAGE_BYTES; };
 
@@ -678,7 +711,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), CG * NUM_EPI_WARPS); }
-    for (int w = 0; w < NUM_EPI_WARPS; ++w) mbar_init(aux_bar(w), 1);
+    for (int w = 0; w < NUM_EPI_WARPS; ++w) { mbar_init(aux_bar(w), 1); mbar_init(aux_bar2(w), 1); }
     // readers of a work-queue answer besides the leader's producer thread (which issues the queries): per CTA the
     // epilogue warps + one of {MMA thread (leader), producer thread (peer)}
     for (int s = 0; s < 2; ++s) { mbar_init(clc_full(s), 1); mbar_init(clc_empty(s), CG * (NUM_EPI_WARPS + 1)); }
@@ -839,8 +872,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ew = (warp - EPI_WARP0) & 3;    // == warp % 4: TMEM lane quarter this warp may access
     const int group = (warp - EPI_WARP0) >> 2;  // which share of the 32-column chunks
     uint8_t* stg = stg_base + (warp - EPI_WARP0) * STG_WARP_BYTES;
-    const uint32_t my_aux_bar = aux_bar(warp - EPI_WARP0);
-    uint32_t aux_phase = 0;
+    const uint32_t my_aux_bar = aux_bar(warp - EPI_WARP0), my_aux_bar2 = aux_bar2(warp - EPI_WARP0);
+    uint32_t aux_phase = 0;   // bit 0: parity of my_aux_bar, bit 1: of my_aux_bar2
     int out_buf = 0;       // which of the warp's two TMA-store staging buffers the next store uses
     int it = 0, q = 0;
     if (first < total_work) for (int64_t w = first;; ++it) {
@@ -850,6 +883,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // Stage this tile's bias slice in shared memory while the MMAs are still running.  Double buffered by
       // accumulator stage; the named barrier also guarantees nobody still reads the buffer of tile it-2.
       float* bias_cur = bias_smem + as * BN;
+      const int64_t m0 = ((int64_t)m_blk * CG + rank) * BM + ew * 32;
+      if constexpr (epi_aux2<OutT, EPI>()) {
+        // the residual / derivative chunks of this tile do not depend on the accumulator: request the first two now
+        if (m0 < p.epi.M)
+          epilogue_aux_prefetch<OutT, BN, NUM_EPI_WARPS / 4>(p.epi, stg, m0, (int64_t)n_blk * BN, lane, group, &tmAuxIn, my_aux_bar, my_aux_bar2);
+      }
       if constexpr (EPI == VB_EPI_BIAS || EPI == VB_EPI_BIAS_GELU || EPI == VB_EPI_BIAS_RELU || EPI == VB_EPI_BIAS_DROP_RES || EPI == VB_EPI_BIAS_ADD) {
         const float* bias_g = (m_blk >= p.split_m_blk) ? p.bias2 : p.epi.bias;
         for (int j = threadIdx.x - EPI_WARP0 * 32; j < BN; j += NUM_EPI_WARPS * 32) {
@@ -864,7 +903,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // release the slot) before the long part
       int64_t w_next = w;
       const bool more = next_work(w_next, q, lane == 0, true);
-      const int64_t m0 = ((int64_t)m_blk * CG + rank) * BM + ew * 32;
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
       void* d_out = p.epi.D;
       if constexpr (EPI == VB_EPI_ACCUM) {
@@ -875,8 +913,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int64_t nb0 = (int64_t)n_blk * BN;
         const bool interior = m0 + 32 <= p.epi.M && nb0 + BN <= p.epi.N;  // warp-uniform
         // OutT is a kernel template parameter: one epilogue body per kernel (code size, register allocation)
-        if (interior) epilogue_tile<OutT, BN, EPI, true, NUM_EPI_WARPS / 4>(p.epi, d_out, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase, out_buf);
-        else epilogue_tile<OutT, BN, EPI, false, NUM_EPI_WARPS / 4>(p.epi, d_out, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, aux_phase, out_buf);
+        if (interior) epilogue_tile<OutT, BN, EPI, true, NUM_EPI_WARPS / 4>(p.epi, d_out, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, my_aux_bar2, aux_phase, out_buf);
+        else epilogue_tile<OutT, BN, EPI, false, NUM_EPI_WARPS / 4>(p.epi, d_out, tmem_acc, stg, m0, nb0, lane, group, bias_cur, &tmD, &tmAux, &tmAuxIn, my_aux_bar, my_aux_bar2, aux_phase, out_buf);
       }
       tcgen05_fence_before();
       __syncwarp();
