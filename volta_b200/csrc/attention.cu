@@ -1211,7 +1211,7 @@ static int launch(const vb_attn_args& a, const P& p, cudaStream_t st) {
 }  // namespace tcf
 
 // ---- host ----------------------------------------------------------------------------
-static int fill(const vb_attn_args& a, P& p, bool bwd) {
+static int fill(const vb_attn_args& a, P& p, bool bwd, bool need_ctx = true) {
   VB_REQUIRE(a.B > 0 && a.heads > 0 && a.d > 0, VB_ERR_ARG, "attention: bad sizes B=%d heads=%d d=%d", a.B, a.heads, a.d);
   VB_REQUIRE(a.qkv_t || a.qkv_v, VB_ERR_ARG, "attention: no stream given");
   VB_REQUIRE((a.pair_mask & ~15) == 0 && a.pair_mask != 0, VB_ERR_ARG, "attention: bad pair_mask %d", a.pair_mask);
@@ -1219,8 +1219,8 @@ static int fill(const vb_attn_args& a, P& p, bool bwd) {
   const bool tk = a.pair_mask & 5, vk = a.pair_mask & 10;         // stream has keys
   VB_REQUIRE(!(tq || tk) || (a.qkv_t && a.mask_t && a.Lt > 0), VB_ERR_ARG, "attention: text stream used but not provided");
   VB_REQUIRE(!(vq || vk) || (a.qkv_v && a.mask_v && a.Lv > 0), VB_ERR_ARG, "attention: vision stream used but not provided");
-  VB_REQUIRE(!tq || (a.ctx_t && a.lse_t), VB_ERR_ARG, "attention: ctx_t/lse_t missing");
-  VB_REQUIRE(!vq || (a.ctx_v && a.lse_v), VB_ERR_ARG, "attention: ctx_v/lse_v missing");
+  VB_REQUIRE(!need_ctx || !tq || (a.ctx_t && a.lse_t), VB_ERR_ARG, "attention: ctx_t/lse_t missing");
+  VB_REQUIRE(!need_ctx || !vq || (a.ctx_v && a.lse_v), VB_ERR_ARG, "attention: ctx_v/lse_v missing");
   if (bwd) {
     VB_REQUIRE(!tq || a.dctx_t, VB_ERR_ARG, "attention_bwd: dctx_t missing");
     VB_REQUIRE(!vq || a.dctx_v, VB_ERR_ARG, "attention_bwd: dctx_v missing");
@@ -1403,14 +1403,8 @@ int vb_attention_fwd(const vb_attn_args* a, void* stream) {
 int vb_attention_probs(const vb_attn_args* a, float* probs_t, float* probs_v, void* stream) {
   VB_REQUIRE(a != nullptr, VB_ERR_ARG, "attention_probs: null args");
   VB_REQUIRE(a->cu_t == nullptr && a->cu_v == nullptr, VB_ERR_UNSUPPORTED, "attention_probs: padded layout only (no cu_*)");
-  vb_attn_args b = *a;
-  float dummy = 0.f;          // fill() insists on ctx / lse for query streams: this entry point writes neither
-  if (!b.ctx_t) b.ctx_t = &dummy;
-  if (!b.ctx_v) b.ctx_v = &dummy;
-  if (!b.lse_t) b.lse_t = &dummy;
-  if (!b.lse_v) b.lse_v = &dummy;
   vb::attn::P p;
-  int rc = vb::attn::fill(b, p, false);
+  int rc = vb::attn::fill(*a, p, false, /*need_ctx=*/false);   // this entry point writes neither ctx nor lse
   if (rc) return rc;
   VB_REQUIRE(a->d <= 256, VB_ERR_UNSUPPORTED, "attention_probs: head size %d > 256", a->d);
   VB_REQUIRE((!(a->pair_mask & 3) || probs_t) && (!(a->pair_mask & 12) || probs_v), VB_ERR_ARG, "attention_probs: output missing for a query stream");
