@@ -210,3 +210,75 @@ def test_other_activations_match_oracle(act, monkeypatch):
         rg = P[key].grad if P[key].grad is not None else torch.zeros_like(P[key])
         got = p.grad if p.grad is not None else torch.zeros_like(p)
         assert float((got - rg).norm()) / max(float(rg.norm()), 1e-6) < 2e-3, (act, key)
+
+
+def _make_ragged(b, seed):
+    """Shortens the samples of a (full-length) synthetic batch in place: text lengths 3 ... T (first sample full, second
+    the minimum), 1 ... V-1 detected regions behind the global row; labels / features beyond the new lengths are cleared
+    the way the loader leaves padding (ids 0, lm label -1, region label -1, zero features)."""
+    g = torch.Generator().manual_seed(seed)
+    B, T = b["input_ids"].shape
+    V = b["image_mask"].shape[1]
+    lens = torch.randint(3, T + 1, (B,), generator=g)
+    nbox = torch.randint(1, V, (B,), generator=g)
+    lens[0], lens[1] = T, 3
+    nbox[0], nbox[1] = V - 1, 1
+    tpos, vpos = torch.arange(T)[None], torch.arange(V)[None]
+    tm = (tpos < lens[:, None]).long()
+    vm = (vpos < (nbox + 1)[:, None]).long()            # global row + nbox regions
+    b["input_mask"] = tm
+    b["input_ids"] = b["input_ids"] * tm
+    b["input_ids"][torch.arange(B), lens - 1] = 102 % int(b["input_ids"].max() + 1)
+    b["lm_label_ids"] = torch.where(tm.bool(), b["lm_label_ids"], torch.full_like(b["lm_label_ids"], -1))
+    b["lm_label_ids"][:, 1] = b["input_ids"][:, 1].clamp(min=1)      # one labelled token per sample survives
+    b["image_mask"] = vm
+    b["image_feat"] = b["image_feat"] * vm[..., None].float()
+    b["image_label"] = torch.where(vm[:, 1:].bool(), b["image_label"], torch.full_like(b["image_label"], -1))
+    b["image_label"][:, 0] = 1                                       # one masked region per sample survives
+    return b, lens, nbox
+
+
+@pytest.mark.parametrize("name,shape", [("mini_ctrl_vilbert", (32, 8, 9)), ("mini_ctrl_lxmert", (32, 8, 9)),
+                                        ("mini_ctrl_visualbert", (32, 8, 9)), ("mini_ctrl_vilbert", (19, 11, 7))])
+def test_packed_rows_plan_on_ragged_batches_matches_oracle(name, shape, monkeypatch):
+    """The packed plan where it matters: samples of very different lengths (3 ... T tokens, 1 ... V-1 regions, one sample
+    at each extreme), so that the packed buffers hold ~60 % of the rows, whole 256-row groups stay empty and the
+    per-sample offsets differ everywhere.  Losses and every parameter gradient against the oracle; the un-packed
+    sequence outputs equal the oracle's on the valid rows and are zero on padding."""
+    from volta_b200 import engine
+    from volta_b200.synthetic import pretraining_batch
+    emu_ops.install(monkeypatch)
+    taken = []
+
+    def forced(rt, bert, keep_layers):
+        ok = not keep_layers
+        taken.append(ok)
+        return ok
+    monkeypatch.setattr(engine, "_pack_supported", forced)
+    monkeypatch.setattr(engine, "PLAN_EMULATED", True)
+    g, cfg, _, model, state = _build(name)
+    b = pretraining_batch(*shape, vocab_size=cfg.vocab_size, feat_dim=cfg.v_feature_size, seed=23, full_length=True)
+    b, lens, nbox = _make_ragged(b, seed=5)
+    losses = model(b["input_ids"], b["image_feat"], b["image_loc"], b["segment_ids"], b["input_mask"], b["image_mask"],
+                   b["lm_label_ids"], b["image_label"], b["image_cls"], None, None, None, None, None, b["is_match"])
+    assert taken and all(taken) and engine.last_plan["packed"]
+    (losses[0] + losses[1] + losses[2]).sum().backward()
+    P = O.params_from_state_dict(state, requires_grad=True)
+    ref = O.pretraining_losses(P, cfg, b)
+    for mine, r in zip(losses, ref):
+        assert abs(float(mine) - float(r)) < 2e-4 * max(1.0, abs(float(r))), (name, float(mine), float(r))
+    sum(ref).backward()
+    for key, p in model.named_parameters():
+        rg = P[key].grad if P[key].grad is not None else torch.zeros_like(P[key])
+        got = p.grad if p.grad is not None else torch.zeros_like(p)
+        err = float((got - rg).norm()) / max(float(rg.norm()), 1e-6)
+        assert err < 2e-3, (name, key, err)
+    with torch.no_grad():
+        st, sv, pt, pv, _ = model.bert(b["input_ids"], b["image_feat"], b["image_loc"], b["segment_ids"], b["input_mask"], b["image_mask"])
+        lt_, lv_, rpt, rpv = O.bert_model(O.params_from_state_dict(state), cfg, b["input_ids"], b["image_feat"], b["image_loc"],
+                                          b["segment_ids"], b["input_mask"], b["image_mask"])[:4]
+        rt_, rv_ = lt_[-1], lv_[-1]
+    tm, vm = b["input_mask"].bool(), b["image_mask"].bool()
+    assert torch.allclose(st.float()[tm], rt_[tm], atol=2e-4) and torch.allclose(sv.float()[vm], rv_[vm], atol=2e-4)
+    assert float(st.float()[~tm].abs().max()) == 0.0 and float(sv.float()[~vm].abs().max()) == 0.0
+    assert torch.allclose(pt.float(), rpt, atol=2e-4) and torch.allclose(pv.float(), rpv, atol=2e-4)
