@@ -636,9 +636,13 @@ def _claim_stdout():
     """stdout carries exactly ONE line, the JSON line: whatever libraries write to file descriptor 1 (NCCL prints its
     version banner there) goes to stderr instead; emit() writes the line to the real stdout."""
     global _JSON_FD
-    sys.stdout.flush()
-    _JSON_FD = os.dup(1)
-    os.dup2(2, 1)
+    try:
+        sys.stdout.flush()
+        fd = os.dup(1)
+        os.dup2(2, 1)
+        _JSON_FD = fd
+    except OSError:       # no usable stderr / stdout descriptor: print the line the ordinary way
+        _JSON_FD = None
 
 
 def emit(line):
